@@ -1,0 +1,240 @@
+/* ============================================================================
+ * sm_b200.h -- C ABI of the B200-native dense-stereo hot path.
+ *
+ * Drop-in boundary for the stage API of xinge456/myStereoMatching
+ * (class StereoMatching, stereoMatching.h:46-2738, and the NL/ aggregator).
+ * Each entry point names the reference interface it replaces (file:line under
+ * the reference root).  Plain pointers and sizes only; every function returns
+ * 0 on success or a negative sm_status (sm_last_error() gives the text).
+ *
+ * Conventions
+ *  - "d_" pointers are DEVICE pointers (allocate with sm_dev_alloc or any CUDA
+ *    allocator on the ctx's device); "h_" pointers are HOST pointers.
+ *  - All work of one sm_ctx is ordered on that ctx's CUDA stream.  Calls on a
+ *    ctx must come from one host thread at a time; distinct ctxs (one per GPU)
+ *    are independent.  Stage calls are asynchronous; sm_ctx_sync() waits.
+ *  - Layouts are the reference's: cost volume [H][W][D] float32 with d fastest
+ *    (stereoMatching.cpp:2080-2081); disparity [H][W] int16, unscaled
+ *    (stereoMatching.cpp:3964); arms [H][W][5] uint16 =
+ *    [left,right,up,down,sum] (stereoMatching.cpp:5555-5559); census codes
+ *    [H][W][nwords] uint64 (stereoMatching.cpp:834-838); images BGR u8
+ *    interleaved / gray u8, row-major, no padding.
+ *  - There is no CPU fallback: without a CUDA device every call fails.
+ * ========================================================================== */
+#ifndef SM_B200_H
+#define SM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sm_ctx sm_ctx;
+
+typedef enum sm_status {
+  SM_OK = 0,
+  SM_ERR_ARG = -1,      /* CV_Assert-style precondition failure                */
+  SM_ERR_CUDA = -2,     /* a CUDA runtime call or kernel launch failed         */
+  SM_ERR_NOMEM = -3,    /* device allocation failed                            */
+  SM_ERR_UNSUPPORTED = -4
+} sm_status;
+
+/* POD copy of the StereoMatching::Parameters fields the hot path reads
+ * (stereoMatching.h:85-351) plus the static step switches it honours
+ * (stereoMatching.h:57-83).  sm_params_default() fills the reference defaults. */
+typedef struct sm_params {
+  int numDisparities;       /* maxDisp+1, stereoMatching.h:209 (<= 512 = CV_CN_MAX)     */
+  int censusFunc;           /* 0 = 9x7 centre census (63 bit), 3 = +8 ring bits (71)  :244 */
+  float adTrunc;            /* AD truncation / out-of-range default, 1000  stereoMatching.cpp:905 */
+  float lamAD, lamCen;      /* 10, 30                                      stereoMatching.cpp:5270 */
+  int cbca_crossL;          /* 17  stereoMatching.h:263 */
+  int cbca_crossL_out;      /* 34  :266 */
+  int cbca_cTresh;          /* 20  :269 */
+  int cbca_cTresh_out;      /* 6   :272 */
+  int cbca_minArmL;         /* 1   :259 */
+  int cbca_iterationNum;    /* 2   :260 */
+  int sgm_paths;            /* 4 (compiled-in, stereoMatching.cpp:6214) or 8 */
+  int sgm_corDifThres;      /* 15  :239 */
+  int sgm_reduCoeffi1;      /* 4   :240 */
+  float LRmaxDiff;          /* 0   :212 */
+  int region_vote_nums;     /* 2   :306 */
+  int regVote_SThres;       /* 20  stereoMatching.cpp:1402 */
+  float regVote_hratioThres;/* 0.4 stereoMatching.cpp:1401 */
+  int DISP_OCC;             /* -32 stereoMatching.h:216 */
+  int DISP_MIS;             /* -48 :217 */
+  int aggregation;          /* 0 none, 1 "CBCA", 2 "NL"  (static string, stereoMatching.h:52) */
+  int Do_refine;            /* stereoMatching.h:70; 1 in the benchmark configs */
+  int Do_LRConsis;          /* :72 */
+  int Do_regionVote;        /* :75 */
+  int Do_properIpol;        /* :76 */
+  int Do_lastMedianBlur;    /* :80 */
+  float crossScaleLambda;   /* <0: skip; >=0: the caller's 1-level SolveAll scale 1/(1+lambda), main_.cpp:158 */
+} sm_params;
+
+void sm_params_default(sm_params* p, int maxDisp);
+
+/* ---- context / memory ---------------------------------------------------- */
+/* stream: a cudaStream_t to launch on (e.g. the caller's current stream), or
+ * NULL to let the ctx create its own non-blocking stream. */
+int sm_ctx_create(sm_ctx** out, int device, void* stream);
+int sm_ctx_destroy(sm_ctx* ctx);
+int sm_ctx_sync(sm_ctx* ctx);
+void* sm_ctx_stream(sm_ctx* ctx);
+const char* sm_last_error(void);
+int sm_device_count(void);
+int sm_dev_alloc(sm_ctx* ctx, void** d_ptr, size_t bytes);
+int sm_dev_free(sm_ctx* ctx, void* d_ptr);
+int sm_host_alloc_pinned(void** h_ptr, size_t bytes);
+int sm_host_free_pinned(void* h_ptr);
+int sm_memcpy_h2d(sm_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int sm_memcpy_d2h(sm_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int sm_memset(sm_ctx* ctx, void* d_dst, int byte, size_t bytes);
+/* number of kernels this ctx has launched since creation (bench: gpu_launches) */
+long long sm_ctx_launch_count(sm_ctx* ctx);
+
+/* ---- cost computation ---------------------------------------------------- */
+/* cv::imread(...,0) gray conversion of a BGR image (main_.cpp:95-96). */
+int sm_bgr2gray(sm_ctx* ctx, const uint8_t* d_bgr, int H, int W, uint8_t* d_gray);
+
+/* genCensusCode<uchar> (func 0, stereoMatching.h:634-688) and
+ * genCensusCode_NC_Sur (func 3, stereoMatching.h:867-934) with the 7x9 window
+ * censusCal fixes (stereoMatching.cpp:815).  d_words: [H][W][nwords] uint64,
+ * nwords = 1 (func 0) or 2 (func 3). */
+int sm_census(sm_ctx* ctx, const uint8_t* d_gray, int H, int W, int func, uint64_t* d_words);
+int sm_census_words(int func);
+int sm_census_code_length(int func);
+
+/* gen_cenVM_XOR (stereoMatching.h:936-981): Hamming cost volume as float32.
+ * LOR 0 = left-referenced, 1 = right-referenced. */
+int sm_cost_hamming(sm_ctx* ctx, const uint64_t* d_cenL, const uint64_t* d_cenR, int H, int W, int D,
+                    int func, int LOR, float* d_vol);
+/* Same volume stored as uint16 (exact; the integer-cost path of costScan,
+ * stereoMatching.cpp:2007-2014). */
+int sm_cost_hamming_u16(sm_ctx* ctx, const uint64_t* d_cenL, const uint64_t* d_cenR, int H, int W,
+                        int D, int func, int LOR, uint16_t* d_vol);
+/* gen_ad_sd_vm with AOS=0 (stereoMatching.cpp:2468-2509). */
+int sm_cost_ad(sm_ctx* ctx, const uint8_t* d_bgrL, const uint8_t* d_bgrR, int H, int W, int D,
+               int LOR, float trunc, float* d_vol);
+/* ADCensusCal (stereoMatching.cpp:894-915) = gen_ad_sd_vm + gen_cenVM_XOR +
+ * gen_vm_from2vm_exp (stereoMatching.cpp:3566-3590) fused into one pass:
+ * vol = 2 - exp(-AD/lamAD) - exp(-census/lamCen); neither intermediate volume
+ * is materialised. */
+int sm_cost_adcensus(sm_ctx* ctx, const uint8_t* d_bgrL, const uint8_t* d_bgrR,
+                     const uint64_t* d_cenL, const uint64_t* d_cenR, int H, int W, int D, int func,
+                     float adTrunc, float lamAD, float lamCen, int LOR, float* d_vol);
+/* gen_vm_from2vm_exp on two materialised volumes (stage API completeness). */
+int sm_combine_exp(sm_ctx* ctx, const float* d_vm0, const float* d_vm1, size_t n, float aru0,
+                   float aru1, float* d_out);
+
+/* ---- aggregation: CBCA ---------------------------------------------------- */
+/* calHorVerDis<uchar> (stereoMatching.cpp:2958-3050) for one 3-channel image.
+ * d_arms: [H][W][5] uint16. */
+int sm_arms(sm_ctx* ctx, const uint8_t* d_bgr, int H, int W, int L, int L_out, int cTresh,
+            int cTresh_out, int minL, uint16_t* d_arms);
+/* genTrueHorVerArms (stereoMatching.cpp:2794-2845), materialised
+ * [H][W][D][5] uint16 -- for inspection/tests; sm_cbca never needs it. */
+int sm_arms_intersect(sm_ctx* ctx, const uint16_t* d_armsL, const uint16_t* d_armsR, int H, int W,
+                      int D, int view, uint16_t* d_out);
+/* cbca_core for one view (stereoMatching.cpp:5585-5666) with
+ * cbca_intersect=true: `iters` iterations of {cumulate, span} along both axes
+ * (H,V on even iterations, V,H on odd) each followed by the area division.
+ * In place on d_vol; d_tmp is a scratch volume of the same size. */
+int sm_cbca(sm_ctx* ctx, float* d_vol, float* d_tmp, const uint16_t* d_armsL,
+            const uint16_t* d_armsR, int H, int W, int D, int iters, int view);
+
+/* ---- aggregation: NL (non-local MST tree filter) -------------------------- */
+/* ctmf (NL/ctmf.h:8, NL/ctmf.c:378-433): (2r+1)^2 median, 8-bit, cn
+ * interleaved channels, edge-replicated border.  r in {1,2,3}. */
+int sm_median_u8(sm_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, int H, int W, int r, int cn);
+/* qx_mst_kruskals_image::mst (NL/qx_mst_kruskals_image.cpp:167-277): the MST of
+ * the 4-connected grid under the total order (weight, edge enumeration index),
+ * rooted at pixel 0.  Outputs, each H*W: parent (root = itself), weight = edge
+ * to parent (root 0), rank = depth.  d_order (nullable): nodes sorted by
+ * (rank, index) -- a valid parent-before-child order (the reference's BFS order
+ * sorts within a level by adjacency; only the fp64 summation order of siblings
+ * depends on it). */
+int sm_mst_build(sm_ctx* ctx, const uint8_t* d_bgr, int H, int W, int cn, int32_t* d_parent,
+                 uint8_t* d_weight, int32_t* d_rank, int32_t* d_order);
+/* qx_tree_filter::filter (NL/qx_tree_filter.cpp:61-117) on a float32 volume with
+ * fp64 arithmetic inside (NLCCA::aggreCV's f32->f64->f32, NL/NLCCA.cpp:56-90).
+ * d_work: scratch of H*W*D doubles. */
+int sm_tree_filter(sm_ctx* ctx, float* d_vol, double* d_work, int H, int W, int D,
+                   const int32_t* d_parent, const uint8_t* d_weight, const int32_t* d_rank,
+                   const int32_t* d_order, double sigma);
+/* StereoMatching::NL (stereoMatching.cpp:4892-4917): aggreCV(vm[0]),
+ * aggreCV(ones), divide.  In place on d_vol. */
+int sm_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, int H, int W, int D);
+
+/* ---- optimisation: SGM ---------------------------------------------------- */
+/* costScan + updateCost<float> for ONE path (stereoMatching.cpp:1983-2029,
+ * stereoMatching.h:2205-2280).  path indexes the reference's direction table
+ * rv={+1,-1,0,0,+1,+1,-1,-1}, ru={0,0,+1,-1,-1,+1,+1,-1}
+ * (stereoMatching.cpp:6207-6208).  d_bgr = colour image of the view.
+ * mode 0: d_out = Lr (the member L[i]); mode 1: d_out += Lr (gen_sgm_vm's
+ * running sum, stereoMatching.cpp:2031-2056). */
+int sm_sgm_path(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int path,
+                int corDifThres, int reduCoeffi1, int mode, float* d_out);
+/* sgm() (stereoMatching.cpp:6204-6224): `paths` sweeps summed in table order
+ * into d_sum (must not alias d_vol). */
+int sm_sgm(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int paths,
+           int corDifThres, int reduCoeffi1, float* d_sum);
+
+/* ---- disparity selection --------------------------------------------------- */
+/* gen_dispFromVm (stereoMatching.cpp:3928-3967), ChooseSmall = true. */
+int sm_wta(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int16_t* d_disp);
+/* wta_Co (stereoMatching.cpp:2709-2792): left map and right map from the LEFT
+ * volume's diagonal, both multiplied by `scale` (DISP_SCALE = 16). */
+int sm_wta_co(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int scale, int16_t* d_D1,
+              int16_t* d_D2);
+
+/* ---- refinement ------------------------------------------------------------ */
+/* LRConsistencyCheck_normal (stereoMatching.cpp:2262-2282): in place on d_D1. */
+int sm_lrc(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int H, int W, float LRmaxDiff);
+/* LRConsistencyCheck, LOR=0 (stereoMatching.cpp:2284-2335): occlusion/mismatch
+ * labelling; d_errMask (nullable) [H][W] u8. */
+int sm_lrc_label(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int H, int W, int D,
+                 float LRmaxDiff, int DISP_OCC, int DISP_MIS, uint8_t* d_errMask);
+/* regionVote_my (stereoMatching.cpp:7219-7277): one Jacobi sweep, in place.
+ * d_arms = HVL[0]; d_tmp = scratch [H][W] int16. */
+int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint16_t* d_arms, int H, int W,
+                   int D, float ratio, int S);
+/* properIpol (stereoMatching.cpp:7395-7490): one Jacobi sweep, in place. */
+int sm_proper_ipol(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* d_bgr, int H, int W,
+                   int DISP_OCC);
+/* cv::medianBlur(CV_16S, 3) (stereoMatching.cpp:1499). d_dst != d_src. */
+int sm_median3_i16(sm_ctx* ctx, const int16_t* d_src, int16_t* d_dst, int H, int W);
+/* SolveAll with one pyramid level (stereoMatching.cpp:2142-2208, main_.cpp:158). */
+int sm_cross_scale_1level(sm_ctx* ctx, float* d_vol, size_t n, float lambda);
+
+/* ---- whole frame ------------------------------------------------------------ */
+/* A frame pipeline owns every device buffer a W x H x D frame needs (three
+ * volumes, codes, arms, images, disparities) so a stream of frames reuses them.
+ * sm_pipeline_run = pipeline() (stereoMatching.cpp:1950-1981): costCalculate
+ * -> dispOptimize -> refine, host images in, host disparity out; the copies are
+ * part of the call.  h_gray* may be NULL (computed on the device from BGR).
+ * h_dispR may be NULL.  sm_pipeline_run_device runs the same stages on images
+ * already uploaded with sm_pipeline_upload (no host traffic). */
+typedef struct sm_pipeline sm_pipeline;
+int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p, sm_pipeline** out);
+int sm_pipeline_destroy(sm_pipeline* pl);
+int sm_pipeline_upload(sm_pipeline* pl, const uint8_t* h_bgrL, const uint8_t* h_bgrR,
+                       const uint8_t* h_grayL, const uint8_t* h_grayR);
+int sm_pipeline_run_device(sm_pipeline* pl);
+int sm_pipeline_download(sm_pipeline* pl, int16_t* h_dispL, int16_t* h_dispR);
+int sm_pipeline_run(sm_pipeline* pl, const uint8_t* h_bgrL, const uint8_t* h_bgrR,
+                    const uint8_t* h_grayL, const uint8_t* h_grayR, int16_t* h_dispL,
+                    int16_t* h_dispR);
+/* device views of the pipeline's buffers (for tests / the C++ class): which =
+ * 0 vm[0], 1 vm[1], 2 DP[0], 3 DP[1], 4 HVL[0], 5 HVL[1], 6 census L, 7 census R */
+void* sm_pipeline_buffer(sm_pipeline* pl, int which);
+/* per-stage device time (ms) of the last sm_pipeline_run_device when timing was
+ * enabled: census, cost, arms, aggregation, sgm, wta, refine, total */
+int sm_pipeline_enable_timing(sm_pipeline* pl, int on);
+int sm_pipeline_stage_ms(sm_pipeline* pl, float* out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SM_B200_H */

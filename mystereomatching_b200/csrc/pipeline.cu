@@ -1,0 +1,250 @@
+// Whole-frame pipeline: StereoMatching::pipeline() (stereoMatching.cpp:1950-1981)
+// = costCalculate (stereoMatching.cpp:945-1021) -> dispOptimize (:1046-1136) ->
+// refine (:1364-1506), with costcalculation="ADCensus", aggregation "CBCA" | "NL"
+// | none, optimization="sgm".  One sm_pipeline owns every device buffer a frame
+// of its size needs, so a stream of frames allocates nothing.
+//
+// HBM residency at 1080p, D=256 (fp32): three volumes (vm[0], vm[1], scratch)
+// = 3 x 2.12 GB; everything else (images, census codes, arms, disparities) is
+// < 120 MB.  The reference's HVL_INTERSECTION (2 x 5.3 GB), its four cost
+// temporaries and its P path volumes L[i] are never materialised.
+#include "common.cuh"
+
+
+enum { ST_CENSUS = 0, ST_COST, ST_ARMS, ST_AGG, ST_SGM, ST_WTA, ST_REFINE, ST_TOTAL, ST_COUNT };
+
+struct sm_pipeline {
+  sm_ctx* ctx = nullptr;
+  int H = 0, W = 0, D = 0;
+  sm_params p;
+  uint8_t *bgr[2] = {nullptr, nullptr}, *gray[2] = {nullptr, nullptr};
+  uint32_t *pix[2] = {nullptr, nullptr}, *armpk[2] = {nullptr, nullptr};
+  uint64_t* cen[2] = {nullptr, nullptr};
+  uint16_t* arms[2] = {nullptr, nullptr};
+  float* vol[3] = {nullptr, nullptr, nullptr};  // vm[0], vm[1], scratch (roles rotate after SGM)
+  double* nlwork = nullptr;
+  int16_t *disp[2] = {nullptr, nullptr}, *dtmp = nullptr;
+  uint8_t* h_in = nullptr;   // pinned staging: bgrL | bgrR | grayL | grayR
+  int16_t* h_out = nullptr;  // pinned staging: dispL | dispR
+  bool have_gray = false, have_arms = false;
+  bool timing = false;
+  cudaEvent_t ev[ST_COUNT + 1];
+  bool ev_ok = false;
+  float ms[ST_COUNT];
+};
+
+static int pl_alloc(sm_ctx* ctx, void** p, size_t bytes) { return sm_dev_alloc(ctx, p, bytes); }
+
+extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
+  if (!pl) return SM_OK;
+  sm_ctx* c = pl->ctx;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(pl->bgr[i]); cudaFree(pl->gray[i]); cudaFree(pl->pix[i]); cudaFree(pl->armpk[i]);
+    cudaFree(pl->cen[i]); cudaFree(pl->arms[i]); cudaFree(pl->disp[i]);
+  }
+  for (int i = 0; i < 3; i++) cudaFree(pl->vol[i]);
+  cudaFree(pl->nlwork);
+  cudaFree(pl->dtmp);
+  if (pl->h_in) cudaFreeHost(pl->h_in);
+  if (pl->h_out) cudaFreeHost(pl->h_out);
+  if (pl->ev_ok)
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(pl->ev[i]);
+  delete pl;
+  return SM_OK;
+}
+
+extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p, sm_pipeline** out) {
+  SM_CHECK_ARG(ctx && p && out && H > 0 && W > 0);
+  SM_CHECK_ARG(p->numDisparities > 0 && p->numDisparities <= 512);
+  SM_CHECK_ARG(p->censusFunc == 0 || p->censusFunc == 3);
+  SM_CHECK_ARG(p->sgm_paths >= 0 && p->sgm_paths <= 8);
+  SM_CHECK_ARG(p->aggregation >= 0 && p->aggregation <= 2);
+  SM_CHECK_ARG(p->cbca_crossL_out >= 0 && p->cbca_crossL_out <= 255);
+  SM_CUDA(cudaSetDevice(ctx->device));
+  sm_pipeline* pl = new sm_pipeline();
+  pl->ctx = ctx; pl->H = H; pl->W = W; pl->D = p->numDisparities; pl->p = *p;
+  const size_t npix = (size_t)H * W, nvol = npix * pl->D;
+  const int nw = sm_census_words(p->censusFunc);
+  int rc = SM_OK;
+  for (int i = 0; i < 2 && rc == SM_OK; i++) {
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->bgr[i], npix * 3);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->gray[i], npix);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->pix[i], npix * 4);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], npix * 4);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->cen[i], npix * 8 * nw);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->arms[i], npix * 5 * 2);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->disp[i], npix * 2);
+  }
+  for (int i = 0; i < 3 && rc == SM_OK; i++) rc = pl_alloc(ctx, (void**)&pl->vol[i], nvol * sizeof(float));
+  if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->dtmp, npix * 2);
+  if (rc == SM_OK && p->aggregation == 2) rc = pl_alloc(ctx, (void**)&pl->nlwork, nvol * sizeof(double));
+  if (rc == SM_OK && cudaMallocHost((void**)&pl->h_in, npix * 8) != cudaSuccess) rc = SM_ERR_NOMEM;
+  if (rc == SM_OK && cudaMallocHost((void**)&pl->h_out, npix * 4) != cudaSuccess) rc = SM_ERR_NOMEM;
+  if (rc != SM_OK) { sm_pipeline_destroy(pl); return rc; }
+  *out = pl;
+  return SM_OK;
+}
+
+extern "C" int sm_pipeline_upload(sm_pipeline* pl, const uint8_t* h_bgrL, const uint8_t* h_bgrR, const uint8_t* h_grayL,
+                                  const uint8_t* h_grayR) {
+  SM_CHECK_ARG(pl && h_bgrL && h_bgrR);
+  SM_CHECK_ARG((h_grayL == nullptr) == (h_grayR == nullptr));
+  sm_ctx* c = pl->ctx;
+  const size_t npix = (size_t)pl->H * pl->W;
+  // The previous frame's async copies out of the staging buffer must have drained.
+  SM_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(pl->h_in, h_bgrL, npix * 3);
+  memcpy(pl->h_in + npix * 3, h_bgrR, npix * 3);
+  SM_CUDA(cudaMemcpyAsync(pl->bgr[0], pl->h_in, npix * 3, cudaMemcpyHostToDevice, c->stream));
+  SM_CUDA(cudaMemcpyAsync(pl->bgr[1], pl->h_in + npix * 3, npix * 3, cudaMemcpyHostToDevice, c->stream));
+  pl->have_gray = h_grayL != nullptr;
+  if (pl->have_gray) {
+    memcpy(pl->h_in + npix * 6, h_grayL, npix);
+    memcpy(pl->h_in + npix * 7, h_grayR, npix);
+    SM_CUDA(cudaMemcpyAsync(pl->gray[0], pl->h_in + npix * 6, npix, cudaMemcpyHostToDevice, c->stream));
+    SM_CUDA(cudaMemcpyAsync(pl->gray[1], pl->h_in + npix * 7, npix, cudaMemcpyHostToDevice, c->stream));
+  }
+  return SM_OK;
+}
+
+#define PL_MARK(k)                                                        \
+  do {                                                                    \
+    if (pl->timing) SM_CUDA(cudaEventRecord(pl->ev[k], c->stream));        \
+  } while (0)
+
+extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
+  SM_CHECK_ARG(pl);
+  sm_ctx* c = pl->ctx;
+  const sm_params& P = pl->p;
+  const int H = pl->H, W = pl->W, D = pl->D;
+  const long long npix = (long long)H * W;
+  const size_t nvol = (size_t)npix * D;
+  SM_CUDA(cudaSetDevice(c->device));
+  PL_MARK(0);
+  // ---- costCalculate: ADCensusCal (stereoMatching.cpp:894-915)
+  for (int i = 0; i < 2; i++) {
+    SM_TRY(smi_pack_bgr(c, pl->bgr[i], npix, pl->pix[i]));
+    if (!pl->have_gray) SM_TRY(sm_bgr2gray(c, pl->bgr[i], H, W, pl->gray[i]));
+    SM_TRY(sm_census(c, pl->gray[i], H, W, P.censusFunc, pl->cen[i]));
+  }
+  PL_MARK(1);
+  const int imgNum = P.Do_LRConsis ? 2 : 1;  // stereoMatching.cpp:898
+  for (int i = 0; i < imgNum; i++)
+    SM_TRY(smi_cost_adcensus_packed(c, pl->pix[0], pl->pix[1], pl->cen[0], pl->cen[1], H, W, D, P.censusFunc,
+                                    P.adTrunc, P.lamAD, P.lamCen, i, pl->vol[i]));
+  PL_MARK(2);
+  // ---- aggregation
+  const int views = (P.Do_refine && P.Do_LRConsis) ? 2 : 1;  // stereoMatching.cpp:1054, 5592
+  pl->have_arms = false;
+  auto ensure_arms = [&]() -> int {
+    if (pl->have_arms) return SM_OK;
+    for (int i = 0; i < 2; i++) {
+      SM_TRY(smi_arms_packed(c, pl->pix[i], H, W, P.cbca_crossL, P.cbca_crossL_out, P.cbca_cTresh, P.cbca_cTresh_out,
+                             P.cbca_minArmL, pl->arms[i]));
+      SM_TRY(smi_pack_arms(c, pl->arms[i], npix, pl->armpk[i]));
+    }
+    pl->have_arms = true;
+    return SM_OK;
+  };
+  if (P.aggregation == 1) {
+    SM_TRY(ensure_arms());
+    PL_MARK(3);
+    const int Lmax = max(1, max(P.cbca_crossL_out, P.cbca_minArmL));
+    for (int i = 0; i < views; i++)
+      SM_TRY(smi_cbca_packed(c, pl->vol[i], pl->vol[2], pl->armpk[0], pl->armpk[1], H, W, D, P.cbca_iterationNum, i,
+                             Lmax));
+  } else if (P.aggregation == 2) {
+    PL_MARK(3);
+    SM_TRY(smi_nl(c, pl->bgr[0], pl->vol[0], pl->nlwork, H, W, D));
+  } else {
+    PL_MARK(3);
+  }
+  if (P.crossScaleLambda >= 0.f)
+    for (int i = 0; i < (P.Do_refine ? 2 : 1); i++) SM_TRY(sm_cross_scale_1level(c, pl->vol[i], nvol, P.crossScaleLambda));
+  PL_MARK(4);
+  // ---- dispOptimize: sgm (stereoMatching.cpp:1051-1089) then WTA (:1108-1128)
+  if (P.sgm_paths > 0) {
+    for (int i = 0; i < views; i++) {
+      for (int k = 0; k < P.sgm_paths; k++)
+        SM_TRY(smi_sgm_path_packed(c, pl->vol[i], pl->pix[i], H, W, D, k, P.sgm_corDifThres, P.sgm_reduCoeffi1,
+                                   k == 0 ? 0 : 1, pl->vol[2]));
+      float* t = pl->vol[i];  // vm[i] <- path sum; the old cost volume becomes the scratch
+      pl->vol[i] = pl->vol[2];
+      pl->vol[2] = t;
+    }
+  }
+  PL_MARK(5);
+  for (int i = 0; i < views; i++) SM_TRY(sm_wta(c, pl->vol[i], H, W, D, pl->disp[i]));
+  PL_MARK(6);
+  // ---- refine (stereoMatching.cpp:1364-1506)
+  if (P.Do_refine) {
+    if (P.Do_LRConsis) SM_TRY(sm_lrc(c, pl->disp[0], pl->disp[1], H, W, P.LRmaxDiff));
+    if (P.Do_regionVote) {
+      SM_TRY(ensure_arms());  // :1393-1396
+      for (int i = 0; i < P.region_vote_nums; i++)
+        SM_TRY(sm_region_vote(c, pl->disp[0], pl->dtmp, pl->arms[0], H, W, D, P.regVote_hratioThres, P.regVote_SThres));
+    }
+    if (P.Do_properIpol)
+      for (int i = 0; i < P.region_vote_nums; i++) SM_TRY(sm_proper_ipol(c, pl->disp[0], pl->dtmp, pl->bgr[0], H, W, P.DISP_OCC));
+    if (P.Do_lastMedianBlur) {
+      SM_TRY(sm_median3_i16(c, pl->disp[0], pl->dtmp, H, W));
+      SM_CUDA(cudaMemcpyAsync(pl->disp[0], pl->dtmp, npix * sizeof(int16_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  PL_MARK(7);
+  return SM_OK;
+}
+
+extern "C" int sm_pipeline_download(sm_pipeline* pl, int16_t* h_dispL, int16_t* h_dispR) {
+  SM_CHECK_ARG(pl && h_dispL);
+  sm_ctx* c = pl->ctx;
+  const size_t npix = (size_t)pl->H * pl->W;
+  SM_CUDA(cudaMemcpyAsync(pl->h_out, pl->disp[0], npix * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (h_dispR) SM_CUDA(cudaMemcpyAsync(pl->h_out + npix, pl->disp[1], npix * 2, cudaMemcpyDeviceToHost, c->stream));
+  SM_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(h_dispL, pl->h_out, npix * 2);
+  if (h_dispR) memcpy(h_dispR, pl->h_out + npix, npix * 2);
+  return SM_OK;
+}
+
+extern "C" int sm_pipeline_run(sm_pipeline* pl, const uint8_t* h_bgrL, const uint8_t* h_bgrR, const uint8_t* h_grayL,
+                               const uint8_t* h_grayR, int16_t* h_dispL, int16_t* h_dispR) {
+  SM_TRY(sm_pipeline_upload(pl, h_bgrL, h_bgrR, h_grayL, h_grayR));
+  SM_TRY(sm_pipeline_run_device(pl));
+  return sm_pipeline_download(pl, h_dispL, h_dispR);
+}
+
+extern "C" void* sm_pipeline_buffer(sm_pipeline* pl, int which) {
+  if (!pl) return nullptr;
+  switch (which) {
+    case 0: return pl->vol[0];
+    case 1: return pl->vol[1];
+    case 2: return pl->disp[0];
+    case 3: return pl->disp[1];
+    case 4: return pl->arms[0];
+    case 5: return pl->arms[1];
+    case 6: return pl->cen[0];
+    case 7: return pl->cen[1];
+    default: return nullptr;
+  }
+}
+
+extern "C" int sm_pipeline_enable_timing(sm_pipeline* pl, int on) {
+  SM_CHECK_ARG(pl);
+  if (on && !pl->ev_ok) {
+    for (int i = 0; i <= ST_COUNT; i++) SM_CUDA(cudaEventCreate(&pl->ev[i]));
+    pl->ev_ok = true;
+  }
+  pl->timing = on != 0;
+  return SM_OK;
+}
+
+extern "C" int sm_pipeline_stage_ms(sm_pipeline* pl, float* out8) {
+  SM_CHECK_ARG(pl && out8 && pl->timing && pl->ev_ok);
+  SM_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+  for (int k = 0; k < 7; k++) SM_CUDA(cudaEventElapsedTime(&out8[k], pl->ev[k], pl->ev[k + 1]));
+  SM_CUDA(cudaEventElapsedTime(&out8[7], pl->ev[0], pl->ev[7]));
+  return SM_OK;
+}

@@ -1,0 +1,309 @@
+// K6: disparity selection and the active refinement chain.
+//
+//   gen_dispFromVm              stereoMatching.cpp:3928-3967   first minimum, unscaled int16, -1 if none
+//   wta_Co                      stereoMatching.cpp:2709-2792   left map + right map from the left volume's diagonal
+//   LRConsistencyCheck_normal   stereoMatching.cpp:2262-2282
+//   LRConsistencyCheck          stereoMatching.cpp:2284-2335   occlusion / mismatch labelling (LOR = 0)
+//   regionVote_my               stereoMatching.cpp:7219-7277
+//   properIpol                  stereoMatching.cpp:7395-7490
+//   cv::medianBlur(CV_16S, 3)   stereoMatching.cpp:1499
+//   SolveAll (1 level)          stereoMatching.cpp:2142-2208
+//
+// WTA is the only volume-sized stage here (one read of the volume, HBM bound):
+// a warp per pixel, lanes stride d so every load instruction is a coalesced 128 B
+// line, then a shuffle argmin that keeps the LOWEST d among equal minima.  All
+// other kernels are O(H*W).
+#include <float.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------ WTA
+#define WTA_WARPS 8
+
+__global__ void __launch_bounds__(WTA_WARPS * 32)
+    k_wta(const float* __restrict__ vol, long long npix, int D, int16_t* __restrict__ disp) {
+  const int lane = threadIdx.x & 31;
+  long long p = (long long)blockIdx.x * WTA_WARPS + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * WTA_WARPS;
+  for (; p < npix; p += stride) {
+    const float* c = vol + p * D;
+    float best = FLT_MAX;
+    int bd = -1;
+    for (int d = lane; d < D; d += 32) {
+      const float x = c[d];
+      if (best > x) { best = x; bd = d; }  // strict: an earlier (lower) d keeps the win
+    }
+    // lanes hold increasing-d candidates; combine preferring smaller value, then smaller d.
+    // bd == -1 (nothing below FLT_MAX) must lose against any real candidate with the same value,
+    // which cannot exist (a real candidate is strictly below FLT_MAX), so (value, d) order is safe.
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+      if (ob < best || (ob == best && od >= 0 && (bd < 0 || od < bd))) { best = ob; bd = od; }
+    }
+    if (lane == 0) disp[p] = (int16_t)bd;
+  }
+}
+
+extern "C" int sm_wta(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int16_t* d_disp) {
+  SM_CHECK_ARG(ctx && d_vol && d_disp && H > 0 && W > 0 && D > 0);
+  const long long npix = (long long)H * W;
+  int grid = (int)min((long long)ctx->num_sms * 8, (npix + WTA_WARPS - 1) / WTA_WARPS);
+  SM_LAUNCH(ctx, k_wta, grid, WTA_WARPS * 32, 0, d_vol, npix, D, d_disp);
+  return SM_OK;
+}
+
+__global__ void __launch_bounds__(WTA_WARPS * 32)
+    k_wta_co(const float* __restrict__ vol, int H, int W, int D, int scale, int16_t* __restrict__ D1,
+             int16_t* __restrict__ D2) {
+  const int lane = threadIdx.x & 31;
+  const long long npix = (long long)H * W;
+  long long p = (long long)blockIdx.x * WTA_WARPS + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * WTA_WARPS;
+  for (; p < npix; p += stride) {
+    const int u = (int)(p % W);
+    float bl = FLT_MAX, br = FLT_MAX;
+    int dl = 0, dr = 0;
+    bool hl = false, hr = false;  // "some d improved on FLT_MAX" (else the reference keeps disp 0)
+    for (int d = lane; d < D; d += 32) {
+      if (u - d >= 0) {
+        const float x = vol[p * D + d];
+        if (x < bl) { bl = x; dl = d; hl = true; }
+      }
+      if (u + d < W) {
+        const float x = vol[(p + d) * D + d];
+        if (x < br) { br = x; dr = d; hr = true; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, bl, o);
+      int od = __shfl_xor_sync(0xffffffffu, dl, o);
+      int oh = __shfl_xor_sync(0xffffffffu, (int)hl, o);
+      if (oh && (!hl || ob < bl || (ob == bl && od < dl))) { bl = ob; dl = od; hl = true; }
+      ob = __shfl_xor_sync(0xffffffffu, br, o);
+      od = __shfl_xor_sync(0xffffffffu, dr, o);
+      oh = __shfl_xor_sync(0xffffffffu, (int)hr, o);
+      if (oh && (!hr || ob < br || (ob == br && od < dr))) { br = ob; dr = od; hr = true; }
+    }
+    if (lane == 0) {
+      D1[p] = (int16_t)((hl ? dl : 0) * scale);
+      D2[p] = (int16_t)((hr ? dr : 0) * scale);
+    }
+  }
+}
+
+extern "C" int sm_wta_co(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int scale, int16_t* d_D1,
+                         int16_t* d_D2) {
+  SM_CHECK_ARG(ctx && d_vol && d_D1 && d_D2 && H > 0 && W > 0 && D > 0);
+  const long long npix = (long long)H * W;
+  int grid = (int)min((long long)ctx->num_sms * 8, (npix + WTA_WARPS - 1) / WTA_WARPS);
+  SM_LAUNCH(ctx, k_wta_co, grid, WTA_WARPS * 32, 0, d_vol, H, W, D, scale, d_D1, d_D2);
+  return SM_OK;
+}
+
+// ------------------------------------------------------------------ LR check
+// In-place on D1 is safe: each thread reads D1 only at its own pixel.
+__global__ void k_lrc(int16_t* __restrict__ D1, const int16_t* __restrict__ D2, int H, int W, float maxDiff) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t i = (size_t)v * W + u;
+  const int d = D1[i];
+  if (d < 0 || u - d < 0 || (float)abs(d - (int)D2[i - d]) > maxDiff) D1[i] = -1;
+}
+
+extern "C" int sm_lrc(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int H, int W, float LRmaxDiff) {
+  SM_CHECK_ARG(ctx && d_D1 && d_D2 && H > 0 && W > 0);
+  dim3 grid(sm_div_up(W, 256), H);
+  SM_LAUNCH(ctx, k_lrc, grid, 256, 0, d_D1, d_D2, H, W, LRmaxDiff);
+  return SM_OK;
+}
+
+__global__ void k_lrc_label(int16_t* __restrict__ D1, const int16_t* __restrict__ D2, int H, int W, int D,
+                            float maxDiff, int occ, int mis, uint8_t* __restrict__ mask) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t i = (size_t)v * W + u;
+  const int d = D1[i];
+  uint8_t m = 0;
+  if (d < 0 || u - d < 0 || (float)abs(d - (int)D2[i - d]) > maxDiff) {
+    m = 255;
+    int disp = occ;
+    for (int dd = 0; dd < D && u - dd >= 0; dd++)
+      if (D2[i - dd] == dd) { disp = mis; break; }
+    D1[i] = (int16_t)disp;
+  }
+  if (mask) mask[i] = m;
+}
+
+extern "C" int sm_lrc_label(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int H, int W, int D, float LRmaxDiff,
+                            int DISP_OCC, int DISP_MIS, uint8_t* d_errMask) {
+  SM_CHECK_ARG(ctx && d_D1 && d_D2 && H > 0 && W > 0 && D > 0);
+  dim3 grid(sm_div_up(W, 256), H);
+  SM_LAUNCH(ctx, k_lrc_label, grid, 256, 0, d_D1, d_D2, H, W, D, LRmaxDiff, DISP_OCC, DISP_MIS, d_errMask);
+  return SM_OK;
+}
+
+// ------------------------------------------------------------------ region voting
+// One warp per pixel; valid pixels copy through.  The votes of the cross region
+// (vertical arm of the anchor, horizontal arm of each pixel on it; image-space
+// arms of the left image) go into a per-warp shared-memory histogram.
+#define RV_WARPS 8
+
+__global__ void __launch_bounds__(RV_WARPS * 32)
+    k_region_vote(const int16_t* __restrict__ src, int16_t* __restrict__ dst, const uint16_t* __restrict__ arms, int H,
+                  int W, int D, float ratio, int S) {
+  extern __shared__ int hist_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* hist = hist_all + warp * D;
+  const long long npix = (long long)H * W;
+  long long p = (long long)blockIdx.x * RV_WARPS + warp;
+  const long long stride = (long long)gridDim.x * RV_WARPS;
+  for (; p < npix; p += stride) {
+    const int16_t cur = src[p];
+    if (cur >= 0) { if (lane == 0) dst[p] = cur; continue; }
+    const int v = (int)(p / W), u = (int)(p - (long long)v * W);
+    for (int d = lane; d < D; d += 32) hist[d] = 0;
+    __syncwarp();
+    const uint16_t* a = arms + p * 5;
+    const int vb = v - a[2], ve = v + a[3];
+    int valid = 0;
+    for (int vn = vb; vn <= ve; vn++) {
+      const uint16_t* b = arms + ((size_t)vn * W + u) * 5;
+      const int ub = u - b[0], ue = u + b[1];
+      for (int un = ub + lane; un <= ue; un += 32) {
+        const int x = src[(size_t)vn * W + un];
+        if (x >= 0) { valid++; if (x < D) atomicAdd(&hist[x], 1); }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    __syncwarp();
+    int16_t res = cur;
+    if (valid > S) {
+      // mode with the lowest d on ties: maximise (count, -d)
+      int bc = -1, bd = 0;
+      for (int d = lane; d < D; d += 32) {
+        const int c = hist[d];
+        if (c > bc) { bc = c; bd = d; }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o), od = __shfl_xor_sync(0xffffffffu, bd, o);
+        if (oc > bc || (oc == bc && od < bd)) { bc = oc; bd = od; }
+      }
+      if ((float)(bc / valid) >= ratio) res = (int16_t)bd;  // integer division, as the reference
+    }
+    if (lane == 0) dst[p] = res;
+    __syncwarp();
+  }
+}
+
+extern "C" int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint16_t* d_arms, int H, int W, int D,
+                              float ratio, int S) {
+  SM_CHECK_ARG(ctx && d_disp && d_tmp && d_arms && H > 0 && W > 0 && D > 0 && D <= 4096);
+  const long long npix = (long long)H * W;
+  int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
+  SM_LAUNCH(ctx, k_region_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio,
+            S);
+  SM_CUDA(cudaMemcpyAsync(d_disp, d_tmp, npix * sizeof(int16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return SM_OK;
+}
+
+// ------------------------------------------------------------------ proper interpolation
+__constant__ int c_dirW[16] = {0, 2, 2, 2, 0, -2, -2, -2, 1, 2, 2, 1, -1, -2, -2, -1};
+__constant__ int c_dirH[16] = {2, 2, 0, -2, -2, -2, 0, 2, 2, 1, -1, -2, -2, -1, 1, 2};
+
+__global__ void k_proper_ipol(const int16_t* __restrict__ src, int16_t* __restrict__ dst,
+                              const uint8_t* __restrict__ bgr, int H, int W, int occ) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t i = (size_t)v * W + u;
+  const int cur = src[i];
+  if (cur >= 0) { dst[i] = (int16_t)cur; return; }
+  const int b0 = bgr[i * 3], g0 = bgr[i * 3 + 1], r0 = bgr[i * 3 + 2];
+  int minDisp = INT_MAX;           // DISP_OCC branch
+  int minDif = 255, dispC = -1;    // colour branch
+#pragma unroll 1
+  for (int k = 0; k < 16; k++) {
+    const int pw = c_dirW[k], ph = c_dirH[k];
+    int x = u, y = v;
+    for (int dep = 0; dep < 20; dep++) {
+      if ((dep & 1) == 0) { x += pw / 2; y += ph / 2; }
+      else { x += pw - pw / 2; y += ph - ph / 2; }
+      if (!(x >= 0 && x < W && y >= 0 && y < H)) break;
+      const size_t q = (size_t)y * W + x;
+      const int dq = src[q];
+      if (dq >= 0) {
+        int cd = max(abs(b0 - (int)bgr[q * 3]), max(abs(g0 - (int)bgr[q * 3 + 1]), abs(r0 - (int)bgr[q * 3 + 2])));
+        if (minDisp > dq) minDisp = dq;
+        if (minDif > cd) { minDif = cd; dispC = dq; }  // strict: first direction wins ties
+        break;
+      }
+    }
+  }
+  int res;
+  if (cur == occ) res = minDisp != INT_MAX ? minDisp : cur;
+  else res = dispC >= 0 ? dispC : cur;
+  dst[i] = (int16_t)res;
+}
+
+extern "C" int sm_proper_ipol(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* d_bgr, int H, int W,
+                              int DISP_OCC) {
+  SM_CHECK_ARG(ctx && d_disp && d_tmp && d_bgr && H > 0 && W > 0);
+  dim3 grid(sm_div_up(W, 128), H);
+  SM_LAUNCH(ctx, k_proper_ipol, grid, 128, 0, d_disp, d_tmp, d_bgr, H, W, DISP_OCC);
+  SM_CUDA(cudaMemcpyAsync(d_disp, d_tmp, (size_t)H * W * sizeof(int16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return SM_OK;
+}
+
+// ------------------------------------------------------------------ 3x3 median, int16, replicated border
+__device__ __forceinline__ void cswap(int& a, int& b) {
+  const int lo = min(a, b), hi = max(a, b);
+  a = lo; b = hi;
+}
+
+__global__ void k_median3_i16(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int H, int W) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  int w[9];
+#pragma unroll
+  for (int dv = -1; dv <= 1; dv++)
+#pragma unroll
+    for (int du = -1; du <= 1; du++) {
+      const int y = min(max(v + dv, 0), H - 1), x = min(max(u + du, 0), W - 1);
+      w[(dv + 1) * 3 + du + 1] = src[(size_t)y * W + x];
+    }
+  // 19-exchange median-of-9 network (Paeth)
+  cswap(w[1], w[2]); cswap(w[4], w[5]); cswap(w[7], w[8]);
+  cswap(w[0], w[1]); cswap(w[3], w[4]); cswap(w[6], w[7]);
+  cswap(w[1], w[2]); cswap(w[4], w[5]); cswap(w[7], w[8]);
+  cswap(w[0], w[3]); cswap(w[5], w[8]); cswap(w[4], w[7]);
+  cswap(w[3], w[6]); cswap(w[1], w[4]); cswap(w[2], w[5]);
+  cswap(w[4], w[7]); cswap(w[4], w[2]); cswap(w[6], w[4]);
+  cswap(w[4], w[2]);
+  dst[(size_t)v * W + u] = (int16_t)w[4];
+}
+
+extern "C" int sm_median3_i16(sm_ctx* ctx, const int16_t* d_src, int16_t* d_dst, int H, int W) {
+  SM_CHECK_ARG(ctx && d_src && d_dst && d_src != d_dst && H > 0 && W > 0);
+  dim3 grid(sm_div_up(W, 128), H);
+  SM_LAUNCH(ctx, k_median3_i16, grid, 128, 0, d_src, d_dst, H, W);
+  return SM_OK;
+}
+
+// ------------------------------------------------------------------ 1-level cross-scale step
+__global__ void k_scale(float* __restrict__ vol, size_t n, float inv) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) vol[i] = 0.0f + inv * vol[i];  // sum = 0; sum += invWgt * cost
+}
+
+extern "C" int sm_cross_scale_1level(sm_ctx* ctx, float* d_vol, size_t n, float lambda) {
+  SM_CHECK_ARG(ctx && d_vol);
+  const float inv = 1.0f / (1.0f + lambda);
+  int grid = (int)min((size_t)ctx->num_sms * 16, (n + 255) / 256);
+  SM_LAUNCH(ctx, k_scale, grid, 256, 0, d_vol, n, inv);
+  return SM_OK;
+}

@@ -1,0 +1,314 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) and, when present, of the
+compiled reference NL library (oracle/_ref/libqxref.so).
+
+TEST INFRASTRUCTURE.  Import only from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Never from the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+class OrcParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("D", "censusFunc", "paths", "iters", "L", "L_out", "tau",
+                                       "tau_out", "minL", "corDifThres", "reduCoeffi1")] + \
+               [(n, C.c_float) for n in ("adTrunc", "lamAD", "lamCen", "LRmaxDiff", "voteRatio")] + \
+               [(n, C.c_int) for n in ("voteS", "voteNums", "DISP_OCC", "do_refine")]
+
+
+def default_params(D, paths=4, census_func=3, do_refine=1):
+    """Reference defaults: stereoMatching.h:204-350, stereoMatching.cpp:905, 5270."""
+    return OrcParams(D=D, censusFunc=census_func, paths=paths, iters=2, L=17, L_out=34, tau=20,
+                     tau_out=6, minL=1, corDifThres=15, reduCoeffi1=4, adTrunc=1000.0, lamAD=10.0,
+                     lamCen=30.0, LRmaxDiff=0.0, voteRatio=0.4, voteS=20, voteNums=2, DISP_OCC=-32,
+                     do_refine=do_refine)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("stereo_oracle.cpp", "nl_oracle.cpp")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    I, F, P = C.c_int, C.c_float, C.c_void_p
+    sig = {
+        "orc_set_threads": ([I], None), "orc_get_threads": ([], I), "orc_has_openmp": ([], I),
+        "orc_bgr2gray": ([u8p, I, I, u8p], None),
+        "orc_census_code_length": ([I, I, I], I),
+        "orc_census": ([u8p, I, I, I, I, I, u64p], None),
+        "orc_hamming_vol": ([u64p, u64p, I, I, I, I, I, F, I, f32p], None),
+        "orc_ad_vol": ([u8p, u8p, I, I, I, I, F, f32p], None),
+        "orc_combine_exp": ([f32p, f32p, C.c_long, F, F, f32p], None),
+        "orc_exp_tables": ([F, F, F, I, f32p, f32p], None),
+        "orc_arms": ([u8p, I, I, I, I, I, I, I, I, u16p], None),
+        "orc_arms_intersect": ([u16p, u16p, I, I, I, I, u16p], None),
+        "orc_cbca": ([f32p, u16p, u16p, I, I, I, I, I, P], None),
+        "orc_sgm_path": ([f32p, u8p, I, I, I, I, I, I, I, f32p], None),
+        "orc_sgm": ([f32p, u8p, I, I, I, I, I, I], None),
+        "orc_wta": ([f32p, I, I, I, i16p], None),
+        "orc_wta_co": ([f32p, I, I, I, I, i16p, i16p], None),
+        "orc_lrc_normal": ([i16p, i16p, I, I, F], None),
+        "orc_lrc_label": ([i16p, i16p, I, I, I, F, I, I, u8p], None),
+        "orc_region_vote": ([i16p, u16p, I, I, I, F, I], None),
+        "orc_proper_ipol": ([i16p, u8p, I, I, I], None),
+        "orc_median3_i16": ([i16p, I, I, i16p], None),
+        "orc_solve_all_1level": ([f32p, C.c_long, F], None),
+        "orc_pipeline": ([u8p, u8p, u8p, u8p, I, I, C.POINTER(OrcParams), i16p, i16p, P, P], None),
+        "orc_ctmf": ([u8p, u8p, I, I, I, I, I, I], None),
+        "orc_mst": ([u8p, I, I, I, i32p, u8p, i32p, i32p, i32p, i32p, P], None),
+        "orc_tree_table": ([C.c_double, f64p], None),
+        "orc_tree_filter": ([f64p, f64p, I, I, i32p, u8p, i32p, i32p, i32p, f64p], None),
+        "orc_nl_aggre": ([u8p, I, I, I, f32p], None),
+        "orc_nl": ([u8p, I, I, I, f32p, P], None),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes, fn.restype = args, res
+    _LIB = L
+    return L
+
+
+def ref_lib():
+    """The reference's own NL sources compiled by oracle/build_ref.sh, or None."""
+    global _REF
+    if _REF is not None:
+        return _REF
+    so = os.path.join(_HERE, "_ref", "libqxref.so")
+    if not os.path.exists(so):
+        return None
+    L = C.CDLL(so)
+    I = C.c_int
+    L.qxref_ctmf.argtypes = [u8p, u8p, I, I, I, I, I, I, C.c_ulong]
+    L.qxref_mst.argtypes = [u8p, I, I, I, i32p, u8p, i32p, i32p, i32p, i32p]
+    L.qxref_tree_filter.argtypes = [u8p, I, I, I, C.c_double, f64p, f64p]
+    for f in (L.qxref_ctmf, L.qxref_mst, L.qxref_tree_filter):
+        f.restype = None
+    _REF = L
+    return L
+
+
+# ----------------------------------------------------------------------------- numpy-level helpers
+def bgr2gray(bgr):
+    H, W, _ = bgr.shape
+    out = np.empty((H, W), np.uint8)
+    lib().orc_bgr2gray(np.ascontiguousarray(bgr), H, W, out)
+    return out
+
+
+def census(gray, func=3, RV=3, RU=4):
+    H, W = gray.shape
+    nw = (lib().orc_census_code_length(func, RV, RU) + 63) // 64
+    out = np.empty((H, W, nw), np.uint64)
+    lib().orc_census(np.ascontiguousarray(gray), H, W, func, RV, RU, out)
+    return out
+
+
+def hamming_vol(cL, cR, D, func=3, LOR=0, trunc_rat=1.0):
+    H, W, nw = cL.shape
+    out = np.empty((H, W, D), np.float32)
+    lib().orc_hamming_vol(cL, cR, H, W, D, nw, lib().orc_census_code_length(func, 3, 4), trunc_rat, LOR, out)
+    return out
+
+
+def ad_vol(bgrL, bgrR, D, LOR=0, trunc=1000.0):
+    H, W, _ = bgrL.shape
+    out = np.empty((H, W, D), np.float32)
+    lib().orc_ad_vol(np.ascontiguousarray(bgrL), np.ascontiguousarray(bgrR), H, W, D, LOR, trunc, out)
+    return out
+
+
+def combine_exp(a, b, l0=10.0, l1=30.0):
+    out = np.empty_like(a)
+    lib().orc_combine_exp(a, b, a.size, l0, l1, out)
+    return out
+
+
+def adcensus_vol(bgrL, bgrR, grayL, grayR, D, LOR=0, func=3, trunc=1000.0, lamAD=10.0, lamCen=30.0):
+    ad = ad_vol(bgrL, bgrR, D, LOR, trunc)
+    cen = hamming_vol(census(grayL, func), census(grayR, func), D, func, LOR)
+    return combine_exp(ad, cen, lamAD, lamCen)
+
+
+def arms(img, L=17, L_out=34, tau=20, tau_out=6, minL=1):
+    H, W, Cn = img.shape
+    out = np.empty((H, W, 5), np.uint16)
+    lib().orc_arms(np.ascontiguousarray(img), H, W, Cn, L, L_out, tau, tau_out, minL, out)
+    return out
+
+
+def arms_intersect(aL, aR, D, view=0):
+    H, W, _ = aL.shape
+    out = np.empty((H, W, D, 5), np.uint16)
+    lib().orc_arms_intersect(aL, aR, H, W, D, view, out)
+    return out
+
+
+def cbca(vol, aL, aR, iters=2, view=0, want_area=False):
+    H, W, D = vol.shape
+    out = np.ascontiguousarray(vol.copy())
+    area = np.empty((H, W, D), np.int32) if want_area else None
+    lib().orc_cbca(out, aL, aR, H, W, D, iters, view, area.ctypes.data if want_area else None)
+    return (out, area) if want_area else out
+
+
+def sgm_path(vol, bgr, path, thr=15, redu=4):
+    H, W, D = vol.shape
+    rv = (+1, -1, 0, 0, +1, +1, -1, -1)[path]
+    ru = (0, 0, +1, -1, -1, +1, +1, -1)[path]
+    out = np.empty_like(vol)
+    lib().orc_sgm_path(np.ascontiguousarray(vol), np.ascontiguousarray(bgr), H, W, D, rv, ru, thr, redu, out)
+    return out
+
+
+def sgm(vol, bgr, paths=4, thr=15, redu=4):
+    H, W, D = vol.shape
+    out = np.ascontiguousarray(vol.copy())
+    lib().orc_sgm(out, np.ascontiguousarray(bgr), H, W, D, paths, thr, redu)
+    return out
+
+
+def wta(vol):
+    H, W, D = vol.shape
+    out = np.empty((H, W), np.int16)
+    lib().orc_wta(np.ascontiguousarray(vol), H, W, D, out)
+    return out
+
+
+def wta_co(vol, scale=16):
+    H, W, D = vol.shape
+    d1 = np.empty((H, W), np.int16)
+    d2 = np.empty((H, W), np.int16)
+    lib().orc_wta_co(np.ascontiguousarray(vol), H, W, D, scale, d1, d2)
+    return d1, d2
+
+
+def lrc_normal(d1, d2, max_diff=0.0):
+    out = np.ascontiguousarray(d1.copy())
+    lib().orc_lrc_normal(out, np.ascontiguousarray(d2), d1.shape[0], d1.shape[1], max_diff)
+    return out
+
+
+def lrc_label(d1, d2, D, max_diff=0.0, occ=-32, mis=-48):
+    out = np.ascontiguousarray(d1.copy())
+    mask = np.empty(d1.shape, np.uint8)
+    lib().orc_lrc_label(out, np.ascontiguousarray(d2), d1.shape[0], d1.shape[1], D, max_diff, occ, mis, mask)
+    return out, mask
+
+
+def region_vote(dp, arms_l, D, ratio=0.4, S=20):
+    out = np.ascontiguousarray(dp.copy())
+    lib().orc_region_vote(out, arms_l, dp.shape[0], dp.shape[1], D, ratio, S)
+    return out
+
+
+def proper_ipol(dp, bgr, occ=-32):
+    out = np.ascontiguousarray(dp.copy())
+    lib().orc_proper_ipol(out, np.ascontiguousarray(bgr), dp.shape[0], dp.shape[1], occ)
+    return out
+
+
+def median3_i16(dp):
+    out = np.empty_like(dp)
+    lib().orc_median3_i16(np.ascontiguousarray(dp), dp.shape[0], dp.shape[1], out)
+    return out
+
+
+def pipeline(bgrL, bgrR, grayL, grayR, params, want_vol=False):
+    H, W, _ = bgrL.shape
+    dl = np.empty((H, W), np.int16)
+    dr = np.empty((H, W), np.int16)
+    vol = np.empty((H, W, params.D), np.float32) if want_vol else None
+    ms = np.zeros(8, np.float32)
+    lib().orc_pipeline(np.ascontiguousarray(bgrL), np.ascontiguousarray(bgrR),
+                       np.ascontiguousarray(grayL), np.ascontiguousarray(grayR), H, W,
+                       C.byref(params), dl, dr, vol.ctypes.data if want_vol else None, ms.ctypes.data)
+    names = ("census", "cost", "arms", "cbca", "sgm", "wta", "refine", "total")
+    return dl, dr, vol, dict(zip(names, ms.tolist()))
+
+
+def ctmf(img, r):
+    img = np.ascontiguousarray(img)
+    H, W = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    lib().orc_ctmf(img, out, W, H, W * cn, W * cn, r, cn)
+    return out
+
+
+def mst(img):
+    img = np.ascontiguousarray(img)
+    H, W = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    N = H * W
+    r = dict(parent=np.empty(N, np.int32), weight=np.empty(N, np.uint8), rank=np.empty(N, np.int32),
+             nr_child=np.empty(N, np.int32), children=np.empty(3 * N, np.int32), order=np.empty(N, np.int32))
+    lib().orc_mst(img, H, W, cn, r["parent"], r["weight"], r["rank"], r["nr_child"], r["children"], r["order"], None)
+    return r
+
+
+def nl_aggre(bgr, vol):
+    H, W, D = vol.shape
+    out = np.ascontiguousarray(vol.copy())
+    lib().orc_nl_aggre(np.ascontiguousarray(bgr), H, W, D, out)
+    return out
+
+
+def nl(bgr, vol):
+    H, W, D = vol.shape
+    out = np.ascontiguousarray(vol.copy())
+    disp = np.empty((H, W), np.int16)
+    lib().orc_nl(np.ascontiguousarray(bgr), H, W, D, out, disp.ctypes.data)
+    return out, disp
+
+
+def ref_ctmf(img, r):
+    L = ref_lib()
+    img = np.ascontiguousarray(img)
+    H, W = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    L.qxref_ctmf(img, out, W, H, W * cn, W * cn, r, cn, H * W * cn)
+    return out
+
+
+def ref_mst(img):
+    L = ref_lib()
+    img = np.ascontiguousarray(img)
+    H, W = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    N = H * W
+    r = dict(parent=np.empty(N, np.int32), weight=np.empty(N, np.uint8), rank=np.empty(N, np.int32),
+             nr_child=np.empty(N, np.int32), children=np.empty(3 * N, np.int32), order=np.empty(N, np.int32))
+    L.qxref_mst(img, H, W, cn, r["parent"], r["weight"], r["rank"], r["nr_child"], r["children"], r["order"])
+    return r
+
+
+def ref_tree_filter(bgr, vol64, sigma=0.1):
+    L = ref_lib()
+    H, W, D = vol64.shape
+    cost = np.ascontiguousarray(vol64.copy())
+    tmp = np.empty_like(cost)
+    L.qxref_tree_filter(np.ascontiguousarray(bgr), H, W, D, sigma, cost, tmp)
+    return cost

@@ -1,0 +1,667 @@
+// ============================================================================
+// stereo_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the dense-stereo hot path of xinge456/myStereoMatching
+// (AD-Census cost -> CBCA -> SGM -> WTA -> LR check -> refinement), written
+// from the reference's arithmetic, loop order and float operation order.
+// Each function cites the reference file:line it follows (paths relative to
+// the reference root).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.
+//
+// Pinning status: the reference ships no tests, fixtures or golden vectors
+// for stereoMatching.{h,cpp} and that file cannot be compiled here (needs
+// OpenCV C++ + ximgproc + a missing util.h), so for the functions in this
+// file parity is pinned by (i) the three OpenCV semantics on the path checked
+// against cv2 4.13 golden vectors (tests/golden/opencv_semantics.npz:
+// BORDER_REFLECT_101, medianBlur on CV_16S, BGR2GRAY) and (ii) hand-derived
+// known-answer cases in tests/.  "parity unpinned" by reference-owned vectors.
+// The NL/ part (ctmf / MST / tree filter, nl_oracle.cpp) IS pinned against the
+// reference's own sources compiled into oracle/_ref.
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off, optional -fopenmp).
+// Float contraction is disabled so a*b+c never becomes an FMA: the reference
+// is an MSVC x64 build, which does not contract.
+// ============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned char u8;
+typedef unsigned short u16;
+typedef uint64_t u64;
+typedef short i16;
+
+// Thread policy: the reference hot loops are single-threaded (OMP_PARALLEL_FOR
+// is commented out on every hot loop, stereoMatching.h:596,648,1661;
+// stereoMatching.cpp:2483,2812,3901,3975).  orc_threads==1 reproduces that.
+// orc_threads>1 parallelises only loops whose iterations are independent, and
+// never changes any result (no reduction order depends on the thread count).
+static int orc_threads = 1;
+#ifdef _OPENMP
+#define ORC_PAR_FOR _Pragma("omp parallel for schedule(static) num_threads(orc_threads)")
+#else
+#define ORC_PAR_FOR
+#endif
+
+extern "C" {
+
+void orc_set_threads(int n) { orc_threads = n < 1 ? 1 : n; }
+int orc_get_threads() { return orc_threads; }
+int orc_has_openmp() {
+#ifdef _OPENMP
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// BGR -> gray as cv::imread(...,0)/cvtColor(BGR2GRAY) does it for 8-bit:
+// fixed point, 14 fractional bits (main_.cpp:95-96 loads the gray pair with
+// imread flag 0).  Pinned against cv2 in tests/golden/opencv_semantics.npz.
+// ---------------------------------------------------------------------------
+void orc_bgr2gray(const u8* bgr, int H, int W, u8* gray) {
+  for (long i = 0; i < (long)H * W; i++) {
+    int b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+    gray[i] = (u8)((1868 * b + 9617 * g + 4899 * r + 8192) >> 14);
+  }
+}
+
+// cv::BORDER_REFLECT_101 index map (stereoMatching.h:642, 871).
+static inline int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) {
+    if (p < 0) p = -p;
+    else p = 2 * (n - 1) - p;
+  }
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// Census codes.  func 0: genCensusCode<uchar> (stereoMatching.h:634-688);
+// func 3: genCensusCode_NC_Sur (stereoMatching.h:867-934).  Window rows
+// dv=-RV..RV (outer), cols du=-RU..RU (inner), centre INCLUDED; bit =
+// (centre < neighbour), shifted in MSB-first; a word is flushed only when a
+// 65th bit arrives (the "step > 63" test).  func 3 appends 8 bits comparing
+// consecutive pixels of the inner 3x3 ring clockwise from top-left.
+// words: [H][W][nwords], nwords = ceil(codeLength/64) (stereoMatching.cpp:829-836).
+// ---------------------------------------------------------------------------
+int orc_census_code_length(int func, int RV, int RU) {
+  int len = (2 * RV + 1) * (2 * RU + 1);
+  if (func == 3) len += 8;
+  return len;
+}
+
+void orc_census(const u8* gray, int H, int W, int func, int RV, int RU, u64* words) {
+  const int codeLen = orc_census_code_length(func, RV, RU);
+  const int nwords = (codeLen + 63) / 64;
+  static const int dv_sur[9] = {-1, -1, -1, 0, 1, 1, 1, 0, -1};
+  static const int du_sur[9] = {-1, 0, 1, 1, 1, 0, -1, -1, -1};
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++) {
+    for (int u = 0; u < W; u++) {
+      u64* out = words + ((long)v * W + u) * nwords;
+      for (int k = 0; k < nwords; k++) out[k] = 0;  // stereoMatching.cpp:839
+      const int centre = gray[(long)v * W + u];
+      u64 cs = 0;
+      int step = 0, dep = 0;
+      auto push = [&](bool bit) {
+        if (step > 63) { out[dep] = cs; cs = 0; step = 0; dep++; }
+        cs <<= 1;
+        if (bit) cs++;
+        step++;
+      };
+      for (int dv = -RV; dv <= RV; dv++)
+        for (int du = -RU; du <= RU; du++) {
+          int nb = gray[(long)reflect101(v + dv, H) * W + reflect101(u + du, W)];
+          push(centre - nb < 0);
+        }
+      if (func == 3) {
+        for (int i = 0; i < 8; i++) {
+          int pre = gray[(long)reflect101(v + dv_sur[i], H) * W + reflect101(u + du_sur[i], W)];
+          int aft = gray[(long)reflect101(v + dv_sur[i + 1], H) * W + reflect101(u + du_sur[i + 1], W)];
+          push(pre - aft < 0);
+        }
+      }
+      if (step > 0) out[dep] = cs;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Hamming cost volume: gen_cenVM_XOR (stereoMatching.h:936-981) with
+// HammingDistance = popcount64 (stereoMatching.cpp:2210).  is_censusNorm = 0
+// (stereoMatching.h:247) so out-of-range = DEFAULT = codeLength*truncRat.
+// LOR 0: lp=u, rp=u-d.  LOR 1: lp=u+d, rp=u.
+// ---------------------------------------------------------------------------
+void orc_hamming_vol(const u64* cenL, const u64* cenR, int H, int W, int D, int nwords,
+                     int codeLength, float truncRat, int LOR, float* vol) {
+  const float DEFAULT = codeLength * truncRat;
+  const int lc = LOR == 1 ? 1 : 0, rc = LOR == 1 ? 0 : 1;
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      float* o = vol + ((long)v * W + u) * D;
+      for (int d = 0; d < D; d++) {
+        int lp = u + d * lc, rp = u - d * rc;
+        if (lp >= W || rp < 0) { o[d] = DEFAULT; continue; }
+        float cost = 0;
+        for (int k = 0; k < nwords; k++)
+          cost += (float)__builtin_popcountll(cenL[((long)v * W + lp) * nwords + k] ^
+                                              cenR[((long)v * W + rp) * nwords + k]);
+        o[d] = std::min(cost, DEFAULT);
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// AD cost volume: gen_ad_sd_vm with AOS=0 (stereoMatching.cpp:2468-2509),
+// 3-channel BGR (SD_AD_channel=3, stereoMatching.h:228), is_adNorm=0.
+// ---------------------------------------------------------------------------
+void orc_ad_vol(const u8* bgrL, const u8* bgrR, int H, int W, int D, int LOR, float trunc,
+                float* vol) {
+  const int lc = LOR == 1 ? 1 : 0, rc = LOR == 1 ? 0 : -1;
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      float* o = vol + ((long)v * W + u) * D;
+      for (int d = 0; d < D; d++) {
+        int uL = u + d * lc, uR = u + d * rc;
+        if (uL >= W || uR < 0) { o[d] = trunc; continue; }
+        const u8* l = bgrL + ((long)v * W + uL) * 3;
+        const u8* r = bgrR + ((long)v * W + uR) * 3;
+        float sum = 0;
+        for (int c = 0; c < 3; c++) sum += std::fabs((float)l[c] - (float)r[c]);
+        o[d] = std::min(sum / 3, trunc);
+      }
+    }
+}
+
+// gen_vm_from2vm_exp (stereoMatching.cpp:3566-3590): 2 - exp(-a/l0) - exp(-b/l1),
+// float exp overload, left-to-right subtraction.
+void orc_combine_exp(const float* a, const float* b, long n, float l0, float l1, float* out) {
+  ORC_PAR_FOR
+  for (long i = 0; i < n; i++) out[i] = 2 - std::exp(-a[i] / l0) - std::exp(-b[i] / l1);
+}
+
+// The two 1-D tables the fused GPU kernel indexes: for every possible AD
+// numerator k = sum_c |l_c - r_c| (0..765, plus slot 766 = out-of-range) and
+// every Hamming count c (0..codeLength) the exact float the reference's libm
+// call produces.  Host-side helper of the same arithmetic as orc_ad_vol +
+// orc_combine_exp; the product library has its own copy of this logic.
+void orc_exp_tables(float trunc, float lamAD, float lamCen, int codeLength, float* tabAD /*767*/,
+                    float* tabCen /*codeLength+1*/) {
+  for (int k = 0; k <= 765; k++) {
+    float ad = std::min((float)k / 3, trunc);
+    tabAD[k] = std::exp(-ad / lamAD);
+  }
+  tabAD[766] = std::exp(-trunc / lamAD);
+  for (int c = 0; c <= codeLength; c++) tabCen[c] = std::exp(-(float)c / lamCen);
+}
+
+// ---------------------------------------------------------------------------
+// Cross arms: calHorVerDis<uchar>(I,cross,L,L_out,C_D,C_D_out,minL)
+// (stereoMatching.cpp:2958-3050) with judgeColorDif (stereoMatching.cpp:2847).
+// cross: [H][W][5] u16 = [left,right,up,down,sum].  C = channels (3 for I_c).
+// ---------------------------------------------------------------------------
+static inline bool color_within(const u8* a, const u8* b, int thres, int C) {
+  for (int c = 0; c < C; c++)
+    if (std::abs((int)a[c] - (int)b[c]) > thres) return false;
+  return true;
+}
+
+void orc_arms(const u8* img, int H, int W, int C, int L, int L_out, int C_D, int C_D_out, int minL,
+              u16* cross) {
+  static const int DU[4] = {-1, +1, 0, 0};  // left, right, up, down
+  static const int DV[4] = {0, 0, -1, +1};
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      const u8* p = img + ((long)v * W + u) * C;
+      u16* out = cross + ((long)v * W + u) * 5;
+      int sum = 0;
+      for (int dir = 0; dir < 4; dir++) {
+        const int du = DU[dir], dv = DV[dir];
+        int arm = 1;
+        for (; arm <= L_out; arm++) {
+          int va = v + arm * dv, ua = u + arm * du;
+          if (va < 0 || va >= H || ua < 0 || ua >= W) break;
+          const u8* q = img + ((long)va * W + ua) * C;
+          const u8* qp = img + ((long)(v + (arm - 1) * dv) * W + (u + (arm - 1) * du)) * C;
+          bool nb_ok = color_within(q, qp, C_D, C);
+          bool an_ok = color_within(p, q, arm <= L ? C_D : C_D_out, C);
+          if (!nb_ok || !an_ok) break;
+        }
+        --arm;
+        int res = 0;
+        if (arm >= minL) res = arm;
+        else {
+          for (int len = minL; len >= 0; len--)
+            if (u + len * du >= 0 && u + len * du <= W - 1 && v + len * dv >= 0 &&
+                v + len * dv <= H - 1) { res = len; break; }
+        }
+        out[dir] = (u16)res;
+        sum += res;
+      }
+      out[4] = (u16)sum;
+    }
+}
+
+// Per-(pixel,d) intersected arms: genTrueHorVerArms (stereoMatching.cpp:2794-2845).
+// view 0: u_l=u, u_r=u-d; view 1: u_l=u+d, u_r=u.  Out-of-range entries stay 0.
+static inline void isect_arms(const u16* armsL, const u16* armsR, int W, int v, int u, int d,
+                              int view, int a[4]) {
+  int ul = view == 1 ? u + d : u, ur = view == 1 ? u : u - d;
+  if (ur < 0 || ul >= W) { a[0] = a[1] = a[2] = a[3] = 0; return; }
+  const u16* l = armsL + ((long)v * W + ul) * 5;
+  const u16* r = armsR + ((long)v * W + ur) * 5;
+  for (int k = 0; k < 4; k++) a[k] = std::min(l[k], r[k]);
+}
+
+// Materialised form (small sizes only; used by tests): [H][W][D][5] u16.
+void orc_arms_intersect(const u16* armsL, const u16* armsR, int H, int W, int D, int view,
+                        u16* out) {
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++)
+      for (int d = 0; d < D; d++) {
+        int a[4];
+        isect_arms(armsL, armsR, W, v, u, d, view, a);
+        u16* o = out + (((long)v * W + u) * D + d) * 5;
+        for (int k = 0; k < 4; k++) o[k] = (u16)a[k];
+        o[4] = (u16)(a[0] + a[1] + a[2] + a[3]);
+      }
+}
+
+// ---------------------------------------------------------------------------
+// CBCA: cbca_core (stereoMatching.cpp:5585-5666) for ONE view with
+// cbca_intersect=true: per iteration areaIS<-1, then (even iteration) H cumsum,
+// H span, V cumsum, V span, (odd iteration) V first then H; then vm /= areaIS.
+// gen1DCumu: stereoMatching.cpp:3896-3926 (in-place raster running sum);
+// cal1DCost: stereoMatching.h:1643-1715; genfinalVm_cbca: stereoMatching.cpp:3969-3992.
+// The reference's H*W*D*5 intersection tensor is evaluated on the fly (same
+// values, see isect_arms).  area_out (nullable) receives the last iteration's
+// areaIS (int32, [H][W][D]).
+// ---------------------------------------------------------------------------
+static void cumu_1d(float* vm, int* area, int H, int W, int D, int dv, int du) {
+  // Sequential dependence along the scan axis only; rows (du=-1) resp. columns
+  // (dv=-1) are independent, which is what the parallel variant exploits.
+  if (du == -1) {
+    ORC_PAR_FOR
+    for (int v = 0; v < H; v++)
+      for (int u = 1; u < W; u++) {
+        float* c = vm + ((long)v * W + u) * D;
+        int* a = area + ((long)v * W + u) * D;
+        for (int d = 0; d < D; d++) { c[d] += c[d - D]; a[d] += a[d - D]; }
+      }
+  } else {
+    const long rs = (long)W * D;
+    for (int v = 1; v < H; v++) {
+      ORC_PAR_FOR
+      for (int u = 0; u < W; u++) {
+        float* c = vm + ((long)v * W + u) * D;
+        int* a = area + ((long)v * W + u) * D;
+        for (int d = 0; d < D; d++) { c[d] += c[d - rs]; a[d] += a[d - rs]; }
+      }
+    }
+  }
+}
+
+static void span_1d(const float* vm, const int* area, float* vmT, int* areaT, const u16* armsL,
+                    const u16* armsR, int H, int W, int D, int view, int dv, int du, int direc) {
+  const int head_num = direc * 2 + 1, tail_num = direc * 2;
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++)
+      for (int d = 0; d < D; d++) {
+        int a[4];
+        isect_arms(armsL, armsR, W, v, u, d, view, a);
+        int tail_u = u + du * a[tail_num], tail_v = v + dv * a[tail_num];
+        int head_u = u - du * a[head_num], head_v = v - dv * a[head_num];
+        int pu = tail_u + du, pv = tail_v + dv;
+        bool inner = pu >= 0 && pu < W && pv >= 0 && pv < H;
+        long ih = ((long)head_v * W + head_u) * D + d, ip = ((long)pv * W + pu) * D + d;
+        long io = ((long)v * W + u) * D + d;
+        areaT[io] = inner ? area[ih] - area[ip] : area[ih];
+        vmT[io] = inner ? vm[ih] - vm[ip] : vm[ih];
+      }
+}
+
+void orc_cbca(float* vol, const u16* armsL, const u16* armsR, int H, int W, int D, int iters,
+              int view, int* area_out) {
+  const long n = (long)H * W * D;
+  std::vector<float> vmT(n);
+  std::vector<int> area(n), areaT(n);
+  for (int it = 0; it < iters; it++) {
+    std::fill(area.begin(), area.end(), 1);
+    for (int pass = 0; pass < 2; pass++) {
+      int direc = (it % 2 == 0) ? pass : 1 - pass;  // 0 = horizontal, 1 = vertical
+      int dv = direc == 0 ? 0 : -1, du = direc == 0 ? -1 : 0;
+      cumu_1d(vol, area.data(), H, W, D, dv, du);
+      span_1d(vol, area.data(), vmT.data(), areaT.data(), armsL, armsR, H, W, D, view, dv, du,
+              direc);
+      std::memcpy(vol, vmT.data(), n * sizeof(float));
+      area.swap(areaT);
+    }
+    ORC_PAR_FOR
+    for (long i = 0; i < n; i++) vol[i] /= area[i];
+  }
+  if (area_out) std::memcpy(area_out, area.data(), n * sizeof(int));
+}
+
+// ---------------------------------------------------------------------------
+// SGM.  sgm (stereoMatching.cpp:6204-6224): predecessor offsets
+// rv={+1,-1,0,0,+1,+1,-1,-1}, ru={0,0,+1,-1,-1,+1,+1,-1}; costScan
+// (stereoMatching.cpp:1983-2029) raster order, reversed when rv>0 or
+// (rv==0 && ru>0); updateCost<float> (stereoMatching.h:2205-2280): literal
+// P1=1, P2=3, both /= reduCoeffi1 when the current-view colour step D1 >
+// corDifThres; P1 -= minC; Lr = C + min4(Lr'[d]-minC, Lr'[d-1]+P1, Lr'[d+1]+P1, P2).
+// bgr = colour image of the view being optimised (I_c[0] if leftFirst).
+// ---------------------------------------------------------------------------
+static const int SGM_RV[8] = {+1, -1, 0, 0, +1, +1, -1, -1};
+static const int SGM_RU[8] = {0, 0, +1, -1, -1, +1, +1, -1};
+
+void orc_sgm_path(const float* vol, const u8* bgr, int H, int W, int D, int rv, int ru,
+                  int corDifThres, int reduCoeffi1, float* Lr) {
+  int v0 = 0, v1 = H, u0 = 0, u1 = W, dv = +1, du = +1;
+  if (rv > 0 || (rv == 0 && ru > 0)) { v0 = H - 1; v1 = -1; u0 = W - 1; u1 = -1; dv = -1; du = -1; }
+  const float FMAX = std::numeric_limits<float>::max();
+  for (int v = v0; v != v1; v += dv)
+    for (int u = u0; u != u1; u += du) {
+      const float* C = vol + ((long)v * W + u) * D;
+      float* out = Lr + ((long)v * W + u) * D;
+      bool inner = !(v + rv > H - 1 || v + rv < 0 || u + ru > W - 1 || u + ru < 0);
+      if (!inner) { for (int d = 0; d < D; d++) out[d] = C[d]; continue; }
+      int D1 = 0;
+      const u8* p = bgr + ((long)v * W + u) * 3;
+      const u8* q = bgr + ((long)(v + rv) * W + (u + ru)) * 3;
+      for (int c = 0; c < 3; c++) D1 = std::max(D1, std::abs((int)p[c] - (int)q[c]));
+      const float* prev = Lr + ((long)(v + rv) * W + (u + ru)) * D;
+      float minC = FMAX;
+      for (int d = 0; d < D; d++) minC = std::min(prev[d], minC);
+      float P1 = 1.0f, P2 = 3.0f;
+      if (D1 > corDifThres) { P1 /= reduCoeffi1; P2 /= reduCoeffi1; }
+      P1 -= minC;
+      for (int d = 0; d < D; d++) {
+        float S1 = prev[d] - minC;
+        float S2 = d - 1 >= 0 ? prev[d - 1] + P1 : FMAX;
+        float S3 = d + 1 < D ? prev[d + 1] + P1 : FMAX;
+        float S4 = P2;
+        out[d] = C[d] + std::min(std::min(S1, S2), std::min(S3, S4));
+      }
+    }
+}
+
+// sgm + gen_sgm_vm (stereoMatching.cpp:2031-2056): vm = ((0+L0)+L1)+... , no
+// averaging.  P = number of paths (reference compiles 4; 8 = same table).
+// The paths are independent of each other, so they may run on separate threads.
+void orc_sgm(float* vol, const u8* bgr, int H, int W, int D, int P, int corDifThres,
+             int reduCoeffi1) {
+  const long n = (long)H * W * D;
+  std::vector<std::vector<float>> L(P);
+  for (int i = 0; i < P; i++) L[i].resize(n);
+  ORC_PAR_FOR
+  for (int i = 0; i < P; i++)
+    orc_sgm_path(vol, bgr, H, W, D, SGM_RV[i], SGM_RU[i], corDifThres, reduCoeffi1, L[i].data());
+  ORC_PAR_FOR
+  for (long i = 0; i < n; i++) {
+    float sum = 0;
+    for (int k = 0; k < P; k++) sum += L[k][i];
+    vol[i] = sum;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// WTA: gen_dispFromVm (stereoMatching.cpp:3928-3967), ChooseSmall=true:
+// strict '>' so the lowest d wins ties; -1 when nothing beats FLT_MAX.
+// ---------------------------------------------------------------------------
+void orc_wta(const float* vol, int H, int W, int D, i16* disp) {
+  ORC_PAR_FOR
+  for (long i = 0; i < (long)H * W; i++) {
+    float minC = std::numeric_limits<float>::max();
+    int best = -1;
+    const float* c = vol + i * D;
+    for (int d = 0; d < D; d++)
+      if (minC > c[d]) { minC = c[d]; best = d; }
+    disp[i] = (i16)best;
+  }
+}
+
+// wta_Co (stereoMatching.cpp:2709-2792) with UniqCk=SubIpl=0: left WTA over
+// d<=u, right map from the LEFT volume along the diagonal, both x DISP_SCALE.
+void orc_wta_co(const float* vol, int H, int W, int D, int scale, i16* D1, i16* D2) {
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      float mR = std::numeric_limits<float>::max(), mL = mR;
+      int dR = 0, dL = 0;
+      for (int d = 0; d < D; d++) {
+        if (u + d >= W) break;
+        float c = vol[((long)v * W + u + d) * D + d];
+        if (c < mR) { mR = c; dR = d; }
+      }
+      D2[(long)v * W + u] = (i16)(dR * scale);
+      const float* c = vol + ((long)v * W + u) * D;
+      for (int d = 0; d < D; d++) {
+        if (u - d < 0) break;
+        if (c[d] < mL) { dL = d; mL = c[d]; }
+      }
+      D1[(long)v * W + u] = (i16)(dL * scale);
+    }
+}
+
+// LRConsistencyCheck_normal (stereoMatching.cpp:2262-2282): invalid -> -1.
+void orc_lrc_normal(i16* D1, const i16* D2, int H, int W, float maxDiff) {
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      i16 d = D1[(long)v * W + u];
+      if (d < 0 || u - d < 0 || std::abs(d - D2[(long)v * W + u - d]) > maxDiff)
+        D1[(long)v * W + u] = -1;
+    }
+}
+
+// LRConsistencyCheck, LOR=0 branch (stereoMatching.cpp:2284-2335): labels
+// occluded (no D2[u-d']==d' exists) vs mismatched, writes an error mask.
+void orc_lrc_label(i16* D1, const i16* D2, int H, int W, int D, float maxDiff, int DISP_OCC,
+                   int DISP_MIS, u8* errMask) {
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      long i = (long)v * W + u;
+      i16 d = D1[i];
+      errMask[i] = 0;
+      if (d < 0 || u - d < 0 || std::abs(d - D2[i - d]) > maxDiff) {
+        errMask[i] = 255;
+        int disp = DISP_OCC;
+        for (int dd = 0; dd < D && u - dd >= 0; dd++)
+          if (D2[i - dd] == dd) { disp = DISP_MIS; break; }
+        D1[i] = (i16)disp;
+      }
+    }
+}
+
+// regionVote_my (stereoMatching.cpp:7219-7277).  arms = HVL[0] (image-space
+// arms of the LEFT image, not intersected).  Note hist[mode]/validNum is an
+// integer division (line 7270).  Jacobi update (reads Dp, writes a clone).
+void orc_region_vote(i16* Dp, const u16* arms, int H, int W, int D, float ratio, int S) {
+  std::vector<i16> res(Dp, Dp + (long)H * W);
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++) {
+    std::vector<int> hist(D);
+    for (int u = 0; u < W; u++) {
+      if (Dp[(long)v * W + u] >= 0) continue;
+      std::fill(hist.begin(), hist.end(), 0);
+      int valid = 0;
+      const u16* a = arms + ((long)v * W + u) * 5;
+      for (int vn = v - a[2]; vn <= v + a[3]; vn++) {
+        const u16* b = arms + ((long)vn * W + u) * 5;
+        for (int un = u - b[0]; un <= u + b[1]; un++) {
+          i16 x = Dp[(long)vn * W + un];
+          if (x >= 0) { valid++; hist[x]++; }
+        }
+      }
+      if (valid <= S) continue;
+      int most = 0;
+      for (int d = 1; d < D; d++)
+        if (hist[d] > hist[most]) most = d;
+      if (hist[most] / valid >= ratio) res[(long)v * W + u] = (i16)most;
+    }
+  }
+  std::memcpy(Dp, res.data(), sizeof(i16) * H * W);
+}
+
+// properIpol (stereoMatching.cpp:7395-7490): 16 directions, <= 20 half/full
+// steps, first valid pixel per direction; DISP_OCC pixels take the minimum
+// disparity, others the disparity of the smallest max-channel colour distance
+// (strictly below 255).  Jacobi.
+void orc_proper_ipol(i16* Dp, const u8* bgr, int H, int W, int DISP_OCC) {
+  static const int dirW[16] = {0, 2, 2, 2, 0, -2, -2, -2, 1, 2, 2, 1, -1, -2, -2, -1};
+  static const int dirH[16] = {2, 2, 0, -2, -2, -2, 0, 2, 2, 1, -1, -2, -2, -1, 1, 2};
+  std::vector<i16> res((long)H * W);
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      long i = (long)v * W + u;
+      i16 cur = Dp[i];
+      if (cur >= 0) { res[i] = cur; continue; }
+      int dDisp[16], dDiff[16];
+      for (int k = 0; k < 16; k++) {
+        dDisp[k] = -1; dDiff[k] = -1;
+        int pw = dirW[k], ph = dirH[k], x = u, y = v;
+        for (int dep = 0; dep < 20; dep++) {
+          if (dep % 2 == 0) { x += pw / 2; y += ph / 2; }
+          else { x += pw - pw / 2; y += ph - ph / 2; }
+          if (!(x >= 0 && x < W && y >= 0 && y < H)) break;
+          i16 q = Dp[(long)y * W + x];
+          if (q >= 0) {
+            dDisp[k] = q;
+            int cd = 0;
+            for (int c = 0; c < 3; c++)
+              cd = std::max(cd, std::abs((int)bgr[i * 3 + c] - (int)bgr[((long)y * W + x) * 3 + c]));
+            dDiff[k] = cd;
+            break;
+          }
+        }
+      }
+      if (cur == DISP_OCC) {
+        int m = std::numeric_limits<int>::max();
+        for (int k = 0; k < 16; k++)
+          if (dDisp[k] >= 0 && m > dDisp[k]) m = dDisp[k];
+        res[i] = (i16)(m != std::numeric_limits<int>::max() ? m : cur);
+      } else {
+        int mc = 255, disp = -1;
+        for (int k = 0; k < 16; k++)
+          if (dDiff[k] >= 0 && mc > dDiff[k]) { mc = dDiff[k]; disp = dDisp[k]; }
+        res[i] = (i16)(disp >= 0 ? disp : cur);
+      }
+    }
+  std::memcpy(Dp, res.data(), sizeof(i16) * H * W);
+}
+
+// cv::medianBlur(CV_16S, ksize 3) == 3x3 median with replicated border
+// (stereoMatching.cpp:1499; pinned against cv2 in tests/golden).
+void orc_median3_i16(const i16* src, int H, int W, i16* dst) {
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      i16 w[9];
+      int k = 0;
+      for (int dv = -1; dv <= 1; dv++)
+        for (int du = -1; du <= 1; du++) {
+          int y = std::min(std::max(v + dv, 0), H - 1), x = std::min(std::max(u + du, 0), W - 1);
+          w[k++] = src[(long)y * W + x];
+        }
+      std::nth_element(w, w + 4, w + 9);
+      dst[(long)v * W + u] = w[4];
+    }
+}
+
+// The caller's single-level cross-scale step: SolveAll with PY_LVL=1
+// (stereoMatching.cpp:2142-2208; main_.cpp:158): regInv = 1/(1+lambda) as a
+// float, vm = 0 + invWgt*vm.
+void orc_solve_all_1level(float* vol, long n, float lambda) {
+  float inv = 1.0f / (1.0f + lambda);  // 1x1 Mat::inv of (1+lambda)
+  ORC_PAR_FOR
+  for (long i = 0; i < n; i++) { float sum = 0; sum += inv * vol[i]; vol[i] = sum; }
+}
+
+// ---------------------------------------------------------------------------
+// Whole default chain for one stereo pair, as main()/pipeline() drive it with
+// costcalculation="ADCensus", aggregation="CBCA", optimization="sgm"
+// (stereoMatching.cpp:945-1021, 1046-1136, 1364-1506), Do_refine=1,
+// Do_LRConsis=1.  stage_ms (nullable, 8 floats) gets per-stage wall times:
+// census, cost, arms, cbca, sgm, wta, refine, total.
+// ---------------------------------------------------------------------------
+struct orc_params {
+  int D, censusFunc, paths, iters, L, L_out, tau, tau_out, minL, corDifThres, reduCoeffi1;
+  float adTrunc, lamAD, lamCen, LRmaxDiff, voteRatio;
+  int voteS, voteNums, DISP_OCC, do_refine;
+};
+}  // extern "C"
+
+#include <chrono>
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" {
+void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* grayR, int H, int W,
+                  const orc_params* p, i16* dispL, i16* dispR, float* volL_out, float* stage_ms) {
+  const int D = p->D;
+  const long n = (long)H * W * D;
+  double t0 = now_ms(), t = t0, ms[8] = {0};
+  auto lap = [&](int k) { double x = now_ms(); ms[k] += x - t; t = x; };
+  const int codeLen = orc_census_code_length(p->censusFunc, 3, 4);  // stereoMatching.cpp:815
+  const int nw = (codeLen + 63) / 64;
+  std::vector<u64> cL((long)H * W * nw), cR((long)H * W * nw);
+  orc_census(grayL, H, W, p->censusFunc, 3, 4, cL.data());
+  orc_census(grayR, H, W, p->censusFunc, 3, 4, cR.data());
+  lap(0);
+  const int views = p->do_refine ? 2 : 1;
+  std::vector<std::vector<float>> vm(2);
+  {
+    std::vector<float> ad(n), cen(n);
+    for (int i = 0; i < 2; i++) {  // cost volumes are always built for both views (:898)
+      vm[i].resize(n);
+      orc_ad_vol(bgrL, bgrR, H, W, D, i, p->adTrunc, ad.data());
+      orc_hamming_vol(cL.data(), cR.data(), H, W, D, nw, codeLen, 1.0f, i, cen.data());
+      orc_combine_exp(ad.data(), cen.data(), n, p->lamAD, p->lamCen, vm[i].data());
+    }
+  }
+  lap(1);
+  std::vector<u16> aL((long)H * W * 5), aR((long)H * W * 5);
+  orc_arms(bgrL, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aL.data());
+  orc_arms(bgrR, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aR.data());
+  lap(2);
+  for (int i = 0; i < views; i++)
+    orc_cbca(vm[i].data(), aL.data(), aR.data(), H, W, D, p->iters, i, nullptr);
+  lap(3);
+  for (int i = 0; i < views; i++)
+    orc_sgm(vm[i].data(), i == 0 ? bgrL : bgrR, H, W, D, p->paths, p->corDifThres, p->reduCoeffi1);
+  lap(4);
+  orc_wta(vm[0].data(), H, W, D, dispL);
+  if (views == 2) orc_wta(vm[1].data(), H, W, D, dispR);
+  lap(5);
+  if (p->do_refine) {
+    orc_lrc_normal(dispL, dispR, H, W, p->LRmaxDiff);
+    for (int i = 0; i < p->voteNums; i++)
+      orc_region_vote(dispL, aL.data(), H, W, D, p->voteRatio, p->voteS);
+    for (int i = 0; i < p->voteNums; i++) orc_proper_ipol(dispL, bgrL, H, W, p->DISP_OCC);
+    std::vector<i16> tmp(dispL, dispL + (long)H * W);
+    orc_median3_i16(tmp.data(), H, W, dispL);
+  }
+  lap(6);
+  if (volL_out) std::memcpy(volL_out, vm[0].data(), n * sizeof(float));
+  ms[7] = now_ms() - t0;
+  if (stage_ms)
+    for (int k = 0; k < 8; k++) stage_ms[k] = (float)ms[k];
+}
+}  // extern "C"
