@@ -77,7 +77,8 @@ void sm_params_default(sm_params* p, int maxDisp);
 
 /* ---- context / memory ---------------------------------------------------- */
 /* stream: a cudaStream_t to launch on (e.g. the caller's current stream), or
- * NULL to let the ctx create its own non-blocking stream. */
+ * NULL to let the ctx create its own non-blocking stream.  To run on the legacy
+ * default stream pass cudaStreamLegacy ((void*)0x1), not 0. */
 int sm_ctx_create(sm_ctx** out, int device, void* stream);
 int sm_ctx_destroy(sm_ctx* ctx);
 int sm_ctx_sync(sm_ctx* ctx);

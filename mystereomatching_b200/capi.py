@@ -139,7 +139,9 @@ class Ctx:
         if L.sm_device_count() <= 0:
             raise SmError("no CUDA device visible: sm_b200 has no CPU fallback")
         torch.cuda.set_device(device)
-        stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
+        # torch's default stream has handle 0, which the C ABI reads as "create your own stream"; the
+        # explicit handle of the legacy default stream is cudaStreamLegacy == 0x1.
+        stream = (torch.cuda.current_stream(device).cuda_stream or 1) if use_torch_stream else None
         h = C.c_void_p()
         check(L.sm_ctx_create(C.byref(h), device, stream))
         self.h = h
