@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the dense-stereo hot path (MDE/s = W*H*D disparity evaluations per second, and fps).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+
+A "step" is one stereo frame through the whole path (AD-Census cost for 2 views -> CBCA x2 iterations -> 8-path
+SGM -> WTA -> LR check -> region vote x2 -> interpolation x2 -> 3x3 median).  The default workload is BASELINE.json's
+metric configuration, 1920x1080 with D=256 (configs[2]/[4]), synthetic texture-warped pairs.
+
+  value  : whole-job MDE/s with the frame already resident in HBM (sm_pipeline_run_device), CUDA events.
+  e2e    : the same through the host-buffer C-ABI call sm_pipeline_run: pinned host images in (H2D), left
+           disparity map out (D2H), copies inside the timed region.
+  roofline / stages : per-stage device time measured live (CUDA events the pipeline records on its stream
+           during the timed steps) against the algorithmic HBM bytes of SURVEY.md section 8(d).
+  cpu_baseline : the CPU oracle (oracle/, a port of the reference's arithmetic) on a bounded band of the same
+           workload, on this box's host cores (N=1, rank 0 only).
+
+N>1 (torchrun, one process per GPU): frames are independent, each rank runs its own K frames (weak scaling), no
+data-path collective; torch.distributed is used only for the barrier and the max-over-ranks time.
+
+--impl reference : the reference's own CPU algorithm for the path (oracle port; the reference's stereoMatching.cpp
+cannot be compiled here: OpenCV C++ + ximgproc + a missing util.h), all host threads, bounded band per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, D, paths, kind)
+    "c1": (450, 375, 64, 4, "random_dot"),
+    "c2": (1280, 720, 128, 8, "texture_warped"),
+    "c3": (1920, 1080, 256, 8, "texture_warped"),
+}
+
+
+def workload_desc(name):
+    W, H, D, P, kind = WORKLOADS[name]
+    return (f"{name}: {W}x{H} D={D} AD-Census(71-bit)+CBCA(2 it, intersected arms)+{P}-path SGM+WTA+LRC+"
+            f"regionVote x2+properIpol x2+median3, 2 views, fp32 volumes, synthetic {kind} pairs")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arms
+def cpu_band(name, rows):
+    """A `rows`-high band of the workload (full width and D): MDE/s is size-normalised, so the band's rate is the
+    workload's rate up to the vertical-arm / vertical-path extent."""
+    from mystereomatching_b200 import synth
+    W, H, D, P, kind = WORKLOADS[name]
+    rows = min(rows, H)
+    return synth.make_pair(rows, W, D, kind, seed=1000), rows
+
+
+def run_oracle(pair, name, threads):
+    from oracle import pyoracle as po
+    W, H, D, P, kind = WORKLOADS[name]
+    po.lib().orc_set_threads(threads)
+    op = po.default_params(D, paths=P)
+    t0 = time.perf_counter()
+    _, _, _, ms = po.pipeline(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], op)
+    return time.perf_counter() - t0, ms
+
+
+def host_threads():
+    from oracle import pyoracle as po
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return n if po.lib().orc_has_openmp() else 1
+
+
+def cpu_baseline(name, budget_rows=48):
+    pair, rows = cpu_band(name, budget_rows)
+    W, H, D, P, kind = WORKLOADS[name]
+    mde = W * rows * D / 1e6
+    nt = host_threads()
+    t1, _ = run_oracle(pair, name, 1)
+    tn, _ = run_oracle(pair, name, nt) if nt > 1 else (t1, None)
+    return {"value": mde / tn, "unit": "MDE/s", "cores": nt, "kind": "port",
+            "value_1thread": mde / t1,
+            "sample": f"one {W}x{rows} band (full width, D={D}) of the workload through the whole oracle chain; "
+                      f"{t1:.1f} s at 1 thread (the reference's own threading), {tn:.1f} s at {nt} threads"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    W, H, D, P, kind = WORKLOADS[name]
+    total = args.steps + args.warmup
+    rows = 48 if total <= 14 else (24 if total <= 40 else 12)
+    pair, rows = cpu_band(name, rows)
+    nt = host_threads()
+    for _ in range(args.warmup):
+        run_oracle(pair, name, nt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_oracle(pair, name, nt)
+    dt = time.perf_counter() - t0
+    mde = W * rows * D / 1e6
+    val = mde * args.steps / dt
+    sample = f"each step = one {W}x{rows} band (full width, D={D}) through the whole oracle chain, {nt} threads"
+    out = {"impl": "reference", "metric": "MDE/s (W*H*D disparity evaluations per second), whole path",
+           "value": val, "unit": "MDE/s", "fps_equiv": val * 1e6 / (W * H * D), "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_desc(name), "parallelism": f"host CPU, {nt} threads"},
+           "cpu_baseline": {"value": val, "unit": "MDE/s", "cores": nt, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "note": "reference's stereoMatching.cpp is not compilable here (OpenCV C++/ximgproc/util.h missing): "
+                   "this arm times the oracle port of its algorithm (oracle/stereo_oracle.cpp)"}
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def stage_bytes(name):
+    """Algorithmic HBM bytes per LAUNCH and launches per frame for each volume stage (b = 4)."""
+    W, H, D, P, kind = WORKLOADS[name]
+    V = W * H * D
+    b = 4
+    return {
+        "cost": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_cost<ADCENSUS>"},
+        "aggregation": {"bytes_per_launch": 2 * V * b, "launches": 8, "kernel": "k_cbca_pass"},
+        "sgm": {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path"},
+        "wta": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_wta"},
+    }
+
+
+def main_ours(args):
+    import numpy as np
+    import torch
+    from mystereomatching_b200 import capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    name = args.workload
+    W, H, D, P, kind = WORKLOADS[name]
+    ctx = capi.Ctx(local)
+    params = capi.default_params(D - 1, sgm_paths=P)
+    pl = capi.Pipeline(ctx, H, W, params)
+
+    # frames of this rank: frame i of the stream uses seed 1000+i, frame i -> rank i mod N
+    n_distinct = 2
+    frames = []
+    for j in range(n_distinct):
+        pr = synth.make_pair(H, W, D, kind, seed=1000 + rank + j * world)
+        pinned = {}
+        for k in ("bgrL", "bgrR", "grayL", "grayR"):
+            t = torch.from_numpy(pr[k]).pin_memory()
+            pinned[k] = t
+        frames.append((pr, pinned))
+    out_pinned = torch.empty((H, W), dtype=torch.int16).pin_memory()
+    out_np = out_pinned.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def host_args(j):
+        p = frames[j % n_distinct][1]
+        return [p[k].numpy() for k in ("bgrL", "bgrR", "grayL", "grayR")]
+
+    # ---- device-resident throughput (value) + live per-stage timing
+    pl.upload(*host_args(0))
+    for _ in range(args.warmup):
+        pl.run_device()
+    pl.enable_timing(True)
+    stage_acc = {}
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pl.run_device()
+        for k, v in pl.stage_ms().items():      # syncs this frame; the gap before the next launch is ~10 us
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launches() - l0
+    pl.enable_timing(False)
+
+    # ---- end to end through the host-buffer call (pinned host in, host disparity out)
+    for j in range(max(1, args.warmup)):
+        pl.run(*host_args(j), out=out_np)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record()
+    chk = 0
+    for j in range(args.steps):
+        pl.run(*host_args(j), out=out_np)
+        chk += int(out_np[H // 2, W // 2])       # the result is read on the host every step
+    f1.record()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), wall_ms if dist is None else f0.elapsed_time(f1)))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # sanity of the measured frames: quality against the synthetic ground truth (not part of the timing)
+    disp = pl.run(*host_args(0)).copy()
+    bad2 = synth.bad_k(disp, frames[0][0]["gt"], frames[0][0]["nonocc"], 2)
+
+    mde_frame = W * H * D / 1e6
+    value = world * args.steps * mde_frame / (dev_ms / 1e3)
+    e2e_val = world * args.steps * mde_frame / (e2e_ms / 1e3)
+    peak, peak_src = peaks()
+    sb = stage_bytes(name)
+    stages = {}
+    for k, info in sb.items():
+        ms = stage_acc.get(k, 0.0) / args.steps
+        per_launch_ms = ms / info["launches"]
+        gbs = info["bytes_per_launch"] / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        stages[k] = {"ms_per_frame": round(ms, 4), "launches": info["launches"], "kernel": info["kernel"],
+                     "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    for k in ("census", "arms", "refine", "total"):
+        stages[k] = {"ms_per_frame": round(stage_acc.get(k, 0.0) / args.steps, 4)}
+    dom = max(sb, key=lambda k: stages[k]["ms_per_frame"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(name, {}).get(sb[dom]["kernel"])
+        except Exception:
+            traffic = None
+    total_alg = sum(v["bytes_per_launch"] * v["launches"] for v in sb.values())
+    roofline = {"bound": "hbm", "kernel": sb[dom]["kernel"], "achieved": stages[dom]["GBps"], "peak": peak,
+                "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sb[dom]["bytes_per_launch"],
+                "whole_frame": {"algorithmic_GB": round(total_alg / 1e9, 2),
+                                "achieved_GBps": round(total_alg / 1e9 / (dev_ms / 1e3 / args.steps), 1),
+                                "frac": round(total_alg / 1e9 / (dev_ms / 1e3 / args.steps) / peak, 4)}}
+
+    if rank == 0:
+        out = {"metric": "MDE/s (W*H*D disparity evaluations per second), whole path",
+               "value": value, "unit": "MDE/s", "fps": value * 1e6 / (W * H * D), "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic",
+               "config": {"workload": workload_desc(name), "frames_per_step_per_gpu": 1,
+                          "parallelism": f"frame-parallel x{world}, no collective",
+                          "l2": "inputs larger than L2: each pass streams 2.1 GB volumes (L2 = 126 MB)"},
+               "e2e": {"value": e2e_val, "unit": "MDE/s", "fps": e2e_val * 1e6 / (W * H * D),
+                       "ms_per_step": e2e_ms / args.steps,
+                       "h2d_bytes_per_step": 8 * W * H, "d2h_bytes_per_step": 2 * W * H},
+               "gpu_launches": launches, "roofline": roofline, "stages": stages, "clocks": clocks,
+               "quality": {"bad2_nonocc_pct": round(bad2, 3), "checksum": chk}}
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(name)
+        print(json.dumps(out))
+    pl.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    return main_reference(args) if args.impl == "reference" else main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -27,6 +27,7 @@ struct sm_pipeline {
   uint8_t* h_in = nullptr;   // pinned staging: bgrL | bgrR | grayL | grayR
   int16_t* h_out = nullptr;  // pinned staging: dispL | dispR
   bool have_gray = false, have_arms = false;
+  bool stage_used = false, stage_drained = true;
   bool timing = false;
   cudaEvent_t ev[ST_COUNT + 1];
   bool ev_ok = false;
@@ -87,24 +88,44 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   return SM_OK;
 }
 
+// Page-locked caller buffers are copied from / to directly; pageable ones go through the pipeline's own
+// pinned staging area (one extra host memcpy) so the PCIe transfer is always a true async DMA.
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int upload_one(sm_pipeline* pl, void* d_dst, const uint8_t* h_src, uint8_t* stage, size_t bytes) {
+  sm_ctx* c = pl->ctx;
+  if (host_is_pinned(h_src)) {
+    SM_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if (!pl->stage_drained) {  // the previous frame's async copies out of the staging area must have finished
+      SM_CUDA(cudaStreamSynchronize(c->stream));
+      pl->stage_drained = true;
+    }
+    memcpy(stage, h_src, bytes);
+    SM_CUDA(cudaMemcpyAsync(d_dst, stage, bytes, cudaMemcpyHostToDevice, c->stream));
+    pl->stage_used = true;
+  }
+  return SM_OK;
+}
+
 extern "C" int sm_pipeline_upload(sm_pipeline* pl, const uint8_t* h_bgrL, const uint8_t* h_bgrR, const uint8_t* h_grayL,
                                   const uint8_t* h_grayR) {
   SM_CHECK_ARG(pl && h_bgrL && h_bgrR);
   SM_CHECK_ARG((h_grayL == nullptr) == (h_grayR == nullptr));
-  sm_ctx* c = pl->ctx;
   const size_t npix = (size_t)pl->H * pl->W;
-  // The previous frame's async copies out of the staging buffer must have drained.
-  SM_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(pl->h_in, h_bgrL, npix * 3);
-  memcpy(pl->h_in + npix * 3, h_bgrR, npix * 3);
-  SM_CUDA(cudaMemcpyAsync(pl->bgr[0], pl->h_in, npix * 3, cudaMemcpyHostToDevice, c->stream));
-  SM_CUDA(cudaMemcpyAsync(pl->bgr[1], pl->h_in + npix * 3, npix * 3, cudaMemcpyHostToDevice, c->stream));
+  SM_CUDA(cudaSetDevice(pl->ctx->device));
+  pl->stage_drained = !pl->stage_used;
+  pl->stage_used = false;
+  SM_TRY(upload_one(pl, pl->bgr[0], h_bgrL, pl->h_in, npix * 3));
+  SM_TRY(upload_one(pl, pl->bgr[1], h_bgrR, pl->h_in + npix * 3, npix * 3));
   pl->have_gray = h_grayL != nullptr;
   if (pl->have_gray) {
-    memcpy(pl->h_in + npix * 6, h_grayL, npix);
-    memcpy(pl->h_in + npix * 7, h_grayR, npix);
-    SM_CUDA(cudaMemcpyAsync(pl->gray[0], pl->h_in + npix * 6, npix, cudaMemcpyHostToDevice, c->stream));
-    SM_CUDA(cudaMemcpyAsync(pl->gray[1], pl->h_in + npix * 7, npix, cudaMemcpyHostToDevice, c->stream));
+    SM_TRY(upload_one(pl, pl->gray[0], h_grayL, pl->h_in + npix * 6, npix));
+    SM_TRY(upload_one(pl, pl->gray[1], h_grayR, pl->h_in + npix * 7, npix));
   }
   return SM_OK;
 }
@@ -201,11 +222,14 @@ extern "C" int sm_pipeline_download(sm_pipeline* pl, int16_t* h_dispL, int16_t* 
   SM_CHECK_ARG(pl && h_dispL);
   sm_ctx* c = pl->ctx;
   const size_t npix = (size_t)pl->H * pl->W;
-  SM_CUDA(cudaMemcpyAsync(pl->h_out, pl->disp[0], npix * 2, cudaMemcpyDeviceToHost, c->stream));
-  if (h_dispR) SM_CUDA(cudaMemcpyAsync(pl->h_out + npix, pl->disp[1], npix * 2, cudaMemcpyDeviceToHost, c->stream));
+  const bool pinL = host_is_pinned(h_dispL), pinR = h_dispR && host_is_pinned(h_dispR);
+  SM_CUDA(cudaMemcpyAsync(pinL ? h_dispL : pl->h_out, pl->disp[0], npix * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (h_dispR)
+    SM_CUDA(cudaMemcpyAsync(pinR ? h_dispR : pl->h_out + npix, pl->disp[1], npix * 2, cudaMemcpyDeviceToHost,
+                            c->stream));
   SM_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(h_dispL, pl->h_out, npix * 2);
-  if (h_dispR) memcpy(h_dispR, pl->h_out + npix, npix * 2);
+  if (!pinL) memcpy(h_dispL, pl->h_out, npix * 2);
+  if (h_dispR && !pinR) memcpy(h_dispR, pl->h_out + npix, npix * 2);
   return SM_OK;
 }
 
