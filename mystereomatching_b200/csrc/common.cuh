@@ -82,8 +82,11 @@ static inline int sm_div_up(long long a, long long b) { return (int)((a + b - 1)
 // ---- internal cross-file helpers ------------------------------------------------
 // BGR u8x3 interleaved -> one uint32 per pixel (b | g<<8 | r<<16), 4-byte loads.
 int smi_pack_bgr(sm_ctx* ctx, const uint8_t* d_bgr, long long npix, uint32_t* d_out);
-// arms [H][W][5] u16 -> one uint32 per pixel (left | right<<8 | up<<16 | down<<24)
-int smi_pack_arms(sm_ctx* ctx, const uint16_t* d_arms, long long npix, uint32_t* d_out);
+// arms [H][W][5] u16 -> one uint2 per pixel {armH = left | right<<16, armV = up | down<<16} in rows of W + 2*PAD
+// entries: pixel u sits at index PAD + u and the PAD entries on either side are zero (partner outside the image).
+// d_out holds 2 * H * (W + 2*PAD) words.
+int smi_pack_arms(sm_ctx* ctx, const uint16_t* d_arms, int H, int W, int PAD, uint32_t* d_out);
+static inline int smi_arm_pad(int D) { return (D + 31) / 32 * 32; }
 // the two exp lookup tables of the fused AD-Census kernel (see cost.cu)
 int smi_exp_tables(sm_ctx* ctx, float trunc, float lamAD, float lamCen, int codeLen, const float** d_tabAD,
                    const float** d_tabCen);
@@ -93,7 +96,7 @@ int smi_cost_adcensus_packed(sm_ctx* ctx, const uint32_t* d_pixL, const uint32_t
                              const uint64_t* d_cenR, int H, int W, int D, int func, float adTrunc, float lamAD,
                              float lamCen, int LOR, float* d_vol);
 int smi_cbca_packed(sm_ctx* ctx, float* d_vol, float* d_tmp, const uint32_t* d_armL, const uint32_t* d_armR, int H,
-                    int W, int D, int iters, int view, int Lmax);
+                    int W, int D, int iters, int view, int Lmax, int PAD);
 int smi_arms_packed(sm_ctx* ctx, const uint32_t* d_pix, int H, int W, int L, int L_out, int tau, int tau_out, int minL,
                     uint16_t* d_arms);
 int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D);

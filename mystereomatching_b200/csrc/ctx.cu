@@ -197,18 +197,27 @@ int smi_pack_bgr(sm_ctx* ctx, const uint8_t* d_bgr, long long npix, uint32_t* d_
   return SM_OK;
 }
 
-__global__ void k_pack_arms(const uint16_t* __restrict__ arms, long long npix, uint32_t* __restrict__ out) {
+__global__ void k_pack_arms(const uint16_t* __restrict__ arms, int H, int W, int PAD, uint32_t* __restrict__ out) {
+  const int Wp = W + 2 * PAD;
+  const long long n = (long long)H * Wp;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < npix; i += stride) {
-    const uint16_t* a = arms + 5 * i;
-    out[i] = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16) | ((uint32_t)a[3] << 24);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int v = (int)(i / Wp), u = (int)(i - (long long)v * Wp) - PAD;
+    uint32_t wh = 0, wv = 0;
+    if (u >= 0 && u < W) {
+      const uint16_t* a = arms + 5 * ((size_t)v * W + u);
+      wh = (uint32_t)a[0] | ((uint32_t)a[1] << 16);
+      wv = (uint32_t)a[2] | ((uint32_t)a[3] << 16);
+    }
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(wh, wv);
   }
 }
 
-int smi_pack_arms(sm_ctx* ctx, const uint16_t* d_arms, long long npix, uint32_t* d_out) {
-  int grid = min(sm_div_up(npix, 256), ctx->num_sms * 8);
-  SM_LAUNCH(ctx, k_pack_arms, grid, 256, 0, d_arms, npix, d_out);
+int smi_pack_arms(sm_ctx* ctx, const uint16_t* d_arms, int H, int W, int PAD, uint32_t* d_out) {
+  const long long n = (long long)H * (W + 2 * PAD);
+  int grid = min(sm_div_up(n, 256), ctx->num_sms * 8);
+  SM_LAUNCH(ctx, k_pack_arms, grid, 256, 0, d_arms, H, W, PAD, d_out);
   return SM_OK;
 }
 

@@ -73,7 +73,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->bgr[i], npix * 3);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->gray[i], npix);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->pix[i], npix * 4);
-    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], npix * 4);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], (size_t)H * (W + 2 * smi_arm_pad(pl->D)) * 8);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->cen[i], npix * 8 * nw);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->arms[i], npix * 5 * 2);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->disp[i], npix * 2);
@@ -164,7 +164,7 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
     for (int i = 0; i < 2; i++) {
       SM_TRY(smi_arms_packed(c, pl->pix[i], H, W, P.cbca_crossL, P.cbca_crossL_out, P.cbca_cTresh, P.cbca_cTresh_out,
                              P.cbca_minArmL, pl->arms[i]));
-      SM_TRY(smi_pack_arms(c, pl->arms[i], npix, pl->armpk[i]));
+      SM_TRY(smi_pack_arms(c, pl->arms[i], H, W, smi_arm_pad(D), pl->armpk[i]));
     }
     pl->have_arms = true;
     return SM_OK;
@@ -175,7 +175,7 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
     const int Lmax = max(1, max(P.cbca_crossL_out, P.cbca_minArmL));
     for (int i = 0; i < views; i++)
       SM_TRY(smi_cbca_packed(c, pl->vol[i], pl->vol[2], pl->armpk[0], pl->armpk[1], H, W, D, P.cbca_iterationNum, i,
-                             Lmax));
+                             Lmax, smi_arm_pad(D)));
   } else if (P.aggregation == 2) {
     PL_MARK(3);
     SM_TRY(smi_nl(c, pl->bgr[0], pl->vol[0], pl->nlwork, H, W, D));
