@@ -1,8 +1,480 @@
-// K8 + K9 placeholder, replaced by the real implementation in this round.
+// K8 + K9: non-local (minimum-spanning-tree) cost aggregation.
+//
+//   qx_mst_kruskals_image::mst     NL/qx_mst_kruskals_image.cpp:167-277   guidance median, edges, Kruskal, BFS rooting
+//   qx_tree_filter::update_table   NL/qx_tree_filter.cpp:21-25            w[i] = exp(-i / (255 * max(0.01, sigma)))
+//   qx_tree_filter::filter         NL/qx_tree_filter.cpp:61-117           leaf-to-root then root-to-leaf recurrences, f64
+//   NLCCA::aggreCV                 NL/NLCCA.cpp:27-95                     f32 -> f64, sigma = 0.1, filter, f64 -> f32
+//   StereoMatching::NL             stereoMatching.cpp:4892-4917           aggreCV(vm[0]), aggreCV(ones), divide
+//
+// Tree identity.  The reference runs Kruskal over a STABLE counting sort of the 4-connected grid edges, i.e. it
+// builds the unique minimum spanning tree under the strict total order key(e) = (weight(e), index(e)) with the
+// reference's edge enumeration (all horizontal edges row-major, then all vertical edges column-major,
+// NL/qx_mst_kruskals_image.cpp:46-69).  Any algorithm that uses the same total order yields the same tree; here it
+// is Boruvka: every component picks its minimum outgoing edge by 64-bit atomicMin on that key, components hook
+// (mutual picks keep the smaller label as the root), labels are flattened by pointer jumping; <= log2(N) rounds.
+// The tree is then rooted at pixel 0 (NL/qx_mst_kruskals_image.cpp:233) by a level-synchronous BFS inside ONE
+// cooperative kernel (grid barrier per level), which also yields the per-level node lists the filter needs.
+// A node's children are kept in increasing key order, which is the order Kruskal appended them to the adjacency
+// list and therefore the order in which the reference's leaf-to-root pass adds them (bit-identical f64 sums).
+//
+// Filter.  Level-synchronous, one cooperative persistent kernel: leaf-to-root over the levels deepest-1 .. 0
+// (A[p] = cost[p] + sum_children w(c) * A[c], children already final), then root-to-leaf over levels 1 .. deepest
+// (out[v] = w * (out[parent] - w * A[v]) + A[v], written over A[v], which no one needs any more).  Threads run
+// along (node, d) with d fastest, so every access is a coalesced run of D doubles.  The all-ones volume of
+// StereoMatching::NL has identical planes, so its filter result is ONE extra plane (index D) carried through the
+// same two sweeps; the division happens in the final conversion.  Time is bound by tree depth x grid-barrier
+// latency, not by bandwidth; the barrier is a monotone atomic counter.
+#include <math.h>
+
 #include "common.cuh"
-extern "C" int sm_mst_build(sm_ctx*, const uint8_t*, int, int, int, int32_t*, uint8_t*, int32_t*, int32_t*) {
-  sm_set_error("sm_mst_build: not built yet"); return SM_ERR_UNSUPPORTED; }
-extern "C" int sm_tree_filter(sm_ctx*, float*, double*, int, int, int, const int32_t*, const uint8_t*, const int32_t*,
-                              const int32_t*, double) { sm_set_error("sm_tree_filter: not built yet"); return SM_ERR_UNSUPPORTED; }
-extern "C" int sm_nl(sm_ctx*, const uint8_t*, float*, int, int, int) { sm_set_error("sm_nl: not built yet"); return SM_ERR_UNSUPPORTED; }
-int smi_nl(sm_ctx*, const uint8_t*, float*, double*, int, int, int) { sm_set_error("nl: not built yet"); return SM_ERR_UNSUPPORTED; }
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ void edge_ends(int e, int H, int W, int& a, int& b) {
+  const int nh = H * (W - 1);
+  if (e < nh) {
+    const int y = e / (W - 1), x = e - y * (W - 1);
+    a = y * W + x; b = a + 1;
+  } else {
+    const int r = e - nh, x = r / (H - 1), y = r - x * (H - 1);
+    a = y * W + x; b = a + W;
+  }
+}
+// index of the edge between pixel p and its right (dir 0) or lower (dir 1) neighbour
+__device__ __forceinline__ int edge_index(int y, int x, int dir, int H, int W) {
+  return dir == 0 ? y * (W - 1) + x : H * (W - 1) + x * (H - 1) + y;
+}
+
+__global__ void k_edge_weights(const uint8_t* __restrict__ img, int H, int W, int cn, uint8_t* __restrict__ ew) {
+  const int E = H * (W - 1) + W * (H - 1);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    int a, b;
+    edge_ends(e, H, W, a, b);
+    int m = 0;
+    for (int c = 0; c < cn; c++) m = max(m, abs((int)img[(size_t)a * cn + c] - (int)img[(size_t)b * cn + c]));
+    ew[e] = (uint8_t)m;
+  }
+}
+
+// ------------------------------------------------------------------ Boruvka
+#define KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+__global__ void k_bor_init(int N, int E, int* comp, int* link, unsigned long long* best, uint8_t* inMST) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) { comp[i] = i; link[i] = i; best[i] = KEY_NONE; }
+  if (i < E) inMST[i] = 0;
+}
+
+__global__ void k_bor_find(const uint8_t* __restrict__ ew, const int* __restrict__ comp, int H, int W,
+                           unsigned long long* best) {
+  const int E = H * (W - 1) + W * (H - 1);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    int a, b;
+    edge_ends(e, H, W, a, b);
+    const int ca = comp[a], cb = comp[b];
+    if (ca == cb) continue;
+    const unsigned long long key = ((unsigned long long)ew[e] << 32) | (unsigned)e;
+    if (key < best[ca]) atomicMin(&best[ca], key);   // plain pre-check keeps late rounds off the hot addresses
+    if (key < best[cb]) atomicMin(&best[cb], key);
+  }
+}
+
+__global__ void k_bor_hook(int N, int H, int W, const int* __restrict__ comp, const unsigned long long* __restrict__ best,
+                           int* __restrict__ link, uint8_t* __restrict__ inMST, int* __restrict__ nHooks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N || comp[c] != c) return;
+  const unsigned long long k = best[c];
+  if (k == KEY_NONE) return;
+  const int e = (int)(k & 0xFFFFFFFFu);
+  int a, b;
+  edge_ends(e, H, W, a, b);
+  const int ca = comp[a], other = ca == c ? comp[b] : ca;
+  inMST[e] = 1;
+  const bool mutual = best[other] == k;
+  if (!mutual || c > other) link[c] = other;   // of a mutual pair the smaller label stays the root
+  atomicAdd(nHooks, 1);
+}
+
+__global__ void k_bor_jump(int N, int* __restrict__ link, int* __restrict__ changed) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const int p = link[c];
+  const int g = link[p];
+  if (g != p) { link[c] = g; *changed = 1; }
+}
+
+__global__ void k_bor_relabel(int N, int* __restrict__ comp, int* __restrict__ link, unsigned long long* __restrict__ best) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  comp[v] = link[comp[v]];
+  best[v] = KEY_NONE;
+}
+
+__global__ void k_bor_fixlink(int N, int* __restrict__ link) {
+  // after relabelling, comp holds roots only: start the next round from the identity again
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) link[v] = v;
+}
+
+// ------------------------------------------------------------------ adjacency (<= 4 tree neighbours, key order)
+struct nl_adj {   // per node
+  int nbr[4];
+};
+
+__global__ void k_tree_adj(int H, int W, const uint8_t* __restrict__ ew, const uint8_t* __restrict__ inMST,
+                           int* __restrict__ nbr /*[N][4]*/, uint8_t* __restrict__ nbw /*[N][4]*/,
+                           uint8_t* __restrict__ deg) {
+  const int N = H * W;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  const int y = v / W, x = v - y * W;
+  unsigned long long key[4];
+  int to[4], n = 0;
+  auto consider = [&](int e, int other) {
+    if (inMST[e]) { key[n] = ((unsigned long long)ew[e] << 32) | (unsigned)e; to[n] = other; n++; }
+  };
+  if (x > 0) consider(edge_index(y, x - 1, 0, H, W), v - 1);
+  if (x < W - 1) consider(edge_index(y, x, 0, H, W), v + 1);
+  if (y > 0) consider(edge_index(y - 1, x, 1, H, W), v - W);
+  if (y < H - 1) consider(edge_index(y, x, 1, H, W), v + W);
+  // insertion sort by key (<= 4 entries)
+  for (int i = 1; i < n; i++) {
+    const unsigned long long k = key[i];
+    const int t = to[i];
+    int j = i - 1;
+    while (j >= 0 && key[j] > k) { key[j + 1] = key[j]; to[j + 1] = to[j]; j--; }
+    key[j + 1] = k; to[j + 1] = t;
+  }
+  for (int i = 0; i < 4; i++) {
+    nbr[(size_t)v * 4 + i] = i < n ? to[i] : -1;
+    nbw[(size_t)v * 4 + i] = i < n ? (uint8_t)(key[i] >> 32) : 0;
+  }
+  deg[v] = (uint8_t)n;
+}
+
+// ------------------------------------------------------------------ grid barrier (cooperative launch only)
+struct nl_sync {
+  unsigned int count;   // monotone arrival counter
+  int tail;             // BFS: end of the order array
+  int nlevels;          // BFS result: number of levels
+  int pad;
+};
+
+__device__ __forceinline__ void grid_barrier(nl_sync* s, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    epoch++;
+    const unsigned int target = epoch * gridDim.x;
+    atomicAdd(&s->count, 1u);
+    while (*(volatile unsigned int*)&s->count < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// BFS from pixel 0 over the tree adjacency: parent, depth (rank), weight of the edge to the parent, the node list
+// grouped by level (order) and the level boundaries (level_start[l] .. level_start[l+1]).
+__global__ void __launch_bounds__(256)
+    k_tree_bfs(int N, const int* __restrict__ nbr, const uint8_t* __restrict__ nbw, const uint8_t* __restrict__ deg,
+               int* __restrict__ parent, uint8_t* __restrict__ wpar, int* __restrict__ rank, int* __restrict__ order,
+               int* __restrict__ level_start, nl_sync* s) {
+  unsigned int epoch = 0;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (tid == 0) {
+    parent[0] = 0; wpar[0] = 0; rank[0] = 0; order[0] = 0; level_start[0] = 0;
+    s->tail = 1;
+  }
+  grid_barrier(s, epoch);
+  int head = 0, tail = 1, level = 0;
+  while (head < tail) {
+    for (int i = head + tid; i < tail; i += nth) {
+      const int v = order[i], p = parent[v], n = deg[v];
+      for (int k = 0; k < n; k++) {
+        const int c = nbr[(size_t)v * 4 + k];
+        if (c == p) continue;   // the root's parent is itself and never appears among its neighbours
+        parent[c] = v;
+        rank[c] = level + 1;
+        wpar[c] = nbw[(size_t)v * 4 + k];
+        order[atomicAdd(&s->tail, 1)] = c;
+      }
+    }
+    grid_barrier(s, epoch);               // all appends of this level are done
+    const int ntail = *(volatile int*)&s->tail;
+    grid_barrier(s, epoch);               // everyone has read the tail before the next level appends
+    head = tail; tail = ntail; level++;
+    if (tid == 0) level_start[level] = head;
+  }
+  if (tid == 0) { s->nlevels = level; level_start[level] = head; }
+}
+
+// children (in key order) from parent / weight arrays alone -- lets sm_tree_filter accept any rooted tree
+__global__ void k_children_from_parent(int H, int W, const int* __restrict__ parent, const uint8_t* __restrict__ wpar,
+                                       int* __restrict__ child /*[N][4]*/, uint8_t* __restrict__ nchild) {
+  const int N = H * W;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  const int y = v / W, x = v - y * W;
+  unsigned long long key[4];
+  int to[4], n = 0;
+  auto consider = [&](int c, int e) {
+    if (c != v && parent[c] == v && c != parent[v]) { key[n] = ((unsigned long long)wpar[c] << 32) | (unsigned)e; to[n] = c; n++; }
+  };
+  if (x > 0) consider(v - 1, edge_index(y, x - 1, 0, H, W));
+  if (x < W - 1) consider(v + 1, edge_index(y, x, 0, H, W));
+  if (y > 0) consider(v - W, edge_index(y - 1, x, 1, H, W));
+  if (y < H - 1) consider(v + W, edge_index(y, x, 1, H, W));
+  for (int i = 1; i < n; i++) {
+    const unsigned long long k = key[i];
+    const int t = to[i];
+    int j = i - 1;
+    while (j >= 0 && key[j] > k) { key[j + 1] = key[j]; to[j + 1] = to[j]; j--; }
+    key[j + 1] = k; to[j + 1] = t;
+  }
+  for (int i = 0; i < 4; i++) child[(size_t)v * 4 + i] = i < n ? to[i] : -1;
+  nchild[v] = (uint8_t)n;
+}
+
+__global__ void k_level_bounds(int N, const int* __restrict__ rank, const int* __restrict__ order,
+                               int* __restrict__ level_start, nl_sync* s) {
+  // order is grouped by rank: level l starts where the rank changes to l
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int r = rank[order[i]];
+    if (i == 0 || rank[order[i - 1]] != r) level_start[r] = i;
+    if (i == N - 1) { level_start[r + 1] = N; s->nlevels = r + 1; }
+  }
+}
+
+// ------------------------------------------------------------------ tree filter
+// A: [N][Dp] doubles (Dp = D, or D+1 with the all-ones plane at index D).
+__global__ void k_tf_load(const float* __restrict__ vol, double* __restrict__ A, size_t N, int D, int Dp) {
+  const size_t n = N * Dp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i / Dp;
+    const int d = (int)(i - v * Dp);
+    A[i] = d < D ? (double)vol[v * D + d] : 1.0;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+    k_tf_sweeps(double* __restrict__ A, int Dp, const int* __restrict__ parent, const uint8_t* __restrict__ wpar,
+                const int* __restrict__ child, const uint8_t* __restrict__ nchild, const int* __restrict__ order,
+                const int* __restrict__ level_start, const double* __restrict__ table, nl_sync* s) {
+  __shared__ double tab[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = table[i];
+  __syncthreads();
+  unsigned int epoch = 0;
+  const int nlevels = s->nlevels;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  // leaf to root: backup[p] += sum over children (adjacency order) of w(c) * backup[c]
+  for (int l = nlevels - 2; l >= 0; l--) {
+    const int lo = level_start[l], cnt = level_start[l + 1] - lo;
+    for (long long t = tid; t < (long long)cnt * Dp; t += nth) {
+      const int i = (int)(t / Dp), d = (int)(t - (long long)i * Dp);
+      const int v = order[lo + i], nc = nchild[v];
+      if (nc == 0) continue;
+      double acc = A[(size_t)v * Dp + d];
+      for (int k = 0; k < nc; k++) {
+        const int c = child[(size_t)v * 4 + k];
+        acc += A[(size_t)c * Dp + d] * tab[wpar[c]];
+      }
+      A[(size_t)v * Dp + d] = acc;
+    }
+    grid_barrier(s, epoch);
+  }
+  // root to leaf: cost[i] = w * (cost[parent] - w * backup[i]) + backup[i]   (the root keeps backup)
+  for (int l = 1; l < nlevels; l++) {
+    const int lo = level_start[l], cnt = level_start[l + 1] - lo;
+    for (long long t = tid; t < (long long)cnt * Dp; t += nth) {
+      const int i = (int)(t / Dp), d = (int)(t - (long long)i * Dp);
+      const int v = order[lo + i];
+      const double w = tab[wpar[v]];
+      const double b = A[(size_t)v * Dp + d];
+      A[(size_t)v * Dp + d] = w * (A[(size_t)parent[v] * Dp + d] - w * b) + b;
+    }
+    grid_barrier(s, epoch);
+  }
+}
+
+__global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp) {
+  const size_t n = N * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i / D;
+    const int d = (int)(i - v * D);
+    const float x = (float)A[v * Dp + d];                     // NLCCA::aggreCV: (float)nlcP[d]
+    vol[i] = Dp > D ? x / (float)A[v * Dp + D] : x;           // StereoMatching::NL: vm[0] /= wetNL
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct nl_tree {   // device buffers of one rooted tree (owned by the ctx scratch slots)
+  int *parent, *rank, *order, *level_start, *child;
+  uint8_t *wpar, *nchild;
+  nl_sync* sync;
+};
+
+static int coop_launch(sm_ctx* ctx, const void* fn, int block, void** args) {
+  int perSM = 0;
+  SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, block, 0));
+  SM_CHECK_ARG(perSM >= 1);
+  const int grid = ctx->num_sms;   // one block per SM: the barrier scales with the block count
+  SM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(block), args, 0, ctx->stream));
+  ctx->launches++;
+  return SM_OK;
+}
+
+// MST + rooting.  img: [H][W][cn] u8 (already median-filtered).  Fills t (buffers must be allocated).
+static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn, nl_tree& t) {
+  const int N = H * W, E = H * (W - 1) + W * (H - 1);
+  void *p_ew, *p_in, *p_comp, *p_link, *p_best, *p_nbr, *p_nbw, *p_deg, *p_cnt;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_MISC0, (size_t)(E > 0 ? E : 1), &p_ew));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_MISC1, (size_t)(E > 0 ? E : 1), &p_in));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_MISC2, (size_t)N * 8, &p_comp));   // comp | link
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_MISC3, (size_t)N * 8, &p_best));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_MISC4, (size_t)N * 16 + (size_t)N * 4 + N, &p_nbr));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_MISC5, 256, &p_cnt));
+  uint8_t *ew = (uint8_t*)p_ew, *inMST = (uint8_t*)p_in;
+  int *comp = (int*)p_comp, *link = comp + N;
+  unsigned long long* best = (unsigned long long*)p_best;
+  int* nbr = (int*)p_nbr;
+  p_nbw = (uint8_t*)p_nbr + (size_t)N * 16;
+  p_deg = (uint8_t*)p_nbw + (size_t)N * 4;
+  uint8_t *nbw = (uint8_t*)p_nbw, *deg = (uint8_t*)p_deg;
+  int* cnt = (int*)p_cnt;   // [0] hooks, [1] changed
+
+  const int TB = 256, gN = sm_div_up(N, TB), gE = max(1, min(sm_div_up(E, TB), ctx->num_sms * 16));
+  if (E > 0) SM_LAUNCH(ctx, k_edge_weights, gE, TB, 0, d_img, H, W, cn, ew);
+  SM_LAUNCH(ctx, k_bor_init, sm_div_up(max(N, E), TB), TB, 0, N, E, comp, link, best, inMST);
+  for (int round = 0; E > 0 && round < 40; round++) {
+    SM_CUDA(cudaMemsetAsync(cnt, 0, 8, ctx->stream));
+    SM_LAUNCH(ctx, k_bor_find, gE, TB, 0, ew, comp, H, W, best);
+    SM_LAUNCH(ctx, k_bor_hook, gN, TB, 0, N, H, W, comp, best, link, inMST, cnt);
+    int h_cnt[2] = {0, 0};
+    SM_CUDA(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_cnt[0] == 0) break;   // no component has an outgoing edge: the forest is the spanning tree
+    for (int it = 0; it < 40; it++) {   // pointer jumping until every label points at its root
+      SM_CUDA(cudaMemsetAsync(cnt + 1, 0, 4, ctx->stream));
+      SM_LAUNCH(ctx, k_bor_jump, gN, TB, 0, N, link, cnt + 1);
+      SM_CUDA(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      SM_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (h_cnt[1] == 0) break;
+    }
+    SM_LAUNCH(ctx, k_bor_relabel, gN, TB, 0, N, comp, link, best);
+    SM_LAUNCH(ctx, k_bor_fixlink, gN, TB, 0, N, link);
+  }
+  SM_LAUNCH(ctx, k_tree_adj, gN, TB, 0, H, W, ew, inMST, nbr, nbw, deg);
+  SM_CUDA(cudaMemsetAsync(t.sync, 0, sizeof(nl_sync), ctx->stream));
+  {
+    void* args[] = {(void*)&N, (void*)&nbr, (void*)&nbw, (void*)&deg, (void*)&t.parent, (void*)&t.wpar, (void*)&t.rank,
+                    (void*)&t.order, (void*)&t.level_start, (void*)&t.sync};
+    SM_TRY(coop_launch(ctx, (const void*)k_tree_bfs, 256, args));
+  }
+  return SM_OK;
+}
+
+// scratch layout of the tree arrays the filter derives (children, levels, barrier state)
+static int nl_tree_scratch(sm_ctx* ctx, int N, nl_tree& t, bool own_arrays) {
+  // SM_SCR_ARM0: child[N][4] | level_start[N+2] ; SM_SCR_ARM1: nchild[N] | sync | (parent | rank | order | wpar)
+  void *p0, *p1;
+  const size_t s1 = (size_t)N + 64 + (own_arrays ? (size_t)N * 13 + 64 : 0);
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_ARM0, (size_t)N * 16 + (size_t)(N + 2) * 4, &p0));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_ARM1, s1, &p1));
+  t.child = (int*)p0;
+  t.level_start = t.child + (size_t)N * 4;
+  uint8_t* q = (uint8_t*)p1;
+  t.sync = (nl_sync*)q; q += 64;
+  if (own_arrays) {
+    t.parent = (int*)q; q += (size_t)N * 4;
+    t.rank = (int*)q; q += (size_t)N * 4;
+    t.order = (int*)q; q += (size_t)N * 4;
+    t.wpar = q; q += (size_t)N;
+    q += (64 - ((size_t)N & 63)) & 63;
+  }
+  t.nchild = q;
+  return SM_OK;
+}
+
+static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D, bool ones_plane, const nl_tree& t,
+                     double sigma) {
+  const size_t N = (size_t)H * W;
+  const int Dp = ones_plane ? D + 1 : D;
+  // weight table, built on the host with the same libm call as update_table
+  double h_tab[256];
+  sigma = fmax(0.01, sigma);
+  for (int i = 0; i <= 255; i++) h_tab[i] = exp(-double(i) / (255 * sigma));
+  void* p_tab;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_TAB, 8192, &p_tab));   // [0, 4096): exp tables of the cost kernel
+  double* d_tab = (double*)((uint8_t*)p_tab + 4096);
+  SM_CUDA(cudaMemcpyAsync(d_tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, ctx->stream));
+  SM_CUDA(cudaStreamSynchronize(ctx->stream));   // h_tab is a stack array
+  const int TB = 256, g = (int)min((size_t)ctx->num_sms * 16, (N * Dp + TB - 1) / TB);
+  SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp);
+  SM_CUDA(cudaMemsetAsync(&t.sync->count, 0, sizeof(unsigned int), ctx->stream));
+  {
+    int dp = Dp;
+    void* args[] = {(void*)&d_A, (void*)&dp, (void*)&t.parent, (void*)&t.wpar, (void*)&t.child, (void*)&t.nchild,
+                    (void*)&t.order, (void*)&t.level_start, (void*)&d_tab, (void*)&t.sync};
+    SM_TRY(coop_launch(ctx, (const void*)k_tf_sweeps, 512, args));
+  }
+  SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp);
+  return SM_OK;
+}
+
+extern "C" int sm_mst_build(sm_ctx* ctx, const uint8_t* d_bgr, int H, int W, int cn, int32_t* d_parent,
+                            uint8_t* d_weight, int32_t* d_rank, int32_t* d_order) {
+  SM_CHECK_ARG(ctx && d_bgr && d_parent && d_weight && d_rank && H > 0 && W > 0 && cn >= 1 && cn <= 4);
+  SM_CHECK_ARG((long long)H * W < (1ll << 30));
+  const int N = H * W;
+  SM_CUDA(cudaSetDevice(ctx->device));
+  // 1. ctmf(r = 1) on the guidance (NL/qx_mst_kruskals_image.cpp:174)
+  void* p_img;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_IMG0, (size_t)N * cn, &p_img));
+  SM_TRY(sm_median_u8(ctx, d_bgr, (uint8_t*)p_img, H, W, 1, cn));
+  nl_tree t;
+  SM_TRY(nl_tree_scratch(ctx, N, t, d_order == nullptr));
+  t.parent = d_parent; t.wpar = d_weight; t.rank = d_rank;
+  if (d_order) t.order = d_order;
+  SM_TRY(nl_build_tree(ctx, (const uint8_t*)p_img, H, W, cn, t));
+  return SM_OK;
+}
+
+extern "C" int sm_tree_filter(sm_ctx* ctx, float* d_vol, double* d_work, int H, int W, int D, const int32_t* d_parent,
+                              const uint8_t* d_weight, const int32_t* d_rank, const int32_t* d_order, double sigma) {
+  SM_CHECK_ARG(ctx && d_vol && d_work && d_parent && d_weight && d_rank && d_order && H > 0 && W > 0 && D > 0);
+  const int N = H * W;
+  SM_CUDA(cudaSetDevice(ctx->device));
+  nl_tree t;
+  SM_TRY(nl_tree_scratch(ctx, N, t, false));
+  t.parent = (int*)d_parent; t.wpar = (uint8_t*)d_weight; t.rank = (int*)d_rank; t.order = (int*)d_order;
+  const int TB = 256;
+  SM_CUDA(cudaMemsetAsync(t.sync, 0, sizeof(nl_sync), ctx->stream));
+  SM_LAUNCH(ctx, k_children_from_parent, sm_div_up(N, TB), TB, 0, H, W, t.parent, t.wpar, t.child, t.nchild);
+  SM_LAUNCH(ctx, k_level_bounds, min(sm_div_up(N, TB), ctx->num_sms * 8), TB, 0, N, t.rank, t.order, t.level_start,
+            t.sync);
+  return nl_filter(ctx, d_vol, d_work, H, W, D, false, t, sigma);
+}
+
+int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D) {
+  // d_work: H*W*(D+1) doubles
+  const int N = H * W;
+  void* p_img;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_IMG0, (size_t)N * 3, &p_img));
+  SM_TRY(sm_median_u8(ctx, d_bgrL, (uint8_t*)p_img, H, W, 1, 3));
+  nl_tree t;
+  SM_TRY(nl_tree_scratch(ctx, N, t, true));
+  SM_TRY(nl_build_tree(ctx, (const uint8_t*)p_img, H, W, 3, t));
+  const int TB = 256;
+  SM_LAUNCH(ctx, k_children_from_parent, sm_div_up(N, TB), TB, 0, H, W, t.parent, t.wpar, t.child, t.nchild);
+  return nl_filter(ctx, d_vol, d_work, H, W, D, true, t, 0.1);   // sigma: NL/NLCCA.cpp:33
+}
+
+extern "C" int sm_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, int H, int W, int D) {
+  SM_CHECK_ARG(ctx && d_bgrL && d_vol && H > 0 && W > 0 && D > 0);
+  SM_CHECK_ARG((long long)H * W < (1ll << 30));
+  SM_CUDA(cudaSetDevice(ctx->device));
+  void* work = nullptr;
+  SM_TRY(sm_dev_alloc(ctx, &work, (size_t)H * W * (D + 1) * sizeof(double)));
+  int rc = smi_nl(ctx, d_bgrL, d_vol, (double*)work, H, W, D);
+  int rc2 = sm_dev_free(ctx, work);   // drains the stream first
+  return rc != SM_OK ? rc : rc2;
+}

@@ -80,7 +80,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   }
   for (int i = 0; i < 3 && rc == SM_OK; i++) rc = pl_alloc(ctx, (void**)&pl->vol[i], nvol * sizeof(float));
   if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->dtmp, npix * 2);
-  if (rc == SM_OK && p->aggregation == 2) rc = pl_alloc(ctx, (void**)&pl->nlwork, nvol * sizeof(double));
+  if (rc == SM_OK && p->aggregation == 2) rc = pl_alloc(ctx, (void**)&pl->nlwork, npix * (size_t)(pl->D + 1) * sizeof(double));
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_in, npix * 8) != cudaSuccess) rc = SM_ERR_NOMEM;
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_out, npix * 4) != cudaSuccess) rc = SM_ERR_NOMEM;
   if (rc != SM_OK) { sm_pipeline_destroy(pl); return rc; }

@@ -235,3 +235,99 @@ def test_pipeline_region_of_validity_errors(ctx):
         capi.Pipeline(ctx, 10, 10, capi.default_params(600))       # D > 512 (CV_CN_MAX)
     with pytest.raises(capi.SmError):
         ctx.sgm_path(ctx.dev(np.zeros((2, 2, 2), np.float32)), ctx.dev(np.zeros((2, 2, 3), np.uint8)), 9)
+
+
+# ---------------------------------------------------------------- NL: MST + tree filter
+def _nl_images():
+    rng = np.random.default_rng(5)
+    noisy = rng.integers(0, 256, (45, 61, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:40, 0:52]
+    smooth = np.stack([(xx * 3 + yy) // 4, (xx + yy * 2) // 5, (xx * yy) // 40], -1).astype(np.uint8)
+    flat = np.full((17, 23, 3), 9, np.uint8)                       # every weight 0: pure index tie-breaking
+    tex = _pair(70, 96, 8, "texture_warped", seed=2)["bgrL"]
+    return {"noisy": noisy, "smooth": smooth, "flat": flat, "tex": tex, "row": noisy[:1].copy(),
+            "col": noisy[:, :1].copy(), "one": noisy[:1, :1].copy()}
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name", ["noisy", "smooth", "flat", "tex", "row", "col", "one"])
+def test_mst_identical_to_reference_tree(ctx, name):
+    img = _nl_images()[name]
+    H, W = img.shape[:2]
+    t = ctx.mst_build(ctx.dev(img))
+    ref = po.mst(img)
+    parent, weight, rank, order = (t[k].cpu().numpy() for k in ("parent", "weight", "rank", "order"))
+    assert np.array_equal(parent[1:], ref["parent"][1:]) and parent[0] == 0     # edge-for-edge the same tree
+    assert np.array_equal(weight[1:], ref["weight"][1:])
+    assert np.array_equal(rank, ref["rank"])
+    assert np.array_equal(np.sort(order), np.arange(H * W))                     # a permutation ...
+    assert np.all(np.diff(rank[order]) >= 0)                                    # ... grouped by depth
+    assert np.array_equal(ctx.median_u8(ctx.dev(img), 1).cpu().numpy(), po.ctmf(img, 1))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name,D", [("noisy", 6), ("smooth", 5), ("flat", 3), ("tex", 33)])
+def test_tree_filter_bit_exact(ctx, name, D):
+    img = _nl_images()[name]
+    H, W = img.shape[:2]
+    vol = np.random.default_rng(3).random((H, W, D)).astype(np.float32)
+    tree = ctx.mst_build(ctx.dev(img))
+    for sigma in (0.1, 0.05):
+        got = ctx.tree_filter(ctx.dev(vol.copy()), tree, sigma).cpu().numpy()
+        t = po.mst(img)
+        table = np.empty(256, np.float64)
+        po.lib().orc_tree_table(sigma, table)
+        cost = vol.astype(np.float64).copy()
+        tmp = np.empty_like(cost)
+        po.lib().orc_tree_filter(cost, tmp, H * W, D, t["parent"], t["weight"], t["nr_child"], t["children"],
+                                 t["order"], table)
+        assert _bits_equal(got, cost.astype(np.float32))     # same f64 operation order -> identical after the cast
+
+
+@pytest.mark.timeout(120)
+def test_tree_filter_matches_reference_golden(ctx, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "nl_ref.npz"))       # outputs of the reference's own qx_tree_filter
+    img, vol = g["mst_noisy_img"], g["tf_vol"]
+    tree = ctx.mst_build(ctx.dev(img))
+    for key, sigma in (("tf_out_sigma0p1", 0.1), ("tf_out_sigma0p05", 0.05)):
+        got = ctx.tree_filter(ctx.dev(vol.copy()), tree, sigma).cpu().numpy()
+        assert _bits_equal(got, g[key].astype(np.float32))
+    for k in ("parent", "weight", "rank"):
+        assert np.array_equal(tree[k].cpu().numpy()[1:], g["mst_noisy_" + k][1:])
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape", [(48, 64, 16), (60, 90, 33)])
+def test_nl_aggregation_matches_oracle(ctx, shape):
+    H, W, D = shape
+    p = _pair(H, W, D, "texture_warped", seed=8)
+    vol = po.adcensus_vol(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D, 0)
+    ref, rdisp = po.nl(p["bgrL"], vol)
+    got = ctx.nl(ctx.dev(p["bgrL"]), ctx.dev(vol.copy()))
+    assert _bits_equal(got.cpu().numpy(), ref)
+    assert np.array_equal(ctx.wta(got).cpu().numpy(), rdisp)
+
+
+@pytest.mark.timeout(180)
+def test_pipeline_nl_matches_oracle_composition(ctx):
+    """aggregation = "NL": StereoMatching::NL aggregates vm[0] only; SGM/WTA/LRC/refine follow as usual."""
+    H, W, D = 64, 96, 32
+    p = _pair(H, W, D, "texture_warped", seed=13)
+    params = capi.default_params(D - 1, sgm_paths=4, aggregation=2)
+    pl = capi.Pipeline(ctx, H, W, params)
+    got = pl.run(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"])
+    pl.close()
+    v0 = po.adcensus_vol(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D, 0)
+    v1 = po.adcensus_vol(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D, 1)
+    v0, _ = po.nl(p["bgrL"], v0)
+    d0 = po.wta(po.sgm(v0, p["bgrL"], 4))
+    d1 = po.wta(po.sgm(v1, p["bgrR"], 4))
+    d = po.lrc_normal(d0, d1)
+    arms = po.arms(p["bgrL"])
+    for _ in range(2):
+        d = po.region_vote(d, arms, D)
+    for _ in range(2):
+        d = po.proper_ipol(d, p["bgrL"])
+    d = po.median3_i16(d)
+    assert (got == d).mean() >= 0.995
