@@ -38,12 +38,15 @@ WORKLOADS = {
     "c1": (450, 375, 64, 4, "random_dot"),
     "c2": (1280, 720, 128, 8, "texture_warped"),
     "c3": (1920, 1080, 256, 8, "texture_warped"),
+    "c4": (640, 480, 64, 4, "texture_warped"),       # NL non-local MST aggregation instead of CBCA
 }
+AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2}
 
 
 def workload_desc(name):
     W, H, D, P, kind = WORKLOADS[name]
-    return (f"{name}: {W}x{H} D={D} AD-Census(71-bit)+CBCA(2 it, intersected arms)+{P}-path SGM+WTA+LRC+"
+    agg = "CBCA(2 it, intersected arms)" if AGGREGATION[name] == 1 else "NL(MST tree filter, sigma 0.1, left view)"
+    return (f"{name}: {W}x{H} D={D} AD-Census(71-bit)+{agg}+{P}-path SGM+WTA+LRC+"
             f"regionVote x2+properIpol x2+median3, 2 views, fp32 volumes, synthetic {kind} pairs")
 
 
@@ -119,7 +122,7 @@ def run_oracle(pair, name, threads):
     from oracle import pyoracle as po
     W, H, D, P, kind = WORKLOADS[name]
     po.lib().orc_set_threads(threads)
-    op = po.default_params(D, paths=P)
+    op = po.default_params(D, paths=P, aggregation=AGGREGATION[name])
     t0 = time.perf_counter()
     _, _, _, ms = po.pipeline(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], op)
     return time.perf_counter() - t0, ms
@@ -183,9 +186,12 @@ def stage_bytes(name):
     W, H, D, P, kind = WORKLOADS[name]
     V = W * H * D
     b = 4
+    agg = {"bytes_per_launch": 2 * V * b, "launches": 8, "kernel": "k_cbca_pass"}
+    if AGGREGATION[name] == 2:   # k_nl = 4 volume passes; MST build + rooting + two tree sweeps
+        agg = {"bytes_per_launch": 4 * V * b, "launches": 1, "kernel": "nl (Boruvka MST + k_tree_bfs + k_tf_sweeps)"}
     return {
         "cost": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_cost<ADCENSUS>"},
-        "aggregation": {"bytes_per_launch": 2 * V * b, "launches": 8, "kernel": "k_cbca_pass"},
+        "aggregation": agg,
         "sgm": {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path"},
         "wta": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_wta"},
     }
@@ -213,7 +219,7 @@ def main_ours(args):
     name = args.workload
     W, H, D, P, kind = WORKLOADS[name]
     ctx = capi.Ctx(local)
-    params = capi.default_params(D - 1, sgm_paths=P)
+    params = capi.default_params(D - 1, sgm_paths=P, aggregation=AGGREGATION[name])
     pl = capi.Pipeline(ctx, H, W, params)
 
     # frames of this rank: frame i of the stream uses seed 1000+i, frame i -> rank i mod N

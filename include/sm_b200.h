@@ -164,6 +164,11 @@ int sm_mst_build(sm_ctx* ctx, const uint8_t* d_bgr, int H, int W, int cn, int32_
 int sm_tree_filter(sm_ctx* ctx, float* d_vol, double* d_work, int H, int W, int D,
                    const int32_t* d_parent, const uint8_t* d_weight, const int32_t* d_rank,
                    const int32_t* d_order, double sigma);
+/* qx_tree_filter::filter itself (NL/qx_tree_filter.cpp:61-117) on a float64
+ * volume [H*W][D], in place -- the entry point a qx_tree_filter drop-in binds
+ * (NL/qx_tree_filter.h:24: filter(double* cost, double* cost_backup, int nr_plane)). */
+int sm_tree_filter_f64(sm_ctx* ctx, double* d_cost, int H, int W, int D, const int32_t* d_parent,
+                       const uint8_t* d_weight, const int32_t* d_rank, const int32_t* d_order, double sigma);
 /* StereoMatching::NL (stereoMatching.cpp:4892-4917): aggreCV(vm[0]),
  * aggreCV(ones), divide.  In place on d_vol. */
 int sm_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, int H, int W, int D);
@@ -181,6 +186,10 @@ int sm_sgm_path(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, in
  * into d_sum (must not alias d_vol). */
 int sm_sgm(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int paths,
            int corDifThres, int reduCoeffi1, float* d_sum);
+
+/* gen_sgm_vm's inner statement `sum += Lr[num]` (stereoMatching.cpp:2051) for one
+ * materialised path volume: d_acc[i] = d_acc[i] + d_x[i]. */
+int sm_vol_accumulate(sm_ctx* ctx, float* d_acc, const float* d_x, size_t n);
 
 /* ---- disparity selection --------------------------------------------------- */
 /* gen_dispFromVm (stereoMatching.cpp:3928-3967), ChooseSmall = true. */

@@ -66,9 +66,11 @@ SIGNATURES = {
     "sm_median_u8": ([_P, _P, _P, _I, _I, _I, _I], _I),
     "sm_mst_build": ([_P, _P, _I, _I, _I, _P, _P, _P, _P], _I),
     "sm_tree_filter": ([_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _D], _I),
+    "sm_tree_filter_f64": ([_P, _P, _I, _I, _I, _P, _P, _P, _P, _D], _I),
     "sm_nl": ([_P, _P, _P, _I, _I, _I], _I),
     "sm_sgm_path": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_sgm": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "sm_vol_accumulate": ([_P, _P, _P, _Z], _I),
     "sm_wta": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_wta_co": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
     "sm_lrc": ([_P, _P, _P, _I, _I, _F], _I),
@@ -318,6 +320,17 @@ class Ctx:
         check(self.L.sm_tree_filter(self.h, _ptr(vol), _ptr(work), H, W, D, _ptr(tree["parent"]),
                                     _ptr(tree["weight"]), _ptr(tree["rank"]), _ptr(tree["order"]), sigma))
         return vol
+
+    def tree_filter_f64(self, cost, tree, H, W, sigma=0.1):
+        """In place on a float64 [H*W, D] tensor."""
+        D = cost.shape[-1]
+        check(self.L.sm_tree_filter_f64(self.h, _ptr(cost), H, W, D, _ptr(tree["parent"]), _ptr(tree["weight"]),
+                                        _ptr(tree["rank"]), _ptr(tree["order"]), sigma))
+        return cost
+
+    def vol_accumulate(self, acc, x):
+        check(self.L.sm_vol_accumulate(self.h, _ptr(acc), _ptr(x), acc.numel()))
+        return acc
 
     def nl(self, bgrL, vol):
         H, W, D = vol.shape

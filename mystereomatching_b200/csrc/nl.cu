@@ -394,6 +394,7 @@ static int nl_tree_scratch(sm_ctx* ctx, int N, nl_tree& t, bool own_arrays) {
   return SM_OK;
 }
 
+// d_vol == nullptr: d_A already holds the float64 cost [N][D] and receives the result (qx_tree_filter::filter).
 static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D, bool ones_plane, const nl_tree& t,
                      double sigma) {
   const size_t N = (size_t)H * W;
@@ -408,7 +409,7 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
   SM_CUDA(cudaMemcpyAsync(d_tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, ctx->stream));
   SM_CUDA(cudaStreamSynchronize(ctx->stream));   // h_tab is a stack array
   const int TB = 256, g = (int)min((size_t)ctx->num_sms * 16, (N * Dp + TB - 1) / TB);
-  SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp);
+  if (d_vol) SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp);
   SM_CUDA(cudaMemsetAsync(&t.sync->count, 0, sizeof(unsigned int), ctx->stream));
   {
     int dp = Dp;
@@ -416,7 +417,7 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
                     (void*)&t.order, (void*)&t.level_start, (void*)&d_tab, (void*)&t.sync};
     SM_TRY(coop_launch(ctx, (const void*)k_tf_sweeps, 512, args));
   }
-  SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp);
+  if (d_vol) SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp);
   return SM_OK;
 }
 
@@ -452,6 +453,22 @@ extern "C" int sm_tree_filter(sm_ctx* ctx, float* d_vol, double* d_work, int H, 
   SM_LAUNCH(ctx, k_level_bounds, min(sm_div_up(N, TB), ctx->num_sms * 8), TB, 0, N, t.rank, t.order, t.level_start,
             t.sync);
   return nl_filter(ctx, d_vol, d_work, H, W, D, false, t, sigma);
+}
+
+extern "C" int sm_tree_filter_f64(sm_ctx* ctx, double* d_cost, int H, int W, int D, const int32_t* d_parent,
+                                  const uint8_t* d_weight, const int32_t* d_rank, const int32_t* d_order, double sigma) {
+  SM_CHECK_ARG(ctx && d_cost && d_parent && d_weight && d_rank && d_order && H > 0 && W > 0 && D > 0);
+  const int N = H * W;
+  SM_CUDA(cudaSetDevice(ctx->device));
+  nl_tree t;
+  SM_TRY(nl_tree_scratch(ctx, N, t, false));
+  t.parent = (int*)d_parent; t.wpar = (uint8_t*)d_weight; t.rank = (int*)d_rank; t.order = (int*)d_order;
+  const int TB = 256;
+  SM_CUDA(cudaMemsetAsync(t.sync, 0, sizeof(nl_sync), ctx->stream));
+  SM_LAUNCH(ctx, k_children_from_parent, sm_div_up(N, TB), TB, 0, H, W, t.parent, t.wpar, t.child, t.nchild);
+  SM_LAUNCH(ctx, k_level_bounds, min(sm_div_up(N, TB), ctx->num_sms * 8), TB, 0, N, t.rank, t.order, t.level_start,
+            t.sync);
+  return nl_filter(ctx, nullptr, d_cost, H, W, D, false, t, sigma);
 }
 
 int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D) {

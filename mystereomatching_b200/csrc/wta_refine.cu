@@ -307,3 +307,16 @@ extern "C" int sm_cross_scale_1level(sm_ctx* ctx, float* d_vol, size_t n, float 
   SM_LAUNCH(ctx, k_scale, grid, 256, 0, d_vol, n, inv);
   return SM_OK;
 }
+
+// ------------------------------------------------------------------ gen_sgm_vm accumulation step
+__global__ void k_vol_accumulate(float* __restrict__ acc, const float* __restrict__ x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) acc[i] = acc[i] + x[i];   // sum += Lr[num]
+}
+
+extern "C" int sm_vol_accumulate(sm_ctx* ctx, float* d_acc, const float* d_x, size_t n) {
+  SM_CHECK_ARG(ctx && d_acc && d_x);
+  int grid = (int)min((size_t)ctx->num_sms * 16, (n + 255) / 256);
+  SM_LAUNCH(ctx, k_vol_accumulate, grid > 0 ? grid : 1, 256, 0, d_acc, d_x, n);
+  return SM_OK;
+}

@@ -1,0 +1,157 @@
+// cvmat_lite.h -- the slice of cv::Mat the StereoMatching stage API touches, so the class header compiles without
+// OpenCV (absent in the build image).  Same names, same memory layout (row-major, channels interleaved, n-dim
+// `size[]`/`step[]`), reference-counted buffer, `ptr<T>(i0[,i1[,i2]])`, `create`, `clone`, `copyTo`, CV_Assert
+// raising cv::Exception.  When real OpenCV is available, define SM_USE_OPENCV before including stereoMatching.h
+// and this file is skipped.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+typedef unsigned char uchar;
+typedef unsigned short ushort;
+
+#define CV_CN_MAX 512
+#define CV_CN_SHIFT 3
+#define CV_DEPTH_MAX (1 << CV_CN_SHIFT)
+#define CV_8U 0
+#define CV_8S 1
+#define CV_16U 2
+#define CV_16S 3
+#define CV_32S 4
+#define CV_32F 5
+#define CV_64F 6
+#define CV_MAT_DEPTH(flags) ((flags) & (CV_DEPTH_MAX - 1))
+#define CV_MAKETYPE(depth, cn) (CV_MAT_DEPTH(depth) + (((cn)-1) << CV_CN_SHIFT))
+#define CV_MAT_CN(flags) ((((flags) >> CV_CN_SHIFT) & (CV_CN_MAX - 1)) + 1)
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
+#define CV_16SC1 CV_MAKETYPE(CV_16S, 1)
+#define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
+#define CV_32FC(n) CV_MAKETYPE(CV_32F, (n))
+#define CV_16UC(n) CV_MAKETYPE(CV_16U, (n))
+
+namespace cv {
+
+class Exception : public std::runtime_error {
+ public:
+  explicit Exception(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define CV_Assert(expr)                                                                                   \
+  do {                                                                                                    \
+    if (!(expr))                                                                                          \
+      throw cv::Exception(std::string("CV_Assert failed: ") + #expr + " at " + __FILE__ + ":" +           \
+                          std::to_string(__LINE__));                                                      \
+  } while (0)
+
+class Mat {
+ public:
+  enum { MAX_DIM = 4 };
+  int flags = 0;  // type
+  int dims = 0;
+  int rows = 0, cols = 0;
+  int size[MAX_DIM] = {0, 0, 0, 0};
+  size_t step[MAX_DIM] = {0, 0, 0, 0};
+  uchar* data = nullptr;
+
+  Mat() {}
+  Mat(int r, int c, int type) { create(r, c, type); }
+  Mat(int nd, const int* sz, int type) { create(nd, sz, type); }
+  // header over caller-owned memory (no copy), like cv::Mat(rows, cols, type, void*)
+  Mat(int r, int c, int type, void* ext) { header2d(r, c, type); data = (uchar*)ext; }
+
+  static size_t depth_bytes(int depth) {
+    static const size_t b[7] = {1, 1, 2, 2, 4, 4, 8};
+    return b[depth];
+  }
+  int type() const { return flags; }
+  int depth() const { return CV_MAT_DEPTH(flags); }
+  int channels() const { return CV_MAT_CN(flags); }
+  size_t elemSize1() const { return depth_bytes(depth()); }
+  size_t elemSize() const { return elemSize1() * channels(); }
+  bool empty() const { return data == nullptr || total() == 0; }
+  bool isContinuous() const { return true; }
+  size_t total() const {
+    if (dims == 0) return 0;
+    size_t n = 1;
+    for (int i = 0; i < dims; i++) n *= (size_t)size[i];
+    return n;
+  }
+  size_t bytes() const { return total() * elemSize(); }
+
+  void create(int r, int c, int type) {
+    if (dims == 2 && rows == r && cols == c && flags == type && data) return;
+    header2d(r, c, type);
+    alloc();
+  }
+  void create(int nd, const int* sz, int type) {
+    CV_Assert(nd >= 1 && nd <= MAX_DIM);
+    bool same = dims == nd && flags == type && data;
+    for (int i = 0; same && i < nd; i++) same = size[i] == sz[i];
+    if (same) return;
+    flags = type; dims = nd;
+    for (int i = 0; i < MAX_DIM; i++) size[i] = i < nd ? sz[i] : 0;
+    rows = nd >= 1 ? sz[0] : 0; cols = nd >= 2 ? sz[1] : 1;
+    if (nd > 2) rows = cols = -1;   // OpenCV convention for n-dim matrices
+    size_t s = elemSize();
+    for (int i = nd - 1; i >= 0; i--) { step[i] = s; s *= (size_t)sz[i]; }
+    alloc();
+  }
+  void release() { buf_.reset(); data = nullptr; dims = 0; rows = cols = 0; }
+
+  template <typename T> T* ptr(int i0 = 0) { return (T*)(data + (size_t)i0 * step[0]); }
+  template <typename T> const T* ptr(int i0 = 0) const { return (const T*)(data + (size_t)i0 * step[0]); }
+  template <typename T> T* ptr(int i0, int i1) { return (T*)(data + (size_t)i0 * step[0] + (size_t)i1 * step[1]); }
+  template <typename T> const T* ptr(int i0, int i1) const { return (const T*)(data + (size_t)i0 * step[0] + (size_t)i1 * step[1]); }
+  template <typename T> T* ptr(int i0, int i1, int i2) {
+    return (T*)(data + (size_t)i0 * step[0] + (size_t)i1 * step[1] + (size_t)i2 * step[2]);
+  }
+  template <typename T> T& at(int i0, int i1) { return *ptr<T>(i0, i1); }
+
+  Mat clone() const { Mat m; copyTo(m); return m; }
+  void copyTo(Mat& dst) const {
+    if (dims <= 2) dst.create(rows, cols, flags); else dst.create(dims, size, flags);
+    if (bytes()) memcpy(dst.data, data, bytes());
+  }
+  Mat& setZero() { if (bytes()) memset(data, 0, bytes()); return *this; }
+
+ private:
+  std::shared_ptr<uchar> buf_;
+  void header2d(int r, int c, int type) {
+    flags = type; dims = 2; rows = r; cols = c;
+    size[0] = r; size[1] = c; size[2] = size[3] = 0;
+    step[1] = elemSize(); step[0] = step[1] * (size_t)c; step[2] = step[3] = 0;
+  }
+  void alloc() {
+    size_t n = bytes();
+    buf_.reset(n ? new uchar[n] : nullptr, std::default_delete<uchar[]>());
+    data = buf_.get();
+  }
+};
+
+template <typename T> struct mat_depth;
+template <> struct mat_depth<uchar> { enum { value = CV_8U }; };
+template <> struct mat_depth<ushort> { enum { value = CV_16U }; };
+template <> struct mat_depth<short> { enum { value = CV_16S }; };
+template <> struct mat_depth<int> { enum { value = CV_32S }; };
+template <> struct mat_depth<float> { enum { value = CV_32F }; };
+template <> struct mat_depth<double> { enum { value = CV_64F }; };
+
+template <typename T>
+class Mat_ : public Mat {
+ public:
+  Mat_() {}
+  Mat_(int r, int c) : Mat(r, c, CV_MAKETYPE(mat_depth<T>::value, 1)) {}
+  void create(int nd, const int* sz) { Mat::create(nd, sz, CV_MAKETYPE(mat_depth<T>::value, 1)); }
+  void create(int r, int c) { Mat::create(r, c, CV_MAKETYPE(mat_depth<T>::value, 1)); }
+};
+typedef Mat_<float> Mat1f;
+
+}  // namespace cv

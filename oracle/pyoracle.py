@@ -27,15 +27,15 @@ class OrcParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("D", "censusFunc", "paths", "iters", "L", "L_out", "tau",
                                        "tau_out", "minL", "corDifThres", "reduCoeffi1")] + \
                [(n, C.c_float) for n in ("adTrunc", "lamAD", "lamCen", "LRmaxDiff", "voteRatio")] + \
-               [(n, C.c_int) for n in ("voteS", "voteNums", "DISP_OCC", "do_refine")]
+               [(n, C.c_int) for n in ("voteS", "voteNums", "DISP_OCC", "do_refine", "aggregation")]
 
 
-def default_params(D, paths=4, census_func=3, do_refine=1):
+def default_params(D, paths=4, census_func=3, do_refine=1, aggregation=1):
     """Reference defaults: stereoMatching.h:204-350, stereoMatching.cpp:905, 5270."""
     return OrcParams(D=D, censusFunc=census_func, paths=paths, iters=2, L=17, L_out=34, tau=20,
                      tau_out=6, minL=1, corDifThres=15, reduCoeffi1=4, adTrunc=1000.0, lamAD=10.0,
                      lamCen=30.0, LRmaxDiff=0.0, voteRatio=0.4, voteS=20, voteNums=2, DISP_OCC=-32,
-                     do_refine=do_refine)
+                     do_refine=do_refine, aggregation=aggregation)
 
 
 def build(force=False):

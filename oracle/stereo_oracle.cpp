@@ -603,7 +603,9 @@ struct orc_params {
   int D, censusFunc, paths, iters, L, L_out, tau, tau_out, minL, corDifThres, reduCoeffi1;
   float adTrunc, lamAD, lamCen, LRmaxDiff, voteRatio;
   int voteS, voteNums, DISP_OCC, do_refine;
+  int aggregation;  // 1 = "CBCA" (cbca_aggregate), 2 = "NL" (StereoMatching::NL: left volume only), 0 = none
 };
+void orc_nl(const u8* bgrL, int H, int W, int D, float* vol, i16* disp);  // nl_oracle.cpp
 }  // extern "C"
 
 #include <chrono>
@@ -641,8 +643,12 @@ void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* gra
   orc_arms(bgrL, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aL.data());
   orc_arms(bgrR, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aR.data());
   lap(2);
-  for (int i = 0; i < views; i++)
-    orc_cbca(vm[i].data(), aL.data(), aR.data(), H, W, D, p->iters, i, nullptr);
+  if (p->aggregation == 1) {
+    for (int i = 0; i < views; i++)
+      orc_cbca(vm[i].data(), aL.data(), aR.data(), H, W, D, p->iters, i, nullptr);
+  } else if (p->aggregation == 2) {
+    orc_nl(bgrL, H, W, D, vm[0].data(), nullptr);  // stereoMatching.cpp:4892-4917: vm[0] only
+  }
   lap(3);
   for (int i = 0; i < views; i++)
     orc_sgm(vm[i].data(), i == 0 ? bgrL : bgrR, H, W, D, p->paths, p->corDifThres, p->reduCoeffi1);

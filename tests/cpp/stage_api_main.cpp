@@ -1,0 +1,113 @@
+// Test driver for the C++ stage API (mystereomatching_b200/host/stereoMatching.h).  Reads a raw stereo pair written
+// by tests/test_cpp_host.py, drives the class the way the reference's main() does (main_.cpp:138-166), and writes
+// raw outputs that the Python test compares with the CPU oracle.
+//   stage_api_test <in.bin> <out_prefix> <H> <W> <D> <paths> <mode>
+// in.bin = bgrL | bgrR | grayL | grayR (u8).  mode: "pipeline" | "stages" | "nl" | "errors"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "NL/NLCCA.h"
+#include "NL/ctmf.h"
+#include "NL/qx_tree_filter.h"
+#include "stereoMatching.h"
+
+static void dump(const std::string& path, const void* p, size_t n) {
+  std::ofstream f(path, std::ios::binary);
+  f.write((const char*)p, (std::streamsize)n);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 8) { fprintf(stderr, "usage\n"); return 2; }
+  const std::string in = argv[1], out = argv[2], mode = argv[7];
+  const int H = atoi(argv[3]), W = atoi(argv[4]), D = atoi(argv[5]), paths = atoi(argv[6]);
+  const size_t npix = (size_t)H * W;
+  std::vector<unsigned char> buf(npix * 8);
+  { std::ifstream f(in, std::ios::binary); f.read((char*)buf.data(), (std::streamsize)buf.size()); if (!f) { fprintf(stderr, "short input\n"); return 2; } }
+  cv::Mat I1c(H, W, CV_8UC3, buf.data()), I2c(H, W, CV_8UC3, buf.data() + npix * 3);
+  cv::Mat I1g(H, W, CV_8UC1, buf.data() + npix * 6), I2g(H, W, CV_8UC1, buf.data() + npix * 7);
+  cv::Mat DT, m0, m1, m2;
+  try {
+    if (mode == "errors") {
+      // CV_Assert-style failures must surface as cv::Exception
+      int caught = 0;
+      try { StereoMatching::Parameters p(600, H, W, 13, 1, 2, 109, 10, "", 1); StereoMatching s(I1c, I2c, I1g, I2g, DT, m0, m1, m2, p); }
+      catch (const cv::Exception&) { caught++; }
+      try {
+        StereoMatching::Parameters p(D - 1, H, W, 13, 1, 2, 109, 10, "", 1);
+        StereoMatching s(I1c, I2c, I1g, I2g, DT, m0, m1, m2, p);
+        cv::Mat lr, v = s.vm[0];
+        s.costScan(lr, s.vm[0], 2, 2, true);   // not a direction of the table
+      } catch (const cv::Exception&) { caught++; }
+      printf("caught %d\n", caught);
+      return caught == 2 ? 0 : 1;
+    }
+    if (mode == "nl") {
+      // the NL/ surface on its own: ctmf, qx_tree_filter, NLCCA::aggreCV
+      std::vector<unsigned char> med(npix * 3);
+      ctmf(I1c.data, med.data(), W, H, W * 3, W * 3, 1, 3, (unsigned long)npix * 3);
+      dump(out + ".ctmf.u8", med.data(), med.size());
+      qx_tree_filter tf;
+      tf.init(H, W, 3, 0.1, 4);
+      tf.build_tree(I1c.data);
+      dump(out + ".rank.i32", tf.get_rank(), npix * 4);
+      dump(out + ".parent.i32", tf.parent().data(), npix * 4);
+      std::vector<double> cost(npix * D), backup(npix * D);
+      for (size_t i = 0; i < cost.size(); i++) cost[i] = (double)((i * 2654435761u) % 1000) / 1000.0;
+      tf.filter(cost.data(), backup.data(), D);
+      dump(out + ".tf.f64", cost.data(), cost.size() * 8);
+      int sz[3] = {H, W, D};
+      cv::Mat vol(3, sz, CV_32FC1);
+      for (size_t i = 0; i < npix * D; i++) vol.ptr<float>()[i] = (float)((i * 2654435761u) % 1000) / 1000.0f;
+      NLCCA nl;
+      nl.aggreCV(I1c, I2c, D, vol);
+      dump(out + ".aggre.f32", vol.data, npix * D * 4);
+      return 0;
+    }
+    StereoMatching::costcalculation = "ADCensus";
+    StereoMatching::aggregation = "CBCA";
+    StereoMatching::optimization = "sgm";
+    StereoMatching::Parameters param(D - 1, H, W, 13, 1, 2, 109, 10, "", 1);   // main_.cpp:60-64, 138
+    StereoMatching sm(I1c, I2c, I1g, I2g, DT, m0, m1, m2, param);
+    sm.setSgmPaths(paths);
+    if (mode == "pipeline") {
+      sm.pipeline();
+    } else {   // "stages": the same chain, one public stage method at a time, through host-visible Mats where the API has them
+      sm.ADCensusCal();
+      sm.initArm();
+      sm.calArms<uchar>(sm.I_c, sm.HVL, sm.HVL_INTERSECTION, 17, 34, 20, 6);
+      sm.cbca_core(sm.HVL, sm.HVL_INTERSECTION, sm.vm, 2);
+      dump(out + ".vm0_cbca.f32", sm.hostVm(0).data, npix * D * 4);
+      for (int i = 0; i < 2; i++) sm.sgm(sm.vm[i], i == 0);
+      sm.DP[0].create(H, W, CV_16SC1); sm.DP[1].create(H, W, CV_16SC1);
+      for (int i = 0; i < 2; i++) sm.gen_dispFromVm(sm.vm[i], sm.DP[i]);
+      dump(out + ".dp0_wta.i16", sm.hostDP(0).data, npix * 2);
+      sm.refine();
+      // explicit-argument forms: host Mats in, host Mats out
+      cv::Mat ad, lr;
+      sm.gen_ad_sd_vm(ad, 0, 0, 1000);
+      dump(out + ".ad0.f32", ad.data, npix * D * 4);
+      std::vector<cv::Mat> cen(2);
+      sm.genCensusCode_NC_Sur(sm.I_g, cen, 3, 4);
+      dump(out + ".cenL.u64", cen[0].data, npix * 16);
+      cv::Mat cv0;
+      sm.gen_cenVM_XOR(cen, cv0, 71, 1.0f, 0);
+      dump(out + ".cen0.f32", cv0.data, npix * D * 4);
+      sm.costScan(lr, cv0, 0, -1, true);
+      dump(out + ".lr3.f32", lr.data, npix * D * 4);
+    }
+    sm.syncToHost(false);
+    dump(out + ".dp0.i16", sm.DP[0].data, npix * 2);
+    dump(out + ".hvl0.u16", sm.HVL[0].data, npix * 10);
+  } catch (const cv::Exception& e) {
+    fprintf(stderr, "cv::Exception: %s\n", e.what());
+    return 1;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "exception: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

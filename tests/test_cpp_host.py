@@ -1,0 +1,107 @@
+"""The C++ host side: class StereoMatching / NLCCA / qx_tree_filter / ctmf with the reference's names and signatures
+(mystereomatching_b200/host/), driven the way the reference's main() drives it, compared with the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from mystereomatching_b200 import synth
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "mystereomatching_b200", "host")
+EXE = os.path.join(HOST, "stage_api_test")
+LIB = os.path.join(ROOT, "mystereomatching_b200", "libstereomatching_b200.so")
+
+
+def test_host_library_exports_the_stage_api():
+    assert os.path.exists(LIB) and os.path.exists(EXE), "run __graft_entry__.build()"
+    out = subprocess.check_output(["nm", "-DC", "--defined-only", LIB], text=True)
+    for sym in ("StereoMatching::pipeline()", "StereoMatching::costCalculate()", "StereoMatching::dispOptimize()",
+                "StereoMatching::refine()", "StereoMatching::ADCensusCal()", "StereoMatching::CBCA()",
+                "StereoMatching::NL()", "StereoMatching::sgm(cv::Mat&, bool)",
+                "StereoMatching::costScan(cv::Mat&, cv::Mat&, int, int, bool)",
+                "StereoMatching::gen_dispFromVm(cv::Mat&, cv::Mat&)", "StereoMatching::wta_Co(",
+                "StereoMatching::regionVote_my(cv::Mat&, float, int)", "StereoMatching::properIpol(",
+                "StereoMatching::LRConsistencyCheck_normal(", "StereoMatching::genCensusCode_NC_Sur(",
+                "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
+                "void StereoMatching::calHorVerDis<unsigned char>(", "void StereoMatching::calArms<unsigned char>(",
+                "NLCCA::aggreCV(", "qx_tree_filter::filter(double*, double*, int)", "qx_tree_filter::build_tree(",
+                "ctmf"):
+        assert sym in out, sym
+
+
+def _run(tmp_path, pair, D, paths, mode):
+    H, W = pair["grayL"].shape
+    inp = tmp_path / "in.bin"
+    with open(inp, "wb") as f:
+        for k in ("bgrL", "bgrR", "grayL", "grayR"):
+            f.write(np.ascontiguousarray(pair[k]).tobytes())
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([EXE, str(inp), prefix, str(H), str(W), str(D), str(paths), mode], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return prefix, r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["pipeline", "stages"])
+def test_cpp_class_matches_oracle(tmp_path, mode):
+    H, W, D, P = 72, 110, 40, 4
+    pair = synth.make_pair(H, W, D, "texture_warped", seed=17)
+    prefix, _ = _run(tmp_path, pair, D, P, mode)
+    ref, _, vol, _ = po.pipeline(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], po.default_params(D, paths=P),
+                                 want_vol=True)
+    dp = np.fromfile(prefix + ".dp0.i16", np.int16).reshape(H, W)
+    assert (dp == ref).mean() >= 0.995
+    hvl = np.fromfile(prefix + ".hvl0.u16", np.uint16).reshape(H, W, 5)
+    assert np.array_equal(hvl, po.arms(pair["bgrL"]))
+    if mode == "stages":
+        aL, aR = po.arms(pair["bgrL"]), po.arms(pair["bgrR"])
+        cost = po.adcensus_vol(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], D, 0)
+        cb = po.cbca(cost, aL, aR, 2, 0)
+        got = np.fromfile(prefix + ".vm0_cbca.f32", np.float32).reshape(H, W, D)
+        assert np.array_equal(got.view(np.uint32), cb.view(np.uint32))
+        wta = np.fromfile(prefix + ".dp0_wta.i16", np.int16).reshape(H, W)
+        assert np.array_equal(wta, po.wta(po.sgm(cb, pair["bgrL"], P)))
+        ad = np.fromfile(prefix + ".ad0.f32", np.float32).reshape(H, W, D)
+        assert np.array_equal(ad, po.ad_vol(pair["bgrL"], pair["bgrR"], D, 0))
+        cen = np.fromfile(prefix + ".cenL.u64", np.uint64).reshape(H, W, 2)
+        assert np.array_equal(cen, po.census(pair["grayL"], 3))
+        cv0 = np.fromfile(prefix + ".cen0.f32", np.float32).reshape(H, W, D)
+        ham = po.hamming_vol(po.census(pair["grayL"]), po.census(pair["grayR"]), D)
+        assert np.array_equal(cv0, ham)
+        lr = np.fromfile(prefix + ".lr3.f32", np.float32).reshape(H, W, D)
+        assert np.array_equal(lr, po.sgm_path(ham, pair["bgrL"], 3))
+
+
+@pytest.mark.gpu
+def test_cpp_nl_surface_matches_oracle(tmp_path):
+    H, W, D = 40, 56, 6
+    pair = synth.make_pair(H, W, 8, "texture_warped", seed=4)
+    prefix, _ = _run(tmp_path, pair, D, 4, "nl")
+    img = pair["bgrL"]
+    assert np.array_equal(np.fromfile(prefix + ".ctmf.u8", np.uint8).reshape(H, W, 3), po.ctmf(img, 1))
+    t = po.mst(img)
+    assert np.array_equal(np.fromfile(prefix + ".rank.i32", np.int32), t["rank"])
+    assert np.array_equal(np.fromfile(prefix + ".parent.i32", np.int32)[1:], t["parent"][1:])
+    i = np.arange(H * W * D, dtype=np.uint64)
+    cost = ((i * np.uint64(2654435761)) % np.uint64(1000)).astype(np.float64) / 1000.0   # 64-bit product, as in C++
+    table = np.empty(256, np.float64)
+    po.lib().orc_tree_table(0.1, table)
+    ref = cost.reshape(H * W, D).copy()
+    tmp = np.empty_like(ref)
+    po.lib().orc_tree_filter(ref, tmp, H * W, D, t["parent"], t["weight"], t["nr_child"], t["children"], t["order"], table)
+    got = np.fromfile(prefix + ".tf.f64", np.float64).reshape(H * W, D)
+    assert np.array_equal(got, ref)                                     # float64, bit for bit
+    vol = ((i * np.uint64(2654435761)) % np.uint64(1000)).astype(np.float32) / np.float32(1000.0)
+    ag = po.nl_aggre(img, vol.reshape(H, W, D))
+    assert np.array_equal(np.fromfile(prefix + ".aggre.f32", np.float32).reshape(H, W, D), ag)
+
+
+@pytest.mark.gpu
+def test_cpp_error_convention(tmp_path):
+    pair = synth.make_pair(24, 32, 8, "random_dot", seed=1)
+    _, out = _run(tmp_path, pair, 8, 4, "errors")
+    assert "caught 2" in out

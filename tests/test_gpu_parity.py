@@ -318,6 +318,8 @@ def test_pipeline_nl_matches_oracle_composition(ctx):
     pl = capi.Pipeline(ctx, H, W, params)
     got = pl.run(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"])
     pl.close()
+    whole, _, _, _ = po.pipeline(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"],
+                                 po.default_params(D, paths=4, aggregation=2))
     v0 = po.adcensus_vol(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D, 0)
     v1 = po.adcensus_vol(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D, 1)
     v0, _ = po.nl(p["bgrL"], v0)
@@ -330,4 +332,5 @@ def test_pipeline_nl_matches_oracle_composition(ctx):
     for _ in range(2):
         d = po.proper_ipol(d, p["bgrL"])
     d = po.median3_i16(d)
+    assert np.array_equal(whole, d)            # the oracle's own NL chain is this composition
     assert (got == d).mean() >= 0.995
