@@ -193,7 +193,8 @@ def stage_bytes(name):
         "cost": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_cost<ADCENSUS>"},
         "aggregation": agg,
         "sgm": {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path"},
-        "wta": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_wta"},
+        # gen_dispFromVm is fused into the last SGM path of each view (no separate read of the summed volume)
+        "wta": {"bytes_per_launch": 0, "launches": 2, "kernel": "fused into k_sgm_path (mode 2)"},
     }
 
 

@@ -84,7 +84,7 @@ static inline int sm_div_up(long long a, long long b) { return (int)((a + b - 1)
 int smi_pack_bgr(sm_ctx* ctx, const uint8_t* d_bgr, long long npix, uint32_t* d_out);
 // arms [H][W][5] u16 -> one uint2 per pixel {armH = left | right<<16, armV = up | down<<16} in rows of W + 2*PAD
 // entries: pixel u sits at index PAD + u and the PAD entries on either side are zero (partner outside the image).
-// d_out holds 2 * H * (W + 2*PAD) words.
+// Followed by the armH plane and the armV plane (one u32 per entry each): d_out holds 4 * H * (W + 2*PAD) words.
 int smi_pack_arms(sm_ctx* ctx, const uint16_t* d_arms, int H, int W, int PAD, uint32_t* d_out);
 static inline int smi_arm_pad(int D) { return (D + 31) / 32 * 32; }
 // the two exp lookup tables of the fused AD-Census kernel (see cost.cu)
@@ -102,6 +102,9 @@ int smi_arms_packed(sm_ctx* ctx, const uint32_t* d_pix, int H, int W, int L, int
 int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D);
 int smi_sgm_path_packed(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                         int corDifThres, int reduCoeffi1, int mode, float* d_out);
+// mode 2: accumulate and write the WTA of the finished sum into d_disp (last path of a view)
+int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
+                         int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp);
 
 __device__ __forceinline__ int smd_absdiff_max3(uint32_t a, uint32_t b) {
   // max over the three low bytes of |a_c - b_c|

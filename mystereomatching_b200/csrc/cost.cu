@@ -14,13 +14,15 @@
 // reference's left-to-right float subtraction -- so the volume equals the CPU
 // result bit for bit, and no transcendental runs on the device.
 //
-// Kernel shape (HBM-write bound, 4 B per element): persistent CTAs (one per SM,
-// 1024 threads).  Each CTA keeps lane-replicated copies of both tables in shared
-// memory ([entry][32 lanes] -> lookups are bank-conflict free by construction)
-// and walks (row, 512-pixel segment) work items: the "other" image's census
-// word + packed pixel for the D-1+512 positions the segment can match against are
-// staged in shared memory once, then every warp takes anchor pixels and its
-// lanes run along d, so each warp store is one fully coalesced 128-byte line.
+// Kernel shape (HBM-write bound, 4 B per element): persistent CTAs (one per SM, 1024 threads).  Each CTA keeps
+// lane-replicated copies of both tables in shared memory ([entry][32 lanes] -> lookups are bank-conflict free
+// by construction) and walks (row, 512-pixel segment) work items: the "other" image's census words and packed
+// pixel for the D-1+512 positions the segment can match against are staged in shared memory once, then every
+// warp takes anchor pixels and its lanes run along d, so each warp store is one fully coalesced 128-byte line.
+// Per element the steady state is ~20 instructions: 2 staged loads, the 71-bit Hamming count as 2 POPC (3-input
+// majority identity), the 3-channel SAD as one VABSDIFF4.U8.ACC, two table loads, one subtraction, one store.
+// Disparities whose partner lies outside the image form a contiguous tail d >= nvalid of every pixel and get
+// the constant out-of-range value without touching the tables per element.
 #include <math.h>
 
 #include "common.cuh"
@@ -32,23 +34,59 @@
 
 enum { COST_ADCENSUS = 0, COST_HAMMING_F32 = 1, COST_AD_F32 = 2, COST_HAMMING_U16 = 3 };
 
+template <int MODE, typename OutT, bool CHECK>
+__device__ __forceinline__ OutT cost_one(int idx, int d, int nvalid, uint32_t pa, uint64_t ca0, uint32_t ca1,
+                                         const uint32_t* __restrict__ sPix, const uint64_t* __restrict__ sCen,
+                                         const uint32_t* __restrict__ sHi, const float* __restrict__ sT1,
+                                         const float* __restrict__ sTabCen, int lane, int nw, OutT oor) {
+  constexpr bool NEED_CEN = MODE != COST_AD_F32, NEED_AD = MODE == COST_ADCENSUS || MODE == COST_AD_F32;
+  int c = 0, k = 0;
+  if (NEED_CEN) {
+    const uint64_t x0 = ca0 ^ sCen[idx];
+    const uint32_t a0 = (uint32_t)x0, a1 = (uint32_t)(x0 >> 32);
+    if (nw == 2) {
+      const uint32_t a2 = ca1 ^ sHi[idx];
+      // popc(a)+popc(b)+popc(c) = popc(a^b^c) + 2*popc(maj(a,b,c)): 2 POPC for 71 bits
+      c = __popc(a0 ^ a1 ^ a2) + 2 * __popc((a0 & a1) | (a0 & a2) | (a1 & a2));
+    } else {
+      c = __popcll(x0);
+    }
+    // min(count, codeLength) of gen_cenVM_XOR is the identity: a code has codeLength bits (truncRat = 1)
+  }
+  if (NEED_AD) k = (int)__vsadu4(pa, sPix[idx]);   // sum_c |l_c - r_c| (byte 3 is zero in both words)
+  OutT r;
+  if (MODE == COST_ADCENSUS) r = (OutT)(sT1[(k << 5) + lane] - sTabCen[(c << 5) + lane]);   // (2 - e^-ad/l) - e^-c/l
+  else if (MODE == COST_AD_F32) r = (OutT)sT1[(k << 5) + lane];
+  else r = (OutT)c;
+  if (CHECK) r = d < nvalid ? r : oor;
+  return r;
+}
+
 template <int MODE, typename OutT>
 __global__ void __launch_bounds__(COST_THREADS, 1)
     k_cost(const uint32_t* __restrict__ pixA, const uint32_t* __restrict__ pixO, const uint64_t* __restrict__ cenA,
            const uint64_t* __restrict__ cenO, int nw, int H, int W, int D, int sgn, int codeLen,
            const float* __restrict__ tabAD, const float* __restrict__ tabCen, OutT* __restrict__ vol) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* sTabAD = reinterpret_cast<float*>(smem_raw);                       // [767][32]
-  float* sTabCen = sTabAD + (MODE == COST_ADCENSUS || MODE == COST_AD_F32 ? COST_TAB_AD * 32 : 0);
+  constexpr bool NEED_CEN = MODE != COST_AD_F32, NEED_AD = MODE == COST_ADCENSUS || MODE == COST_AD_F32;
+  float* sT1 = reinterpret_cast<float*>(smem_raw);                          // [767][32]: 2 - tabAD (or raw AD)
+  float* sTabCen = sT1 + (NEED_AD ? COST_TAB_AD * 32 : 0);                  // [72][32]
   uint64_t* sCen = reinterpret_cast<uint64_t*>(sTabCen + (MODE == COST_ADCENSUS ? (COST_MAX_CODE + 1) * 32 : 0));
   const int maxEntries = COST_SEG + D - 1;
-  uint32_t* sM = reinterpret_cast<uint32_t*>(sCen + maxEntries);
+  uint32_t* sPix = reinterpret_cast<uint32_t*>(sCen + maxEntries);
+  uint32_t* sHi = sPix + maxEntries;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (MODE == COST_ADCENSUS || MODE == COST_AD_F32)
-    for (int i = tid; i < COST_TAB_AD * 32; i += COST_THREADS) sTabAD[i] = tabAD[i >> 5];
+  if (NEED_AD)
+    for (int i = tid; i < COST_TAB_AD * 32; i += COST_THREADS)
+      sT1[i] = MODE == COST_ADCENSUS ? 2.0f - tabAD[i >> 5] : tabAD[i >> 5];   // first operation of "2 - a - b"
   if (MODE == COST_ADCENSUS)
     for (int i = tid; i < (codeLen + 1) * 32; i += COST_THREADS) sTabCen[i] = tabCen[i >> 5];
+  // value of every out-of-range disparity (gen_ad_sd_vm: trunc; gen_cenVM_XOR: codeLength)
+  OutT oor;
+  if (MODE == COST_ADCENSUS) oor = (OutT)((2.0f - tabAD[766]) - tabCen[codeLen]);
+  else if (MODE == COST_AD_F32) oor = (OutT)tabAD[766];
+  else oor = (OutT)codeLen;
 
   const int nSeg = (W + COST_SEG - 1) / COST_SEG;
   const int nItems = H * nSeg;
@@ -60,59 +98,48 @@ __global__ void __launch_bounds__(COST_THREADS, 1)
     const int cnt = nA + D - 1;
     __syncthreads();  // previous item's readers are done (also orders the table fill)
     for (int i = tid; i < cnt; i += COST_THREADS) {
-      int e = elo + i;
-      uint32_t m = 0xFFFFFFFFu;  // bit 31 set = outside the image
+      const int e = elo + i;
+      uint32_t px = 0, hi = 0;
       uint64_t c0 = 0;
       if (e >= 0 && e < W) {
-        size_t p = (size_t)v * W + e;
-        m = MODE == COST_HAMMING_F32 || MODE == COST_HAMMING_U16 ? 0u : (pixO[p] & 0x00FFFFFFu);
-        if (MODE != COST_AD_F32) {
+        const size_t p = (size_t)v * W + e;
+        if (NEED_AD) px = pixO[p] & 0x00FFFFFFu;
+        if (NEED_CEN) {
           c0 = cenO[p * nw];
-          if (nw == 2) m |= (uint32_t)cenO[p * nw + 1] << 24;
+          if (nw == 2) hi = (uint32_t)cenO[p * nw + 1];
         }
       }
-      sCen[i] = c0;
-      sM[i] = m;
+      sCen[i] = c0; sPix[i] = px; sHi[i] = hi;
     }
     __syncthreads();
     for (int a = warp; a < nA; a += COST_THREADS / 32) {
       const int u = ua + a;
       const size_t p = (size_t)v * W + u;
-      uint32_t ma = MODE == COST_HAMMING_F32 || MODE == COST_HAMMING_U16 ? 0u : (pixA[p] & 0x00FFFFFFu);
+      const uint32_t pa = NEED_AD ? (pixA[p] & 0x00FFFFFFu) : 0u;
       uint64_t ca0 = 0;
-      if (MODE != COST_AD_F32) {
+      uint32_t ca1 = 0;
+      if (NEED_CEN) {
         ca0 = cenA[p * nw];
-        if (nw == 2) ma |= (uint32_t)cenA[p * nw + 1] << 24;
+        if (nw == 2) ca1 = (uint32_t)cenA[p * nw + 1];
       }
-      OutT* out = vol + p * D;
-      const int base = u - elo;
-      for (int j = 0; j < nd; j++) {
-        const int d = lane + (j << 5);
+      OutT* out = vol + p * D + lane;
+      // in-range disparities of this pixel: view 0 (sgn +1): u - d >= 0; view 1: u + d < W
+      const int nvalid = min(D, sgn > 0 ? u + 1 : W - u);
+      const int base = u - elo - sgn * lane;   // staged index of d = lane; d += 32 moves it by -sgn*32
+      int j = 0;
+      // chunks of 32 disparities that are entirely in range: no predicate, 4 at a time
+      for (; (j + 4) * 32 <= nvalid; j += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          out[(j + q) * 32] = cost_one<MODE, OutT, false>(base - sgn * (j + q) * 32, 0, 0, pa, ca0, ca1, sPix, sCen, sHi,
+                                                          sT1, sTabCen, lane, nw, oor);
+      }
+      for (; j < nd; j++) {
+        const int d = lane + j * 32;
         if (d >= D) break;
-        const int idx = base - sgn * d;
-        const uint32_t mo = sM[idx];
-        int k = 0, c = 0;
-        if (mo & 0x80000000u) {
-          k = 766;
-          c = codeLen;
-        } else {
-          const uint32_t x = ma ^ mo;
-          if (MODE != COST_AD_F32) {
-            const uint64_t x0 = ca0 ^ sCen[idx];
-            // popc(a)+popc(b)+popc(c) = popc(a^b^c) + 2*popc(maj(a,b,c)): 2 POPC for 71 bits
-            const uint32_t a0 = (uint32_t)x0, a1 = (uint32_t)(x0 >> 32), a2 = x >> 24;
-            c = __popc(a0 ^ a1 ^ a2) + 2 * __popc((a0 & a1) | (a0 & a2) | (a1 & a2));
-            c = min(c, codeLen);
-          }
-          if (MODE == COST_ADCENSUS || MODE == COST_AD_F32)
-            k = __dp4a(__vabsdiffu4(ma, mo) & 0x00FFFFFFu, 0x01010101u, 0u);
-        }
-        if (MODE == COST_ADCENSUS)
-          out[d] = (OutT)((2.0f - sTabAD[(k << 5) + lane]) - sTabCen[(c << 5) + lane]);
-        else if (MODE == COST_AD_F32)
-          out[d] = (OutT)sTabAD[(k << 5) + lane];
-        else
-          out[d] = (OutT)c;
+        if (j * 32 >= nvalid) out[j * 32] = oor;   // chunk entirely out of range: constant
+        else out[j * 32] = cost_one<MODE, OutT, true>(base - sgn * j * 32, d, nvalid, pa, ca0, ca1, sPix, sCen, sHi, sT1,
+                                                      sTabCen, lane, nw, oor);
       }
     }
   }
@@ -152,7 +179,7 @@ static int launch_cost(sm_ctx* ctx, const uint32_t* pixA, const uint32_t* pixO, 
   size_t smem = 0;
   if (MODE == COST_ADCENSUS || MODE == COST_AD_F32) smem += COST_TAB_AD * 32 * sizeof(float);
   if (MODE == COST_ADCENSUS) smem += (COST_MAX_CODE + 1) * 32 * sizeof(float);
-  smem += (size_t)(COST_SEG + D - 1) * (sizeof(uint64_t) + sizeof(uint32_t));
+  smem += (size_t)(COST_SEG + D - 1) * (sizeof(uint64_t) + 2 * sizeof(uint32_t));
   SM_CUDA(cudaFuncSetAttribute(k_cost<MODE, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int nItems = H * sm_div_up(W, COST_SEG);
   int grid = min(nItems, ctx->num_sms);

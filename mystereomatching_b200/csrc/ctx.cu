@@ -210,7 +210,9 @@ __global__ void k_pack_arms(const uint16_t* __restrict__ arms, int H, int W, int
       wh = (uint32_t)a[0] | ((uint32_t)a[1] << 16);
       wv = (uint32_t)a[2] | ((uint32_t)a[3] << 16);
     }
-    reinterpret_cast<uint2*>(out)[i] = make_uint2(wh, wv);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(wh, wv);   // pair map
+    out[2 * n + i] = wh;                                     // armH plane
+    out[3 * n + i] = wv;                                     // armV plane
   }
 }
 

@@ -73,7 +73,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->bgr[i], npix * 3);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->gray[i], npix);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->pix[i], npix * 4);
-    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], (size_t)H * (W + 2 * smi_arm_pad(pl->D)) * 8);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], (size_t)H * (W + 2 * smi_arm_pad(pl->D)) * 16);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->cen[i], npix * 8 * nw);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->arms[i], npix * 5 * 2);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->disp[i], npix * 2);
@@ -188,16 +188,20 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   // ---- dispOptimize: sgm (stereoMatching.cpp:1051-1089) then WTA (:1108-1128)
   if (P.sgm_paths > 0) {
     for (int i = 0; i < views; i++) {
-      for (int k = 0; k < P.sgm_paths; k++)
-        SM_TRY(smi_sgm_path_packed(c, pl->vol[i], pl->pix[i], H, W, D, k, P.sgm_corDifThres, P.sgm_reduCoeffi1,
-                                   k == 0 ? 0 : 1, pl->vol[2]));
+      for (int k = 0; k < P.sgm_paths; k++) {
+        // the last path also does gen_dispFromVm on the finished sum (saves one read of the volume)
+        const int mode = k == 0 ? 0 : (k == P.sgm_paths - 1 ? 2 : 1);
+        SM_TRY(smi_sgm_path_packed2(c, pl->vol[i], pl->pix[i], H, W, D, k, P.sgm_corDifThres, P.sgm_reduCoeffi1, mode,
+                                    pl->vol[2], pl->disp[i]));
+      }
       float* t = pl->vol[i];  // vm[i] <- path sum; the old cost volume becomes the scratch
       pl->vol[i] = pl->vol[2];
       pl->vol[2] = t;
     }
   }
   PL_MARK(5);
-  for (int i = 0; i < views; i++) SM_TRY(sm_wta(c, pl->vol[i], H, W, D, pl->disp[i]));
+  if (P.sgm_paths < 2)   // otherwise the WTA was fused into the last SGM path
+    for (int i = 0; i < views; i++) SM_TRY(sm_wta(c, pl->vol[i], H, W, D, pl->disp[i]));
   PL_MARK(6);
   // ---- refine (stereoMatching.cpp:1364-1506)
   if (P.Do_refine) {

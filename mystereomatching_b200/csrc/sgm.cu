@@ -20,10 +20,39 @@
 // to the running sum S (mode 1: read-modify-write, in the reference's path
 // order so the float sum is bit-identical).
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 #define SGM_WARPS 2
+#define SGM_NSTG 12   // staged variant: pixels in flight per warp (cp.async), one extra slot so a refill never
+                      // targets the slot being read
+
+// MODE 0: out = Lr.  MODE 1: out += Lr (path sum).  MODE 2: out += Lr and the final WTA of gen_dispFromVm
+// (stereoMatching.cpp:3928-3967: first minimum, -1 if nothing is below FLT_MAX) fused into the last path, which
+// saves the separate read of the summed volume.
+// STAGED (horizontal paths only): a row is contiguous in memory and there are only H of them (7 warps per SM at
+// 1080p), so register prefetch cannot keep enough bytes in flight; the C and S runs and the pixel word are instead
+// staged SGM_NSTG pixels ahead with cp.async into per-lane shared-memory slots.
+__device__ __forceinline__ void sgm_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sgm_cp4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sgm_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sgm_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 sgm_lds16(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t sgm_lds4(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ uint32_t f2key(float x) {
   uint32_t b = __float_as_uint(x);
@@ -85,10 +114,66 @@ __device__ __forceinline__ void line_start(const sgm_geom& g, int k, int& v, int
   }
 }
 
+// One step of the recurrence for one pixel: updateCost<float> (stereoMatching.h:2205-2280) + gen_sgm_vm's sum.
+template <int VPL, int MODE>
+__device__ __forceinline__ void sgm_step(bool first, const float (&c)[VPL], float (&s)[VPL], float (&prev)[VPL],
+                                         float& minC, uint32_t x, uint32_t& xprev, int d0, int D, int corDifThres,
+                                         float redu, int lane, int16_t* __restrict__ disp, long long p) {
+  float lr[VPL];
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < VPL; j++) lr[j] = c[j];
+  } else {
+    const int D1 = smd_absdiff_max3(x, xprev);
+    float P1 = 1.0f, P2 = 3.0f;
+    if (D1 > corDifThres) { P1 = P1 / redu; P2 = P2 / redu; }
+    P1 = P1 - minC;
+    float lo = __shfl_up_sync(0xffffffffu, prev[VPL - 1], 1);   // Lr'[d0-1]
+    float hi = __shfl_down_sync(0xffffffffu, prev[0], 1);       // Lr'[d0+VPL]
+#pragma unroll
+    for (int j = 0; j < VPL; j++) {
+      const int d = d0 + j;
+      const float pm = j == 0 ? lo : prev[j - 1];
+      const float pp = j == VPL - 1 ? hi : prev[j + 1];
+      const float S1 = prev[j] - minC;
+      const float S2 = d - 1 >= 0 ? pm + P1 : FLT_MAX;
+      const float S3 = d + 1 < D ? pp + P1 : FLT_MAX;
+      lr[j] = c[j] + fminf(fminf(S1, S2), fminf(S3, P2));
+    }
+  }
+  // D-wide minimum of the new row (padding lanes hold FLT_MAX via c[])
+  float m = FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < VPL; j++) m = (d0 + j < D) ? fminf(m, lr[j]) : m;
+  minC = key2f(__reduce_min_sync(0xffffffffu, f2key(m)));
+#pragma unroll
+  for (int j = 0; j < VPL; j++) prev[j] = lr[j];
+  xprev = x;
+  if (MODE >= 1) {
+#pragma unroll
+    for (int j = 0; j < VPL; j++) s[j] = s[j] + lr[j];  // gen_sgm_vm: sum += L[num]
+  } else {
+#pragma unroll
+    for (int j = 0; j < VPL; j++) s[j] = lr[j];
+  }
+  if (MODE == 2) {
+    // gen_dispFromVm on the finished sum: strict '>' scan in increasing d -> the lowest d among the minima
+    float bm = FLT_MAX;
+    int bd = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < VPL; j++)
+      if (d0 + j < D && bm > s[j]) { bm = s[j]; bd = d0 + j; }
+    const uint32_t km = __reduce_min_sync(0xffffffffu, f2key(bm));
+    const int cand = (f2key(bm) == km && bd != 0x7fffffff) ? bd : 0x7fffffff;
+    const int best = (int)__reduce_min_sync(0xffffffffu, (unsigned)cand);
+    if (lane == 0) disp[p] = (int16_t)(best == 0x7fffffff ? -1 : best);
+  }
+}
+
 template <int VPL, int PF, bool VEC, int MODE>
 __global__ void __launch_bounds__(SGM_WARPS * 32)
     k_sgm_path(const float* __restrict__ vol, const uint32_t* __restrict__ pix, float* __restrict__ out, sgm_geom g,
-               int D, int corDifThres, float redu) {
+               int D, int corDifThres, float redu, int16_t* __restrict__ disp) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * SGM_WARPS + (threadIdx.x >> 5);
   if (k >= g.nLines) return;
@@ -98,14 +183,14 @@ __global__ void __launch_bounds__(SGM_WARPS * 32)
   const long long pstep = (long long)g.mv * g.W + g.mu;
   long long p = (long long)v * g.W + u;
 
-  float cpf[PF][VPL], spf[MODE == 1 ? PF : 1][VPL];
+  float cpf[PF][VPL], spf[MODE >= 1 ? PF : 1][VPL];
   uint32_t xpf[PF];
 #pragma unroll
   for (int i = 0; i < PF; i++) {
     if (i < len) {
       const long long q = p + pstep * i;
       load_run<VPL, VEC>(vol + q * D, d0, D, cpf[i]);
-      if (MODE == 1) load_run<VPL, VEC>(out + q * D, d0, D, spf[i]);
+      if (MODE >= 1) load_run<VPL, VEC>(out + q * D, d0, D, spf[i]);
       xpf[i] = pix[q];
     }
   }
@@ -118,54 +203,89 @@ __global__ void __launch_bounds__(SGM_WARPS * 32)
     for (int i = 0; i < PF; i++) {
       const int t = t0 + i;
       if (t < len) {
-        float c[VPL], s[VPL], lr[VPL];
+        float c[VPL], s[VPL];
 #pragma unroll
-        for (int j = 0; j < VPL; j++) { c[j] = cpf[i][j]; if (MODE == 1) s[j] = spf[i][j]; }
+        for (int j = 0; j < VPL; j++) { c[j] = cpf[i][j]; s[j] = MODE >= 1 ? spf[MODE >= 1 ? i : 0][j] : 0.f; }
         const uint32_t x = xpf[i];
         if (t + PF < len) {  // refill this prefetch slot for pixel t+PF
           const long long q = p + pstep * PF;
           load_run<VPL, VEC>(vol + q * D, d0, D, cpf[i]);
-          if (MODE == 1) load_run<VPL, VEC>(out + q * D, d0, D, spf[i]);
+          if (MODE >= 1) load_run<VPL, VEC>(out + q * D, d0, D, spf[MODE >= 1 ? i : 0]);
           xpf[i] = pix[q];
         }
-        if (t == 0) {
-#pragma unroll
-          for (int j = 0; j < VPL; j++) lr[j] = c[j];
-        } else {
-          const int D1 = smd_absdiff_max3(x, xprev);
-          float P1 = 1.0f, P2 = 3.0f;
-          if (D1 > corDifThres) { P1 = P1 / redu; P2 = P2 / redu; }
-          P1 = P1 - minC;
-          float lo = __shfl_up_sync(0xffffffffu, prev[VPL - 1], 1);   // Lr'[d0-1]
-          float hi = __shfl_down_sync(0xffffffffu, prev[0], 1);       // Lr'[d0+VPL]
-#pragma unroll
-          for (int j = 0; j < VPL; j++) {
-            const int d = d0 + j;
-            const float pm = j == 0 ? lo : prev[j - 1];
-            const float pp = j == VPL - 1 ? hi : prev[j + 1];
-            const float S1 = prev[j] - minC;
-            const float S2 = d - 1 >= 0 ? pm + P1 : FLT_MAX;
-            const float S3 = d + 1 < D ? pp + P1 : FLT_MAX;
-            lr[j] = c[j] + fminf(fminf(S1, S2), fminf(S3, P2));
-          }
-        }
-        // D-wide minimum of the new row (padding lanes hold FLT_MAX via c[])
-        float m = FLT_MAX;
-#pragma unroll
-        for (int j = 0; j < VPL; j++) m = (d0 + j < D) ? fminf(m, lr[j]) : m;
-        minC = key2f(__reduce_min_sync(0xffffffffu, f2key(m)));
-#pragma unroll
-        for (int j = 0; j < VPL; j++) prev[j] = lr[j];
-        xprev = x;
-        if (MODE == 1) {
-#pragma unroll
-          for (int j = 0; j < VPL; j++) lr[j] = s[j] + lr[j];  // gen_sgm_vm: sum += L[num]
-        }
-        store_run<VPL, VEC>(out + p * D, d0, D, lr);
+        sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, p);
+        store_run<VPL, VEC>(out + p * D, d0, D, s);
         p += pstep;
       }
     }
   }
+}
+
+// Horizontal paths, cp.async staged (VPL % 4 == 0, D % 4 == 0, 16-byte aligned volumes).
+template <int VPL, int MODE>
+__global__ void __launch_bounds__(32)
+    k_sgm_path_h(const float* __restrict__ vol, const uint32_t* __restrict__ pix, float* __restrict__ out, int H, int W,
+                 int mu, int D, int corDifThres, float redu, int16_t* __restrict__ disp) {
+  extern __shared__ __align__(16) uint8_t sgm_smem[];
+  constexpr int NS = SGM_NSTG + 1;                       // slots
+  constexpr int RUNB = VPL * 4;                          // bytes of one lane's run
+  constexpr int SLOTB = 32 * RUNB * (MODE >= 1 ? 2 : 1) + 128;   // C run | S run | pixel word, per lane
+  const int lane = threadIdx.x;
+  const int v = blockIdx.x;
+  const int d0 = lane * VPL;
+  const bool act = d0 < D;                               // D % 4 == 0 and VPL % 4 == 0: a run is wholly in or out
+  const int nq = act ? min(VPL, D - d0) / 4 : 0;         // 16-byte pieces of this lane's run
+  const long long pstep = mu;
+  long long p = (long long)v * W + (mu > 0 ? 0 : W - 1);
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sgm_smem);
+  const uint32_t cOff = base + lane * RUNB, sOff = cOff + 32 * RUNB, xOff = base + 32 * RUNB * (MODE >= 1 ? 2 : 1) + lane * 4;
+
+  auto issue = [&](int t, int slot) {
+    if (t < W) {
+      const long long q = p + pstep * t;
+      const uint32_t so = slot * SLOTB;
+      for (int k = 0; k < nq; k++) {
+        sgm_cp16(cOff + so + k * 16, vol + q * D + d0 + k * 4);
+        if (MODE >= 1) sgm_cp16(sOff + so + k * 16, out + q * D + d0 + k * 4);
+      }
+      sgm_cp4(xOff + so, pix + q);
+    }
+    sgm_commit();
+  };
+  const long long p0 = p;
+  (void)p0;
+  for (int t = 0; t < SGM_NSTG; t++) issue(t, t);
+  float prev[VPL];
+  float minC = 0.f;
+  uint32_t xprev = 0;
+  int rd = 0, wr = SGM_NSTG;
+  // note: `issue` indexes pixels from the line start, so keep p fixed and carry the running pixel separately
+  long long pc = p;
+  for (int t = 0; t < W; t++) {
+    sgm_wait<SGM_NSTG - 1>();
+    float c[VPL], s[VPL];
+    const uint32_t so = rd * SLOTB;
+#pragma unroll
+    for (int k = 0; k < VPL / 4; k++) {
+      float4 a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < nq) {
+        a = sgm_lds16(cOff + so + k * 16);
+        if (MODE >= 1) b = sgm_lds16(sOff + so + k * 16);
+      }
+      c[4 * k] = a.x; c[4 * k + 1] = a.y; c[4 * k + 2] = a.z; c[4 * k + 3] = a.w;
+      s[4 * k] = b.x; s[4 * k + 1] = b.y; s[4 * k + 2] = b.z; s[4 * k + 3] = b.w;
+    }
+    const uint32_t x = sgm_lds4(xOff + so);
+    issue(t + SGM_NSTG, wr);
+    sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, pc);
+#pragma unroll
+    for (int k = 0; k < VPL / 4; k++)
+      if (k < nq) *reinterpret_cast<float4*>(out + pc * D + d0 + k * 4) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    pc += pstep;
+    if (++rd == NS) rd = 0;
+    if (++wr == NS) wr = 0;
+  }
+  sgm_wait<0>();
 }
 
 static const int SGM_RV[8] = {+1, -1, 0, 0, +1, +1, -1, -1};
@@ -173,37 +293,67 @@ static const int SGM_RU[8] = {0, 0, +1, -1, -1, +1, +1, -1};
 
 template <int VPL, int PF, bool VEC>
 static int launch_sgm(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, const sgm_geom& g, int D,
-                      int thr, float redu, int mode) {
+                      int thr, float redu, int mode, int16_t* disp) {
   int grid = sm_div_up(g.nLines, SGM_WARPS);
   if (mode == 0)
-    SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 0>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu);
+    SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 0>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu, disp);
+  else if (mode == 1)
+    SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 1>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu, disp);
   else
-    SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 1>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu);
+    SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 2>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu, disp);
   return SM_OK;
 }
 
-int smi_sgm_path_packed(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
-                        int corDifThres, int reduCoeffi1, int mode, float* d_out) {
+template <int VPL, int MODE>
+static int launch_sgm_h1(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, int H, int W, int mu, int D,
+                         int thr, float redu, int16_t* disp) {
+  const size_t smem = (size_t)(SGM_NSTG + 1) * (32 * VPL * 4 * (MODE >= 1 ? 2 : 1) + 128);
+  SM_CUDA(cudaFuncSetAttribute(k_sgm_path_h<VPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SM_LAUNCH(ctx, (k_sgm_path_h<VPL, MODE>), H, 32, smem, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  return SM_OK;
+}
+template <int VPL>
+static int launch_sgm_h(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, int H, int W, int mu, int D,
+                        int thr, float redu, int mode, int16_t* disp) {
+  if (mode == 0) return launch_sgm_h1<VPL, 0>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  if (mode == 1) return launch_sgm_h1<VPL, 1>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  return launch_sgm_h1<VPL, 2>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+}
+
+// mode 0: d_out = Lr; 1: d_out += Lr; 2: d_out += Lr and d_disp = WTA of the finished sum
+int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
+                         int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp) {
   sgm_geom g;
   g.H = H; g.W = W; g.mv = -SGM_RV[path]; g.mu = -SGM_RU[path];
   g.nLines = g.mv == 0 ? H : (g.mu == 0 ? W : W + H - 1);
   const float redu = (float)reduCoeffi1;
   const bool vec = (D % 4 == 0) && (((uintptr_t)d_vol | (uintptr_t)d_out) % 16 == 0);
   const int vpl = D <= 32 ? 1 : D <= 64 ? 2 : D <= 128 ? 4 : D <= 256 ? 8 : 16;
+  static const int staged_env = getenv("SM_SGM_STAGED") ? atoi(getenv("SM_SGM_STAGED")) : 1;   // tuning switch
+  if (g.mv == 0 && vec && vpl >= 4 && staged_env) {   // horizontal: few, contiguous lines -> cp.async staged variant
+    if (vpl == 4) return launch_sgm_h<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
+    if (vpl == 8) return launch_sgm_h<8>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
+    return launch_sgm_h<16>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
+  }
   // 16-byte loads need D % 4 == 0 (then every float4 of a run is wholly inside or outside [0,D))
   switch (vpl) {
-    case 1: return launch_sgm<1, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
-    case 2: return launch_sgm<2, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
+    case 1: return launch_sgm<1, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+    case 2: return launch_sgm<2, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
     case 4:
-      if (vec) return launch_sgm<4, 8, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
-      return launch_sgm<4, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
+      if (vec) return launch_sgm<4, 8, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+      return launch_sgm<4, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
     case 8:
-      if (vec) return launch_sgm<8, 4, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
-      return launch_sgm<8, 4, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
+      if (vec) return launch_sgm<8, 4, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+      return launch_sgm<8, 4, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
     default:
-      if (vec) return launch_sgm<16, 2, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
-      return launch_sgm<16, 2, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode);
+      if (vec) return launch_sgm<16, 2, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+      return launch_sgm<16, 2, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
   }
+}
+
+int smi_sgm_path_packed(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
+                        int corDifThres, int reduCoeffi1, int mode, float* d_out) {
+  return smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, path, corDifThres, reduCoeffi1, mode, d_out, nullptr);
 }
 
 extern "C" int sm_sgm_path(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int path,
