@@ -92,6 +92,7 @@ int sm_host_free_pinned(void* h_ptr);
 int sm_memcpy_h2d(sm_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int sm_memcpy_d2h(sm_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 int sm_memset(sm_ctx* ctx, void* d_dst, int byte, size_t bytes);
+int sm_memcpy_d2d(sm_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
 /* number of kernels this ctx has launched since creation (bench: gpu_launches) */
 long long sm_ctx_launch_count(sm_ctx* ctx);
 
@@ -172,6 +173,26 @@ int sm_tree_filter_f64(sm_ctx* ctx, double* d_cost, int H, int W, int D, const i
 /* StereoMatching::NL (stereoMatching.cpp:4892-4917): aggreCV(vm[0]),
  * aggreCV(ones), divide.  In place on d_vol. */
 int sm_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, int H, int W, int D);
+
+/* ---- Yang's own driver: qx_nonlocal_cost_aggregation (float64 volumes [H][W][D]) --- */
+/* compute_gradient (NL/qx_nonlocal_cost_aggregation.cpp:219-236). */
+int sm_nlca_gradient(sm_ctx* ctx, const uint8_t* d_img, int H, int W, float* d_grad);
+/* matching_cost_from_color_and_gradient (NL/qx_nonlocal_cost_aggregation.cpp:190-218):
+ * w*min(mean|dRGB|, maxc) + (1-w)*min(|dgrad|, maxg); class defaults 7, 2, 0.11. */
+int sm_nlca_cost(sm_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int H, int W, int D,
+                 double max_color_difference, double max_gradient_difference, double weight_on_color,
+                 double* d_vol);
+/* qx_stereo_flip_corr_vol (NL/qx_basic.cpp:577-588). */
+int sm_nlca_flip(sm_ctx* ctx, const double* d_vol, int H, int W, int D, double* d_vol_right);
+/* depth_best_cost / vec_min_pos (NL/qx_basic.cpp:589-602): first minimum as u8 (D <= 256). */
+int sm_depth_best_cost(sm_ctx* ctx, const double* d_vol, int H, int W, int D, uint8_t* d_depth);
+/* qx_detect_occlusion_left_right (NL/qx_basic.cpp:603-624). */
+int sm_nlca_occlusion(sm_ctx* ctx, const uint8_t* d_disp_left, const uint8_t* d_disp_right, int H, int W,
+                      uint8_t* d_mask);
+/* disparity()'s refinement volume (NL/qx_nonlocal_cost_aggregation.cpp:92-99):
+ * 0 on occluded pixels, |disp - d| elsewhere. */
+int sm_nlca_refine_cost(sm_ctx* ctx, const uint8_t* d_disp, const uint8_t* d_mask, int H, int W, int D,
+                        double* d_vol);
 
 /* ---- optimisation: SGM ---------------------------------------------------- */
 /* costScan + updateCost<float> for ONE path (stereoMatching.cpp:1983-2029,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "sm_memcpy_h2d": ([_P, _P, _P, _Z], _I),
     "sm_memcpy_d2h": ([_P, _P, _P, _Z], _I),
     "sm_memset": ([_P, _P, _I, _Z], _I),
+    "sm_memcpy_d2d": ([_P, _P, _P, _Z], _I),
     "sm_ctx_launch_count": ([_P], _LL),
     "sm_bgr2gray": ([_P, _P, _I, _I, _P], _I),
     "sm_census": ([_P, _P, _I, _I, _I, _P], _I),
@@ -68,6 +69,12 @@ SIGNATURES = {
     "sm_tree_filter": ([_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _D], _I),
     "sm_tree_filter_f64": ([_P, _P, _I, _I, _I, _P, _P, _P, _P, _D], _I),
     "sm_nl": ([_P, _P, _P, _I, _I, _I], _I),
+    "sm_nlca_gradient": ([_P, _P, _I, _I, _P], _I),
+    "sm_nlca_cost": ([_P, _P, _P, _I, _I, _I, _D, _D, _D, _P], _I),
+    "sm_nlca_flip": ([_P, _P, _I, _I, _I, _P], _I),
+    "sm_depth_best_cost": ([_P, _P, _I, _I, _I, _P], _I),
+    "sm_nlca_occlusion": ([_P, _P, _P, _I, _I, _P], _I),
+    "sm_nlca_refine_cost": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "sm_sgm_path": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_sgm": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_vol_accumulate": ([_P, _P, _P, _Z], _I),
@@ -331,6 +338,60 @@ class Ctx:
     def vol_accumulate(self, acc, x):
         check(self.L.sm_vol_accumulate(self.h, _ptr(acc), _ptr(x), acc.numel()))
         return acc
+
+    # -- Yang's driver (float64 volumes)
+    def nlca_gradient(self, img):
+        H, W, _ = img.shape
+        out = self.empty((H, W), self.torch.float32)
+        check(self.L.sm_nlca_gradient(self.h, _ptr(img), H, W, _ptr(out)))
+        return out
+
+    def nlca_cost(self, left, right, D, maxc=7.0, maxg=2.0, wc=0.11):
+        H, W, _ = left.shape
+        out = self.empty((H, W, D), self.torch.float64)
+        check(self.L.sm_nlca_cost(self.h, _ptr(left), _ptr(right), H, W, D, maxc, maxg, wc, _ptr(out)))
+        return out
+
+    def nlca_flip(self, vol):
+        H, W, D = vol.shape
+        out = self.torch.empty_like(vol)
+        check(self.L.sm_nlca_flip(self.h, _ptr(vol), H, W, D, _ptr(out)))
+        return out
+
+    def depth_best_cost(self, vol):
+        H, W, D = vol.shape
+        out = self.empty((H, W), self.torch.uint8)
+        check(self.L.sm_depth_best_cost(self.h, _ptr(vol), H, W, D, _ptr(out)))
+        return out
+
+    def nlca_occlusion(self, dl, dr):
+        H, W = dl.shape
+        out = self.torch.empty_like(dl)
+        check(self.L.sm_nlca_occlusion(self.h, _ptr(dl), _ptr(dr), H, W, _ptr(out)))
+        return out
+
+    def nlca_refine_cost(self, disp, mask, D):
+        H, W = disp.shape
+        out = self.empty((H, W, D), self.torch.float64)
+        check(self.L.sm_nlca_refine_cost(self.h, _ptr(disp), _ptr(mask), H, W, D, _ptr(out)))
+        return out
+
+    def nlca_disparity(self, left, right, D, sigma=0.1, post=False):
+        """qx_nonlocal_cost_aggregation::matching_cost + disparity composed from the C entry points."""
+        H, W, _ = left.shape
+        cost = self.nlca_cost(left, right, D)
+        treeL = self.mst_build(left)
+        vol = self.tree_filter_f64(cost.clone().view(H * W, D), treeL, H, W, sigma).view(H, W, D)
+        disp = self.median_u8(self.depth_best_cost(vol), 2)
+        if not post:
+            return disp
+        treeR = self.mst_build(right)
+        volR = self.tree_filter_f64(self.nlca_flip(cost).view(H * W, D), treeR, H, W, sigma).view(H, W, D)
+        dr = self.median_u8(self.depth_best_cost(volR), 2)
+        mask = self.nlca_occlusion(disp, dr)
+        ref = self.nlca_refine_cost(disp, mask, D)
+        ref = self.tree_filter_f64(ref.view(H * W, D), treeL, H, W, sigma / 2).view(H, W, D)
+        return self.median_u8(self.depth_best_cost(ref), 2)
 
     def nl(self, bgrL, vol):
         H, W, D = vol.shape

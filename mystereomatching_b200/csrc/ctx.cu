@@ -156,6 +156,12 @@ extern "C" int sm_memset(sm_ctx* ctx, void* d_dst, int byte, size_t bytes) {
   return SM_OK;
 }
 
+extern "C" int sm_memcpy_d2d(sm_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+  SM_CHECK_ARG(ctx && d_dst && d_src);
+  SM_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return SM_OK;
+}
+
 int sm_scratch_get(sm_ctx* ctx, int slot, size_t bytes, void** out) {
   sm_scratch& s = ctx->scr[slot];
   if (s.cap < bytes) {

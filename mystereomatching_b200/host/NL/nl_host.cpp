@@ -104,3 +104,77 @@ void NLCCA::aggreCV(const Mat& lImg, const Mat& rImg, const int maxDis, Mat& cos
                     (const int32_t*)rk.p, (const int32_t*)ord.p, 0.1), "sm_tree_filter");   // sigma: NL/NLCCA.cpp:33
   d2h(c, costVol.data, vol.p, vb);
 }
+
+// ------------------------------------------------------------------ qx_nonlocal_cost_aggregation
+#include "qx_nonlocal_cost_aggregation.h"
+
+qx_nonlocal_cost_aggregation::qx_nonlocal_cost_aggregation() {}
+qx_nonlocal_cost_aggregation::~qx_nonlocal_cost_aggregation() { clean(); }
+void qx_nonlocal_cost_aggregation::clean() {
+  if (!ctx_) return;
+  void* ptrs[] = {d_left_, d_right_, d_disp_, d_disp2_, d_dispR_, d_mask_, d_wt_[0], d_wt_[1], d_cost_, d_costR_, d_vol_,
+                  d_parent_[0], d_parent_[1], d_rank_[0], d_rank_[1], d_order_[0], d_order_[1]};
+  for (void* p : ptrs) sm_dev_free(ctx_, p);
+  sm_ctx_destroy(ctx_);
+  ctx_ = nullptr;
+}
+int qx_nonlocal_cost_aggregation::init(int h, int w, int nr_plane, double sigma_range, double max_color_difference,
+                                       double max_gradient_difference, double weight_on_color) {
+  clean();
+  if (nr_plane > 256) throw std::runtime_error("qx_nonlocal_cost_aggregation: disparities are unsigned char (nr_plane <= 256)");
+  m_h = h; m_w = w; m_nr_plane = nr_plane; m_sigma_range = sigma_range;
+  m_max_color_difference = max_color_difference; m_max_gradient_difference = max_gradient_difference;
+  m_weight_on_color = weight_on_color;
+  ok(sm_ctx_create(&ctx_, 0, nullptr), "sm_ctx_create");
+  const size_t np = (size_t)h * w, nv = np * nr_plane * sizeof(double);
+  auto A = [&](void** p, size_t n) { ok(sm_dev_alloc(ctx_, p, n), "sm_dev_alloc"); };
+  A((void**)&d_left_, np * 3); A((void**)&d_right_, np * 3);
+  A((void**)&d_disp_, np); A((void**)&d_disp2_, np); A((void**)&d_dispR_, np); A((void**)&d_mask_, np);
+  A((void**)&d_cost_, nv); A((void**)&d_costR_, nv); A((void**)&d_vol_, nv);
+  for (int i = 0; i < 2; i++) {
+    A((void**)&d_wt_[i], np); A((void**)&d_parent_[i], np * 4); A((void**)&d_rank_[i], np * 4); A((void**)&d_order_[i], np * 4);
+  }
+  return 0;
+}
+int qx_nonlocal_cost_aggregation::matching_cost(unsigned char*** left, unsigned char*** right) {
+  const size_t np = (size_t)m_h * m_w;
+  h2d(ctx_, d_left_, left[0][0], np * 3);
+  h2d(ctx_, d_right_, right[0][0], np * 3);
+  ok(sm_nlca_cost(ctx_, d_left_, d_right_, m_h, m_w, m_nr_plane, m_max_color_difference, m_max_gradient_difference,
+                  m_weight_on_color, d_cost_), "sm_nlca_cost");
+  ok(sm_nlca_flip(ctx_, d_cost_, m_h, m_w, m_nr_plane, d_costR_), "sm_nlca_flip");
+  ok(sm_mst_build(ctx_, d_left_, m_h, m_w, 3, d_parent_[0], d_wt_[0], d_rank_[0], d_order_[0]), "sm_mst_build");
+  ok(sm_mst_build(ctx_, d_right_, m_h, m_w, 3, d_parent_[1], d_wt_[1], d_rank_[1], d_order_[1]), "sm_mst_build");
+  return 0;
+}
+void qx_nonlocal_cost_aggregation::filter(double* d_vol, bool right_tree, double sigma) {
+  const int t = right_tree ? 1 : 0;
+  ok(sm_tree_filter_f64(ctx_, d_vol, m_h, m_w, m_nr_plane, d_parent_[t], d_wt_[t], d_rank_[t], d_order_[t], sigma),
+     "sm_tree_filter_f64");
+}
+int qx_nonlocal_cost_aggregation::disparity(unsigned char** disparity, bool use_nonlocal_post_processing) {
+  const int radius = 2;
+  const size_t np = (size_t)m_h * m_w, nv = np * m_nr_plane * sizeof(double);
+  auto copy = [&](double* dst, const double* src) {   // image_copy(m_cost_vol, ...): device to device
+    ok(sm_memcpy_d2d(ctx_, dst, src, nv), "sm_memcpy_d2d");
+  };
+  copy(d_vol_, d_cost_);
+  filter(d_vol_, false, m_sigma_range);
+  ok(sm_depth_best_cost(ctx_, d_vol_, m_h, m_w, m_nr_plane, d_disp2_), "sm_depth_best_cost");
+  ok(sm_median_u8(ctx_, d_disp2_, d_disp_, m_h, m_w, radius, 1), "sm_median_u8");
+  if (use_nonlocal_post_processing) {
+    copy(d_vol_, d_costR_);
+    filter(d_vol_, true, m_sigma_range);
+    ok(sm_depth_best_cost(ctx_, d_vol_, m_h, m_w, m_nr_plane, d_disp2_), "sm_depth_best_cost");
+    ok(sm_median_u8(ctx_, d_disp2_, d_dispR_, m_h, m_w, radius, 1), "sm_median_u8");
+    ok(sm_nlca_occlusion(ctx_, d_disp_, d_dispR_, m_h, m_w, d_mask_), "sm_nlca_occlusion");
+    ok(sm_nlca_refine_cost(ctx_, d_disp_, d_mask_, m_h, m_w, m_nr_plane, d_vol_), "sm_nlca_refine_cost");
+    filter(d_vol_, false, m_sigma_range / 2);   // m_tf.update_table(m_sigma_range / 2)
+    ok(sm_depth_best_cost(ctx_, d_vol_, m_h, m_w, m_nr_plane, d_disp2_), "sm_depth_best_cost");
+    ok(sm_median_u8(ctx_, d_disp2_, d_disp_, m_h, m_w, radius, 1), "sm_median_u8");
+  }
+  d2h(ctx_, disparity[0], d_disp_, np);
+  return 0;
+}
+void qx_nonlocal_cost_aggregation::get_cost_volume(double* out) { d2h(ctx_, out, d_cost_, (size_t)m_h * m_w * m_nr_plane * 8); }
+void qx_nonlocal_cost_aggregation::get_cost_volume_right(double* out) { d2h(ctx_, out, d_costR_, (size_t)m_h * m_w * m_nr_plane * 8); }

@@ -211,4 +211,130 @@ void orc_nl(const u8* bgrL, int H, int W, int D, float* vol, i16* disp) {
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Yang's own driver, qx_nonlocal_cost_aggregation (API surface named by the north star; pinned against the
+// reference's compiled class through oracle/_ref: qxref_nlca).
+// ---------------------------------------------------------------------------
+// rgb_2_gray (NL/qx_basic.h:72): (unsigned char)(0.299*in[0] + 0.587*in[1] + 0.114*in[2] + 0.5), double arithmetic.
+static inline u8 qx_gray(const u8* in) { return (u8)(0.299 * in[0] + 0.587 * in[1] + 0.114 * in[2] + 0.5); }
+
+// compute_gradient (NL/qx_nonlocal_cost_aggregation.cpp:219-236): central x-difference of the gray image + 127.5,
+// one-sided (un-halved) at both borders.
+void orc_nlca_gradient(const u8* img, int H, int W, float* grad) {
+  for (int y = 0; y < H; y++) {
+    const u8* row = img + (size_t)y * W * 3;
+    float* g = grad + (size_t)y * W;
+    float gray, gray_minus, gray_plus;
+    gray_minus = qx_gray(row);
+    gray = gray_plus = qx_gray(row + 3);
+    g[0] = gray_plus - gray_minus + 127.5;
+    for (int x = 1; x < W - 1; x++) {
+      gray_plus = qx_gray(row + 3 * (x + 1));
+      g[x] = 0.5 * (gray_plus - gray_minus) + 127.5;
+      gray_minus = gray;
+      gray = gray_plus;
+    }
+    g[W - 1] = gray_plus - gray_minus + 127.5;
+  }
+}
+
+// matching_cost_from_color_and_gradient (NL/qx_nonlocal_cost_aggregation.cpp:190-218): for plane i the right image
+// and gradient are shifted by i pixels (columns < i replicate column 0); cost = w*min(mean|dRGB|, maxc) +
+// (1-w)*min(|dgrad|, maxg), double.
+void orc_nlca_cost(const u8* left, const u8* right, int H, int W, int D, double maxc, double maxg, double wc,
+                   double* vol) {
+  std::vector<float> gl((size_t)H * W), gr((size_t)H * W);
+  orc_nlca_gradient(left, H, W, gl.data());
+  orc_nlca_gradient(right, H, W, gr.data());
+  const double wci = 1 - wc;
+  for (int i = 0; i < D; i++)
+    for (int y = 0; y < H; y++)
+      for (int x = 0; x < W; x++) {
+        const int xs = x >= i ? x - i : 0;
+        const u8* l = left + ((size_t)y * W + x) * 3;
+        const u8* r = right + ((size_t)y * W + xs) * 3;
+        double cost = 0;
+        for (int c = 0; c < 3; c++) cost += std::abs((int)l[c] - (int)r[c]);
+        cost = std::min(cost / 3, maxc);
+        double cg = std::min((double)std::abs(gl[(size_t)y * W + x] - gr[(size_t)y * W + xs]), maxg);
+        vol[((size_t)y * W + x) * D + i] = wc * cost + wci * cg;
+      }
+}
+
+// qx_stereo_flip_corr_vol (NL/qx_basic.cpp:577-588): right-view volume from the left one along the diagonal; where
+// x+d leaves the image the previous plane's value is repeated.
+void orc_flip_vol(const double* vol, int H, int W, int D, double* volR) {
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++)
+      for (int d = 0; d < D; d++) {
+        size_t o = ((size_t)y * W + x) * D + d;
+        if (x + d < W) volR[o] = vol[((size_t)y * W + x + d) * D + d];
+        else volR[o] = volR[o - 1];
+      }
+}
+
+// depth_best_cost / vec_min_pos (NL/qx_basic.cpp:589-602): first minimum, as unsigned char.
+void orc_depth_best_cost(const double* vol, int H, int W, int D, u8* depth) {
+  for (size_t p = 0; p < (size_t)H * W; p++) {
+    const double* in = vol + p * D;
+    double mv = in[0];
+    int mp = 0;
+    for (int i = 1; i < D; i++)
+      if (in[i] < mv) { mv = in[i]; mp = i; }
+    depth[p] = (u8)mp;
+  }
+}
+
+// qx_detect_occlusion_left_right (NL/qx_basic.cpp:603-624): 255 where the left disparity is 0, maps outside the
+// image, or differs from the right map at the matched column.
+void orc_detect_occlusion(const u8* dl, const u8* dr, int H, int W, u8* mask) {
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      int d = dl[(size_t)y * W + x], xr = x - d;
+      u8 m = 0;
+      if (xr >= 0) { if (d == 0 || std::abs(d - (int)dr[(size_t)y * W + xr]) >= 1) m = 255; }
+      else m = 255;
+      mask[(size_t)y * W + x] = m;
+    }
+}
+
+static void nlca_filter(double* vol, int N, int D, const u8* img, int H, int W, double sigma) {
+  std::vector<int> parent(N), rank(N), nch(N), ch(3 * (size_t)N), order(N);
+  std::vector<u8> wt(N);
+  orc_mst(img, H, W, 3, parent.data(), wt.data(), rank.data(), nch.data(), ch.data(), order.data(), nullptr);
+  double table[256];
+  orc_tree_table(sigma, table);
+  std::vector<double> tmp((size_t)N * D);
+  orc_tree_filter(vol, tmp.data(), N, D, parent.data(), wt.data(), nch.data(), ch.data(), order.data(), table);
+}
+
+// init + matching_cost + disparity (NL/qx_nonlocal_cost_aggregation.cpp:22-109) with the class defaults
+// (max colour difference 7, max gradient difference 2, weight on colour 0.11).  post = the optional non-local
+// refinement: right disparity, occlusion mask, |d - disp| volume on the stable pixels, sigma/2, filter, WTA, median.
+void orc_nlca_disparity(const u8* left, const u8* right, int H, int W, int D, double sigma, int post, u8* disp) {
+  const int N = H * W;
+  std::vector<double> cost((size_t)N * D), vol((size_t)N * D), costR((size_t)N * D);
+  orc_nlca_cost(left, right, H, W, D, 7, 2, 0.11, cost.data());
+  orc_flip_vol(cost.data(), H, W, D, costR.data());
+  std::vector<u8> d0(N), dr(N), mask(N);
+  vol = cost;
+  nlca_filter(vol.data(), N, D, left, H, W, sigma);
+  orc_depth_best_cost(vol.data(), H, W, D, d0.data());
+  orc_ctmf(d0.data(), disp, W, H, W, W, 2, 1);
+  if (!post) return;
+  vol = costR;
+  nlca_filter(vol.data(), N, D, right, H, W, sigma);
+  orc_depth_best_cost(vol.data(), H, W, D, d0.data());
+  orc_ctmf(d0.data(), dr.data(), W, H, W, W, 2, 1);
+  orc_detect_occlusion(disp, dr.data(), H, W, mask.data());
+  std::fill(vol.begin(), vol.end(), 0.0);
+  for (int p = 0; p < N; p++)
+    if (!mask[p])
+      for (int d = 0; d < D; d++) vol[(size_t)p * D + d] = std::abs((int)disp[p] - d);
+  nlca_filter(vol.data(), N, D, left, H, W, sigma / 2);
+  orc_depth_best_cost(vol.data(), H, W, D, d0.data());
+  orc_ctmf(d0.data(), disp, W, H, W, W, 2, 1);
+}
+
 }  // extern "C"

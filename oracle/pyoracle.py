@@ -82,6 +82,12 @@ def lib():
         "orc_tree_filter": ([f64p, f64p, I, I, i32p, u8p, i32p, i32p, i32p, f64p], None),
         "orc_nl_aggre": ([u8p, I, I, I, f32p], None),
         "orc_nl": ([u8p, I, I, I, f32p, P], None),
+        "orc_nlca_gradient": ([u8p, I, I, f32p], None),
+        "orc_nlca_cost": ([u8p, u8p, I, I, I, C.c_double, C.c_double, C.c_double, f64p], None),
+        "orc_flip_vol": ([f64p, I, I, I, f64p], None),
+        "orc_depth_best_cost": ([f64p, I, I, I, u8p], None),
+        "orc_detect_occlusion": ([u8p, u8p, I, I, u8p], None),
+        "orc_nlca_disparity": ([u8p, u8p, I, I, I, C.c_double, I, u8p], None),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -103,7 +109,8 @@ def ref_lib():
     L.qxref_ctmf.argtypes = [u8p, u8p, I, I, I, I, I, I, C.c_ulong]
     L.qxref_mst.argtypes = [u8p, I, I, I, i32p, u8p, i32p, i32p, i32p, i32p]
     L.qxref_tree_filter.argtypes = [u8p, I, I, I, C.c_double, f64p, f64p]
-    for f in (L.qxref_ctmf, L.qxref_mst, L.qxref_tree_filter):
+    L.qxref_nlca.argtypes = [u8p, u8p, I, I, I, C.c_double, I, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for f in (L.qxref_ctmf, L.qxref_mst, L.qxref_tree_filter, L.qxref_nlca):
         f.restype = None
     _REF = L
     return L
@@ -312,3 +319,59 @@ def ref_tree_filter(bgr, vol64, sigma=0.1):
     tmp = np.empty_like(cost)
     L.qxref_tree_filter(np.ascontiguousarray(bgr), H, W, D, sigma, cost, tmp)
     return cost
+
+
+# ----------------------------------------------------------------------------- Yang's driver (qx_nonlocal_cost_aggregation)
+def nlca_gradient(img):
+    H, W, _ = img.shape
+    out = np.empty((H, W), np.float32)
+    lib().orc_nlca_gradient(np.ascontiguousarray(img), H, W, out)
+    return out
+
+
+def nlca_cost(left, right, D, maxc=7.0, maxg=2.0, wc=0.11):
+    H, W, _ = left.shape
+    out = np.empty((H, W, D), np.float64)
+    lib().orc_nlca_cost(np.ascontiguousarray(left), np.ascontiguousarray(right), H, W, D, maxc, maxg, wc, out)
+    return out
+
+
+def flip_vol(vol):
+    H, W, D = vol.shape
+    out = np.empty_like(vol)
+    lib().orc_flip_vol(np.ascontiguousarray(vol), H, W, D, out)
+    return out
+
+
+def depth_best_cost(vol):
+    H, W, D = vol.shape
+    out = np.empty((H, W), np.uint8)
+    lib().orc_depth_best_cost(np.ascontiguousarray(vol), H, W, D, out)
+    return out
+
+
+def detect_occlusion(dl, dr):
+    H, W = dl.shape
+    out = np.empty((H, W), np.uint8)
+    lib().orc_detect_occlusion(np.ascontiguousarray(dl), np.ascontiguousarray(dr), H, W, out)
+    return out
+
+
+def nlca_disparity(left, right, D, sigma=0.1, post=False):
+    H, W, _ = left.shape
+    out = np.empty((H, W), np.uint8)
+    lib().orc_nlca_disparity(np.ascontiguousarray(left), np.ascontiguousarray(right), H, W, D, sigma, int(post), out)
+    return out
+
+
+def ref_nlca(left, right, D, sigma=0.1, post=False, want_disp=True):
+    """The reference's own qx_nonlocal_cost_aggregation (compiled into oracle/_ref)."""
+    L = ref_lib()
+    H, W, _ = left.shape
+    cost = np.empty((H, W, D), np.float64)
+    costR = np.empty((H, W, D), np.float64)
+    grad = np.empty((H, W), np.float32)
+    disp = np.empty((H, W), np.uint8) if want_disp else None
+    L.qxref_nlca(np.ascontiguousarray(left), np.ascontiguousarray(right), H, W, D, sigma, int(post), cost.ctypes.data,
+                 costR.ctypes.data, grad.ctypes.data, disp.ctypes.data if want_disp else None)
+    return dict(cost=cost, cost_right=costR, grad_left=grad, disp=disp)

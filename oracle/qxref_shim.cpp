@@ -7,6 +7,7 @@
 #include "qx_mst_kruskals_image.h"
 #include "qx_tree_filter.h"
 #include "ctmf.h"
+#include "qx_nonlocal_cost_aggregation.h"
 
 // qx_timer lives in NL/qx_basic.cpp, which needs <windows.h>; it is only used
 // for (disabled) prints, so a do-nothing definition stands in for that file.
@@ -49,5 +50,30 @@ void qxref_tree_filter(unsigned char* image, int h, int w, int nr_plane, double 
   tf.init(h, w, 3, sigma, 4);
   tf.build_tree(image);
   tf.filter(cost, tmp, nr_plane);
+}
+
+// Yang's own driver class, qx_nonlocal_cost_aggregation (NL/qx_nonlocal_cost_aggregation.cpp:22-109, 190-236):
+// init + matching_cost [+ disparity].  left/right: h*w*3 bytes.  Outputs (nullable): the raw left cost volume and
+// its right-view flip (double [h][w][nr_plane]), the x-gradients (float [h][w]) and the final disparity map.
+void qxref_nlca(unsigned char* left, unsigned char* right, int h, int w, int nr_plane, double sigma, int post,
+                double* cost_out, double* cost_right_out, float* grad_left_out, unsigned char* disp_out) {
+  unsigned char*** l = qx_allocu_3(h, w, 3);
+  unsigned char*** r = qx_allocu_3(h, w, 3);
+  memcpy(l[0][0], left, (size_t)h * w * 3);
+  memcpy(r[0][0], right, (size_t)h * w * 3);
+  qx_nonlocal_cost_aggregation nl;
+  nl.init(h, w, nr_plane, sigma);
+  nl.matching_cost(l, r);
+  if (cost_out) memcpy(cost_out, nl.m_cost_vol_backup[0][0], sizeof(double) * h * w * nr_plane);
+  if (cost_right_out) memcpy(cost_right_out, nl.m_cost_vol_right[0][0], sizeof(double) * h * w * nr_plane);
+  if (grad_left_out) memcpy(grad_left_out, nl.m_gradient_left[0], sizeof(float) * h * w);
+  if (disp_out) {
+    unsigned char** d = qx_allocu(h, w);
+    nl.disparity(d, post != 0);
+    memcpy(disp_out, d[0], (size_t)h * w);
+    qx_freeu(d);
+  }
+  qx_freeu_3(l);
+  qx_freeu_3(r);
 }
 }

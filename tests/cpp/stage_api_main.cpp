@@ -12,6 +12,7 @@
 
 #include "NL/NLCCA.h"
 #include "NL/ctmf.h"
+#include "NL/qx_nonlocal_cost_aggregation.h"
 #include "NL/qx_tree_filter.h"
 #include "stereoMatching.h"
 
@@ -65,6 +66,23 @@ int main(int argc, char** argv) {
       NLCCA nl;
       nl.aggreCV(I1c, I2c, D, vol);
       dump(out + ".aggre.f32", vol.data, npix * D * 4);
+      // Yang's driver class, used as in his own main(): init, matching_cost, disparity
+      unsigned char*** l3 = qx_allocu_3(H, W, 3);
+      unsigned char*** r3 = qx_allocu_3(H, W, 3);
+      memcpy(l3[0][0], I1c.data, npix * 3);
+      memcpy(r3[0][0], I2c.data, npix * 3);
+      unsigned char** disp = qx_allocu(H, W);
+      qx_nonlocal_cost_aggregation nlca;
+      nlca.init(H, W, D);
+      nlca.matching_cost(l3, r3);
+      std::vector<double> cv(npix * D);
+      nlca.get_cost_volume(cv.data());
+      dump(out + ".nlca_cost.f64", cv.data(), cv.size() * 8);
+      nlca.disparity(disp, false);
+      dump(out + ".nlca_disp.u8", disp[0], npix);
+      nlca.disparity(disp, true);
+      dump(out + ".nlca_disp_post.u8", disp[0], npix);
+      qx_freeu(disp); qx_freeu_3(l3); qx_freeu_3(r3);
       return 0;
     }
     StereoMatching::costcalculation = "ADCensus";

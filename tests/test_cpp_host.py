@@ -28,6 +28,8 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
                 "void StereoMatching::calHorVerDis<unsigned char>(", "void StereoMatching::calArms<unsigned char>(",
                 "NLCCA::aggreCV(", "qx_tree_filter::filter(double*, double*, int)", "qx_tree_filter::build_tree(",
+                "qx_nonlocal_cost_aggregation::matching_cost(unsigned char***, unsigned char***)",
+                "qx_nonlocal_cost_aggregation::disparity(unsigned char**, bool)", "qx_nonlocal_cost_aggregation::init(",
                 "ctmf"):
         assert sym in out, sym
 
@@ -78,7 +80,7 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
 
 @pytest.mark.gpu
 def test_cpp_nl_surface_matches_oracle(tmp_path):
-    H, W, D = 40, 56, 6
+    H, W, D = 64, 80, 6          # ctmf r = 2 in the reference needs h*w >= 5*544
     pair = synth.make_pair(H, W, 8, "texture_warped", seed=4)
     prefix, _ = _run(tmp_path, pair, D, 4, "nl")
     img = pair["bgrL"]
@@ -98,6 +100,12 @@ def test_cpp_nl_surface_matches_oracle(tmp_path):
     vol = ((i * np.uint64(2654435761)) % np.uint64(1000)).astype(np.float32) / np.float32(1000.0)
     ag = po.nl_aggre(img, vol.reshape(H, W, D))
     assert np.array_equal(np.fromfile(prefix + ".aggre.f32", np.float32).reshape(H, W, D), ag)
+    # qx_nonlocal_cost_aggregation: init / matching_cost / disparity
+    L, R = pair["bgrL"], pair["bgrR"]
+    assert np.array_equal(np.fromfile(prefix + ".nlca_cost.f64", np.float64).reshape(H, W, D), po.nlca_cost(L, R, D))
+    assert np.array_equal(np.fromfile(prefix + ".nlca_disp.u8", np.uint8).reshape(H, W), po.nlca_disparity(L, R, D))
+    assert np.array_equal(np.fromfile(prefix + ".nlca_disp_post.u8", np.uint8).reshape(H, W),
+                          po.nlca_disparity(L, R, D, post=True))
 
 
 @pytest.mark.gpu

@@ -334,3 +334,29 @@ def test_pipeline_nl_matches_oracle_composition(ctx):
     d = po.median3_i16(d)
     assert np.array_equal(whole, d)            # the oracle's own NL chain is this composition
     assert (got == d).mean() >= 0.995
+
+
+# ---------------------------------------------------------------- Yang's driver (qx_nonlocal_cost_aggregation)
+@pytest.mark.timeout(180)
+def test_nlca_stages_bit_exact(ctx, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "nlca_ref.npz"))      # outputs of the reference's own compiled class
+    L, R, D = g["left"], g["right"], int(g["D"])
+    dL, dR = ctx.dev(L), ctx.dev(R)
+    assert np.array_equal(ctx.nlca_gradient(dL).cpu().numpy(), g["grad_left"])
+    cost = ctx.nlca_cost(dL, dR, D)
+    assert np.array_equal(cost.cpu().numpy(), g["cost"])
+    assert np.array_equal(ctx.nlca_flip(cost).cpu().numpy(), g["cost_right"])
+    assert np.array_equal(ctx.nlca_disparity(dL, dR, D).cpu().numpy(), g["disp"])
+    assert np.array_equal(ctx.nlca_disparity(dL, dR, D, post=True).cpu().numpy(), g["disp_post"])
+    # helpers against the oracle on random data
+    rng = np.random.default_rng(6)
+    vol = rng.integers(0, 5, (33, 47, 9)).astype(np.float64)
+    assert np.array_equal(ctx.depth_best_cost(ctx.dev(vol)).cpu().numpy(), po.depth_best_cost(vol))
+    assert np.array_equal(ctx.nlca_flip(ctx.dev(vol)).cpu().numpy(), po.flip_vol(vol))
+    dl = rng.integers(0, 9, (33, 47)).astype(np.uint8)
+    dr = rng.integers(0, 9, (33, 47)).astype(np.uint8)
+    m = po.detect_occlusion(dl, dr)
+    assert np.array_equal(ctx.nlca_occlusion(ctx.dev(dl), ctx.dev(dr)).cpu().numpy(), m)
+    ref = np.where(m[..., None] != 0, 0.0, np.abs(dl[..., None].astype(np.int64) - np.arange(9)).astype(np.float64))
+    assert np.array_equal(ctx.nlca_refine_cost(ctx.dev(dl), ctx.dev(m), 9).cpu().numpy(), ref)

@@ -297,3 +297,37 @@ def test_pipeline_recovers_synthetic_disparity():
     dl4, _, _, _ = po.pipeline(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], p)
     po.lib().orc_set_threads(1)
     assert np.array_equal(dl, dl4)   # thread count never changes a result
+
+
+# ---------------------------------------------------------------- Yang's driver class: pinned against the compiled reference
+@pytest.fixture(scope="module")
+def nlcag(golden_dir):
+    return np.load(os.path.join(golden_dir, "nlca_ref.npz"))
+
+
+def test_nlca_cost_and_flip_match_reference(nlcag):
+    L, R, D = nlcag["left"], nlcag["right"], int(nlcag["D"])
+    assert np.array_equal(po.nlca_gradient(L), nlcag["grad_left"])
+    c = po.nlca_cost(L, R, D)
+    assert np.array_equal(c, nlcag["cost"])
+    assert np.array_equal(po.flip_vol(c), nlcag["cost_right"])
+
+
+def test_nlca_disparity_matches_reference(nlcag):
+    L, R, D = nlcag["left"], nlcag["right"], int(nlcag["D"])
+    assert np.array_equal(po.nlca_disparity(L, R, D, 0.1, post=False), nlcag["disp"])
+    assert np.array_equal(po.nlca_disparity(L, R, D, 0.1, post=True), nlcag["disp_post"])
+
+
+def test_nlca_helpers_known_answers():
+    v = np.array([[[3.0, 1.0, 1.0], [0.5, 0.5, 0.2]]])
+    assert po.depth_best_cost(v).tolist() == [[1, 2]]                     # first minimum
+    dl = np.array([[0, 1, 2, 3]], np.uint8)
+    dr = np.array([[1, 9, 9, 9]], np.uint8)
+    # x=0: d=0 -> 255; x=1: xr=0, |1-1|=0 -> 0; x=2: xr=0, |2-1|>=1 -> 255; x=3: xr=0, |3-1| -> 255
+    assert po.detect_occlusion(dl, dr).tolist() == [[255, 0, 255, 255]]
+    vol = np.arange(2 * 3 * 2, dtype=np.float64).reshape(1, 6, 2) if False else np.arange(12, dtype=np.float64).reshape(1, 3, 4)
+    f = po.flip_vol(vol)
+    # right[x][d] = left[x+d][d] while x+d < W, else the previous plane's value
+    assert f[0, 0].tolist() == [vol[0, 0, 0], vol[0, 1, 1], vol[0, 2, 2], vol[0, 2, 2]]
+    assert f[0, 2].tolist() == [vol[0, 2, 0]] * 4
