@@ -214,6 +214,7 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"     # NCCL's version banner goes to stdout; stdout carries ONE JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
