@@ -86,7 +86,7 @@ int smi_pack_bgr(sm_ctx* ctx, const uint8_t* d_bgr, long long npix, uint32_t* d_
 // entries: pixel u sits at index PAD + u and the PAD entries on either side are zero (partner outside the image).
 // Followed by the armH plane and the armV plane (one u32 per entry each): d_out holds 4 * H * (W + 2*PAD) words.
 int smi_pack_arms(sm_ctx* ctx, const uint16_t* d_arms, int H, int W, int PAD, uint32_t* d_out);
-static inline int smi_arm_pad(int D) { return (D + 31) / 32 * 32; }
+static inline int smi_arm_pad(int D) { return (D + 31) / 32 * 32 + 4; }   // +4: 16-byte aligned supersets stay in the row
 // the two exp lookup tables of the fused AD-Census kernel (see cost.cu)
 int smi_exp_tables(sm_ctx* ctx, float trunc, float lamAD, float lamCen, int codeLen, const float** d_tabAD,
                    const float** d_tabCen);

@@ -217,8 +217,8 @@ __global__ void k_pack_arms(const uint16_t* __restrict__ arms, int H, int W, int
       wv = (uint32_t)a[2] | ((uint32_t)a[3] << 16);
     }
     reinterpret_cast<uint2*>(out)[i] = make_uint2(wh, wv);   // pair map
-    out[2 * n + i] = wh;                                     // armH plane
-    out[3 * n + i] = wv;                                     // armV plane
+    out[2 * n + i] = wh << 7;                                // armH plane, lengths x 128 (ring bytes of the first pass)
+    out[3 * n + i] = wv << 7;                                // armV plane, likewise
   }
 }
 

@@ -95,7 +95,7 @@ def test_arms_intersect_bit_exact(ctx):
         assert np.array_equal(got, po.arms_intersect(aL, aR, 12, view))
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", SHAPES + [(48, 96, 40), (100, 132, 96), (44, 200, 36), (120, 64, 256)])   # last 4: wide-staging path
 @pytest.mark.parametrize("view", [0, 1])
 def test_cbca_bit_exact(ctx, shape, view):
     H, W, D = shape
