@@ -288,6 +288,113 @@ __global__ void __launch_bounds__(32)
   sgm_wait<0>();
 }
 
+// Horizontal paths through the TMA unit.  A row is one contiguous run of W*D floats, so whole groups of SGM_TK
+// pixels (C run, S run, pixel words) are fetched with cp.async.bulk by one lane and land on an mbarrier; the
+// LDGSTS pipe, which caps cp.async at ~16 B/clk/SM (~4.7 TB/s chip-wide, see scripts/microbench), is not involved.
+// Needs D % 4 == 0 and W % SGM_TK == 0 (16-byte granular, 16-byte aligned copies).
+#define SGM_TK 4    // pixels per stage
+#define SGM_TNS 3   // stages in flight per warp
+
+__device__ __forceinline__ void sgm_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sgm_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sgm_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sgm_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int VPL, int MODE>
+__global__ void __launch_bounds__(32)
+    k_sgm_path_t(const float* __restrict__ vol, const uint32_t* __restrict__ pix, float* __restrict__ out, int H, int W,
+                 int mu, int D, int corDifThres, float redu, int16_t* __restrict__ disp) {
+  extern __shared__ __align__(128) uint8_t sgm_smem[];
+  const int lane = threadIdx.x;
+  const int v = blockIdx.x;
+  const int d0 = lane * VPL;
+  const int nq = d0 < D ? min(VPL, D - d0) / 4 : 0;      // 16-byte pieces of this lane's run
+  const uint32_t runB = (uint32_t)D * 4;                 // bytes of one pixel's D values
+  const uint32_t cB = SGM_TK * runB, sB = MODE >= 1 ? cB : 0u, stageB = cB + sB + 16;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sgm_smem);
+  const uint32_t bars = base + SGM_TNS * stageB;
+  const int nStages = W / SGM_TK;
+  const size_t row = (size_t)v * W;
+
+  // stage k covers pixels [x0, x0 + TK) in memory order, x0 = mu > 0 ? TK*k : W - TK*(k+1)
+  auto issue = [&](int k, int slot) {
+    const int x0 = mu > 0 ? SGM_TK * k : W - SGM_TK * (k + 1);
+    const uint32_t st = base + slot * stageB, bar = bars + slot * 8;
+    sgm_mbar_expect(bar, stageB);
+    sgm_bulk(st, vol + (row + x0) * D, cB, bar);
+    if (MODE >= 1) sgm_bulk(st + cB, out + (row + x0) * D, sB, bar);
+    sgm_bulk(st + cB + sB, pix + row + x0, 16, bar);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < SGM_TNS; s++) sgm_mbar_init(bars + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int k = 0; k < SGM_TNS && k < nStages; k++) issue(k, k);
+  }
+  __syncwarp();
+
+  float prev[VPL];
+  float minC = 0.f;
+  uint32_t xprev = 0;
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int k = 0; k < nStages; k++) {
+    const uint32_t st = base + slot * stageB;
+    sgm_mbar_wait(bars + slot * 8, parity);
+    float c[SGM_TK][VPL], s[SGM_TK][VPL];
+    uint32_t x[SGM_TK];
+#pragma unroll
+    for (int i = 0; i < SGM_TK; i++) {
+      const int pi = mu > 0 ? i : SGM_TK - 1 - i;        // pixel inside the stage, in traversal order
+#pragma unroll
+      for (int q = 0; q < VPL / 4; q++) {
+        float4 a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < nq) {
+          a = sgm_lds16(st + pi * runB + d0 * 4 + q * 16);
+          if (MODE >= 1) b = sgm_lds16(st + cB + pi * runB + d0 * 4 + q * 16);
+        }
+        c[i][4 * q] = a.x; c[i][4 * q + 1] = a.y; c[i][4 * q + 2] = a.z; c[i][4 * q + 3] = a.w;
+        s[i][4 * q] = b.x; s[i][4 * q + 1] = b.y; s[i][4 * q + 2] = b.z; s[i][4 * q + 3] = b.w;
+      }
+      x[i] = sgm_lds4(st + cB + sB + pi * 4);
+    }
+    __syncwarp();   // every lane has read the stage
+    if (lane == 0 && k + SGM_TNS < nStages) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(k + SGM_TNS, slot);
+    }
+#pragma unroll
+    for (int i = 0; i < SGM_TK; i++) {
+      const int xi = mu > 0 ? SGM_TK * k + i : W - 1 - (SGM_TK * k + i);
+      const long long p = (long long)row + xi;
+      sgm_step<VPL, MODE>(k == 0 && i == 0, c[i], s[i], prev, minC, x[i], xprev, d0, D, corDifThres, redu, lane, disp, p);
+#pragma unroll
+      for (int q = 0; q < VPL / 4; q++)
+        if (q < nq)
+          *reinterpret_cast<float4*>(out + p * D + d0 + q * 4) = make_float4(s[i][4 * q], s[i][4 * q + 1], s[i][4 * q + 2], s[i][4 * q + 3]);
+    }
+    if (++slot == SGM_TNS) { slot = 0; parity ^= 1u; }
+  }
+}
+
 static const int SGM_RV[8] = {+1, -1, 0, 0, +1, +1, -1, -1};
 static const int SGM_RU[8] = {0, 0, +1, -1, -1, +1, +1, -1};
 
@@ -312,6 +419,23 @@ static int launch_sgm_h1(sm_ctx* ctx, const float* vol, const uint32_t* pix, flo
   SM_LAUNCH(ctx, (k_sgm_path_h<VPL, MODE>), H, 32, smem, vol, pix, out, H, W, mu, D, thr, redu, disp);
   return SM_OK;
 }
+template <int VPL, int MODE>
+static int launch_sgm_t1(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, int H, int W, int mu, int D,
+                         int thr, float redu, int16_t* disp) {
+  const size_t stageB = (size_t)SGM_TK * D * 4 * (MODE >= 1 ? 2 : 1) + 16;
+  const size_t smem = SGM_TNS * stageB + SGM_TNS * 8;
+  SM_CUDA(cudaFuncSetAttribute(k_sgm_path_t<VPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SM_LAUNCH(ctx, (k_sgm_path_t<VPL, MODE>), H, 32, smem, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  return SM_OK;
+}
+template <int VPL>
+static int launch_sgm_t(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, int H, int W, int mu, int D,
+                        int thr, float redu, int mode, int16_t* disp) {
+  if (mode == 0) return launch_sgm_t1<VPL, 0>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  if (mode == 1) return launch_sgm_t1<VPL, 1>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  return launch_sgm_t1<VPL, 2>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+}
+
 template <int VPL>
 static int launch_sgm_h(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, int H, int W, int mu, int D,
                         int thr, float redu, int mode, int16_t* disp) {
@@ -329,8 +453,14 @@ int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix,
   const float redu = (float)reduCoeffi1;
   const bool vec = (D % 4 == 0) && (((uintptr_t)d_vol | (uintptr_t)d_out) % 16 == 0);
   const int vpl = D <= 32 ? 1 : D <= 64 ? 2 : D <= 128 ? 4 : D <= 256 ? 8 : 16;
-  static const int staged_env = getenv("SM_SGM_STAGED") ? atoi(getenv("SM_SGM_STAGED")) : 1;   // tuning switch
-  if (g.mv == 0 && vec && vpl >= 4 && staged_env) {   // horizontal: few, contiguous lines -> cp.async staged variant
+  static const int staged_env = getenv("SM_SGM_STAGED") ? atoi(getenv("SM_SGM_STAGED")) : 2;   // tuning switch
+  // horizontal: few, contiguous lines.  2 = TMA bulk staging, 1 = cp.async staging, 0 = the generic kernel
+  if (g.mv == 0 && vec && vpl >= 4 && staged_env == 2 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0) {
+    if (vpl == 4) return launch_sgm_t<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
+    if (vpl == 8) return launch_sgm_t<8>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
+    return launch_sgm_t<16>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
+  }
+  if (g.mv == 0 && vec && vpl >= 4 && staged_env) {   // cp.async staged variant
     if (vpl == 4) return launch_sgm_h<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
     if (vpl == 8) return launch_sgm_h<8>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
     return launch_sgm_h<16>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
