@@ -71,6 +71,11 @@ typedef struct sm_params {
   int Do_properIpol;        /* :76 */
   int Do_lastMedianBlur;    /* :80 */
   float crossScaleLambda;   /* <0: skip; >=0: the caller's 1-level SolveAll scale 1/(1+lambda), main_.cpp:158 */
+  int sgm_grouped;          /* 8 paths only.  0: add the path volumes in the reference's order L0+L1+...+L7
+                             * (bit-exact).  1 (default): sweep the row-wise paths {0,4,5} and {1,6,7} together
+                             * (one read of C and one read-modify-write of the sum for three paths); every path
+                             * volume is still exact, only the order of the eight additions differs: integer-valued
+                             * costs stay bit-exact, float sums agree to a few ulp (see sm_sgm_grouped). */
 } sm_params;
 
 void sm_params_default(sm_params* p, int maxDisp);
@@ -211,6 +216,14 @@ int sm_sgm(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, 
 /* gen_sgm_vm's inner statement `sum += Lr[num]` (stereoMatching.cpp:2051) for one
  * materialised path volume: d_acc[i] = d_acc[i] + d_x[i]. */
 int sm_vol_accumulate(sm_ctx* ctx, float* d_acc, const float* d_x, size_t n);
+
+/* sgm() with 8 paths where the three upward paths {0,4,5} and the three downward paths {1,6,7} are each computed
+ * in ONE sweep over the rows (3 V b of HBM traffic per group instead of 9 V b).  Each path's Lr is computed exactly
+ * as updateCost does; the sum is formed as ((L0+L4)+L5) + L1 + L6 + L7 + L2 + L3 instead of L0+L1+...+L7, so it is
+ * bit-exact for integer-valued costs and within a few ulp (<= 1e-6 relative) otherwise.  Falls back to sm_sgm's
+ * path-by-path order when the shape is unsupported (D % 4 != 0, D <= 64, very wide images). */
+int sm_sgm_grouped(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int corDifThres,
+                   int reduCoeffi1, float* d_sum);
 
 /* ---- disparity selection --------------------------------------------------- */
 /* gen_dispFromVm (stereoMatching.cpp:3928-3967), ChooseSmall = true. */

@@ -29,7 +29,7 @@ class SmParams(C.Structure):
         ("regVote_hratioThres", C.c_float), ("DISP_OCC", C.c_int), ("DISP_MIS", C.c_int),
         ("aggregation", C.c_int), ("Do_refine", C.c_int), ("Do_LRConsis", C.c_int),
         ("Do_regionVote", C.c_int), ("Do_properIpol", C.c_int), ("Do_lastMedianBlur", C.c_int),
-        ("crossScaleLambda", C.c_float),
+        ("crossScaleLambda", C.c_float), ("sgm_grouped", C.c_int),
     ]
 
 
@@ -77,6 +77,7 @@ SIGNATURES = {
     "sm_nlca_refine_cost": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "sm_sgm_path": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_sgm": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "sm_sgm_grouped": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "sm_vol_accumulate": ([_P, _P, _P, _Z], _I),
     "sm_wta": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_wta_co": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
@@ -256,6 +257,12 @@ class Ctx:
         H, W, D = vol.shape
         out = self.torch.empty_like(vol)
         check(self.L.sm_sgm(self.h, _ptr(vol), _ptr(bgr), H, W, D, paths, thr, redu, _ptr(out)))
+        return out
+
+    def sgm_grouped(self, vol, bgr, thr=15, redu=4):
+        H, W, D = vol.shape
+        out = self.torch.empty_like(vol)
+        check(self.L.sm_sgm_grouped(self.h, _ptr(vol), _ptr(bgr), H, W, D, thr, redu, _ptr(out)))
         return out
 
     def wta(self, vol):

@@ -22,7 +22,7 @@ struct sm_scratch {
 };
 
 enum { SM_SCR_IMG0 = 0, SM_SCR_IMG1, SM_SCR_ARM0, SM_SCR_ARM1, SM_SCR_TAB, SM_SCR_MISC0, SM_SCR_MISC1,
-       SM_SCR_MISC2, SM_SCR_MISC3, SM_SCR_MISC4, SM_SCR_MISC5, SM_SCR_NLWORK, SM_SCR_COUNT };
+       SM_SCR_MISC2, SM_SCR_MISC3, SM_SCR_MISC4, SM_SCR_MISC5, SM_SCR_NLWORK, SM_SCR_SGMEDGE, SM_SCR_COUNT };
 
 struct sm_ctx {
   int device = 0;
@@ -105,6 +105,13 @@ int smi_sgm_path_packed(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, 
 // mode 2: accumulate and write the WTA of the finished sum into d_disp (last path of a view)
 int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                          int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp);
+
+// grouped SGM sweep (sgm_group.cu): up = 1 -> paths {0,4,5}, up = 0 -> paths {1,6,7}; mode 0 writes, 1 accumulates
+int smi_sgm_group(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int up, int mode,
+                  int corDifThres, int reduCoeffi1, float* d_sum);
+
+int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int corDifThres,
+                     int reduCoeffi1, float* d_sum, int16_t* d_disp);
 
 __device__ __forceinline__ int smd_absdiff_max3(uint32_t a, uint32_t b) {
   // max over the three low bytes of |a_c - b_c|

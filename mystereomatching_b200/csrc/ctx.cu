@@ -49,6 +49,7 @@ extern "C" void sm_params_default(sm_params* p, int maxDisp) {
   p->Do_properIpol = 1;
   p->Do_lastMedianBlur = 1;
   p->crossScaleLambda = -1.f;
+  p->sgm_grouped = 1;
 }
 
 extern "C" int sm_ctx_create(sm_ctx** out, int device, void* stream) {

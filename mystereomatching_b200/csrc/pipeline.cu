@@ -188,6 +188,10 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   // ---- dispOptimize: sgm (stereoMatching.cpp:1051-1089) then WTA (:1108-1128)
   if (P.sgm_paths > 0) {
     for (int i = 0; i < views; i++) {
+      if (P.sgm_paths == 8 && P.sgm_grouped) {
+        SM_TRY(smi_sgm8_grouped(c, pl->vol[i], pl->pix[i], H, W, D, P.sgm_corDifThres, P.sgm_reduCoeffi1, pl->vol[2],
+                                pl->disp[i]));
+      } else
       for (int k = 0; k < P.sgm_paths; k++) {
         // the last path also does gen_dispFromVm on the finished sum (saves one read of the volume)
         const int mode = k == 0 ? 0 : (k == P.sgm_paths - 1 ? 2 : 1);

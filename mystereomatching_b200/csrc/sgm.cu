@@ -499,6 +499,34 @@ extern "C" int sm_sgm_path(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr
   return smi_sgm_path_packed(ctx, d_vol, (const uint32_t*)pk, H, W, D, path, corDifThres, reduCoeffi1, mode, d_out);
 }
 
+// 8 paths, row-wise groups first (see sgm_group.cu); d_disp (nullable): WTA of the finished sum fused into the last path
+int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int corDifThres,
+                     int reduCoeffi1, float* d_sum, int16_t* d_disp) {
+  int rc = smi_sgm_group(ctx, d_vol, d_pix, H, W, D, /*up*/1, /*mode*/0, corDifThres, reduCoeffi1, d_sum);
+  if (rc == SM_ERR_UNSUPPORTED) {   // shape outside the grouped kernel: reference order, path by path
+    for (int i = 0; i < 8; i++)
+      SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, i, corDifThres, reduCoeffi1,
+                                  i == 0 ? 0 : (i == 7 && d_disp ? 2 : 1), d_sum, d_disp));
+    return SM_OK;
+  }
+  SM_TRY(rc);
+  SM_TRY(smi_sgm_group(ctx, d_vol, d_pix, H, W, D, /*up*/0, /*mode*/1, corDifThres, reduCoeffi1, d_sum));
+  SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, 2, corDifThres, reduCoeffi1, 1, d_sum, nullptr));
+  SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, 3, corDifThres, reduCoeffi1, d_disp ? 2 : 1, d_sum, d_disp));
+  return SM_OK;
+}
+
+extern "C" int sm_sgm_grouped(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int corDifThres,
+                              int reduCoeffi1, float* d_sum) {
+  SM_CHECK_ARG(ctx && d_vol && d_bgr && d_sum);
+  SM_CHECK_ARG(H > 0 && W > 0 && D > 0 && D <= 512 && reduCoeffi1 != 0 && d_vol != d_sum);
+  const long long npix = (long long)H * W;
+  void* pk;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_IMG0, npix * 4, &pk));
+  SM_TRY(smi_pack_bgr(ctx, d_bgr, npix, (uint32_t*)pk));
+  return smi_sgm8_grouped(ctx, d_vol, (const uint32_t*)pk, H, W, D, corDifThres, reduCoeffi1, d_sum, nullptr);
+}
+
 extern "C" int sm_sgm(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int paths,
                       int corDifThres, int reduCoeffi1, float* d_sum) {
   SM_CHECK_ARG(ctx && d_vol && d_bgr && d_sum);

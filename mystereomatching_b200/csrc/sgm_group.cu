@@ -1,0 +1,405 @@
+// K5b: grouped SGM sweeps -- three path directions per pass over the volume.
+//
+// The per-path kernels (sgm.cu) read C and read-modify-write the path sum S once PER PATH: (3P-1) V b bytes, which
+// is what bounds them (83 % of the HBM roofline).  Three of the eight reference directions advance together row by
+// row: the predecessors of paths {1, 6, 7} (stereoMatching.cpp:6207-6208: rv = -1, ru = 0 / +1 / -1) all lie in row
+// v-1, those of paths {0, 4, 5} (rv = +1, ru = 0 / -1 / +1) in row v+1.  One sweep over the rows can therefore
+// carry all three recurrences on ONE read of C and ONE read-modify-write of S: 3 V b per group instead of 9 V b.
+//
+// Shape: one cooperative launch, one CTA per SM, a CTA owns CW adjacent columns, a warp owns one column (D spread
+// over lanes as runs of VPL), rows in lock step:
+//   * the vertical path's previous Lr row stays in registers;
+//   * the two diagonal paths need the previous row of the NEIGHBOUR column: warps publish their rows (and row
+//     minima) in shared memory, double buffered, one __syncthreads per row;
+//   * across CTA boundaries the edge columns' rows go through global memory (each CTA waits only for its two
+//     neighbours: a wavefront, not a grid barrier).  The hand-off carries no flag and no fence: the edge buffers
+//     are pre-set to a NaN bit pattern no Lr value can have, the writer stores the row, and every reader lane polls
+//     ITS OWN words until none is the sentinel (each word changes exactly once, so no ordering between words is
+//     needed).  That is one L2 round trip per row instead of store + fence + flag + load (measured 5.9 -> see
+//     DESIGN.md us per row);
+//   * C and S rows of the next SGMG_NS rows are staged per warp by the TMA unit (cp.async.bulk + mbarrier).
+//
+// Arithmetic: every Lr value is computed exactly as updateCost<float> does (stereoMatching.h:2205-2280), so each
+// path volume is bit-identical to the reference's.  Only the ORDER in which the eight path volumes are added into
+// S differs from gen_sgm_vm's (stereoMatching.cpp:2031-2056: L0+L1+...+L7): here ((L0+L4)+L5), then +L1+L6+L7,
+// then +L2, +L3.  For integer-valued costs (the Census path) every partial sum is exact, so S is still bit-exact;
+// for float costs S agrees to a few ulp (tests: <= 1e-6 relative, the north star allows 1e-4) and the disparity
+// maps agree to >= 99.5 %.  The reference-order variant (sm_sgm) stays available and bit-exact.
+#include <float.h>
+
+#include "common.cuh"
+
+#define SGMG_NS 4   // rows of C / S in flight per warp
+
+__device__ __forceinline__ uint32_t g_f2key(float x) {
+  uint32_t b = __float_as_uint(x);
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float g_key2f(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void g_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float4 g_lds16(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void g_sts16(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ int g_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void g_st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One pixel of one path: updateCost<float> given the predecessor's Lr row (pr), its minimum and the colour step.
+// Disparities outside [0, D) are FLT_MAX in pr and c: FLT_MAX + P1 rounds back to FLT_MAX, which never wins a
+// minimum against the finite candidates, so no per-disparity range predicate is needed.
+template <int VPL>
+__device__ __forceinline__ void g_lr(const float (&c)[VPL], const float (&pr)[VPL], float minP, bool step, float P1r, float P2r,
+                                     int lane, float (&lr)[VPL], float& minNew) {
+  const float P2 = step ? P2r : 3.0f;
+  const float P1 = (step ? P1r : 1.0f) - minP;
+  float lo = __shfl_up_sync(0xffffffffu, pr[VPL - 1], 1);
+  float hi = __shfl_down_sync(0xffffffffu, pr[0], 1);
+  lo = lane == 0 ? FLT_MAX : lo;
+  hi = lane == 31 ? FLT_MAX : hi;
+  float m = FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < VPL; j++) {
+    const float pm = j == 0 ? lo : pr[j - 1];
+    const float pp = j == VPL - 1 ? hi : pr[j + 1];
+    lr[j] = c[j] + fminf(fminf(pr[j] - minP, pm + P1), fminf(pp + P1, P2));
+    m = fminf(m, lr[j]);
+  }
+  minNew = g_key2f(__reduce_min_sync(0xffffffffu, g_f2key(m)));
+}
+template <int VPL>
+__device__ __forceinline__ float g_rowmin(const float (&lr)[VPL]) {
+  float m = FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < VPL; j++) m = fminf(m, lr[j]);
+  return g_key2f(__reduce_min_sync(0xffffffffu, g_f2key(m)));
+}
+
+// edge exchange between neighbouring CTAs: rows of one path of one boundary column
+struct sgmg_edges {
+  float* rowsP;   // [nb][H][Dp]  first column of CTA b, path whose predecessor is column u+1 (read by CTA b-1)
+  float* rowsM;   // [nb][H][Dp]  last column of CTA b, path whose predecessor is column u-1 (read by CTA b+1)
+  int Dp;         // row pitch in floats: D values + 1 minimum, padded to a multiple of 4
+};
+#define SGMG_SENTINEL 0xFFFFFFFFu   // a NaN pattern: never a valid Lr value or minimum
+
+__device__ __forceinline__ uint4 g_ld_relaxed16(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t g_ld_relaxed4(const void* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float g_lds4(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void g_sts4(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void g_pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// a row of D floats of this lane's run (quads beyond D read as FLT_MAX / are not written)
+template <int VPL>
+__device__ __forceinline__ void g_ldrow(uint32_t a, int nq, float (&x)[VPL]) {
+#pragma unroll
+  for (int q = 0; q < VPL / 4; q++) {
+    float4 t = q < nq ? g_lds16(a + q * 16) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+  }
+}
+template <int VPL>
+__device__ __forceinline__ void g_strow(uint32_t a, int nq, const float (&x)[VPL]) {
+#pragma unroll
+  for (int q = 0; q < VPL / 4; q++)
+    if (q < nq) g_sts16(a + q * 16, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+}
+// wait for and read this lane's part of a neighbour CTA's published row (and the row minimum)
+template <int VPL>
+__device__ __forceinline__ void g_read_edge(const float* src, int nq, int D, float (&pr)[VPL], float& pm) {
+#pragma unroll
+  for (int q = 0; q < VPL / 4; q++) {
+    uint4 t = make_uint4(0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu);   // FLT_MAX padding
+    if (q < nq) {
+      do { t = g_ld_relaxed16(src + q * 4); }
+      while (t.x == SGMG_SENTINEL || t.y == SGMG_SENTINEL || t.z == SGMG_SENTINEL || t.w == SGMG_SENTINEL);
+    }
+    pr[4 * q] = __uint_as_float(t.x); pr[4 * q + 1] = __uint_as_float(t.y);
+    pr[4 * q + 2] = __uint_as_float(t.z); pr[4 * q + 3] = __uint_as_float(t.w);
+  }
+  uint32_t m;
+  do { m = g_ld_relaxed4(src + D); } while (m == SGMG_SENTINEL);   // src is lane-relative: the minimum sits at D - d0
+  pm = __uint_as_float(m);
+}
+
+// UP = 0: rows 0 .. H-1, paths {1, 6, 7} (predecessor columns u, u+1, u-1).
+// UP = 1: rows H-1 .. 0, paths {0, 4, 5} (predecessor columns u, u-1, u+1).
+// MODE 0: S = LA + LB + LC; MODE 1: S = ((S + LA) + LB) + LC.   FULL: D == 32 * VPL (no padding lanes).
+template <int VPL, int UP, int MODE, bool FULL>
+__global__ void __launch_bounds__(512, 1)
+    k_sgm_group(const float* __restrict__ vol, const uint32_t* __restrict__ pix, float* __restrict__ out, int H, int W, int D,
+                int corDifThres, float redu, sgmg_edges E) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarp = blockDim.x >> 5;   // widest CTA's column count
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int u0 = (int)(((long long)b * W) / nb);
+  const int nCols = (int)(((long long)(b + 1) * W) / nb) - u0;   // >= 2 (host: nb <= W / 4)
+  if (warp >= nCols) return;                                     // no CTA-wide barrier below
+  const int u = u0 + warp;
+  const int d0 = lane * VPL;
+  const int nq = FULL ? VPL / 4 : (d0 < D ? min(VPL, D - d0) / 4 : 0);
+  const uint32_t runB = (uint32_t)D * 4;
+  constexpr int ob = UP ? -1 : +1, oc = -ob;   // predecessor column offsets of paths B and C (reference order)
+
+  // shared memory: per warp SGMG_NS stages {C run, S run}; exchange rows [path][buf][CW][D]; minima [path][buf][CW]
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(gsm);
+  const uint32_t stageB = runB * (MODE >= 1 ? 2 : 1);
+  const uint32_t stLo = base + (uint32_t)warp * SGMG_NS * stageB;
+  const uint32_t exLo = base + (uint32_t)nwarp * SGMG_NS * stageB;
+  const uint32_t exBufB = (uint32_t)nwarp * runB, exPathB = 2u * exBufB;
+  const uint32_t minLo = exLo + 2 * exPathB;
+  const uint32_t minBufB = (uint32_t)nwarp * 4, minPathB = 2u * minBufB;
+  const uint32_t bars = minLo + 2 * minPathB + (uint32_t)warp * SGMG_NS * 8;   // (8-byte aligned: see host)
+
+  const long long rowStep = UP ? -(long long)W : (long long)W;   // pixels from one row of the sweep to the next
+  const size_t p0 = (size_t)(UP ? H - 1 : 0) * W + u;            // first pixel of this column in sweep order
+  auto issue = [&](int r, int slot) {
+    const size_t p = (size_t)((long long)p0 + rowStep * r);
+    const uint32_t st = stLo + slot * stageB, bar = bars + slot * 8;
+    g_mbar_expect(bar, stageB);
+    g_bulk(st, vol + p * D, runB, bar);
+    if (MODE >= 1) g_bulk(st + runB, out + p * D, runB, bar);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < SGMG_NS; s++) g_mbar_init(bars + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int r = 0; r < SGMG_NS && r < H; r++) issue(r, r);
+  }
+  __syncwarp();
+
+  // roles.  A path whose previous row sits in the neighbour CTA ("far") is fed through the global edge rows; the
+  // other diagonal of an edge column ("near") is what the neighbour CTA consumes and is published there.
+  const bool isFirst = warp == 0, isLast = warp == nCols - 1;
+  const bool special = isFirst || isLast;
+  const int nearOff = isFirst ? +1 : -1;
+  const bool nearIsB = nearOff == ob;
+  const bool nbrCta = isFirst ? b > 0 : b + 1 < nb;   // the CTA on the far side exists (else: image border)
+  float* pubRow = (isFirst ? E.rowsP : E.rowsM) + (size_t)b * H * E.Dp + d0;
+  const float* farRow = (isFirst ? E.rowsM : E.rowsP) + (size_t)(nbrCta ? (isFirst ? b - 1 : b + 1) : b) * H * E.Dp + d0;
+  const float P1r = 1.0f / redu, P2r = 3.0f / redu;
+
+  // pixel words (BGR packed): own column's next row, and the two diagonal predecessors of the next row
+  const int ub = min(max(u + ob, 0), W - 1) - u, uc = min(max(u + oc, 0), W - 1) - u;
+  const uint32_t* px = pix + p0;
+  uint32_t xrow = *px, xpA = 0, xpB = 0, xpC = 0;
+  float* o = out + p0 * D + d0;
+  const long long oStep = rowStep * D;
+
+  float prevA[VPL], minA = 0.f;
+  int slot = 0;
+  uint32_t parity = 0;
+  const int barL = warp, barR = warp + 1;   // named barrier of the pair (w-1, w) is w: ids 1 .. 15
+  const bool hasL = warp > 0, hasR = warp + 1 < nCols;
+
+  for (int r = 0; r < H; r++) {
+    const uint32_t bufOff = (r & 1) ? exBufB : 0u, pbufOff = exBufB - bufOff;
+    const uint32_t mbufOff = (r & 1) ? minBufB : 0u, mpbufOff = minBufB - mbufOff;
+    float c[VPL], s[VPL], lrA[VPL], lrB[VPL], lrC[VPL];
+    // next row's pixel words, one row ahead of their use
+    uint32_t xnext = 0, xnB = 0, xnC = 0;
+    if (r + 1 < H) { xnext = px[rowStep]; xnB = px[ub]; xnC = px[uc]; }
+    const uint32_t st = stLo + slot * stageB + d0 * 4;
+    g_mbar_wait(bars + slot * 8, parity);
+    g_ldrow<VPL>(st, nq, c);
+    if (MODE >= 1) g_ldrow<VPL>(st + runB, nq, s);
+    __syncwarp();
+    if (lane == 0 && r + SGMG_NS < H) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(r + SGMG_NS, slot);
+    }
+    const uint32_t myB = exLo + bufOff + (uint32_t)warp * runB + d0 * 4, myC = myB + exPathB;
+    const uint32_t myMinB = minLo + mbufOff + (uint32_t)warp * 4, myMinC = myMinB + minPathB;
+    if (r == 0) {   // first row of the sweep: no predecessor inside the image -> Lr = C on all three paths
+      const float m = g_rowmin<VPL>(c);
+#pragma unroll
+      for (int j = 0; j < VPL; j++) lrA[j] = lrB[j] = lrC[j] = c[j];
+      minA = m;
+      if (!special) {
+        g_strow<VPL>(myB, nq, c); g_strow<VPL>(myC, nq, c);
+        if (lane == 0) { g_sts4(myMinB, m); g_sts4(myMinC, m); }
+      } else {
+        if (nbrCta) {
+#pragma unroll
+          for (int q = 0; q < VPL / 4; q++)
+            if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]));
+          if (lane == 0) __stcg(pubRow + D, m);
+        }
+        g_strow<VPL>(nearIsB ? myC : myB, nq, c);
+        if (lane == 0) g_sts4(nearIsB ? myMinC : myMinB, m);
+      }
+    } else if (!special) {
+      // interior column: three independent recurrences, all fed from registers / shared memory
+      float prB[VPL], prC[VPL];
+      g_ldrow<VPL>(exLo + pbufOff + (uint32_t)(warp + ob) * runB + d0 * 4, nq, prB);
+      g_ldrow<VPL>(exLo + exPathB + pbufOff + (uint32_t)(warp + oc) * runB + d0 * 4, nq, prC);
+      const float pmB = g_lds4(minLo + mpbufOff + (uint32_t)(warp + ob) * 4);
+      const float pmC = g_lds4(minLo + minPathB + mpbufOff + (uint32_t)(warp + oc) * 4);
+      float mB, mC, mA;
+      g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
+      g_lr<VPL>(c, prB, pmB, (int)smd_absdiff_max3(xrow, xpB) > corDifThres, P1r, P2r, lane, lrB, mB);
+      g_lr<VPL>(c, prC, pmC, (int)smd_absdiff_max3(xrow, xpC) > corDifThres, P1r, P2r, lane, lrC, mC);
+      minA = mA;
+      g_strow<VPL>(myB, nq, lrB); g_strow<VPL>(myC, nq, lrC);
+      if (lane == 0) { g_sts4(myMinB, mB); g_sts4(myMinC, mC); }
+    } else {
+      // edge column.  The near diagonal and the vertical path first; the near row goes to the neighbour CTA at once.
+      // The far diagonal last, so the neighbour's store (issued early in ITS row) has had a row period to land.
+      float prN[VPL], lrN[VPL], lrF[VPL], mN, mF, mA;
+      const uint32_t nearPath = nearIsB ? 0u : exPathB, nearMin = nearIsB ? 0u : minPathB;
+      g_ldrow<VPL>(exLo + nearPath + pbufOff + (uint32_t)(warp + nearOff) * runB + d0 * 4, nq, prN);
+      const float pmN = g_lds4(minLo + nearMin + mpbufOff + (uint32_t)(warp + nearOff) * 4);
+      const uint32_t xpN = nearIsB ? xpB : xpC, xpF = nearIsB ? xpC : xpB;
+      g_lr<VPL>(c, prN, pmN, (int)smd_absdiff_max3(xrow, xpN) > corDifThres, P1r, P2r, lane, lrN, mN);
+      if (nbrCta) {
+#pragma unroll
+        for (int q = 0; q < VPL / 4; q++)
+          if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(lrN[4 * q], lrN[4 * q + 1], lrN[4 * q + 2], lrN[4 * q + 3]));
+        if (lane == 0) __stcg(pubRow + D, mN);
+      }
+      g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
+      minA = mA;
+      if (nbrCta) {
+        float prF[VPL], pmF;
+        g_read_edge<VPL>(farRow, nq, D - d0, prF, pmF);
+        g_lr<VPL>(c, prF, pmF, (int)smd_absdiff_max3(xrow, xpF) > corDifThres, P1r, P2r, lane, lrF, mF);
+      } else {   // predecessor column outside the image: Lr = C
+#pragma unroll
+        for (int j = 0; j < VPL; j++) lrF[j] = c[j];
+        mF = g_rowmin<VPL>(c);
+      }
+      g_strow<VPL>(nearIsB ? myC : myB, nq, lrF);
+      if (lane == 0) g_sts4(nearIsB ? myMinC : myMinB, mF);
+#pragma unroll
+      for (int j = 0; j < VPL; j++) { lrB[j] = nearIsB ? lrN[j] : lrF[j]; lrC[j] = nearIsB ? lrF[j] : lrN[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; j++) prevA[j] = lrA[j];
+    // ---- path sum (gen_sgm_vm: sum += L[num], within the group in reference path order)
+#pragma unroll
+    for (int q = 0; q < VPL / 4; q++)
+      if (q < nq) {
+        float4 t;
+        float* tp = &t.x;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int j = 4 * q + e;
+          tp[e] = MODE >= 1 ? ((s[j] + lrA[j]) + lrB[j]) + lrC[j] : (lrA[j] + lrB[j]) + lrC[j];
+        }
+        *reinterpret_cast<float4*>(o + q * 4) = t;
+      }
+    // advance to the next row of the sweep
+    xpA = xrow; xpB = xnB; xpC = xnC; xrow = xnext;
+    px += rowStep; o += oStep;
+    pubRow += E.Dp;
+    if (r > 0) farRow += E.Dp;   // the far row read at row r is the neighbour's row r-1
+    if (++slot == SGMG_NS) { slot = 0; parity ^= 1u; }
+    // the rows published in shared memory become visible to the two neighbour warps (and theirs to this one);
+    // even pairs first, odd pairs second, so the pairwise barriers never ripple across the CTA
+    if (warp & 1) { if (hasL) g_pair_bar(barL); if (hasR) g_pair_bar(barR); }
+    else          { if (hasR) g_pair_bar(barR); if (hasL) g_pair_bar(barL); }
+  }
+}
+
+// ------------------------------------------------------------------ host
+template <int VPL, int UP>
+static int launch_group(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, int H, int W, int D, int mode,
+                        int corDifThres, float redu) {
+  const int nb = min(ctx->num_sms, W / 4);       // every CTA owns >= 4 columns: first and last column are distinct warps
+  const int CW = sm_div_up(W, nb);               // widest CTA (columns b*W/nb .. (b+1)*W/nb - 1)
+  SM_CHECK_ARG(nb >= 1 && CW <= 16);             // 512 threads (register budget of three recurrences); 15 named barriers
+  const size_t runB = (size_t)D * 4;
+  const size_t stageB = runB * (mode >= 1 ? 2 : 1);
+  size_t smem = (size_t)CW * SGMG_NS * stageB + 2 * 2 * CW * runB + 2 * 2 * CW * 4;
+  smem = (smem + 7) & ~(size_t)7;
+  smem += (size_t)CW * SGMG_NS * 8;
+  SM_CHECK_ARG(smem <= 227 * 1024);
+  sgmg_edges E;
+  E.Dp = (D + 1 + 3) & ~3;
+  const size_t rowsBytes = (size_t)nb * H * E.Dp * sizeof(float);
+  void* p;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_SGMEDGE, 2 * rowsBytes, &p));
+  E.rowsP = (float*)p;
+  E.rowsM = (float*)((uint8_t*)p + rowsBytes);
+  SM_CUDA(cudaMemsetAsync(p, 0xFF, 2 * rowsBytes, ctx->stream));   // sentinel: "row not published yet"
+  void* args[] = {(void*)&vol, (void*)&pix, (void*)&out, (void*)&H, (void*)&W, (void*)&D,
+                  (void*)&corDifThres, (void*)&redu, (void*)&E};
+  const bool full = D == 32 * VPL;
+  const void* fn = full ? (mode == 0 ? (const void*)k_sgm_group<VPL, UP, 0, true> : (const void*)k_sgm_group<VPL, UP, 1, true>)
+                        : (mode == 0 ? (const void*)k_sgm_group<VPL, UP, 0, false> : (const void*)k_sgm_group<VPL, UP, 1, false>);
+  SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = 0;
+  SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, CW * 32, smem));
+  SM_CHECK_ARG(perSM >= 1);
+  // neighbouring CTAs wait on each other: all of them must be resident -> cooperative launch
+  SM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(CW * 32), args, smem, ctx->stream));
+  ctx->launches++;
+  return SM_OK;
+}
+
+// The two row-wise groups of the 8-path table: UP = paths {0,4,5}, DOWN = paths {1,6,7}.  mode 0: d_sum = group sum,
+// mode 1: d_sum += group sum.  Returns SM_ERR_UNSUPPORTED when the shape does not fit (caller falls back to paths).
+int smi_sgm_group(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int up, int mode,
+                  int corDifThres, int reduCoeffi1, float* d_sum) {
+  const bool ok = D % 4 == 0 && D > 64 && D <= 256 && (((uintptr_t)d_vol | (uintptr_t)d_sum) & 15) == 0 && H >= 2 && W >= 8;
+  if (!ok) return SM_ERR_UNSUPPORTED;
+  const float redu = (float)reduCoeffi1;
+  const int vpl = D <= 128 ? 4 : 8;
+  // shared memory per column must leave room for at least W/num_sms columns
+  {
+    const int nb = min(ctx->num_sms, W / 4);
+    const int CW = sm_div_up(W, nb);
+    const size_t smem = (size_t)CW * SGMG_NS * D * 4 * (mode >= 1 ? 2 : 1) + 4 * (size_t)CW * D * 4 + 16 * CW + CW * SGMG_NS * 8 + 8;
+    if (smem > 227 * 1024 || CW > 16) return SM_ERR_UNSUPPORTED;
+  }
+  if (vpl == 4) return up ? launch_group<4, 1>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
+                          : launch_group<4, 0>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
+  return up ? launch_group<8, 1>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
+            : launch_group<8, 0>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
+}

@@ -360,3 +360,47 @@ def test_nlca_stages_bit_exact(ctx, golden_dir):
     assert np.array_equal(ctx.nlca_occlusion(ctx.dev(dl), ctx.dev(dr)).cpu().numpy(), m)
     ref = np.where(m[..., None] != 0, 0.0, np.abs(dl[..., None].astype(np.int64) - np.arange(9)).astype(np.float64))
     assert np.array_equal(ctx.nlca_refine_cost(ctx.dev(dl), ctx.dev(m), 9).cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------- grouped SGM sweeps (3 paths per pass over the volume)
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("shape", [(40, 64, 128), (37, 53, 132), (50, 200, 256), (64, 96, 68), (9, 8, 72), (120, 330, 96)])
+def test_sgm_grouped_matches_reference_sum(ctx, shape):
+    """Every path volume is exact; only the order of the eight additions differs from gen_sgm_vm's."""
+    H, W, D = shape
+    rng = np.random.default_rng(H + W + D)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    bgr[:, : W // 2] //= 32
+    vol = (rng.random((H, W, D)) * 2).astype(np.float32)
+    ref = po.sgm(vol, bgr, 8)
+    got = ctx.sgm_grouped(ctx.dev(vol), ctx.dev(bgr)).cpu().numpy()
+    rel = np.abs(got - ref) / np.abs(ref)
+    assert rel.max() <= 1e-6, float(rel.max())          # north_star: float SGM volumes within 1e-4 relative
+    # the same eight path volumes added in the grouped order reproduce the result bit for bit
+    L = [po.sgm_path(vol, bgr, p) for p in range(8)]
+    grouped = ((L[0] + L[4]) + L[5])
+    grouped = ((grouped + L[1]) + L[6]) + L[7]
+    grouped = (grouped + L[2]) + L[3]
+    if D % 4 == 0 and D > 64:
+        assert _bits_equal(got, grouped)
+    # integer-valued costs: exact in any order
+    ivol = rng.integers(0, 72, (H, W, D)).astype(np.float32)
+    assert np.array_equal(ctx.sgm_grouped(ctx.dev(ivol), ctx.dev(bgr)).cpu().numpy(), po.sgm(ivol, bgr, 8))
+
+
+@pytest.mark.timeout(180)
+def test_pipeline_reference_order_is_bit_exact_and_grouped_agrees(ctx):
+    H, W, D = 80, 144, 96
+    p = _pair(H, W, D, "texture_warped", seed=41)
+    op = po.default_params(D, paths=8)
+    rl, _, rvol, _ = po.pipeline(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], op, want_vol=True)
+    out = {}
+    for grouped in (0, 1):
+        pl = capi.Pipeline(ctx, H, W, capi.default_params(D - 1, sgm_paths=8, sgm_grouped=grouped))
+        pl.upload(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"])
+        pl.run_device()
+        out[grouped] = (pl.download(), pl.buffer(0, (H, W, D), torch.float32).cpu().numpy())
+        pl.close()
+    assert _bits_equal(out[0][1], rvol) and np.array_equal(out[0][0], rl)      # reference order: identical
+    assert np.all(np.abs(out[1][1] - rvol) <= 1e-6 * np.abs(rvol))
+    assert (out[1][0] == rl).mean() >= 0.995
