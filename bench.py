@@ -181,6 +181,13 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def sgm_is_grouped(name):
+    """Shapes the grouped row sweeps (k_sgm_group) accept: mirrors smi_sgm_group's own check (sgm_group.cu)."""
+    W, H, D, P, kind = WORKLOADS[name]
+    nb = min(148, W // 4)
+    return P == 8 and D % 4 == 0 and 64 < D <= 256 and nb >= 1 and -(-W // nb) <= 14
+
+
 def stage_bytes(name):
     """Algorithmic HBM bytes per LAUNCH and launches per frame for each volume stage (b = 4)."""
     W, H, D, P, kind = WORKLOADS[name]
@@ -189,13 +196,21 @@ def stage_bytes(name):
     agg = {"bytes_per_launch": 2 * V * b, "launches": 8, "kernel": "k_cbca_pass"}
     if AGGREGATION[name] == 2:   # k_nl = 4 volume passes; MST build + rooting + two tree sweeps
         agg = {"bytes_per_launch": 4 * V * b, "launches": 1, "kernel": "nl (Boruvka MST + k_tree_bfs + k_tf_sweeps)"}
-    return {
+    st = {
         "cost": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_cost<ADCENSUS>"},
         "aggregation": agg,
-        "sgm": {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path"},
         # gen_dispFromVm is fused into the last SGM path of each view (no separate read of the summed volume)
         "wta": {"bytes_per_launch": 0, "launches": 2, "kernel": "fused into k_sgm_path (mode 2)"},
     }
+    if sgm_is_grouped(name):
+        # per view: sweep UP writes S (C + S = 2 V b), sweep DOWN read-modify-writes it (3 V b); then paths 2 and 3
+        # (C, S in, S out = 3 V b each; the fused WTA of path 3 still leaves the summed volume behind as vm)
+        st["sgm_group"] = {"bytes_per_launch": 2.5 * V * b, "launches": 4, "kernel": "k_sgm_group"}
+        st["sgm_path"] = {"bytes_per_launch": 3 * V * b, "launches": 4, "kernel": "k_sgm_path"}
+    else:
+        # first path writes S (2 V b), the others read-modify-write it (3 V b)
+        st["sgm"] = {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path"}
+    return st
 
 
 def main_ours(args):
@@ -310,7 +325,7 @@ def main_ours(args):
         gbs = info["bytes_per_launch"] / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         stages[k] = {"ms_per_frame": round(ms, 4), "launches": info["launches"], "kernel": info["kernel"],
                      "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
-    for k in ("census", "arms", "refine", "total"):
+    for k in ("census", "arms", "refine", "total") + (("sgm",) if "sgm" not in sb else ()):
         stages[k] = {"ms_per_frame": round(stage_acc.get(k, 0.0) / args.steps, 4)}
     dom = max(sb, key=lambda k: stages[k]["ms_per_frame"])
     traffic = None

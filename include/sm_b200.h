@@ -277,6 +277,9 @@ void* sm_pipeline_buffer(sm_pipeline* pl, int which);
  * enabled: census, cost, arms, aggregation, sgm, wta, refine, total */
 int sm_pipeline_enable_timing(sm_pipeline* pl, int on);
 int sm_pipeline_stage_ms(sm_pipeline* pl, float* out8);
+/* split of the sgm stage of that run: out2[0] = the grouped row sweeps (k_sgm_group), out2[1] = the single-path
+ * launches (k_sgm_path*); {0, sgm} when the grouped sweeps did not run */
+int sm_pipeline_sgm_split_ms(sm_pipeline* pl, float* out2);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,7 @@ SIGNATURES = {
     "sm_pipeline_buffer": ([_P, _I], _P),
     "sm_pipeline_enable_timing": ([_P, _I], _I),
     "sm_pipeline_stage_ms": ([_P, C.POINTER(C.c_float)], _I),
+    "sm_pipeline_sgm_split_ms": ([_P, C.POINTER(C.c_float)], _I),
 }
 
 
@@ -476,4 +477,8 @@ class Pipeline:
         arr = (C.c_float * 8)()
         check(self.ctx.L.sm_pipeline_stage_ms(self.h, arr))
         names = ("census", "cost", "arms", "aggregation", "sgm", "wta", "refine", "total")
-        return dict(zip(names, list(arr)))
+        out = dict(zip(names, list(arr)))
+        sp = (C.c_float * 2)()
+        check(self.ctx.L.sm_pipeline_sgm_split_ms(self.h, sp))
+        out["sgm_group"], out["sgm_path"] = float(sp[0]), float(sp[1])
+        return out

@@ -111,7 +111,8 @@ int smi_sgm_group(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H,
                   int corDifThres, int reduCoeffi1, float* d_sum);
 
 int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int corDifThres,
-                     int reduCoeffi1, float* d_sum, int16_t* d_disp);
+                     int reduCoeffi1, float* d_sum, int16_t* d_disp, cudaEvent_t ev_after_sweeps = nullptr,
+                     bool* used_sweeps = nullptr);
 
 __device__ __forceinline__ int smd_absdiff_max3(uint32_t a, uint32_t b) {
   // max over the three low bytes of |a_c - b_c|

@@ -30,6 +30,8 @@ struct sm_pipeline {
   bool stage_used = false, stage_drained = true;
   bool timing = false;
   cudaEvent_t ev[ST_COUNT + 1];
+  cudaEvent_t evs[2][2];          // sgm stage, per view: start, after the grouped sweeps
+  bool sweeps[2] = {false, false};
   bool ev_ok = false;
   float ms[ST_COUNT];
 };
@@ -50,8 +52,10 @@ extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
   cudaFree(pl->dtmp);
   if (pl->h_in) cudaFreeHost(pl->h_in);
   if (pl->h_out) cudaFreeHost(pl->h_out);
-  if (pl->ev_ok)
+  if (pl->ev_ok) {
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(pl->ev[i]);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(pl->evs[i / 2][i % 2]);
+  }
   delete pl;
   return SM_OK;
 }
@@ -188,9 +192,11 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   // ---- dispOptimize: sgm (stereoMatching.cpp:1051-1089) then WTA (:1108-1128)
   if (P.sgm_paths > 0) {
     for (int i = 0; i < views; i++) {
+      pl->sweeps[i] = false;
       if (P.sgm_paths == 8 && P.sgm_grouped) {
+        if (pl->timing) SM_CUDA(cudaEventRecord(pl->evs[i][0], c->stream));
         SM_TRY(smi_sgm8_grouped(c, pl->vol[i], pl->pix[i], H, W, D, P.sgm_corDifThres, P.sgm_reduCoeffi1, pl->vol[2],
-                                pl->disp[i]));
+                                pl->disp[i], pl->timing ? pl->evs[i][1] : nullptr, &pl->sweeps[i]));
       } else
       for (int k = 0; k < P.sgm_paths; k++) {
         // the last path also does gen_dispFromVm on the finished sum (saves one read of the volume)
@@ -223,6 +229,22 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
     }
   }
   PL_MARK(7);
+  return SM_OK;
+}
+
+extern "C" int sm_pipeline_sgm_split_ms(sm_pipeline* pl, float* out2) {
+  SM_CHECK_ARG(pl && out2 && pl->timing && pl->ev_ok);
+  SM_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+  float sgm = 0.f, sweeps = 0.f;
+  SM_CUDA(cudaEventElapsedTime(&sgm, pl->ev[4], pl->ev[5]));
+  for (int i = 0; i < 2; i++)
+    if (pl->sweeps[i]) {
+      float t = 0.f;
+      SM_CUDA(cudaEventElapsedTime(&t, pl->evs[i][0], pl->evs[i][1]));
+      sweeps += t;
+    }
+  out2[0] = sweeps;
+  out2[1] = sgm - sweeps;
   return SM_OK;
 }
 
@@ -267,6 +289,7 @@ extern "C" int sm_pipeline_enable_timing(sm_pipeline* pl, int on) {
   SM_CHECK_ARG(pl);
   if (on && !pl->ev_ok) {
     for (int i = 0; i <= ST_COUNT; i++) SM_CUDA(cudaEventCreate(&pl->ev[i]));
+    for (int i = 0; i < 4; i++) SM_CUDA(cudaEventCreate(&pl->evs[i / 2][i % 2]));
     pl->ev_ok = true;
   }
   pl->timing = on != 0;

@@ -376,11 +376,6 @@ __global__ void __launch_bounds__(32)
       }
       x[i] = sgm_lds4(st + cB + sB + pi * 4);
     }
-    __syncwarp();   // every lane has read the stage
-    if (lane == 0 && k + SGM_TNS < nStages) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(k + SGM_TNS, slot);
-    }
 #pragma unroll
     for (int i = 0; i < SGM_TK; i++) {
       const int xi = mu > 0 ? SGM_TK * k + i : W - 1 - (SGM_TK * k + i);
@@ -391,6 +386,10 @@ __global__ void __launch_bounds__(32)
         if (q < nq)
           *reinterpret_cast<float4*>(out + p * D + d0 + q * 4) = make_float4(s[i][4 * q], s[i][4 * q + 1], s[i][4 * q + 2], s[i][4 * q + 3]);
     }
+    // refill the stage: it was only read (generic proxy) and every lane has consumed what it read, so no proxy
+    // fence is needed -- one here would also wait for the warp's outstanding stores of S
+    __syncwarp();
+    if (lane == 0 && k + SGM_TNS < nStages) issue(k + SGM_TNS, slot);
     if (++slot == SGM_TNS) { slot = 0; parity ^= 1u; }
   }
 }
@@ -501,7 +500,8 @@ extern "C" int sm_sgm_path(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr
 
 // 8 paths, row-wise groups first (see sgm_group.cu); d_disp (nullable): WTA of the finished sum fused into the last path
 int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int corDifThres,
-                     int reduCoeffi1, float* d_sum, int16_t* d_disp) {
+                     int reduCoeffi1, float* d_sum, int16_t* d_disp, cudaEvent_t ev_after_sweeps, bool* used_sweeps) {
+  if (used_sweeps) *used_sweeps = false;
   int rc = smi_sgm_group(ctx, d_vol, d_pix, H, W, D, /*up*/1, /*mode*/0, corDifThres, reduCoeffi1, d_sum);
   if (rc == SM_ERR_UNSUPPORTED) {   // shape outside the grouped kernel: reference order, path by path
     for (int i = 0; i < 8; i++)
@@ -511,6 +511,8 @@ int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int
   }
   SM_TRY(rc);
   SM_TRY(smi_sgm_group(ctx, d_vol, d_pix, H, W, D, /*up*/0, /*mode*/1, corDifThres, reduCoeffi1, d_sum));
+  if (used_sweeps) *used_sweeps = true;
+  if (ev_after_sweeps) SM_CUDA(cudaEventRecord(ev_after_sweeps, ctx->stream));
   SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, 2, corDifThres, reduCoeffi1, 1, d_sum, nullptr));
   SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, 3, corDifThres, reduCoeffi1, d_disp ? 2 : 1, d_sum, d_disp));
   return SM_OK;

@@ -26,6 +26,10 @@
 // for float costs S agrees to a few ulp (tests: <= 1e-6 relative, the north star allows 1e-4) and the disparity
 // maps agree to >= 99.5 %.  The reference-order variant (sm_sgm) stays available and bit-exact.
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -113,7 +117,13 @@ struct sgmg_edges {
   float* rowsP;   // [nb][H][Dp]  first column of CTA b, path whose predecessor is column u+1 (read by CTA b-1)
   float* rowsM;   // [nb][H][Dp]  last column of CTA b, path whose predecessor is column u-1 (read by CTA b+1)
   int Dp;         // row pitch in floats: D values + 1 minimum, padded to a multiple of 4
+  unsigned long long* trace;   // diagnostics (SM_SGMG_TRACE=<file>): [cta][first|last][row]{t_publish, t_request, t_got, polls} in ns
 };
+__device__ __forceinline__ unsigned long long g_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define SGMG_SENTINEL 0xFFFFFFFFu   // a NaN pattern: never a valid Lr value or minimum
 
 __device__ __forceinline__ uint4 g_ld_relaxed16(const void* p) {
@@ -149,21 +159,32 @@ __device__ __forceinline__ void g_strow(uint32_t a, int nq, const float (&x)[VPL
   for (int q = 0; q < VPL / 4; q++)
     if (q < nq) g_sts16(a + q * 16, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
 }
-// wait for and read this lane's part of a neighbour CTA's published row (and the row minimum)
+// This lane's part of a neighbour CTA's published row (and the row minimum).  g_edge_issue starts the loads (at the
+// top of the row, so the L2 round trip overlaps the other two recurrences); g_edge_finish re-polls whatever still
+// carries the sentinel.
 template <int VPL>
-__device__ __forceinline__ void g_read_edge(const float* src, int nq, int D, float (&pr)[VPL], float& pm) {
+struct g_edge_regs { uint4 t[VPL / 4]; uint32_t m; };
+template <int VPL>
+__device__ __forceinline__ void g_edge_issue(const float* src, int nq, int D, g_edge_regs<VPL>& e) {
 #pragma unroll
   for (int q = 0; q < VPL / 4; q++) {
-    uint4 t = make_uint4(0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu);   // FLT_MAX padding
-    if (q < nq) {
-      do { t = g_ld_relaxed16(src + q * 4); }
-      while (t.x == SGMG_SENTINEL || t.y == SGMG_SENTINEL || t.z == SGMG_SENTINEL || t.w == SGMG_SENTINEL);
-    }
+    e.t[q] = make_uint4(0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu);   // FLT_MAX padding
+    if (q < nq) e.t[q] = g_ld_relaxed16(src + q * 4);
+  }
+  e.m = g_ld_relaxed4(src + D);   // src is lane-relative: the minimum sits at D - d0
+}
+template <int VPL>
+__device__ __forceinline__ void g_edge_finish(const float* src, int nq, int D, const g_edge_regs<VPL>& e, float (&pr)[VPL], float& pm,
+                                              int& polls) {
+#pragma unroll
+  for (int q = 0; q < VPL / 4; q++) {
+    uint4 t = e.t[q];
+    while (t.x == SGMG_SENTINEL || t.y == SGMG_SENTINEL || t.z == SGMG_SENTINEL || t.w == SGMG_SENTINEL) { t = g_ld_relaxed16(src + q * 4); polls++; }
     pr[4 * q] = __uint_as_float(t.x); pr[4 * q + 1] = __uint_as_float(t.y);
     pr[4 * q + 2] = __uint_as_float(t.z); pr[4 * q + 3] = __uint_as_float(t.w);
   }
-  uint32_t m;
-  do { m = g_ld_relaxed4(src + D); } while (m == SGMG_SENTINEL);   // src is lane-relative: the minimum sits at D - d0
+  uint32_t m = e.m;
+  while (m == SGMG_SENTINEL) m = g_ld_relaxed4(src + D);
   pm = __uint_as_float(m);
 }
 
@@ -171,16 +192,20 @@ __device__ __forceinline__ void g_read_edge(const float* src, int nq, int D, flo
 // UP = 1: rows H-1 .. 0, paths {0, 4, 5} (predecessor columns u, u-1, u+1).
 // MODE 0: S = LA + LB + LC; MODE 1: S = ((S + LA) + LB) + LC.   FULL: D == 32 * VPL (no padding lanes).
 template <int VPL, int UP, int MODE, bool FULL>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(448, 1)
     k_sgm_group(const float* __restrict__ vol, const uint32_t* __restrict__ pix, float* __restrict__ out, int H, int W, int D,
                 int corDifThres, float redu, sgmg_edges E) {
   extern __shared__ __align__(128) uint8_t gsm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
   const int nwarp = blockDim.x >> 5;   // widest CTA's column count
   const int b = blockIdx.x, nb = gridDim.x;
   const int u0 = (int)(((long long)b * W) / nb);
-  const int nCols = (int)(((long long)(b + 1) * W) / nb) - u0;   // >= 2 (host: nb <= W / 4)
-  if (warp >= nCols) return;                                     // no CTA-wide barrier below
+  const int nCols = (int)(((long long)(b + 1) * W) / nb) - u0;   // >= 4 (host: nb <= W / 4)
+  if ((int)(threadIdx.x >> 5) >= nCols) return;                  // no CTA-wide barrier below
+  // Column of this warp inside the CTA.  Rotated by two so that the two edge columns (the slowest: their far
+  // diagonal cannot interleave with the rest) do not share a warp scheduler (warp id mod 4) with each other, nor,
+  // for the usual 4k+1 columns, sit on the scheduler that carries one warp more than the others.
+  const int warp = ((int)(threadIdx.x >> 5) + nCols - 2) % nCols;
   const int u = u0 + warp;
   const int d0 = lane * VPL;
   const int nq = FULL ? VPL / 4 : (d0 < D ? min(VPL, D - d0) / 4 : 0);
@@ -225,10 +250,21 @@ __global__ void __launch_bounds__(512, 1)
   const float* farRow = (isFirst ? E.rowsM : E.rowsP) + (size_t)(nbrCta ? (isFirst ? b - 1 : b + 1) : b) * H * E.Dp + d0;
   const float P1r = 1.0f / redu, P2r = 3.0f / redu;
 
-  // pixel words (BGR packed): own column's next row, and the two diagonal predecessors of the next row
+  // pixel words (BGR packed), 32 rows at a time: lane i holds sweep row 32 * chunk + i of this column and of the two
+  // diagonal predecessor columns.  One strided fetch per 32 rows and three shuffles per row keep the LSU free for
+  // the edge polls, which otherwise queue behind these loads (L1 returns in order).
   const int ub = min(max(u + ob, 0), W - 1) - u, uc = min(max(u + oc, 0), W - 1) - u;
-  const uint32_t* px = pix + p0;
-  uint32_t xrow = *px, xpA = 0, xpB = 0, xpC = 0;
+  uint32_t curO = 0, curB = 0, curC = 0, nxtO = 0, nxtB = 0, nxtC = 0;
+  auto loadChunk = [&](int chunk, uint32_t& o_, uint32_t& b_, uint32_t& c_) {
+    const int rr = chunk * 32 + lane;
+    if (rr < H) {
+      const uint32_t* q = pix + (size_t)((long long)p0 + rowStep * rr);
+      o_ = q[0]; b_ = q[ub]; c_ = q[uc];
+    }
+  };
+  loadChunk(0, curO, curB, curC);
+  loadChunk(1, nxtO, nxtB, nxtC);
+  uint32_t xrow = __shfl_sync(0xffffffffu, curO, 0), xpA = 0, xpB = 0, xpC = 0;
   float* o = out + p0 * D + d0;
   const long long oStep = rowStep * D;
 
@@ -242,18 +278,14 @@ __global__ void __launch_bounds__(512, 1)
     const uint32_t bufOff = (r & 1) ? exBufB : 0u, pbufOff = exBufB - bufOff;
     const uint32_t mbufOff = (r & 1) ? minBufB : 0u, mpbufOff = minBufB - mbufOff;
     float c[VPL], s[VPL], lrA[VPL], lrB[VPL], lrC[VPL];
-    // next row's pixel words, one row ahead of their use
-    uint32_t xnext = 0, xnB = 0, xnC = 0;
-    if (r + 1 < H) { xnext = px[rowStep]; xnB = px[ub]; xnC = px[uc]; }
+    unsigned long long* tl = (E.trace && b == 70 && r >= 400 && r < 432 && lane == 0)
+                                 ? E.trace + (size_t)nb * 2 * H * 4 + ((size_t)warp * 32 + (r - 400)) * 8 : nullptr;
+    if (tl) tl[0] = g_now();
     const uint32_t st = stLo + slot * stageB + d0 * 4;
     g_mbar_wait(bars + slot * 8, parity);
     g_ldrow<VPL>(st, nq, c);
     if (MODE >= 1) g_ldrow<VPL>(st + runB, nq, s);
-    __syncwarp();
-    if (lane == 0 && r + SGMG_NS < H) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(r + SGMG_NS, slot);
-    }
+    if (tl) tl[1] = g_now();
     const uint32_t myB = exLo + bufOff + (uint32_t)warp * runB + d0 * 4, myC = myB + exPathB;
     const uint32_t myMinB = minLo + mbufOff + (uint32_t)warp * 4, myMinC = myMinB + minPathB;
     if (r == 0) {   // first row of the sweep: no predecessor inside the image -> Lr = C on all three paths
@@ -289,25 +321,33 @@ __global__ void __launch_bounds__(512, 1)
       g_strow<VPL>(myB, nq, lrB); g_strow<VPL>(myC, nq, lrC);
       if (lane == 0) { g_sts4(myMinB, mB); g_sts4(myMinC, mC); }
     } else {
-      // edge column.  The near diagonal and the vertical path first; the near row goes to the neighbour CTA at once.
-      // The far diagonal last, so the neighbour's store (issued early in ITS row) has had a row period to land.
+      // edge column.  The far diagonal's previous row is requested first and used last: the neighbour CTA stored it
+      // early in ITS previous row, and the L2 round trip runs under the near diagonal and the vertical path, which
+      // are independent and interleave.  The near row goes to the neighbour CTA as soon as it exists.
       float prN[VPL], lrN[VPL], lrF[VPL], mN, mF, mA;
+      g_edge_regs<VPL> er;
+      unsigned long long* tr = E.trace ? E.trace + ((size_t)(b * 2 + (isLast ? 1 : 0)) * H + r) * 4 : nullptr;
+      if (tr && lane == 0) tr[1] = g_now();
+      // (requesting the row one row period earlier, alone or in addition, was measured and is slower: a loop-carried
+      //  register set is copied at the loop head, which waits for the loads in flight)
+      if (nbrCta) g_edge_issue<VPL>(farRow, nq, D - d0, er);
       const uint32_t nearPath = nearIsB ? 0u : exPathB, nearMin = nearIsB ? 0u : minPathB;
       g_ldrow<VPL>(exLo + nearPath + pbufOff + (uint32_t)(warp + nearOff) * runB + d0 * 4, nq, prN);
       const float pmN = g_lds4(minLo + nearMin + mpbufOff + (uint32_t)(warp + nearOff) * 4);
       const uint32_t xpN = nearIsB ? xpB : xpC, xpF = nearIsB ? xpC : xpB;
       g_lr<VPL>(c, prN, pmN, (int)smd_absdiff_max3(xrow, xpN) > corDifThres, P1r, P2r, lane, lrN, mN);
+      g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
+      minA = mA;
       if (nbrCta) {
 #pragma unroll
         for (int q = 0; q < VPL / 4; q++)
           if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(lrN[4 * q], lrN[4 * q + 1], lrN[4 * q + 2], lrN[4 * q + 3]));
         if (lane == 0) __stcg(pubRow + D, mN);
-      }
-      g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
-      minA = mA;
-      if (nbrCta) {
+        if (tr && lane == 0) tr[0] = g_now();
         float prF[VPL], pmF;
-        g_read_edge<VPL>(farRow, nq, D - d0, prF, pmF);
+        int polls = 0;
+        g_edge_finish<VPL>(farRow, nq, D - d0, er, prF, pmF, polls);
+        if (tr && lane == 0) { tr[2] = g_now(); tr[3] = (unsigned long long)polls; }
         g_lr<VPL>(c, prF, pmF, (int)smd_absdiff_max3(xrow, xpF) > corDifThres, P1r, P2r, lane, lrF, mF);
       } else {   // predecessor column outside the image: Lr = C
 #pragma unroll
@@ -321,6 +361,7 @@ __global__ void __launch_bounds__(512, 1)
     }
 #pragma unroll
     for (int j = 0; j < VPL; j++) prevA[j] = lrA[j];
+    if (tl) tl[2] = g_now();
     // ---- path sum (gen_sgm_vm: sum += L[num], within the group in reference path order)
 #pragma unroll
     for (int q = 0; q < VPL / 4; q++)
@@ -335,15 +376,29 @@ __global__ void __launch_bounds__(512, 1)
         *reinterpret_cast<float4*>(o + q * 4) = t;
       }
     // advance to the next row of the sweep
-    xpA = xrow; xpB = xnB; xpC = xnC; xrow = xnext;
-    px += rowStep; o += oStep;
+    xpA = xrow;
+    xpB = __shfl_sync(0xffffffffu, curB, r & 31);
+    xpC = __shfl_sync(0xffffffffu, curC, r & 31);
+    if ((r & 31) == 31) {
+      curO = nxtO; curB = nxtB; curC = nxtC;
+      loadChunk((r >> 5) + 2, nxtO, nxtB, nxtC);
+    }
+    xrow = __shfl_sync(0xffffffffu, curO, (r + 1) & 31);
+    o += oStep;
     pubRow += E.Dp;
     if (r > 0) farRow += E.Dp;   // the far row read at row r is the neighbour's row r-1
+    // Refill this stage.  No proxy fence: the stage was only READ through the generic proxy, and every lane's reads
+    // have been consumed by arithmetic above (a fence.proxy.async here also waits for the warp's outstanding global
+    // stores and edge loads: measured 250 ns per row, 700 ns on the edge columns).
+    __syncwarp();
+    if (lane == 0 && r + SGMG_NS < H) issue(r + SGMG_NS, slot);
     if (++slot == SGMG_NS) { slot = 0; parity ^= 1u; }
+    if (tl) tl[3] = g_now();
     // the rows published in shared memory become visible to the two neighbour warps (and theirs to this one);
     // even pairs first, odd pairs second, so the pairwise barriers never ripple across the CTA
     if (warp & 1) { if (hasL) g_pair_bar(barL); if (hasR) g_pair_bar(barR); }
     else          { if (hasR) g_pair_bar(barR); if (hasL) g_pair_bar(barL); }
+    if (tl) tl[4] = g_now();
   }
 }
 
@@ -353,7 +408,7 @@ static int launch_group(sm_ctx* ctx, const float* vol, const uint32_t* pix, floa
                         int corDifThres, float redu) {
   const int nb = min(ctx->num_sms, W / 4);       // every CTA owns >= 4 columns: first and last column are distinct warps
   const int CW = sm_div_up(W, nb);               // widest CTA (columns b*W/nb .. (b+1)*W/nb - 1)
-  SM_CHECK_ARG(nb >= 1 && CW <= 16);             // 512 threads (register budget of three recurrences); 15 named barriers
+  SM_CHECK_ARG(nb >= 1 && CW <= 14);             // 448 threads (register budget of three recurrences); 15 named barriers
   const size_t runB = (size_t)D * 4;
   const size_t stageB = runB * (mode >= 1 ? 2 : 1);
   size_t smem = (size_t)CW * SGMG_NS * stageB + 2 * 2 * CW * runB + 2 * 2 * CW * 4;
@@ -368,6 +423,10 @@ static int launch_group(sm_ctx* ctx, const float* vol, const uint32_t* pix, floa
   E.rowsP = (float*)p;
   E.rowsM = (float*)((uint8_t*)p + rowsBytes);
   SM_CUDA(cudaMemsetAsync(p, 0xFF, 2 * rowsBytes, ctx->stream));   // sentinel: "row not published yet"
+  E.trace = nullptr;
+  const char* traceFile = getenv("SM_SGMG_TRACE");
+  const size_t traceBytes = ((size_t)nb * 2 * H * 4 + 16 * 32 * 8) * sizeof(unsigned long long);
+  if (traceFile) { SM_CUDA(cudaMalloc((void**)&E.trace, traceBytes)); SM_CUDA(cudaMemsetAsync(E.trace, 0, traceBytes, ctx->stream)); }
   void* args[] = {(void*)&vol, (void*)&pix, (void*)&out, (void*)&H, (void*)&W, (void*)&D,
                   (void*)&corDifThres, (void*)&redu, (void*)&E};
   const bool full = D == 32 * VPL;
@@ -380,6 +439,13 @@ static int launch_group(sm_ctx* ctx, const float* vol, const uint32_t* pix, floa
   // neighbouring CTAs wait on each other: all of them must be resident -> cooperative launch
   SM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(CW * 32), args, smem, ctx->stream));
   ctx->launches++;
+  if (traceFile) {   // diagnostics only: synchronous dump of the hand-off time stamps of this launch
+    std::vector<unsigned long long> h(traceBytes / 8);
+    SM_CUDA(cudaStreamSynchronize(ctx->stream));
+    SM_CUDA(cudaMemcpy(h.data(), E.trace, traceBytes, cudaMemcpyDeviceToHost));
+    SM_CUDA(cudaFree(E.trace));
+    if (FILE* f = fopen(traceFile, "wb")) { fwrite(h.data(), 1, traceBytes, f); fclose(f); }
+  }
   return SM_OK;
 }
 
@@ -396,7 +462,7 @@ int smi_sgm_group(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H,
     const int nb = min(ctx->num_sms, W / 4);
     const int CW = sm_div_up(W, nb);
     const size_t smem = (size_t)CW * SGMG_NS * D * 4 * (mode >= 1 ? 2 : 1) + 4 * (size_t)CW * D * 4 + 16 * CW + CW * SGMG_NS * 8 + 8;
-    if (smem > 227 * 1024 || CW > 16) return SM_ERR_UNSUPPORTED;
+    if (smem > 227 * 1024 || CW > 14) return SM_ERR_UNSUPPORTED;
   }
   if (vpl == 4) return up ? launch_group<4, 1>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
                           : launch_group<4, 0>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
