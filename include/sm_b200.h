@@ -224,6 +224,11 @@ int sm_vol_accumulate(sm_ctx* ctx, float* d_acc, const float* d_x, size_t n);
  * path-by-path order when the shape is unsupported (D % 4 != 0, D <= 64, very wide images). */
 int sm_sgm_grouped(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int corDifThres,
                    int reduCoeffi1, float* d_sum);
+/* The same for both views of a frame at once (StereoMatching::dispOptimize runs sgm() on vm[0] and vm[1],
+ * stereoMatching.cpp:1051-1089): each row sweep processes the left and the right volume in ONE launch, two thread
+ * blocks per SM, which hides the sweep's row-to-row latency.  Results are identical to two sm_sgm_grouped calls. */
+int sm_sgm_grouped2(sm_ctx* ctx, const float* d_volL, const float* d_volR, const uint8_t* d_bgrL, const uint8_t* d_bgrR,
+                    int H, int W, int D, int corDifThres, int reduCoeffi1, float* d_sumL, float* d_sumR);
 
 /* ---- disparity selection --------------------------------------------------- */
 /* gen_dispFromVm (stereoMatching.cpp:3928-3967), ChooseSmall = true. */

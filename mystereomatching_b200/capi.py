@@ -78,6 +78,7 @@ SIGNATURES = {
     "sm_sgm_path": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_sgm": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_sgm_grouped": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "sm_sgm_grouped2": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "sm_vol_accumulate": ([_P, _P, _P, _Z], _I),
     "sm_wta": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_wta_co": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
@@ -265,6 +266,13 @@ class Ctx:
         out = self.torch.empty_like(vol)
         check(self.L.sm_sgm_grouped(self.h, _ptr(vol), _ptr(bgr), H, W, D, thr, redu, _ptr(out)))
         return out
+
+    def sgm_grouped2(self, volL, volR, bgrL, bgrR, thr=15, redu=4):
+        H, W, D = volL.shape
+        outL, outR = self.torch.empty_like(volL), self.torch.empty_like(volR)
+        check(self.L.sm_sgm_grouped2(self.h, _ptr(volL), _ptr(volR), _ptr(bgrL), _ptr(bgrR), H, W, D, thr, redu,
+                                     _ptr(outL), _ptr(outR)))
+        return outL, outR
 
     def wta(self, vol):
         H, W, D = vol.shape

@@ -107,6 +107,11 @@ int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix,
                          int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp);
 
 // grouped SGM sweep (sgm_group.cu): up = 1 -> paths {0,4,5}, up = 0 -> paths {1,6,7}; mode 0 writes, 1 accumulates
+int smi_sgm_group2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int up, int mode,
+                   int corDifThres, int reduCoeffi1, float* const* d_sum);
+int smi_sgm8_grouped2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int corDifThres,
+                      int reduCoeffi1, float* const* d_sum, int16_t* const* d_disp, cudaEvent_t ev_after_sweeps = nullptr,
+                      bool* used_sweeps = nullptr);
 int smi_sgm_group(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int up, int mode,
                   int corDifThres, int reduCoeffi1, float* d_sum);
 

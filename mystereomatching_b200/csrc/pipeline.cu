@@ -21,7 +21,7 @@ struct sm_pipeline {
   uint32_t *pix[2] = {nullptr, nullptr}, *armpk[2] = {nullptr, nullptr};
   uint64_t* cen[2] = {nullptr, nullptr};
   uint16_t* arms[2] = {nullptr, nullptr};
-  float* vol[3] = {nullptr, nullptr, nullptr};  // vm[0], vm[1], scratch (roles rotate after SGM)
+  float* vol[4] = {nullptr, nullptr, nullptr, nullptr};  // vm[0], vm[1], scratch, second scratch (roles rotate after SGM)
   double* nlwork = nullptr;
   int16_t *disp[2] = {nullptr, nullptr}, *dtmp = nullptr;
   uint8_t* h_in = nullptr;   // pinned staging: bgrL | bgrR | grayL | grayR
@@ -47,7 +47,7 @@ extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
     cudaFree(pl->bgr[i]); cudaFree(pl->gray[i]); cudaFree(pl->pix[i]); cudaFree(pl->armpk[i]);
     cudaFree(pl->cen[i]); cudaFree(pl->arms[i]); cudaFree(pl->disp[i]);
   }
-  for (int i = 0; i < 3; i++) cudaFree(pl->vol[i]);
+  for (int i = 0; i < 4; i++) cudaFree(pl->vol[i]);
   cudaFree(pl->nlwork);
   cudaFree(pl->dtmp);
   if (pl->h_in) cudaFreeHost(pl->h_in);
@@ -82,7 +82,9 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->arms[i], npix * 5 * 2);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->disp[i], npix * 2);
   }
-  for (int i = 0; i < 3 && rc == SM_OK; i++) rc = pl_alloc(ctx, (void**)&pl->vol[i], nvol * sizeof(float));
+  // a fourth volume only where the two views' SGM sweeps can share a launch (two sums are written at once)
+  const bool two_view_sgm = p->sgm_paths == 8 && p->sgm_grouped && p->Do_refine && p->Do_LRConsis;
+  for (int i = 0; i < (two_view_sgm ? 4 : 3) && rc == SM_OK; i++) rc = pl_alloc(ctx, (void**)&pl->vol[i], nvol * sizeof(float));
   if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->dtmp, npix * 2);
   if (rc == SM_OK && p->aggregation == 2) rc = pl_alloc(ctx, (void**)&pl->nlwork, npix * (size_t)(pl->D + 1) * sizeof(double));
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_in, npix * 8) != cudaSuccess) rc = SM_ERR_NOMEM;
@@ -191,7 +193,29 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   PL_MARK(4);
   // ---- dispOptimize: sgm (stereoMatching.cpp:1051-1089) then WTA (:1108-1128)
   if (P.sgm_paths > 0) {
-    for (int i = 0; i < views; i++) {
+    bool done = false;
+    pl->sweeps[0] = pl->sweeps[1] = false;
+    if (P.sgm_paths == 8 && P.sgm_grouped && views == 2 && pl->vol[3]) {
+      // both views per sweep launch (two CTAs per SM); falls through to one view at a time if the shape does not fit
+      const float* vols[2] = {pl->vol[0], pl->vol[1]};
+      const uint32_t* pixs[2] = {pl->pix[0], pl->pix[1]};
+      float* sums[2] = {pl->vol[2], pl->vol[3]};
+      int16_t* disps[2] = {pl->disp[0], pl->disp[1]};
+      if (pl->timing) SM_CUDA(cudaEventRecord(pl->evs[0][0], c->stream));
+      const int rc = smi_sgm8_grouped2(c, vols, pixs, H, W, D, P.sgm_corDifThres, P.sgm_reduCoeffi1, sums, disps,
+                                       pl->timing ? pl->evs[0][1] : nullptr, &pl->sweeps[0]);
+      if (rc == SM_OK) {
+        for (int i = 0; i < 2; i++) {   // vm[i] <- path sum; the old cost volumes become the scratch
+          float* t = pl->vol[i];
+          pl->vol[i] = pl->vol[2 + i];
+          pl->vol[2 + i] = t;
+        }
+        done = true;
+      } else if (rc != SM_ERR_UNSUPPORTED) {
+        return rc;
+      }
+    }
+    for (int i = 0; i < views && !done; i++) {
       pl->sweeps[i] = false;
       if (P.sgm_paths == 8 && P.sgm_grouped) {
         if (pl->timing) SM_CUDA(cudaEventRecord(pl->evs[i][0], c->stream));

@@ -518,6 +518,45 @@ int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int
   return SM_OK;
 }
 
+// Both views of a frame: the two row sweeps run the left and the right volume in one launch each (two CTAs per SM),
+// then the horizontal paths per view.  SM_ERR_UNSUPPORTED when the shape does not fit two CTAs per SM.
+int smi_sgm8_grouped2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int corDifThres,
+                      int reduCoeffi1, float* const* d_sum, int16_t* const* d_disp, cudaEvent_t ev_after_sweeps, bool* used_sweeps) {
+  if (used_sweeps) *used_sweeps = false;
+  int rc = smi_sgm_group2(ctx, d_vol, d_pix, H, W, D, /*up*/1, /*mode*/0, corDifThres, reduCoeffi1, d_sum);
+  if (rc != SM_OK) return rc;
+  SM_TRY(smi_sgm_group2(ctx, d_vol, d_pix, H, W, D, /*up*/0, /*mode*/1, corDifThres, reduCoeffi1, d_sum));
+  if (used_sweeps) *used_sweeps = true;
+  if (ev_after_sweeps) SM_CUDA(cudaEventRecord(ev_after_sweeps, ctx->stream));
+  for (int i = 0; i < 2; i++) {
+    int16_t* dd = d_disp ? d_disp[i] : nullptr;
+    SM_TRY(smi_sgm_path_packed2(ctx, d_vol[i], d_pix[i], H, W, D, 2, corDifThres, reduCoeffi1, 1, d_sum[i], nullptr));
+    SM_TRY(smi_sgm_path_packed2(ctx, d_vol[i], d_pix[i], H, W, D, 3, corDifThres, reduCoeffi1, dd ? 2 : 1, d_sum[i], dd));
+  }
+  return SM_OK;
+}
+
+extern "C" int sm_sgm_grouped2(sm_ctx* ctx, const float* d_volL, const float* d_volR, const uint8_t* d_bgrL, const uint8_t* d_bgrR,
+                               int H, int W, int D, int corDifThres, int reduCoeffi1, float* d_sumL, float* d_sumR) {
+  SM_CHECK_ARG(ctx && d_volL && d_volR && d_bgrL && d_bgrR && d_sumL && d_sumR);
+  SM_CHECK_ARG(H > 0 && W > 0 && D > 0 && D <= 512 && reduCoeffi1 != 0);
+  SM_CHECK_ARG(d_volL != d_sumL && d_volR != d_sumR && d_sumL != d_sumR && d_volL != d_sumR && d_volR != d_sumL);
+  const long long npix = (long long)H * W;
+  void *pk0, *pk1;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_IMG0, npix * 4, &pk0));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_IMG1, npix * 4, &pk1));
+  SM_TRY(smi_pack_bgr(ctx, d_bgrL, npix, (uint32_t*)pk0));
+  SM_TRY(smi_pack_bgr(ctx, d_bgrR, npix, (uint32_t*)pk1));
+  const float* vols[2] = {d_volL, d_volR};
+  const uint32_t* pixs[2] = {(const uint32_t*)pk0, (const uint32_t*)pk1};
+  float* sums[2] = {d_sumL, d_sumR};
+  int rc = smi_sgm8_grouped2(ctx, vols, pixs, H, W, D, corDifThres, reduCoeffi1, sums, nullptr);
+  if (rc != SM_ERR_UNSUPPORTED) return rc;
+  for (int i = 0; i < 2; i++)   // shape outside the two-view launch: one view at a time
+    SM_TRY(smi_sgm8_grouped(ctx, vols[i], pixs[i], H, W, D, corDifThres, reduCoeffi1, sums[i], nullptr));
+  return SM_OK;
+}
+
 extern "C" int sm_sgm_grouped(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int corDifThres,
                               int reduCoeffi1, float* d_sum) {
   SM_CHECK_ARG(ctx && d_vol && d_bgr && d_sum);

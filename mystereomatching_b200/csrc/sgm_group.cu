@@ -17,7 +17,7 @@
 //     ITS OWN words until none is the sentinel (each word changes exactly once, so no ordering between words is
 //     needed).  That is one L2 round trip per row instead of store + fence + flag + load (measured 5.9 -> see
 //     DESIGN.md us per row);
-//   * C and S rows of the next SGMG_NS rows are staged per warp by the TMA unit (cp.async.bulk + mbarrier).
+//   * C and S rows of the next NS (4, or 2 when two views share an SM) rows are staged per warp by the TMA unit (cp.async.bulk + mbarrier).
 //
 // Arithmetic: every Lr value is computed exactly as updateCost<float> does (stereoMatching.h:2205-2280), so each
 // path volume is bit-identical to the reference's.  Only the ORDER in which the eight path volumes are added into
@@ -33,7 +33,6 @@
 
 #include "common.cuh"
 
-#define SGMG_NS 4   // rows of C / S in flight per warp
 
 __device__ __forceinline__ uint32_t g_f2key(float x) {
   uint32_t b = __float_as_uint(x);
@@ -191,14 +190,34 @@ __device__ __forceinline__ void g_edge_finish(const float* src, int nq, int D, c
 // UP = 0: rows 0 .. H-1, paths {1, 6, 7} (predecessor columns u, u+1, u-1).
 // UP = 1: rows H-1 .. 0, paths {0, 4, 5} (predecessor columns u, u-1, u+1).
 // MODE 0: S = LA + LB + LC; MODE 1: S = ((S + LA) + LB) + LC.   FULL: D == 32 * VPL (no padding lanes).
-template <int VPL, int UP, int MODE, bool FULL>
-__global__ void __launch_bounds__(448, 1)
-    k_sgm_group(const float* __restrict__ vol, const uint32_t* __restrict__ pix, float* __restrict__ out, int H, int W, int D,
-                int corDifThres, float redu, sgmg_edges E) {
+// One view of a frame for the sweep: NV = 2 runs the left and the right volume in ONE cooperative launch, two CTAs
+// per SM (one per view where the scheduler places them so): the kernel is latency-bound with 13 warps per SM, a
+// second, independent set of warps hides that.
+struct sgmg_view {
+  const float* vol;
+  const uint32_t* pix;
+  float* out;
+  float* rowsP;
+  float* rowsM;
+};
+template <int VPL, int UP, int MODE, bool FULL, int NS, int NV>
+__global__ void __launch_bounds__(448, NV)
+    k_sgm_group(const sgmg_view v0, const sgmg_view v1, int H, int W, int D, int corDifThres, float redu, int Dp,
+                unsigned long long* trace) {
   extern __shared__ __align__(128) uint8_t gsm[];
   const int lane = threadIdx.x & 31;
   const int nwarp = blockDim.x >> 5;   // widest CTA's column count
-  const int b = blockIdx.x, nb = gridDim.x;
+  const int nb = gridDim.x / NV;
+  const int view = NV == 2 ? (int)(blockIdx.x >= (unsigned)nb) : 0;
+  const int b = blockIdx.x - view * nb;
+  const float* __restrict__ vol = view ? v1.vol : v0.vol;
+  const uint32_t* __restrict__ pix = view ? v1.pix : v0.pix;
+  float* __restrict__ out = view ? v1.out : v0.out;
+  sgmg_edges E;
+  E.rowsP = view ? v1.rowsP : v0.rowsP;
+  E.rowsM = view ? v1.rowsM : v0.rowsM;
+  E.Dp = Dp;
+  E.trace = trace;
   const int u0 = (int)(((long long)b * W) / nb);
   const int nCols = (int)(((long long)(b + 1) * W) / nb) - u0;   // >= 4 (host: nb <= W / 4)
   if ((int)(threadIdx.x >> 5) >= nCols) return;                  // no CTA-wide barrier below
@@ -212,15 +231,15 @@ __global__ void __launch_bounds__(448, 1)
   const uint32_t runB = (uint32_t)D * 4;
   constexpr int ob = UP ? -1 : +1, oc = -ob;   // predecessor column offsets of paths B and C (reference order)
 
-  // shared memory: per warp SGMG_NS stages {C run, S run}; exchange rows [path][buf][CW][D]; minima [path][buf][CW]
+  // shared memory: per warp NS stages {C run, S run}; exchange rows [path][buf][CW][D]; minima [path][buf][CW]
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(gsm);
   const uint32_t stageB = runB * (MODE >= 1 ? 2 : 1);
-  const uint32_t stLo = base + (uint32_t)warp * SGMG_NS * stageB;
-  const uint32_t exLo = base + (uint32_t)nwarp * SGMG_NS * stageB;
+  const uint32_t stLo = base + (uint32_t)warp * NS * stageB;
+  const uint32_t exLo = base + (uint32_t)nwarp * NS * stageB;
   const uint32_t exBufB = (uint32_t)nwarp * runB, exPathB = 2u * exBufB;
   const uint32_t minLo = exLo + 2 * exPathB;
   const uint32_t minBufB = (uint32_t)nwarp * 4, minPathB = 2u * minBufB;
-  const uint32_t bars = minLo + 2 * minPathB + (uint32_t)warp * SGMG_NS * 8;   // (8-byte aligned: see host)
+  const uint32_t bars = minLo + 2 * minPathB + (uint32_t)warp * NS * 8;   // (8-byte aligned: see host)
 
   const long long rowStep = UP ? -(long long)W : (long long)W;   // pixels from one row of the sweep to the next
   const size_t p0 = (size_t)(UP ? H - 1 : 0) * W + u;            // first pixel of this column in sweep order
@@ -232,10 +251,10 @@ __global__ void __launch_bounds__(448, 1)
     if (MODE >= 1) g_bulk(st + runB, out + p * D, runB, bar);
   };
   if (lane == 0) {
-    for (int s = 0; s < SGMG_NS; s++) g_mbar_init(bars + s * 8, 1);
+    for (int s = 0; s < NS; s++) g_mbar_init(bars + s * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int r = 0; r < SGMG_NS && r < H; r++) issue(r, r);
+    for (int r = 0; r < NS && r < H; r++) issue(r, r);
   }
   __syncwarp();
 
@@ -391,8 +410,8 @@ __global__ void __launch_bounds__(448, 1)
     // have been consumed by arithmetic above (a fence.proxy.async here also waits for the warp's outstanding global
     // stores and edge loads: measured 250 ns per row, 700 ns on the edge columns).
     __syncwarp();
-    if (lane == 0 && r + SGMG_NS < H) issue(r + SGMG_NS, slot);
-    if (++slot == SGMG_NS) { slot = 0; parity ^= 1u; }
+    if (lane == 0 && r + NS < H) issue(r + NS, slot);
+    if (++slot == NS) { slot = 0; parity ^= 1u; }
     if (tl) tl[3] = g_now();
     // the rows published in shared memory become visible to the two neighbour warps (and theirs to this one);
     // even pairs first, odd pairs second, so the pairwise barriers never ripple across the CTA
@@ -403,69 +422,90 @@ __global__ void __launch_bounds__(448, 1)
 }
 
 // ------------------------------------------------------------------ host
-template <int VPL, int UP>
-static int launch_group(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, int H, int W, int D, int mode,
-                        int corDifThres, float redu) {
+template <int VPL, int UP, int NV>
+static int launch_group(sm_ctx* ctx, const float* const* vol, const uint32_t* const* pix, float* const* out, int H, int W, int D,
+                        int mode, int corDifThres, float redu) {
+  constexpr int NS = NV == 2 ? 2 : 4;
   const int nb = min(ctx->num_sms, W / 4);       // every CTA owns >= 4 columns: first and last column are distinct warps
   const int CW = sm_div_up(W, nb);               // widest CTA (columns b*W/nb .. (b+1)*W/nb - 1)
   SM_CHECK_ARG(nb >= 1 && CW <= 14);             // 448 threads (register budget of three recurrences); 15 named barriers
   const size_t runB = (size_t)D * 4;
   const size_t stageB = runB * (mode >= 1 ? 2 : 1);
-  size_t smem = (size_t)CW * SGMG_NS * stageB + 2 * 2 * CW * runB + 2 * 2 * CW * 4;
+  size_t smem = (size_t)CW * NS * stageB + 2 * 2 * CW * runB + 2 * 2 * CW * 4;
   smem = (smem + 7) & ~(size_t)7;
-  smem += (size_t)CW * SGMG_NS * 8;
+  smem += (size_t)CW * NS * 8;
   SM_CHECK_ARG(smem <= 227 * 1024);
-  sgmg_edges E;
-  E.Dp = (D + 1 + 3) & ~3;
-  const size_t rowsBytes = (size_t)nb * H * E.Dp * sizeof(float);
+  int Dp = (D + 1 + 3) & ~3;
+  const size_t rowsBytes = (size_t)nb * H * Dp * sizeof(float);
   void* p;
-  SM_TRY(sm_scratch_get(ctx, SM_SCR_SGMEDGE, 2 * rowsBytes, &p));
-  E.rowsP = (float*)p;
-  E.rowsM = (float*)((uint8_t*)p + rowsBytes);
-  SM_CUDA(cudaMemsetAsync(p, 0xFF, 2 * rowsBytes, ctx->stream));   // sentinel: "row not published yet"
-  E.trace = nullptr;
-  const char* traceFile = getenv("SM_SGMG_TRACE");
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_SGMEDGE, 2 * NV * rowsBytes, &p));
+  SM_CUDA(cudaMemsetAsync(p, 0xFF, 2 * NV * rowsBytes, ctx->stream));   // sentinel: "row not published yet"
+  sgmg_view v[2];
+  for (int i = 0; i < 2; i++) {
+    const int k = i < NV ? i : 0;
+    v[i].vol = vol[k]; v[i].pix = pix[k]; v[i].out = out[k];
+    v[i].rowsP = (float*)((uint8_t*)p + (size_t)(2 * k) * rowsBytes);
+    v[i].rowsM = (float*)((uint8_t*)p + (size_t)(2 * k + 1) * rowsBytes);
+  }
+  unsigned long long* trace = nullptr;
+  const char* traceFile = NV == 1 ? getenv("SM_SGMG_TRACE") : nullptr;
   const size_t traceBytes = ((size_t)nb * 2 * H * 4 + 16 * 32 * 8) * sizeof(unsigned long long);
-  if (traceFile) { SM_CUDA(cudaMalloc((void**)&E.trace, traceBytes)); SM_CUDA(cudaMemsetAsync(E.trace, 0, traceBytes, ctx->stream)); }
-  void* args[] = {(void*)&vol, (void*)&pix, (void*)&out, (void*)&H, (void*)&W, (void*)&D,
-                  (void*)&corDifThres, (void*)&redu, (void*)&E};
+  if (traceFile) { SM_CUDA(cudaMalloc((void**)&trace, traceBytes)); SM_CUDA(cudaMemsetAsync(trace, 0, traceBytes, ctx->stream)); }
+  void* args[] = {(void*)&v[0], (void*)&v[1], (void*)&H, (void*)&W, (void*)&D, (void*)&corDifThres, (void*)&redu, (void*)&Dp,
+                  (void*)&trace};
   const bool full = D == 32 * VPL;
-  const void* fn = full ? (mode == 0 ? (const void*)k_sgm_group<VPL, UP, 0, true> : (const void*)k_sgm_group<VPL, UP, 1, true>)
-                        : (mode == 0 ? (const void*)k_sgm_group<VPL, UP, 0, false> : (const void*)k_sgm_group<VPL, UP, 1, false>);
+  const void* fn = full ? (mode == 0 ? (const void*)k_sgm_group<VPL, UP, 0, true, NS, NV> : (const void*)k_sgm_group<VPL, UP, 1, true, NS, NV>)
+                        : (mode == 0 ? (const void*)k_sgm_group<VPL, UP, 0, false, NS, NV> : (const void*)k_sgm_group<VPL, UP, 1, false, NS, NV>);
   SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSM = 0;
   SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, CW * 32, smem));
-  SM_CHECK_ARG(perSM >= 1);
-  // neighbouring CTAs wait on each other: all of them must be resident -> cooperative launch
-  SM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(CW * 32), args, smem, ctx->stream));
+  if (perSM * ctx->num_sms < NV * nb) return SM_ERR_UNSUPPORTED;   // the CTAs wait on each other: all must be resident
+  SM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(NV * nb), dim3(CW * 32), args, smem, ctx->stream));
   ctx->launches++;
   if (traceFile) {   // diagnostics only: synchronous dump of the hand-off time stamps of this launch
     std::vector<unsigned long long> h(traceBytes / 8);
     SM_CUDA(cudaStreamSynchronize(ctx->stream));
-    SM_CUDA(cudaMemcpy(h.data(), E.trace, traceBytes, cudaMemcpyDeviceToHost));
-    SM_CUDA(cudaFree(E.trace));
+    SM_CUDA(cudaMemcpy(h.data(), trace, traceBytes, cudaMemcpyDeviceToHost));
+    SM_CUDA(cudaFree(trace));
     if (FILE* f = fopen(traceFile, "wb")) { fwrite(h.data(), 1, traceBytes, f); fclose(f); }
   }
   return SM_OK;
+}
+
+static bool group_shape_ok(sm_ctx* ctx, int H, int W, int D, int mode, int nv) {
+  if (!(D % 4 == 0 && D > 64 && D <= 256 && H >= 2 && W >= 8)) return false;
+  // Two views per launch need two CTAs per SM, i.e. <= 72 registers per thread: runs of 4 disparities per lane fit
+  // (D <= 128: 1.62 instead of 2.20 ms per view at 1280x720 D=128), runs of 8 spill and lose (6.1 vs 5.5 ms per
+  // view at 1920x1080 D=256).
+  if (nv == 2 && D > 128) return false;
+  const int ns = nv == 2 ? 2 : 4;
+  const int nb = min(ctx->num_sms, W / 4);
+  const int CW = sm_div_up(W, nb);
+  const size_t smem = (size_t)CW * ns * D * 4 * (mode >= 1 ? 2 : 1) + 4 * (size_t)CW * D * 4 + 16 * CW + CW * ns * 8 + 8;
+  return CW <= 14 && smem <= (size_t)(nv == 2 ? 113 : 227) * 1024;
 }
 
 // The two row-wise groups of the 8-path table: UP = paths {0,4,5}, DOWN = paths {1,6,7}.  mode 0: d_sum = group sum,
 // mode 1: d_sum += group sum.  Returns SM_ERR_UNSUPPORTED when the shape does not fit (caller falls back to paths).
 int smi_sgm_group(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int up, int mode,
                   int corDifThres, int reduCoeffi1, float* d_sum) {
-  const bool ok = D % 4 == 0 && D > 64 && D <= 256 && (((uintptr_t)d_vol | (uintptr_t)d_sum) & 15) == 0 && H >= 2 && W >= 8;
-  if (!ok) return SM_ERR_UNSUPPORTED;
+  if (!group_shape_ok(ctx, H, W, D, mode, 1) || ((((uintptr_t)d_vol | (uintptr_t)d_sum) & 15) != 0)) return SM_ERR_UNSUPPORTED;
   const float redu = (float)reduCoeffi1;
-  const int vpl = D <= 128 ? 4 : 8;
-  // shared memory per column must leave room for at least W/num_sms columns
-  {
-    const int nb = min(ctx->num_sms, W / 4);
-    const int CW = sm_div_up(W, nb);
-    const size_t smem = (size_t)CW * SGMG_NS * D * 4 * (mode >= 1 ? 2 : 1) + 4 * (size_t)CW * D * 4 + 16 * CW + CW * SGMG_NS * 8 + 8;
-    if (smem > 227 * 1024 || CW > 14) return SM_ERR_UNSUPPORTED;
-  }
-  if (vpl == 4) return up ? launch_group<4, 1>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
-                          : launch_group<4, 0>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
-  return up ? launch_group<8, 1>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
-            : launch_group<8, 0>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
+  if (D <= 128) return up ? launch_group<4, 1, 1>(ctx, &d_vol, &d_pix, &d_sum, H, W, D, mode, corDifThres, redu)
+                          : launch_group<4, 0, 1>(ctx, &d_vol, &d_pix, &d_sum, H, W, D, mode, corDifThres, redu);
+  return up ? launch_group<8, 1, 1>(ctx, &d_vol, &d_pix, &d_sum, H, W, D, mode, corDifThres, redu)
+            : launch_group<8, 0, 1>(ctx, &d_vol, &d_pix, &d_sum, H, W, D, mode, corDifThres, redu);
+}
+
+// Both views of a frame in one launch (two CTAs per SM).  SM_ERR_UNSUPPORTED: use smi_sgm_group per view.
+int smi_sgm_group2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int up, int mode,
+                   int corDifThres, int reduCoeffi1, float* const* d_sum) {
+  if (!group_shape_ok(ctx, H, W, D, mode, 2)) return SM_ERR_UNSUPPORTED;
+  for (int i = 0; i < 2; i++)
+    if ((((uintptr_t)d_vol[i] | (uintptr_t)d_sum[i]) & 15) != 0) return SM_ERR_UNSUPPORTED;
+  const float redu = (float)reduCoeffi1;
+  if (D <= 128) return up ? launch_group<4, 1, 2>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
+                          : launch_group<4, 0, 2>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
+  return up ? launch_group<8, 1, 2>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
+            : launch_group<8, 0, 2>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
 }

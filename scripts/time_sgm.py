@@ -14,4 +14,8 @@ def timeit(f, n=3):
     for _ in range(n): f()
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n * 1e3
+img2 = ctx.dev(p["bgrR"])
+vol2 = torch.rand((H, W, D), device="cuda")
+t2 = timeit(lambda: ctx.sgm_grouped2(vol, vol2, img, img2))
+print(f"{W}x{H} D={D}: sm_sgm_grouped2 (two views) {t2:.3f} ms = {t2 / 2:.3f} per view")
 print(f"{W}x{H} D={D}: sm_sgm(8) {timeit(lambda: ctx.sgm(vol, img, 8)):.3f} ms   sm_sgm_grouped {timeit(lambda: ctx.sgm_grouped(vol, img)):.3f} ms")

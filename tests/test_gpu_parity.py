@@ -388,6 +388,18 @@ def test_sgm_grouped_matches_reference_sum(ctx, shape):
     assert np.array_equal(ctx.sgm_grouped(ctx.dev(ivol), ctx.dev(bgr)).cpu().numpy(), po.sgm(ivol, bgr, 8))
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("shape", [(40, 64, 128), (37, 53, 132), (50, 200, 256), (64, 96, 68), (33, 600, 96)])
+def test_sgm_grouped_two_views_in_one_launch_equals_one_view_at_a_time(ctx, shape):
+    H, W, D = shape
+    rng = np.random.default_rng(H * W + D)
+    bgr = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(2)]
+    vol = [(rng.random((H, W, D)) * 2).astype(np.float32) for _ in range(2)]
+    one = [ctx.sgm_grouped(ctx.dev(vol[i]), ctx.dev(bgr[i])).cpu().numpy() for i in range(2)]
+    gl, gr = ctx.sgm_grouped2(ctx.dev(vol[0]), ctx.dev(vol[1]), ctx.dev(bgr[0]), ctx.dev(bgr[1]))
+    assert _bits_equal(gl.cpu().numpy(), one[0]) and _bits_equal(gr.cpu().numpy(), one[1])
+
+
 @pytest.mark.timeout(180)
 def test_pipeline_reference_order_is_bit_exact_and_grouped_agrees(ctx):
     H, W, D = 80, 144, 96
@@ -423,6 +435,12 @@ def test_full_size_grouped_sweeps_equal_sum_of_single_path_kernels(ctx):
     assert torch.equal(got.view(torch.int32), acc.view(torch.int32))
     # and a second call gives the same bits (edge hand-off buffers are re-armed per launch)
     assert torch.equal(ctx.sgm_grouped(vol, bgr).view(torch.int32), got.view(torch.int32))
+    # both views in one launch (two CTAs per SM): the same bits for each
+    bgr2 = ctx.dev(p["bgrR"])
+    vol2 = torch.rand((H, W, D), device="cuda", generator=g) * 2
+    gl, gr = ctx.sgm_grouped2(vol, vol2, bgr, bgr2)
+    assert torch.equal(gl.view(torch.int32), got.view(torch.int32))
+    assert torch.equal(gr.view(torch.int32), ctx.sgm_grouped(vol2, bgr2).view(torch.int32))
 
 
 @pytest.mark.timeout(300)
