@@ -205,7 +205,9 @@ def stage_bytes(name):
     if sgm_is_grouped(name):
         # per view: sweep UP writes S (C + S = 2 V b), sweep DOWN read-modify-writes it (3 V b); then paths 2 and 3
         # (C, S in, S out = 3 V b each; the fused WTA of path 3 still leaves the summed volume behind as vm)
-        st["sgm_group"] = {"bytes_per_launch": 2.5 * V * b, "launches": 4, "kernel": "k_sgm_group"}
+        # (D <= 128: both views share a launch, two CTAs per SM: 2 launches of twice the bytes)
+        nl = 2 if D <= 128 else 4
+        st["sgm_group"] = {"bytes_per_launch": 10.0 / nl * V * b, "launches": nl, "kernel": "k_sgm_group"}
         st["sgm_path"] = {"bytes_per_launch": 3 * V * b, "launches": 4, "kernel": "k_sgm_path"}
     else:
         # first path writes S (2 V b), the others read-modify-write it (3 V b)
