@@ -164,35 +164,35 @@ __global__ void k_tree_adj(int H, int W, const uint8_t* __restrict__ ew, const u
 // depth, not the barrier; prefetching the next level's static data one level ahead did not change the time.
 #define NL_CLUSTER 8
 #define NL_CTA 1024
+#define NL_TF_CTA 512
 
 struct nl_sync {
   int cnt[3];           // BFS: nodes appended per level, rotating (level % 3)
   int nlevels;          // BFS result: number of levels
 };
 
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 // BFS from pixel 0 over the tree adjacency: parent, depth (rank), weight of the edge to the parent, the node list
 // grouped by level (order) and the level boundaries (level_start[l] .. level_start[l+1]).  One barrier per level:
 // the per-level append counters rotate over three slots so a counter is reset two levels after its last reader.
-__global__ void __cluster_dims__(NL_CLUSTER, 1, 1) __launch_bounds__(NL_CTA)
+// ONE CTA: a level holds tens of nodes on average (image MSTs are deep: 4366 levels for 640x480), so the time is
+// (levels) x (hand-off latency), and a CTA barrier plus an L1/L2 access on one SM (~0.5 us per level) beats any
+// barrier across SMs (cluster or grid: ~2.6 us per level, measured).
+__global__ void __launch_bounds__(NL_CTA)
     k_tree_bfs(int N, const int* __restrict__ nbr, const uint8_t* __restrict__ nbw, const uint8_t* __restrict__ deg,
-               int* __restrict__ parent, uint8_t* __restrict__ wpar, int* __restrict__ rank, int* __restrict__ order,
-               int* __restrict__ level_start, nl_sync* s) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+               int* parent, uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* s) {
+  __shared__ int cnt[2];
+  const int tid = threadIdx.x, nth = blockDim.x;
   if (tid == 0) {
     parent[0] = 0; wpar[0] = 0; rank[0] = 0; order[0] = 0; level_start[0] = 0;
-    s->cnt[0] = 0; s->cnt[1] = 0; s->cnt[2] = 0;
+    cnt[0] = 0; cnt[1] = 0;
   }
-  cluster_barrier();
+  __syncthreads();
   int head = 0, tail = 1, level = 0;
   while (head < tail) {
-    int* cnt_next = &s->cnt[(level + 1) % 3];
-    if (tid == 0) s->cnt[(level + 2) % 3] = 0;   // last read after the barrier two levels ago
+    int* cnt_next = &cnt[(level + 1) & 1];
     for (int i = head + tid; i < tail; i += nth) {
-      const int v = __ldcg(order + i), p = __ldcg(parent + v), n = deg[v];
+      const int v = order[i], p = parent[v], n = deg[v];
       for (int k = 0; k < n; k++) {
         const int c = nbr[(size_t)v * 4 + k];
         if (c == p) continue;   // the root's parent is itself and never appears among its neighbours
@@ -202,10 +202,11 @@ __global__ void __cluster_dims__(NL_CLUSTER, 1, 1) __launch_bounds__(NL_CTA)
         order[tail + atomicAdd(cnt_next, 1)] = c;
       }
     }
-    cluster_barrier();                      // all appends of this level are done and visible
-    const int added = __ldcg(cnt_next);
+    __syncthreads();                        // all appends of this level are done and visible
+    const int added = *cnt_next;
     head = tail; tail += added; level++;
-    if (tid == 0) level_start[level] = head;
+    if (tid == 0) { level_start[level] = head; cnt[level & 1 ^ 1] = 0; }   // the counter of the level after next
+    __syncthreads();
   }
   if (tid == 0) { s->nlevels = level; level_start[level] = head; }
 }
@@ -248,52 +249,61 @@ __global__ void k_level_bounds(int N, const int* __restrict__ rank, const int* _
 }
 
 // ------------------------------------------------------------------ tree filter
-// A: [N][Dp] doubles (Dp = D, or D+1 with the all-ones plane at index D).
+// A: Dp planes of N doubles (Dp = D, or D+1 with the all-ones plane at index D), element (v, d) at A[v * sn + d * sd]:
+// plane-major (sn = 1, sd = N) for the work buffer the filter owns, node-major (sn = D, sd = 1) in place for
+// qx_tree_filter::filter's own layout.
 __global__ void k_tf_load(const float* __restrict__ vol, double* __restrict__ A, size_t N, int D, int Dp) {
   const size_t n = N * Dp;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t v = i / Dp;
-    const int d = (int)(i - v * Dp);
-    A[i] = d < D ? (double)vol[v * D + d] : 1.0;
+    const size_t d = i / N, v = i - d * N;
+    A[i] = d < (size_t)D ? (double)vol[v * D + d] : 1.0;
   }
 }
 
-__global__ void __cluster_dims__(NL_CLUSTER, 1, 1) __launch_bounds__(NL_CTA)
-    k_tf_sweeps(double* __restrict__ A, int Dp, const int* __restrict__ parent, const uint8_t* __restrict__ wpar,
-                const int* __restrict__ child, const uint8_t* __restrict__ nchild, const int* __restrict__ order,
-                const int* __restrict__ level_start, const double* __restrict__ table, nl_sync* s) {
+// The two sweeps.  Planes never interact, so the volume is split BY PLANE: a CTA owns a few planes of ALL nodes and
+// walks the levels alone, one __syncthreads per level; no barrier across SMs is needed at all (the cluster-wide
+// version cost 2.6 us per level, this one ~0.5 us: a level's values are produced and consumed on the same SM).
+// Per (node, plane) the operations and their order are exactly the reference's, so the result is bit-identical.
+__global__ void __launch_bounds__(NL_TF_CTA)
+    k_tf_sweeps(double* A, size_t sn, size_t sd, int Dp, int planesPerCta, const int* __restrict__ parent,
+                const uint8_t* __restrict__ wpar, const int* __restrict__ child, const uint8_t* __restrict__ nchild,
+                const int* __restrict__ order, const int* __restrict__ level_start, const double* __restrict__ table,
+                const nl_sync* __restrict__ s) {
   __shared__ double tab[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = table[i];
   __syncthreads();
   const int nlevels = s->nlevels;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const int dlo = blockIdx.x * planesPerCta, np = min(planesPerCta, Dp - dlo);
+  if (np <= 0) return;
   // leaf to root: backup[p] += sum over children (adjacency order) of w(c) * backup[c]
   for (int l = nlevels - 2; l >= 0; l--) {
     const int lo = level_start[l], cnt = level_start[l + 1] - lo;
-    for (long long t = tid; t < (long long)cnt * Dp; t += nth) {
-      const int i = (int)(t / Dp), d = (int)(t - (long long)i * Dp);
+    for (int t = threadIdx.x; t < cnt * np; t += blockDim.x) {
+      const int i = t / np, d = dlo + (t - i * np);
       const int v = order[lo + i], nc = nchild[v];
       if (nc == 0) continue;
-      double acc = A[(size_t)v * Dp + d];   // this node's own cost: written before the kernel
+      double* a = A + (size_t)d * sd;
+      double acc = a[(size_t)v * sn];   // this node's own cost: written before the kernel
       for (int k = 0; k < nc; k++) {
         const int c = child[(size_t)v * 4 + k];
-        acc += __ldcg(A + (size_t)c * Dp + d) * tab[wpar[c]];
+        acc += a[(size_t)c * sn] * tab[wpar[c]];
       }
-      A[(size_t)v * Dp + d] = acc;
+      a[(size_t)v * sn] = acc;
     }
-    cluster_barrier();
+    __syncthreads();
   }
   // root to leaf: cost[i] = w * (cost[parent] - w * backup[i]) + backup[i]   (the root keeps backup)
   for (int l = 1; l < nlevels; l++) {
     const int lo = level_start[l], cnt = level_start[l + 1] - lo;
-    for (long long t = tid; t < (long long)cnt * Dp; t += nth) {
-      const int i = (int)(t / Dp), d = (int)(t - (long long)i * Dp);
+    for (int t = threadIdx.x; t < cnt * np; t += blockDim.x) {
+      const int i = t / np, d = dlo + (t - i * np);
       const int v = order[lo + i];
+      double* a = A + (size_t)d * sd;
       const double w = tab[wpar[v]];
-      const double b = __ldcg(A + (size_t)v * Dp + d);
-      A[(size_t)v * Dp + d] = w * (__ldcg(A + (size_t)parent[v] * Dp + d) - w * b) + b;
+      const double b = a[(size_t)v * sn];
+      a[(size_t)v * sn] = w * (a[(size_t)parent[v] * sn] - w * b) + b;
     }
-    cluster_barrier();
+    __syncthreads();
   }
 }
 
@@ -302,8 +312,8 @@ __global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t v = i / D;
     const int d = (int)(i - v * D);
-    const float x = (float)A[v * Dp + d];                     // NLCCA::aggreCV: (float)nlcP[d]
-    vol[i] = Dp > D ? x / (float)A[v * Dp + D] : x;           // StereoMatching::NL: vm[0] /= wetNL
+    const float x = (float)A[(size_t)d * N + v];                     // NLCCA::aggreCV: (float)nlcP[d]
+    vol[i] = Dp > D ? x / (float)A[(size_t)D * N + v] : x;           // StereoMatching::NL: vm[0] /= wetNL
   }
 }
 
@@ -314,12 +324,6 @@ struct nl_tree {   // device buffers of one rooted tree (owned by the ctx scratc
   nl_sync* sync;
 };
 
-static int cluster_launch(sm_ctx* ctx, const void* fn, void** args) {
-  // one cluster (the __cluster_dims__ attribute of the kernel fixes its shape)
-  SM_CUDA(cudaLaunchKernel(fn, dim3(NL_CLUSTER), dim3(NL_CTA), args, 0, ctx->stream));
-  ctx->launches++;
-  return SM_OK;
-}
 
 // MST + rooting.  img: [H][W][cn] u8 (already median-filtered).  Fills t (buffers must be allocated).
 static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn, nl_tree& t) {
@@ -366,7 +370,8 @@ static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn
   {
     void* args[] = {(void*)&N, (void*)&nbr, (void*)&nbw, (void*)&deg, (void*)&t.parent, (void*)&t.wpar, (void*)&t.rank,
                     (void*)&t.order, (void*)&t.level_start, (void*)&t.sync};
-    SM_TRY(cluster_launch(ctx, (const void*)k_tree_bfs, args));
+    SM_CUDA(cudaLaunchKernel((const void*)k_tree_bfs, dim3(1), dim3(NL_CTA), args, 0, ctx->stream));
+    ctx->launches++;
   }
   return SM_OK;
 }
@@ -410,10 +415,12 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
   const int TB = 256, g = (int)min((size_t)ctx->num_sms * 16, (N * Dp + TB - 1) / TB);
   if (d_vol) SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp);
   {
-    int dp = Dp;
-    void* args[] = {(void*)&d_A, (void*)&dp, (void*)&t.parent, (void*)&t.wpar, (void*)&t.child, (void*)&t.nchild,
-                    (void*)&t.order, (void*)&t.level_start, (void*)&d_tab, (void*)&t.sync};
-    SM_TRY(cluster_launch(ctx, (const void*)k_tf_sweeps, args));
+    // one CTA per plane while there are SMs for them, else the same number of planes for every CTA
+    const int ppc = sm_div_up(Dp, min(Dp, ctx->num_sms));
+    const int grid = sm_div_up(Dp, ppc);
+    const size_t sn = d_vol ? 1 : (size_t)D, sd = d_vol ? N : 1;
+    SM_LAUNCH(ctx, k_tf_sweeps, grid, NL_TF_CTA, 0, d_A, sn, sd, Dp, ppc, t.parent, t.wpar, t.child, t.nchild, t.order,
+              t.level_start, d_tab, t.sync);
   }
   if (d_vol) SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp);
   return SM_OK;
