@@ -152,19 +152,21 @@ __global__ void k_tree_adj(int H, int W, const uint8_t* __restrict__ ew, const u
   deg[v] = (uint8_t)n;
 }
 
-// ------------------------------------------------------------------ level-synchronous kernels: ONE thread-block cluster
-// A tree level holds a few dozen to a few thousand nodes, so the level loops are latency bound: what matters is
-// the cost of the barrier between levels, not the number of SMs.  Both level-synchronous kernels therefore run as
-// a single cluster of NL_CLUSTER CTAs x 1024 threads and synchronise with the hardware cluster barrier
-// (barrier.cluster.arrive.release / wait.acquire, a few hundred ns) instead of a grid-wide atomic barrier in L2
-// (measured ~3 us per level on 148 CTAs).  Data written in one level and read in the next crosses CTAs through
-// L2: those loads use ld.global.cg.
-// Measured (B200, 640x480, depth 4366): 2.6-2.8 us per level either way -- the level-to-level hand-off through L2
-// (store acknowledge, barrier with release/acquire, dependent load) is the floor, so the remaining lever is tree
-// depth, not the barrier; prefetching the next level's static data one level ahead did not change the time.
-#define NL_CLUSTER 8
+// ------------------------------------------------------------------ level-synchronous kernels
+// A tree level holds a few dozen to a few thousand nodes and image MSTs are deep (4366 levels at 640x480, 17051 at
+// 1920x1080), so rooting and filtering are latency bound: time = levels x (cost of handing a level's results to the
+// next).  Measured on B200: any barrier ACROSS SMs costs 2.6-2.8 us per level (hardware cluster barrier of 8 CTAs and
+// a grid-wide atomic barrier alike: store acknowledge + release/acquire + dependent L2 load).  Both kernels therefore
+// keep every dependency inside ONE SM and synchronise with __syncthreads only:
+//   * k_tree_bfs: a single CTA, the frontier as (node, parent) pairs in shared memory -> one dependent global access
+//     (the adjacency record) per level, ~1.0 us per level;
+//   * k_tf_sweeps: the volume is split by PLANE (planes never interact), one CTA per plane walking all levels, the
+//     values of the adjacent level in shared memory, records and own values fetched four levels ahead, level bounds in
+//     shared memory: ~0.9 us per level (what remains is the dependent instruction chain of the few working threads).
 #define NL_CTA 1024
 #define NL_TF_CTA 512
+#define NL_TF_CAP 4096   // nodes of a level kept in shared memory (x planes per CTA; 2 buffers of doubles: 64 KB)
+#define NL_TF_LS 32768   // level bounds kept in shared memory (128 KB); deeper trees read the rest from global memory
 
 struct nl_sync {
   int cnt[3];           // BFS: nodes appended per level, rotating (level % 3)
@@ -178,28 +180,46 @@ struct nl_sync {
 // ONE CTA: a level holds tens of nodes on average (image MSTs are deep: 4366 levels for 640x480), so the time is
 // (levels) x (hand-off latency), and a CTA barrier plus an L1/L2 access on one SM (~0.5 us per level) beats any
 // barrier across SMs (cluster or grid: ~2.6 us per level, measured).
+#define NL_BFS_FCAP 8192   // frontier entries (node, parent) kept in shared memory per level (2 x 64 KB)
 __global__ void __launch_bounds__(NL_CTA)
-    k_tree_bfs(int N, const int* __restrict__ nbr, const uint8_t* __restrict__ nbw, const uint8_t* __restrict__ deg,
+    k_tree_bfs(int N, const int4* __restrict__ nbr, const uchar4* __restrict__ nbw, const uint8_t* __restrict__ deg,
                int* parent, uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* s) {
+  // The frontier of a level lives in shared memory as (node, parent) pairs, so a level costs ONE dependent global
+  // access (the node's adjacency record) instead of order -> parent -> adjacency.
+  extern __shared__ int2 fr[];   // [2][NL_BFS_FCAP]
   __shared__ int cnt[2];
   const int tid = threadIdx.x, nth = blockDim.x;
   if (tid == 0) {
     parent[0] = 0; wpar[0] = 0; rank[0] = 0; order[0] = 0; level_start[0] = 0;
     cnt[0] = 0; cnt[1] = 0;
+    fr[0] = make_int2(0, 0);
   }
   __syncthreads();
   int head = 0, tail = 1, level = 0;
   while (head < tail) {
     int* cnt_next = &cnt[(level + 1) & 1];
-    for (int i = head + tid; i < tail; i += nth) {
-      const int v = order[i], p = parent[v], n = deg[v];
-      for (int k = 0; k < n; k++) {
-        const int c = nbr[(size_t)v * 4 + k];
+    const int2* cur = fr + (size_t)(level & 1) * NL_BFS_FCAP;
+    int2* nxt = fr + (size_t)((level + 1) & 1) * NL_BFS_FCAP;
+    for (int i = tid; i < tail - head; i += nth) {
+      int v, p;
+      if (i < NL_BFS_FCAP) { const int2 e = cur[i]; v = e.x; p = e.y; }
+      else { v = order[head + i]; p = parent[v]; }
+      const int n = deg[v];
+      const int4 nb = nbr[v];
+      const uchar4 nw = nbw[v];
+      const int c4[4] = {nb.x, nb.y, nb.z, nb.w};
+      const uint8_t w4[4] = {nw.x, nw.y, nw.z, nw.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k >= n) continue;
+        const int c = c4[k];
         if (c == p) continue;   // the root's parent is itself and never appears among its neighbours
         parent[c] = v;
         rank[c] = level + 1;
-        wpar[c] = nbw[(size_t)v * 4 + k];
-        order[tail + atomicAdd(cnt_next, 1)] = c;
+        wpar[c] = w4[k];
+        const int slot = atomicAdd(cnt_next, 1);
+        order[tail + slot] = c;
+        if (slot < NL_BFS_FCAP) nxt[slot] = make_int2(c, v);
       }
     }
     __syncthreads();                        // all appends of this level are done and visible
@@ -252,68 +272,190 @@ __global__ void k_level_bounds(int N, const int* __restrict__ rank, const int* _
 // A: Dp planes of N doubles (Dp = D, or D+1 with the all-ones plane at index D), element (v, d) at A[v * sn + d * sd]:
 // plane-major (sn = 1, sd = N) for the work buffer the filter owns, node-major (sn = D, sd = 1) in place for
 // qx_tree_filter::filter's own layout.
-__global__ void k_tf_load(const float* __restrict__ vol, double* __restrict__ A, size_t N, int D, int Dp) {
+__global__ void k_tf_load(const float* __restrict__ vol, double* __restrict__ A, size_t N, int D, int Dp,
+                          const int* __restrict__ order) {
+  // work buffer: plane-major AND level-ordered, element (position q of `order`, plane d) at A[d * N + q]
   const size_t n = N * Dp;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t d = i / N, v = i - d * N;
-    A[i] = d < (size_t)D ? (double)vol[v * D + d] : 1.0;
+    const size_t d = i / N, q = i - d * N;
+    A[i] = d < (size_t)D ? (double)vol[(size_t)order[q] * D + d] : 1.0;
+  }
+}
+
+// Level-ordered records of the rooted tree, so that a level's static data is read contiguously (and one level
+// ahead) instead of through order -> node -> child -> value chains:
+//   position i of `order` (node v = order[i]):  rnc[i] = number of children, rcp[i][k] = position of child k INSIDE
+//   its level (the next deeper one), rcw[i] = the four child weights packed, rpp[i] = position of the parent inside
+//   its level, rw[i] = weight of the edge to the parent.
+__global__ void k_tf_positions(int N, const int* __restrict__ order, int* __restrict__ pos) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) pos[order[i]] = i;
+}
+__global__ void k_tf_records(int N, const int* __restrict__ order, const int* __restrict__ pos, const int* __restrict__ rank,
+                             const int* __restrict__ level_start, const int* __restrict__ parent,
+                             const uint8_t* __restrict__ wpar, const int* __restrict__ child, const uint8_t* __restrict__ nchild,
+                             int4* __restrict__ rcp, uint32_t* __restrict__ rcw, uint8_t* __restrict__ rnc, int* __restrict__ rpp,
+                             uint8_t* __restrict__ rw) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int v = order[i], l = rank[v], nc = nchild[v];
+    int cp[4] = {0, 0, 0, 0};
+    uint32_t cw = 0;
+    for (int k = 0; k < nc; k++) {
+      const int c = child[(size_t)v * 4 + k];
+      cp[k] = pos[c] - level_start[l + 1];
+      cw |= (uint32_t)wpar[c] << (8 * k);
+    }
+    rcp[i] = make_int4(cp[0], cp[1], cp[2], cp[3]);
+    rcw[i] = cw;
+    rnc[i] = (uint8_t)nc;
+    rpp[i] = l > 0 ? pos[parent[v]] - level_start[l - 1] : 0;
+    rw[i] = wpar[v];
   }
 }
 
 // The two sweeps.  Planes never interact, so the volume is split BY PLANE: a CTA owns a few planes of ALL nodes and
 // walks the levels alone, one __syncthreads per level; no barrier across SMs is needed at all (the cluster-wide
-// version cost 2.6 us per level, this one ~0.5 us: a level's values are produced and consumed on the same SM).
+// version cost 2.6 us per level).  A level only consumes the level next to it, which this CTA has just produced:
+// those values are kept in shared memory (two level buffers of NL_TF_CAP nodes; wider levels fall back to global
+// memory for the excess), and each thread fetches its first item of the NEXT level -- record and own value, which
+// do not depend on the level in progress -- before it works on the current one.  What is left per level is a
+// barrier, a shared-memory read and the arithmetic.
 // Per (node, plane) the operations and their order are exactly the reference's, so the result is bit-identical.
+struct nl_up_item { int v; int nc; int4 cp; uint32_t cw; double own; };
+struct nl_dn_item { int v; int pp; uint32_t w; double own; };
+#define NL_TF_PF 4   // levels fetched ahead (first item of every thread)
+
+// LEVELORD: A is the filter's own work buffer, plane-major and level-ordered (A[d * N + position]): every address of a
+// level is known from the level bounds alone.  Otherwise A is the caller's node-major array (A[v * sn + d * sd]) and
+// the node index comes from `order`.
+template <bool LEVELORD, bool NP1>
 __global__ void __launch_bounds__(NL_TF_CTA)
-    k_tf_sweeps(double* A, size_t sn, size_t sd, int Dp, int planesPerCta, const int* __restrict__ parent,
-                const uint8_t* __restrict__ wpar, const int* __restrict__ child, const uint8_t* __restrict__ nchild,
-                const int* __restrict__ order, const int* __restrict__ level_start, const double* __restrict__ table,
-                const nl_sync* __restrict__ s) {
+    k_tf_sweeps(double* A, size_t sn, size_t sd, int Dp, int planesPerCta, int cap, const int* __restrict__ order,
+                const int* __restrict__ level_start, const int4* __restrict__ rcp, const uint32_t* __restrict__ rcw,
+                const uint8_t* __restrict__ rnc, const int* __restrict__ rpp, const uint8_t* __restrict__ rw,
+                const double* __restrict__ table, const nl_sync* __restrict__ s) {
+  extern __shared__ double lv[];   // [2][cap * planesPerCta] values of two adjacent levels, then NL_TF_LS level bounds
   __shared__ double tab[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = table[i];
-  __syncthreads();
   const int nlevels = s->nlevels;
-  const int dlo = blockIdx.x * planesPerCta, np = min(planesPerCta, Dp - dlo);
+  // the level bounds are read by every warp at every level: from shared memory, not through L1/L2
+  int* ls = reinterpret_cast<int*>(lv + 2 * (size_t)cap * planesPerCta);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = table[i];
+  for (int i = threadIdx.x; i <= nlevels && i < NL_TF_LS; i += blockDim.x) ls[i] = level_start[i];
+  __syncthreads();
+  const uint32_t lsAddr = (uint32_t)__cvta_generic_to_shared(ls);
+  auto lstart = [&](int l) -> int {
+    if (l >= NL_TF_LS) return level_start[l];
+    int v;   // explicit ld.shared: through the cast pointer the compiler emits a generic load
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(lsAddr + (uint32_t)l * 4) : "memory");
+    return v;
+  };
+  const int dlo = blockIdx.x * planesPerCta, np = NP1 ? 1 : min(planesPerCta, Dp - dlo);   // NP1: one plane per CTA
   if (np <= 0) return;
-  // leaf to root: backup[p] += sum over children (adjacency order) of w(c) * backup[c]
-  for (int l = nlevels - 2; l >= 0; l--) {
-    const int lo = level_start[l], cnt = level_start[l + 1] - lo;
-    for (int t = threadIdx.x; t < cnt * np; t += blockDim.x) {
-      const int i = t / np, d = dlo + (t - i * np);
-      const int v = order[lo + i], nc = nchild[v];
-      if (nc == 0) continue;
-      double* a = A + (size_t)d * sd;
-      double acc = a[(size_t)v * sn];   // this node's own cost: written before the kernel
-      for (int k = 0; k < nc; k++) {
-        const int c = child[(size_t)v * 4 + k];
-        acc += a[(size_t)c * sn] * tab[wpar[c]];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const size_t lvB = (size_t)cap * np;
+  auto at = [&](int d, int q, int v) -> double* {   // element of plane d: position q of `order` = node v
+    return LEVELORD ? A + (size_t)d * sd + q : A + (size_t)d * sd + (size_t)v * sn;
+  };
+
+  // ---- leaf to root: backup[p] += sum over children (adjacency order) of w(c) * backup[c]
+  auto loadUp = [&](int l, int t, nl_up_item& it) {
+    it.v = -1; it.nc = 0;
+    if (l < 0) return;
+    const int lo = lstart(l), cnt = lstart(l + 1) - lo;
+    if (t < cnt * np) {
+      const int i = NP1 ? t : t / np, d = dlo + (t - i * np);
+      it.v = LEVELORD ? 0 : order[lo + i];
+      it.nc = rnc[lo + i];
+      it.cp = rcp[lo + i];
+      it.cw = rcw[lo + i];
+      it.own = *at(d, lo + i, it.v);   // this node's own cost: written before the kernel
+    }
+  };
+  {
+    // The items fetched ahead live in four NAMED register sets used in rotation (the level loop is unrolled by four):
+    // shifting them through an array would copy registers whose loads are still in flight, and such a copy waits.
+    auto stepUp = [&](int l, nl_up_item& slot) {
+      if (l < 0) return;
+      const int lo = lstart(l), cnt = lstart(l + 1) - lo;
+      double* cur = lv + (size_t)(l & 1) * lvB;
+      const double* kid = lv + (size_t)((l + 1) & 1) * lvB;
+      nl_up_item it = slot;
+      loadUp(l - NL_TF_PF, tid, slot);   // in flight while the next levels are computed
+      for (int t = tid; t < cnt * np; t += nth) {
+        if (t != tid) loadUp(l, t, it);
+        const int i = NP1 ? t : t / np, dd = t - i * np, d = dlo + dd;
+        double acc = it.own;
+        const int cp[4] = {it.cp.x, it.cp.y, it.cp.z, it.cp.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {   // unrolled: cp[] stays in registers (a node has at most 4 children)
+          if (k < it.nc) {
+            const int p = cp[k];
+            double val;
+            if (p < cap) val = kid[(size_t)p * np + dd];
+            else { const int q = lstart(l + 1) + p; val = *at(d, q, LEVELORD ? 0 : order[q]); }
+            acc += val * tab[(it.cw >> (8 * k)) & 0xff];
+          }
+        }
+        if (it.nc) *at(d, lo + i, it.v) = acc;
+        if (i < cap) cur[(size_t)i * np + dd] = acc;
       }
-      a[(size_t)v * sn] = acc;
-    }
-    __syncthreads();
+      __syncthreads();
+    };
+    nl_up_item p0, p1, p2, p3;
+    loadUp(nlevels - 1, tid, p0); loadUp(nlevels - 2, tid, p1); loadUp(nlevels - 3, tid, p2); loadUp(nlevels - 4, tid, p3);
+    for (int l = nlevels - 1; l >= 0; l -= 4) { stepUp(l, p0); stepUp(l - 1, p1); stepUp(l - 2, p2); stepUp(l - 3, p3); }
   }
-  // root to leaf: cost[i] = w * (cost[parent] - w * backup[i]) + backup[i]   (the root keeps backup)
-  for (int l = 1; l < nlevels; l++) {
-    const int lo = level_start[l], cnt = level_start[l + 1] - lo;
-    for (int t = threadIdx.x; t < cnt * np; t += blockDim.x) {
-      const int i = t / np, d = dlo + (t - i * np);
-      const int v = order[lo + i];
-      double* a = A + (size_t)d * sd;
-      const double w = tab[wpar[v]];
-      const double b = a[(size_t)v * sn];
-      a[(size_t)v * sn] = w * (a[(size_t)parent[v] * sn] - w * b) + b;
+  // ---- root to leaf: cost[i] = w * (cost[parent] - w * backup[i]) + backup[i]   (the root keeps backup)
+  auto loadDn = [&](int l, int t, nl_dn_item& it) {
+    it.v = -1;
+    if (l >= nlevels) return;
+    const int lo = lstart(l), cnt = lstart(l + 1) - lo;
+    if (t < cnt * np) {
+      const int i = NP1 ? t : t / np, d = dlo + (t - i * np);
+      it.v = LEVELORD ? 0 : order[lo + i];
+      it.pp = rpp[lo + i];
+      it.w = rw[lo + i];
+      it.own = *at(d, lo + i, it.v);   // backup[i]: written by the sweep above, at least NL_TF_PF barriers ago
     }
-    __syncthreads();
+  };
+  // level 0 (the root) is final already and sits in lv[0] from the sweep above.  The first NL_TF_PF levels are
+  // fetched only now: their backup values were written by the last iterations of the sweep above.
+  {
+    auto stepDn = [&](int l, nl_dn_item& slot) {
+      if (l >= nlevels) return;
+      const int lo = lstart(l), cnt = lstart(l + 1) - lo;
+      double* cur = lv + (size_t)(l & 1) * lvB;
+      const double* par = lv + (size_t)((l - 1) & 1) * lvB;
+      nl_dn_item it = slot;
+      loadDn(l + NL_TF_PF, tid, slot);
+      for (int t = tid; t < cnt * np; t += nth) {
+        if (t != tid) loadDn(l, t, it);
+        const int i = NP1 ? t : t / np, dd = t - i * np, d = dlo + dd;
+        const double w = tab[it.w];
+        const double b = it.own;
+        double pv;
+        if (it.pp < cap) pv = par[(size_t)it.pp * np + dd];
+        else { const int q = lstart(l - 1) + it.pp; pv = *at(d, q, LEVELORD ? 0 : order[q]); }
+        const double r = w * (pv - w * b) + b;
+        *at(d, lo + i, it.v) = r;
+        if (i < cap) cur[(size_t)i * np + dd] = r;
+      }
+      __syncthreads();
+    };
+    nl_dn_item p0, p1, p2, p3;
+    loadDn(1, tid, p0); loadDn(2, tid, p1); loadDn(3, tid, p2); loadDn(4, tid, p3);
+    for (int l = 1; l < nlevels; l += 4) { stepDn(l, p0); stepDn(l + 1, p1); stepDn(l + 2, p2); stepDn(l + 3, p3); }
   }
 }
 
-__global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp) {
+__global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp,
+                           const int* __restrict__ pos) {
   const size_t n = N * D;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t v = i / D;
     const int d = (int)(i - v * D);
-    const float x = (float)A[(size_t)d * N + v];                     // NLCCA::aggreCV: (float)nlcP[d]
-    vol[i] = Dp > D ? x / (float)A[(size_t)D * N + v] : x;           // StereoMatching::NL: vm[0] /= wetNL
+    const size_t q = (size_t)pos[v];
+    const float x = (float)A[(size_t)d * N + q];                     // NLCCA::aggreCV: (float)nlcP[d]
+    vol[i] = Dp > D ? x / (float)A[(size_t)D * N + q] : x;           // StereoMatching::NL: vm[0] /= wetNL
   }
 }
 
@@ -322,6 +464,8 @@ struct nl_tree {   // device buffers of one rooted tree (owned by the ctx scratc
   int *parent, *rank, *order, *level_start, *child;
   uint8_t *wpar, *nchild;
   nl_sync* sync;
+  // level-ordered records (k_tf_records)
+  int4* rcp; uint32_t* rcw; int* rpp; int* pos; uint8_t *rnc, *rw;
 };
 
 
@@ -370,7 +514,9 @@ static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn
   {
     void* args[] = {(void*)&N, (void*)&nbr, (void*)&nbw, (void*)&deg, (void*)&t.parent, (void*)&t.wpar, (void*)&t.rank,
                     (void*)&t.order, (void*)&t.level_start, (void*)&t.sync};
-    SM_CUDA(cudaLaunchKernel((const void*)k_tree_bfs, dim3(1), dim3(NL_CTA), args, 0, ctx->stream));
+    const size_t smem = 2 * (size_t)NL_BFS_FCAP * sizeof(int2);
+    SM_CUDA(cudaFuncSetAttribute(k_tree_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SM_CUDA(cudaLaunchKernel((const void*)k_tree_bfs, dim3(1), dim3(NL_CTA), args, smem, ctx->stream));
     ctx->launches++;
   }
   return SM_OK;
@@ -395,6 +541,16 @@ static int nl_tree_scratch(sm_ctx* ctx, int N, nl_tree& t, bool own_arrays) {
     q += (64 - ((size_t)N & 63)) & 63;
   }
   t.nchild = q;
+  // SM_SCR_NLREC: rcp[N] int4 | rcw[N] | rpp[N] | pos[N] | rnc[N] | rw[N]
+  void* p2;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_NLREC, (size_t)N * 30 + 64, &p2));
+  uint8_t* r = (uint8_t*)p2;
+  t.rcp = (int4*)r; r += (size_t)N * 16;
+  t.rcw = (uint32_t*)r; r += (size_t)N * 4;
+  t.rpp = (int*)r; r += (size_t)N * 4;
+  t.pos = (int*)r; r += (size_t)N * 4;
+  t.rnc = r; r += (size_t)N;
+  t.rw = r;
   return SM_OK;
 }
 
@@ -413,16 +569,29 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
   SM_CUDA(cudaMemcpyAsync(d_tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, ctx->stream));
   SM_CUDA(cudaStreamSynchronize(ctx->stream));   // h_tab is a stack array
   const int TB = 256, g = (int)min((size_t)ctx->num_sms * 16, (N * Dp + TB - 1) / TB);
-  if (d_vol) SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp);
+  const int n = (int)N, gr = min(sm_div_up(n, TB), ctx->num_sms * 8);
+  SM_LAUNCH(ctx, k_tf_positions, gr, TB, 0, n, t.order, t.pos);
+  SM_LAUNCH(ctx, k_tf_records, gr, TB, 0, n, t.order, t.pos, t.rank, t.level_start, t.parent, t.wpar, t.child, t.nchild,
+            t.rcp, t.rcw, t.rnc, t.rpp, t.rw);
+  if (d_vol) SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp, t.order);
   {
     // one CTA per plane while there are SMs for them, else the same number of planes for every CTA
     const int ppc = sm_div_up(Dp, min(Dp, ctx->num_sms));
     const int grid = sm_div_up(Dp, ppc);
-    const size_t sn = d_vol ? 1 : (size_t)D, sd = d_vol ? N : 1;
-    SM_LAUNCH(ctx, k_tf_sweeps, grid, NL_TF_CTA, 0, d_A, sn, sd, Dp, ppc, t.parent, t.wpar, t.child, t.nchild, t.order,
-              t.level_start, d_tab, t.sync);
+    const int cap = NL_TF_CAP / ppc;
+    const size_t smem = 2 * (size_t)cap * ppc * sizeof(double) + (size_t)NL_TF_LS * sizeof(int);
+    const void* fn = d_vol ? (ppc == 1 ? (const void*)k_tf_sweeps<true, true> : (const void*)k_tf_sweeps<true, false>)
+                           : (ppc == 1 ? (const void*)k_tf_sweeps<false, true> : (const void*)k_tf_sweeps<false, false>);
+    double* a = d_A;
+    size_t sn = d_vol ? 1 : (size_t)D, sd = d_vol ? N : 1;
+    int dp = Dp, pp = ppc, cp = cap;
+    void* args[] = {(void*)&a, (void*)&sn, (void*)&sd, (void*)&dp, (void*)&pp, (void*)&cp, (void*)&t.order, (void*)&t.level_start,
+                    (void*)&t.rcp, (void*)&t.rcw, (void*)&t.rnc, (void*)&t.rpp, (void*)&t.rw, (void*)&d_tab, (void*)&t.sync};
+    SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(NL_TF_CTA), args, smem, ctx->stream));
+    ctx->launches++;
   }
-  if (d_vol) SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp);
+  if (d_vol) SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp, t.pos);
   return SM_OK;
 }
 
