@@ -12,14 +12,16 @@ metric configuration, 1920x1080 with D=256 (configs[2]/[4]), synthetic texture-w
            disparity map out (D2H), copies inside the timed region.
   roofline / stages : per-stage device time measured live (CUDA events the pipeline records on its stream
            during the timed steps) against the algorithmic HBM bytes of SURVEY.md section 8(d).
-  cpu_baseline : the CPU oracle (oracle/, a port of the reference's arithmetic) on a bounded band of the same
-           workload, on this box's host cores (N=1, rank 0 only).
+  cpu_baseline : the compiled reference (oracle/_ref/libsmref.so; else the oracle port) on bounded bands of the
+           same workload, on this box's host cores (N=1, rank 0 only).
 
 N>1 (torchrun, one process per GPU): frames are independent, each rank runs its own K frames (weak scaling), no
 data-path collective; torch.distributed is used only for the barrier and the max-over-ranks time.
 
---impl reference : the reference's own CPU algorithm for the path (oracle port; the reference's stereoMatching.cpp
-cannot be compiled here: OpenCV C++ + ximgproc + a missing util.h), all host threads, bounded band per step.
+--impl reference : the reference's own CPU code for the path -- its hot-path function bodies cut from
+stereoMatching.{h,cpp} and compiled against a cv::Mat stand-in (oracle/_ref/libsmref.so, oracle/build_ref_sm.py);
+one instance per host thread (the reference is single-threaded), a bounded band per instance per step.  Falls back
+to the oracle port when that library is absent or the workload uses NL aggregation.
 """
 import argparse
 import json
@@ -134,9 +136,65 @@ def host_threads():
     return n if po.lib().orc_has_openmp() else 1
 
 
-def cpu_baseline(name, budget_rows=48):
-    pair, rows = cpu_band(name, budget_rows)
+def have_compiled_reference(name):
+    """oracle/_ref/libsmref.so = the reference's own stereoMatching.{h,cpp} function bodies (oracle/build_ref_sm.py).
+    It covers the CBCA workloads; c4 (NL aggregation inside StereoMatching::NL) stays on the oracle port."""
+    from oracle import pyoracle as po
+    return AGGREGATION[name] == 1 and po.smref_lib() is not None
+
+
+def reference_threads(name, rows):
+    """The reference is single-threaded (every `omp parallel for` in it is commented out, stereoMatching.h:596, 648,
+    1661), so 'all the host threads it can use' = one independent instance per core, each on its own band --
+    the same frame-level partition the GPU side uses.  Capped by memory: an instance holds ~88 B per (pixel, d)
+    (vm x2, four ADCensusCal temporaries, three cbca temporaries, L[8], HVL_INTERSECTION x2)."""
     W, H, D, P, kind = WORKLOADS[name]
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per = rows * W * D * 88
+    try:
+        import psutil
+        n = max(1, min(n, int(0.5 * psutil.virtual_memory().available / per)))
+    except Exception:
+        n = min(n, 8)
+    return min(n, 32)
+
+
+def run_reference(name, rows, threads, seed0=1000):
+    """`threads` compiled-reference StereoMatching instances, each running the whole default chain on its own
+    W x rows band.  Returns wall seconds."""
+    from oracle import pyoracle as po
+    from mystereomatching_b200 import synth
+    W, H, D, P, kind = WORKLOADS[name]
+    pairs = [synth.make_pair(rows, W, D, kind, seed=seed0 + i) for i in range(threads)]
+
+    def work(p):
+        r = po.SmRef(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D)
+        r.pipeline(P, 2)          # ctypes releases the GIL for the duration of the call
+        r.close()
+
+    ts = [threading.Thread(target=work, args=(p,)) for p in pairs]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(name, budget_rows=48):
+    W, H, D, P, kind = WORKLOADS[name]
+    if have_compiled_reference(name):
+        rows = min(H, 12)
+        nt = reference_threads(name, rows)
+        mde = W * rows * D / 1e6
+        t1 = run_reference(name, rows, 1)
+        tn = run_reference(name, rows, nt) if nt > 1 else t1
+        return {"value": nt * mde / tn, "unit": "MDE/s", "cores": nt, "kind": "reference",
+                "value_1thread": mde / t1,
+                "sample": f"the reference's own code (oracle/_ref/libsmref.so): whole chain on {W}x{rows} bands (full "
+                          f"width, D={D}); one band on 1 thread {t1:.1f} s (the reference's own threading), "
+                          f"{nt} bands on {nt} threads {tn:.1f} s"}
+    pair, rows = cpu_band(name, budget_rows)
     mde = W * rows * D / 1e6
     nt = host_threads()
     t1, _ = run_oracle(pair, name, 1)
@@ -154,28 +212,45 @@ def main_reference(args):
     name = args.workload
     W, H, D, P, kind = WORKLOADS[name]
     total = args.steps + args.warmup
-    rows = 48 if total <= 14 else (24 if total <= 40 else 12)
-    pair, rows = cpu_band(name, rows)
-    nt = host_threads()
-    for _ in range(args.warmup):
-        run_oracle(pair, name, nt)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        run_oracle(pair, name, nt)
-    dt = time.perf_counter() - t0
-    mde = W * rows * D / 1e6
+    compiled = have_compiled_reference(name)
+    if compiled:
+        rows = min(H, 12 if total <= 20 else 6)
+        nt = reference_threads(name, rows)
+        for i in range(args.warmup):
+            run_reference(name, rows, nt, 1000 + 100 * i)
+        dt = 0.0
+        for i in range(args.steps):
+            dt += run_reference(name, rows, nt, 5000 + 100 * i)
+        mde = nt * W * rows * D / 1e6
+        kindb = "reference"
+        sample = (f"each step = {nt} instances of the reference's own StereoMatching code (oracle/_ref/libsmref.so), one "
+                  f"per host thread, each running the whole chain on its own {W}x{rows} band (full width, D={D})")
+        note = ("the reference's hot-path function bodies, cut from stereoMatching.{h,cpp} and compiled against a "
+                "cv::Mat stand-in (oracle/build_ref_sm.py); the reference itself is single-threaded")
+    else:
+        rows = 48 if total <= 14 else (24 if total <= 40 else 12)
+        pair, rows = cpu_band(name, rows)
+        nt = host_threads()
+        for _ in range(args.warmup):
+            run_oracle(pair, name, nt)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run_oracle(pair, name, nt)
+        dt = time.perf_counter() - t0
+        mde = W * rows * D / 1e6
+        kindb = "port"
+        sample = f"each step = one {W}x{rows} band (full width, D={D}) through the whole oracle chain, {nt} threads"
+        note = ("no compiled reference for this workload here (oracle/_ref/libsmref.so absent, or NL aggregation): "
+                "this arm times the oracle port of the reference's algorithm (oracle/stereo_oracle.cpp)")
     val = mde * args.steps / dt
-    sample = f"each step = one {W}x{rows} band (full width, D={D}) through the whole oracle chain, {nt} threads"
     out = {"impl": "reference", "metric": "MDE/s (W*H*D disparity evaluations per second), whole path",
            "value": val, "unit": "MDE/s", "fps_equiv": val * 1e6 / (W * H * D), "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": workload_desc(name), "parallelism": f"host CPU, {nt} threads"},
-           "cpu_baseline": {"value": val, "unit": "MDE/s", "cores": nt, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "MDE/s", "cores": nt, "kind": kindb, "sample": sample},
            "e2e": {"value": val, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0,
-           "note": "reference's stereoMatching.cpp is not compilable here (OpenCV C++/ximgproc/util.h missing): "
-                   "this arm times the oracle port of its algorithm (oracle/stereo_oracle.cpp)"}
+           "gpu_launches": 0, "note": note}
     print(json.dumps(out))
     return 0
 

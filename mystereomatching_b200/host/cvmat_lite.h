@@ -51,6 +51,12 @@ class Exception : public std::runtime_error {
                           std::to_string(__LINE__));                                                      \
   } while (0)
 
+struct Scalar {
+  double val[4];
+  Scalar(double v0 = 0, double v1 = 0, double v2 = 0, double v3 = 0) { val[0] = v0; val[1] = v1; val[2] = v2; val[3] = v3; }
+  static Scalar all(double v) { return Scalar(v, v, v, v); }
+};
+
 class Mat {
  public:
   enum { MAX_DIM = 4 };
@@ -64,6 +70,10 @@ class Mat {
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
   Mat(int nd, const int* sz, int type) { create(nd, sz, type); }
+  Mat(int r, int c, int type, const Scalar& s) { create(r, c, type); *this = s; }
+  Mat(int nd, const int* sz, int type, const Scalar& s) { create(nd, sz, type); *this = s; }
+  static Mat zeros(int r, int c, int type) { return Mat(r, c, type, Scalar::all(0)); }
+  static Mat ones(int r, int c, int type) { return Mat(r, c, type, Scalar(1)); }
   // header over caller-owned memory (no copy), like cv::Mat(rows, cols, type, void*)
   Mat(int r, int c, int type, void* ext) { header2d(r, c, type); data = (uchar*)ext; }
 
@@ -121,6 +131,27 @@ class Mat {
     if (bytes()) memcpy(dst.data, data, bytes());
   }
   Mat& setZero() { if (bytes()) memset(data, 0, bytes()); return *this; }
+  // `m = s`: every element's channel c becomes s.val[c] (saturate_cast semantics are not needed by the callers:
+  // they only assign 0, 1 and small integers)
+  Mat& operator=(const Scalar& s) {
+    const int cn = channels();
+    const size_t n = total();
+    for (size_t i = 0; i < n; i++)
+      for (int c = 0; c < cn; c++) {
+        const double v = s.val[c < 4 ? c : 3];
+        uchar* p = data + (i * cn + c) * elemSize1();
+        switch (depth()) {
+          case CV_8U: *(uchar*)p = (uchar)v; break;
+          case CV_8S: *(signed char*)p = (signed char)v; break;
+          case CV_16U: *(ushort*)p = (ushort)v; break;
+          case CV_16S: *(short*)p = (short)v; break;
+          case CV_32S: *(int*)p = (int)v; break;
+          case CV_32F: *(float*)p = (float)v; break;
+          default: *(double*)p = v; break;
+        }
+      }
+    return *this;
+  }
 
  private:
   std::shared_ptr<uchar> buf_;

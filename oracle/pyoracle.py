@@ -375,3 +375,182 @@ def ref_nlca(left, right, D, sigma=0.1, post=False, want_disp=True):
     L.qxref_nlca(np.ascontiguousarray(left), np.ascontiguousarray(right), H, W, D, sigma, int(post), cost.ctypes.data,
                  costR.ctypes.data, grad.ctypes.data, disp.ctypes.data if want_disp else None)
     return dict(cost=cost, cost_right=costR, grad_left=grad, disp=disp)
+
+
+# ----------------------------------------------------------------------------- compiled StereoMatching reference
+_SMREF = None
+
+
+def smref_lib():
+    """The reference's own stereoMatching.{h,cpp} hot-path function bodies compiled by oracle/build_ref_sm.py
+    (oracle/_ref/libsmref.so), or None when it has not been built."""
+    global _SMREF
+    if _SMREF is not None:
+        return _SMREF
+    so = os.path.join(_HERE, "_ref", "libsmref.so")
+    if not os.path.exists(so):
+        return None
+    L = C.CDLL(so)
+    I, F, P, D_ = C.c_int, C.c_float, C.c_void_p, C.c_double
+    sig = {
+        "smref_create": ([u8p, u8p, u8p, u8p, I, I, I], P), "smref_destroy": ([P], None),
+        "smref_do_refine": ([], I),
+        "smref_set_param": ([P, C.c_char_p, D_], I), "smref_get_param": ([P, C.c_char_p], D_),
+        "smref_census": ([P, I, u64p], I), "smref_census_cal": ([P, I, f32p, f32p], None),
+        "smref_ad": ([P, I, F, f32p], None), "smref_combine_exp": ([P, f32p, f32p, F, F, f32p], None),
+        "smref_adcensus": ([P], None), "smref_get_vm": ([P, I, f32p], None), "smref_set_vm": ([P, I, f32p], None),
+        "smref_arms": ([P, u16p, u16p], None), "smref_arms_intersection": ([P, I, u16p], None),
+        "smref_cbca": ([P, I], None), "smref_cost_scan": ([P, I, I, f32p], None), "smref_sgm": ([P, I, I], None),
+        "smref_wta": ([P, I, i16p], None), "smref_wta_co": ([P, I, i16p, i16p], None),
+        "smref_lrc_normal": ([P, i16p, i16p], None), "smref_lrc_label": ([P, i16p, i16p, I, P], None),
+        "smref_lrc_new": ([P, i16p, i16p, u8p], None),
+        "smref_region_vote": ([P, i16p, F, I], None), "smref_proper_ipol": ([P, i16p], None),
+        "smref_median3_i16": ([i16p, I, I, i16p], None),
+        "smref_pipeline": ([P, I, I, P, P, P, P], None),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes, fn.restype = args, res
+    _SMREF = L
+    return L
+
+
+class SmRef:
+    """One compiled-reference `StereoMatching` instance (constructed as main_.cpp:60-64,138 does) on one stereo
+    pair.  Methods are the reference's own functions; see oracle/smref_shim.inc."""
+
+    def __init__(self, bgrL, bgrR, grayL, grayR, D):
+        L = smref_lib()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libsmref.so is not built (python oracle/build_ref_sm.py)")
+        self.L = L
+        self.H, self.W, _ = bgrL.shape
+        self.D = D
+        self.h = L.smref_create(np.ascontiguousarray(bgrL), np.ascontiguousarray(bgrR),
+                                np.ascontiguousarray(grayL), np.ascontiguousarray(grayR), self.H, self.W, D - 1)
+
+    def close(self):
+        if self.h:
+            self.L.smref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set(self, name, v):
+        if self.L.smref_set_param(self.h, name.encode(), float(v)) != 0:
+            raise KeyError(name)
+
+    def get(self, name):
+        v = self.L.smref_get_param(self.h, name.encode())
+        if v < -1e299:
+            raise KeyError(name)
+        return v
+
+    def _vol(self):
+        return np.empty((self.H, self.W, self.D), np.float32)
+
+    def census(self, func=3):
+        nw = 2 if func == 3 else 1
+        out = np.empty((2, self.H, self.W, nw), np.uint64)
+        assert self.L.smref_census(self.h, func, out) == nw
+        return out[0], out[1]
+
+    def census_cal(self, func=3):
+        a, b = self._vol(), self._vol()
+        self.L.smref_census_cal(self.h, func, a, b)
+        return a, b
+
+    def ad(self, LOR=0, trunc=1000.0):
+        a = self._vol()
+        self.L.smref_ad(self.h, LOR, trunc, a)
+        return a
+
+    def combine_exp(self, a, b, l0=10.0, l1=30.0):
+        o = self._vol()
+        self.L.smref_combine_exp(self.h, np.ascontiguousarray(a), np.ascontiguousarray(b), l0, l1, o)
+        return o
+
+    def adcensus(self):
+        self.L.smref_adcensus(self.h)
+        return self.vm(0), self.vm(1)
+
+    def vm(self, view):
+        a = self._vol()
+        self.L.smref_get_vm(self.h, view, a)
+        return a
+
+    def set_vm(self, view, vol):
+        assert vol.shape == (self.H, self.W, self.D)
+        self.L.smref_set_vm(self.h, view, np.ascontiguousarray(vol, np.float32))
+
+    def arms(self):
+        a = np.empty((self.H, self.W, 5), np.uint16)
+        b = np.empty((self.H, self.W, 5), np.uint16)
+        self.L.smref_arms(self.h, a, b)
+        return a, b
+
+    def arms_intersection(self, view):
+        o = np.empty((self.H, self.W, self.D, 5), np.uint16)
+        self.L.smref_arms_intersection(self.h, view, o)
+        return o
+
+    def cbca(self, iters=2):
+        self.L.smref_cbca(self.h, iters)
+        return self.vm(0), self.vm(1)
+
+    def cost_scan(self, view, path):
+        o = self._vol()
+        self.L.smref_cost_scan(self.h, view, path, o)
+        return o
+
+    def sgm(self, view, paths):
+        self.L.smref_sgm(self.h, view, paths)
+        return self.vm(view)
+
+    def wta(self, view):
+        o = np.empty((self.H, self.W), np.int16)
+        self.L.smref_wta(self.h, view, o)
+        return o
+
+    def wta_co(self, view=0):
+        a = np.empty((self.H, self.W), np.int16)
+        b = np.empty((self.H, self.W), np.int16)
+        self.L.smref_wta_co(self.h, view, a, b)
+        return a, b
+
+    def lrc_normal(self, d1, d2):
+        a = np.ascontiguousarray(d1, np.int16).copy()
+        self.L.smref_lrc_normal(self.h, a, np.ascontiguousarray(d2, np.int16))
+        return a
+
+    def lrc_label(self, d1, d2, LOR=0):
+        a = np.ascontiguousarray(d1, np.int16).copy()
+        b = np.ascontiguousarray(d2, np.int16).copy()
+        m = np.zeros((self.H, self.W), np.uint8)
+        self.L.smref_lrc_label(self.h, a, b, LOR, m.ctypes.data if LOR == 0 else None)
+        return a, b, m
+
+    def lrc_new(self, d1, d2, mask):
+        m = np.ascontiguousarray(mask, np.uint8).copy()
+        self.L.smref_lrc_new(self.h, np.ascontiguousarray(d1, np.int16), np.ascontiguousarray(d2, np.int16), m)
+        return m
+
+    def region_vote(self, dp, ratio=0.4, S=20):
+        a = np.ascontiguousarray(dp, np.int16).copy()
+        self.L.smref_region_vote(self.h, a, ratio, S)
+        return a
+
+    def proper_ipol(self, dp):
+        a = np.ascontiguousarray(dp, np.int16).copy()
+        self.L.smref_proper_ipol(self.h, a)
+        return a
+
+    def pipeline(self, paths=4, iters=2, want_vol=False):
+        wl = np.empty((self.H, self.W), np.int16)
+        wr = np.empty((self.H, self.W), np.int16)
+        rf = np.empty((self.H, self.W), np.int16)
+        vol = self._vol() if want_vol else None
+        self.L.smref_pipeline(self.h, paths, iters, wl.ctypes.data, wr.ctypes.data, rf.ctypes.data,
+                              vol.ctypes.data if want_vol else None)
+        return wl, wr, rf, vol
