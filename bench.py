@@ -184,7 +184,7 @@ def run_reference(name, rows, threads, seed0=1000):
 def cpu_baseline(name, budget_rows=48):
     W, H, D, P, kind = WORKLOADS[name]
     if have_compiled_reference(name):
-        rows = min(H, 12)
+        rows = min(H, 48)
         nt = reference_threads(name, rows)
         mde = W * rows * D / 1e6
         t1 = run_reference(name, rows, 1)
@@ -214,7 +214,7 @@ def main_reference(args):
     total = args.steps + args.warmup
     compiled = have_compiled_reference(name)
     if compiled:
-        rows = min(H, 12 if total <= 20 else 6)
+        rows = min(H, 24 if total <= 20 else 12)
         nt = reference_threads(name, rows)
         for i in range(args.warmup):
             run_reference(name, rows, nt, 1000 + 100 * i)

@@ -8,15 +8,19 @@
 // the reference root).  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load this library.
 //
-// Pinning status: the reference ships no tests, fixtures or golden vectors
-// for stereoMatching.{h,cpp} and that file cannot be compiled here (needs
-// OpenCV C++ + ximgproc + a missing util.h), so for the functions in this
-// file parity is pinned by (i) the three OpenCV semantics on the path checked
-// against cv2 4.13 golden vectors (tests/golden/opencv_semantics.npz:
-// BORDER_REFLECT_101, medianBlur on CV_16S, BGR2GRAY) and (ii) hand-derived
-// known-answer cases in tests/.  "parity unpinned" by reference-owned vectors.
-// The NL/ part (ctmf / MST / tree filter, nl_oracle.cpp) IS pinned against the
-// reference's own sources compiled into oracle/_ref.
+// Pinning status: PINNED.  The reference ships no tests, fixtures or golden
+// vectors for stereoMatching.{h,cpp} and those files cannot be compiled as
+// files here (OpenCV C++ + ximgproc + a missing util.h), but the hot-path
+// function bodies can: oracle/build_ref_sm.py cuts them out of the reference
+// where it lies and compiles them against a cv::Mat stand-in into
+// oracle/_ref/libsmref.so.  tests/golden/sm_ref.npz holds that library's outputs
+// at every stage boundary on three seeded stereo pairs;
+// tests/test_oracle_sm_golden.py requires every function in this file to
+// reproduce them bit for bit (and to agree with the live library on further
+// shapes when it is present).  The three OpenCV semantics on the path
+// (BORDER_REFLECT_101, medianBlur on CV_16S, BGR2GRAY) are pinned by cv2 4.13
+// golden vectors (tests/golden/opencv_semantics.npz).  The NL/ part (ctmf /
+// MST / tree filter, nl_oracle.cpp) is pinned against oracle/_ref/libqxref.so.
 //
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off, optional -fopenmp).
 // Float contraction is disabled so a*b+c never becomes an FMA: the reference
