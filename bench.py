@@ -41,14 +41,17 @@ WORKLOADS = {
     "c2": (1280, 720, 128, 8, "texture_warped"),
     "c3": (1920, 1080, 256, 8, "texture_warped"),
     "c4": (640, 480, 64, 4, "texture_warped"),       # NL non-local MST aggregation instead of CBCA
+    "c3cg": (1920, 1080, 256, 8, "texture_warped"),  # c3 with the cost main_.cpp:15 compiles in: censusGrad
 }
-AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2}
+AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2, "c3cg": 1}
+COSTCALC = {"c3cg": 1}        # 0 = AD-Census (BASELINE configs), 1 = censusGrad
 
 
 def workload_desc(name):
     W, H, D, P, kind = WORKLOADS[name]
     agg = "CBCA(2 it, intersected arms)" if AGGREGATION[name] == 1 else "NL(MST tree filter, sigma 0.1, left view)"
-    return (f"{name}: {W}x{H} D={D} AD-Census(71-bit)+{agg}+{P}-path SGM+WTA+LRC+"
+    cost = "censusGrad(71-bit census + arm-weighted x/y gradient)" if COSTCALC.get(name, 0) else "AD-Census(71-bit)"
+    return (f"{name}: {W}x{H} D={D} {cost}+{agg}+{P}-path SGM+WTA+LRC+"
             f"regionVote x2+properIpol x2+median3, 2 views, fp32 volumes, synthetic {kind} pairs")
 
 
@@ -124,7 +127,7 @@ def run_oracle(pair, name, threads):
     from oracle import pyoracle as po
     W, H, D, P, kind = WORKLOADS[name]
     po.lib().orc_set_threads(threads)
-    op = po.default_params(D, paths=P, aggregation=AGGREGATION[name])
+    op = po.default_params(D, paths=P, aggregation=AGGREGATION[name], costcalc=COSTCALC.get(name, 0))
     t0 = time.perf_counter()
     _, _, _, ms = po.pipeline(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], op)
     return time.perf_counter() - t0, ms
@@ -169,7 +172,7 @@ def run_reference(name, rows, threads, seed0=1000):
 
     def work(p):
         r = po.SmRef(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D)
-        r.pipeline(P, 2)          # ctypes releases the GIL for the duration of the call
+        r.pipeline(P, 2, costcalc=COSTCALC.get(name, 0))   # ctypes releases the GIL for the duration of the call
         r.close()
 
     ts = [threading.Thread(target=work, args=(p,)) for p in pairs]
@@ -272,7 +275,8 @@ def stage_bytes(name):
     if AGGREGATION[name] == 2:   # k_nl = 4 volume passes; MST build + rooting + two tree sweeps
         agg = {"bytes_per_launch": 4 * V * b, "launches": 1, "kernel": "nl (Boruvka MST + k_tree_bfs + k_tf_sweeps)"}
     st = {
-        "cost": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_cost<ADCENSUS>"},
+        "cost": {"bytes_per_launch": V * b, "launches": 2,
+                 "kernel": "k_cost_grad<FUSED>" if COSTCALC.get(name, 0) else "k_cost<ADCENSUS>"},
         "aggregation": agg,
         # gen_dispFromVm is fused into the last SGM path of each view (no separate read of the summed volume)
         "wta": {"bytes_per_launch": 0, "launches": 2, "kernel": "fused into k_sgm_path (mode 2)"},
@@ -313,7 +317,8 @@ def main_ours(args):
     name = args.workload
     W, H, D, P, kind = WORKLOADS[name]
     ctx = capi.Ctx(local)
-    params = capi.default_params(D - 1, sgm_paths=P, aggregation=AGGREGATION[name])
+    params = capi.default_params(D - 1, sgm_paths=P, aggregation=AGGREGATION[name],
+                                 costcalculation=COSTCALC.get(name, 0))
     pl = capi.Pipeline(ctx, H, W, params)
 
     # frames of this rank: frame i of the stream uses seed 1000+i, frame i -> rank i mod N

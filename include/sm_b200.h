@@ -76,6 +76,9 @@ typedef struct sm_params {
                              * (one read of C and one read-modify-write of the sum for three paths); every path
                              * volume is still exact, only the order of the eight additions differs: integer-valued
                              * costs stay bit-exact, float sums agree to a few ulp (see sm_sgm_grouped). */
+  int costcalculation;      /* 0 "ADCensus" (BASELINE configs), 1 "censusGrad" (the selector main_.cpp:15 compiles in) */
+  float cg_lamCen, cg_lamG; /* censusGrad: Parameters::lamCen = 13, lamG = 1 (main_.cpp:60-61, stereoMatching.cpp:37-41) */
+  float gradTrunc;          /* 500  (censusGrad -> grad(gradVm, 500), stereoMatching.cpp:34) */
 } sm_params;
 
 void sm_params_default(sm_params* p, int maxDisp);
@@ -134,6 +137,23 @@ int sm_cost_adcensus(sm_ctx* ctx, const uint8_t* d_bgrL, const uint8_t* d_bgrR,
 /* gen_vm_from2vm_exp on two materialised volumes (stage API completeness). */
 int sm_combine_exp(sm_ctx* ctx, const float* d_vm0, const float* d_vm1, size_t n, float aru0,
                    float aru1, float* d_out);
+
+/* ---- gradient cost family ---------------------------- */
+/* calGrad + calGrad_y (stereoMatching.cpp:271-368) on a gray image: central differences 0.5*(next-prev), one-sided
+ * (not halved) in the border column / row.  H, W >= 2 (the reference reads pixel 1 and H-2 unconditionally). */
+int sm_grad_xy(sm_ctx* ctx, const uint8_t* d_gray, int H, int W, float* d_gx, float* d_gy);
+/* grad() -> calgradvm (stereoMatching.cpp:603-656, 388-455; gradFuse_adpWgt = 1, grad_use2direc = 1):
+ * vol[v][u][d] = a*min(|gx0[u0]-gx1[u1]|,trunc) + (1-a)*min(|gy0[u0]-gy1[u1]|,trunc), a = sH/(sH+sV) from the arms
+ * of the view's own image (d_armsView = HVL[LOR]); out of range sqrt(2 trunc^2).  Bit-exact. */
+int sm_cost_grad(sm_ctx* ctx, const float* d_gxL, const float* d_gyL, const float* d_gxR, const float* d_gyR,
+                 const uint16_t* d_armsView, int H, int W, int D, float trunc, int LOR, float* d_vol);
+/* censusGrad (stereoMatching.cpp:25-48) fused: 2 - exp(-hamming/lamCen) - exp(-grad/lamG); neither the census nor
+ * the gradient volume is materialised.  Census term from a host libm table (exact), gradient term by the device expf:
+ * <= 1e-4 relative (in practice ~1e-7). */
+int sm_cost_censusgrad(sm_ctx* ctx, const uint64_t* d_cenL, const uint64_t* d_cenR, const float* d_gxL,
+                       const float* d_gyL, const float* d_gxR, const float* d_gyR, const uint16_t* d_armsView,
+                       int H, int W, int D, int func, float lamCen, float lamG, float gradTrunc, int LOR,
+                       float* d_vol);
 
 /* ---- aggregation: CBCA ---------------------------------------------------- */
 /* calHorVerDis<uchar> (stereoMatching.cpp:2958-3050) for one 3-channel image.

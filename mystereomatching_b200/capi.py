@@ -30,6 +30,7 @@ class SmParams(C.Structure):
         ("aggregation", C.c_int), ("Do_refine", C.c_int), ("Do_LRConsis", C.c_int),
         ("Do_regionVote", C.c_int), ("Do_properIpol", C.c_int), ("Do_lastMedianBlur", C.c_int),
         ("crossScaleLambda", C.c_float), ("sgm_grouped", C.c_int),
+        ("costcalculation", C.c_int), ("cg_lamCen", C.c_float), ("cg_lamG", C.c_float), ("gradTrunc", C.c_float),
     ]
 
 
@@ -61,6 +62,9 @@ SIGNATURES = {
     "sm_cost_ad": ([_P, _P, _P, _I, _I, _I, _I, _F, _P], _I),
     "sm_cost_adcensus": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P], _I),
     "sm_combine_exp": ([_P, _P, _P, _Z, _F, _F, _P], _I),
+    "sm_grad_xy": ([_P, _P, _I, _I, _P, _P], _I),
+    "sm_cost_grad": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P], _I),
+    "sm_cost_censusgrad": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P], _I),
     "sm_arms": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_arms_intersect": ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
     "sm_cbca": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I], _I),
@@ -224,6 +228,28 @@ class Ctx:
     def combine_exp(self, a, b, l0=10.0, l1=30.0):
         out = self.torch.empty_like(a)
         check(self.L.sm_combine_exp(self.h, _ptr(a), _ptr(b), a.numel(), l0, l1, _ptr(out)))
+        return out
+
+    def grad_xy(self, gray):
+        H, W = gray.shape
+        gx = self.empty((H, W), self.torch.float32)
+        gy = self.empty((H, W), self.torch.float32)
+        check(self.L.sm_grad_xy(self.h, _ptr(gray), H, W, _ptr(gx), _ptr(gy)))
+        return gx, gy
+
+    def cost_grad(self, gL, gR, arms_view, D, LOR=0, trunc=500.0):
+        """gL / gR = (gx, gy) of the left / right gray image; arms_view = HVL[LOR]."""
+        H, W = gL[0].shape
+        out = self.empty((H, W, D), self.torch.float32)
+        check(self.L.sm_cost_grad(self.h, _ptr(gL[0]), _ptr(gL[1]), _ptr(gR[0]), _ptr(gR[1]), _ptr(arms_view), H, W, D,
+                                  trunc, LOR, _ptr(out)))
+        return out
+
+    def cost_censusgrad(self, cL, cR, gL, gR, arms_view, D, func=3, LOR=0, lamCen=13.0, lamG=1.0, trunc=500.0):
+        H, W = gL[0].shape
+        out = self.empty((H, W, D), self.torch.float32)
+        check(self.L.sm_cost_censusgrad(self.h, _ptr(cL), _ptr(cR), _ptr(gL[0]), _ptr(gL[1]), _ptr(gR[0]), _ptr(gR[1]),
+                                        _ptr(arms_view), H, W, D, func, lamCen, lamG, trunc, LOR, _ptr(out)))
         return out
 
     def arms(self, bgr, L=17, L_out=34, tau=20, tau_out=6, minL=1):

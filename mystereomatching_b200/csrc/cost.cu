@@ -112,15 +112,30 @@ __global__ void __launch_bounds__(COST_THREADS, 1)
       sCen[i] = c0; sPix[i] = px; sHi[i] = hi;
     }
     __syncthreads();
+    // the anchor's own words are fetched one anchor ahead, so the warp never waits on global memory between anchors
+    uint32_t pa_n = 0, ca1_n = 0;
+    uint64_t ca0_n = 0;
+    if (warp < nA) {
+      const size_t p0 = (size_t)v * W + ua + warp;
+      if (NEED_AD) pa_n = pixA[p0];
+      if (NEED_CEN) {
+        ca0_n = cenA[p0 * nw];
+        if (nw == 2) ca1_n = (uint32_t)cenA[p0 * nw + 1];
+      }
+    }
     for (int a = warp; a < nA; a += COST_THREADS / 32) {
       const int u = ua + a;
       const size_t p = (size_t)v * W + u;
-      const uint32_t pa = NEED_AD ? (pixA[p] & 0x00FFFFFFu) : 0u;
-      uint64_t ca0 = 0;
-      uint32_t ca1 = 0;
-      if (NEED_CEN) {
-        ca0 = cenA[p * nw];
-        if (nw == 2) ca1 = (uint32_t)cenA[p * nw + 1];
+      const uint32_t pa = pa_n & 0x00FFFFFFu;
+      const uint64_t ca0 = ca0_n;
+      const uint32_t ca1 = ca1_n;
+      if (a + COST_THREADS / 32 < nA) {
+        const size_t pn = p + COST_THREADS / 32;
+        if (NEED_AD) pa_n = pixA[pn];
+        if (NEED_CEN) {
+          ca0_n = cenA[pn * nw];
+          if (nw == 2) ca1_n = (uint32_t)cenA[pn * nw + 1];
+        }
       }
       OutT* out = vol + p * D + lane;
       // in-range disparities of this pixel: view 0 (sgn +1): u - d >= 0; view 1: u + d < W

@@ -1,0 +1,189 @@
+// Gradient cost family -- SURVEY.md 8(f) rank 3: `costcalculation = "censusGrad"` is the selector the reference's
+// main_.cpp:15 compiles in, so it is the cost the reference's own driver feeds into CBCA.
+//
+//   calGrad / calGrad_y   stereoMatching.cpp:271-368   central differences on the gray image
+//   grad -> calgradvm     stereoMatching.cpp:603-656, 388-455   arm-weighted |dgx| , |dgy| volume
+//   censusGrad            stereoMatching.cpp:25-48     2 - exp(-census/lamCen) - exp(-grad/lamG)
+//
+// One pass writes vol[v][u][d] (float32, d fastest).  The gradient volume and the census volume of the reference
+// (two H*W*D temporaries each, stereoMatching.cpp:27-33, 609-617) are never materialised.  Same shape as k_cost
+// (cost.cu): persistent CTAs walk (row, segment) items, the partner image's census words and two gradient planes
+// for the segment's D-1+SEG positions are staged in shared memory, a warp takes an anchor pixel and its lanes run
+// along d, so every warp store is one coalesced 128-byte line.
+//
+// Parity.  sm_cost_grad (the gradient volume alone): bit-exact -- gradients are multiples of 0.5 (exact floats),
+// a = sH / (sH + sV) is one IEEE division, a*dx + (1-a)*dy is two multiplications and one addition, none contracted
+// (-fmad=false; the intrinsics below say so explicitly).  sm_cost_censusgrad: the census term comes from a host
+// table built with the same libm expf the reference calls; exp(-grad/lamG) takes a continuous argument, so it is
+// evaluated by the device expf (<= 2 ulp) -> the combined volume agrees to ~1e-7 relative; the tests assert the
+// north star's 1e-4.
+#include <math.h>
+
+#include "common.cuh"
+
+__global__ void k_grad_xy(const uint8_t* __restrict__ gray, int H, int W, float* __restrict__ gx,
+                          float* __restrict__ gy) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+  if (u >= W || v >= H) return;
+  const size_t p = (size_t)v * W + u;
+  // interior: 0.5 * (next - prev) (double product of an int, exact in float); borders: next - prev of the border pair
+  int dx, dy;
+  float sx = 0.5f, sy = 0.5f;
+  if (u == 0) { dx = (int)gray[p + 1] - (int)gray[p]; sx = 1.f; }
+  else if (u == W - 1) { dx = (int)gray[p] - (int)gray[p - 1]; sx = 1.f; }
+  else dx = (int)gray[p + 1] - (int)gray[p - 1];
+  if (v == 0) { dy = (int)gray[p + W] - (int)gray[p]; sy = 1.f; }
+  else if (v == H - 1) { dy = (int)gray[p] - (int)gray[p - W]; sy = 1.f; }
+  else dy = (int)gray[p + W] - (int)gray[p - W];
+  gx[p] = sx * (float)dx;
+  gy[p] = sy * (float)dy;
+}
+
+extern "C" int sm_grad_xy(sm_ctx* ctx, const uint8_t* d_gray, int H, int W, float* d_gx, float* d_gy) {
+  SM_CHECK_ARG(ctx && d_gray && d_gx && d_gy && H >= 2 && W >= 2);   // the reference reads pixel 1 / H-2 unconditionally
+  dim3 block(32, 8), grid(sm_div_up(W, 32), sm_div_up(H, 8));
+  SM_LAUNCH(ctx, k_grad_xy, grid, block, 0, d_gray, H, W, d_gx, d_gy);
+  return SM_OK;
+}
+
+#define CG_THREADS 512
+#define CG_SEG 256
+#define CG_MAX_CODE 71
+
+// FUSED 0: gradient volume (calgradvm).  FUSED 1: censusGrad.
+template <int FUSED>
+__global__ void __launch_bounds__(CG_THREADS, 2)
+    k_cost_grad(const float* __restrict__ gxA, const float* __restrict__ gyA, const float* __restrict__ gxO,
+                const float* __restrict__ gyO, const uint16_t* __restrict__ armsA, const uint64_t* __restrict__ cenA,
+                const uint64_t* __restrict__ cenO, int nw, int H, int W, int D, int sgn, int codeLen, float Trunc,
+                float oorGrad, float lamG, const float* __restrict__ tabCen, float* __restrict__ vol) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int maxEntries = CG_SEG + D - 1;
+  float* sT1 = reinterpret_cast<float*>(smem_raw);                       // [72][32]: 2 - exp(-c/lamCen)
+  uint64_t* sCen = reinterpret_cast<uint64_t*>(sT1 + (FUSED ? (CG_MAX_CODE + 1) * 32 : 0));
+  float* sGx = reinterpret_cast<float*>(sCen + (FUSED ? maxEntries : 0));
+  float* sGy = sGx + maxEntries;
+  uint32_t* sHi = reinterpret_cast<uint32_t*>(sGy + maxEntries);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float oor = oorGrad;
+  if (FUSED) {
+    for (int i = tid; i < (codeLen + 1) * 32; i += CG_THREADS) sT1[i] = 2.0f - tabCen[i >> 5];
+    oor = __fsub_rn(2.0f - tabCen[codeLen], expf(__fdiv_rn(-oorGrad, lamG)));
+  }
+  const int nSeg = (W + CG_SEG - 1) / CG_SEG;
+  const int nItems = H * nSeg;
+  const int nd = (D + 31) >> 5;
+  for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+    const int v = item / nSeg, ua = (item - v * nSeg) * CG_SEG;
+    const int nA = min(CG_SEG, W - ua);
+    const int elo = sgn > 0 ? ua - (D - 1) : ua;
+    const int cnt = nA + D - 1;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += CG_THREADS) {
+      const int e = elo + i;
+      float x = 0.f, y = 0.f;
+      uint64_t c0 = 0;
+      uint32_t hi = 0;
+      if (e >= 0 && e < W) {
+        const size_t p = (size_t)v * W + e;
+        x = gxO[p]; y = gyO[p];
+        if (FUSED) {
+          c0 = cenO[p * nw];
+          if (nw == 2) hi = (uint32_t)cenO[p * nw + 1];
+        }
+      }
+      sGx[i] = x; sGy[i] = y;
+      if (FUSED) { sCen[i] = c0; sHi[i] = hi; }
+    }
+    __syncthreads();
+    for (int a = warp; a < nA; a += CG_THREADS / 32) {
+      const int u = ua + a;
+      const size_t p = (size_t)v * W + u;
+      const float ax = gxA[p], ay = gyA[p];
+      // a = shortestH / (shortestH + shortestV) from the view's own arms, read as short (stereoMatching.cpp:403-420)
+      const uint16_t* ar = armsA + p * 5;
+      float sH = (float)min((int)(short)ar[0], (int)(short)ar[1]);
+      float sV = (float)min((int)(short)ar[2], (int)(short)ar[3]);
+      if (sH == 0.f) sH = 1.f;
+      if (sV == 0.f) sV = 1.f;
+      const float wa = __fdiv_rn(sH, __fadd_rn(sH, sV)), wb = __fsub_rn(1.f, wa);
+      uint64_t ca0 = 0;
+      uint32_t ca1 = 0;
+      if (FUSED) {
+        ca0 = cenA[p * nw];
+        if (nw == 2) ca1 = (uint32_t)cenA[p * nw + 1];
+      }
+      float* out = vol + p * D + lane;
+      const int nvalid = min(D, sgn > 0 ? u + 1 : W - u);
+      const int base = u - elo - sgn * lane;
+      for (int j = 0; j < nd; j++) {
+        const int d = lane + j * 32;
+        if (d >= D) break;
+        float r = oor;
+        if (d < nvalid) {
+          const int idx = base - sgn * j * 32;
+          const float dx = fminf(fabsf(__fsub_rn(ax, sGx[idx])), Trunc);
+          const float dy = fminf(fabsf(__fsub_rn(ay, sGy[idx])), Trunc);
+          // view 1: the reference subtracts grad0[u0] - grad1[u1] with the anchor on the right; |.| makes the order moot
+          const float g = __fadd_rn(__fmul_rn(wa, dx), __fmul_rn(wb, dy));
+          if (FUSED) {
+            const uint64_t x0 = ca0 ^ sCen[idx];
+            int c;
+            if (nw == 2) c = __popcll(x0) + __popc(ca1 ^ sHi[idx]);
+            else c = __popcll(x0);
+            r = __fsub_rn(sT1[(c << 5) + lane], expf(__fdiv_rn(-g, lamG)));
+          } else {
+            r = g;
+          }
+        }
+        out[j * 32] = r;
+      }
+    }
+  }
+}
+
+template <int FUSED>
+static int launch_cost_grad(sm_ctx* ctx, const float* gxA, const float* gyA, const float* gxO, const float* gyO,
+                            const uint16_t* armsA, const uint64_t* cenA, const uint64_t* cenO, int nw, int H, int W, int D,
+                            int sgn, int codeLen, float Trunc, float lamG, const float* tabCen, float* vol) {
+  size_t smem = (size_t)(CG_SEG + D - 1) * (2 * sizeof(float));
+  if (FUSED) smem += (CG_MAX_CODE + 1) * 32 * sizeof(float) + (size_t)(CG_SEG + D - 1) * (sizeof(uint64_t) + sizeof(uint32_t));
+  SM_CUDA(cudaFuncSetAttribute(k_cost_grad<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nItems = H * sm_div_up(W, CG_SEG);
+  const int grid = min(nItems, 2 * ctx->num_sms);
+  // out of range: sqrt(pow(Trunc, 2) * 2) in double (pow(float, int) promotes), stored to float (stereoMatching.cpp:433)
+  const float oorGrad = (float)sqrt(pow((double)Trunc, 2) * 2);
+  SM_LAUNCH(ctx, (k_cost_grad<FUSED>), grid, CG_THREADS, smem, gxA, gyA, gxO, gyO, armsA, cenA, cenO, nw, H, W, D, sgn,
+            codeLen, Trunc, oorGrad, lamG, tabCen, vol);
+  return SM_OK;
+}
+
+extern "C" int sm_cost_grad(sm_ctx* ctx, const float* d_gxL, const float* d_gyL, const float* d_gxR, const float* d_gyR,
+                            const uint16_t* d_armsView, int H, int W, int D, float trunc, int LOR, float* d_vol) {
+  SM_CHECK_ARG(ctx && d_gxL && d_gyL && d_gxR && d_gyR && d_armsView && d_vol);
+  SM_CHECK_ARG(H > 0 && W > 0 && D > 0 && D <= 512 && (LOR == 0 || LOR == 1));
+  if (LOR == 0)
+    return launch_cost_grad<0>(ctx, d_gxL, d_gyL, d_gxR, d_gyR, d_armsView, nullptr, nullptr, 0, H, W, D, +1, 0, trunc, 1.f,
+                               nullptr, d_vol);
+  return launch_cost_grad<0>(ctx, d_gxR, d_gyR, d_gxL, d_gyL, d_armsView, nullptr, nullptr, 0, H, W, D, -1, 0, trunc, 1.f,
+                             nullptr, d_vol);
+}
+
+extern "C" int sm_cost_censusgrad(sm_ctx* ctx, const uint64_t* d_cenL, const uint64_t* d_cenR, const float* d_gxL,
+                                  const float* d_gyL, const float* d_gxR, const float* d_gyR, const uint16_t* d_armsView,
+                                  int H, int W, int D, int func, float lamCen, float lamG, float gradTrunc, int LOR,
+                                  float* d_vol) {
+  SM_CHECK_ARG(ctx && d_cenL && d_cenR && d_gxL && d_gyL && d_gxR && d_gyR && d_armsView && d_vol);
+  SM_CHECK_ARG(H > 0 && W > 0 && D > 0 && D <= 512 && (LOR == 0 || LOR == 1) && (func == 0 || func == 3));
+  SM_CHECK_ARG(lamCen > 0.f && lamG > 0.f);
+  const int codeLen = sm_census_code_length(func), nw = sm_census_words(func);
+  const float *tAD, *tCen;
+  // only the census table is used; the AD half of the cached pair keeps whatever the pipeline last asked for
+  SM_TRY(smi_exp_tables(ctx, ctx->tab_trunc >= 0.f ? ctx->tab_trunc : 1000.f, ctx->tab_lamAD > 0.f ? ctx->tab_lamAD : 10.f,
+                        lamCen, codeLen, &tAD, &tCen));
+  if (LOR == 0)
+    return launch_cost_grad<1>(ctx, d_gxL, d_gyL, d_gxR, d_gyR, d_armsView, d_cenL, d_cenR, nw, H, W, D, +1, codeLen,
+                               gradTrunc, lamG, tCen, d_vol);
+  return launch_cost_grad<1>(ctx, d_gxR, d_gyR, d_gxL, d_gyL, d_armsView, d_cenR, d_cenL, nw, H, W, D, -1, codeLen,
+                             gradTrunc, lamG, tCen, d_vol);
+}

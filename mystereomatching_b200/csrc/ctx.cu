@@ -50,6 +50,10 @@ extern "C" void sm_params_default(sm_params* p, int maxDisp) {
   p->Do_lastMedianBlur = 1;
   p->crossScaleLambda = -1.f;
   p->sgm_grouped = 1;
+  p->costcalculation = 0;
+  p->cg_lamCen = 13.f;
+  p->cg_lamG = 1.f;
+  p->gradTrunc = 500.f;
 }
 
 extern "C" int sm_ctx_create(sm_ctx** out, int device, void* stream) {

@@ -22,6 +22,7 @@ struct sm_pipeline {
   uint64_t* cen[2] = {nullptr, nullptr};
   uint16_t* arms[2] = {nullptr, nullptr};
   float* vol[4] = {nullptr, nullptr, nullptr, nullptr};  // vm[0], vm[1], scratch, second scratch (roles rotate after SGM)
+  float* grad[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // censusGrad: gx, gy per image
   double* nlwork = nullptr;
   int16_t *disp[2] = {nullptr, nullptr}, *dtmp = nullptr;
   uint8_t* h_in = nullptr;   // pinned staging: bgrL | bgrR | grayL | grayR
@@ -46,6 +47,7 @@ extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
   for (int i = 0; i < 2; i++) {
     cudaFree(pl->bgr[i]); cudaFree(pl->gray[i]); cudaFree(pl->pix[i]); cudaFree(pl->armpk[i]);
     cudaFree(pl->cen[i]); cudaFree(pl->arms[i]); cudaFree(pl->disp[i]);
+    cudaFree(pl->grad[i][0]); cudaFree(pl->grad[i][1]);
   }
   for (int i = 0; i < 4; i++) cudaFree(pl->vol[i]);
   cudaFree(pl->nlwork);
@@ -66,6 +68,8 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   SM_CHECK_ARG(p->censusFunc == 0 || p->censusFunc == 3);
   SM_CHECK_ARG(p->sgm_paths >= 0 && p->sgm_paths <= 8);
   SM_CHECK_ARG(p->aggregation >= 0 && p->aggregation <= 2);
+  SM_CHECK_ARG(p->costcalculation == 0 || p->costcalculation == 1);
+  SM_CHECK_ARG(p->costcalculation == 0 || (H >= 2 && W >= 2 && p->cg_lamCen > 0.f && p->cg_lamG > 0.f));
   SM_CHECK_ARG(p->cbca_crossL_out >= 0 && p->cbca_crossL_out <= 255);
   SM_CUDA(cudaSetDevice(ctx->device));
   sm_pipeline* pl = new sm_pipeline();
@@ -81,6 +85,8 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->cen[i], npix * 8 * nw);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->arms[i], npix * 5 * 2);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->disp[i], npix * 2);
+    for (int k = 0; k < 2 && p->costcalculation == 1; k++)
+      if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->grad[i][k], npix * sizeof(float));
   }
   // a fourth volume only where the two views' SGM sweeps can share a launch (two sums are written at once)
   const bool two_view_sgm = p->sgm_paths == 8 && p->sgm_grouped && p->Do_refine && p->Do_LRConsis;
@@ -158,11 +164,6 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   }
   PL_MARK(1);
   const int imgNum = P.Do_LRConsis ? 2 : 1;  // stereoMatching.cpp:898
-  for (int i = 0; i < imgNum; i++)
-    SM_TRY(smi_cost_adcensus_packed(c, pl->pix[0], pl->pix[1], pl->cen[0], pl->cen[1], H, W, D, P.censusFunc,
-                                    P.adTrunc, P.lamAD, P.lamCen, i, pl->vol[i]));
-  PL_MARK(2);
-  // ---- aggregation
   const int views = (P.Do_refine && P.Do_LRConsis) ? 2 : 1;  // stereoMatching.cpp:1054, 5592
   pl->have_arms = false;
   auto ensure_arms = [&]() -> int {
@@ -175,6 +176,20 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
     pl->have_arms = true;
     return SM_OK;
   };
+  if (P.costcalculation == 0) {
+    for (int i = 0; i < imgNum; i++)
+      SM_TRY(smi_cost_adcensus_packed(c, pl->pix[0], pl->pix[1], pl->cen[0], pl->cen[1], H, W, D, P.censusFunc,
+                                      P.adTrunc, P.lamAD, P.lamCen, i, pl->vol[i]));
+  } else {
+    // censusGrad (stereoMatching.cpp:25-48): grad() computes the arms first (stereoMatching.cpp:628-631)
+    for (int i = 0; i < 2; i++) SM_TRY(sm_grad_xy(c, pl->gray[i], H, W, pl->grad[i][0], pl->grad[i][1]));
+    SM_TRY(ensure_arms());
+    for (int i = 0; i < imgNum; i++)
+      SM_TRY(sm_cost_censusgrad(c, pl->cen[0], pl->cen[1], pl->grad[0][0], pl->grad[0][1], pl->grad[1][0], pl->grad[1][1],
+                                pl->arms[i], H, W, D, P.censusFunc, P.cg_lamCen, P.cg_lamG, P.gradTrunc, i, pl->vol[i]));
+  }
+  PL_MARK(2);
+  // ---- aggregation
   if (P.aggregation == 1) {
     SM_TRY(ensure_arms());
     PL_MARK(3);

@@ -151,6 +151,7 @@ void StereoMatching::pipeline() {
 
 void StereoMatching::costCalculate() {
   if (costcalculation == "ADCensus") ADCensusCal();
+  else if (costcalculation == "censusGrad") censusGrad(vm);
   else if (costcalculation == "Census") censusCal(vm, 1);
   else if (costcalculation == "AD") asdCal(vm, "AD", Do_LRConsis ? 2 : 1, 1000);
   else throw cv::Exception("costCalculate: costcalculation \"" + costcalculation + "\" is outside the hot path");
@@ -304,6 +305,73 @@ void StereoMatching::adCensus(vector<Mat>& vm_ad, vector<Mat>& vm_census) {
 }
 
 // ------------------------------------------------------------------ aggregation
+// ---- gradient cost family (stereoMatching.cpp:25-48, 271-368, 388-455, 603-656)
+void StereoMatching::ensureGrad() {
+  for (int i = 0; i < 2; i++) {
+    for (int k = 0; k < 2; k++)
+      if (!d_grad_[i][k]) d_grad_[i][k] = (float*)dalloc((size_t)h_ * w_ * sizeof(float));
+    check(sm_grad_xy(ctx_, d_gray_[i], h_, w_, d_grad_[i][0], d_grad_[i][1]), "sm_grad_xy");
+  }
+}
+void StereoMatching::calGrad(Mat& grad, Mat& img) {
+  CV_Assert(img.channels() == 1 && img.rows == h_ && img.cols == w_);   // the path feeds I_g (stereoMatching.cpp:620)
+  if (grad.empty()) grad.create(h_, w_, CV_32F);
+  const size_t n = (size_t)h_ * w_;
+  TmpDev g(ctx_, n), gx(ctx_, n * 4), gy(ctx_, n * 4);
+  upload(g.p, img.data, n);
+  check(sm_grad_xy(ctx_, g.as<uint8_t>(), h_, w_, gx.as<float>(), gy.as<float>()), "sm_grad_xy");
+  download(grad.data, gx.p, n * 4);
+}
+void StereoMatching::calGrad_y(Mat& grad, Mat& img) {
+  CV_Assert(img.channels() == 1 && img.rows == h_ && img.cols == w_);
+  if (grad.empty()) grad.create(h_, w_, CV_32F);
+  const size_t n = (size_t)h_ * w_;
+  TmpDev g(ctx_, n), gx(ctx_, n * 4), gy(ctx_, n * 4);
+  upload(g.p, img.data, n);
+  check(sm_grad_xy(ctx_, g.as<uint8_t>(), h_, w_, gx.as<float>(), gy.as<float>()), "sm_grad_xy");
+  download(grad.data, gy.p, n * 4);
+}
+void StereoMatching::calgradvm(Mat& vm_, vector<Mat>& grad_, vector<Mat>& grad_y, int num, float Trunc) {
+  CV_Assert(grad_.size() >= 2 && grad_y.size() >= 2 && grad_[0].depth() == CV_32F && (num == 0 || num == 1));
+  ensureArms();
+  ensure_vol(vm_, h_, w_, d_);
+  const size_t n = (size_t)h_ * w_;
+  TmpDev gx0(ctx_, n * 4), gy0(ctx_, n * 4), gx1(ctx_, n * 4), gy1(ctx_, n * 4), out(ctx_, n * d_ * 4);
+  upload(gx0.p, grad_[0].data, n * 4); upload(gx1.p, grad_[1].data, n * 4);
+  upload(gy0.p, grad_y[0].data, n * 4); upload(gy1.p, grad_y[1].data, n * 4);
+  check(sm_cost_grad(ctx_, gx0.as<float>(), gy0.as<float>(), gx1.as<float>(), gy1.as<float>(), d_arms_[num], h_, w_, d_,
+                     Trunc, num, out.as<float>()), "sm_cost_grad");
+  download(vm_.data, out.p, n * d_ * 4);
+}
+void StereoMatching::grad(vector<Mat>& vm_grad, float Trunc) {
+  const int imgNum = Do_LRConsis ? 2 : 1;
+  CV_Assert((int)vm_grad.size() >= imgNum);
+  ensureGrad();
+  ensureArms();   // stereoMatching.cpp:628-631
+  for (int i = 0; i < imgNum; i++) {
+    float* dst = &vm_grad == &vm ? d_vol_[i] : d_vol_[2];
+    check(sm_cost_grad(ctx_, d_grad_[0][0], d_grad_[0][1], d_grad_[1][0], d_grad_[1][1], d_arms_[i], h_, w_, d_, Trunc, i,
+                       dst), "sm_cost_grad");
+    if (&vm_grad == &vm) vm_dev_fresh_[i] = true;
+    else { ensure_vol(vm_grad[i], h_, w_, d_); download(vm_grad[i].data, dst, (size_t)h_ * w_ * d_ * 4); }
+  }
+}
+void StereoMatching::censusGrad(vector<Mat>& vm_) {
+  const int imgNum = Do_LRConsis ? 2 : 1;
+  CV_Assert((int)vm_.size() >= imgNum);
+  for (int i = 0; i < 2; i++) check(sm_census(ctx_, d_gray_[i], h_, w_, param_.censusFunc, d_cen_[i]), "sm_census");
+  ensureGrad();
+  ensureArms();
+  for (int i = 0; i < imgNum; i++) {
+    float* dst = &vm_ == &vm ? d_vol_[i] : d_vol_[2];
+    check(sm_cost_censusgrad(ctx_, d_cen_[0], d_cen_[1], d_grad_[0][0], d_grad_[0][1], d_grad_[1][0], d_grad_[1][1],
+                             d_arms_[i], h_, w_, d_, param_.censusFunc, (float)param_.lamCen, (float)param_.lamG, 500.f, i,
+                             dst), "sm_cost_censusgrad");
+    if (&vm_ == &vm) vm_dev_fresh_[i] = true;
+    else { ensure_vol(vm_[i], h_, w_, d_); download(vm_[i].data, dst, (size_t)h_ * w_ * d_ * 4); }
+  }
+}
+
 void StereoMatching::initArm() {
   HVL_num = 2;
   HVL.resize(2);

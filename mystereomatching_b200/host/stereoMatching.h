@@ -37,7 +37,7 @@ class StereoMatching {
  public:
   // algorithm selection lives in mutable statics, as in the reference (stereoMatching.h:50-54, main_.cpp:15-19)
   static const std::string root;
-  static std::string costcalculation;  // "ADCensus" | "Census" | "AD"
+  static std::string costcalculation;  // "ADCensus" | "censusGrad" | "Census" | "AD"
   static std::string aggregation;      // "CBCA" | "NL" | ""
   static std::string optimization;     // "sgm" | ""
   static std::string object;
@@ -102,6 +102,13 @@ class StereoMatching {
   void gen_cenVM_XOR(vector<Mat>& census, Mat& cenVm, int codeLength, float truncRat, int LOR = 0);  // :936-981
   void gen_vm_from2vm_exp(cv::Mat& combinedVm, cv::Mat& vm0, cv::Mat& vm1, const float ARU0, const float ARU1,
                           int LOR);                                                     // stereoMatching.cpp:3566-3590
+
+  // gradient family ("censusGrad" is the selector main_.cpp:15 compiles in)
+  void censusGrad(vector<Mat>& vm);                                                     // stereoMatching.cpp:25-48
+  void grad(vector<Mat>& vm_grad, float Trunc);                                         // stereoMatching.cpp:603-656
+  void calGrad(Mat& grad, Mat& img);                                                    // stereoMatching.cpp:271-318
+  void calGrad_y(Mat& grad, Mat& img);                                                  // stereoMatching.cpp:320-368
+  void calgradvm(Mat& vm, vector<Mat>& grad, vector<Mat>& grad_y, int num, float Trunc);  // stereoMatching.cpp:388-455
 
   // ---- aggregation
   void CBCA();                                                                          // stereoMatching.cpp:4333-4402
@@ -168,6 +175,8 @@ class StereoMatching {
   uint8_t *d_bgr_[2] = {nullptr, nullptr}, *d_gray_[2] = {nullptr, nullptr};
   uint64_t* d_cen_[2] = {nullptr, nullptr};
   uint16_t* d_arms_[2] = {nullptr, nullptr};
+  float* d_grad_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // gx, gy per image (allocated on first use)
+  void ensureGrad();
   float* d_vol_[3] = {nullptr, nullptr, nullptr};   // vm[0], vm[1], scratch
   int16_t *d_disp_[2] = {nullptr, nullptr}, *d_tmp16_ = nullptr;
   bool vm_dev_fresh_[2] = {false, false};   // device copy is the authoritative one (host Mat stale)

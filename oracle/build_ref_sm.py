@@ -65,6 +65,13 @@ CPP_FUNCS = [
     (r"^void StereoMatching::LRConsistencyCheck_new\(", "LRConsistencyCheck_new"),
     (r"^void StereoMatching::regionVote_my\(", "regionVote_my"),
     (r"^void StereoMatching::properIpol\(", "properIpol"),
+    # the gradient cost family: "censusGrad" is the selector main_.cpp:15 compiles in
+    (r"^void StereoMatching::censusGrad\(", "censusGrad"),
+    (r"^void StereoMatching::grad\(vector<Mat>& vm_grad, float Trunc\)", "grad"),
+    (r"^void StereoMatching::calGrad\(", "calGrad"),
+    (r"^void StereoMatching::calGrad_y\(", "calGrad_y"),
+    (r"^void StereoMatching::calgradvm\(", "calgradvm"),
+    (r"^void StereoMatching::calgradvm_1d\(", "calgradvm_1d"),
 ]
 # member functions defined inside the class body of stereoMatching.h
 H_FUNCS = [

@@ -27,15 +27,17 @@ class OrcParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("D", "censusFunc", "paths", "iters", "L", "L_out", "tau",
                                        "tau_out", "minL", "corDifThres", "reduCoeffi1")] + \
                [(n, C.c_float) for n in ("adTrunc", "lamAD", "lamCen", "LRmaxDiff", "voteRatio")] + \
-               [(n, C.c_int) for n in ("voteS", "voteNums", "DISP_OCC", "do_refine", "aggregation")]
+               [(n, C.c_int) for n in ("voteS", "voteNums", "DISP_OCC", "do_refine", "aggregation", "costcalc")] + \
+               [(n, C.c_float) for n in ("cgLamCen", "cgLamG", "gradTrunc")]
 
 
-def default_params(D, paths=4, census_func=3, do_refine=1, aggregation=1):
+def default_params(D, paths=4, census_func=3, do_refine=1, aggregation=1, costcalc=0):
     """Reference defaults: stereoMatching.h:204-350, stereoMatching.cpp:905, 5270."""
     return OrcParams(D=D, censusFunc=census_func, paths=paths, iters=2, L=17, L_out=34, tau=20,
                      tau_out=6, minL=1, corDifThres=15, reduCoeffi1=4, adTrunc=1000.0, lamAD=10.0,
                      lamCen=30.0, LRmaxDiff=0.0, voteRatio=0.4, voteS=20, voteNums=2, DISP_OCC=-32,
-                     do_refine=do_refine, aggregation=aggregation)
+                     do_refine=do_refine, aggregation=aggregation, costcalc=costcalc, cgLamCen=13.0, cgLamG=1.0,
+                     gradTrunc=500.0)
 
 
 def build(force=False):
@@ -62,6 +64,8 @@ def lib():
         "orc_ad_vol": ([u8p, u8p, I, I, I, I, F, f32p], None),
         "orc_combine_exp": ([f32p, f32p, C.c_long, F, F, f32p], None),
         "orc_exp_tables": ([F, F, F, I, f32p, f32p], None),
+        "orc_grad_xy": ([u8p, I, I, f32p, f32p], None),
+        "orc_grad_vol": ([f32p, f32p, f32p, f32p, u16p, I, I, I, I, F, f32p], None),
         "orc_arms": ([u8p, I, I, I, I, I, I, I, I, u16p], None),
         "orc_arms_intersect": ([u16p, u16p, I, I, I, I, u16p], None),
         "orc_cbca": ([f32p, u16p, u16p, I, I, I, I, I, P], None),
@@ -156,6 +160,32 @@ def adcensus_vol(bgrL, bgrR, grayL, grayR, D, LOR=0, func=3, trunc=1000.0, lamAD
     ad = ad_vol(bgrL, bgrR, D, LOR, trunc)
     cen = hamming_vol(census(grayL, func), census(grayR, func), D, func, LOR)
     return combine_exp(ad, cen, lamAD, lamCen)
+
+
+def grad_xy(gray):
+    """calGrad / calGrad_y on a gray image (stereoMatching.cpp:271-368)."""
+    H, W = gray.shape
+    gx, gy = np.empty((H, W), np.float32), np.empty((H, W), np.float32)
+    lib().orc_grad_xy(np.ascontiguousarray(gray), H, W, gx, gy)
+    return gx, gy
+
+
+def grad_vol(grayL, grayR, arms_view, D, view=0, trunc=500.0):
+    """grad() -> calgradvm (stereoMatching.cpp:603-656, 388-455); arms_view = HVL[view]."""
+    H, W = grayL.shape
+    gx0, gy0 = grad_xy(grayL)
+    gx1, gy1 = grad_xy(grayR)
+    out = np.empty((H, W, D), np.float32)
+    lib().orc_grad_vol(gx0, gx1, gy0, gy1, np.ascontiguousarray(arms_view), H, W, D, view, trunc, out)
+    return out
+
+
+def censusgrad_vol(bgrL, bgrR, grayL, grayR, D, view=0, func=3, lamCen=13.0, lamG=1.0, trunc=500.0):
+    """censusGrad (stereoMatching.cpp:25-48): 2 - exp(-census/lamCen) - exp(-grad/lamG)."""
+    cl, cr = census(grayL, func), census(grayR, func)
+    ham = hamming_vol(cl, cr, D, func, view)
+    a = arms(bgrL if view == 0 else bgrR)
+    return combine_exp(ham, grad_vol(grayL, grayR, a, D, view, trunc), lamCen, lamG)
 
 
 def arms(img, L=17, L_out=34, tau=20, tau_out=6, minL=1):
@@ -398,7 +428,8 @@ def smref_lib():
         "smref_set_param": ([P, C.c_char_p, D_], I), "smref_get_param": ([P, C.c_char_p], D_),
         "smref_census": ([P, I, u64p], I), "smref_census_cal": ([P, I, f32p, f32p], None),
         "smref_ad": ([P, I, F, f32p], None), "smref_combine_exp": ([P, f32p, f32p, F, F, f32p], None),
-        "smref_adcensus": ([P], None), "smref_get_vm": ([P, I, f32p], None), "smref_set_vm": ([P, I, f32p], None),
+        "smref_adcensus": ([P], None), "smref_grad_xy": ([P, I, f32p, f32p], None),
+        "smref_grad_vm": ([P, F, f32p, f32p], None), "smref_censusgrad": ([P], None), "smref_get_vm": ([P, I, f32p], None), "smref_set_vm": ([P, I, f32p], None),
         "smref_arms": ([P, u16p, u16p], None), "smref_arms_intersection": ([P, I, u16p], None),
         "smref_cbca": ([P, I], None), "smref_cost_scan": ([P, I, I, f32p], None), "smref_sgm": ([P, I, I], None),
         "smref_wta": ([P, I, i16p], None), "smref_wta_co": ([P, I, i16p, i16p], None),
@@ -406,7 +437,7 @@ def smref_lib():
         "smref_lrc_new": ([P, i16p, i16p, u8p], None),
         "smref_region_vote": ([P, i16p, F, I], None), "smref_proper_ipol": ([P, i16p], None),
         "smref_median3_i16": ([i16p, I, I, i16p], None),
-        "smref_pipeline": ([P, I, I, P, P, P, P], None),
+        "smref_pipeline": ([P, I, I, P, P, P, P], None), "smref_pipeline2": ([P, I, I, I, P, P, P, P], None),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -473,6 +504,20 @@ class SmRef:
 
     def adcensus(self):
         self.L.smref_adcensus(self.h)
+        return self.vm(0), self.vm(1)
+
+    def grad_xy(self, img):
+        gx, gy = np.empty((self.H, self.W), np.float32), np.empty((self.H, self.W), np.float32)
+        self.L.smref_grad_xy(self.h, img, gx, gy)
+        return gx, gy
+
+    def grad_vm(self, trunc=500.0):
+        a, b = self._vol(), self._vol()
+        self.L.smref_grad_vm(self.h, trunc, a, b)
+        return a, b
+
+    def censusgrad(self):
+        self.L.smref_censusgrad(self.h)
         return self.vm(0), self.vm(1)
 
     def vm(self, view):
@@ -546,11 +591,11 @@ class SmRef:
         self.L.smref_proper_ipol(self.h, a)
         return a
 
-    def pipeline(self, paths=4, iters=2, want_vol=False):
+    def pipeline(self, paths=4, iters=2, want_vol=False, costcalc=0):
         wl = np.empty((self.H, self.W), np.int16)
         wr = np.empty((self.H, self.W), np.int16)
         rf = np.empty((self.H, self.W), np.int16)
         vol = self._vol() if want_vol else None
-        self.L.smref_pipeline(self.h, paths, iters, wl.ctypes.data, wr.ctypes.data, rf.ctypes.data,
-                              vol.ctypes.data if want_vol else None)
+        self.L.smref_pipeline2(self.h, costcalc, paths, iters, wl.ctypes.data, wr.ctypes.data, rf.ctypes.data,
+                               vol.ctypes.data if want_vol else None)
         return wl, wr, rf, vol

@@ -211,6 +211,56 @@ void orc_exp_tables(float trunc, float lamAD, float lamCen, int codeLength, floa
 }
 
 // ---------------------------------------------------------------------------
+// Gradient cost family ("censusGrad" is the selector main_.cpp:15 compiles in).
+//   calGrad / calGrad_y (stereoMatching.cpp:271-368), gray input: central difference 0.5*(next - prev), one-sided
+//     (next - prev of the two border pixels, NOT halved) in the first/last column resp. row.  Needs W,H >= 2.
+//   calgradvm (stereoMatching.cpp:388-455), gradFuse_adpWgt = 1, grad_use2direc = 1 (stereoMatching.h:245-246):
+//     a = sH / (sH + sV), sH = min(left,right) arm, sV = min(up,down) arm of the VIEW's own image (0 -> 1), read as
+//     short; in range: a*min(|gx0[u0]-gx1[u1]|,T) + (1-a)*min(|gy0[u0]-gy1[u1]|,T); out of range:
+//     sqrt(pow(T,2)*2) evaluated in double (pow(float,int) promotes), stored as float.
+//   censusGrad (stereoMatching.cpp:25-48): gen_vm_from2vm_exp(vm, censusVm, gradVm, lamCen, lamG) with grad(.,500).
+// ---------------------------------------------------------------------------
+void orc_grad_xy(const u8* gray, int H, int W, float* gx, float* gy) {
+  for (int v = 0; v < H; v++) {
+    const u8* i = gray + (long)v * W;
+    float* g = gx + (long)v * W;
+    for (int u = 1; u < W - 1; u++) g[u] = 0.5 * (i[u + 1] - i[u - 1]);
+    g[0] = i[1] - i[0];
+    g[W - 1] = i[W - 1] - i[W - 2];
+  }
+  for (int v = 1; v < H - 1; v++)
+    for (int u = 0; u < W; u++) gy[(long)v * W + u] = 0.5 * (gray[(long)(v + 1) * W + u] - gray[(long)(v - 1) * W + u]);
+  for (int u = 0; u < W; u++) {
+    gy[u] = gray[W + u] - gray[u];
+    gy[(long)(H - 1) * W + u] = gray[(long)(H - 1) * W + u] - gray[(long)(H - 2) * W + u];
+  }
+}
+
+void orc_grad_vol(const float* gx0, const float* gx1, const float* gy0, const float* gy1, const u16* armsView,
+                  int H, int W, int D, int num, float Trunc, float* vol) {
+  const int leftCoe = num == 1 ? 1 : 0, rightCoe = num == 1 ? 0 : -1;
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      const short* arm = (const short*)(armsView + ((long)v * W + u) * 5);
+      float shortestH = 10000, shortestV = 10000;
+      for (int dir = 0; dir < 2; dir++) if (arm[dir] < shortestH) shortestH = arm[dir];
+      for (int dir = 2; dir < 4; dir++) if (arm[dir] < shortestV) shortestV = arm[dir];
+      if (shortestH == 0) shortestH++;
+      if (shortestV == 0) shortestV++;
+      const float a = shortestH / (shortestH + shortestV);
+      float* o = vol + ((long)v * W + u) * D;
+      for (int d = 0; d < D; d++) {
+        const int u0 = u + leftCoe * d, u1 = u + rightCoe * d;
+        if (u0 >= W || u1 < 0) { o[d] = std::sqrt(std::pow((double)Trunc, 2) * 2); continue; }
+        const float dx = std::min(std::fabs(gx0[(long)v * W + u0] - gx1[(long)v * W + u1]), Trunc);
+        const float dy = std::min(std::fabs(gy0[(long)v * W + u0] - gy1[(long)v * W + u1]), Trunc);
+        o[d] = a * dx + (1 - a) * dy;
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Cross arms: calHorVerDis<uchar>(I,cross,L,L_out,C_D,C_D_out,minL)
 // (stereoMatching.cpp:2958-3050) with judgeColorDif (stereoMatching.cpp:2847).
 // cross: [H][W][5] u16 = [left,right,up,down,sum].  C = channels (3 for I_c).
@@ -608,6 +658,8 @@ struct orc_params {
   float adTrunc, lamAD, lamCen, LRmaxDiff, voteRatio;
   int voteS, voteNums, DISP_OCC, do_refine;
   int aggregation;  // 1 = "CBCA" (cbca_aggregate), 2 = "NL" (StereoMatching::NL: left volume only), 0 = none
+  int costcalc;     // 0 = "ADCensus", 1 = "censusGrad" (main_.cpp:15)
+  float cgLamCen, cgLamG, gradTrunc;  // 13, 1 (main_.cpp:60-61), 500 (stereoMatching.cpp:34)
 };
 void orc_nl(const u8* bgrL, int H, int W, int D, float* vol, i16* disp);  // nl_oracle.cpp
 }  // extern "C"
@@ -633,7 +685,12 @@ void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* gra
   lap(0);
   const int views = p->do_refine ? 2 : 1;
   std::vector<std::vector<float>> vm(2);
-  {
+  std::vector<u16> aL((long)H * W * 5), aR((long)H * W * 5);
+  auto arms = [&]() {
+    orc_arms(bgrL, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aL.data());
+    orc_arms(bgrR, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aR.data());
+  };
+  if (p->costcalc == 0) {
     std::vector<float> ad(n), cen(n);
     for (int i = 0; i < 2; i++) {  // cost volumes are always built for both views (:898)
       vm[i].resize(n);
@@ -641,11 +698,23 @@ void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* gra
       orc_hamming_vol(cL.data(), cR.data(), H, W, D, nw, codeLen, 1.0f, i, cen.data());
       orc_combine_exp(ad.data(), cen.data(), n, p->lamAD, p->lamCen, vm[i].data());
     }
+    lap(1);
+    arms();
+  } else {  // censusGrad (stereoMatching.cpp:25-48); grad() needs the arms first (:628-631)
+    const long np = (long)H * W;
+    std::vector<float> g(4 * np), gr(n), cen(n);
+    orc_grad_xy(grayL, H, W, g.data(), g.data() + np);
+    orc_grad_xy(grayR, H, W, g.data() + 2 * np, g.data() + 3 * np);
+    arms();
+    for (int i = 0; i < 2; i++) {
+      vm[i].resize(n);
+      orc_grad_vol(g.data(), g.data() + 2 * np, g.data() + np, g.data() + 3 * np, i == 0 ? aL.data() : aR.data(), H, W, D,
+                   i, p->gradTrunc, gr.data());
+      orc_hamming_vol(cL.data(), cR.data(), H, W, D, nw, codeLen, 1.0f, i, cen.data());
+      orc_combine_exp(cen.data(), gr.data(), n, p->cgLamCen, p->cgLamG, vm[i].data());
+    }
+    lap(1);
   }
-  lap(1);
-  std::vector<u16> aL((long)H * W * 5), aR((long)H * W * 5);
-  orc_arms(bgrL, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aL.data());
-  orc_arms(bgrR, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aR.data());
   lap(2);
   if (p->aggregation == 1) {
     for (int i = 0; i < views; i++)

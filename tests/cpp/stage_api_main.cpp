@@ -2,7 +2,7 @@
 // by tests/test_cpp_host.py, drives the class the way the reference's main() does (main_.cpp:138-166), and writes
 // raw outputs that the Python test compares with the CPU oracle.
 //   stage_api_test <in.bin> <out_prefix> <H> <W> <D> <paths> <mode>
-// in.bin = bgrL | bgrR | grayL | grayR (u8).  mode: "pipeline" | "stages" | "nl" | "errors"
+// in.bin = bgrL | bgrR | grayL | grayR (u8).  mode: "pipeline" | "stages" | "censusgrad" | "nl" | "errors"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -85,13 +85,27 @@ int main(int argc, char** argv) {
       qx_freeu(disp); qx_freeu_3(l3); qx_freeu_3(r3);
       return 0;
     }
-    StereoMatching::costcalculation = "ADCensus";
+    // "censusgrad": the selectors main_.cpp:15-17 compiles in (censusGrad + CBCA + sgm)
+    StereoMatching::costcalculation = mode == "censusgrad" ? "censusGrad" : "ADCensus";
     StereoMatching::aggregation = "CBCA";
     StereoMatching::optimization = "sgm";
     StereoMatching::Parameters param(D - 1, H, W, 13, 1, 2, 109, 10, "", 1);   // main_.cpp:60-64, 138
     StereoMatching sm(I1c, I2c, I1g, I2g, DT, m0, m1, m2, param);
     sm.setSgmPaths(paths);
     if (mode == "pipeline") {
+      sm.pipeline();
+    } else if (mode == "censusgrad") {
+      // the gradient family through its explicit-argument forms, then the whole chain with the reference's own selectors
+      std::vector<cv::Mat> g(2), gy(2);
+      for (int i = 0; i < 2; i++) { sm.calGrad(g[i], sm.I_g[i]); sm.calGrad_y(gy[i], sm.I_g[i]); }
+      dump(out + ".gx0.f32", g[0].data, npix * 4);
+      dump(out + ".gy1.f32", gy[1].data, npix * 4);
+      cv::Mat gv;
+      sm.calgradvm(gv, g, gy, 1, 500);
+      dump(out + ".gradvm1.f32", gv.data, npix * D * 4);
+      std::vector<cv::Mat> cg(2);
+      sm.censusGrad(cg);
+      dump(out + ".cg0.f32", cg[0].data, npix * D * 4);
       sm.pipeline();
     } else {   // "stages": the same chain, one public stage method at a time, through host-visible Mats where the API has them
       sm.ADCensusCal();

@@ -77,6 +77,20 @@ def stages(tag, H, W, D, kind, seed, full):
     out[f"{tag}_ipol1"] = ip1
     out[f"{tag}_ipol_labelled"] = r.proper_ipol(la)   # DISP_OCC / DISP_MIS branches
     r.close()
+    r = po.SmRef(bl, br, gl, gr, D)                   # gradient cost family, fresh instance
+    for i in (0, 1):                                  # calGrad / calGrad_y
+        gx, gy = r.grad_xy(i)
+        out[f"{tag}_gx{i}"], out[f"{tag}_gy{i}"] = gx.astype(np.float16), gy.astype(np.float16)   # multiples of 0.5, |.| <= 255
+        assert np.array_equal(gx, out[f"{tag}_gx{i}"].astype(np.float32))
+    g0, g1 = r.grad_vm(500.0)                         # grad() -> calgradvm
+    out[f"{tag}_gradvm_v0"], out[f"{tag}_gradvm_v1"] = g0, g1
+    v0, v1 = r.censusgrad()                           # censusGrad(vm)
+    out[f"{tag}_censusgrad_v0"], out[f"{tag}_censusgrad_v1"] = v0, v1
+    r.close()
+    rcg = po.SmRef(bl, br, gl, gr, D)
+    _, _, rf, _ = rcg.pipeline(8, 2, costcalc=1)      # main_.cpp:15's own selector through the whole chain
+    out[f"{tag}_pipe8_censusgrad_refined"] = rf
+    rcg.close()
     for paths in (4, 8):                              # whole default chain, fresh instance
         r = po.SmRef(bl, br, gl, gr, D)
         wl, wr, rf, _ = r.pipeline(paths, 2)

@@ -26,6 +26,8 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::regionVote_my(cv::Mat&, float, int)", "StereoMatching::properIpol(",
                 "StereoMatching::LRConsistencyCheck_normal(", "StereoMatching::genCensusCode_NC_Sur(",
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
+                "StereoMatching::censusGrad(", "StereoMatching::grad(", "StereoMatching::calGrad(",
+                "StereoMatching::calGrad_y(", "StereoMatching::calgradvm(",
                 "void StereoMatching::calHorVerDis<unsigned char>(", "void StereoMatching::calArms<unsigned char>(",
                 "NLCCA::aggreCV(", "qx_tree_filter::filter(double*, double*, int)", "qx_tree_filter::build_tree(",
                 "qx_nonlocal_cost_aggregation::matching_cost(unsigned char***, unsigned char***)",
@@ -76,6 +78,27 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
         assert np.array_equal(cv0, ham)
         lr = np.fromfile(prefix + ".lr3.f32", np.float32).reshape(H, W, D)
         assert np.array_equal(lr, po.sgm_path(ham, pair["bgrL"], 3))
+
+
+@pytest.mark.gpu
+def test_cpp_class_censusgrad_chain_matches_oracle(tmp_path):
+    """costcalculation = "censusGrad" (the selector the reference's main_.cpp:15 compiles in) through the C++ class."""
+    H, W, D, P = 60, 96, 24, 4
+    pair = synth.make_pair(H, W, D, "texture_warped", seed=23)
+    prefix, _ = _run(tmp_path, pair, D, P, "censusgrad")
+    bl, br, gl, gr = pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"]
+    gx0, _ = po.grad_xy(gl)
+    _, gy1 = po.grad_xy(gr)
+    assert np.array_equal(np.fromfile(prefix + ".gx0.f32", np.float32).reshape(H, W), gx0)
+    assert np.array_equal(np.fromfile(prefix + ".gy1.f32", np.float32).reshape(H, W), gy1)
+    gv = np.fromfile(prefix + ".gradvm1.f32", np.float32).reshape(H, W, D)
+    assert np.array_equal(gv.view(np.uint32), po.grad_vol(gl, gr, po.arms(br), D, 1).view(np.uint32))
+    cg = np.fromfile(prefix + ".cg0.f32", np.float32).reshape(H, W, D)
+    ref = po.censusgrad_vol(bl, br, gl, gr, D, 0)
+    assert np.all(np.abs(cg - ref) <= 1e-4 * np.abs(ref))
+    res = po.pipeline(bl, br, gl, gr, po.default_params(D, paths=P, costcalc=1))
+    dp = np.fromfile(prefix + ".dp0.i16", np.int16).reshape(H, W)
+    assert (dp == res[0]).mean() >= 0.995
 
 
 @pytest.mark.gpu

@@ -130,3 +130,30 @@ def test_whole_chain_equals_reference(ctx, g, tag, paths, grouped):
         assert _same(dl, ref)                      # reference summation order: identical map
     else:
         assert (dl == ref).mean() >= 0.995         # north_star: >= 99.5 % identical pixels
+
+
+# ---------------------------------------------------------------- gradient cost family
+@pytest.mark.parametrize("tag", TAGS)
+def test_gradient_family_equals_reference(ctx, g, tag):
+    bl, br, gl, gr, D = _inputs(g, tag)
+    H, W = gl.shape
+    gL, gR = ctx.grad_xy(ctx.dev(gl)), ctx.grad_xy(ctx.dev(gr))
+    for i, gg in enumerate((gL, gR)):
+        assert _same(gg[0].cpu().numpy(), g[f"{tag}_gx{i}"].astype(np.float32))
+        assert _same(gg[1].cpu().numpy(), g[f"{tag}_gy{i}"].astype(np.float32))
+    arms = [ctx.dev(g[f"{tag}_arms_L"].view(np.int16)), ctx.dev(g[f"{tag}_arms_R"].view(np.int16))]
+    dL, dR = _census(ctx, gl, 3), _census(ctx, gr, 3)
+    for v in (0, 1):
+        got = ctx.cost_grad(gL, gR, arms[v], D, v).cpu().numpy()
+        assert _same(got, g[f"{tag}_gradvm_v{v}"])                       # calgradvm: bit-exact
+        got = ctx.cost_censusgrad(dL, dR, gL, gR, arms[v], D, 3, v).cpu().numpy()
+        ref = g[f"{tag}_censusgrad_v{v}"]
+        assert np.all(np.abs(got - ref) <= 1e-4 * np.abs(ref))           # device expf: north_star's 1e-4 relative
+        assert np.abs(got - ref).max() <= 4e-7                           # in fact a couple of ulp of values in [0, 2]
+    params = capi.default_params(D - 1, sgm_paths=8, sgm_grouped=0, costcalculation=1)
+    pl = capi.Pipeline(ctx, H, W, params)
+    pl.upload(bl, br, gl, gr)
+    pl.run_device()
+    dl, _ = pl.download(want_right=True)
+    pl.close()
+    assert (dl == g[f"{tag}_pipe8_censusgrad_refined"]).mean() >= 0.995  # north_star: >= 99.5 % identical pixels
