@@ -19,8 +19,10 @@
 // by construction) and walks (row, 512-pixel segment) work items: the "other" image's census words and packed
 // pixel for the D-1+512 positions the segment can match against are staged in shared memory once, then every
 // warp takes anchor pixels and its lanes run along d, so each warp store is one fully coalesced 128-byte line.
-// Per element the steady state is ~20 instructions: 2 staged loads, the 71-bit Hamming count as 2 POPC (3-input
-// majority identity), the 3-channel SAD as one VABSDIFF4.U8.ACC, two table loads, one subtraction, one store.
+// Per element the steady state is: one 16-byte staged load (census words + pixel of the partner), the 71-bit Hamming
+// count as 2 POPC (3-input majority identity), the 3-channel SAD as one VABSDIFF4.U8.ACC, two table loads, one
+// subtraction, one store; the view's sign and the census word count are template parameters, so staged entries and
+// table slots are addressed as pointer + immediate.
 // Disparities whose partner lies outside the image form a contiguous tail d >= nvalid of every pixel and get
 // the constant out-of-range value without touching the tables per element.
 #include <math.h>
@@ -34,47 +36,49 @@
 
 enum { COST_ADCENSUS = 0, COST_HAMMING_F32 = 1, COST_AD_F32 = 2, COST_HAMMING_U16 = 3 };
 
-template <int MODE, typename OutT, bool CHECK>
-__device__ __forceinline__ OutT cost_one(int idx, int d, int nvalid, uint32_t pa, uint64_t ca0, uint32_t ca1,
-                                         const uint32_t* __restrict__ sPix, const uint64_t* __restrict__ sCen,
-                                         const uint32_t* __restrict__ sHi, const float* __restrict__ sT1,
-                                         const float* __restrict__ sTabCen, int lane, int nw, OutT oor) {
+// One staged entry per position of the "other" image: {census word 0 lo, hi, census word 1 (low 32 bits), packed pixel}
+// -> one LDS.128 per element.  eb points at the entry of d = lane of the current 32-chunk; the entries of the
+// following chunks sit at compile-time offsets -SGN*32*q, so the steady state does no index arithmetic at all.
+// t1 / t2 are per-lane byte pointers into the lane-replicated tables (base + lane*4): an entry is 128 bytes.
+template <int MODE, int NW, typename OutT>
+__device__ __forceinline__ OutT cost_one(const uint4 e, uint32_t pa, uint32_t ca0lo, uint32_t ca0hi, uint32_t ca1,
+                                         const char* __restrict__ t1, const char* __restrict__ t2) {
   constexpr bool NEED_CEN = MODE != COST_AD_F32, NEED_AD = MODE == COST_ADCENSUS || MODE == COST_AD_F32;
-  int c = 0, k = 0;
+  int c = 0;
+  uint32_t off2 = 0;
   if (NEED_CEN) {
-    const uint64_t x0 = ca0 ^ sCen[idx];
-    const uint32_t a0 = (uint32_t)x0, a1 = (uint32_t)(x0 >> 32);
-    if (nw == 2) {
-      const uint32_t a2 = ca1 ^ sHi[idx];
+    const uint32_t a0 = ca0lo ^ e.x, a1 = ca0hi ^ e.y;
+    if (NW == 2) {
+      const uint32_t a2 = ca1 ^ e.z;
       // popc(a)+popc(b)+popc(c) = popc(a^b^c) + 2*popc(maj(a,b,c)): 2 POPC for 71 bits
-      c = __popc(a0 ^ a1 ^ a2) + 2 * __popc((a0 & a1) | (a0 & a2) | (a1 & a2));
+      const int p1 = __popc(a0 ^ a1 ^ a2), p2 = __popc((a0 & a1) | (a0 & a2) | (a1 & a2));
+      c = p1 + 2 * p2;
+      off2 = (uint32_t)p1 * 128u + (uint32_t)p2 * 256u;
     } else {
-      c = __popcll(x0);
+      c = __popc(a0) + __popc(a1);
+      off2 = (uint32_t)c * 128u;
     }
     // min(count, codeLength) of gen_cenVM_XOR is the identity: a code has codeLength bits (truncRat = 1)
   }
-  if (NEED_AD) k = (int)__vsadu4(pa, sPix[idx]);   // sum_c |l_c - r_c| (byte 3 is zero in both words)
-  OutT r;
-  if (MODE == COST_ADCENSUS) r = (OutT)(sT1[(k << 5) + lane] - sTabCen[(c << 5) + lane]);   // (2 - e^-ad/l) - e^-c/l
-  else if (MODE == COST_AD_F32) r = (OutT)sT1[(k << 5) + lane];
-  else r = (OutT)c;
-  if (CHECK) r = d < nvalid ? r : oor;
-  return r;
+  if (MODE == COST_ADCENSUS || MODE == COST_AD_F32) {
+    const uint32_t k = __vsadu4(pa, e.w);   // sum_c |l_c - r_c| (byte 3 is zero in both words)
+    const float v1 = *reinterpret_cast<const float*>(t1 + k * 128u);
+    if (MODE == COST_AD_F32) return (OutT)v1;
+    return (OutT)(v1 - *reinterpret_cast<const float*>(t2 + off2));   // (2 - e^-ad/l) - e^-c/l
+  }
+  return (OutT)c;
 }
 
-template <int MODE, typename OutT>
+template <int MODE, int NW, int SGN, typename OutT>
 __global__ void __launch_bounds__(COST_THREADS, 1)
     k_cost(const uint32_t* __restrict__ pixA, const uint32_t* __restrict__ pixO, const uint64_t* __restrict__ cenA,
-           const uint64_t* __restrict__ cenO, int nw, int H, int W, int D, int sgn, int codeLen,
+           const uint64_t* __restrict__ cenO, int H, int W, int D, int codeLen,
            const float* __restrict__ tabAD, const float* __restrict__ tabCen, OutT* __restrict__ vol) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr bool NEED_CEN = MODE != COST_AD_F32, NEED_AD = MODE == COST_ADCENSUS || MODE == COST_AD_F32;
   float* sT1 = reinterpret_cast<float*>(smem_raw);                          // [767][32]: 2 - tabAD (or raw AD)
   float* sTabCen = sT1 + (NEED_AD ? COST_TAB_AD * 32 : 0);                  // [72][32]
-  uint64_t* sCen = reinterpret_cast<uint64_t*>(sTabCen + (MODE == COST_ADCENSUS ? (COST_MAX_CODE + 1) * 32 : 0));
-  const int maxEntries = COST_SEG + D - 1;
-  uint32_t* sPix = reinterpret_cast<uint32_t*>(sCen + maxEntries);
-  uint32_t* sHi = sPix + maxEntries;
+  uint4* sEnt = reinterpret_cast<uint4*>(sTabCen + (MODE == COST_ADCENSUS ? (COST_MAX_CODE + 1) * 32 : 0));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (NEED_AD)
@@ -87,6 +91,8 @@ __global__ void __launch_bounds__(COST_THREADS, 1)
   if (MODE == COST_ADCENSUS) oor = (OutT)((2.0f - tabAD[766]) - tabCen[codeLen]);
   else if (MODE == COST_AD_F32) oor = (OutT)tabAD[766];
   else oor = (OutT)codeLen;
+  const char* t1 = reinterpret_cast<const char*>(sT1 + lane);
+  const char* t2 = reinterpret_cast<const char*>(sTabCen + lane);
 
   const int nSeg = (W + COST_SEG - 1) / COST_SEG;
   const int nItems = H * nSeg;
@@ -94,22 +100,22 @@ __global__ void __launch_bounds__(COST_THREADS, 1)
   for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
     const int v = item / nSeg, ua = (item - v * nSeg) * COST_SEG;
     const int nA = min(COST_SEG, W - ua);
-    const int elo = sgn > 0 ? ua - (D - 1) : ua;
+    const int elo = SGN > 0 ? ua - (D - 1) : ua;
     const int cnt = nA + D - 1;
     __syncthreads();  // previous item's readers are done (also orders the table fill)
     for (int i = tid; i < cnt; i += COST_THREADS) {
       const int e = elo + i;
-      uint32_t px = 0, hi = 0;
-      uint64_t c0 = 0;
+      uint4 ent = make_uint4(0u, 0u, 0u, 0u);
       if (e >= 0 && e < W) {
         const size_t p = (size_t)v * W + e;
-        if (NEED_AD) px = pixO[p] & 0x00FFFFFFu;
+        if (NEED_AD) ent.w = pixO[p] & 0x00FFFFFFu;
         if (NEED_CEN) {
-          c0 = cenO[p * nw];
-          if (nw == 2) hi = (uint32_t)cenO[p * nw + 1];
+          const uint64_t c0 = cenO[p * NW];
+          ent.x = (uint32_t)c0; ent.y = (uint32_t)(c0 >> 32);
+          if (NW == 2) ent.z = (uint32_t)cenO[p * NW + 1];
         }
       }
-      sCen[i] = c0; sPix[i] = px; sHi[i] = hi;
+      sEnt[i] = ent;
     }
     __syncthreads();
     // the anchor's own words are fetched one anchor ahead, so the warp never waits on global memory between anchors
@@ -119,42 +125,44 @@ __global__ void __launch_bounds__(COST_THREADS, 1)
       const size_t p0 = (size_t)v * W + ua + warp;
       if (NEED_AD) pa_n = pixA[p0];
       if (NEED_CEN) {
-        ca0_n = cenA[p0 * nw];
-        if (nw == 2) ca1_n = (uint32_t)cenA[p0 * nw + 1];
+        ca0_n = cenA[p0 * NW];
+        if (NW == 2) ca1_n = (uint32_t)cenA[p0 * NW + 1];
       }
     }
     for (int a = warp; a < nA; a += COST_THREADS / 32) {
       const int u = ua + a;
       const size_t p = (size_t)v * W + u;
       const uint32_t pa = pa_n & 0x00FFFFFFu;
-      const uint64_t ca0 = ca0_n;
-      const uint32_t ca1 = ca1_n;
+      const uint32_t ca0lo = (uint32_t)ca0_n, ca0hi = (uint32_t)(ca0_n >> 32), ca1 = ca1_n;
       if (a + COST_THREADS / 32 < nA) {
         const size_t pn = p + COST_THREADS / 32;
         if (NEED_AD) pa_n = pixA[pn];
         if (NEED_CEN) {
-          ca0_n = cenA[pn * nw];
-          if (nw == 2) ca1_n = (uint32_t)cenA[pn * nw + 1];
+          ca0_n = cenA[pn * NW];
+          if (NW == 2) ca1_n = (uint32_t)cenA[pn * NW + 1];
         }
       }
       OutT* out = vol + p * D + lane;
-      // in-range disparities of this pixel: view 0 (sgn +1): u - d >= 0; view 1: u + d < W
-      const int nvalid = min(D, sgn > 0 ? u + 1 : W - u);
-      const int base = u - elo - sgn * lane;   // staged index of d = lane; d += 32 moves it by -sgn*32
+      // in-range disparities of this pixel: view 0 (SGN +1): u - d >= 0; view 1: u + d < W
+      const int nvalid = min(D, SGN > 0 ? u + 1 : W - u);
+      const uint4* eb = sEnt + (u - elo - SGN * lane);   // entry of d = lane; d += 32 moves it by -SGN*32
       int j = 0;
       // chunks of 32 disparities that are entirely in range: no predicate, 4 at a time
       for (; (j + 4) * 32 <= nvalid; j += 4) {
 #pragma unroll
         for (int q = 0; q < 4; q++)
-          out[(j + q) * 32] = cost_one<MODE, OutT, false>(base - sgn * (j + q) * 32, 0, 0, pa, ca0, ca1, sPix, sCen, sHi,
-                                                          sT1, sTabCen, lane, nw, oor);
+          out[q * 32] = cost_one<MODE, NW, OutT>(eb[-SGN * q * 32], pa, ca0lo, ca0hi, ca1, t1, t2);
+        eb -= SGN * 128;
+        out += 128;
       }
       for (; j < nd; j++) {
         const int d = lane + j * 32;
         if (d >= D) break;
-        if (j * 32 >= nvalid) out[j * 32] = oor;   // chunk entirely out of range: constant
-        else out[j * 32] = cost_one<MODE, OutT, true>(base - sgn * j * 32, d, nvalid, pa, ca0, ca1, sPix, sCen, sHi, sT1,
-                                                      sTabCen, lane, nw, oor);
+        OutT r = oor;                              // chunk (partly) out of range: constant tail
+        if (d < nvalid) r = cost_one<MODE, NW, OutT>(eb[0], pa, ca0lo, ca0hi, ca1, t1, t2);
+        out[0] = r;
+        eb -= SGN * 32;
+        out += 32;
       }
     }
   }
@@ -187,20 +195,31 @@ int smi_exp_tables(sm_ctx* ctx, float trunc, float lamAD, float lamCen, int code
   return SM_OK;
 }
 
+template <int MODE, int NW, int SGN, typename OutT>
+static int launch_cost3(sm_ctx* ctx, const uint32_t* pixA, const uint32_t* pixO, const uint64_t* cenA, const uint64_t* cenO,
+                        int H, int W, int D, int codeLen, const float* tAD, const float* tCen, OutT* vol) {
+  size_t smem = 0;
+  if (MODE == COST_ADCENSUS || MODE == COST_AD_F32) smem += COST_TAB_AD * 32 * sizeof(float);
+  if (MODE == COST_ADCENSUS) smem += (COST_MAX_CODE + 1) * 32 * sizeof(float);
+  smem += (size_t)(COST_SEG + D - 1) * sizeof(uint4);
+  SM_CUDA(cudaFuncSetAttribute(k_cost<MODE, NW, SGN, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int nItems = H * sm_div_up(W, COST_SEG);
+  int grid = min(nItems, ctx->num_sms);
+  SM_LAUNCH(ctx, (k_cost<MODE, NW, SGN, OutT>), grid, COST_THREADS, smem, pixA, pixO, cenA, cenO, H, W, D, codeLen, tAD,
+            tCen, vol);
+  return SM_OK;
+}
+
+// the word count (1: 63-bit census, 2: 71-bit) and the view's sign are compile-time in the kernel
 template <int MODE, typename OutT>
 static int launch_cost(sm_ctx* ctx, const uint32_t* pixA, const uint32_t* pixO, const uint64_t* cenA,
                        const uint64_t* cenO, int nw, int H, int W, int D, int sgn, int codeLen, const float* tAD,
                        const float* tCen, OutT* vol) {
-  size_t smem = 0;
-  if (MODE == COST_ADCENSUS || MODE == COST_AD_F32) smem += COST_TAB_AD * 32 * sizeof(float);
-  if (MODE == COST_ADCENSUS) smem += (COST_MAX_CODE + 1) * 32 * sizeof(float);
-  smem += (size_t)(COST_SEG + D - 1) * (sizeof(uint64_t) + 2 * sizeof(uint32_t));
-  SM_CUDA(cudaFuncSetAttribute(k_cost<MODE, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int nItems = H * sm_div_up(W, COST_SEG);
-  int grid = min(nItems, ctx->num_sms);
-  SM_LAUNCH(ctx, (k_cost<MODE, OutT>), grid, COST_THREADS, smem, pixA, pixO, cenA, cenO, nw, H, W, D, sgn, codeLen,
-            tAD, tCen, vol);
-  return SM_OK;
+  if (nw == 2)
+    return sgn > 0 ? launch_cost3<MODE, 2, +1, OutT>(ctx, pixA, pixO, cenA, cenO, H, W, D, codeLen, tAD, tCen, vol)
+                   : launch_cost3<MODE, 2, -1, OutT>(ctx, pixA, pixO, cenA, cenO, H, W, D, codeLen, tAD, tCen, vol);
+  return sgn > 0 ? launch_cost3<MODE, 1, +1, OutT>(ctx, pixA, pixO, cenA, cenO, H, W, D, codeLen, tAD, tCen, vol)
+                 : launch_cost3<MODE, 1, -1, OutT>(ctx, pixA, pixO, cenA, cenO, H, W, D, codeLen, tAD, tCen, vol);
 }
 
 int smi_cost_adcensus_packed(sm_ctx* ctx, const uint32_t* d_pixL, const uint32_t* d_pixR, const uint64_t* d_cenL,
