@@ -70,7 +70,7 @@ typedef struct sm_params {
   int Do_regionVote;        /* :75 */
   int Do_properIpol;        /* :76 */
   int Do_lastMedianBlur;    /* :80 */
-  float crossScaleLambda;   /* <0: skip; >=0: the caller's 1-level SolveAll scale 1/(1+lambda), main_.cpp:158 */
+  float crossScaleLambda;   /* <0: skip; >=0: the caller's SolveAll step with REG_LAMBDA = this (0.3 in main_.cpp:157) */
   int sgm_grouped;          /* 8 paths only.  0: add the path volumes in the reference's order L0+L1+...+L7
                              * (bit-exact).  1 (default): sweep the row-wise paths {0,4,5} and {1,6,7} together
                              * (one read of C and one read-modify-write of the sum for three paths); every path
@@ -79,6 +79,9 @@ typedef struct sm_params {
   int costcalculation;      /* 0 "ADCensus" (BASELINE configs), 1 "censusGrad" (the selector main_.cpp:15 compiles in) */
   float cg_lamCen, cg_lamG; /* censusGrad: Parameters::lamCen = 13, lamG = 1 (main_.cpp:60-61, stereoMatching.cpp:37-41) */
   float gradTrunc;          /* 500  (censusGrad -> grad(gradVm, 500), stereoMatching.cpp:34) */
+  int pyramidLevels;        /* PY_LEV of main_.cpp:132 (1 there).  > 1 with crossScaleLambda >= 0: cost + aggregation run
+                             * on every level of the pyrDown pyramid (maxDisp/2+1, arm lengths / 2 per level,
+                             * main_.cpp:134-151) and SolveAll blends them into level 0 before SGM */
 } sm_params;
 
 void sm_params_default(sm_params* p, int maxDisp);
@@ -276,6 +279,18 @@ int sm_proper_ipol(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* 
 int sm_median3_i16(sm_ctx* ctx, const int16_t* d_src, int16_t* d_dst, int H, int W);
 /* SolveAll with one pyramid level (stereoMatching.cpp:2142-2208, main_.cpp:158). */
 int sm_cross_scale_1level(sm_ctx* ctx, float* d_vol, size_t n, float lambda);
+/* ---- the caller's cross-scale step, any number of levels ---- */
+#define SM_MAX_PYRAMID 6
+/* cv::pyrDown on an 8-bit image, cn = 1 | 3 (main_.cpp:145-148): [1 4 6 4 1]/16 separable, REFLECT_101,
+ * d_dst is ((H+1)/2) x ((W+1)/2).  Bit-exact. */
+int sm_pyr_down_u8(sm_ctx* ctx, const uint8_t* d_src, int H, int W, int cn, uint8_t* d_dst);
+/* invWgt[0..n) = row 0 of regMat.inv() (stereoMatching.cpp:2147-2170), exactly as cv::invert computes it on
+ * CV_32F.  Host-only helper (no device work). */
+int sm_cross_scale_weights(int n, float lambda, float* invWgt);
+/* SolveAll (stereoMatching.cpp:2142-2208): d_vols[s] is the level-s volume [Hs[s]][Ws[s]][Ds[s]]; d_vols[0] is
+ * replaced by sum_s invWgt[s] * vol_s[y>>s][x>>s][d_s], d_{s+1} = (d_s+1)/2.  Bit-exact. */
+int sm_cross_scale(sm_ctx* ctx, float* const* d_vols, const int* Hs, const int* Ws, const int* Ds, int levels,
+                   float lambda);
 
 /* ---- whole frame ------------------------------------------------------------ */
 /* A frame pipeline owns every device buffer a W x H x D frame needs (three

@@ -31,6 +31,7 @@ class SmParams(C.Structure):
         ("Do_regionVote", C.c_int), ("Do_properIpol", C.c_int), ("Do_lastMedianBlur", C.c_int),
         ("crossScaleLambda", C.c_float), ("sgm_grouped", C.c_int),
         ("costcalculation", C.c_int), ("cg_lamCen", C.c_float), ("cg_lamG", C.c_float), ("gradTrunc", C.c_float),
+        ("pyramidLevels", C.c_int),
     ]
 
 
@@ -62,6 +63,9 @@ SIGNATURES = {
     "sm_cost_ad": ([_P, _P, _P, _I, _I, _I, _I, _F, _P], _I),
     "sm_cost_adcensus": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P], _I),
     "sm_combine_exp": ([_P, _P, _P, _Z, _F, _F, _P], _I),
+    "sm_pyr_down_u8": ([_P, _P, _I, _I, _I, _P], _I),
+    "sm_cross_scale_weights": ([_I, _F, _P], _I),
+    "sm_cross_scale": ([_P, _P, _P, _P, _P, _I, _F], _I),
     "sm_grad_xy": ([_P, _P, _I, _I, _P, _P], _I),
     "sm_cost_grad": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P], _I),
     "sm_cost_censusgrad": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P], _I),
@@ -133,6 +137,12 @@ def default_params(max_disp, **over):
             raise AttributeError(k)
         setattr(p, k, v)
     return p
+
+
+def cross_scale_weights(levels, lam=0.3):
+    w = (C.c_float * levels)()
+    check(lib().sm_cross_scale_weights(levels, lam, w))
+    return list(w)
 
 
 def _ptr(t):
@@ -229,6 +239,23 @@ class Ctx:
         out = self.torch.empty_like(a)
         check(self.L.sm_combine_exp(self.h, _ptr(a), _ptr(b), a.numel(), l0, l1, _ptr(out)))
         return out
+
+    def pyr_down(self, img):
+        H, W = img.shape[:2]
+        cn = 1 if img.dim() == 2 else img.shape[2]
+        out = self.empty(((H + 1) // 2, (W + 1) // 2) + ((cn,) if img.dim() == 3 else ()), self.torch.uint8)
+        check(self.L.sm_pyr_down_u8(self.h, _ptr(img), H, W, cn, _ptr(out)))
+        return out
+
+    def cross_scale(self, vols, lam=0.3):
+        """SolveAll on a list of per-level device volumes; vols[0] is updated in place and returned."""
+        n = len(vols)
+        ptrs = (C.c_void_p * n)(*[_ptr(v) for v in vols])
+        Hs = (C.c_int * n)(*[v.shape[0] for v in vols])
+        Ws = (C.c_int * n)(*[v.shape[1] for v in vols])
+        Ds = (C.c_int * n)(*[v.shape[2] for v in vols])
+        check(self.L.sm_cross_scale(self.h, ptrs, Hs, Ws, Ds, n, lam))
+        return vols[0]
 
     def grad_xy(self, gray):
         H, W = gray.shape

@@ -54,6 +54,7 @@ extern "C" void sm_params_default(sm_params* p, int maxDisp) {
   p->cg_lamCen = 13.f;
   p->cg_lamG = 1.f;
   p->gradTrunc = 500.f;
+  p->pyramidLevels = 1;
 }
 
 extern "C" int sm_ctx_create(sm_ctx** out, int device, void* stream) {

@@ -27,6 +27,8 @@ struct sm_pipeline {
   int16_t *disp[2] = {nullptr, nullptr}, *dtmp = nullptr;
   uint8_t* h_in = nullptr;   // pinned staging: bgrL | bgrR | grayL | grayR
   int16_t* h_out = nullptr;  // pinned staging: dispL | dispR
+  sm_pipeline* child = nullptr;   // next pyramid level (cost + aggregation only), pyramidLevels > 1
+  bool is_child = false;
   bool have_gray = false, have_arms = false;
   bool stage_used = false, stage_drained = true;
   bool timing = false;
@@ -41,6 +43,7 @@ static int pl_alloc(sm_ctx* ctx, void** p, size_t bytes) { return sm_dev_alloc(c
 
 extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
   if (!pl) return SM_OK;
+  if (pl->child) sm_pipeline_destroy(pl->child);
   sm_ctx* c = pl->ctx;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
@@ -70,6 +73,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   SM_CHECK_ARG(p->aggregation >= 0 && p->aggregation <= 2);
   SM_CHECK_ARG(p->costcalculation == 0 || p->costcalculation == 1);
   SM_CHECK_ARG(p->costcalculation == 0 || (H >= 2 && W >= 2 && p->cg_lamCen > 0.f && p->cg_lamG > 0.f));
+  SM_CHECK_ARG(p->pyramidLevels >= 1 && p->pyramidLevels <= SM_MAX_PYRAMID);
   SM_CHECK_ARG(p->cbca_crossL_out >= 0 && p->cbca_crossL_out <= 255);
   SM_CUDA(cudaSetDevice(ctx->device));
   sm_pipeline* pl = new sm_pipeline();
@@ -95,6 +99,17 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   if (rc == SM_OK && p->aggregation == 2) rc = pl_alloc(ctx, (void**)&pl->nlwork, npix * (size_t)(pl->D + 1) * sizeof(double));
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_in, npix * 8) != cudaSuccess) rc = SM_ERR_NOMEM;
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_out, npix * 4) != cudaSuccess) rc = SM_ERR_NOMEM;
+  if (rc == SM_OK && p->pyramidLevels > 1 && p->crossScaleLambda >= 0.f) {
+    // next level of the caller's pyramid (main_.cpp:134-151): half-size images, maxDisp/2 + 1, disSc * 2 (arm lengths
+    // L/scale, L_out/scale, stereoMatching.cpp:5368-5371); it runs costCalculate() only
+    sm_params cp = *p;
+    cp.numDisparities = (p->numDisparities - 1) / 2 + 1 + 1;
+    cp.cbca_crossL = p->cbca_crossL / 2;
+    cp.cbca_crossL_out = p->cbca_crossL_out / 2;
+    cp.pyramidLevels = p->pyramidLevels - 1;
+    rc = sm_pipeline_create(ctx, (H + 1) / 2, (W + 1) / 2, &cp, &pl->child);
+    if (rc == SM_OK) pl->child->is_child = true;
+  }
   if (rc != SM_OK) { sm_pipeline_destroy(pl); return rc; }
   *out = pl;
   return SM_OK;
@@ -147,14 +162,25 @@ extern "C" int sm_pipeline_upload(sm_pipeline* pl, const uint8_t* h_bgrL, const 
     if (pl->timing) SM_CUDA(cudaEventRecord(pl->ev[k], c->stream));        \
   } while (0)
 
-extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
-  SM_CHECK_ARG(pl);
+static int pl_ensure_arms(sm_pipeline* pl) {
+  if (pl->have_arms) return SM_OK;
+  sm_ctx* c = pl->ctx;
+  const sm_params& P = pl->p;
+  for (int i = 0; i < 2; i++) {
+    SM_TRY(smi_arms_packed(c, pl->pix[i], pl->H, pl->W, P.cbca_crossL, P.cbca_crossL_out, P.cbca_cTresh, P.cbca_cTresh_out,
+                           P.cbca_minArmL, pl->arms[i]));
+    SM_TRY(smi_pack_arms(c, pl->arms[i], pl->H, pl->W, smi_arm_pad(pl->D), pl->armpk[i]));
+  }
+  pl->have_arms = true;
+  return SM_OK;
+}
+
+// costCalculate() of one pyramid level (stereoMatching.cpp:945-1044): census, cost volumes, arms, aggregation.
+static int pl_cost_calculate(sm_pipeline* pl) {
   sm_ctx* c = pl->ctx;
   const sm_params& P = pl->p;
   const int H = pl->H, W = pl->W, D = pl->D;
   const long long npix = (long long)H * W;
-  const size_t nvol = (size_t)npix * D;
-  SM_CUDA(cudaSetDevice(c->device));
   PL_MARK(0);
   // ---- costCalculate: ADCensusCal (stereoMatching.cpp:894-915)
   for (int i = 0; i < 2; i++) {
@@ -166,16 +192,7 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   const int imgNum = P.Do_LRConsis ? 2 : 1;  // stereoMatching.cpp:898
   const int views = (P.Do_refine && P.Do_LRConsis) ? 2 : 1;  // stereoMatching.cpp:1054, 5592
   pl->have_arms = false;
-  auto ensure_arms = [&]() -> int {
-    if (pl->have_arms) return SM_OK;
-    for (int i = 0; i < 2; i++) {
-      SM_TRY(smi_arms_packed(c, pl->pix[i], H, W, P.cbca_crossL, P.cbca_crossL_out, P.cbca_cTresh, P.cbca_cTresh_out,
-                             P.cbca_minArmL, pl->arms[i]));
-      SM_TRY(smi_pack_arms(c, pl->arms[i], H, W, smi_arm_pad(D), pl->armpk[i]));
-    }
-    pl->have_arms = true;
-    return SM_OK;
-  };
+  auto ensure_arms = [&]() -> int { return pl_ensure_arms(pl); };
   if (P.costcalculation == 0) {
     for (int i = 0; i < imgNum; i++)
       SM_TRY(smi_cost_adcensus_packed(c, pl->pix[0], pl->pix[1], pl->cen[0], pl->cen[1], H, W, D, P.censusFunc,
@@ -203,8 +220,42 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   } else {
     PL_MARK(3);
   }
-  if (P.crossScaleLambda >= 0.f)
-    for (int i = 0; i < (P.Do_refine ? 2 : 1); i++) SM_TRY(sm_cross_scale_1level(c, pl->vol[i], nvol, P.crossScaleLambda));
+  return SM_OK;
+}
+
+extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
+  SM_CHECK_ARG(pl && !pl->is_child);
+  sm_ctx* c = pl->ctx;
+  const sm_params& P = pl->p;
+  const int H = pl->H, W = pl->W, D = pl->D;
+  const long long npix = (long long)H * W;
+  SM_CUDA(cudaSetDevice(c->device));
+  const int views = (P.Do_refine && P.Do_LRConsis) ? 2 : 1;  // stereoMatching.cpp:1054, 5592
+  auto ensure_arms = [&]() -> int { return pl_ensure_arms(pl); };
+  SM_TRY(pl_cost_calculate(pl));
+  if (P.crossScaleLambda >= 0.f) {
+    // the caller's pyramid loop + SolveAll (main_.cpp:131-158, stereoMatching.cpp:2142-2208)
+    float* vols[2][SM_MAX_PYRAMID];
+    int Hs[SM_MAX_PYRAMID], Ws[SM_MAX_PYRAMID], Ds[SM_MAX_PYRAMID], levels = 0;
+    for (sm_pipeline* q = pl; q; q = q->child) {
+      if (q != pl) {
+        // pyrDown of the level above: colour and gray images separately (main_.cpp:145-148)
+        sm_pipeline* up = nullptr;
+        for (sm_pipeline* r = pl; r != q; r = r->child) up = r;
+        for (int i = 0; i < 2; i++) {
+          SM_TRY(sm_pyr_down_u8(c, up->bgr[i], up->H, up->W, 3, q->bgr[i]));
+          SM_TRY(sm_pyr_down_u8(c, up->gray[i], up->H, up->W, 1, q->gray[i]));
+        }
+        q->have_gray = true;
+        SM_TRY(pl_cost_calculate(q));
+      }
+      Hs[levels] = q->H; Ws[levels] = q->W; Ds[levels] = q->D;
+      vols[0][levels] = q->vol[0]; vols[1][levels] = q->vol[1];
+      levels++;
+    }
+    for (int i = 0; i < (P.Do_refine ? 2 : 1); i++)   // img_n = Do_refine ? 2 : 1 (stereoMatching.cpp:2179)
+      SM_TRY(sm_cross_scale(c, vols[i], Hs, Ws, Ds, levels, P.crossScaleLambda));
+  }
   PL_MARK(4);
   // ---- dispOptimize: sgm (stereoMatching.cpp:1051-1089) then WTA (:1108-1128)
   if (P.sgm_paths > 0) {

@@ -302,7 +302,7 @@ __global__ void k_scale(float* __restrict__ vol, size_t n, float inv) {
 
 extern "C" int sm_cross_scale_1level(sm_ctx* ctx, float* d_vol, size_t n, float lambda) {
   SM_CHECK_ARG(ctx && d_vol);
-  const float inv = 1.0f / (1.0f + lambda);
+  const float inv = (float)(1. / (double)(1.0f + lambda));   // cv::invert of the 1x1 float matrix (1 + lambda)
   int grid = (int)min((size_t)ctx->num_sms * 16, (n + 255) / 256);
   SM_LAUNCH(ctx, k_scale, grid, 256, 0, d_vol, n, inv);
   return SM_OK;

@@ -4,11 +4,14 @@
 // raising cv::Exception.  When real OpenCV is available, define SM_USE_OPENCV before including stereoMatching.h
 // and this file is skipped.
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 typedef unsigned char uchar;
@@ -124,6 +127,69 @@ class Mat {
     return (T*)(data + (size_t)i0 * step[0] + (size_t)i1 * step[1] + (size_t)i2 * step[2]);
   }
   template <typename T> T& at(int i0, int i1) { return *ptr<T>(i0, i1); }
+  template <typename T> const T& at(int i0, int i1) const { return *ptr<T>(i0, i1); }
+  // cv::Mat::inv() (DECOMP_LU) for a square CV_32F matrix, the way cv::invert evaluates it: n = 1, 3 closed forms in
+  // double rounded once; n = 2 determinant in double, float products with (float)(1/det) (the SIMD128 branch);
+  // n > 3 Gaussian elimination with partial pivoting in float.  Reproduces cv2.invert bit for bit on the matrices
+  // SolveAll builds (tests/golden/opencv_semantics.npz); a singular matrix yields zeros, as in OpenCV.
+  Mat inv() const {
+    CV_Assert(dims == 2 && rows == cols && type() == CV_32FC1);
+    const int n = rows;
+    Mat out = zeros(n, n, CV_32FC1);
+    auto S = [&](int r, int c) { return at<float>(r, c); };
+    if (n == 1) {
+      const double d = S(0, 0);
+      if (d != 0.) out.at<float>(0, 0) = (float)(1. / d);
+    } else if (n == 2) {
+      double d = (double)S(0, 0) * S(1, 1) - (double)S(0, 1) * S(1, 0);
+      if (d != 0.) {
+        const float f = (float)(1. / d);
+        out.at<float>(1, 1) = S(0, 0) * f; out.at<float>(0, 0) = S(1, 1) * f;
+        out.at<float>(0, 1) = -(S(0, 1) * f); out.at<float>(1, 0) = -(S(1, 0) * f);
+      }
+    } else if (n == 3) {
+      auto D = [&](int r, int c) { return (double)at<float>(r, c); };
+      double d = D(0, 0) * (D(1, 1) * D(2, 2) - D(1, 2) * D(2, 1)) - D(0, 1) * (D(1, 0) * D(2, 2) - D(1, 2) * D(2, 0)) +
+                 D(0, 2) * (D(1, 0) * D(2, 1) - D(1, 1) * D(2, 0));
+      if (d != 0.) {
+        d = 1. / d;
+        out.at<float>(0, 0) = (float)((D(1, 1) * D(2, 2) - D(1, 2) * D(2, 1)) * d);
+        out.at<float>(0, 1) = (float)((D(0, 2) * D(2, 1) - D(0, 1) * D(2, 2)) * d);
+        out.at<float>(0, 2) = (float)((D(0, 1) * D(1, 2) - D(0, 2) * D(1, 1)) * d);
+        out.at<float>(1, 0) = (float)((D(1, 2) * D(2, 0) - D(1, 0) * D(2, 2)) * d);
+        out.at<float>(1, 1) = (float)((D(0, 0) * D(2, 2) - D(0, 2) * D(2, 0)) * d);
+        out.at<float>(1, 2) = (float)((D(0, 2) * D(1, 0) - D(0, 0) * D(1, 2)) * d);
+        out.at<float>(2, 0) = (float)((D(1, 0) * D(2, 1) - D(1, 1) * D(2, 0)) * d);
+        out.at<float>(2, 1) = (float)((D(0, 1) * D(2, 0) - D(0, 0) * D(2, 1)) * d);
+        out.at<float>(2, 2) = (float)((D(0, 0) * D(1, 1) - D(0, 1) * D(1, 0)) * d);
+      }
+    } else {
+      Mat A = clone();
+      for (int i = 0; i < n; i++) out.at<float>(i, i) = 1.f;
+      volatile float t;   // every product and sum stays a rounded float
+      for (int i = 0; i < n; i++) {
+        int k = i;
+        for (int j = i + 1; j < n; j++)
+          if (std::abs(A.at<float>(j, i)) > std::abs(A.at<float>(k, i))) k = j;
+        if (std::abs(A.at<float>(k, i)) < 1.1920929e-06f) return zeros(n, n, CV_32FC1);   // FLT_EPSILON * 10
+        if (k != i)
+          for (int c = 0; c < n; c++) { std::swap(A.at<float>(i, c), A.at<float>(k, c)); std::swap(out.at<float>(i, c), out.at<float>(k, c)); }
+        const float d = -1 / A.at<float>(i, i);
+        for (int j = i + 1; j < n; j++) {
+          const float alpha = A.at<float>(j, i) * d;
+          for (int c = i + 1; c < n; c++) { t = alpha * A.at<float>(i, c); A.at<float>(j, c) += t; }
+          for (int c = 0; c < n; c++) { t = alpha * out.at<float>(i, c); out.at<float>(j, c) += t; }
+        }
+      }
+      for (int i = n - 1; i >= 0; i--)
+        for (int j = 0; j < n; j++) {
+          float sacc = out.at<float>(i, j);
+          for (int c = i + 1; c < n; c++) { t = A.at<float>(i, c) * out.at<float>(c, j); sacc -= t; }
+          out.at<float>(i, j) = sacc / A.at<float>(i, i);
+        }
+    }
+    return out;
+  }
 
   Mat clone() const { Mat m; copyTo(m); return m; }
   void copyTo(Mat& dst) const {

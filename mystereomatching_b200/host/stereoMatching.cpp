@@ -489,6 +489,44 @@ void StereoMatching::NL() {
   for (size_t i = 0; i < (size_t)h_ * w_; i++) guideDisp.ptr<float>()[i] = (float)tmp.ptr<short>()[i];
 }
 
+void SolveAll(StereoMatching**& smPyr, const int PY_LVL, const float REG_LAMBDA) {
+  CV_Assert(smPyr && PY_LVL >= 1 && PY_LVL <= SM_MAX_PYRAMID);
+  StereoMatching* s0 = smPyr[0];
+  int Hs[SM_MAX_PYRAMID], Ws[SM_MAX_PYRAMID], Ds[SM_MAX_PYRAMID];
+  for (int s = 0; s < PY_LVL; s++) {
+    CV_Assert(smPyr[s] != nullptr);
+    Hs[s] = smPyr[s]->h_; Ws[s] = smPyr[s]->w_; Ds[s] = smPyr[s]->d_;
+    for (int i = 0; i < 2; i++) smPyr[s]->uploadVm(i);
+    smPyr[s]->check(sm_ctx_sync(smPyr[s]->ctx_), "sm_ctx_sync");   // each level has its own stream: finish before the gather
+  }
+  const int img_n = StereoMatching::Do_refine ? 2 : 1;   // stereoMatching.cpp:2179
+  for (int n = 0; n < img_n; n++) {
+    float* vols[SM_MAX_PYRAMID];
+    for (int s = 0; s < PY_LVL; s++) vols[s] = smPyr[s]->d_vol_[n];
+    s0->check(sm_cross_scale(s0->ctx_, vols, Hs, Ws, Ds, PY_LVL, REG_LAMBDA), "sm_cross_scale");
+    s0->vm_dev_fresh_[n] = true;
+  }
+}
+
+void pyrDown_u8(const cv::Mat& src, cv::Mat& dst) {
+  CV_Assert(src.dims == 2 && src.depth() == CV_8U && (src.channels() == 1 || src.channels() == 3) && !src.empty());
+  sm_ctx* c = nullptr;
+  if (sm_ctx_create(&c, 0, nullptr) != SM_OK) throw cv::Exception(std::string("sm_ctx_create: ") + sm_last_error());
+  const int H = src.rows, W = src.cols, cn = src.channels();
+  cv::Mat out((H + 1) / 2, (W + 1) / 2, src.type());
+  void *ds = nullptr, *dd = nullptr;
+  int rc = sm_dev_alloc(c, &ds, (size_t)H * W * cn);
+  if (rc == SM_OK) rc = sm_dev_alloc(c, &dd, out.total() * cn);
+  if (rc == SM_OK) rc = sm_memcpy_h2d(c, ds, src.data, (size_t)H * W * cn);
+  if (rc == SM_OK) rc = sm_pyr_down_u8(c, (const uint8_t*)ds, H, W, cn, (uint8_t*)dd);
+  if (rc == SM_OK) rc = sm_memcpy_d2h(c, out.data, dd, out.total() * cn);
+  if (rc == SM_OK) rc = sm_ctx_sync(c);
+  const std::string err = rc == SM_OK ? "" : sm_last_error();
+  sm_dev_free(c, ds); sm_dev_free(c, dd); sm_ctx_destroy(c);
+  if (rc != SM_OK) throw cv::Exception("pyrDown_u8: " + err);
+  dst = out;
+}
+
 void StereoMatching::SolveAll(int PY_LVL, float REG_LAMBDA) {
   CV_Assert(PY_LVL == 1);   // main_.cpp:132: one pyramid level
   for (int i = 0; i < 2; i++) {

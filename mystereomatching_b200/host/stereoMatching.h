@@ -123,7 +123,8 @@ class StereoMatching {
   template <typename T>
   void calHorVerDis(Mat& I, Mat& cross, int L, int L_out, int C_D, int C_D_out, int minL);  // :2958-3050
   void genTrueHorVerArms(vector<Mat>& HVL, vector<Mat>& HVL_INTERSECTION);              // stereoMatching.cpp:2794-2845
-  void SolveAll(int PY_LVL, float REG_LAMBDA);                                          // 1 level only (main_.cpp:158)
+  void SolveAll(int PY_LVL, float REG_LAMBDA);                                          // member form, 1 level (main_.cpp:158)
+  friend void SolveAll(StereoMatching**& smPyr, const int PY_LVL, const float REG_LAMBDA);
 
   // ---- optimisation / selection
   void sgm(cv::Mat& vm, bool leftFirst = true);                                         // stereoMatching.cpp:6204-6224
@@ -184,3 +185,10 @@ class StereoMatching {
   bool arms_dev_ = false, arms_host_stale_ = false;
   vector<void*> owned_;
 };
+
+// The caller's cross-scale step, as the reference declares it (stereoMatching.h:2740, stereoMatching.cpp:2142-2208):
+// smPyr[s] = the StereoMatching of pyramid level s after costCalculate(); level 0's vm[] is replaced by the blend.
+void SolveAll(StereoMatching**& smPyr, const int PY_LVL, const float REG_LAMBDA);
+// cv::pyrDown for the 8-bit images of the pyramid loop (main_.cpp:145-148), on the GPU (addition: OpenCV's own
+// pyrDown serves equally when the build has it).
+void pyrDown_u8(const cv::Mat& src, cv::Mat& dst);

@@ -72,6 +72,9 @@ CPP_FUNCS = [
     (r"^void StereoMatching::calGrad_y\(", "calGrad_y"),
     (r"^void StereoMatching::calgradvm\(", "calgradvm"),
     (r"^void StereoMatching::calgradvm_1d\(", "calgradvm_1d"),
+    # the caller's cross-scale step: free functions of stereoMatching.cpp
+    (r"^void PrintMat\(const Mat& mat\)", "PrintMat"),
+    (r"^void SolveAll\(StereoMatching\*\*& smPyr", "SolveAll"),
 ]
 # member functions defined inside the class body of stereoMatching.h
 H_FUNCS = [

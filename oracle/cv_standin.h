@@ -44,6 +44,25 @@ inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int le
   dst = out;
 }
 inline bool imwrite(const std::string&, const Mat&) { return true; }  // debug dumps of the reference: dropped
+// cv::pyrDown on 8-bit images (main_.cpp:145-148): [1 4 6 4 1]/16 separable, BORDER_REFLECT_101, (sum + 128) >> 8,
+// dst = ((cols+1)/2, (rows+1)/2); pinned against cv2.pyrDown (tests/golden/opencv_semantics.npz)
+inline void pyrDown(const Mat& src, Mat& dst) {
+  if (src.dims != 2 || src.depth() != CV_8U) { fprintf(stderr, "cv_standin: unsupported pyrDown\n"); abort(); }
+  static const int k[5] = {1, 4, 6, 4, 1};
+  const int cn = src.channels(), Ho = (src.rows + 1) / 2, Wo = (src.cols + 1) / 2;
+  Mat out(Ho, Wo, src.type());
+  for (int y = 0; y < Ho; y++)
+    for (int x = 0; x < Wo; x++)
+      for (int c = 0; c < cn; c++) {
+        int s = 0;
+        for (int i = 0; i < 5; i++) {
+          const uchar* row = src.data + (size_t)reflect101_index(2 * y + i - 2, src.rows) * src.step[0];
+          for (int j = 0; j < 5; j++) s += k[i] * k[j] * row[reflect101_index(2 * x + j - 2, src.cols) * cn + c];
+        }
+        out.data[(size_t)y * out.step[0] + x * cn + c] = (uchar)((s + 128) >> 8);
+      }
+  dst = out;
+}
 namespace ximgproc {
 inline void guidedFilter(const Mat&, const Mat&, Mat&, int, double) {
   fprintf(stderr, "cv_standin: ximgproc::guidedFilter is not available (doGF_bef_calArm must stay false)\n");
@@ -54,3 +73,7 @@ inline void guidedFilter(const Mat&, const Mat&, Mat&, int, double) {
 using namespace std;
 using namespace cv;
 #define popcnt64 __builtin_popcountll   // stereoMatching.cpp:9 (the non-MSVC branch)
+// SolveAll / PrintMat report on stdout with printf (stereoMatching.cpp:2144-2145, 2127-2136); stdout carries
+// bench.py's one JSON line, so that chatter is dropped
+inline int smref_printf_sink(const char*, ...) { return 0; }
+#define printf smref_printf_sink

@@ -28,16 +28,17 @@ class OrcParams(C.Structure):
                                        "tau_out", "minL", "corDifThres", "reduCoeffi1")] + \
                [(n, C.c_float) for n in ("adTrunc", "lamAD", "lamCen", "LRmaxDiff", "voteRatio")] + \
                [(n, C.c_int) for n in ("voteS", "voteNums", "DISP_OCC", "do_refine", "aggregation", "costcalc")] + \
-               [(n, C.c_float) for n in ("cgLamCen", "cgLamG", "gradTrunc")]
+               [(n, C.c_float) for n in ("cgLamCen", "cgLamG", "gradTrunc")] + \
+               [("pyrLevels", C.c_int), ("crossLambda", C.c_float)]
 
 
-def default_params(D, paths=4, census_func=3, do_refine=1, aggregation=1, costcalc=0):
+def default_params(D, paths=4, census_func=3, do_refine=1, aggregation=1, costcalc=0, pyr_levels=1, cross_lambda=-1.0):
     """Reference defaults: stereoMatching.h:204-350, stereoMatching.cpp:905, 5270."""
     return OrcParams(D=D, censusFunc=census_func, paths=paths, iters=2, L=17, L_out=34, tau=20,
                      tau_out=6, minL=1, corDifThres=15, reduCoeffi1=4, adTrunc=1000.0, lamAD=10.0,
                      lamCen=30.0, LRmaxDiff=0.0, voteRatio=0.4, voteS=20, voteNums=2, DISP_OCC=-32,
                      do_refine=do_refine, aggregation=aggregation, costcalc=costcalc, cgLamCen=13.0, cgLamG=1.0,
-                     gradTrunc=500.0)
+                     gradTrunc=500.0, pyrLevels=pyr_levels, crossLambda=cross_lambda)
 
 
 def build(force=False):
@@ -79,6 +80,9 @@ def lib():
         "orc_proper_ipol": ([i16p, u8p, I, I, I], None),
         "orc_median3_i16": ([i16p, I, I, i16p], None),
         "orc_solve_all_1level": ([f32p, C.c_long, F], None),
+        "orc_pyr_down_u8": ([u8p, I, I, I, u8p], None),
+        "orc_cross_scale_weights": ([I, F, f32p], None),
+        "orc_solve_all": ([C.POINTER(C.c_void_p), i32p, i32p, i32p, I, F], None),
         "orc_pipeline": ([u8p, u8p, u8p, u8p, I, I, C.POINTER(OrcParams), i16p, i16p, P, P], None),
         "orc_ctmf": ([u8p, u8p, I, I, I, I, I, I], None),
         "orc_mst": ([u8p, I, I, I, i32p, u8p, i32p, i32p, i32p, i32p, P], None),
@@ -186,6 +190,34 @@ def censusgrad_vol(bgrL, bgrR, grayL, grayR, D, view=0, func=3, lamCen=13.0, lam
     ham = hamming_vol(cl, cr, D, func, view)
     a = arms(bgrL if view == 0 else bgrR)
     return combine_exp(ham, grad_vol(grayL, grayR, a, D, view, trunc), lamCen, lamG)
+
+
+def pyr_down(img):
+    """cv::pyrDown on an 8-bit image (1 or 3 channels)."""
+    H, W = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty(((H + 1) // 2, (W + 1) // 2) + ((cn,) if img.ndim == 3 else ()), np.uint8)
+    lib().orc_pyr_down_u8(np.ascontiguousarray(img), H, W, cn, out)
+    return out
+
+
+def cross_scale_weights(levels, lam=0.3):
+    """Row 0 of regMat.inv() in SolveAll (stereoMatching.cpp:2147-2170)."""
+    w = np.empty(levels, np.float32)
+    lib().orc_cross_scale_weights(levels, lam, w)
+    return w
+
+
+def solve_all(vols, lam=0.3):
+    """SolveAll (stereoMatching.cpp:2142-2208) on a list of per-level volumes; returns the new level-0 volume."""
+    vols = [np.ascontiguousarray(v, np.float32) for v in vols]
+    out = vols[0].copy()
+    ptrs = (C.c_void_p * len(vols))(out.ctypes.data, *[v.ctypes.data for v in vols[1:]])
+    Hs = np.array([v.shape[0] for v in vols], np.int32)
+    Ws = np.array([v.shape[1] for v in vols], np.int32)
+    Ds = np.array([v.shape[2] for v in vols], np.int32)
+    lib().orc_solve_all(ptrs, Hs, Ws, Ds, len(vols), lam)
+    return out
 
 
 def arms(img, L=17, L_out=34, tau=20, tau_out=6, minL=1):
@@ -438,6 +470,7 @@ def smref_lib():
         "smref_region_vote": ([P, i16p, F, I], None), "smref_proper_ipol": ([P, i16p], None),
         "smref_median3_i16": ([i16p, I, I, i16p], None),
         "smref_pipeline": ([P, I, I, P, P, P, P], None), "smref_pipeline2": ([P, I, I, I, P, P, P, P], None),
+        "smref_pipeline_pyr": ([P, I, I, I, I, F, P, P, P], None),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -590,6 +623,13 @@ class SmRef:
         a = np.ascontiguousarray(dp, np.int16).copy()
         self.L.smref_proper_ipol(self.h, a)
         return a
+
+    def pipeline_pyr(self, levels, lam=0.3, paths=8, iters=2, costcalc=0):
+        """main_.cpp:131-166 with PY_LEV = levels: returns (refined left map, vm[0], vm[1] right after SolveAll)."""
+        rf = np.empty((self.H, self.W), np.int16)
+        v0, v1 = self._vol(), self._vol()
+        self.L.smref_pipeline_pyr(self.h, costcalc, paths, iters, levels, lam, rf.ctypes.data, v0.ctypes.data, v1.ctypes.data)
+        return rf, v0, v1
 
     def pipeline(self, paths=4, iters=2, want_vol=False, costcalc=0):
         wl = np.empty((self.H, self.W), np.int16)

@@ -641,9 +641,104 @@ void orc_median3_i16(const i16* src, int H, int W, i16* dst) {
 // (stereoMatching.cpp:2142-2208; main_.cpp:158): regInv = 1/(1+lambda) as a
 // float, vm = 0 + invWgt*vm.
 void orc_solve_all_1level(float* vol, long n, float lambda) {
-  float inv = 1.0f / (1.0f + lambda);  // 1x1 Mat::inv of (1+lambda)
+  float inv = (float)(1. / (double)(1.0f + lambda));  // 1x1 Mat::inv of (1+lambda): cv::invert rounds the double reciprocal
   ORC_PAR_FOR
   for (long i = 0; i < n; i++) { float sum = 0; sum += inv * vol[i]; vol[i] = sum; }
+}
+
+// ---------------------------------------------------------------------------
+// Cross-scale step of the caller: the pyramid loop of main_.cpp:131-158 and
+// SolveAll (stereoMatching.cpp:2142-2208).
+//   cv::pyrDown on 8-bit images: separable [1 4 6 4 1]/16, BORDER_REFLECT_101, dst = ((W+1)/2, (H+1)/2),
+//     (sum + 128) >> 8  [probe: equal to cv2.pyrDown for odd/even/1-wide shapes, tests/golden/opencv_semantics.npz].
+//   regMat (float): tridiagonal {1+l, -l; -l, 1+2l, -l; ...; -l, 1+l}; invWgt = row 0 of regMat.inv().
+//     cv::invert(DECOMP_LU) on CV_32F: n = 1, 3 closed forms evaluated in double and rounded once, n = 2 determinant
+//     in double then float products with (float)(1/det) (the SIMD128 branch); n > 3 Gaussian
+//     elimination with partial pivoting in float (hal::LU32f)  [probe: both reproduce cv2.invert bit for bit].
+//   SolveAll: vm0[y][x][d] = sum_s invWgt[s] * vm_s[y>>s][x>>s][d_s], d_0 = d, d_{s+1} = (d_s + 1) / 2, float
+//     accumulation in level order starting from 0.
+// ---------------------------------------------------------------------------
+void orc_pyr_down_u8(const u8* src, int H, int W, int cn, u8* dst) {
+  static const int k[5] = {1, 4, 6, 4, 1};
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  for (int y = 0; y < Ho; y++)
+    for (int x = 0; x < Wo; x++)
+      for (int c = 0; c < cn; c++) {
+        int s = 0;
+        for (int i = 0; i < 5; i++) {
+          const int yy = reflect101(2 * y + i - 2, H);
+          for (int j = 0; j < 5; j++) s += k[i] * k[j] * src[((long)yy * W + reflect101(2 * x + j - 2, W)) * cn + c];
+        }
+        dst[((long)y * Wo + x) * cn + c] = (u8)((s + 128) >> 8);
+      }
+}
+
+void orc_cross_scale_weights(int n, float lambda, float* invWgt) {
+  std::vector<float> M((size_t)n * n, 0.f);
+  for (int s = 0; s < n; s++) {
+    if (s == 0) { M[0] = 1 + lambda; if (n > 1) M[1] = -lambda; }
+    else if (s == n - 1) { M[(size_t)s * n + s] = 1 + lambda; M[(size_t)s * n + s - 1] = -lambda; }
+    else { M[(size_t)s * n + s] = 1 + 2 * lambda; M[(size_t)s * n + s - 1] = -lambda; M[(size_t)s * n + s + 1] = -lambda; }
+  }
+  if (n == 1) { invWgt[0] = (float)(1. / (double)M[0]); return; }
+  if (n == 2) {
+    double d = (double)M[0] * M[3] - (double)M[1] * M[2];
+    d = 1. / d;
+    // the CV_SIMD128 branch of cv::invert's 2x2 float case multiplies in float by (float)d  [probe: 300 lambdas]
+    invWgt[0] = M[3] * (float)d;
+    invWgt[1] = -(M[1] * (float)d);
+    return;
+  }
+  if (n == 3) {
+    auto S = [&](int r, int c) { return (double)M[r * 3 + c]; };
+    double d = S(0, 0) * (S(1, 1) * S(2, 2) - S(1, 2) * S(2, 1)) - S(0, 1) * (S(1, 0) * S(2, 2) - S(1, 2) * S(2, 0)) +
+               S(0, 2) * (S(1, 0) * S(2, 1) - S(1, 1) * S(2, 0));
+    d = 1. / d;
+    invWgt[0] = (float)((S(1, 1) * S(2, 2) - S(1, 2) * S(2, 1)) * d);
+    invWgt[1] = (float)((S(0, 2) * S(2, 1) - S(0, 1) * S(2, 2)) * d);
+    invWgt[2] = (float)((S(0, 1) * S(1, 2) - S(0, 2) * S(1, 1)) * d);
+    return;
+  }
+  std::vector<float> b((size_t)n * n, 0.f);
+  for (int i = 0; i < n; i++) b[(size_t)i * n + i] = 1.f;
+  float* A = M.data();
+  for (int i = 0; i < n; i++) {
+    int k = i;
+    for (int j = i + 1; j < n; j++) if (std::fabs(A[j * n + i]) > std::fabs(A[k * n + i])) k = j;
+    if (k != i) for (int c = 0; c < n; c++) { std::swap(A[i * n + c], A[k * n + c]); std::swap(b[i * n + c], b[k * n + c]); }
+    const float d = -1 / A[i * n + i];
+    for (int j = i + 1; j < n; j++) {
+      const float alpha = A[j * n + i] * d;
+      for (int c = i + 1; c < n; c++) A[j * n + c] += alpha * A[i * n + c];
+      for (int c = 0; c < n; c++) b[j * n + c] += alpha * b[i * n + c];
+    }
+  }
+  for (int i = n - 1; i >= 0; i--)
+    for (int j = 0; j < n; j++) {
+      float sacc = b[i * n + j];
+      for (int c = i + 1; c < n; c++) sacc -= A[i * n + c] * b[c * n + j];
+      b[i * n + j] = sacc / A[i * n + i];
+    }
+  for (int s = 0; s < n; s++) invWgt[s] = b[s];
+}
+
+// vols[s]: level-s volume [Hs[s]][Ws[s]][Ds[s]]; vols[0] is updated in place.
+void orc_solve_all(float** vols, const int* Hs, const int* Ws, const int* Ds, int levels, float lambda) {
+  std::vector<float> w(levels);
+  orc_cross_scale_weights(levels, lambda, w.data());
+  const int H = Hs[0], W = Ws[0], D = Ds[0];
+  ORC_PAR_FOR
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++)
+      for (int d = 0; d < D; d++) {
+        int cy = y, cx = x, cd = d;
+        float sum = 0;
+        for (int s = 0; s < levels; s++) {
+          sum += w[s] * vols[s][((long)cy * Ws[s] + cx) * Ds[s] + cd];
+          cy /= 2; cx /= 2; cd = (cd + 1) / 2;
+        }
+        vols[0][((long)y * W + x) * D + d] = sum;
+      }
 }
 
 // ---------------------------------------------------------------------------
@@ -660,6 +755,8 @@ struct orc_params {
   int aggregation;  // 1 = "CBCA" (cbca_aggregate), 2 = "NL" (StereoMatching::NL: left volume only), 0 = none
   int costcalc;     // 0 = "ADCensus", 1 = "censusGrad" (main_.cpp:15)
   float cgLamCen, cgLamG, gradTrunc;  // 13, 1 (main_.cpp:60-61), 500 (stereoMatching.cpp:34)
+  int pyrLevels;      // PY_LEV of main_.cpp:132 (1 in the reference's driver)
+  float crossLambda;  // REG_LAMBDA (0.3, main_.cpp:157); < 0: skip SolveAll
 };
 void orc_nl(const u8* bgrL, int H, int W, int D, float* vol, i16* disp);  // nl_oracle.cpp
 }  // extern "C"
@@ -670,25 +767,25 @@ static double now_ms() {
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-extern "C" {
-void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* grayR, int H, int W,
-                  const orc_params* p, i16* dispL, i16* dispR, float* volL_out, float* stage_ms) {
-  const int D = p->D;
-  const long n = (long)H * W * D;
-  double t0 = now_ms(), t = t0, ms[8] = {0};
+// costCalculate() (stereoMatching.cpp:945-1044) for one pyramid level: cost volumes of both views, arms, aggregation.
+// scale = Parameters::disSc of the level (arm lengths L/scale, L_out/scale, stereoMatching.cpp:5368-5371).
+static void cost_calculate(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* grayR, int H, int W, int D,
+                           const orc_params* p, int scale, int views, std::vector<std::vector<float>>& vm,
+                           std::vector<u16>& aL, std::vector<u16>& aR, double* ms, double& t) {
   auto lap = [&](int k) { double x = now_ms(); ms[k] += x - t; t = x; };
+  const long n = (long)H * W * D;
   const int codeLen = orc_census_code_length(p->censusFunc, 3, 4);  // stereoMatching.cpp:815
   const int nw = (codeLen + 63) / 64;
   std::vector<u64> cL((long)H * W * nw), cR((long)H * W * nw);
   orc_census(grayL, H, W, p->censusFunc, 3, 4, cL.data());
   orc_census(grayR, H, W, p->censusFunc, 3, 4, cR.data());
   lap(0);
-  const int views = p->do_refine ? 2 : 1;
-  std::vector<std::vector<float>> vm(2);
-  std::vector<u16> aL((long)H * W * 5), aR((long)H * W * 5);
+  vm.assign(2, std::vector<float>());
+  aL.assign((long)H * W * 5, 0);
+  aR.assign((long)H * W * 5, 0);
   auto arms = [&]() {
-    orc_arms(bgrL, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aL.data());
-    orc_arms(bgrR, H, W, 3, p->L, p->L_out, p->tau, p->tau_out, p->minL, aR.data());
+    orc_arms(bgrL, H, W, 3, p->L / scale, p->L_out / scale, p->tau, p->tau_out, p->minL, aL.data());
+    orc_arms(bgrR, H, W, 3, p->L / scale, p->L_out / scale, p->tau, p->tau_out, p->minL, aR.data());
   };
   if (p->costcalc == 0) {
     std::vector<float> ad(n), cen(n);
@@ -721,6 +818,51 @@ void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* gra
       orc_cbca(vm[i].data(), aL.data(), aR.data(), H, W, D, p->iters, i, nullptr);
   } else if (p->aggregation == 2) {
     orc_nl(bgrL, H, W, D, vm[0].data(), nullptr);  // stereoMatching.cpp:4892-4917: vm[0] only
+  }
+  lap(3);
+}
+
+extern "C" {
+void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* grayR, int H, int W,
+                  const orc_params* p, i16* dispL, i16* dispR, float* volL_out, float* stage_ms) {
+  const int D = p->D;
+  const long n = (long)H * W * D;
+  double t0 = now_ms(), t = t0, ms[8] = {0};
+  auto lap = [&](int k) { double x = now_ms(); ms[k] += x - t; t = x; };
+  const int views = p->do_refine ? 2 : 1;
+  std::vector<std::vector<float>> vm;
+  std::vector<u16> aL, aR;
+  cost_calculate(bgrL, bgrR, grayL, grayR, H, W, D, p, 1, views, vm, aL, aR, ms, t);
+  if (p->crossLambda >= 0.f) {
+    // the caller's pyramid loop (main_.cpp:131-158): level s+1 = pyrDown of level s's colour AND gray images,
+    // maxDisp/2 + 1, disSc*2; costCalculate() per level; then SolveAll
+    const int levels = p->pyrLevels < 1 ? 1 : p->pyrLevels;
+    std::vector<std::vector<std::vector<float>>> lv(levels);   // [level][view]
+    std::vector<int> Hs(levels), Ws(levels), Ds(levels);
+    Hs[0] = H; Ws[0] = W; Ds[0] = D;
+    std::vector<u8> cb[2], cg[2], nb[2], ng[2];
+    const u8 *pbL = bgrL, *pbR = bgrR, *pgL = grayL, *pgR = grayR;
+    int maxDisp = D - 1, scale = 1;
+    for (int s = 1; s < levels; s++) {
+      const int h = Hs[s - 1], w = Ws[s - 1], ho = (h + 1) / 2, wo = (w + 1) / 2;
+      nb[0].resize((long)ho * wo * 3); nb[1].resize((long)ho * wo * 3); ng[0].resize((long)ho * wo); ng[1].resize((long)ho * wo);
+      orc_pyr_down_u8(pbL, h, w, 3, nb[0].data()); orc_pyr_down_u8(pbR, h, w, 3, nb[1].data());
+      orc_pyr_down_u8(pgL, h, w, 1, ng[0].data()); orc_pyr_down_u8(pgR, h, w, 1, ng[1].data());
+      for (int i = 0; i < 2; i++) { cb[i].swap(nb[i]); cg[i].swap(ng[i]); }
+      pbL = cb[0].data(); pbR = cb[1].data(); pgL = cg[0].data(); pgR = cg[1].data();
+      maxDisp = maxDisp / 2 + 1; scale *= 2;
+      Hs[s] = ho; Ws[s] = wo; Ds[s] = maxDisp + 1;
+      std::vector<u16> a0, a1;
+      double dms[8] = {0}, dt = now_ms();
+      cost_calculate(pbL, pbR, pgL, pgR, ho, wo, Ds[s], p, scale, views, lv[s], a0, a1, dms, dt);
+    }
+    for (int i = 0; i < views; i++) {   // SolveAll: img_n = Do_refine ? 2 : 1 (stereoMatching.cpp:2179)
+      std::vector<float*> ptr(levels);
+      ptr[0] = vm[i].data();
+      for (int s = 1; s < levels; s++) ptr[s] = lv[s][i].data();
+      orc_solve_all(ptr.data(), Hs.data(), Ws.data(), Ds.data(), levels, p->crossLambda);
+    }
+    t = now_ms();
   }
   lap(3);
   for (int i = 0; i < views; i++)

@@ -85,6 +85,34 @@ int main(int argc, char** argv) {
       qx_freeu(disp); qx_freeu_3(l3); qx_freeu_3(r3);
       return 0;
     }
+    if (mode == "pyramid") {
+      // the reference's main() flow with PY_LEV = 3 (main_.cpp:131-166): pyramid loop, SolveAll, dispOptimize, refine
+      StereoMatching::costcalculation = "ADCensus";
+      StereoMatching::aggregation = "CBCA";
+      StereoMatching::optimization = "sgm";
+      const int PY_LEV = 3;
+      int maxDisp = D - 1, disSc = 1;
+      cv::Mat c1 = I1c, c2 = I2c, g1 = I1g, g2 = I2g;
+      StereoMatching** smPsy = new StereoMatching*[PY_LEV];
+      for (int p = 0; p < PY_LEV; p++) {
+        StereoMatching::Parameters param(maxDisp, c1.rows, c1.cols, 13, 1, 2, 109, 10, "", disSc);
+        smPsy[p] = new StereoMatching(c1, c2, g1, g2, DT, m0, m1, m2, param);
+        smPsy[p]->setSgmPaths(paths);
+        smPsy[p]->costCalculate();
+        maxDisp = maxDisp / 2 + 1;
+        disSc *= 2;
+        cv::Mat t;
+        pyrDown_u8(c1, t); c1 = t; pyrDown_u8(c2, t); c2 = t; pyrDown_u8(g1, t); g1 = t; pyrDown_u8(g2, t); g2 = t;
+      }
+      SolveAll(smPsy, PY_LEV, 0.3f);
+      smPsy[0]->dispOptimize();
+      smPsy[0]->refine();
+      smPsy[0]->syncToHost(false);
+      dump(out + ".dp0.i16", smPsy[0]->DP[0].data, npix * 2);
+      for (int p = 0; p < PY_LEV; p++) delete smPsy[p];
+      delete[] smPsy;
+      return 0;
+    }
     // "censusgrad": the selectors main_.cpp:15-17 compiles in (censusGrad + CBCA + sgm)
     StereoMatching::costcalculation = mode == "censusgrad" ? "censusGrad" : "ADCensus";
     StereoMatching::aggregation = "CBCA";

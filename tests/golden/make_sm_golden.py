@@ -91,6 +91,15 @@ def stages(tag, H, W, D, kind, seed, full):
     _, _, rf, _ = rcg.pipeline(8, 2, costcalc=1)      # main_.cpp:15's own selector through the whole chain
     out[f"{tag}_pipe8_censusgrad_refined"] = rf
     rcg.close()
+    for levels in ((2, 3) if full else (3,)):         # main_.cpp:131-166 with PY_LEV = levels (pyrDown pyramid + SolveAll)
+        rp = po.SmRef(bl, br, gl, gr, D)
+        rf, s0, s1 = rp.pipeline_pyr(levels, 0.3, 8, 2, 0)
+        out[f"{tag}_pyr{levels}_refined"] = rf
+        if full:
+            out[f"{tag}_pyr{levels}_vm0"] = s0          # vm[0] right after SolveAll
+            if levels == 2:
+                out[f"{tag}_pyr{levels}_vm1"] = s1
+        rp.close()
     for paths in (4, 8):                              # whole default chain, fresh instance
         r = po.SmRef(bl, br, gl, gr, D)
         wl, wr, rf, _ = r.pipeline(paths, 2)

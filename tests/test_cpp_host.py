@@ -26,7 +26,7 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::regionVote_my(cv::Mat&, float, int)", "StereoMatching::properIpol(",
                 "StereoMatching::LRConsistencyCheck_normal(", "StereoMatching::genCensusCode_NC_Sur(",
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
-                "StereoMatching::censusGrad(", "StereoMatching::grad(", "StereoMatching::calGrad(",
+                "SolveAll(StereoMatching**&, int, float)", "pyrDown_u8(", "StereoMatching::censusGrad(", "StereoMatching::grad(", "StereoMatching::calGrad(",
                 "StereoMatching::calGrad_y(", "StereoMatching::calgradvm(",
                 "void StereoMatching::calHorVerDis<unsigned char>(", "void StereoMatching::calArms<unsigned char>(",
                 "NLCCA::aggreCV(", "qx_tree_filter::filter(double*, double*, int)", "qx_tree_filter::build_tree(",
@@ -99,6 +99,19 @@ def test_cpp_class_censusgrad_chain_matches_oracle(tmp_path):
     res = po.pipeline(bl, br, gl, gr, po.default_params(D, paths=P, costcalc=1))
     dp = np.fromfile(prefix + ".dp0.i16", np.int16).reshape(H, W)
     assert (dp == res[0]).mean() >= 0.995
+
+
+@pytest.mark.gpu
+def test_cpp_pyramid_main_flow_matches_oracle(tmp_path):
+    """The reference's main() loop with PY_LEV = 3 written against the C++ class: per-level costCalculate(),
+    the free function SolveAll(smPyr, PY_LEV, 0.3), dispOptimize(), refine()."""
+    H, W, D, P = 66, 100, 32, 4
+    pair = synth.make_pair(H, W, D, "texture_warped", seed=29)
+    prefix, _ = _run(tmp_path, pair, D, P, "pyramid")
+    res = po.pipeline(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"],
+                      po.default_params(D, paths=P, pyr_levels=3, cross_lambda=0.3))
+    dp = np.fromfile(prefix + ".dp0.i16", np.int16).reshape(H, W)
+    assert np.array_equal(dp, res[0])       # 4 paths in the reference's order: identical map
 
 
 @pytest.mark.gpu

@@ -157,3 +157,49 @@ def test_gradient_family_equals_reference(ctx, g, tag):
     dl, _ = pl.download(want_right=True)
     pl.close()
     assert (dl == g[f"{tag}_pipe8_censusgrad_refined"]).mean() >= 0.995  # north_star: >= 99.5 % identical pixels
+
+
+# ---------------------------------------------------------------- cross-scale step
+def test_pyr_down_and_weights_equal_cv2(ctx, golden_dir):
+    cvg = np.load(os.path.join(golden_dir, "opencv_semantics.npz"))
+    for k in range(int(cvg["n_pyr"])):
+        got = ctx.pyr_down(ctx.dev(cvg[f"pyr_in{k}"])).cpu().numpy()
+        assert np.array_equal(got, cvg[f"pyr_out{k}"]), k
+    for a, lam in enumerate(cvg["inv_lams"]):
+        for n in range(1, 7):
+            got = np.array(capi.cross_scale_weights(n, float(lam)), np.float32)
+            assert np.array_equal(got.view(np.uint32), cvg["inv_rows"][a, n - 1, :n].view(np.uint32)), (lam, n)
+
+
+def test_solve_all_volumes_equal_reference(ctx, g):
+    """Stage by stage on the device: pyrDown pyramid, per-level cost + CBCA, SolveAll -> vm right after SolveAll."""
+    bl, br, gl, gr, D = _inputs(g, "a")
+    for levels, views in ((2, (0, 1)), (3, (0,))):
+        for v in views:
+            imgs = [ctx.dev(x) for x in (bl, br, gl, gr)]
+            vols, maxd, scale = [], D - 1, 1
+            for s in range(levels):
+                if s > 0:
+                    imgs = [ctx.pyr_down(x) for x in imgs]
+                    maxd, scale = maxd // 2 + 1, scale * 2
+                cL, cR = ctx.census(imgs[2], 3), ctx.census(imgs[3], 3)
+                vol = ctx.cost_adcensus(imgs[0], imgs[1], cL, cR, maxd + 1, 3, v)
+                aL, aR = ctx.arms(imgs[0], 17 // scale, 34 // scale), ctx.arms(imgs[1], 17 // scale, 34 // scale)
+                vols.append(ctx.cbca(vol, aL, aR, 2, v))
+            got = ctx.cross_scale(vols, 0.3).cpu().numpy()
+            assert _same(got, g[f"a_pyr{levels}_vm{v}"]), (levels, v)
+
+
+@pytest.mark.parametrize("tag,levels", [("a", 2), ("a", 3), ("b", 3), ("c", 3)])
+def test_pyramid_chain_equals_reference(ctx, g, tag, levels):
+    bl, br, gl, gr, D = _inputs(g, tag)
+    H, W = gl.shape
+    params = capi.default_params(D - 1, sgm_paths=8, sgm_grouped=0, pyramidLevels=levels, crossScaleLambda=0.3)
+    pl = capi.Pipeline(ctx, H, W, params)
+    pl.upload(bl, br, gl, gr)
+    pl.run_device()
+    dl, _ = pl.download(want_right=True)
+    again = pl.run(bl, br, gl, gr)          # a second frame through the same pipeline (buffers rotate after SGM)
+    pl.close()
+    assert _same(dl, g[f"{tag}_pyr{levels}_refined"])
+    assert np.array_equal(again, dl)

@@ -331,3 +331,37 @@ def test_nlca_helpers_known_answers():
     # right[x][d] = left[x+d][d] while x+d < W, else the previous plane's value
     assert f[0, 0].tolist() == [vol[0, 0, 0], vol[0, 1, 1], vol[0, 2, 2], vol[0, 2, 2]]
     assert f[0, 2].tolist() == [vol[0, 2, 0]] * 4
+
+
+# ---------------------------------------------------------------- cross-scale step
+def test_pyr_down_matches_cv2(cvg):
+    for k in range(int(cvg["n_pyr"])):
+        assert np.array_equal(po.pyr_down(cvg[f"pyr_in{k}"]), cvg[f"pyr_out{k}"]), k
+
+
+def test_cross_scale_weights_match_cv2_invert(cvg):
+    for a, lam in enumerate(cvg["inv_lams"]):
+        for n in range(1, 8):
+            got = po.cross_scale_weights(n, float(lam))
+            assert np.array_equal(got.view(np.uint32), cvg["inv_rows"][a, n - 1, :n].view(np.uint32)), (lam, n)
+
+
+def test_solve_all_known_answer():
+    """SolveAll by hand: 2 levels, weights w; out[y,x,d] = w0*v0[y,x,d] + w1*v1[y//2,x//2,(d+1)//2] in float order."""
+    rng = np.random.default_rng(3)
+    v0 = rng.random((5, 6, 7)).astype(np.float32)
+    v1 = rng.random((3, 3, 5)).astype(np.float32)
+    w = po.cross_scale_weights(2, 0.3)
+    want = np.empty_like(v0)
+    for y in range(5):
+        for x in range(6):
+            for d in range(7):
+                s = np.float32(0)
+                s = np.float32(s + np.float32(w[0] * v0[y, x, d]))
+                s = np.float32(s + np.float32(w[1] * v1[y // 2, x // 2, (d + 1) // 2]))
+                want[y, x, d] = s
+    assert np.array_equal(po.solve_all([v0, v1], 0.3).view(np.uint32), want.view(np.uint32))
+    one = po.solve_all([v0], 0.3)
+    ref = v0.copy().reshape(-1)
+    po.lib().orc_solve_all_1level(ref, ref.size, 0.3)
+    assert np.allclose(one.reshape(-1), ref, rtol=2e-7)      # 1/(1+l): float division vs (float)(1./double) of cv
