@@ -149,7 +149,7 @@ def test_gradient_family_equals_reference(ctx, g, tag):
         got = ctx.cost_censusgrad(dL, dR, gL, gR, arms[v], D, 3, v).cpu().numpy()
         ref = g[f"{tag}_censusgrad_v{v}"]
         assert np.all(np.abs(got - ref) <= 1e-4 * np.abs(ref))           # device expf: north_star's 1e-4 relative
-        assert np.abs(got - ref).max() <= 4e-7                           # in fact a couple of ulp of values in [0, 2]
+        assert np.abs(got - ref).max() <= 1e-6                           # in fact a few ulp of values in [0, 2]
     params = capi.default_params(D - 1, sgm_paths=8, sgm_grouped=0, costcalculation=1)
     pl = capi.Pipeline(ctx, H, W, params)
     pl.upload(bl, br, gl, gr)
