@@ -254,7 +254,7 @@ def main_reference(args):
            "cpu_baseline": {"value": val, "unit": "MDE/s", "cores": nt, "kind": kindb, "sample": sample},
            "e2e": {"value": val, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "note": note}
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
@@ -441,7 +441,7 @@ def main_ours(args):
                "quality": {"bad2_nonocc_pct": round(bad2, 3), "checksum": chk}}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(name)
-        print(json.dumps(out))
+        emit(out)
     pl.close()
     ctx.close()
     if dist is not None:
@@ -449,7 +449,39 @@ def main_ours(args):
     return 0
 
 
+class QuietStdout:
+    """stdout carries exactly ONE JSON line.  Native libraries (NCCL's version banner, the reference's printf
+    chatter) write to file descriptor 1 directly, so for the duration of the run fd 1 is pointed at stderr and the
+    JSON line is written to the saved descriptor at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def close(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+OUT = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line)
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -459,7 +491,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    return main_reference(args) if args.impl == "reference" else main_ours(args)
+    OUT = QuietStdout()
+    try:
+        return main_reference(args) if args.impl == "reference" else main_ours(args)
+    finally:
+        OUT.close()
 
 
 if __name__ == "__main__":
