@@ -292,6 +292,24 @@ int sm_cross_scale_weights(int n, float lambda, float* invWgt);
 int sm_cross_scale(sm_ctx* ctx, float* const* d_vols, const int* Hs, const int* Ws, const int* Ds, int levels,
                    float lambda);
 
+/* ---- stage-API sub-steps the pipeline kernels fuse, one by one (stage_parts.cu) ---- */
+/* gen1DCumu (stereoMatching.cpp:3896-3926): in-place running sum along -u ((dv,du) = (0,-1)) or -v ((-1,0)) of the
+ * volume and, when not NULL, of the int32 area volume.  Sequential float order: bit-exact. */
+int sm_cumsum_1d(sm_ctx* ctx, float* d_vol, int32_t* d_areaIS, int H, int W, int D, int dv, int du);
+/* cal1DCost (stereoMatching.h:1643-1715, cbca_intersect = true): out = cum[head] - cum[pre_tail] with the
+ * materialised intersected arms d_hvl_is [H][W][D][5] (sm_arms_intersect); results replace d_vol / d_areaIS
+ * (d_tmp_*: scratch of the same sizes).  direc 0: horizontal span, 1: vertical. */
+int sm_span_1d(sm_ctx* ctx, float* d_vol, int32_t* d_areaIS, const uint16_t* d_hvl_is, float* d_tmp_vol,
+               int32_t* d_tmp_area, int H, int W, int D, int dv, int du, int direc);
+/* genfinalVm_cbca (stereoMatching.cpp:3969-3992): vol[i] /= (float)areaIS[i]. */
+int sm_div_area(sm_ctx* ctx, float* d_vol, const int32_t* d_areaIS, size_t n);
+/* updateCost<float> (stereoMatching.h:2205-2280) at ONE pixel (v,u) of path (rv,ru); d_bgr = the image of the view
+ * (I_c[0] if leftFirst else I_c[1]). */
+int sm_update_cost(sm_ctx* ctx, float* d_Lr, const float* d_vm, const uint8_t* d_bgr, int H, int W, int n, int v,
+                   int u, int rv, int ru, int preIsInner, int corDifThres, int reduCoeffi1);
+/* LRConsistencyCheck_new (stereoMatching.cpp:2367-2382): mask[v][u] = 0 where the left-right check fails (Thres 0). */
+int sm_lrc_mask(sm_ctx* ctx, const int16_t* d_D1, const int16_t* d_D2, int H, int W, uint8_t* d_mask);
+
 /* ---- whole frame ------------------------------------------------------------ */
 /* A frame pipeline owns every device buffer a W x H x D frame needs (three
  * volumes, codes, arms, images, disparities) so a stream of frames reuses them.

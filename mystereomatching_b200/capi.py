@@ -63,6 +63,11 @@ SIGNATURES = {
     "sm_cost_ad": ([_P, _P, _P, _I, _I, _I, _I, _F, _P], _I),
     "sm_cost_adcensus": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P], _I),
     "sm_combine_exp": ([_P, _P, _P, _Z, _F, _F, _P], _I),
+    "sm_cumsum_1d": ([_P, _P, _P, _I, _I, _I, _I, _I], _I),
+    "sm_span_1d": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I], _I),
+    "sm_div_area": ([_P, _P, _P, _Z], _I),
+    "sm_update_cost": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I], _I),
+    "sm_lrc_mask": ([_P, _P, _P, _I, _I, _P], _I),
     "sm_pyr_down_u8": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_cross_scale_weights": ([_I, _F, _P], _I),
     "sm_cross_scale": ([_P, _P, _P, _P, _P, _I, _F], _I),
@@ -239,6 +244,32 @@ class Ctx:
         out = self.torch.empty_like(a)
         check(self.L.sm_combine_exp(self.h, _ptr(a), _ptr(b), a.numel(), l0, l1, _ptr(out)))
         return out
+
+    def cumsum_1d(self, vol, area, dv, du):
+        H, W, D = vol.shape
+        check(self.L.sm_cumsum_1d(self.h, _ptr(vol), _ptr(area), H, W, D, dv, du))
+        return vol, area
+
+    def span_1d(self, vol, area, hvl_is, dv, du, direc):
+        H, W, D = vol.shape
+        tv = self.torch.empty_like(vol)
+        ta = self.torch.empty_like(area) if area is not None else None
+        check(self.L.sm_span_1d(self.h, _ptr(vol), _ptr(area), _ptr(hvl_is), _ptr(tv), _ptr(ta), H, W, D, dv, du, direc))
+        return vol, area
+
+    def div_area(self, vol, area):
+        check(self.L.sm_div_area(self.h, _ptr(vol), _ptr(area), vol.numel()))
+        return vol
+
+    def update_cost(self, Lr, vm, bgr, v, u, rv, ru, pre_is_inner, thr=15, redu=4):
+        H, W, n = vm.shape
+        check(self.L.sm_update_cost(self.h, _ptr(Lr), _ptr(vm), _ptr(bgr), H, W, n, v, u, rv, ru, int(pre_is_inner), thr, redu))
+        return Lr
+
+    def lrc_mask(self, d1, d2, mask):
+        H, W = d1.shape
+        check(self.L.sm_lrc_mask(self.h, _ptr(d1), _ptr(d2), H, W, _ptr(mask)))
+        return mask
 
     def pyr_down(self, img):
         H, W = img.shape[:2]

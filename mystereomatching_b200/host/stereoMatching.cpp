@@ -442,6 +442,64 @@ void StereoMatching::genTrueHorVerArms(vector<Mat>& HVL_, vector<Mat>& HVL_IS) {
   }
 }
 
+void StereoMatching::gen1DCumu(cv::Mat& vm_, cv::Mat& area, Mat& areaIS, int dv, int du) {
+  (void)area;   // cbca_intersect = true: the per-disparity areaIS is the one in use (stereoMatching.h:262)
+  const size_t n = (size_t)h_ * w_ * d_;
+  CV_Assert(vm_.depth() == CV_32F && vm_.total() * vm_.channels() == n);
+  CV_Assert(areaIS.depth() == CV_32S && areaIS.total() * areaIS.channels() == n);
+  TmpDev v(ctx_, n * 4), a(ctx_, n * 4);
+  upload(v.p, vm_.data, n * 4); upload(a.p, areaIS.data, n * 4);
+  check(sm_cumsum_1d(ctx_, v.as<float>(), a.as<int32_t>(), h_, w_, d_, dv, du), "sm_cumsum_1d");
+  download(vm_.data, v.p, n * 4); download(areaIS.data, a.p, n * 4);
+}
+void StereoMatching::cal1DCost(Mat& vm_, cv::Mat& HVL_, cv::Mat& area, Mat& areaIS, Mat& HVL_IS, int dv, int du, int direc) {
+  (void)area;
+  CV_Assert(HVL_.depth() == CV_16U);   // stereoMatching.h:1647
+  const size_t n = (size_t)h_ * w_ * d_;
+  CV_Assert(vm_.depth() == CV_32F && vm_.total() * vm_.channels() == n);
+  CV_Assert(areaIS.depth() == CV_32S && areaIS.total() * areaIS.channels() == n);
+  CV_Assert(HVL_IS.depth() == CV_16U && HVL_IS.total() * HVL_IS.channels() == n * 5);
+  TmpDev v(ctx_, n * 4), a(ctx_, n * 4), tv(ctx_, n * 4), ta(ctx_, n * 4), is(ctx_, n * 10);
+  upload(v.p, vm_.data, n * 4); upload(a.p, areaIS.data, n * 4); upload(is.p, HVL_IS.data, n * 10);
+  check(sm_span_1d(ctx_, v.as<float>(), a.as<int32_t>(), is.as<uint16_t>(), tv.as<float>(), ta.as<int32_t>(), h_, w_, d_, dv,
+                   du, direc), "sm_span_1d");
+  download(vm_.data, v.p, n * 4); download(areaIS.data, a.p, n * 4);
+}
+void StereoMatching::genfinalVm_cbca(Mat& vm_, Mat& area, Mat& areaIS, int imgNum) {
+  (void)area; (void)imgNum;
+  CV_Assert(vm_.depth() == CV_32F);   // stereoMatching.cpp:3971
+  const size_t n = (size_t)h_ * w_ * d_;
+  CV_Assert(vm_.total() * vm_.channels() == n && areaIS.depth() == CV_32S && areaIS.total() * areaIS.channels() == n);
+  TmpDev v(ctx_, n * 4), a(ctx_, n * 4);
+  upload(v.p, vm_.data, n * 4); upload(a.p, areaIS.data, n * 4);
+  check(sm_div_area(ctx_, v.as<float>(), a.as<int32_t>(), n), "sm_div_area");
+  download(vm_.data, v.p, n * 4);
+}
+template <typename T>
+void StereoMatching::updateCost(cv::Mat& Lr, cv::Mat& vm_, int v, int u, int n, int rv, int ru, bool preIsInner, bool leftFirst) {
+  static_assert(sizeof(T) == sizeof(float), "the ctor only ever allocates CV_32F volumes (stereoMatching.cpp:2080)");
+  const size_t nv = (size_t)h_ * w_ * n;
+  CV_Assert(vm_.depth() == CV_32F && Lr.depth() == CV_32F && n == d_);
+  CV_Assert(vm_.total() * vm_.channels() == nv && Lr.total() * Lr.channels() == nv);
+  TmpDev l(ctx_, nv * 4), c(ctx_, nv * 4);
+  upload(l.p, Lr.data, nv * 4); upload(c.p, vm_.data, nv * 4);
+  check(sm_update_cost(ctx_, l.as<float>(), c.as<float>(), d_bgr_[leftFirst ? 0 : 1], h_, w_, n, v, u, rv, ru, preIsInner ? 1 : 0,
+                       param_.sgm_corDifThres, param_.sgm_reduCoeffi1), "sm_update_cost");
+  download(Lr.data, l.p, nv * 4);
+}
+template void StereoMatching::updateCost<float>(cv::Mat&, cv::Mat&, int, int, int, int, int, bool, bool);
+
+void StereoMatching::LRConsistencyCheck_new(Mat& errorMask) {
+  CV_Assert(errorMask.depth() == CV_8U && errorMask.rows == h_ && errorMask.cols == w_);
+  const size_t n = (size_t)h_ * w_;
+  for (int i = 0; i < 2; i++)
+    if (!dp_dev_fresh_[i]) { CV_Assert(!DP[i].empty()); upload(d_disp_[i], DP[i].data, n * 2); }
+  TmpDev m(ctx_, n);
+  upload(m.p, errorMask.data, n);
+  check(sm_lrc_mask(ctx_, d_disp_[0], d_disp_[1], h_, w_, m.as<uint8_t>()), "sm_lrc_mask");
+  download(errorMask.data, m.p, n);
+}
+
 void StereoMatching::cbca_core(vector<Mat>& HVL_, vector<Mat>& HVL_IS, vector<Mat>& vm_, int ITNUM) {
   (void)HVL_IS;
   const int imgNum = (Do_refine && Do_LRConsis) ? 2 : 1;

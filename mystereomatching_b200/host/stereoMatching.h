@@ -123,6 +123,12 @@ class StereoMatching {
   template <typename T>
   void calHorVerDis(Mat& I, Mat& cross, int L, int L_out, int C_D, int C_D_out, int minL);  // :2958-3050
   void genTrueHorVerArms(vector<Mat>& HVL, vector<Mat>& HVL_INTERSECTION);              // stereoMatching.cpp:2794-2845
+  // the sub-steps cbca_core composes, on caller-provided Mats (host in, host out; the fused k_cbca_pass is what
+  // cbca_core itself runs)
+  void gen1DCumu(cv::Mat& vm, cv::Mat& area, Mat& areaIS, int dv, int du);              // stereoMatching.cpp:3896-3926
+  void cal1DCost(Mat& vm, cv::Mat& HVL, cv::Mat& area, Mat& areaIS, Mat& HVL_INTERSECTION, int dv, int du,
+                 int direc);                                                           // stereoMatching.h:1643-1715
+  void genfinalVm_cbca(Mat& vm, Mat& area, Mat& areaIS, int imgNum);                    // stereoMatching.cpp:3969-3992
   void SolveAll(int PY_LVL, float REG_LAMBDA);                                          // member form, 1 level (main_.cpp:158)
   friend void SolveAll(StereoMatching**& smPyr, const int PY_LVL, const float REG_LAMBDA);
 
@@ -131,12 +137,15 @@ class StereoMatching {
   void costScan(cv::Mat& Lr, cv::Mat& vm, int rv, int ru, bool leftFirst);              // stereoMatching.cpp:1983-2029
   void gen_sgm_vm(Mat& vm, vector<cv::Mat1f>& Lr, int numOfDirec);                      // stereoMatching.cpp:2031-2056
   static float min4(float a, float b, float c, float d) { return std::min(std::min(a, b), std::min(c, d)); }
+  template <typename T>
+  void updateCost(cv::Mat& Lr, cv::Mat& vm, int v, int u, int n, int rv, int ru, bool preIsInner, bool leftFirst);  // stereoMatching.h:2205-2280
   void gen_dispFromVm(Mat& vm, Mat& dispMap);                                           // stereoMatching.cpp:3928-3967
   void wta_Co(cv::Mat& vm, cv::Mat& D1, cv::Mat& D2);                                   // stereoMatching.cpp:2709-2792
 
   // ---- refinement
   void LRConsistencyCheck(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR = 0);         // :2284-2364
   void LRConsistencyCheck_normal(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR = 0);  // :2262-2282
+  void LRConsistencyCheck_new(Mat& errorMask);                                              // :2367-2382 (reads DP[0], DP[1])
   void regionVote_my(cv::Mat& Dp, float rv_ratio, int rv_s);                            // stereoMatching.cpp:7219-7277
   void properIpol(cv::Mat& Dp, cv::Mat& I1_c);                                          // stereoMatching.cpp:7395-7490
 

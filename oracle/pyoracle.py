@@ -463,7 +463,9 @@ def smref_lib():
         "smref_adcensus": ([P], None), "smref_grad_xy": ([P, I, f32p, f32p], None),
         "smref_grad_vm": ([P, F, f32p, f32p], None), "smref_censusgrad": ([P], None), "smref_get_vm": ([P, I, f32p], None), "smref_set_vm": ([P, I, f32p], None),
         "smref_arms": ([P, u16p, u16p], None), "smref_arms_intersection": ([P, I, u16p], None),
-        "smref_cbca": ([P, I], None), "smref_cost_scan": ([P, I, I, f32p], None), "smref_sgm": ([P, I, I], None),
+        "smref_cbca": ([P, I], None), "smref_gen1dcumu": ([P, f32p, i32p, I, I], None),
+        "smref_cal1dcost": ([P, I, f32p, i32p, I, I, I], None), "smref_genfinal": ([P, f32p, i32p], None),
+        "smref_update_cost": ([P, I, f32p, I, I, I, I, I], None), "smref_cost_scan": ([P, I, I, f32p], None), "smref_sgm": ([P, I, I], None),
         "smref_wta": ([P, I, i16p], None), "smref_wta_co": ([P, I, i16p, i16p], None),
         "smref_lrc_normal": ([P, i16p, i16p], None), "smref_lrc_label": ([P, i16p, i16p, I, P], None),
         "smref_lrc_new": ([P, i16p, i16p, u8p], None),
@@ -572,6 +574,26 @@ class SmRef:
         o = np.empty((self.H, self.W, self.D, 5), np.uint16)
         self.L.smref_arms_intersection(self.h, view, o)
         return o
+
+    def gen1dcumu(self, vol, area, dv, du):
+        v, a = np.ascontiguousarray(vol, np.float32).copy(), np.ascontiguousarray(area, np.int32).copy()
+        self.L.smref_gen1dcumu(self.h, v, a, dv, du)
+        return v, a
+
+    def cal1dcost(self, view, vol, area, dv, du, direc):
+        v, a = np.ascontiguousarray(vol, np.float32).copy(), np.ascontiguousarray(area, np.int32).copy()
+        self.L.smref_cal1dcost(self.h, view, v, a, dv, du, direc)
+        return v, a
+
+    def genfinal(self, vol, area):
+        v = np.ascontiguousarray(vol, np.float32).copy()
+        self.L.smref_genfinal(self.h, v, np.ascontiguousarray(area, np.int32))
+        return v
+
+    def update_cost(self, view, Lr, v, u, rv, ru, pre_is_inner):
+        l = np.ascontiguousarray(Lr, np.float32).copy()
+        self.L.smref_update_cost(self.h, view, l, v, u, rv, ru, int(pre_is_inner))
+        return l
 
     def cbca(self, iters=2):
         self.L.smref_cbca(self.h, iters)

@@ -158,6 +158,30 @@ int main(int argc, char** argv) {
       dump(out + ".cen0.f32", cv0.data, npix * D * 4);
       sm.costScan(lr, cv0, 0, -1, true);
       dump(out + ".lr3.f32", lr.data, npix * D * 4);
+      // the sub-steps cbca_core composes, one public method at a time (first iteration, view 0), on host Mats
+      {
+        cv::Mat v0;
+        sm.gen_ad_sd_vm(v0, 0, 0, 1000);            // any float volume serves; AD is at hand
+        int sz[3] = {H, W, D};
+        cv::Mat areaIS(3, sz, CV_32SC1, cv::Scalar::all(1)), none;
+        std::vector<cv::Mat> hvl = sm.HVL, is(2);
+        sm.syncToHost(false);
+        sm.genTrueHorVerArms(sm.HVL, is);
+        sm.gen1DCumu(v0, none, areaIS, 0, -1);
+        sm.cal1DCost(v0, sm.HVL[0], none, areaIS, is[0], 0, -1, 0);
+        sm.gen1DCumu(v0, none, areaIS, -1, 0);
+        sm.cal1DCost(v0, sm.HVL[0], none, areaIS, is[0], -1, 0, 1);
+        sm.genfinalVm_cbca(v0, none, areaIS, 0);
+        dump(out + ".parts_cbca1.f32", v0.data, npix * D * 4);
+        // updateCost<float> at one pixel of path 3 (rv = 0, ru = -1): recompute pixel (H/2, W/2) of lr
+        cv::Mat lr2 = lr.clone();
+        for (int d = 0; d < D; d++) lr2.ptr<float>(H / 2, W / 2)[d] = -1.f;
+        sm.updateCost<float>(lr2, cv0, H / 2, W / 2, D, 0, -1, true, true);
+        dump(out + ".lr3_pixel.f32", lr2.data, npix * D * 4);
+        cv::Mat mask(H, W, CV_8UC1, cv::Scalar::all(255));
+        sm.LRConsistencyCheck_new(mask);
+        dump(out + ".lrc_new.u8", mask.data, npix);
+      }
     }
     sm.syncToHost(false);
     dump(out + ".dp0.i16", sm.DP[0].data, npix * 2);

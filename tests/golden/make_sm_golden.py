@@ -49,6 +49,17 @@ def stages(tag, H, W, D, kind, seed, full):
         c1, _ = r1.cbca(1)                            # one iteration only
         out[f"{tag}_cbca1_v0"] = c1
         r1.close()
+    if full:
+        # the CBCA sub-steps one by one on view 0 (first iteration: H cumsum, H span, V cumsum, V span, divide)
+        ones = np.ones((H, W, D), np.int32)
+        sv, sa = r.gen1dcumu(v0, ones, 0, -1)         # gen1DCumu along u
+        out[f"{tag}_part_cumH_vol"], out[f"{tag}_part_cumH_area"] = sv, sa.astype(np.int16)
+        sv, sa = r.cal1dcost(0, sv, sa, 0, -1, 0)     # cal1DCost, horizontal span
+        out[f"{tag}_part_spanH_vol"], out[f"{tag}_part_spanH_area"] = sv, sa.astype(np.int16)
+        sv, sa = r.gen1dcumu(sv, sa, -1, 0)           # gen1DCumu along v
+        sv, sa = r.cal1dcost(0, sv, sa, -1, 0, 1)     # cal1DCost, vertical span
+        out[f"{tag}_part_spanV_vol"], out[f"{tag}_part_spanV_area"] = sv, sa.astype(np.int16)
+        out[f"{tag}_part_final_vol"] = r.genfinal(sv, sa)   # genfinalVm_cbca  (== cbca1_v0)
     c0, c1 = r.cbca(2)                                # cbca_aggregate -> cbca_core, 2 iterations, both views
     out[f"{tag}_cbca2_v0"], out[f"{tag}_cbca2_v1"] = c0, c1
     if full:
@@ -67,6 +78,7 @@ def stages(tag, H, W, D, kind, seed, full):
     out[f"{tag}_wtaco_D1"], out[f"{tag}_wtaco_D2"] = w1, w2
     lrc = r.lrc_normal(d0, d1)                        # LRConsistencyCheck_normal
     out[f"{tag}_lrc"] = lrc
+    out[f"{tag}_lrc_new_mask"] = r.lrc_new(d0, d1, np.full((H, W), 255, np.uint8))   # LRConsistencyCheck_new
     la, lb, lm = r.lrc_label(d0, d1, 0)               # LRConsistencyCheck (labelling form)
     out[f"{tag}_lrc_label"], out[f"{tag}_lrc_mask"] = la, lm
     rv1 = r.region_vote(lrc, 0.4, 20)                 # regionVote_my

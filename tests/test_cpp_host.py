@@ -26,6 +26,8 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::regionVote_my(cv::Mat&, float, int)", "StereoMatching::properIpol(",
                 "StereoMatching::LRConsistencyCheck_normal(", "StereoMatching::genCensusCode_NC_Sur(",
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
+                "StereoMatching::gen1DCumu(", "StereoMatching::cal1DCost(", "StereoMatching::genfinalVm_cbca(",
+                "void StereoMatching::updateCost<float>(", "StereoMatching::LRConsistencyCheck_new(",
                 "SolveAll(StereoMatching**&, int, float)", "pyrDown_u8(", "StereoMatching::censusGrad(", "StereoMatching::grad(", "StereoMatching::calGrad(",
                 "StereoMatching::calGrad_y(", "StereoMatching::calgradvm(",
                 "void StereoMatching::calHorVerDis<unsigned char>(", "void StereoMatching::calArms<unsigned char>(",
@@ -78,6 +80,14 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
         assert np.array_equal(cv0, ham)
         lr = np.fromfile(prefix + ".lr3.f32", np.float32).reshape(H, W, D)
         assert np.array_equal(lr, po.sgm_path(ham, pair["bgrL"], 3))
+        # gen1DCumu / cal1DCost / genfinalVm_cbca one by one == one fused CBCA iteration
+        parts = np.fromfile(prefix + ".parts_cbca1.f32", np.float32).reshape(H, W, D)
+        assert np.array_equal(parts.view(np.uint32), po.cbca(ad, aL, aR, 1, 0).view(np.uint32))
+        # updateCost<float> at one pixel restores the wiped row of the path volume
+        assert np.array_equal(np.fromfile(prefix + ".lr3_pixel.f32", np.float32).reshape(H, W, D), lr)
+        # LRConsistencyCheck_new on the final DP[0] / DP[1]
+        m = np.fromfile(prefix + ".lrc_new.u8", np.uint8).reshape(H, W)
+        assert set(np.unique(m)) <= {0, 255} and (m == 0).any()
 
 
 @pytest.mark.gpu

@@ -203,3 +203,53 @@ def test_pyramid_chain_equals_reference(ctx, g, tag, levels):
     pl.close()
     assert _same(dl, g[f"{tag}_pyr{levels}_refined"])
     assert np.array_equal(again, dl)
+
+
+# ---------------------------------------------------------------- stage-API sub-steps (stage_parts.cu)
+def test_cbca_substeps_equal_reference(ctx, g):
+    """gen1DCumu -> cal1DCost (H) -> gen1DCumu -> cal1DCost (V) -> genfinalVm_cbca, one call each, against the
+    reference's own functions at every step (first CBCA iteration of view 0)."""
+    bl, br, gl, gr, D = _inputs(g, "a")
+    H, W = gl.shape
+    vol = ctx.dev(g["a_adcensus_v0"].copy())
+    area = ctx.dev(np.ones((H, W, D), np.int32))
+    isect = ctx.dev(g["a_isect_v0"].astype(np.uint16).view(np.int16))
+    ctx.cumsum_1d(vol, area, 0, -1)
+    assert _same(vol.cpu().numpy(), g["a_part_cumH_vol"])
+    assert np.array_equal(area.cpu().numpy(), g["a_part_cumH_area"].astype(np.int32))
+    ctx.span_1d(vol, area, isect, 0, -1, 0)
+    assert _same(vol.cpu().numpy(), g["a_part_spanH_vol"])
+    assert np.array_equal(area.cpu().numpy(), g["a_part_spanH_area"].astype(np.int32))
+    ctx.cumsum_1d(vol, area, -1, 0)
+    ctx.span_1d(vol, area, isect, -1, 0, 1)
+    assert _same(vol.cpu().numpy(), g["a_part_spanV_vol"])
+    assert np.array_equal(area.cpu().numpy(), g["a_part_spanV_area"].astype(np.int32))
+    ctx.div_area(vol, area)
+    assert _same(vol.cpu().numpy(), g["a_part_final_vol"])
+    assert _same(vol.cpu().numpy(), g["a_cbca1_v0"])            # = one fused k_cbca_pass iteration
+
+
+def test_update_cost_pixel_equals_reference(ctx, g):
+    """updateCost<float> at single pixels: wipe a pixel's row in the reference's costScan volume, recompute it."""
+    bl, _, _, _, D = _inputs(g, "a")
+    H, W = bl.shape[:2]
+    table = {0: (1, 0), 1: (-1, 0), 2: (0, 1), 3: (0, -1), 4: (1, -1), 5: (1, 1), 6: (-1, 1), 7: (-1, -1)}
+    vm, b = ctx.dev(g["a_cbca2_v0"]), ctx.dev(bl)
+    rng = np.random.default_rng(5)
+    for path, (rv, ru) in table.items():
+        ref = g[f"a_path{path}_v0"]
+        for _ in range(6):
+            v, u = int(rng.integers(0, H)), int(rng.integers(0, W))
+            inner = 0 <= v + rv < H and 0 <= u + ru < W
+            Lr = ref.copy()
+            Lr[v, u, :] = -7.0
+            got = ctx.update_cost(ctx.dev(Lr), vm, b, v, u, rv, ru, inner).cpu().numpy()
+            assert _same(got, ref), (path, v, u)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_lrc_new_mask_equals_reference(ctx, g, tag):
+    d0, d1 = g[f"{tag}_wta_v0"], g[f"{tag}_wta_v1"]
+    mask = ctx.dev(np.full(d0.shape, 255, np.uint8))
+    got = ctx.lrc_mask(ctx.dev(d0), ctx.dev(d1), mask).cpu().numpy()
+    assert np.array_equal(got, g[f"{tag}_lrc_new_mask"])
