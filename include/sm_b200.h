@@ -307,6 +307,10 @@ int sm_div_area(sm_ctx* ctx, float* d_vol, const int32_t* d_areaIS, size_t n);
  * (I_c[0] if leftFirst else I_c[1]). */
 int sm_update_cost(sm_ctx* ctx, float* d_Lr, const float* d_vm, const uint8_t* d_bgr, int H, int W, int n, int v,
                    int u, int rv, int ru, int preIsInner, int corDifThres, int reduCoeffi1);
+/* The integer-cost entry of costScan (vm.depth() CV_8U / CV_16U, stereoMatching.cpp:2007-2021): updateCost<uchar> /
+ * <ushort> add `T cost` to a float, i.e. they see the volume converted to float; convert (elem_bytes 1 | 2), then
+ * sm_sgm_path / sm_sgm.  Exact. */
+int sm_vol_to_f32(sm_ctx* ctx, const void* d_src, int elem_bytes, size_t n, float* d_dst);
 /* LRConsistencyCheck_new (stereoMatching.cpp:2367-2382): mask[v][u] = 0 where the left-right check fails (Thres 0). */
 int sm_lrc_mask(sm_ctx* ctx, const int16_t* d_D1, const int16_t* d_D2, int H, int W, uint8_t* d_mask);
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "sm_div_area": ([_P, _P, _P, _Z], _I),
     "sm_update_cost": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I], _I),
     "sm_lrc_mask": ([_P, _P, _P, _I, _I, _P], _I),
+    "sm_vol_to_f32": ([_P, _P, _I, _Z, _P], _I),
     "sm_pyr_down_u8": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_cross_scale_weights": ([_I, _F, _P], _I),
     "sm_cross_scale": ([_P, _P, _P, _P, _P, _I, _F], _I),
@@ -265,6 +266,11 @@ class Ctx:
         H, W, n = vm.shape
         check(self.L.sm_update_cost(self.h, _ptr(Lr), _ptr(vm), _ptr(bgr), H, W, n, v, u, rv, ru, int(pre_is_inner), thr, redu))
         return Lr
+
+    def vol_to_f32(self, vol):
+        out = self.empty(tuple(vol.shape), self.torch.float32)
+        check(self.L.sm_vol_to_f32(self.h, _ptr(vol), vol.element_size(), vol.numel(), _ptr(out)))
+        return out
 
     def lrc_mask(self, d1, d2, mask):
         H, W = d1.shape

@@ -142,3 +142,21 @@ extern "C" int sm_lrc_mask(sm_ctx* ctx, const int16_t* d_D1, const int16_t* d_D2
   SM_LAUNCH(ctx, k_lrc_mask, grid, 128, 0, d_D1, d_D2, H, W, d_mask);
   return SM_OK;
 }
+
+// costScan dispatches on vm.depth() in {CV_8U, CV_16U, CV_32F} (stereoMatching.cpp:2007-2021): updateCost<uchar> /
+// <ushort> read `T cost = vmPtr[d]` and add it to a float, i.e. they see the integer volume converted to float --
+// exactly what this conversion followed by the float sweep computes.
+template <typename T>
+__global__ void k_to_f32(const T* __restrict__ src, size_t n, float* __restrict__ dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = (float)src[i];
+}
+
+extern "C" int sm_vol_to_f32(sm_ctx* ctx, const void* d_src, int elem_bytes, size_t n, float* d_dst) {
+  SM_CHECK_ARG(ctx && d_src && d_dst && (elem_bytes == 1 || elem_bytes == 2));
+  const int grid = (int)min((size_t)ctx->num_sms * 16, (n + 255) / 256);
+  if (elem_bytes == 1) SM_LAUNCH(ctx, k_to_f32<uint8_t>, grid > 0 ? grid : 1, 256, 0, (const uint8_t*)d_src, n, d_dst);
+  else SM_LAUNCH(ctx, k_to_f32<uint16_t>, grid > 0 ? grid : 1, 256, 0, (const uint16_t*)d_src, n, d_dst);
+  return SM_OK;
+}

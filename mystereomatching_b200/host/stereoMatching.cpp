@@ -624,9 +624,22 @@ void StereoMatching::sgm(cv::Mat& vm_, bool leftFirst) {
 void StereoMatching::costScan(cv::Mat& Lr, cv::Mat& vm_, int rv, int ru, bool leftFirst) {
   const int path = sgm_path_index(rv, ru);
   CV_Assert(path >= 0);
-  CV_Assert(vm_.depth() == CV_32F);   // the ctor only ever allocates CV_32F (stereoMatching.cpp:2080)
   const size_t vb = (size_t)h_ * w_ * d_ * 4;
   ensure_vol(Lr, h_, w_, d_);
+  if (vm_.depth() == CV_8U || vm_.depth() == CV_16U) {
+    // the integer-cost entries (stereoMatching.cpp:2007-2014): updateCost<uchar> / <ushort> see the cost as a float
+    const size_t nel = (size_t)h_ * w_ * d_, eb = vm_.depth() == CV_8U ? 1 : 2;
+    CV_Assert(vm_.total() * vm_.channels() == nel);
+    TmpDev raw(ctx_, nel * eb), f(ctx_, vb);
+    upload(raw.p, vm_.data, nel * eb);
+    check(sm_vol_to_f32(ctx_, raw.p, (int)eb, nel, f.as<float>()), "sm_vol_to_f32");
+    check(sm_sgm_path(ctx_, f.as<float>(), leftFirst ? d_bgr_[0] : d_bgr_[1], h_, w_, d_, path, param_.sgm_corDifThres,
+                      param_.sgm_reduCoeffi1, 0, d_vol_[2]), "sm_sgm_path");
+    download(Lr.data, d_vol_[2], vb);
+    return;
+  }
+  if (vm_.depth() != CV_32F) throw cv::Exception("cost volumn's type is not reasonable");   // stereoMatching.cpp:2019
+
   const int idx = &vm_ == &vm[0] ? 0 : (&vm_ == &vm[1] ? 1 : -1);
   const float* src;
   TmpDev v(ctx_, idx >= 0 ? 16 : vb);

@@ -178,6 +178,11 @@ int main(int argc, char** argv) {
         for (int d = 0; d < D; d++) lr2.ptr<float>(H / 2, W / 2)[d] = -1.f;
         sm.updateCost<float>(lr2, cv0, H / 2, W / 2, D, 0, -1, true, true);
         dump(out + ".lr3_pixel.f32", lr2.data, npix * D * 4);
+        // costScan's integer-cost entry: the Hamming volume as CV_16U gives the same Lr as the float volume
+        cv::Mat cv16(3, sz, CV_16UC1), lr16;
+        for (size_t i = 0; i < npix * D; i++) cv16.ptr<ushort>()[i] = (ushort)cv0.ptr<float>()[i];
+        sm.costScan(lr16, cv16, 0, -1, true);
+        dump(out + ".lr3_u16.f32", lr16.data, npix * D * 4);
         cv::Mat mask(H, W, CV_8UC1, cv::Scalar::all(255));
         sm.LRConsistencyCheck_new(mask);
         dump(out + ".lrc_new.u8", mask.data, npix);

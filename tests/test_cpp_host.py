@@ -85,6 +85,7 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
         assert np.array_equal(parts.view(np.uint32), po.cbca(ad, aL, aR, 1, 0).view(np.uint32))
         # updateCost<float> at one pixel restores the wiped row of the path volume
         assert np.array_equal(np.fromfile(prefix + ".lr3_pixel.f32", np.float32).reshape(H, W, D), lr)
+        assert np.array_equal(np.fromfile(prefix + ".lr3_u16.f32", np.float32).reshape(H, W, D), lr)   # CV_16U entry
         # LRConsistencyCheck_new on the final DP[0] / DP[1]
         m = np.fromfile(prefix + ".lrc_new.u8", np.uint8).reshape(H, W)
         assert set(np.unique(m)) <= {0, 255} and (m == 0).any()

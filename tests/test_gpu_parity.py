@@ -138,6 +138,22 @@ def test_sgm_integer_cost_bit_exact(ctx):
     assert np.array_equal(got, ref)
 
 
+def test_sgm_u8_u16_cost_entries_bit_exact(ctx):
+    """costScan's CV_8U / CV_16U entries (updateCost<uchar> / <ushort>): the u16 Hamming volume written by
+    sm_cost_hamming_u16, converted on the device, gives exactly the float volume's SGM."""
+    H, W, D = 40, 70, 24
+    p = _pair(H, W, D, "random_dot")
+    cL, cR = po.census(p["grayL"]), po.census(p["grayR"])
+    dL, dR = ctx.dev(cL.view(np.int64)), ctx.dev(cR.view(np.int64))
+    v16 = ctx.cost_hamming(dL, dR, D, 3, 0, u16=True)
+    vf = ctx.vol_to_f32(v16)
+    ham = po.hamming_vol(cL, cR, D)
+    assert np.array_equal(vf.cpu().numpy(), ham)
+    v8 = ctx.dev(ham.astype(np.uint8))
+    assert np.array_equal(ctx.vol_to_f32(v8).cpu().numpy(), ham)
+    assert np.array_equal(ctx.sgm(vf, ctx.dev(p["bgrL"]), 8).cpu().numpy(), po.sgm(ham, p["bgrL"], 8))
+
+
 # ---------------------------------------------------------------- WTA / refine
 @pytest.mark.parametrize("shape", SHAPES)
 def test_wta_bit_exact(ctx, shape):
@@ -180,6 +196,10 @@ def test_region_vote_and_ipol_and_median_bit_exact(ctx):
     got = ctx.region_vote(ctx.dev(d.copy()), ctx.dev(arms.view(np.int16)), D).cpu().numpy()
     assert np.array_equal(got, ref)
     assert (ref != d).any()    # the test input must actually exercise the vote
+    for ratio, S in ((0.0, 5), (1.0, 5), (1.5, 5), (0.4, 0)):   # histogram path (mode always wins / never) and the unanimity path
+        ref_r = po.region_vote(d, arms, D, ratio, S)
+        got_r = ctx.region_vote(ctx.dev(d.copy()), ctx.dev(arms.view(np.int16)), D, ratio, S).cpu().numpy()
+        assert np.array_equal(got_r, ref_r), (ratio, S)
     ref = po.proper_ipol(d, p["bgrL"])
     got = ctx.proper_ipol(ctx.dev(d.copy()), ctx.dev(p["bgrL"])).cpu().numpy()
     assert np.array_equal(got, ref)
