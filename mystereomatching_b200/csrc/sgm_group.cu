@@ -144,19 +144,23 @@ __device__ __forceinline__ void g_sts4(uint32_t a, float v) { asm volatile("st.s
 __device__ __forceinline__ void g_pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // a row of D floats of this lane's run (quads beyond D read as FLT_MAX / are not written)
-template <int VPL>
+// QS: byte distance between the lane's quads.  16: the global layout (a run of VPL floats per lane; with VPL = 8 the
+// lanes of a quarter-warp sit 32 bytes apart, so every LDS.128 / STS.128 is a 2-way bank conflict -- unavoidable
+// for the TMA-staged C / S rows, which arrive in global order).  512: the exchange rows' own layout
+// [quad][lane][4]: a quad of all 32 lanes is 512 contiguous bytes, conflict-free.
+template <int VPL, int QS = 16>
 __device__ __forceinline__ void g_ldrow(uint32_t a, int nq, float (&x)[VPL]) {
 #pragma unroll
   for (int q = 0; q < VPL / 4; q++) {
-    float4 t = q < nq ? g_lds16(a + q * 16) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    float4 t = q < nq ? g_lds16(a + q * QS) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
     x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
   }
 }
-template <int VPL>
+template <int VPL, int QS = 16>
 __device__ __forceinline__ void g_strow(uint32_t a, int nq, const float (&x)[VPL]) {
 #pragma unroll
   for (int q = 0; q < VPL / 4; q++)
-    if (q < nq) g_sts16(a + q * 16, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+    if (q < nq) g_sts16(a + q * QS, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
 }
 // This lane's part of a neighbour CTA's published row (and the row minimum).  g_edge_issue starts the loads (at the
 // top of the row, so the L2 round trip overlaps the other two recurrences); g_edge_finish re-polls whatever still
@@ -229,6 +233,10 @@ __global__ void __launch_bounds__(448, NV)
   const int d0 = lane * VPL;
   const int nq = FULL ? VPL / 4 : (d0 < D ? min(VPL, D - d0) / 4 : 0);
   const uint32_t runB = (uint32_t)D * 4;
+  // exchange rows (written and read only by this kernel): conflict-free layout when a lane owns two quads
+  constexpr bool SWZ = FULL && VPL == 8;
+  constexpr int XQ = SWZ ? 512 : 16;
+  const uint32_t exOff = SWZ ? (uint32_t)lane * 16u : (uint32_t)d0 * 4u;
   constexpr int ob = UP ? -1 : +1, oc = -ob;   // predecessor column offsets of paths B and C (reference order)
 
   // shared memory: per warp NS stages {C run, S run}; exchange rows [path][buf][CW][D]; minima [path][buf][CW]
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(448, NV)
     g_ldrow<VPL>(st, nq, c);
     if (MODE >= 1) g_ldrow<VPL>(st + runB, nq, s);
     if (tl) tl[1] = g_now();
-    const uint32_t myB = exLo + bufOff + (uint32_t)warp * runB + d0 * 4, myC = myB + exPathB;
+    const uint32_t myB = exLo + bufOff + (uint32_t)warp * runB + exOff, myC = myB + exPathB;
     const uint32_t myMinB = minLo + mbufOff + (uint32_t)warp * 4, myMinC = myMinB + minPathB;
     if (r == 0) {   // first row of the sweep: no predecessor inside the image -> Lr = C on all three paths
       const float m = g_rowmin<VPL>(c);
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(448, NV)
       for (int j = 0; j < VPL; j++) lrA[j] = lrB[j] = lrC[j] = c[j];
       minA = m;
       if (!special) {
-        g_strow<VPL>(myB, nq, c); g_strow<VPL>(myC, nq, c);
+        g_strow<VPL, XQ>(myB, nq, c); g_strow<VPL, XQ>(myC, nq, c);
         if (lane == 0) { g_sts4(myMinB, m); g_sts4(myMinC, m); }
       } else {
         if (nbrCta) {
@@ -322,14 +330,14 @@ __global__ void __launch_bounds__(448, NV)
             if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]));
           if (lane == 0) __stcg(pubRow + D, m);
         }
-        g_strow<VPL>(nearIsB ? myC : myB, nq, c);
+        g_strow<VPL, XQ>(nearIsB ? myC : myB, nq, c);
         if (lane == 0) g_sts4(nearIsB ? myMinC : myMinB, m);
       }
     } else if (!special) {
       // interior column: three independent recurrences, all fed from registers / shared memory
       float prB[VPL], prC[VPL];
-      g_ldrow<VPL>(exLo + pbufOff + (uint32_t)(warp + ob) * runB + d0 * 4, nq, prB);
-      g_ldrow<VPL>(exLo + exPathB + pbufOff + (uint32_t)(warp + oc) * runB + d0 * 4, nq, prC);
+      g_ldrow<VPL, XQ>(exLo + pbufOff + (uint32_t)(warp + ob) * runB + exOff, nq, prB);
+      g_ldrow<VPL, XQ>(exLo + exPathB + pbufOff + (uint32_t)(warp + oc) * runB + exOff, nq, prC);
       const float pmB = g_lds4(minLo + mpbufOff + (uint32_t)(warp + ob) * 4);
       const float pmC = g_lds4(minLo + minPathB + mpbufOff + (uint32_t)(warp + oc) * 4);
       float mB, mC, mA;
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(448, NV)
       g_lr<VPL>(c, prB, pmB, (int)smd_absdiff_max3(xrow, xpB) > corDifThres, P1r, P2r, lane, lrB, mB);
       g_lr<VPL>(c, prC, pmC, (int)smd_absdiff_max3(xrow, xpC) > corDifThres, P1r, P2r, lane, lrC, mC);
       minA = mA;
-      g_strow<VPL>(myB, nq, lrB); g_strow<VPL>(myC, nq, lrC);
+      g_strow<VPL, XQ>(myB, nq, lrB); g_strow<VPL, XQ>(myC, nq, lrC);
       if (lane == 0) { g_sts4(myMinB, mB); g_sts4(myMinC, mC); }
     } else {
       // edge column.  The far diagonal's previous row is requested first and used last: the neighbour CTA stored it
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(448, NV)
       //  register set is copied at the loop head, which waits for the loads in flight)
       if (nbrCta) g_edge_issue<VPL>(farRow, nq, D - d0, er);
       const uint32_t nearPath = nearIsB ? 0u : exPathB, nearMin = nearIsB ? 0u : minPathB;
-      g_ldrow<VPL>(exLo + nearPath + pbufOff + (uint32_t)(warp + nearOff) * runB + d0 * 4, nq, prN);
+      g_ldrow<VPL, XQ>(exLo + nearPath + pbufOff + (uint32_t)(warp + nearOff) * runB + exOff, nq, prN);
       const float pmN = g_lds4(minLo + nearMin + mpbufOff + (uint32_t)(warp + nearOff) * 4);
       const uint32_t xpN = nearIsB ? xpB : xpC, xpF = nearIsB ? xpC : xpB;
       g_lr<VPL>(c, prN, pmN, (int)smd_absdiff_max3(xrow, xpN) > corDifThres, P1r, P2r, lane, lrN, mN);
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(448, NV)
         for (int j = 0; j < VPL; j++) lrF[j] = c[j];
         mF = g_rowmin<VPL>(c);
       }
-      g_strow<VPL>(nearIsB ? myC : myB, nq, lrF);
+      g_strow<VPL, XQ>(nearIsB ? myC : myB, nq, lrF);
       if (lane == 0) g_sts4(nearIsB ? myMinC : myMinB, mF);
 #pragma unroll
       for (int j = 0; j < VPL; j++) { lrB[j] = nearIsB ? lrN[j] : lrF[j]; lrC[j] = nearIsB ? lrF[j] : lrN[j]; }
