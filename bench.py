@@ -42,15 +42,20 @@ WORKLOADS = {
     "c3": (1920, 1080, 256, 8, "texture_warped"),
     "c4": (640, 480, 64, 4, "texture_warped"),       # NL non-local MST aggregation instead of CBCA
     "c3cg": (1920, 1080, 256, 8, "texture_warped"),  # c3 with the cost main_.cpp:15 compiles in: censusGrad
+    "c3main": (1920, 1080, 256, 8, "texture_warped"),  # the reference's main() as compiled: censusGrad + SolveAll(PY_LEV 1, 0.3)
+    "c3py3": (1920, 1080, 256, 8, "texture_warped"),   # c3 with the caller's cross-scale step over a 3-level pyramid
 }
-AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2, "c3cg": 1}
-COSTCALC = {"c3cg": 1}        # 0 = AD-Census (BASELINE configs), 1 = censusGrad
+AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2, "c3cg": 1, "c3main": 1, "c3py3": 1}
+COSTCALC = {"c3cg": 1, "c3main": 1}        # 0 = AD-Census (BASELINE configs), 1 = censusGrad
+PYRAMID = {"c3main": (1, 0.3), "c3py3": (3, 0.3)}   # (PY_LEV, REG_LAMBDA) of main_.cpp:132, 157; absent: no SolveAll
 
 
 def workload_desc(name):
     W, H, D, P, kind = WORKLOADS[name]
     agg = "CBCA(2 it, intersected arms)" if AGGREGATION[name] == 1 else "NL(MST tree filter, sigma 0.1, left view)"
     cost = "censusGrad(71-bit census + arm-weighted x/y gradient)" if COSTCALC.get(name, 0) else "AD-Census(71-bit)"
+    if name in PYRAMID:
+        agg += f"+SolveAll({PYRAMID[name][0]} level(s), lambda {PYRAMID[name][1]})"
     return (f"{name}: {W}x{H} D={D} {cost}+{agg}+{P}-path SGM+WTA+LRC+"
             f"regionVote x2+properIpol x2+median3, 2 views, fp32 volumes, synthetic {kind} pairs")
 
@@ -127,7 +132,9 @@ def run_oracle(pair, name, threads):
     from oracle import pyoracle as po
     W, H, D, P, kind = WORKLOADS[name]
     po.lib().orc_set_threads(threads)
-    op = po.default_params(D, paths=P, aggregation=AGGREGATION[name], costcalc=COSTCALC.get(name, 0))
+    lv, lam = PYRAMID.get(name, (1, -1.0))
+    op = po.default_params(D, paths=P, aggregation=AGGREGATION[name], costcalc=COSTCALC.get(name, 0), pyr_levels=lv,
+                           cross_lambda=lam)
     t0 = time.perf_counter()
     _, _, _, ms = po.pipeline(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], op)
     return time.perf_counter() - t0, ms
@@ -172,7 +179,10 @@ def run_reference(name, rows, threads, seed0=1000):
 
     def work(p):
         r = po.SmRef(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D)
-        r.pipeline(P, 2, costcalc=COSTCALC.get(name, 0))   # ctypes releases the GIL for the duration of the call
+        if name in PYRAMID:
+            r.pipeline_pyr(PYRAMID[name][0], PYRAMID[name][1], P, 2, COSTCALC.get(name, 0))
+        else:
+            r.pipeline(P, 2, costcalc=COSTCALC.get(name, 0))   # ctypes releases the GIL for the duration of the call
         r.close()
 
     ts = [threading.Thread(target=work, args=(p,)) for p in pairs]
@@ -317,8 +327,9 @@ def main_ours(args):
     name = args.workload
     W, H, D, P, kind = WORKLOADS[name]
     ctx = capi.Ctx(local)
+    lv, lam = PYRAMID.get(name, (1, -1.0))
     params = capi.default_params(D - 1, sgm_paths=P, aggregation=AGGREGATION[name],
-                                 costcalculation=COSTCALC.get(name, 0))
+                                 costcalculation=COSTCALC.get(name, 0), pyramidLevels=lv, crossScaleLambda=lam)
     pl = capi.Pipeline(ctx, H, W, params)
 
     # frames of this rank: frame i of the stream uses seed 1000+i, frame i -> rank i mod N

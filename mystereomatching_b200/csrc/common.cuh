@@ -95,8 +95,9 @@ int smi_exp_tables(sm_ctx* ctx, float trunc, float lamAD, float lamCen, int code
 int smi_cost_adcensus_packed(sm_ctx* ctx, const uint32_t* d_pixL, const uint32_t* d_pixR, const uint64_t* d_cenL,
                              const uint64_t* d_cenR, int H, int W, int D, int func, float adTrunc, float lamAD,
                              float lamCen, int LOR, float* d_vol);
+// postScale != 1: the last pass also applies the caller's one-level SolveAll (vm = 0 + postScale * vm)
 int smi_cbca_packed(sm_ctx* ctx, float* d_vol, float* d_tmp, const uint32_t* d_armL, const uint32_t* d_armR, int H,
-                    int W, int D, int iters, int view, int Lmax, int PAD);
+                    int W, int D, int iters, int view, int Lmax, int PAD, float postScale = 1.0f);
 int smi_arms_packed(sm_ctx* ctx, const uint32_t* d_pix, int H, int W, int L, int L_out, int tau, int tau_out, int minL,
                     uint16_t* d_arms);
 int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D);

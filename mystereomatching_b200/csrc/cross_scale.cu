@@ -108,23 +108,31 @@ struct cs_levels {
   float w[SM_MAX_PYRAMID];
 };
 
+// One CTA walks pixels (grid-stride), its threads run along d: coalesced level-0 accesses, no per-element division
+// (the first version's 64-bit i / D, i % D, % W made it issue-bound at 1.1 TB/s; this one: see DESIGN.md).
 template <int LEVELS>
-__global__ void k_cross_scale(float* __restrict__ vol0, cs_levels L, int H, int W, int D) {
-  const size_t n = (size_t)H * W * D;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const int d = (int)(i % D);
-    const size_t pxl = i / D;
-    const int x = (int)(pxl % W), y = (int)(pxl / W);
-    float sum = __fadd_rn(0.f, __fmul_rn(L.w[0], vol0[i]));
-    int cy = y, cx = x, cd = d;
+__global__ void __launch_bounds__(256) k_cross_scale(float* __restrict__ vol0, cs_levels L, int H, int W, int D) {
+  const int npix = H * W;
+  for (int p = blockIdx.x; p < npix; p += gridDim.x) {
+    const int y = p / W, x = p - y * W;
+    const float* src[LEVELS];
+    int cy = y, cx = x;
 #pragma unroll
     for (int s = 1; s < LEVELS; s++) {
-      cy >>= 1; cx >>= 1; cd = (cd + 1) >> 1;
-      sum = __fadd_rn(sum, __fmul_rn(L.w[s], L.vol[s][((size_t)cy * L.W[s] + cx) * L.D[s] + cd]));
+      cy >>= 1; cx >>= 1;
+      src[s] = L.vol[s] + ((size_t)cy * L.W[s] + cx) * L.D[s];
     }
-    vol0[i] = sum;
+    float* o = vol0 + (size_t)p * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float sum = __fadd_rn(0.f, __fmul_rn(L.w[0], o[d]));
+      int cd = d;
+#pragma unroll
+      for (int s = 1; s < LEVELS; s++) {
+        cd = (cd + 1) >> 1;
+        sum = __fadd_rn(sum, __fmul_rn(L.w[s], src[s][cd]));
+      }
+      o[d] = sum;
+    }
   }
 }
 
@@ -140,16 +148,18 @@ extern "C" int sm_cross_scale(sm_ctx* ctx, float* const* d_vols, const int* Hs, 
     }
     L.vol[s] = d_vols[s]; L.W[s] = Ws[s]; L.D[s] = Ds[s];
   }
-  const size_t n = (size_t)Hs[0] * Ws[0] * Ds[0];
-  const int grid = (int)min((size_t)ctx->num_sms * 16, (n + 255) / 256);
+  SM_CHECK_ARG((long long)Hs[0] * Ws[0] < (1ll << 31));
+  const int npix = Hs[0] * Ws[0];
+  const int block = Ds[0] >= 192 ? 256 : (Ds[0] >= 96 ? 128 : (Ds[0] >= 48 ? 64 : 32));
+  const int grid = min(npix, ctx->num_sms * (2048 / block));
   float* v0 = d_vols[0];
   switch (levels) {
-    case 1: SM_LAUNCH(ctx, k_cross_scale<1>, grid, 256, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
-    case 2: SM_LAUNCH(ctx, k_cross_scale<2>, grid, 256, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
-    case 3: SM_LAUNCH(ctx, k_cross_scale<3>, grid, 256, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
-    case 4: SM_LAUNCH(ctx, k_cross_scale<4>, grid, 256, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
-    case 5: SM_LAUNCH(ctx, k_cross_scale<5>, grid, 256, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
-    default: SM_LAUNCH(ctx, k_cross_scale<SM_MAX_PYRAMID>, grid, 256, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
+    case 1: SM_LAUNCH(ctx, k_cross_scale<1>, grid, block, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
+    case 2: SM_LAUNCH(ctx, k_cross_scale<2>, grid, block, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
+    case 3: SM_LAUNCH(ctx, k_cross_scale<3>, grid, block, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
+    case 4: SM_LAUNCH(ctx, k_cross_scale<4>, grid, block, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
+    case 5: SM_LAUNCH(ctx, k_cross_scale<5>, grid, block, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
+    default: SM_LAUNCH(ctx, k_cross_scale<SM_MAX_PYRAMID>, grid, block, 0, v0, L, Hs[0], Ws[0], Ds[0]); break;
   }
   return SM_OK;
 }

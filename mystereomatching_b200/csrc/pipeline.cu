@@ -29,7 +29,7 @@ struct sm_pipeline {
   int16_t* h_out = nullptr;  // pinned staging: dispL | dispR
   sm_pipeline* child = nullptr;   // next pyramid level (cost + aggregation only), pyramidLevels > 1
   bool is_child = false;
-  bool have_gray = false, have_arms = false;
+  bool have_gray = false, have_arms = false, scale_folded = false;
   bool stage_used = false, stage_drained = true;
   bool timing = false;
   cudaEvent_t ev[ST_COUNT + 1];
@@ -211,9 +211,17 @@ static int pl_cost_calculate(sm_pipeline* pl) {
     SM_TRY(ensure_arms());
     PL_MARK(3);
     const int Lmax = max(1, max(P.cbca_crossL_out, P.cbca_minArmL));
+    // a one-level SolveAll (the reference's main() as compiled: PY_LEV = 1) is a plain scale of vm: folded into the
+    // last CBCA pass (same two rounded operations per element, one pass over the volume less)
+    pl->scale_folded = false;
+    float post = 1.0f;
+    if (!pl->is_child && !pl->child && P.crossScaleLambda >= 0.f && P.cbca_iterationNum >= 1 && views == (P.Do_refine ? 2 : 1)) {
+      SM_TRY(sm_cross_scale_weights(1, P.crossScaleLambda, &post));
+      pl->scale_folded = post != 1.0f;
+    }
     for (int i = 0; i < views; i++)
       SM_TRY(smi_cbca_packed(c, pl->vol[i], pl->vol[2], pl->armpk[0], pl->armpk[1], H, W, D, P.cbca_iterationNum, i,
-                             Lmax, smi_arm_pad(D)));
+                             Lmax, smi_arm_pad(D), post));
   } else if (P.aggregation == 2) {
     PL_MARK(3);
     SM_TRY(smi_nl(c, pl->bgr[0], pl->vol[0], pl->nlwork, H, W, D));
@@ -232,8 +240,9 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   SM_CUDA(cudaSetDevice(c->device));
   const int views = (P.Do_refine && P.Do_LRConsis) ? 2 : 1;  // stereoMatching.cpp:1054, 5592
   auto ensure_arms = [&]() -> int { return pl_ensure_arms(pl); };
+  pl->scale_folded = false;
   SM_TRY(pl_cost_calculate(pl));
-  if (P.crossScaleLambda >= 0.f) {
+  if (P.crossScaleLambda >= 0.f && !pl->scale_folded) {
     // the caller's pyramid loop + SolveAll (main_.cpp:131-158, stereoMatching.cpp:2142-2208)
     float* vols[2][SM_MAX_PYRAMID];
     int Hs[SM_MAX_PYRAMID], Ws[SM_MAX_PYRAMID], Ds[SM_MAX_PYRAMID], levels = 0;

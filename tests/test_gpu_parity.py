@@ -250,6 +250,25 @@ def test_pipeline_matches_oracle(ctx, cfg):
     pl.close()
 
 
+@pytest.mark.parametrize("paths", [4, 8])
+def test_pipeline_one_level_solve_all_folded_into_cbca_is_bit_exact(ctx, paths):
+    """main() as the reference compiles it (PY_LEV = 1, REG_LAMBDA = 0.3): the scale 1/(1+lambda) rides in the last
+    CBCA pass; the volume after SGM (reference path order) and the map must equal the oracle's bit for bit."""
+    H, W, D = 70, 120, 40
+    p = _pair(H, W, D, "texture_warped", seed=41)
+    params = capi.default_params(D - 1, sgm_paths=paths, sgm_grouped=0, crossScaleLambda=0.3, pyramidLevels=1)
+    pl = capi.Pipeline(ctx, H, W, params)
+    pl.upload(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"])
+    pl.run_device()
+    dl, _ = pl.download(want_right=True)
+    vol = pl.buffer(0, (H, W, D), torch.float32).cpu().numpy()
+    pl.close()
+    op = po.default_params(D, paths=paths, pyr_levels=1, cross_lambda=0.3)
+    rl, _, rvol, _ = po.pipeline(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], op, want_vol=True)
+    assert _bits_equal(vol, rvol)
+    assert np.array_equal(dl, rl)
+
+
 def test_pipeline_region_of_validity_errors(ctx):
     with pytest.raises(capi.SmError):
         capi.Pipeline(ctx, 10, 10, capi.default_params(600))       # D > 512 (CV_CN_MAX)
