@@ -366,6 +366,14 @@ def main_ours(args):
     pl.upload(*host_args(0))
     for _ in range(args.warmup):
         pl.run_device()
+    # clocks and power state settle over a few hundred ms of load: keep warming (untimed) until ~0.5 s has been spent
+    extra_warm = 0
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.5 and extra_warm < 40:
+        pl.run_device()
+        torch.cuda.synchronize()
+        extra_warm += 1
     pl.enable_timing(True)
     stage_acc = {}
     barrier()
@@ -443,6 +451,7 @@ def main_ours(args):
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": workload_desc(name), "frames_per_step_per_gpu": 1,
+                          "extra_untimed_warmup_steps": extra_warm,
                           "parallelism": f"frame-parallel x{world}, no collective",
                           "l2": "inputs larger than L2: each pass streams 2.1 GB volumes (L2 = 126 MB)"},
                "e2e": {"value": e2e_val, "unit": "MDE/s", "fps": e2e_val * 1e6 / (W * H * D),
