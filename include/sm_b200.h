@@ -314,6 +314,12 @@ int sm_vol_to_f32(sm_ctx* ctx, const void* d_src, int elem_bytes, size_t n, floa
 /* LRConsistencyCheck_new (stereoMatching.cpp:2367-2382): mask[v][u] = 0 where the left-right check fails (Thres 0). */
 int sm_lrc_mask(sm_ctx* ctx, const int16_t* d_D1, const int16_t* d_D2, int H, int W, uint8_t* d_mask);
 
+/* calErr<short> (stereoMatching.h:1748-1825): over mask == 255: *h_sumNum pixels, *h_errorNum of them with
+ * |gt - disp| > thres or disp < 0, *h_errorValueSum = sum of dif^2 (2 for an invalid pixel).  PBM = errorNum / sumNum,
+ * RMS = sqrt(errorValueSum / sumNum).  Synchronous (returns host values). */
+int sm_cal_err(sm_ctx* ctx, const int16_t* d_disp, const float* d_gt, const uint8_t* d_mask, int H, int W, int thres,
+               long long* h_sumNum, long long* h_errorNum, double* h_errorValueSum);
+
 /* ---- whole frame ------------------------------------------------------------ */
 /* A frame pipeline owns every device buffer a W x H x D frame needs (three
  * volumes, codes, arms, images, disparities) so a stream of frames reuses them.

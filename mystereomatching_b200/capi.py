@@ -69,6 +69,7 @@ SIGNATURES = {
     "sm_update_cost": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I], _I),
     "sm_lrc_mask": ([_P, _P, _P, _I, _I, _P], _I),
     "sm_vol_to_f32": ([_P, _P, _I, _Z, _P], _I),
+    "sm_cal_err": ([_P, _P, _P, _P, _I, _I, _I, C.POINTER(_LL), C.POINTER(_LL), C.POINTER(_D)], _I),
     "sm_pyr_down_u8": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_cross_scale_weights": ([_I, _F, _P], _I),
     "sm_cross_scale": ([_P, _P, _P, _P, _P, _I, _F], _I),
@@ -271,6 +272,14 @@ class Ctx:
         out = self.empty(tuple(vol.shape), self.torch.float32)
         check(self.L.sm_vol_to_f32(self.h, _ptr(vol), vol.element_size(), vol.numel(), _ptr(out)))
         return out
+
+    def cal_err(self, disp, gt, mask, thres=1):
+        """calErr: returns (PBM, RMS, sumNum, errorNum) over mask == 255."""
+        H, W = disp.shape
+        a, b, e = _LL(0), _LL(0), _D(0.0)
+        check(self.L.sm_cal_err(self.h, _ptr(disp), _ptr(gt), _ptr(mask), H, W, thres, C.byref(a), C.byref(b), C.byref(e)))
+        n = max(a.value, 1)
+        return b.value / n, (e.value / n) ** 0.5, a.value, b.value
 
     def lrc_mask(self, d1, d2, mask):
         H, W = d1.shape

@@ -160,3 +160,55 @@ extern "C" int sm_vol_to_f32(sm_ctx* ctx, const void* d_src, int elem_bytes, siz
   else SM_LAUNCH(ctx, k_to_f32<uint16_t>, grid > 0 ? grid : 1, 256, 0, (const uint16_t*)d_src, n, d_dst);
   return SM_OK;
 }
+
+// calErr<short> (stereoMatching.h:1748-1825), the evaluation the reference prints after every stage: over the pixels
+// of a region mask (== 255): sumNum, errorNumer (|DT - DP| > THRES, or DP < 0) and errorValueSum (dif^2, or 2 for an
+// invalid pixel).  The two counts are exact; the reference accumulates the squared error in a float sequentially,
+// here it is a double sum over block partials (agrees to ~1e-7 relative).
+__global__ void k_cal_err(const int16_t* __restrict__ dp, const float* __restrict__ dt, const uint8_t* __restrict__ mask,
+                          long long n, int thres, unsigned long long* __restrict__ counts, double* __restrict__ esum) {
+  unsigned long long c0 = 0, c1 = 0;
+  double e = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (mask[i] != 255) continue;
+    c0++;
+    const int d = dp[i];
+    if (d >= 0) {
+      const float dif = fabsf(__fsub_rn(dt[i], (float)d));
+      e += (double)dif * (double)dif;     // pow(dif, 2) is evaluated in double
+      if (dif > (float)thres) c1++;
+    } else {
+      c1++;
+      e += 2.0;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c0) atomicAdd(&counts[0], c0);
+    if (c1) atomicAdd(&counts[1], c1);
+    if (e != 0.0) atomicAdd(esum, e);
+  }
+}
+
+extern "C" int sm_cal_err(sm_ctx* ctx, const int16_t* d_disp, const float* d_gt, const uint8_t* d_mask, int H, int W,
+                          int thres, long long* h_sumNum, long long* h_errorNum, double* h_errorValueSum) {
+  SM_CHECK_ARG(ctx && d_disp && d_gt && d_mask && H > 0 && W > 0 && h_sumNum && h_errorNum && h_errorValueSum);
+  void* p;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_MISC0, 64, &p));
+  SM_CUDA(cudaMemsetAsync(p, 0, 24, ctx->stream));
+  const long long n = (long long)H * W;
+  const int grid = (int)min((long long)ctx->num_sms * 4, (n + 255) / 256);
+  SM_LAUNCH(ctx, k_cal_err, grid, 256, 0, d_disp, d_gt, d_mask, n, thres, (unsigned long long*)p,
+            (double*)((char*)p + 16));
+  unsigned long long h[3];
+  SM_CUDA(cudaMemcpyAsync(h, p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+  SM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *h_sumNum = (long long)h[0];
+  *h_errorNum = (long long)h[1];
+  memcpy(h_errorValueSum, &h[2], 8);
+  return SM_OK;
+}

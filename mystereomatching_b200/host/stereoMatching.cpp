@@ -2,6 +2,9 @@
 // Each method names the reference body it replaces (file:line under the reference root) in stereoMatching.h.
 #include "stereoMatching.h"
 
+#include <cmath>
+#include <iostream>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -488,6 +491,33 @@ void StereoMatching::updateCost(cv::Mat& Lr, cv::Mat& vm_, int v, int u, int n, 
   download(Lr.data, l.p, nv * 4);
 }
 template void StereoMatching::updateCost<float>(cv::Mat&, cv::Mat&, int, int, int, int, int, bool, bool);
+
+template <typename T>
+void StereoMatching::calErr(Mat& DP_, Mat& DT_, string procedure, bool calCSV) {
+  (void)calCSV;
+  static_assert(sizeof(T) == sizeof(short), "the path evaluates CV_16S disparity maps (stereoMatching.cpp:1128)");
+  CV_Assert(DP_.depth() == CV_16S && DT_.depth() == CV_32F && DP_.rows == h_ && DP_.cols == w_ && DT_.rows == h_ && DT_.cols == w_);
+  const size_t n = (size_t)h_ * w_;
+  TmpDev d(ctx_, n * 2), g(ctx_, n * 4), m(ctx_, n);
+  upload(d.p, DP_.data, n * 2); upload(g.p, DT_.data, n * 4);
+  static const char* names[3] = {"nonocc", "all", "disc"};
+  for (int region = 0; region < 3; region++) {
+    lastErr[region] = ErrPair();
+    if (region >= (int)I_mask.size() || I_mask[region].empty()) continue;
+    CV_Assert(I_mask[region].depth() == CV_8U && I_mask[region].rows == h_ && I_mask[region].cols == w_);
+    upload(m.p, I_mask[region].data, n);
+    long long sumNum = 0, errorNumer = 0;
+    double esum = 0.0;
+    check(sm_cal_err(ctx_, d.as<int16_t>(), g.as<float>(), m.as<uint8_t>(), h_, w_, param_.errorThreshold, &sumNum, &errorNumer,
+                     &esum), "sm_cal_err");
+    lastErr[region].PBM = (float)errorNumer / sumNum;
+    lastErr[region].RMS = std::sqrt((float)esum / sumNum);
+    lastErr[region].valid = true;
+    std::cout << std::endl << names[region] << "\terrorRatio: " << lastErr[region].PBM << " epe: " << lastErr[region].RMS
+              << " " + procedure << std::endl;   // stereoMatching.h:1797
+  }
+}
+template void StereoMatching::calErr<short>(Mat&, Mat&, string, bool);
 
 void StereoMatching::LRConsistencyCheck_new(Mat& errorMask) {
   CV_Assert(errorMask.depth() == CV_8U && errorMask.rows == h_ && errorMask.cols == w_);

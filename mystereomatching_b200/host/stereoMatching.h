@@ -149,6 +149,15 @@ class StereoMatching {
   void regionVote_my(cv::Mat& Dp, float rv_ratio, int rv_s);                            // stereoMatching.cpp:7219-7277
   void properIpol(cv::Mat& Dp, cv::Mat& I1_c);                                          // stereoMatching.cpp:7395-7490
 
+  // ---- evaluation (stereoMatching.h:1748-1825).  Same arithmetic and the same console line per region
+  // ("nonocc" / "all" / "disc" = I_mask[0..2], skipped when empty); the reference also appends to
+  // param_.savePath + err_name and to the CSV stream -- file output is outside the path, the numbers are kept in
+  // lastErr instead (addition): lastErr[region] = {PBM, RMS}.
+  template <typename T>
+  void calErr(Mat& DP, Mat& DT, string procedure, bool calCSV = false);
+  struct ErrPair { float PBM = 0.f, RMS = 0.f; bool valid = false; };
+  ErrPair lastErr[3];
+
   // ---- device <-> host mirroring (additions; everything above is the reference's surface)
   void syncToHost(bool volumes = true);   // refresh vm[], HVL[], DP[] host Mats from the device
   Mat& hostDP(int i);                     // DP[i], refreshed if stale

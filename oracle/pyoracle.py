@@ -80,6 +80,7 @@ def lib():
         "orc_proper_ipol": ([i16p, u8p, I, I, I], None),
         "orc_median3_i16": ([i16p, I, I, i16p], None),
         "orc_solve_all_1level": ([f32p, C.c_long, F], None),
+        "orc_cal_err": ([i16p, f32p, u8p, I, I, I, f32p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")], None),
         "orc_pyr_down_u8": ([u8p, I, I, I, u8p], None),
         "orc_cross_scale_weights": ([I, F, f32p], None),
         "orc_solve_all": ([C.POINTER(C.c_void_p), i32p, i32p, i32p, I, F], None),
@@ -190,6 +191,15 @@ def censusgrad_vol(bgrL, bgrR, grayL, grayR, D, view=0, func=3, lamCen=13.0, lam
     ham = hamming_vol(cl, cr, D, func, view)
     a = arms(bgrL if view == 0 else bgrR)
     return combine_exp(ham, grad_vol(grayL, grayR, a, D, view, trunc), lamCen, lamG)
+
+
+def cal_err(dp, gt, mask, thres=1):
+    """calErr<short> (stereoMatching.h:1748-1825): (PBM, RMS, sumNum, errorNum) over mask == 255."""
+    H, W = dp.shape
+    out, cnt = np.empty(2, np.float32), np.empty(2, np.int64)
+    lib().orc_cal_err(np.ascontiguousarray(dp, np.int16), np.ascontiguousarray(gt, np.float32),
+                      np.ascontiguousarray(mask, np.uint8), H, W, thres, out, cnt)
+    return float(out[0]), float(out[1]), int(cnt[0]), int(cnt[1])
 
 
 def pyr_down(img):

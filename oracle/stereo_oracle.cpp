@@ -646,6 +646,30 @@ void orc_solve_all_1level(float* vol, long n, float lambda) {
   for (long i = 0; i < n; i++) { float sum = 0; sum += inv * vol[i]; vol[i] = sum; }
 }
 
+// calErr<short> (stereoMatching.h:1748-1825) for one region mask: float accumulation of pow(dif, 2) in pixel order,
+// invalid pixels (DP < 0) count as errors and add 2.  out[0] = PBM, out[1] = rms, counts[0] = sumNum, [1] = errorNumer.
+void orc_cal_err(const i16* dp, const float* dt, const u8* mask, int H, int W, int thres, float* out, long* counts) {
+  int sumNum = 0, errorNumer = 0;
+  float errorValueSum = 0;
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      const long i = (long)v * W + u;
+      if (mask[i] != 255) continue;
+      sumNum++;
+      if (dp[i] >= 0) {
+        float dif = std::abs(dt[i] - dp[i]);
+        errorValueSum += std::pow(dif, 2);
+        if (dif > thres) errorNumer++;
+      } else {
+        errorNumer++;
+        errorValueSum += 2;
+      }
+    }
+  out[0] = (float)errorNumer / sumNum;
+  out[1] = std::sqrt(errorValueSum / sumNum);
+  counts[0] = sumNum; counts[1] = errorNumer;
+}
+
 // ---------------------------------------------------------------------------
 // Cross-scale step of the caller: the pyramid loop of main_.cpp:131-158 and
 // SolveAll (stereoMatching.cpp:2142-2208).

@@ -122,6 +122,16 @@ int main(int argc, char** argv) {
     sm.setSgmPaths(paths);
     if (mode == "pipeline") {
       sm.pipeline();
+      // calErr on the refined map against a synthetic truth (= the map itself shifted by one on a stripe), "all" mask
+      sm.syncToHost(false);
+      cv::Mat gtm(H, W, CV_32FC1), all(H, W, CV_8UC1, cv::Scalar::all(255));
+      for (int v = 0; v < H; v++)
+        for (int u = 0; u < W; u++) gtm.ptr<float>(v)[u] = (float)sm.DP[0].ptr<short>(v)[u] + (u % 7 == 0 ? 2.f : 0.f);
+      sm.I_mask[1] = all;
+      sm.DT = gtm;
+      sm.calErr<short>(sm.DP[0], sm.DT, "final");
+      float e[2] = {sm.lastErr[1].PBM, sm.lastErr[1].RMS};
+      dump(out + ".err_all.f32", e, sizeof(e));
     } else if (mode == "censusgrad") {
       // the gradient family through its explicit-argument forms, then the whole chain with the reference's own selectors
       std::vector<cv::Mat> g(2), gy(2);

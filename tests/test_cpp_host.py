@@ -28,7 +28,7 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
                 "StereoMatching::gen1DCumu(", "StereoMatching::cal1DCost(", "StereoMatching::genfinalVm_cbca(",
                 "void StereoMatching::updateCost<float>(", "StereoMatching::LRConsistencyCheck_new(",
-                "SolveAll(StereoMatching**&, int, float)", "pyrDown_u8(", "StereoMatching::censusGrad(", "StereoMatching::grad(", "StereoMatching::calGrad(",
+                "void StereoMatching::calErr<short>(", "SolveAll(StereoMatching**&, int, float)", "pyrDown_u8(", "StereoMatching::censusGrad(", "StereoMatching::grad(", "StereoMatching::calGrad(",
                 "StereoMatching::calGrad_y(", "StereoMatching::calgradvm(",
                 "void StereoMatching::calHorVerDis<unsigned char>(", "void StereoMatching::calArms<unsigned char>(",
                 "NLCCA::aggreCV(", "qx_tree_filter::filter(double*, double*, int)", "qx_tree_filter::build_tree(",
@@ -63,6 +63,11 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
     assert (dp == ref).mean() >= 0.995
     hvl = np.fromfile(prefix + ".hvl0.u16", np.uint16).reshape(H, W, 5)
     assert np.array_equal(hvl, po.arms(pair["bgrL"]))
+    if mode == "pipeline":
+        gt = dp.astype(np.float32) + np.where(np.arange(W)[None, :] % 7 == 0, 2.0, 0.0).astype(np.float32)
+        pbm, rms, _, _ = po.cal_err(dp, gt, np.full((H, W), 255, np.uint8), 1)
+        e = np.fromfile(prefix + ".err_all.f32", np.float32)
+        assert abs(e[0] - pbm) < 1e-6 and abs(e[1] - rms) <= 1e-5 * rms and pbm > 0
     if mode == "stages":
         aL, aR = po.arms(pair["bgrL"]), po.arms(pair["bgrR"])
         cost = po.adcensus_vol(pair["bgrL"], pair["bgrR"], pair["grayL"], pair["grayR"], D, 0)

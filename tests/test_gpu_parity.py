@@ -269,6 +269,22 @@ def test_pipeline_one_level_solve_all_folded_into_cbca_is_bit_exact(ctx, paths):
     assert np.array_equal(dl, rl)
 
 
+def test_cal_err_matches_oracle(ctx):
+    """calErr<short>: the two counts are exact, the RMS agrees to float accumulation accuracy."""
+    H, W, D = 90, 140, 32
+    p, d = _noisy_disp(H, W, D, 33)
+    d[5:9, 7:30] += 3                                   # some errors above the threshold
+    gt = p["gt"].astype(np.float32) + 0.25
+    for mask_key, thres in (("nonocc", 1), ("all", 1), ("nonocc", 2)):
+        mask = (p[mask_key].astype(np.uint8) * 255) if p[mask_key].dtype == np.bool_ else p[mask_key].astype(np.uint8)
+        if mask.max() == 1:
+            mask = mask * 255
+        ref = po.cal_err(d, gt, mask, thres)
+        got = ctx.cal_err(ctx.dev(d), ctx.dev(gt), ctx.dev(mask), thres)
+        assert got[2] == ref[2] and got[3] == ref[3] and ref[2] > 0 and 0 < ref[3] < ref[2]
+        assert abs(got[0] - ref[0]) < 1e-6 and abs(got[1] - ref[1]) <= 1e-5 * ref[1]
+
+
 def test_pipeline_region_of_validity_errors(ctx):
     with pytest.raises(capi.SmError):
         capi.Pipeline(ctx, 10, 10, capi.default_params(600))       # D > 512 (CV_CN_MAX)

@@ -365,3 +365,13 @@ def test_solve_all_known_answer():
     ref = v0.copy().reshape(-1)
     po.lib().orc_solve_all_1level(ref, ref.size, 0.3)
     assert np.allclose(one.reshape(-1), ref, rtol=2e-7)      # 1/(1+l): float division vs (float)(1./double) of cv
+
+
+def test_cal_err_known_answer():
+    """calErr by hand: 5 masked pixels; errors = one invalid (-1), one |7.5 - 5| > 1, one invalid (-48) -> PBM 3/5;
+    squared error sum 0 + 2 + 6.25 + 0.25 + 2 = 10.5 -> RMS sqrt(2.1)."""
+    dp = np.array([[3, -1, 5], [2, 2, -48]], np.int16)
+    gt = np.array([[3, 4, 7.5], [0, 2.5, 1]], np.float32)
+    mask = np.array([[255, 255, 255], [0, 255, 255]], np.uint8)
+    pbm, rms, n, e = po.cal_err(dp, gt, mask, 1)
+    assert (n, e) == (5, 3) and abs(pbm - 0.6) < 1e-7 and abs(rms - np.sqrt(2.1)) < 1e-6
