@@ -2,7 +2,6 @@ import sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
 from mystereomatching_b200 import capi, synth
-from oracle import pyoracle as po
 ctx = capi.Ctx(0)
 for (H, W, D, kind) in [(480, 640, 64, "texture_warped"), (480, 640, 64, "random_dot"), (1080, 1920, 64, "texture_warped")]:
     p = synth.make_pair(H, W, D, kind, seed=1000)
