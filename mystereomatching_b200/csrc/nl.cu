@@ -27,6 +27,8 @@
 // not by bandwidth.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------ small helpers
@@ -516,7 +518,8 @@ static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn
                     (void*)&t.order, (void*)&t.level_start, (void*)&t.sync};
     const size_t smem = 2 * (size_t)NL_BFS_FCAP * sizeof(int2);
     SM_CUDA(cudaFuncSetAttribute(k_tree_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SM_CUDA(cudaLaunchKernel((const void*)k_tree_bfs, dim3(1), dim3(NL_CTA), args, smem, ctx->stream));
+    static const int bfs_cta = getenv("SM_NL_BFS_CTA") ? atoi(getenv("SM_NL_BFS_CTA")) : 256;   // measured (MST + rooting): 1024 -> 5.56 ms, 512 -> 5.28, 256 -> 5.15, 128 -> 5.41
+    SM_CUDA(cudaLaunchKernel((const void*)k_tree_bfs, dim3(1), dim3(bfs_cta), args, smem, ctx->stream));
     ctx->launches++;
   }
   return SM_OK;
@@ -588,7 +591,8 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     void* args[] = {(void*)&a, (void*)&sn, (void*)&sd, (void*)&dp, (void*)&pp, (void*)&cp, (void*)&t.order, (void*)&t.level_start,
                     (void*)&t.rcp, (void*)&t.rcw, (void*)&t.rnc, (void*)&t.rpp, (void*)&t.rw, (void*)&d_tab, (void*)&t.sync};
     SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(NL_TF_CTA), args, smem, ctx->stream));
+    static const int tf_cta = getenv("SM_NL_TF_CTA") ? atoi(getenv("SM_NL_TF_CTA")) : 256;   // measured 640x480 D=64: 512 -> 8.12 ms, 256 -> 7.78, 128 -> 8.31, 64 -> 11.07
+    SM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(tf_cta), args, smem, ctx->stream));
     ctx->launches++;
   }
   if (d_vol) SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp, t.pos);
