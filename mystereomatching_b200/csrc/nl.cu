@@ -105,6 +105,20 @@ __global__ void k_bor_jump(int N, int* __restrict__ link, int* __restrict__ chan
   if (g != p) { link[c] = g; *changed = 1; }
 }
 
+// Every hooked root follows its links to the root of the merged tree in ONE launch (the links of a round form a
+// forest: a component hooks along its minimum edge, keys are unique, the mutual pair keeps the smaller label as root).
+// Concurrent writers only ever replace a link by an ancestor further up, so a reader that sees either value still
+// walks to the same root.  This replaces the pointer-jumping loop, which cost a host round trip per iteration.
+__global__ void k_bor_chase(int N, int* link) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  volatile int* vl = link;
+  int r = vl[c];
+  if (r == c) return;
+  for (int g = vl[r]; g != r; g = vl[r]) r = g;
+  link[c] = r;
+}
+
 __global__ void k_bor_relabel(int N, int* __restrict__ comp, int* __restrict__ link, unsigned long long* __restrict__ best) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= N) return;
@@ -501,13 +515,7 @@ static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn
     SM_CUDA(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     SM_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h_cnt[0] == 0) break;   // no component has an outgoing edge: the forest is the spanning tree
-    for (int it = 0; it < 40; it++) {   // pointer jumping until every label points at its root
-      SM_CUDA(cudaMemsetAsync(cnt + 1, 0, 4, ctx->stream));
-      SM_LAUNCH(ctx, k_bor_jump, gN, TB, 0, N, link, cnt + 1);
-      SM_CUDA(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      SM_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (h_cnt[1] == 0) break;
-    }
+    SM_LAUNCH(ctx, k_bor_chase, gN, TB, 0, N, link);   // every label points at its root
     SM_LAUNCH(ctx, k_bor_relabel, gN, TB, 0, N, comp, link, best);
     SM_LAUNCH(ctx, k_bor_fixlink, gN, TB, 0, N, link);
   }
