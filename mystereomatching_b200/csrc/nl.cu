@@ -29,6 +29,9 @@
 
 #include <stdlib.h>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------ small helpers
@@ -246,6 +249,84 @@ __global__ void __launch_bounds__(NL_CTA)
   }
   if (tid == 0) { s->nlevels = level; level_start[level] = head; }
 }
+
+// ------------------------------------------------------------------ rooting without a level-by-level walk
+// The BFS above costs one dependent global access per LEVEL (0.75 us x 4366 levels at 640x480, x 17051 at 1080p).  The
+// same parent / depth / level order follow from the tree's EULER TOUR in O(log N) data-parallel steps:
+//   * directed edge (u -> k-th neighbour v) has id 4u + k; its successor in the tour is (v -> the neighbour after u in
+//     v's adjacency list, cyclically); the tour starts with edge (0 -> first neighbour of 0), the edge whose successor
+//     would be that one ends it;
+//   * list ranking by pointer jumping gives every edge its position in the tour;
+//   * an edge is DOWNWARD (u is v's parent) iff it comes before its reverse; parent[v] = u, wpar[v] = its weight;
+//   * +1 for downward, -1 for upward edges, inclusive scan over the tour: the value at a downward edge is depth(v);
+//   * a stable radix sort of the nodes by depth (tour order within a level) is the level order.
+// Identical parent / weight / rank to the BFS (a rooted tree has one parent function); `order` is grouped by level,
+// which is all the filter needs (its results do not depend on the order inside a level).
+#define ET_END (-1)
+__global__ void k_et_init(int N, const int4* __restrict__ nbr, const uint8_t* __restrict__ deg, int* __restrict__ succ,
+                          int* __restrict__ dist) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * N) return;
+  const int u = e >> 2, k = e & 3;
+  int s = ET_END, d = 0;
+  if (k < deg[u]) {
+    const int4 a = nbr[u];
+    const int v = k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w));
+    const int4 b = nbr[v];
+    const int dv = deg[v];
+    const int j = b.x == u ? 0 : (b.y == u ? 1 : (b.z == u ? 2 : 3));
+    const int nj = j + 1 == dv ? 0 : j + 1;
+    s = 4 * v + nj;
+    if (s == 0) s = ET_END;   // edge (0, 0) starts the tour: whoever precedes it is the last edge
+    d = s == ET_END ? 0 : 1;
+  }
+  succ[e] = s; dist[e] = d;
+}
+__global__ void k_et_jump(int n, const int* __restrict__ succ, const int* __restrict__ dist, int* __restrict__ succ2,
+                          int* __restrict__ dist2) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int s = succ[e];
+  int d = dist[e], s2 = s;
+  if (s != ET_END) { d += dist[s]; s2 = succ[s]; }
+  succ2[e] = s2; dist2[e] = d;
+}
+// dist = number of edges after e in the tour; T = 2(N-1) edges; position = T - 1 - dist
+__global__ void k_et_classify(int N, int T, const int4* __restrict__ nbr, const uchar4* __restrict__ nbw,
+                              const uint8_t* __restrict__ deg, const int* __restrict__ dist, int* __restrict__ parent,
+                              uint8_t* __restrict__ wpar, int* __restrict__ pm, int* __restrict__ node_at) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * N) return;
+  const int u = e >> 2, k = e & 3;
+  if (k >= deg[u]) return;
+  const int4 a = nbr[u];
+  const uchar4 w = nbw[u];
+  const int v = k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w));
+  const int wk = k == 0 ? w.x : (k == 1 ? w.y : (k == 2 ? w.z : w.w));
+  const int4 b = nbr[v];
+  const int j = b.x == u ? 0 : (b.y == u ? 1 : (b.z == u ? 2 : 3));
+  const int pe = T - 1 - dist[e], pr = T - 1 - dist[4 * v + j];
+  const bool down = pe < pr;
+  pm[pe] = down ? 1 : -1;
+  node_at[pe] = down ? v : -1;
+  if (down) { parent[v] = u; wpar[v] = (uint8_t)wk; }
+}
+// after the inclusive scan: depth of the node entered by the downward edge at tour position p; sort keys / values
+__global__ void k_et_keys(int N, int T, const int* __restrict__ scan, const int* __restrict__ node_at, int* __restrict__ rank,
+                          unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T) return;
+  if (i == 0) { keys[0] = 0u; vals[0] = 0; rank[0] = 0; return; }   // the root leads the order
+  const int p = i - 1, v = node_at[p];
+  if (v >= 0) { const int d = scan[p]; rank[v] = d; keys[i] = (unsigned)d; vals[i] = v; }
+  else { keys[i] = 0x7fffffffu; vals[i] = -1; }                     // upward edges sort behind every node
+}
+
+// rooted tree from the adjacency by the Euler tour; returns SM_OK and fills parent / wpar / rank / order /
+// level_start / sync->nlevels exactly as k_tree_bfs does (order: grouped by level)
+struct nl_tree;
+static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw, const uint8_t* deg, int* parent,
+                         uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* sync);
 
 // children (in key order) from parent / weight arrays alone -- lets sm_tree_filter accept any rooted tree
 __global__ void k_children_from_parent(int H, int W, const int* __restrict__ parent, const uint8_t* __restrict__ wpar,
@@ -485,6 +566,52 @@ struct nl_tree {   // device buffers of one rooted tree (owned by the ctx scratc
 };
 
 
+__global__ void k_root_single(int* parent, uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* s) {
+  parent[0] = 0; wpar[0] = 0; rank[0] = 0; order[0] = 0; level_start[0] = 0; level_start[1] = 1; s->nlevels = 1;
+}
+__global__ void k_root_fix(int* parent, uint8_t* wpar) { parent[0] = 0; wpar[0] = 0; }
+
+static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw, const uint8_t* deg, int* parent,
+                         uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* sync) {
+  if (N == 1) { SM_LAUNCH(ctx, k_root_single, 1, 1, 0, parent, wpar, rank, order, level_start, sync); return SM_OK; }
+  const int T = 2 * (N - 1), n4 = 4 * N, TB = 256;
+  size_t tmpScan = 0, tmpSort = 0;
+  SM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpScan, (const int*)nullptr, (int*)nullptr, T, ctx->stream));
+  SM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
+                                          (int*)nullptr, T + 1, 0, 32, ctx->stream));
+  const size_t tmpB = (max(tmpScan, tmpSort) + 255) & ~(size_t)255;
+  // succ | dist | succ2 | dist2 (4N ints each) ; pm | node_at | scan (T) ; keys | keys2 | vals | vals2 (T+1) ; cub
+  const size_t ints = (size_t)4 * n4 + (size_t)3 * T + (size_t)4 * (T + 1) + 64;
+  void* p;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_NLEULER, ints * 4 + tmpB, &p));
+  int* succ = (int*)p; int* dist = succ + n4; int* succ2 = dist + n4; int* dist2 = succ2 + n4;
+  int* pm = dist2 + n4; int* node_at = pm + T; int* scan = node_at + T;
+  unsigned* keys = (unsigned*)(scan + T); unsigned* keys2 = keys + (T + 1);
+  int* vals = (int*)(keys2 + (T + 1)); int* vals2 = vals + (T + 1);
+  void* tmp = (void*)(((uintptr_t)(vals2 + (T + 1)) + 255) & ~(uintptr_t)255);
+  SM_LAUNCH(ctx, k_et_init, sm_div_up(n4, TB), TB, 0, N, (const int4*)nbr, deg, succ, dist);
+  for (long long span = 1; span < T; span *= 2) {   // list ranking: ceil(log2 T) jumps
+    SM_LAUNCH(ctx, k_et_jump, sm_div_up(n4, TB), TB, 0, n4, succ, dist, succ2, dist2);
+    int* t = succ; succ = succ2; succ2 = t;
+    t = dist; dist = dist2; dist2 = t;
+  }
+  SM_LAUNCH(ctx, k_et_classify, sm_div_up(n4, TB), TB, 0, N, T, (const int4*)nbr, (const uchar4*)nbw, deg, dist, parent, wpar, pm,
+            node_at);
+  SM_LAUNCH(ctx, k_root_fix, 1, 1, 0, parent, wpar);
+  size_t tb = tmpB;
+  SM_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, pm, scan, T, ctx->stream));
+  ctx->launches += 2;
+  SM_LAUNCH(ctx, k_et_keys, sm_div_up(T + 1, TB), TB, 0, N, T, scan, node_at, rank, keys, vals);
+  int bits = 1;
+  while (bits < 31 && (1ll << bits) <= (long long)N) bits++;   // depth < N; the sentinel 0x7fffffff needs bit 30..: sort all 31 bits
+  tb = tmpB;
+  SM_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, vals, vals2, T + 1, 0, 31, ctx->stream));
+  ctx->launches += 8;
+  SM_CUDA(cudaMemcpyAsync(order, vals2, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  SM_LAUNCH(ctx, k_level_bounds, min(sm_div_up(N, TB), ctx->num_sms * 8), TB, 0, N, rank, order, level_start, sync);
+  return SM_OK;
+}
+
 // MST + rooting.  img: [H][W][cn] u8 (already median-filtered).  Fills t (buffers must be allocated).
 static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn, nl_tree& t) {
   const int N = H * W, E = H * (W - 1) + W * (H - 1);
@@ -521,6 +648,8 @@ static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn
   }
   SM_LAUNCH(ctx, k_tree_adj, gN, TB, 0, H, W, ew, inMST, nbr, nbw, deg);
   SM_CUDA(cudaMemsetAsync(t.sync, 0, sizeof(nl_sync), ctx->stream));
+  static const int euler_env = getenv("SM_NL_EULER") ? atoi(getenv("SM_NL_EULER")) : 1;   // 0: the level-by-level BFS
+  if (euler_env) return nl_root_euler(ctx, N, nbr, nbw, deg, t.parent, t.wpar, t.rank, t.order, t.level_start, t.sync);
   {
     void* args[] = {(void*)&N, (void*)&nbr, (void*)&nbw, (void*)&deg, (void*)&t.parent, (void*)&t.wpar, (void*)&t.rank,
                     (void*)&t.order, (void*)&t.level_start, (void*)&t.sync};
