@@ -391,7 +391,7 @@ __global__ void k_tf_records(int N, const int* __restrict__ order, const int* __
                              const int* __restrict__ level_start, const int* __restrict__ parent,
                              const uint8_t* __restrict__ wpar, const int* __restrict__ child, const uint8_t* __restrict__ nchild,
                              int4* __restrict__ rcp, uint32_t* __restrict__ rcw, uint8_t* __restrict__ rnc, int* __restrict__ rpp,
-                             uint8_t* __restrict__ rw) {
+                             uint8_t* __restrict__ rw, uint4* __restrict__ rup, int2* __restrict__ rdn) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     const int v = order[i], l = rank[v], nc = nchild[v];
     int cp[4] = {0, 0, 0, 0};
@@ -406,6 +406,9 @@ __global__ void k_tf_records(int N, const int* __restrict__ order, const int* __
     rnc[i] = (uint8_t)nc;
     rpp[i] = l > 0 ? pos[parent[v]] - level_start[l - 1] : 0;
     rw[i] = wpar[v];
+    rup[2 * (size_t)i] = make_uint4((unsigned)cp[0], (unsigned)cp[1], (unsigned)cp[2], (unsigned)cp[3]);
+    rup[2 * (size_t)i + 1] = make_uint4(cw, (unsigned)nc, 0u, 0u);
+    rdn[i] = make_int2(rpp[i], (int)wpar[v]);
   }
 }
 
@@ -544,6 +547,160 @@ __global__ void __launch_bounds__(NL_TF_CTA)
   }
 }
 
+// ---- one CTA per plane, streamed -----------------------------------------------------------------------------------
+// k_tf_sweeps spends ~1700 cycles per level although a level is 70 nodes (at most a few hundred): its per-thread
+// register prefetch, 64-bit addressing and level-bound lookups cost every warp ~70 instructions per level, and the
+// records come through dependent global loads.  Here the static records and the plane's own values -- level-ordered,
+// i.e. read LINEARLY by the two sweeps (descending, then ascending) -- are streamed through a 3-stage shared-memory
+// ring by cp.async in chunks of 1024 positions, independent of the level bounds, so no global load sits in the
+// per-level chain; a level is processed piece by piece along the chunk boundaries (one node per thread), the values of
+// the adjacent level stay in two shared-memory level buffers, all level bounds are in shared memory, and a level costs
+// one __syncthreads.  Per (node, plane) the operations and their order are those of k_tf_sweeps, i.e. the
+// reference's: bit-identical.
+#define TFW_T 256          // threads per plane
+#define TFW_C 1024         // positions per chunk
+#define TFW_S 3            // stages
+#define TFW_CAP 1024       // nodes of a level kept in shared memory (wider levels read the excess back from global memory)
+__device__ __forceinline__ void tfw_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tfw_cp8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tfw_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tfw_wait_oldest() { asm volatile("cp.async.wait_group %0;" ::"n"(TFW_S - 1) : "memory"); }
+__device__ __forceinline__ void tfw_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ double tfw_ldcg(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(TFW_T)
+    k_tf_cta(double* __restrict__ A, int N, int Dp, int lsCap, const int* __restrict__ level_start,
+             const uint4* __restrict__ rup, const int2* __restrict__ rdn, const double* __restrict__ table,
+             const nl_sync* __restrict__ s) {
+  extern __shared__ __align__(16) uint8_t tfw_smem[];
+  __shared__ double tab[256];
+  const int tid = threadIdx.x;
+  const int d = blockIdx.x;
+  const int nlevels = s->nlevels;
+  double* lvb = reinterpret_cast<double*>(tfw_smem);                                              // [2][CAP]
+  uint4* ringRec = reinterpret_cast<uint4*>(tfw_smem + 2 * (size_t)TFW_CAP * 8);                   // [S*C][2] (up) / int2 [S*C] (down)
+  double* ringOwn = reinterpret_cast<double*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 32);   // [S*C]
+  int* ls = reinterpret_cast<int*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40);            // [lsCap]
+  for (int i = tid; i < 256; i += TFW_T) tab[i] = table[i];
+  for (int i = tid; i <= nlevels && i < lsCap; i += TFW_T) ls[i] = level_start[i];
+  __syncthreads();
+  auto lstart = [&](int l) -> int { return l < lsCap ? ls[l] : level_start[l]; };
+  const uint32_t recA = (uint32_t)__cvta_generic_to_shared(ringRec), ownA = (uint32_t)__cvta_generic_to_shared(ringOwn);
+  double* Ad = A + (size_t)d * N;
+  const int kTop = (N - 1) / TFW_C;
+  auto ring_index = [&](int q) -> int { return ((q / TFW_C) % TFW_S) * TFW_C + (q % TFW_C); };
+
+  // ------------------------------------------------------------------ leaf to root (positions descending)
+  auto issue_up = [&](int k) {
+    if (k >= 0 && k <= kTop) {
+      const int st = k % TFW_S, base = k * TFW_C;
+      for (int i = tid; i < TFW_C * 2; i += TFW_T)
+        if (base + (i >> 1) < N) tfw_cp16(recA + (uint32_t)(st * TFW_C * 2 + i) * 16u, rup + (size_t)base * 2 + i);
+      for (int i = tid; i < TFW_C; i += TFW_T)
+        if (base + i < N) tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
+    }
+    tfw_commit();   // an empty group keeps the count uniform
+  };
+  for (int j = 0; j < TFW_S; j++) issue_up(kTop - j);
+  int curChunk = kTop + 1;   // chunks >= curChunk are done with; chunk curChunk - 1 is the oldest group in flight
+  {
+    int hi = N;              // = level_start[nlevels]
+    for (int l = nlevels - 1; l >= 0; l--) {
+      const int lo = lstart(l);
+      double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
+      const double* kid = lvb + (size_t)((l + 1) & 1) * TFW_CAP;
+      const int kidLo = hi;  // first position of level l + 1
+      for (int c = (hi - 1) / TFW_C; c >= lo / TFW_C && hi > lo; c--) {
+        while (curChunk > c) {           // first touch of chunk curChunk - 1: it is the oldest group in flight
+          if (curChunk <= kTop) { __syncthreads(); issue_up(curChunk - TFW_S); }   // chunk curChunk is done with: refill its stage
+          tfw_wait_oldest();
+          __syncthreads();
+          curChunk--;
+        }
+        const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
+        for (int q = p0 + tid; q < p1; q += TFW_T) {
+          const int ri = ring_index(q);
+          const uint4 r0 = ringRec[2 * ri], r1 = ringRec[2 * ri + 1];
+          double acc = ringOwn[ri];
+          const int nc = (int)r1.y;
+          const int cp[4] = {(int)r0.x, (int)r0.y, (int)r0.z, (int)r0.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < nc) {
+              const int p = cp[k];
+              const double val = p < TFW_CAP ? kid[p] : tfw_ldcg(Ad + kidLo + p);
+              acc += val * tab[(r1.x >> (8 * k)) & 0xff];
+            }
+          }
+          if (nc) Ad[q] = acc;
+          if (q - lo < TFW_CAP) cur[q - lo] = acc;
+        }
+      }
+      __syncthreads();   // the level's values are visible to the CTA before the next level reads them
+      hi = lo;
+    }
+  }
+  tfw_wait_all();
+  __threadfence();   // the backup values written above are read back through cp.async below
+  __syncthreads();
+
+  // ------------------------------------------------------------------ root to leaf (positions ascending)
+  auto issue_dn = [&](int k) {
+    if (k >= 0 && k <= kTop) {
+      const int st = k % TFW_S, base = k * TFW_C;
+      for (int i = tid; i < TFW_C; i += TFW_T)
+        if (base + i < N) {
+          tfw_cp8(recA + (uint32_t)(st * TFW_C + i) * 8u, rdn + base + i);
+          tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
+        }
+    }
+    tfw_commit();
+  };
+  const int2* ringDn = reinterpret_cast<const int2*>(ringRec);
+  for (int j = 0; j < TFW_S; j++) issue_dn(j);
+  curChunk = -1;             // chunks <= curChunk are done with; chunk curChunk + 1 is the oldest group in flight
+  {
+    int lo = 0, prevLo = 0;
+    for (int l = 0; l < nlevels; l++) {
+      const int hi = lstart(l + 1);
+      double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
+      const double* par = lvb + (size_t)((l - 1) & 1) * TFW_CAP;
+      for (int c = lo / TFW_C; c <= (hi - 1) / TFW_C && hi > lo; c++) {
+        while (curChunk < c) {
+          if (curChunk >= 0) { __syncthreads(); issue_dn(curChunk + TFW_S); }
+          tfw_wait_oldest();
+          __syncthreads();
+          curChunk++;
+        }
+        if (l == 0) continue;            // the root keeps its backup value (already in A and in the level buffer)
+        const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
+        for (int q = p0 + tid; q < p1; q += TFW_T) {
+          const int ri = ring_index(q);
+          const int2 rec = ringDn[ri];
+          const double b = ringOwn[ri];
+          const double w = tab[rec.y];
+          const double pv = rec.x < TFW_CAP ? par[rec.x] : tfw_ldcg(Ad + prevLo + rec.x);
+          const double r = w * (pv - w * b) + b;
+          Ad[q] = r;
+          if (q - lo < TFW_CAP) cur[q - lo] = r;
+        }
+      }
+      __syncthreads();
+      prevLo = lo;
+      lo = hi;
+    }
+  }
+  tfw_wait_all();
+}
+
 __global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp,
                            const int* __restrict__ pos) {
   const size_t n = N * D;
@@ -563,6 +720,8 @@ struct nl_tree {   // device buffers of one rooted tree (owned by the ctx scratc
   nl_sync* sync;
   // level-ordered records (k_tf_records)
   int4* rcp; uint32_t* rcw; int* rpp; int* pos; uint8_t *rnc, *rw;
+  uint4* rup;   // [N][2]: {cp0, cp1, cp2, cp3}, {cw, nc, 0, 0}   (k_tf_warp: one 32-byte record per position)
+  int2* rdn;    // [N]: {pp, w}
 };
 
 
@@ -683,9 +842,11 @@ static int nl_tree_scratch(sm_ctx* ctx, int N, nl_tree& t, bool own_arrays) {
   t.nchild = q;
   // SM_SCR_NLREC: rcp[N] int4 | rcw[N] | rpp[N] | pos[N] | rnc[N] | rw[N]
   void* p2;
-  SM_TRY(sm_scratch_get(ctx, SM_SCR_NLREC, (size_t)N * 30 + 64, &p2));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_NLREC, (size_t)N * 70 + 128, &p2));
   uint8_t* r = (uint8_t*)p2;
+  t.rup = (uint4*)r; r += (size_t)N * 32;    // 16-byte aligned arrays first (N may be odd)
   t.rcp = (int4*)r; r += (size_t)N * 16;
+  t.rdn = (int2*)r; r += (size_t)N * 8;
   t.rcw = (uint32_t*)r; r += (size_t)N * 4;
   t.rpp = (int*)r; r += (size_t)N * 4;
   t.pos = (int*)r; r += (size_t)N * 4;
@@ -712,9 +873,25 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
   const int n = (int)N, gr = min(sm_div_up(n, TB), ctx->num_sms * 8);
   SM_LAUNCH(ctx, k_tf_positions, gr, TB, 0, n, t.order, t.pos);
   SM_LAUNCH(ctx, k_tf_records, gr, TB, 0, n, t.order, t.pos, t.rank, t.level_start, t.parent, t.wpar, t.child, t.nchild,
-            t.rcp, t.rcw, t.rnc, t.rpp, t.rw);
+            t.rcp, t.rcw, t.rnc, t.rpp, t.rw, t.rup, t.rdn);
   if (d_vol) SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp, t.order);
-  {
+  static const int tfw_env = getenv("SM_NL_TF_STREAM") ? atoi(getenv("SM_NL_TF_STREAM")) : 1;   // 0: k_tf_sweeps
+  const size_t tfwFixed = 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40;
+  if (d_vol && tfw_env) {
+    // one CTA per plane, records and values streamed (k_tf_cta); level bounds in shared memory as far as they fit
+    int h_nlev = 0;
+    SM_CUDA(cudaMemcpyAsync(&h_nlev, &t.sync->nlevels, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SM_CUDA(cudaStreamSynchronize(ctx->stream));
+    int lsCap = (int)min((size_t)h_nlev + 1, (227 * 1024 - tfwFixed - 2048 - 64) / 4);
+    const size_t smem = tfwFixed + (size_t)lsCap * 4;
+    double* a = d_A;
+    int n_ = (int)N, dp = Dp;
+    void* args[] = {(void*)&a, (void*)&n_, (void*)&dp, (void*)&lsCap, (void*)&t.level_start, (void*)&t.rup, (void*)&t.rdn,
+                    (void*)&d_tab, (void*)&t.sync};
+    SM_CUDA(cudaFuncSetAttribute((const void*)k_tf_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SM_CUDA(cudaLaunchKernel((const void*)k_tf_cta, dim3(Dp), dim3(TFW_T), args, smem, ctx->stream));
+    ctx->launches++;
+  } else {
     // one CTA per plane while there are SMs for them, else the same number of planes for every CTA
     const int ppc = sm_div_up(Dp, min(Dp, ctx->num_sms));
     const int grid = sm_div_up(Dp, ppc);
