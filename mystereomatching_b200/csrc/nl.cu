@@ -582,15 +582,15 @@ __global__ void __launch_bounds__(TFW_T)
              const nl_sync* __restrict__ s) {
   extern __shared__ __align__(16) uint8_t tfw_smem[];
   __shared__ double tab[256];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nth = blockDim.x;
   const int d = blockIdx.x;
   const int nlevels = s->nlevels;
   double* lvb = reinterpret_cast<double*>(tfw_smem);                                              // [2][CAP]
   uint4* ringRec = reinterpret_cast<uint4*>(tfw_smem + 2 * (size_t)TFW_CAP * 8);                   // [S*C][2] (up) / int2 [S*C] (down)
   double* ringOwn = reinterpret_cast<double*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 32);   // [S*C]
   int* ls = reinterpret_cast<int*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40);            // [lsCap]
-  for (int i = tid; i < 256; i += TFW_T) tab[i] = table[i];
-  for (int i = tid; i <= nlevels && i < lsCap; i += TFW_T) ls[i] = level_start[i];
+  for (int i = tid; i < 256; i += nth) tab[i] = table[i];
+  for (int i = tid; i <= nlevels && i < lsCap; i += nth) ls[i] = level_start[i];
   __syncthreads();
   auto lstart = [&](int l) -> int { return l < lsCap ? ls[l] : level_start[l]; };
   const uint32_t recA = (uint32_t)__cvta_generic_to_shared(ringRec), ownA = (uint32_t)__cvta_generic_to_shared(ringOwn);
@@ -602,9 +602,9 @@ __global__ void __launch_bounds__(TFW_T)
   auto issue_up = [&](int k) {
     if (k >= 0 && k <= kTop) {
       const int st = k % TFW_S, base = k * TFW_C;
-      for (int i = tid; i < TFW_C * 2; i += TFW_T)
+      for (int i = tid; i < TFW_C * 2; i += nth)
         if (base + (i >> 1) < N) tfw_cp16(recA + (uint32_t)(st * TFW_C * 2 + i) * 16u, rup + (size_t)base * 2 + i);
-      for (int i = tid; i < TFW_C; i += TFW_T)
+      for (int i = tid; i < TFW_C; i += nth)
         if (base + i < N) tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
     }
     tfw_commit();   // an empty group keeps the count uniform
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(TFW_T)
           curChunk--;
         }
         const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
-        for (int q = p0 + tid; q < p1; q += TFW_T) {
+        for (int q = p0 + tid; q < p1; q += nth) {
           const int ri = ring_index(q);
           const uint4 r0 = ringRec[2 * ri], r1 = ringRec[2 * ri + 1];
           double acc = ringOwn[ri];
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(TFW_T)
   auto issue_dn = [&](int k) {
     if (k >= 0 && k <= kTop) {
       const int st = k % TFW_S, base = k * TFW_C;
-      for (int i = tid; i < TFW_C; i += TFW_T)
+      for (int i = tid; i < TFW_C; i += nth)
         if (base + i < N) {
           tfw_cp8(recA + (uint32_t)(st * TFW_C + i) * 8u, rdn + base + i);
           tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(TFW_T)
         }
         if (l == 0) continue;            // the root keeps its backup value (already in A and in the level buffer)
         const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
-        for (int q = p0 + tid; q < p1; q += TFW_T) {
+        for (int q = p0 + tid; q < p1; q += nth) {
           const int ri = ring_index(q);
           const int2 rec = ringDn[ri];
           const double b = ringOwn[ri];
@@ -889,7 +889,8 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     void* args[] = {(void*)&a, (void*)&n_, (void*)&dp, (void*)&lsCap, (void*)&t.level_start, (void*)&t.rup, (void*)&t.rdn,
                     (void*)&d_tab, (void*)&t.sync};
     SM_CUDA(cudaFuncSetAttribute((const void*)k_tf_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SM_CUDA(cudaLaunchKernel((const void*)k_tf_cta, dim3(Dp), dim3(TFW_T), args, smem, ctx->stream));
+    static const int tfw_t = getenv("SM_NL_TFW_T") ? atoi(getenv("SM_NL_TFW_T")) : TFW_T;   // tuning switch (<= 256)
+    SM_CUDA(cudaLaunchKernel((const void*)k_tf_cta, dim3(Dp), dim3(tfw_t), args, smem, ctx->stream));
     ctx->launches++;
   } else {
     // one CTA per plane while there are SMs for them, else the same number of planes for every CTA
