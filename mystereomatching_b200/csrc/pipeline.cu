@@ -27,6 +27,10 @@ struct sm_pipeline {
   int16_t *disp[2] = {nullptr, nullptr}, *dtmp = nullptr;
   uint8_t* h_in = nullptr;   // pinned staging: bgrL | bgrR | grayL | grayR
   int16_t* h_out = nullptr;  // pinned staging: dispL | dispR
+  // small frames (a single-path SGM sweep is then a chain of H or W dependent steps on a few hundred warps, far from
+  // filling the GPU): the two views' sweeps run concurrently, view 1 on a second stream
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   sm_pipeline* child = nullptr;   // next pyramid level (cost + aggregation only), pyramidLevels > 1
   bool is_child = false;
   bool have_gray = false, have_arms = false, scale_folded = false;
@@ -53,6 +57,9 @@ extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
     cudaFree(pl->grad[i][0]); cudaFree(pl->grad[i][1]);
   }
   for (int i = 0; i < 4; i++) cudaFree(pl->vol[i]);
+  if (pl->stream2) cudaStreamDestroy(pl->stream2);
+  if (pl->evFork) cudaEventDestroy(pl->evFork);
+  if (pl->evJoin) cudaEventDestroy(pl->evJoin);
   cudaFree(pl->nlwork);
   cudaFree(pl->dtmp);
   if (pl->h_in) cudaFreeHost(pl->h_in);
@@ -94,7 +101,15 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   }
   // a fourth volume only where the two views' SGM sweeps can share a launch (two sums are written at once)
   const bool two_view_sgm = p->sgm_paths == 8 && p->sgm_grouped && p->Do_refine && p->Do_LRConsis;
-  for (int i = 0; i < (two_view_sgm ? 4 : 3) && rc == SM_OK; i++) rc = pl_alloc(ctx, (void**)&pl->vol[i], nvol * sizeof(float));
+  const bool two_stream_sgm = !two_view_sgm && p->sgm_paths > 0 && p->Do_refine && p->Do_LRConsis && nvol <= ((size_t)48 << 20);
+  for (int i = 0; i < ((two_view_sgm || two_stream_sgm) ? 4 : 3) && rc == SM_OK; i++)
+    rc = pl_alloc(ctx, (void**)&pl->vol[i], nvol * sizeof(float));
+  if (rc == SM_OK && two_stream_sgm) {
+    if (cudaStreamCreateWithFlags(&pl->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming) != cudaSuccess)
+      rc = SM_ERR_CUDA;
+  }
   if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->dtmp, npix * 2);
   if (rc == SM_OK && p->aggregation == 2) rc = pl_alloc(ctx, (void**)&pl->nlwork, npix * (size_t)(pl->D + 1) * sizeof(double));
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_in, npix * 8) != cudaSuccess) rc = SM_ERR_NOMEM;
@@ -289,6 +304,31 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
       } else if (rc != SM_ERR_UNSUPPORTED) {
         return rc;
       }
+    }
+    if (!done && views == 2 && pl->stream2 && !(P.sgm_paths == 8 && P.sgm_grouped)) {
+      // both views at once: view 0 on the ctx stream into vol[2], view 1 on the second stream into vol[3]
+      SM_CUDA(cudaEventRecord(pl->evFork, c->stream));
+      SM_CUDA(cudaStreamWaitEvent(pl->stream2, pl->evFork, 0));
+      cudaStream_t main_stream = c->stream;
+      int rc2 = SM_OK;
+      for (int i = 0; i < 2 && rc2 == SM_OK; i++) {
+        c->stream = i == 0 ? main_stream : pl->stream2;
+        for (int k = 0; k < P.sgm_paths && rc2 == SM_OK; k++) {
+          const int mode = k == 0 ? 0 : (k == P.sgm_paths - 1 ? 2 : 1);
+          rc2 = smi_sgm_path_packed2(c, pl->vol[i], pl->pix[i], H, W, D, k, P.sgm_corDifThres, P.sgm_reduCoeffi1, mode,
+                                     pl->vol[2 + i], pl->disp[i]);
+        }
+      }
+      c->stream = main_stream;
+      SM_TRY(rc2);
+      SM_CUDA(cudaEventRecord(pl->evJoin, pl->stream2));
+      SM_CUDA(cudaStreamWaitEvent(c->stream, pl->evJoin, 0));
+      for (int i = 0; i < 2; i++) {   // vm[i] <- path sum; the old cost volumes become the scratch
+        float* t = pl->vol[i];
+        pl->vol[i] = pl->vol[2 + i];
+        pl->vol[2 + i] = t;
+      }
+      done = true;
     }
     for (int i = 0; i < views && !done; i++) {
       pl->sweeps[i] = false;
