@@ -701,6 +701,198 @@ __global__ void __launch_bounds__(TFW_T)
   tfw_wait_all();
 }
 
+// ---- one CTA per plane, streamed, lean level loop ------------------------------------------------------------------
+// ncu on k_tf_cta (profiles/r01_nl_fast_ncu.md): every warp executes ~90 instructions of loop bookkeeping per level
+// (chunk range of the level, ring index by division, bounds with an l < lsCap test, uniform-register traffic) before the
+// ~60 of the node itself, at 0.17 IPC -- a single dependent chain, so time per level = instructions on that chain x ~6
+// cycles.  Nearly every level is narrow (<= one node per thread), lies inside the chunk the sweep is already in, and
+// has its neighbour level wholly in the shared-memory level buffer.  Whether that holds is a property of the level
+// bounds alone, so it is decided once, when the bounds are copied to shared memory (two flag bits in the entry), and such
+// a level runs a straight-line body: position = lo + tid, ring slot = position + a per-chunk offset, children read
+// without the wide-level fallback (no branch inside), one barrier.  Every other level (chunk change, wide level) takes
+// k_tf_cta's general code.  Per (node, plane) the operations and their order are unchanged: bit-identical.
+#define TFF_UP 0x80000000u
+#define TFF_DN 0x40000000u
+#define TFF_LO 0x3fffffff
+__global__ void __launch_bounds__(TFW_T)
+    k_tf_cta_fast(double* __restrict__ A, int N, int Dp, int lsCap, const int* __restrict__ level_start,
+                  const uint4* __restrict__ rup, const int2* __restrict__ rdn, const double* __restrict__ table,
+                  const nl_sync* __restrict__ s) {
+  extern __shared__ __align__(16) uint8_t tfw_smem[];
+  __shared__ double tab[256];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int d = blockIdx.x;
+  const int nlevels = s->nlevels;   // the launcher guarantees nlevels < lsCap: every bound sits in shared memory
+  double* lvb = reinterpret_cast<double*>(tfw_smem);                                              // [2][CAP]
+  uint4* ringRec = reinterpret_cast<uint4*>(tfw_smem + 2 * (size_t)TFW_CAP * 8);                   // [S*C][2] (up) / int2 [S*C] (down)
+  double* ringOwn = reinterpret_cast<double*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 32);   // [S*C]
+  uint32_t* ls = reinterpret_cast<uint32_t*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40);    // [nlevels + 1]
+  for (int i = tid; i < 256; i += nth) tab[i] = table[i];
+  for (int l = tid; l <= nlevels; l += nth) {
+    const int lo = level_start[l];
+    uint32_t e = (uint32_t)lo;
+    if (l < nlevels) {
+      const int hi = level_start[l + 1];
+      const bool one = hi > lo && hi - lo <= nth && lo / TFW_C == (hi - 1) / TFW_C;
+      // up sweep: level l + 1 was processed just before (its last piece lies in chunk hi / C) and feeds this one
+      if (one && l + 1 < nlevels && hi / TFW_C == lo / TFW_C && level_start[l + 2] - hi <= TFW_CAP) e |= TFF_UP;
+      // down sweep: level l - 1 was processed just before (its last piece lies in chunk (lo - 1) / C)
+      if (one && l >= 1 && (lo - 1) / TFW_C == lo / TFW_C && lo - level_start[l - 1] <= TFW_CAP) e |= TFF_DN;
+    }
+    ls[l] = e;
+  }
+  __syncthreads();
+  const uint32_t recA = (uint32_t)__cvta_generic_to_shared(ringRec), ownA = (uint32_t)__cvta_generic_to_shared(ringOwn);
+  double* Ad = A + (size_t)d * N;
+  const int kTop = (N - 1) / TFW_C;
+  auto ring_index = [&](int q) -> int { return ((q / TFW_C) % TFW_S) * TFW_C + (q % TFW_C); };
+
+  // ------------------------------------------------------------------ leaf to root (positions descending)
+  auto issue_up = [&](int k) {
+    if (k >= 0 && k <= kTop) {
+      const int st = k % TFW_S, base = k * TFW_C;
+      for (int i = tid; i < TFW_C * 2; i += nth)
+        if (base + (i >> 1) < N) tfw_cp16(recA + (uint32_t)(st * TFW_C * 2 + i) * 16u, rup + (size_t)base * 2 + i);
+      for (int i = tid; i < TFW_C; i += nth)
+        if (base + i < N) tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
+    }
+    tfw_commit();   // an empty group keeps the count uniform
+  };
+  for (int j = 0; j < TFW_S; j++) issue_up(kTop - j);
+  int curChunk = kTop + 1;   // chunks >= curChunk are done with; chunk curChunk - 1 is the oldest group in flight
+  int ringOff = 0;           // ring slot of position q inside the current chunk = q + ringOff
+  {
+    int hi = N;              // = level_start[nlevels]
+    uint32_t e = ls[nlevels - 1];
+    for (int l = nlevels - 1; l >= 0; l--) {
+      const uint32_t eN = ls[l > 0 ? l - 1 : 0];
+      const int lo = (int)(e & TFF_LO);
+      double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
+      const double* kid = lvb + (size_t)((l + 1) & 1) * TFW_CAP;
+      if (e & TFF_UP) {
+        const int q = lo + tid;
+        if (q < hi) {
+          const int ri = q + ringOff;
+          const uint4 r0 = ringRec[2 * ri], r1 = ringRec[2 * ri + 1];
+          double acc = ringOwn[ri];
+          const int nc = (int)r1.y;
+          const double t0 = kid[r0.x] * tab[r1.x & 0xff];
+          const double t1 = kid[r0.y] * tab[(r1.x >> 8) & 0xff];
+          const double t2 = kid[r0.z] * tab[(r1.x >> 16) & 0xff];
+          const double t3 = kid[r0.w] * tab[r1.x >> 24];
+          if (nc > 0) acc += t0;
+          if (nc > 1) acc += t1;
+          if (nc > 2) acc += t2;
+          if (nc > 3) acc += t3;
+          if (nc) Ad[q] = acc;
+          cur[tid] = acc;
+        }
+      } else {
+        const int kidLo = hi;  // first position of level l + 1
+        for (int c = (hi - 1) / TFW_C; c >= lo / TFW_C && hi > lo; c--) {
+          while (curChunk > c) {           // first touch of chunk curChunk - 1: it is the oldest group in flight
+            if (curChunk <= kTop) { __syncthreads(); issue_up(curChunk - TFW_S); }   // chunk curChunk is done with: refill its stage
+            tfw_wait_oldest();
+            __syncthreads();
+            curChunk--;
+          }
+          const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
+          for (int q = p0 + tid; q < p1; q += nth) {
+            const int ri = ring_index(q);
+            const uint4 r0 = ringRec[2 * ri], r1 = ringRec[2 * ri + 1];
+            double acc = ringOwn[ri];
+            const int nc = (int)r1.y;
+            const int cp[4] = {(int)r0.x, (int)r0.y, (int)r0.z, (int)r0.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              if (k < nc) {
+                const int p = cp[k];
+                const double val = p < TFW_CAP ? kid[p] : tfw_ldcg(Ad + kidLo + p);
+                acc += val * tab[(r1.x >> (8 * k)) & 0xff];
+              }
+            }
+            if (nc) Ad[q] = acc;
+            if (q - lo < TFW_CAP) cur[q - lo] = acc;
+          }
+        }
+        ringOff = (curChunk % TFW_S) * TFW_C - curChunk * TFW_C;
+      }
+      __syncthreads();   // the level's values are visible to the CTA before the next level reads them
+      hi = lo;
+      e = eN;
+    }
+  }
+  tfw_wait_all();
+  __threadfence();   // the backup values written above are read back through cp.async below
+  __syncthreads();
+
+  // ------------------------------------------------------------------ root to leaf (positions ascending)
+  auto issue_dn = [&](int k) {
+    if (k >= 0 && k <= kTop) {
+      const int st = k % TFW_S, base = k * TFW_C;
+      for (int i = tid; i < TFW_C; i += nth)
+        if (base + i < N) {
+          tfw_cp8(recA + (uint32_t)(st * TFW_C + i) * 8u, rdn + base + i);
+          tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
+        }
+    }
+    tfw_commit();
+  };
+  const int2* ringDn = reinterpret_cast<const int2*>(ringRec);
+  for (int j = 0; j < TFW_S; j++) issue_dn(j);
+  curChunk = -1;             // chunks <= curChunk are done with; chunk curChunk + 1 is the oldest group in flight
+  {
+    int lo = 0, prevLo = 0;
+    uint32_t e = ls[0], eH = ls[1];
+    for (int l = 0; l < nlevels; l++) {
+      const uint32_t eHN = ls[l + 2 <= nlevels ? l + 2 : nlevels];
+      const int hi = (int)(eH & TFF_LO);
+      double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
+      const double* par = lvb + (size_t)((l - 1) & 1) * TFW_CAP;
+      if (e & TFF_DN) {
+        const int q = lo + tid;
+        if (q < hi) {
+          const int ri = q + ringOff;
+          const int2 rec = ringDn[ri];
+          const double b = ringOwn[ri];
+          const double w = tab[rec.y];
+          const double pv = par[rec.x];
+          const double r = w * (pv - w * b) + b;
+          Ad[q] = r;
+          cur[tid] = r;
+        }
+      } else {
+        for (int c = lo / TFW_C; c <= (hi - 1) / TFW_C && hi > lo; c++) {
+          while (curChunk < c) {
+            if (curChunk >= 0) { __syncthreads(); issue_dn(curChunk + TFW_S); }
+            tfw_wait_oldest();
+            __syncthreads();
+            curChunk++;
+          }
+          if (l == 0) continue;            // the root keeps its backup value (already in A and in the level buffer)
+          const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
+          for (int q = p0 + tid; q < p1; q += nth) {
+            const int ri = ring_index(q);
+            const int2 rec = ringDn[ri];
+            const double b = ringOwn[ri];
+            const double w = tab[rec.y];
+            const double pv = rec.x < TFW_CAP ? par[rec.x] : tfw_ldcg(Ad + prevLo + rec.x);
+            const double r = w * (pv - w * b) + b;
+            Ad[q] = r;
+            if (q - lo < TFW_CAP) cur[q - lo] = r;
+          }
+        }
+        ringOff = (curChunk % TFW_S) * TFW_C - curChunk * TFW_C;
+      }
+      __syncthreads();
+      prevLo = lo;
+      lo = hi;
+      e = eH; eH = eHN;
+    }
+  }
+  tfw_wait_all();
+}
+
 __global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp,
                            const int* __restrict__ pos) {
   const size_t n = N * D;
@@ -888,9 +1080,11 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     int n_ = (int)N, dp = Dp;
     void* args[] = {(void*)&a, (void*)&n_, (void*)&dp, (void*)&lsCap, (void*)&t.level_start, (void*)&t.rup, (void*)&t.rdn,
                     (void*)&d_tab, (void*)&t.sync};
-    SM_CUDA(cudaFuncSetAttribute((const void*)k_tf_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const int tfw_fast = getenv("SM_NL_TF_FAST") ? atoi(getenv("SM_NL_TF_FAST")) : 1;   // 0: k_tf_cta (general code at every level)
+    const void* fn = (tfw_fast && h_nlev < lsCap) ? (const void*)k_tf_cta_fast : (const void*)k_tf_cta;
+    SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const int tfw_t = getenv("SM_NL_TFW_T") ? atoi(getenv("SM_NL_TFW_T")) : TFW_T;   // tuning switch (<= 256)
-    SM_CUDA(cudaLaunchKernel((const void*)k_tf_cta, dim3(Dp), dim3(tfw_t), args, smem, ctx->stream));
+    SM_CUDA(cudaLaunchKernel(fn, dim3(Dp), dim3(tfw_t), args, smem, ctx->stream));
     ctx->launches++;
   } else {
     // one CTA per plane while there are SMs for them, else the same number of planes for every CTA

@@ -3,7 +3,10 @@ sys.path.insert(0, ".")
 import numpy as np, torch
 from mystereomatching_b200 import capi, synth
 ctx = capi.Ctx(0)
-for (H, W, D, kind) in [(480, 640, 64, "texture_warped"), (480, 640, 64, "random_dot"), (1080, 1920, 64, "texture_warped")]:
+torch.manual_seed(0)
+CONFIGS = [(480, 640, 64, "texture_warped"), (480, 640, 64, "random_dot"), (1080, 1920, 64, "texture_warped")]
+if len(sys.argv) > 1: CONFIGS = CONFIGS[:int(sys.argv[1])]
+for (H, W, D, kind) in CONFIGS:
     p = synth.make_pair(H, W, D, kind, seed=1000)
     img = ctx.dev(p["bgrL"])
     vol = torch.rand((H, W, D), device="cuda")
@@ -21,4 +24,6 @@ for (H, W, D, kind) in [(480, 640, 64, "texture_warped"), (480, 640, 64, "random
     t_tf = timeit(lambda: ctx.tree_filter(vol, tree, 0.1))
     t_nl = timeit(lambda: ctx.nl(img, vol))
     depth = int(tree["rank"].max().item()) + 1
-    print(f"{W}x{H} D={D} {kind}: depth {depth}  mst_build {t_mst:.2f} ms ({nl_launch} launches)  tree_filter {t_tf:.2f} ms  sm_nl {t_nl:.2f} ms", flush=True)
+    import hashlib
+    sha = hashlib.sha1(ctx.tree_filter(vol, tree, 0.1).cpu().numpy().tobytes()).hexdigest()[:12]
+    print(f"{W}x{H} D={D} {kind}: depth {depth}  mst_build {t_mst:.2f} ms ({nl_launch} launches)  tree_filter {t_tf:.2f} ms  sm_nl {t_nl:.2f} ms  sha {sha}", flush=True)
