@@ -711,6 +711,27 @@ __global__ void __launch_bounds__(TFW_T)
 // a level runs a straight-line body: position = lo + tid, ring slot = position + a per-chunk offset, children read
 // without the wide-level fallback (no branch inside), one barrier.  Every other level (chunk change, wide level) takes
 // k_tf_cta's general code.  Per (node, plane) the operations and their order are unchanged: bit-identical.
+__device__ __forceinline__ uint4 tff_lds16(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 tff_lds8(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t tff_lds4(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double tff_ldsd(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tff_stsd(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 #define TFF_UP 0x80000000u
 #define TFF_DN 0x40000000u
 #define TFF_LO 0x3fffffff
@@ -726,8 +747,10 @@ __global__ void __launch_bounds__(TFW_T)
   double* lvb = reinterpret_cast<double*>(tfw_smem);                                              // [2][CAP]
   uint4* ringRec = reinterpret_cast<uint4*>(tfw_smem + 2 * (size_t)TFW_CAP * 8);                   // [S*C][2] (up) / int2 [S*C] (down)
   double* ringOwn = reinterpret_cast<double*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 32);   // [S*C]
-  uint32_t* ls = reinterpret_cast<uint32_t*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40);    // [nlevels + 1]
+  // [2 + nlevels + 1 + 2]: two pad entries on either side, so that the bounds fetched two levels ahead need no clamp
+  uint32_t* ls = reinterpret_cast<uint32_t*>(tfw_smem + 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40) + 2;
   for (int i = tid; i < 256; i += nth) tab[i] = table[i];
+  if (tid < 2) { ls[-1 - tid] = 0u; ls[nlevels + 1 + tid] = (uint32_t)N; }
   for (int l = tid; l <= nlevels; l += nth) {
     const int lo = level_start[l];
     uint32_t e = (uint32_t)lo;
@@ -743,6 +766,14 @@ __global__ void __launch_bounds__(TFW_T)
   }
   __syncthreads();
   const uint32_t recA = (uint32_t)__cvta_generic_to_shared(ringRec), ownA = (uint32_t)__cvta_generic_to_shared(ringOwn);
+  // the straight-line level body addresses shared memory by 32-bit window offsets (through generic pointers the compiler
+  // rebuilt the window base from SR_CgaCtaId at every level, on the dependent chain)
+  // (and passes them through an opaque move: otherwise they are rematerialised inside the loop just the same)
+  auto opaque = [](uint32_t x) -> uint32_t { uint32_t y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; };
+  const uint32_t lvbA = opaque((uint32_t)__cvta_generic_to_shared(lvb)), tabA = opaque((uint32_t)__cvta_generic_to_shared(tab));
+  const uint32_t lsA = opaque((uint32_t)__cvta_generic_to_shared(ls)), myA = opaque((uint32_t)tid * 8u);
+  const uint32_t recF = opaque(recA), ownF = opaque(ownA);
+  const int tidF = (int)opaque((uint32_t)tid);
   double* Ad = A + (size_t)d * N;
   const int kTop = (N - 1) / TFW_C;
   auto ring_index = [&](int q) -> int { return ((q / TFW_C) % TFW_S) * TFW_C + (q % TFW_C); };
@@ -763,31 +794,40 @@ __global__ void __launch_bounds__(TFW_T)
   int ringOff = 0;           // ring slot of position q inside the current chunk = q + ringOff
   {
     int hi = N;              // = level_start[nlevels]
-    uint32_t e = ls[nlevels - 1];
+    uint32_t e = ls[nlevels - 1], eN = ls[nlevels - 2];
+    uint32_t lsP = lsA + (uint32_t)(nlevels - 3) * 4u;   // the entry fetched two levels ahead
+    uint32_t curA = lvbA + (uint32_t)((nlevels - 1) & 1) * (TFW_CAP * 8u), kidA = lvbA + (uint32_t)(nlevels & 1) * (TFW_CAP * 8u);
     for (int l = nlevels - 1; l >= 0; l--) {
-      const uint32_t eN = ls[l > 0 ? l - 1 : 0];
+      const uint32_t eNN = tff_lds4(lsP);
       const int lo = (int)(e & TFF_LO);
-      double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
-      const double* kid = lvb + (size_t)((l + 1) & 1) * TFW_CAP;
       if (e & TFF_UP) {
-        const int q = lo + tid;
+        const int q = lo + tidF;
         if (q < hi) {
-          const int ri = q + ringOff;
-          const uint4 r0 = ringRec[2 * ri], r1 = ringRec[2 * ri + 1];
-          double acc = ringOwn[ri];
+          const uint32_t ri = (uint32_t)(q + ringOff);
+          const uint4 r0 = tff_lds16(recF + ri * 32u);
+          const uint2 r1 = tff_lds8(recF + ri * 32u + 16u);
+          const double own = tff_ldsd(ownF + ri * 8u);
+          const double v0 = tff_ldsd(kidA + r0.x * 8u), w0 = tff_ldsd(tabA + (r1.x & 0xffu) * 8u);
+          const double v1 = tff_ldsd(kidA + r0.y * 8u), w1 = tff_ldsd(tabA + ((r1.x >> 8) & 0xffu) * 8u);
+          const double v2 = tff_ldsd(kidA + r0.z * 8u), w2 = tff_ldsd(tabA + ((r1.x >> 16) & 0xffu) * 8u);
+          const double v3 = tff_ldsd(kidA + r0.w * 8u), w3 = tff_ldsd(tabA + (r1.x >> 24) * 8u);
           const int nc = (int)r1.y;
-          const double t0 = kid[r0.x] * tab[r1.x & 0xff];
-          const double t1 = kid[r0.y] * tab[(r1.x >> 8) & 0xff];
-          const double t2 = kid[r0.z] * tab[(r1.x >> 16) & 0xff];
-          const double t3 = kid[r0.w] * tab[r1.x >> 24];
-          if (nc > 0) acc += t0;
-          if (nc > 1) acc += t1;
-          if (nc > 2) acc += t2;
-          if (nc > 3) acc += t3;
+          // x + (-0.0) == x for every x (either zero included): a missing child adds -0.0, so the four additions form
+          // one unconditional chain and the selects sit beside it, not in it
+          const double t0 = nc > 0 ? v0 * w0 : -0.0;
+          const double t1 = nc > 1 ? v1 * w1 : -0.0;
+          const double t2 = nc > 2 ? v2 * w2 : -0.0;
+          const double t3 = nc > 3 ? v3 * w3 : -0.0;
+          double acc = own + t0;
+          acc += t1;
+          acc += t2;
+          acc += t3;
+          tff_stsd(curA + myA, acc);
           if (nc) Ad[q] = acc;
-          cur[tid] = acc;
         }
       } else {
+        double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
+        const double* kid = lvb + (size_t)((l + 1) & 1) * TFW_CAP;
         const int kidLo = hi;  // first position of level l + 1
         for (int c = (hi - 1) / TFW_C; c >= lo / TFW_C && hi > lo; c--) {
           while (curChunk > c) {           // first touch of chunk curChunk - 1: it is the oldest group in flight
@@ -819,7 +859,9 @@ __global__ void __launch_bounds__(TFW_T)
       }
       __syncthreads();   // the level's values are visible to the CTA before the next level reads them
       hi = lo;
-      e = eN;
+      e = eN; eN = eNN;
+      lsP -= 4u;
+      { const uint32_t t = curA; curA = kidA; kidA = t; }
     }
   }
   tfw_wait_all();
@@ -843,25 +885,27 @@ __global__ void __launch_bounds__(TFW_T)
   curChunk = -1;             // chunks <= curChunk are done with; chunk curChunk + 1 is the oldest group in flight
   {
     int lo = 0, prevLo = 0;
-    uint32_t e = ls[0], eH = ls[1];
+    uint32_t e = ls[0], eH = ls[1], eHN = ls[2];
+    uint32_t lsP = lsA + 3u * 4u;   // the entry fetched two levels ahead
+    uint32_t curA = lvbA, parA = lvbA + TFW_CAP * 8u;   // level l -> buffer l & 1; level l - 1 -> the other one
     for (int l = 0; l < nlevels; l++) {
-      const uint32_t eHN = ls[l + 2 <= nlevels ? l + 2 : nlevels];
+      const uint32_t eHNN = tff_lds4(lsP);
       const int hi = (int)(eH & TFF_LO);
-      double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
-      const double* par = lvb + (size_t)((l - 1) & 1) * TFW_CAP;
       if (e & TFF_DN) {
-        const int q = lo + tid;
+        const int q = lo + tidF;
         if (q < hi) {
-          const int ri = q + ringOff;
-          const int2 rec = ringDn[ri];
-          const double b = ringOwn[ri];
-          const double w = tab[rec.y];
-          const double pv = par[rec.x];
+          const uint32_t ri = (uint32_t)(q + ringOff);
+          const uint2 rec = tff_lds8(recF + ri * 8u);
+          const double b = tff_ldsd(ownF + ri * 8u);
+          const double w = tff_ldsd(tabA + rec.y * 8u);
+          const double pv = tff_ldsd(parA + rec.x * 8u);
           const double r = w * (pv - w * b) + b;
+          tff_stsd(curA + myA, r);
           Ad[q] = r;
-          cur[tid] = r;
         }
       } else {
+        double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
+        const double* par = lvb + (size_t)((l - 1) & 1) * TFW_CAP;
         for (int c = lo / TFW_C; c <= (hi - 1) / TFW_C && hi > lo; c++) {
           while (curChunk < c) {
             if (curChunk >= 0) { __syncthreads(); issue_dn(curChunk + TFW_S); }
@@ -887,7 +931,9 @@ __global__ void __launch_bounds__(TFW_T)
       __syncthreads();
       prevLo = lo;
       lo = hi;
-      e = eH; eH = eHN;
+      e = eH; eH = eHN; eHN = eHNN;
+      lsP += 4u;
+      { const uint32_t t = curA; curA = parA; parA = t; }
     }
   }
   tfw_wait_all();
@@ -1075,7 +1121,7 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     SM_CUDA(cudaMemcpyAsync(&h_nlev, &t.sync->nlevels, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SM_CUDA(cudaStreamSynchronize(ctx->stream));
     int lsCap = (int)min((size_t)h_nlev + 1, (227 * 1024 - tfwFixed - 2048 - 64) / 4);
-    const size_t smem = tfwFixed + (size_t)lsCap * 4;
+    const size_t smem = tfwFixed + (size_t)lsCap * 4 + 16;   // + two pad entries on either side of the bounds (k_tf_cta_fast)
     double* a = d_A;
     int n_ = (int)N, dp = Dp;
     void* args[] = {(void*)&a, (void*)&n_, (void*)&dp, (void*)&lsCap, (void*)&t.level_start, (void*)&t.rup, (void*)&t.rdn,
