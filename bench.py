@@ -283,7 +283,7 @@ def stage_bytes(name):
     b = 4
     agg = {"bytes_per_launch": 2 * V * b, "launches": 8, "kernel": "k_cbca_pass"}
     if AGGREGATION[name] == 2:   # k_nl = 4 volume passes; MST build + rooting + two tree sweeps
-        agg = {"bytes_per_launch": 4 * V * b, "launches": 1, "kernel": "nl (Boruvka MST + k_tree_bfs + k_tf_sweeps)"}
+        agg = {"bytes_per_launch": 4 * V * b, "launches": 1, "kernel": "nl (Boruvka MST + Euler-tour rooting + k_tf_cta_fast)"}
     st = {
         "cost": {"bytes_per_launch": V * b, "launches": 2,
                  "kernel": "k_cost_grad<FUSED>" if COSTCALC.get(name, 0) else "k_cost<ADCENSUS>"},

@@ -735,12 +735,36 @@ __device__ __forceinline__ void tff_stsd(uint32_t a, double v) { asm volatile("s
 #define TFF_UP 0x80000000u
 #define TFF_DN 0x40000000u
 #define TFF_LO 0x3fffffff
+__device__ __forceinline__ void tff_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tff_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tff_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tff_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __global__ void __launch_bounds__(TFW_T)
     k_tf_cta_fast(double* __restrict__ A, int N, int Dp, int lsCap, const int* __restrict__ level_start,
                   const uint4* __restrict__ rup, const int2* __restrict__ rdn, const double* __restrict__ table,
                   const nl_sync* __restrict__ s) {
   extern __shared__ __align__(16) uint8_t tfw_smem[];
   __shared__ double tab[256];
+  __shared__ __align__(8) uint64_t bars[2 * TFW_S];   // one mbarrier per ring stage and sweep
   const int tid = threadIdx.x, nth = blockDim.x;
   const int d = blockIdx.x;
   const int nlevels = s->nlevels;   // the launcher guarantees nlevels < lsCap: every bound sits in shared memory
@@ -764,6 +788,12 @@ __global__ void __launch_bounds__(TFW_T)
     }
     ls[l] = e;
   }
+  const uint32_t barA = (uint32_t)__cvta_generic_to_shared(bars);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * TFW_S; i++) tff_mbar_init(barA + i * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncthreads();
   const uint32_t recA = (uint32_t)__cvta_generic_to_shared(ringRec), ownA = (uint32_t)__cvta_generic_to_shared(ringOwn);
   // the straight-line level body addresses shared memory by 32-bit window offsets (through generic pointers the compiler
@@ -775,21 +805,25 @@ __global__ void __launch_bounds__(TFW_T)
   const uint32_t recF = opaque(recA), ownF = opaque(ownA);
   const int tidF = (int)opaque((uint32_t)tid);
   double* Ad = A + (size_t)d * N;
+  asm volatile("" : "+l"(Ad));   // one 64-bit base: a store address is then a single IMAD.WIDE
   const int kTop = (N - 1) / TFW_C;
   auto ring_index = [&](int q) -> int { return ((q / TFW_C) % TFW_S) * TFW_C + (q % TFW_C); };
 
   // ------------------------------------------------------------------ leaf to root (positions descending)
+  // a chunk = 1024 consecutive positions = one contiguous run of records and one of values: two bulk copies by the TMA
+  // unit onto the stage's mbarrier, issued by one thread (the cp.async version spent ~0.9 us of all eight warps per chunk
+  // on 3072 per-thread copies).  N is even (launcher), so every run is a multiple of 16 bytes and 16-byte aligned.
   auto issue_up = [&](int k) {
     if (k >= 0 && k <= kTop) {
-      const int st = k % TFW_S, base = k * TFW_C;
-      for (int i = tid; i < TFW_C * 2; i += nth)
-        if (base + (i >> 1) < N) tfw_cp16(recA + (uint32_t)(st * TFW_C * 2 + i) * 16u, rup + (size_t)base * 2 + i);
-      for (int i = tid; i < TFW_C; i += nth)
-        if (base + i < N) tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
+      const int st = k % TFW_S, base = k * TFW_C, cnt = min(TFW_C, N - base);
+      const uint32_t bar = barA + st * 8;
+      tff_mbar_expect(bar, (uint32_t)cnt * 40u);
+      tff_bulk(recA + (uint32_t)(st * TFW_C) * 32u, rup + (size_t)base * 2, (uint32_t)cnt * 32u, bar);
+      tff_bulk(ownA + (uint32_t)(st * TFW_C) * 8u, Ad + base, (uint32_t)cnt * 8u, bar);
     }
-    tfw_commit();   // an empty group keeps the count uniform
   };
-  for (int j = 0; j < TFW_S; j++) issue_up(kTop - j);
+  if (tid == 0)
+    for (int j = 0; j < TFW_S; j++) issue_up(kTop - j);
   int curChunk = kTop + 1;   // chunks >= curChunk are done with; chunk curChunk - 1 is the oldest group in flight
   int ringOff = 0;           // ring slot of position q inside the current chunk = q + ringOff
   {
@@ -823,18 +857,20 @@ __global__ void __launch_bounds__(TFW_T)
           acc += t2;
           acc += t3;
           tff_stsd(curA + myA, acc);
-          if (nc) Ad[q] = acc;
+          if (nc) asm volatile("st.global.f64 [%0], %1;" ::"l"(Ad + q), "d"(acc) : "memory");
         }
       } else {
         double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
         const double* kid = lvb + (size_t)((l + 1) & 1) * TFW_CAP;
         const int kidLo = hi;  // first position of level l + 1
         for (int c = (hi - 1) / TFW_C; c >= lo / TFW_C && hi > lo; c--) {
-          while (curChunk > c) {           // first touch of chunk curChunk - 1: it is the oldest group in flight
-            if (curChunk <= kTop) { __syncthreads(); issue_up(curChunk - TFW_S); }   // chunk curChunk is done with: refill its stage
-            tfw_wait_oldest();
-            __syncthreads();
+          while (curChunk > c) {           // first touch of chunk curChunk - 1
+            if (curChunk <= kTop) {          // chunk curChunk is done with: refill its stage (read only, no proxy fence)
+              __syncthreads();
+              if (tid == 0) issue_up(curChunk - TFW_S);
+            }
             curChunk--;
+            tff_mbar_wait(barA + (curChunk % TFW_S) * 8, (uint32_t)((kTop - curChunk) / TFW_S) & 1u);
           }
           const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
           for (int q = p0 + tid; q < p1; q += nth) {
@@ -857,31 +893,33 @@ __global__ void __launch_bounds__(TFW_T)
         }
         ringOff = (curChunk % TFW_S) * TFW_C - curChunk * TFW_C;
       }
+      // rotate the bounds here, not at the top: the entry loaded at the top has arrived by now
+      e = eN;
+      asm volatile("mov.u32 %0, %1;" : "=r"(eN) : "r"(eNN));
       __syncthreads();   // the level's values are visible to the CTA before the next level reads them
       hi = lo;
-      e = eN; eN = eNN;
       lsP -= 4u;
       { const uint32_t t = curA; curA = kidA; kidA = t; }
     }
   }
-  tfw_wait_all();
-  __threadfence();   // the backup values written above are read back through cp.async below
+  // the backup values written above (generic proxy) are read back by the TMA unit (async proxy) below
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
 
   // ------------------------------------------------------------------ root to leaf (positions ascending)
   auto issue_dn = [&](int k) {
     if (k >= 0 && k <= kTop) {
-      const int st = k % TFW_S, base = k * TFW_C;
-      for (int i = tid; i < TFW_C; i += nth)
-        if (base + i < N) {
-          tfw_cp8(recA + (uint32_t)(st * TFW_C + i) * 8u, rdn + base + i);
-          tfw_cp8(ownA + (uint32_t)(st * TFW_C + i) * 8u, Ad + base + i);
-        }
+      const int st = k % TFW_S, base = k * TFW_C, cnt = min(TFW_C, N - base);
+      const uint32_t bar = barA + (TFW_S + st) * 8;
+      tff_mbar_expect(bar, (uint32_t)cnt * 16u);
+      tff_bulk(recA + (uint32_t)(st * TFW_C) * 8u, rdn + base, (uint32_t)cnt * 8u, bar);
+      tff_bulk(ownA + (uint32_t)(st * TFW_C) * 8u, Ad + base, (uint32_t)cnt * 8u, bar);
     }
-    tfw_commit();
   };
   const int2* ringDn = reinterpret_cast<const int2*>(ringRec);
-  for (int j = 0; j < TFW_S; j++) issue_dn(j);
+  if (tid == 0)
+    for (int j = 0; j < TFW_S; j++) issue_dn(j);
   curChunk = -1;             // chunks <= curChunk are done with; chunk curChunk + 1 is the oldest group in flight
   {
     int lo = 0, prevLo = 0;
@@ -901,17 +939,19 @@ __global__ void __launch_bounds__(TFW_T)
           const double pv = tff_ldsd(parA + rec.x * 8u);
           const double r = w * (pv - w * b) + b;
           tff_stsd(curA + myA, r);
-          Ad[q] = r;
+          asm volatile("st.global.f64 [%0], %1;" ::"l"(Ad + q), "d"(r) : "memory");
         }
       } else {
         double* cur = lvb + (size_t)(l & 1) * TFW_CAP;
         const double* par = lvb + (size_t)((l - 1) & 1) * TFW_CAP;
         for (int c = lo / TFW_C; c <= (hi - 1) / TFW_C && hi > lo; c++) {
           while (curChunk < c) {
-            if (curChunk >= 0) { __syncthreads(); issue_dn(curChunk + TFW_S); }
-            tfw_wait_oldest();
-            __syncthreads();
+            if (curChunk >= 0) {
+              __syncthreads();
+              if (tid == 0) issue_dn(curChunk + TFW_S);
+            }
             curChunk++;
+            tff_mbar_wait(barA + (TFW_S + curChunk % TFW_S) * 8, (uint32_t)(curChunk / TFW_S) & 1u);
           }
           if (l == 0) continue;            // the root keeps its backup value (already in A and in the level buffer)
           const int p0 = max(lo, c * TFW_C), p1 = min(hi, (c + 1) * TFW_C);
@@ -928,15 +968,15 @@ __global__ void __launch_bounds__(TFW_T)
         }
         ringOff = (curChunk % TFW_S) * TFW_C - curChunk * TFW_C;
       }
+      e = eH; eH = eHN;
+      asm volatile("mov.u32 %0, %1;" : "=r"(eHN) : "r"(eHNN));
       __syncthreads();
       prevLo = lo;
       lo = hi;
-      e = eH; eH = eHN; eHN = eHNN;
       lsP += 4u;
       { const uint32_t t = curA; curA = parA; parA = t; }
     }
   }
-  tfw_wait_all();
 }
 
 __global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp,
@@ -1127,7 +1167,7 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     void* args[] = {(void*)&a, (void*)&n_, (void*)&dp, (void*)&lsCap, (void*)&t.level_start, (void*)&t.rup, (void*)&t.rdn,
                     (void*)&d_tab, (void*)&t.sync};
     static const int tfw_fast = getenv("SM_NL_TF_FAST") ? atoi(getenv("SM_NL_TF_FAST")) : 1;   // 0: k_tf_cta (general code at every level)
-    const void* fn = (tfw_fast && h_nlev < lsCap) ? (const void*)k_tf_cta_fast : (const void*)k_tf_cta;
+    const void* fn = (tfw_fast && h_nlev < lsCap && N % 2 == 0) ? (const void*)k_tf_cta_fast : (const void*)k_tf_cta;
     SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const int tfw_t = getenv("SM_NL_TFW_T") ? atoi(getenv("SM_NL_TFW_T")) : TFW_T;   // tuning switch (<= 256)
     SM_CUDA(cudaLaunchKernel(fn, dim3(Dp), dim3(tfw_t), args, smem, ctx->stream));
