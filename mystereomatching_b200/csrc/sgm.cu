@@ -288,6 +288,79 @@ __global__ void __launch_bounds__(32)
   sgm_wait<0>();
 }
 
+// Any direction, cp.async staged: k_sgm_path_h's pipeline on the scan-line geometry of k_sgm_path.  For SMALL frames: a
+// sweep is then a few hundred warps (3 per SM at 450x375), each a chain of H or W dependent steps, and k_sgm_path's
+// register prefetch cannot run ahead of the chain -- a warp has six scoreboards for all its loads, shuffles and the
+// redux, so consuming slot i+1 waits for the refill of slot i just issued: ncu launch list, 450x375 D=64: 0.6 us per
+// step = one memory latency per pixel.  cp.async completes in order against ONE counter (wait_group), so SGM_NSTG
+// pixels really are in flight.  Runs of 4 disparities per lane (D <= 128: the lanes past D idle).
+template <int VPL, int MODE>
+__global__ void __launch_bounds__(32)
+    k_sgm_path_s(const float* __restrict__ vol, const uint32_t* __restrict__ pix, float* __restrict__ out, sgm_geom g,
+                 int D, int corDifThres, float redu, int16_t* __restrict__ disp) {
+  extern __shared__ __align__(16) uint8_t sgm_smem[];
+  constexpr int NS = SGM_NSTG + 1;                       // slots
+  constexpr int RUNB = VPL * 4;                          // bytes of one lane's run
+  constexpr int SLOTB = 32 * RUNB * (MODE >= 1 ? 2 : 1) + 128;   // C run | S run | pixel word, per lane
+  const int lane = threadIdx.x;
+  int v, u, len;
+  line_start(g, blockIdx.x, v, u, len);
+  const int d0 = lane * VPL;
+  const bool act = d0 < D;                               // D % 4 == 0 and VPL % 4 == 0: a run is wholly in or out
+  const int nq = act ? min(VPL, D - d0) / 4 : 0;         // 16-byte pieces of this lane's run
+  const long long pstep = (long long)g.mv * g.W + g.mu;
+  long long p = (long long)v * g.W + u;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sgm_smem);
+  const uint32_t cOff = base + lane * RUNB, sOff = cOff + 32 * RUNB, xOff = base + 32 * RUNB * (MODE >= 1 ? 2 : 1) + lane * 4;
+
+  auto issue = [&](int t, int slot) {
+    if (t < len) {
+      const long long q = p + pstep * t;
+      const uint32_t so = slot * SLOTB;
+      for (int k = 0; k < nq; k++) {
+        sgm_cp16(cOff + so + k * 16, vol + q * D + d0 + k * 4);
+        if (MODE >= 1) sgm_cp16(sOff + so + k * 16, out + q * D + d0 + k * 4);
+      }
+      sgm_cp4(xOff + so, pix + q);
+    }
+    sgm_commit();
+  };
+  const long long p0 = p;
+  (void)p0;
+  for (int t = 0; t < SGM_NSTG; t++) issue(t, t);
+  float prev[VPL];
+  float minC = 0.f;
+  uint32_t xprev = 0;
+  int rd = 0, wr = SGM_NSTG;
+  // note: `issue` indexes pixels from the line start, so keep p fixed and carry the running pixel separately
+  long long pc = p;
+  for (int t = 0; t < len; t++) {
+    sgm_wait<SGM_NSTG - 1>();
+    float c[VPL], s[VPL];
+    const uint32_t so = rd * SLOTB;
+#pragma unroll
+    for (int k = 0; k < VPL / 4; k++) {
+      float4 a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < nq) {
+        a = sgm_lds16(cOff + so + k * 16);
+        if (MODE >= 1) b = sgm_lds16(sOff + so + k * 16);
+      }
+      c[4 * k] = a.x; c[4 * k + 1] = a.y; c[4 * k + 2] = a.z; c[4 * k + 3] = a.w;
+      s[4 * k] = b.x; s[4 * k + 1] = b.y; s[4 * k + 2] = b.z; s[4 * k + 3] = b.w;
+    }
+    const uint32_t x = sgm_lds4(xOff + so);
+    issue(t + SGM_NSTG, wr);
+    sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, pc);
+#pragma unroll
+    for (int k = 0; k < VPL / 4; k++)
+      if (k < nq) *reinterpret_cast<float4*>(out + pc * D + d0 + k * 4) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    pc += pstep;
+    if (++rd == NS) rd = 0;
+    if (++wr == NS) wr = 0;
+  }
+  sgm_wait<0>();
+}
+
 // Horizontal paths through the TMA unit.  A row is one contiguous run of W*D floats, so whole groups of SGM_TK
 // pixels (C run, S run, pixel words) are fetched with cp.async.bulk by one lane and land on an mbarrier; the
 // LDGSTS pipe, which caps cp.async at ~16 B/clk/SM (~4.7 TB/s chip-wide, see scripts/microbench), is not involved.
@@ -443,6 +516,22 @@ static int launch_sgm_h(sm_ctx* ctx, const float* vol, const uint32_t* pix, floa
   return launch_sgm_h1<VPL, 2>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
 }
 
+template <int VPL, int MODE>
+static int launch_sgm_s1(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, const sgm_geom& g, int D, int thr,
+                         float redu, int16_t* disp) {
+  const size_t smem = (size_t)(SGM_NSTG + 1) * (32 * VPL * 4 * (MODE >= 1 ? 2 : 1) + 128);
+  SM_CUDA(cudaFuncSetAttribute(k_sgm_path_s<VPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SM_LAUNCH(ctx, (k_sgm_path_s<VPL, MODE>), g.nLines, 32, smem, vol, pix, out, g, D, thr, redu, disp);
+  return SM_OK;
+}
+template <int VPL>
+static int launch_sgm_s(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, const sgm_geom& g, int D, int thr,
+                        float redu, int mode, int16_t* disp) {
+  if (mode == 0) return launch_sgm_s1<VPL, 0>(ctx, vol, pix, out, g, D, thr, redu, disp);
+  if (mode == 1) return launch_sgm_s1<VPL, 1>(ctx, vol, pix, out, g, D, thr, redu, disp);
+  return launch_sgm_s1<VPL, 2>(ctx, vol, pix, out, g, D, thr, redu, disp);
+}
+
 // mode 0: d_out = Lr; 1: d_out += Lr; 2: d_out += Lr and d_disp = WTA of the finished sum
 int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                          int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp) {
@@ -453,6 +542,18 @@ int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix,
   const bool vec = (D % 4 == 0) && (((uintptr_t)d_vol | (uintptr_t)d_out) % 16 == 0);
   const int vpl = D <= 32 ? 1 : D <= 64 ? 2 : D <= 128 ? 4 : D <= 256 ? 8 : 16;
   static const int staged_env = getenv("SM_SGM_STAGED") ? atoi(getenv("SM_SGM_STAGED")) : 2;   // tuning switch
+  // small frames (few scan lines): the cp.async staged kernel in every direction, runs of >= 4 disparities per lane
+  static const int small_env = getenv("SM_SGM_SMALL_LINES") ? atoi(getenv("SM_SGM_SMALL_LINES")) : 1024;   // 0: off
+  if (vec && ((uintptr_t)d_pix & 3) == 0 && g.nLines <= small_env) {
+    const int vs = max(vpl, 4);
+    const bool tma = g.mv == 0 && staged_env == 2 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0;
+    if (!tma) {
+      if (vs == 4) return launch_sgm_s<4>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+      if (vs == 8) return launch_sgm_s<8>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+      return launch_sgm_s<16>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+    }
+    if (vs == 4) return launch_sgm_t<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
+  }
   // horizontal: few, contiguous lines.  2 = TMA bulk staging, 1 = cp.async staging, 0 = the generic kernel
   if (g.mv == 0 && vec && vpl >= 4 && staged_env == 2 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0) {
     if (vpl == 4) return launch_sgm_t<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);

@@ -339,6 +339,28 @@ def test_tree_filter_bit_exact(ctx, name, D):
         assert _bits_equal(got, cost.astype(np.float32))     # same f64 operation order -> identical after the cast
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape", [(200, 300), (201, 301), (96, 1024)])
+def test_tree_filter_bit_exact_many_chunks(ctx, shape):
+    """Enough nodes for dozens of 1024-position chunks (the streamed filter's ring wraps many times, levels straddle
+    chunk boundaries); odd N takes the general kernel, even N the lean level loop -- both must equal the oracle."""
+    H, W = shape
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    img[: H // 2] = (img[: H // 2] // 64) * 64          # a flatter half: wider levels
+    D = 3
+    vol = rng.random((H, W, D)).astype(np.float32) - 0.25   # negative costs too (the -0.0 identity must hold)
+    tree = ctx.mst_build(ctx.dev(img))
+    got = ctx.tree_filter(ctx.dev(vol.copy()), tree, 0.1).cpu().numpy()
+    t = po.mst(img)
+    table = np.empty(256, np.float64)
+    po.lib().orc_tree_table(0.1, table)
+    cost = vol.astype(np.float64).copy()
+    tmp = np.empty_like(cost)
+    po.lib().orc_tree_filter(cost, tmp, H * W, D, t["parent"], t["weight"], t["nr_child"], t["children"], t["order"], table)
+    assert _bits_equal(got, cost.astype(np.float32))
+
+
 @pytest.mark.timeout(120)
 def test_tree_filter_matches_reference_golden(ctx, golden_dir):
     import os
