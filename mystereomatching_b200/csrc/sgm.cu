@@ -300,63 +300,72 @@ __global__ void __launch_bounds__(32)
                  int D, int corDifThres, float redu, int16_t* __restrict__ disp) {
   extern __shared__ __align__(16) uint8_t sgm_smem[];
   constexpr int NS = SGM_NSTG + 1;                       // slots
+  constexpr int NQ = VPL / 4;                            // 16-byte pieces of one lane's run
   constexpr int RUNB = VPL * 4;                          // bytes of one lane's run
-  constexpr int SLOTB = 32 * RUNB * (MODE >= 1 ? 2 : 1) + 128;   // C run | S run | pixel word, per lane
+  constexpr uint32_t SLOTB = 32 * RUNB * (MODE >= 1 ? 2 : 1) + 128;   // C run | S run | pixel word, per lane
   const int lane = threadIdx.x;
   int v, u, len;
   line_start(g, blockIdx.x, v, u, len);
   const int d0 = lane * VPL;
-  const bool act = d0 < D;                               // D % 4 == 0 and VPL % 4 == 0: a run is wholly in or out
-  const int nq = act ? min(VPL, D - d0) / 4 : 0;         // 16-byte pieces of this lane's run
+  // with a single warp per scan line the time per pixel is the warp's own instruction count (ncu: 170 per pixel at
+  // 0.33 IPC, no memory stall left), so everything per pixel is incremental: byte pointers advanced by the line step,
+  // slot offsets wrapped by one compare, the pieces of a run unrolled under per-lane predicates
   const long long pstep = (long long)g.mv * g.W + g.mu;
-  long long p = (long long)v * g.W + u;
+  const long long stepB = pstep * D * 4;
+  long long pc = (long long)v * g.W + u;
+  const uint8_t* cg = reinterpret_cast<const uint8_t*>(vol + pc * D + d0);   // next pixel to fetch: C run, S run, pixel word
+  const uint8_t* sg = reinterpret_cast<const uint8_t*>(out + pc * D + d0);
+  const uint8_t* xg = reinterpret_cast<const uint8_t*>(pix + pc);
+  uint8_t* og = reinterpret_cast<uint8_t*>(out + pc * D + d0);               // pixel being computed: S run
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(sgm_smem);
   const uint32_t cOff = base + lane * RUNB, sOff = cOff + 32 * RUNB, xOff = base + 32 * RUNB * (MODE >= 1 ? 2 : 1) + lane * 4;
+  int ti = 0;                 // pixels issued so far
+  uint32_t wr = 0, rd = 0;    // slot byte offsets
 
-  auto issue = [&](int t, int slot) {
-    if (t < len) {
-      const long long q = p + pstep * t;
-      const uint32_t so = slot * SLOTB;
-      for (int k = 0; k < nq; k++) {
-        sgm_cp16(cOff + so + k * 16, vol + q * D + d0 + k * 4);
-        if (MODE >= 1) sgm_cp16(sOff + so + k * 16, out + q * D + d0 + k * 4);
-      }
-      sgm_cp4(xOff + so, pix + q);
+  auto issue = [&]() {
+    if (ti < len) {
+#pragma unroll
+      for (int k = 0; k < NQ; k++)
+        if (d0 + 4 * k < D) {  // D % 4 == 0: a piece is wholly in or out
+          sgm_cp16(cOff + wr + k * 16, cg + k * 16);
+          if (MODE >= 1) sgm_cp16(sOff + wr + k * 16, sg + k * 16);
+        }
+      sgm_cp4(xOff + wr, xg);
     }
     sgm_commit();
+    cg += stepB; sg += stepB; xg += pstep * 4;
+    ti++;
+    wr += SLOTB;
+    if (wr == NS * SLOTB) wr = 0;
   };
-  const long long p0 = p;
-  (void)p0;
-  for (int t = 0; t < SGM_NSTG; t++) issue(t, t);
+  for (int t = 0; t < SGM_NSTG; t++) issue();
   float prev[VPL];
   float minC = 0.f;
   uint32_t xprev = 0;
-  int rd = 0, wr = SGM_NSTG;
-  // note: `issue` indexes pixels from the line start, so keep p fixed and carry the running pixel separately
-  long long pc = p;
   for (int t = 0; t < len; t++) {
     sgm_wait<SGM_NSTG - 1>();
     float c[VPL], s[VPL];
-    const uint32_t so = rd * SLOTB;
 #pragma unroll
-    for (int k = 0; k < VPL / 4; k++) {
+    for (int k = 0; k < NQ; k++) {
       float4 a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX), b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k < nq) {
-        a = sgm_lds16(cOff + so + k * 16);
-        if (MODE >= 1) b = sgm_lds16(sOff + so + k * 16);
+      if (d0 + 4 * k < D) {
+        a = sgm_lds16(cOff + rd + k * 16);
+        if (MODE >= 1) b = sgm_lds16(sOff + rd + k * 16);
       }
       c[4 * k] = a.x; c[4 * k + 1] = a.y; c[4 * k + 2] = a.z; c[4 * k + 3] = a.w;
       s[4 * k] = b.x; s[4 * k + 1] = b.y; s[4 * k + 2] = b.z; s[4 * k + 3] = b.w;
     }
-    const uint32_t x = sgm_lds4(xOff + so);
-    issue(t + SGM_NSTG, wr);
+    const uint32_t x = sgm_lds4(xOff + rd);
+    issue();
     sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, pc);
 #pragma unroll
-    for (int k = 0; k < VPL / 4; k++)
-      if (k < nq) *reinterpret_cast<float4*>(out + pc * D + d0 + k * 4) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    for (int k = 0; k < NQ; k++)
+      if (d0 + 4 * k < D)
+        *reinterpret_cast<float4*>(og + k * 16) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    og += stepB;
     pc += pstep;
-    if (++rd == NS) rd = 0;
-    if (++wr == NS) wr = 0;
+    rd += SLOTB;
+    if (rd == NS * SLOTB) rd = 0;
   }
   sgm_wait<0>();
 }
