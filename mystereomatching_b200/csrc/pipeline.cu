@@ -234,11 +234,31 @@ static int pl_cost_calculate(sm_pipeline* pl) {
       SM_TRY(sm_cross_scale_weights(1, P.crossScaleLambda, &post));
       pl->scale_folded = post != 1.0f;
     }
+    if (views == 2 && pl->stream2 && pl->vol[3]) {
+      // small frames: a pass is a few hundred one-warp blocks marching along their lines (5 per SM at 450x375), so the
+      // two views' passes run concurrently, view 1 on the second stream with its own scratch volume
+      SM_CUDA(cudaEventRecord(pl->evFork, c->stream));
+      SM_CUDA(cudaStreamWaitEvent(pl->stream2, pl->evFork, 0));
+      cudaStream_t main_stream = c->stream;
+      int rc2 = smi_cbca_packed(c, pl->vol[0], pl->vol[2], pl->armpk[0], pl->armpk[1], H, W, D, P.cbca_iterationNum, 0,
+                                Lmax, smi_arm_pad(D), post);
+      c->stream = pl->stream2;
+      if (rc2 == SM_OK)
+        rc2 = smi_cbca_packed(c, pl->vol[1], pl->vol[3], pl->armpk[0], pl->armpk[1], H, W, D, P.cbca_iterationNum, 1,
+                              Lmax, smi_arm_pad(D), post);
+      c->stream = main_stream;
+      SM_TRY(rc2);
+      SM_CUDA(cudaEventRecord(pl->evJoin, pl->stream2));
+      SM_CUDA(cudaStreamWaitEvent(c->stream, pl->evJoin, 0));
+    } else
     for (int i = 0; i < views; i++)
       SM_TRY(smi_cbca_packed(c, pl->vol[i], pl->vol[2], pl->armpk[0], pl->armpk[1], H, W, D, P.cbca_iterationNum, i,
                              Lmax, smi_arm_pad(D), post));
   } else if (P.aggregation == 2) {
     PL_MARK(3);
+    // (tried: view 1's SGM sweeps on the second stream under the MST build and tree filter of view 0 -- its volume is final
+    // before the aggregation in NL mode.  Slower: the filter is a latency chain of one CTA per SM, and the sweeps' warps on
+    // the same SMs stretch it, 2.93 -> 3.13 ms against 0.14 ms saved.)
     SM_TRY(smi_nl(c, pl->bgr[0], pl->vol[0], pl->nlwork, H, W, D));
   } else {
     PL_MARK(3);
