@@ -22,7 +22,7 @@ struct sm_scratch {
 };
 
 enum { SM_SCR_IMG0 = 0, SM_SCR_IMG1, SM_SCR_ARM0, SM_SCR_ARM1, SM_SCR_TAB, SM_SCR_MISC0, SM_SCR_MISC1,
-       SM_SCR_MISC2, SM_SCR_MISC3, SM_SCR_MISC4, SM_SCR_MISC5, SM_SCR_NLWORK, SM_SCR_SGMEDGE, SM_SCR_NLREC, SM_SCR_NLEULER, SM_SCR_COUNT };
+       SM_SCR_MISC2, SM_SCR_MISC3, SM_SCR_MISC4, SM_SCR_MISC5, SM_SCR_NLWORK, SM_SCR_SGMEDGE, SM_SCR_NLREC, SM_SCR_NLEULER, SM_SCR_RVLIST, SM_SCR_COUNT };
 
 struct sm_ctx {
   int device = 0;

@@ -16,6 +16,9 @@
 #include <float.h>
 #include <limits.h>
 
+#include <stdlib.h>
+#include <limits.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------ WTA
@@ -201,13 +204,111 @@ __global__ void __launch_bounds__(RV_WARPS * 32)
   }
 }
 
+// Two steps instead of one persistent sweep.  k_region_vote walks ALL pixels one per warp iteration (a dependent 2-byte
+// load each) and, inside a vote, reads one row's arms, then that row's disparities, row after row -- two dependent
+// global loads per row, ~20 rows per vote: a chain of latencies (0.26 ms per call at 1080p).  Here k_rv_scan copies the
+// valid pixels through (one thread per pixel, coalesced) and appends the invalid ones to a list; k_rv_vote takes one
+// warp per list entry, fetches the arms of ALL rows of the region in one round (lane = row), broadcasts them by
+// shuffles, and reads the disparities of four rows per round.  Same votes, same integer rule: identical output.
+__global__ void k_rv_scan(const int16_t* __restrict__ src, int16_t* __restrict__ dst, long long npix, int* __restrict__ count,
+                          int* __restrict__ list) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int16_t cur = src[p];
+  if (cur >= 0) dst[p] = cur;
+  else list[atomicAdd(count, 1)] = (int)p;   // warp-aggregated by the compiler
+}
+
+__global__ void __launch_bounds__(RV_WARPS * 32)
+    k_rv_vote(const int16_t* __restrict__ src, int16_t* __restrict__ dst, const uint16_t* __restrict__ arms, int H, int W,
+              int D, float ratio, int S, const int* __restrict__ count, const int* __restrict__ list) {
+  extern __shared__ int hist_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* hist = hist_all + warp * D;
+  const int n = *count;
+  for (int e = blockIdx.x * RV_WARPS + warp; e < n; e += gridDim.x * RV_WARPS) {
+    const int p = list[e];
+    const int16_t cur = src[p];
+    const int v = p / W, u = p - v * W;
+    for (int d = lane; d < D; d += 32) hist[d] = 0;
+    const uint16_t* a = arms + (size_t)p * 5;
+    const int vb = v - a[2], ve = v + a[3];
+    const int nrows = ve - vb + 1;           // <= 2 * 255 + 1
+    __syncwarp();
+    int valid = 0;
+    for (int r0 = 0; r0 < nrows; r0 += 32) {
+      // lane = row: the horizontal arms of 32 rows of the region in one round
+      int ub = 0, ue = -1;
+      if (r0 + lane < nrows) {
+        const uint16_t* b = arms + ((size_t)(vb + r0 + lane) * W + u) * 5;
+        ub = u - b[0]; ue = u + b[1];
+      }
+      const int nr = min(32, nrows - r0);
+      for (int r = 0; r < nr; r += 4) {
+        int x[4], un[4], uE[4];
+        const int16_t* row[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {        // four rows' first 32 columns in flight together
+          const int rr = min(r + k, nr - 1);
+          const int b0 = __shfl_sync(0xffffffffu, ub, rr);
+          uE[k] = r + k < nr ? __shfl_sync(0xffffffffu, ue, rr) : INT_MIN;
+          un[k] = b0 + lane;
+          row[k] = src + (size_t)(vb + r0 + rr) * W;
+          x[k] = un[k] <= uE[k] ? (int)row[k][un[k]] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (x[k] >= 0) { valid++; if (x[k] < D) atomicAdd(&hist[x[k]], 1); }
+          for (int w = un[k] + 32; w <= uE[k]; w += 32) {   // rows wider than a warp
+            const int y = row[k][w];
+            if (y >= 0) { valid++; if (y < D) atomicAdd(&hist[y], 1); }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    __syncwarp();
+    int16_t res = cur;
+    if (valid > S) {
+      // mode with the lowest d on ties: maximise (count, -d)
+      int bc = -1, bd = 0;
+      for (int d = lane; d < D; d += 32) {
+        const int c = hist[d];
+        if (c > bc) { bc = c; bd = d; }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o), od = __shfl_xor_sync(0xffffffffu, bd, o);
+        if (oc > bc || (oc == bc && od < bd)) { bc = oc; bd = od; }
+      }
+      if ((float)(bc / valid) >= ratio) res = (int16_t)bd;  // integer division, as the reference
+    }
+    if (lane == 0) dst[p] = res;
+    __syncwarp();
+  }
+}
+
 extern "C" int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint16_t* d_arms, int H, int W, int D,
                               float ratio, int S) {
   SM_CHECK_ARG(ctx && d_disp && d_tmp && d_arms && H > 0 && W > 0 && D > 0 && D <= 4096);
   const long long npix = (long long)H * W;
-  int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
-  SM_LAUNCH(ctx, k_region_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio,
-            S);
+  static const int rv_list = getenv("SM_RV_LIST") ? atoi(getenv("SM_RV_LIST")) : 1;   // 0: the one-kernel sweep
+  if (rv_list && npix < (1ll << 31)) {
+    void* p;
+    SM_TRY(sm_scratch_get(ctx, SM_SCR_RVLIST, 256 + (size_t)npix * 4, &p));
+    int* count = (int*)p;
+    int* list = (int*)((uint8_t*)p + 256);
+    SM_CUDA(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream));
+    SM_LAUNCH(ctx, k_rv_scan, (int)((npix + 255) / 256), 256, 0, d_disp, d_tmp, npix, count, list);
+    const int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
+    SM_LAUNCH(ctx, k_rv_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio, S,
+              count, list);
+  } else {
+    int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
+    SM_LAUNCH(ctx, k_region_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio,
+              S);
+  }
   SM_CUDA(cudaMemcpyAsync(d_disp, d_tmp, npix * sizeof(int16_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return SM_OK;
 }
