@@ -258,6 +258,14 @@ int sm_sgm_grouped2(sm_ctx* ctx, const float* d_volL, const float* d_volR, const
 int sm_wta(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int16_t* d_disp);
 /* wta_Co (stereoMatching.cpp:2709-2792): left map and right map from the LEFT
  * volume's diagonal, both multiplied by `scale` (DISP_SCALE = 16). */
+/* selectTopCostFromVolumn (stereoMatching.h:2405-2461; called on a clone of vm,
+ * stereoMatching.cpp:1118-1119): per pixel up to `num` candidate disparities in
+ * order of increasing cost -- first minimum of what is left, lowest d on ties;
+ * candidate 0 always, candidate k > 0 only while cost < firstCost * thres.
+ * d_top = float [H][W][num+1][2]: [k] = {d, cost}, [num][0] = candidate count;
+ * entries the reference leaves unwritten are 0.  d_vol is not modified. */
+int sm_select_top_cost(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int num,
+                       float thres, float* d_top);
 int sm_wta_co(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int scale, int16_t* d_D1,
               int16_t* d_D2);
 

@@ -97,6 +97,7 @@ SIGNATURES = {
     "sm_vol_accumulate": ([_P, _P, _P, _Z], _I),
     "sm_wta": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_wta_co": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
+    "sm_select_top_cost": ([_P, _P, _I, _I, _I, _I, _F, _P], _I),
     "sm_lrc": ([_P, _P, _P, _I, _I, _F], _I),
     "sm_lrc_label": ([_P, _P, _P, _I, _I, _I, _F, _I, _I, _P], _I),
     "sm_region_vote": ([_P, _P, _P, _P, _I, _I, _I, _F, _I], _I),
@@ -377,6 +378,14 @@ class Ctx:
         H, W, D = vol.shape
         out = self.empty((H, W), self.torch.int16)
         check(self.L.sm_wta(self.h, _ptr(vol), H, W, D, _ptr(out)))
+        return out
+
+    def select_top_cost(self, vol, num, thres):
+        """selectTopCostFromVolumn (stereoMatching.h:2405-2461): float [H][W][num+1][2] = {d, cost} per candidate,
+        [num][0] = candidate count."""
+        H, W, D = vol.shape
+        out = self.empty((H, W, num + 1, 2), self.torch.float32)
+        check(self.L.sm_select_top_cost(self.h, _ptr(vol), H, W, D, num, thres, _ptr(out)))
         return out
 
     def wta_co(self, vol, scale=16):

@@ -107,6 +107,64 @@ extern "C" int sm_wta_co(sm_ctx* ctx, const float* d_vol, int H, int W, int D, i
   return SM_OK;
 }
 
+// ------------------------------------------------------------------ candidate disparities (first half)
+// selectTopCostFromVolumn (stereoMatching.h:2405-2461): per pixel, up to `num` rounds of "first minimum of what is left"
+// (strict '>' scan in increasing d -> the lowest d among equal minima; a taken entry becomes FLT_MAX); candidate 0 is
+// always taken, candidate k > 0 only while its cost < firstCost * thres.  topDisp[v][u][k] = {d, cost},
+// topDisp[v][u][num][0] = number of candidates.  The reference works on a clone of vm, so d_vol is read only here; the
+// entries the reference leaves unwritten (its Mat is uninitialised there) are 0.
+// One warp per pixel: the D costs sit in shared memory, lane l scans d = l, l + 32, ...; a round is a lane-local first
+// minimum, one redux over the order-preserving integer image of the floats and one over the candidate d.
+#define TOP_WARPS 8
+__device__ __forceinline__ uint32_t top_f2key(float x) {
+  uint32_t b = __float_as_uint(x + 0.0f);   // -0 -> +0: the reference's '>' does not tell them apart
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__global__ void __launch_bounds__(TOP_WARPS * 32)
+    k_select_top(const float* __restrict__ vol, long long npix, int D, int num, float thres, float* __restrict__ top) {
+  extern __shared__ float top_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* c = top_smem + (size_t)warp * D;
+  long long p = (long long)blockIdx.x * TOP_WARPS + warp;
+  const long long stride = (long long)gridDim.x * TOP_WARPS;
+  for (; p < npix; p += stride) {
+    for (int d = lane; d < D; d += 32) c[d] = vol[p * D + d];
+    float* o = top + p * (long long)(num + 1) * 2;
+    for (int i = lane; i < (num + 1) * 2; i += 32) o[i] = 0.f;
+    __syncwarp();
+    float firstV = 0.f;
+    int count = 0;
+    for (int k = 0; k < num; k++) {
+      uint32_t bk = 0xffffffffu;
+      int bd = 0x7fffffff;
+      for (int d = lane; d < D; d += 32) {
+        const uint32_t key = top_f2key(c[d]);
+        if (key < bk) { bk = key; bd = d; }     // strict: the lowest d of this lane's equal minima
+      }
+      const uint32_t km = __reduce_min_sync(0xffffffffu, bk);
+      const int d = (int)__reduce_min_sync(0xffffffffu, bk == km ? (unsigned)bd : 0x7fffffffu);
+      const float val = c[d];                    // the value as stored (sign of zero included)
+      if (k == 0) firstV = val;
+      else if (!(val < firstV * thres)) break;
+      __syncwarp();
+      if (lane == 0) { c[d] = FLT_MAX; o[2 * k] = (float)d; o[2 * k + 1] = val; }
+      count++;
+      __syncwarp();
+    }
+    if (lane == 0) o[2 * num] = (float)count;
+    __syncwarp();
+  }
+}
+
+extern "C" int sm_select_top_cost(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int num, float thres,
+                                  float* d_top) {
+  SM_CHECK_ARG(ctx && d_vol && d_top && H > 0 && W > 0 && D > 0 && D <= 1024 && num >= 1 && num <= 64);   // 8 warps x D floats of shared memory
+  const long long npix = (long long)H * W;
+  const int grid = (int)min((long long)ctx->num_sms * 8, (npix + TOP_WARPS - 1) / TOP_WARPS);
+  SM_LAUNCH(ctx, k_select_top, grid, TOP_WARPS * 32, TOP_WARPS * D * sizeof(float), d_vol, npix, D, num, thres, d_top);
+  return SM_OK;
+}
+
 // ------------------------------------------------------------------ LR check
 // In-place on D1 is safe: each thread reads D1 only at its own pixel.
 __global__ void k_lrc(int16_t* __restrict__ D1, const int16_t* __restrict__ D2, int H, int W, float maxDiff) {

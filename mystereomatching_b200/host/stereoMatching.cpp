@@ -721,6 +721,30 @@ void StereoMatching::wta_Co(cv::Mat& vm_, cv::Mat& D1, cv::Mat& D2) {
   download(D2.data, b.p, pb);
 }
 
+// selectTopCostFromVolumn (stereoMatching.h:2405-2461): the candidates come from sm_select_top_cost; the reference also
+// overwrites the entries it takes in the Mat it is handed (its caller passes a clone, stereoMatching.cpp:1118), which
+// is replayed on the host copy from the candidate list.
+void StereoMatching::selectTopCostFromVolumn(Mat& vm_, Mat& topDisp, float thres) {
+  CV_Assert(topDisp.dims == 4);
+  CV_Assert(topDisp.type() == CV_32F);
+  CV_Assert(topDisp.size[0] == h_ && topDisp.size[1] == w_ && topDisp.size[2] >= 2 && topDisp.size[3] == 2);
+  const int num = topDisp.size[2] - 1;
+  const int idx = &vm_ == &vm[0] ? 0 : (&vm_ == &vm[1] ? 1 : -1);
+  const size_t vb = (size_t)h_ * w_ * d_ * 4, tb = (size_t)h_ * w_ * (num + 1) * 2 * 4;
+  const float* src;
+  TmpDev v(ctx_, idx >= 0 ? 16 : vb), t(ctx_, tb);
+  if (idx >= 0) { uploadVm(idx); src = d_vol_[idx]; }
+  else { upload(v.p, vm_.data, vb); src = v.as<float>(); }
+  check(sm_select_top_cost(ctx_, src, h_, w_, d_, num, thres, t.as<float>()), "sm_select_top_cost");
+  download(topDisp.data, t.p, tb);
+  if (idx >= 0) hostVm(idx);   // the host copy is brought up to date before its taken entries are overwritten
+  float* c = vm_.ptr<float>();
+  const float* o = topDisp.ptr<float>();
+  for (size_t i = 0; i < (size_t)h_ * w_; i++, c += d_, o += (size_t)(num + 1) * 2)
+    for (int k = 0; k < (int)o[2 * num]; k++) c[(int)o[2 * k]] = std::numeric_limits<float>::max();
+  if (idx >= 0) vm_dev_fresh_[idx] = false;
+}
+
 // ------------------------------------------------------------------ refinement
 void StereoMatching::LRConsistencyCheck_normal(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR) {
   (void)errMask;

@@ -141,6 +141,8 @@ class StereoMatching {
   void updateCost(cv::Mat& Lr, cv::Mat& vm, int v, int u, int n, int rv, int ru, bool preIsInner, bool leftFirst);  // stereoMatching.h:2205-2280
   void gen_dispFromVm(Mat& vm, Mat& dispMap);                                           // stereoMatching.cpp:3928-3967
   void wta_Co(cv::Mat& vm, cv::Mat& D1, cv::Mat& D2);                                   // stereoMatching.cpp:2709-2792
+  // topDisp: 4-D CV_32F {h, w, num + 1, 2}; like the reference, the Mat handed in has its taken entries set to FLT_MAX
+  void selectTopCostFromVolumn(Mat& vm, Mat& topDisp, float thres);                     // stereoMatching.h:2405-2461
 
   // ---- refinement
   void LRConsistencyCheck(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR = 0);         // :2284-2364

@@ -85,6 +85,7 @@ H_FUNCS = [
     (r"^\tvoid cal1DCost\(", "cal1DCost"),
     (r"^\tstatic float min4\(", "min4"),
     (r"^\tvoid updateCost\(", "updateCost"),
+    (r"^\tvoid selectTopCostFromVolumn\(", "selectTopCostFromVolumn"),
 ]
 
 
@@ -172,7 +173,8 @@ def main():
             f.write("\n".join(switches) + "\n")
             f.write(h_parts["Parameters"])
             f.write('#include "smref_class_decls.inc"\n')     # ours: declarations + data members
-            for n in ("genCensusCode", "genCensusCode_NC_Sur", "gen_cenVM_XOR", "cal1DCost", "min4", "updateCost"):
+            for n in ("genCensusCode", "genCensusCode_NC_Sur", "gen_cenVM_XOR", "cal1DCost", "min4", "updateCost",
+                      "selectTopCostFromVolumn"):
                 f.write(h_parts[n])
             f.write("};\n")
             f.write('#include "smref_class_tail.inc"\n')      # ours: static member definitions, stubs

@@ -74,6 +74,7 @@ def lib():
         "orc_sgm": ([f32p, u8p, I, I, I, I, I, I], None),
         "orc_wta": ([f32p, I, I, I, i16p], None),
         "orc_wta_co": ([f32p, I, I, I, I, i16p, i16p], None),
+        "orc_select_top": ([f32p, I, I, I, I, F, f32p], None),
         "orc_lrc_normal": ([i16p, i16p, I, I, F], None),
         "orc_lrc_label": ([i16p, i16p, I, I, I, F, I, I, u8p], None),
         "orc_region_vote": ([i16p, u16p, I, I, I, F, I], None),
@@ -272,6 +273,14 @@ def wta(vol):
     H, W, D = vol.shape
     out = np.empty((H, W), np.int16)
     lib().orc_wta(np.ascontiguousarray(vol), H, W, D, out)
+    return out
+
+
+def select_top(vol, num, thres):
+    """selectTopCostFromVolumn (stereoMatching.h:2405-2461): float [H][W][num+1][2]."""
+    H, W, D = vol.shape
+    out = np.empty((H, W, num + 1, 2), np.float32)
+    lib().orc_select_top(np.ascontiguousarray(vol, np.float32), H, W, D, num, thres, out)
     return out
 
 
@@ -477,6 +486,7 @@ def smref_lib():
         "smref_cal1dcost": ([P, I, f32p, i32p, I, I, I], None), "smref_genfinal": ([P, f32p, i32p], None),
         "smref_update_cost": ([P, I, f32p, I, I, I, I, I], None), "smref_cost_scan": ([P, I, I, f32p], None), "smref_sgm": ([P, I, I], None),
         "smref_wta": ([P, I, i16p], None), "smref_wta_co": ([P, I, i16p, i16p], None),
+        "smref_select_top": ([P, I, I, F, f32p], None),
         "smref_lrc_normal": ([P, i16p, i16p], None), "smref_lrc_label": ([P, i16p, i16p, I, P], None),
         "smref_lrc_new": ([P, i16p, i16p, u8p], None),
         "smref_region_vote": ([P, i16p, F, I], None), "smref_proper_ipol": ([P, i16p], None),
@@ -621,6 +631,12 @@ class SmRef:
     def wta(self, view):
         o = np.empty((self.H, self.W), np.int16)
         self.L.smref_wta(self.h, view, o)
+        return o
+
+    def select_top(self, view, num, thres):
+        """The reference's own selectTopCostFromVolumn on a clone of vm[view] (topDisp zero-initialised)."""
+        o = np.empty((self.H, self.W, num + 1, 2), np.float32)
+        self.L.smref_select_top(self.h, view, num, thres, o)
         return o
 
     def wta_co(self, view=0):

@@ -487,6 +487,32 @@ void orc_wta(const float* vol, int H, int W, int D, i16* disp) {
   }
 }
 
+// selectTopCostFromVolumn (stereoMatching.h:2405-2461; the caller hands it a clone of vm,
+// stereoMatching.cpp:1118-1119): per pixel, up to num rounds of a first-minimum scan (strict '>'); the winner is taken
+// out by overwriting it with FLT_MAX; round 0 is always kept, round k > 0 only while cost < firstCost * thres.
+// top = float [H][W][num+1][2], zero where the reference writes nothing; top[..][num][0] = candidate count.
+void orc_select_top(const float* vol, int H, int W, int D, int num, float thres, float* top) {
+  ORC_PAR_FOR
+  for (long i = 0; i < (long)H * W; i++) {
+    std::vector<float> c(vol + i * D, vol + i * D + D);
+    float* o = top + i * (long)(num + 1) * 2;
+    for (int k = 0; k < (num + 1) * 2; k++) o[k] = 0.f;
+    float firstV = 0.f;
+    for (int k = 0; k < num; k++) {
+      float m = c[0];
+      int disp = 0;
+      for (int d = 1; d < D; d++)
+        if (m > c[d]) { m = c[d]; disp = d; }
+      if (k == 0) firstV = m;
+      else if (!(m < firstV * thres)) break;
+      c[disp] = std::numeric_limits<float>::max();
+      o[2 * num] += 1.f;
+      o[2 * k] = (float)disp;
+      o[2 * k + 1] = m;
+    }
+  }
+}
+
 // wta_Co (stereoMatching.cpp:2709-2792) with UniqCk=SubIpl=0: left WTA over
 // d<=u, right map from the LEFT volume along the diagonal, both x DISP_SCALE.
 void orc_wta_co(const float* vol, int H, int W, int D, int scale, i16* D1, i16* D2) {

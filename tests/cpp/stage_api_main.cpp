@@ -152,6 +152,15 @@ int main(int argc, char** argv) {
       sm.cbca_core(sm.HVL, sm.HVL_INTERSECTION, sm.vm, 2);
       dump(out + ".vm0_cbca.f32", sm.hostVm(0).data, npix * D * 4);
       for (int i = 0; i < 2; i++) sm.sgm(sm.vm[i], i == 0);
+      {  // the vmTop candidate selection as dispOptimize() calls it (stereoMatching.cpp:1114-1119): on a clone of vm
+        dump(out + ".vm0_sgm.f32", sm.hostVm(0).data, npix * D * 4);
+        int szTop[] = {H, W, 6 + 1, 2};
+        cv::Mat topDisp(4, szTop, CV_32F);
+        cv::Mat vm_copy = sm.hostVm(0).clone();
+        sm.selectTopCostFromVolumn(vm_copy, topDisp, 1.08f);
+        dump(out + ".top0.f32", topDisp.data, npix * 7 * 2 * 4);
+        dump(out + ".top0_vm.f32", vm_copy.data, npix * D * 4);
+      }
       sm.DP[0].create(H, W, CV_16SC1); sm.DP[1].create(H, W, CV_16SC1);
       for (int i = 0; i < 2; i++) sm.gen_dispFromVm(sm.vm[i], sm.DP[i]);
       dump(out + ".dp0_wta.i16", sm.hostDP(0).data, npix * 2);

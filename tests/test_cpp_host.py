@@ -23,6 +23,7 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::NL()", "StereoMatching::sgm(cv::Mat&, bool)",
                 "StereoMatching::costScan(cv::Mat&, cv::Mat&, int, int, bool)",
                 "StereoMatching::gen_dispFromVm(cv::Mat&, cv::Mat&)", "StereoMatching::wta_Co(",
+                "StereoMatching::selectTopCostFromVolumn(cv::Mat&, cv::Mat&, float)",
                 "StereoMatching::regionVote_my(cv::Mat&, float, int)", "StereoMatching::properIpol(",
                 "StereoMatching::LRConsistencyCheck_normal(", "StereoMatching::genCensusCode_NC_Sur(",
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
@@ -74,6 +75,18 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
         cb = po.cbca(cost, aL, aR, 2, 0)
         got = np.fromfile(prefix + ".vm0_cbca.f32", np.float32).reshape(H, W, D)
         assert np.array_equal(got.view(np.uint32), cb.view(np.uint32))
+        # selectTopCostFromVolumn on a clone of the SGM volume: candidates = the oracle's, taken entries -> FLT_MAX
+        sg = np.fromfile(prefix + ".vm0_sgm.f32", np.float32).reshape(H, W, D)
+        top = np.fromfile(prefix + ".top0.f32", np.float32).reshape(H, W, 7, 2)
+        want = po.select_top(sg, 6, 1.08)
+        assert np.array_equal(top.view(np.uint32), want.view(np.uint32))
+        marked = np.fromfile(prefix + ".top0_vm.f32", np.float32).reshape(H, W, D)
+        exp = sg.copy()
+        for k in range(6):
+            sel = want[:, :, 6, 0] > k
+            vv, uu = np.nonzero(sel)
+            exp[vv, uu, want[vv, uu, k, 0].astype(np.int64)] = np.finfo(np.float32).max
+        assert np.array_equal(marked.view(np.uint32), exp.view(np.uint32)) and (want[:, :, 6, 0] > 1).any()
         wta = np.fromfile(prefix + ".dp0_wta.i16", np.int16).reshape(H, W)
         assert np.array_equal(wta, po.wta(po.sgm(cb, pair["bgrL"], P)))
         ad = np.fromfile(prefix + ".ad0.f32", np.float32).reshape(H, W, D)

@@ -537,3 +537,34 @@ def test_full_size_pipeline_is_deterministic_and_order_insensitive(ctx):
     assert (maps[0] == maps[1]).mean() >= 0.995
     assert maps[1].max() < D and maps[1].min() >= -48        # DISP_MIS, the lowest label refine can leave
     assert abs(synth.bad_k(maps[1], p["gt"], p["nonocc"], 2) - synth.bad_k(maps[0], p["gt"], p["nonocc"], 2)) <= 0.1
+
+
+# ---------------------------------------------------------------- candidate disparities (first half)
+@pytest.mark.timeout(120)
+def test_select_top_cost_matches_reference_golden(ctx, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "top_ref.npz"))    # outputs of the reference's own selectTopCostFromVolumn
+    for k in g.files:
+        if "_top_" not in k:
+            continue
+        vol = g[k.split("_top_")[0] + "_vol"]
+        num, thres = int(k.split("_n")[1].split("_")[0]), float(k.split("_t")[-1])
+        dv = ctx.dev(vol.copy())
+        got = ctx.select_top_cost(dv, num, thres).cpu().numpy()
+        assert _bits_equal(got, g[k]), k
+        assert _bits_equal(dv.cpu().numpy(), vol)             # the volume itself is left alone (the reference clones it)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape,num,thres", [((37, 53, 33), 6, 1.08), ((24, 40, 256), 6, 1.3), ((30, 31, 64), 2, 1.01),
+                                             ((9, 11, 5), 8, 100.0)])
+def test_select_top_cost_matches_oracle(ctx, shape, num, thres):
+    H, W, D = shape
+    rng = np.random.default_rng(17)
+    vol = rng.random((H, W, D)).astype(np.float32) + 0.5
+    vol[::3] = np.round(vol[::3] * 4) / 4                     # equal minima: the lowest d must win
+    vol[1, 1] = 0.0                                           # first cost 0: cost < 0 * thres never holds
+    vol[2, 2, 0] = -0.0                                       # the reference's '>' does not tell -0 from +0
+    vol[2, 2, 1:] = np.where(np.arange(1, D) % 2 == 0, 0.0, 1.0)
+    got = ctx.select_top_cost(ctx.dev(vol.copy()), num, thres).cpu().numpy()
+    assert _bits_equal(got, po.select_top(vol, num, thres))

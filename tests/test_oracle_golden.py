@@ -375,3 +375,24 @@ def test_cal_err_known_answer():
     mask = np.array([[255, 255, 255], [0, 255, 255]], np.uint8)
     pbm, rms, n, e = po.cal_err(dp, gt, mask, 1)
     assert (n, e) == (5, 3) and abs(pbm - 0.6) < 1e-7 and abs(rms - np.sqrt(2.1)) < 1e-6
+
+
+def test_select_top_equals_reference(golden_dir):
+    """orc_select_top against the outputs of the reference's own selectTopCostFromVolumn (tests/golden/top_ref.npz)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "top_ref.npz"))
+    n = 0
+    for k in g.files:
+        if "_top_" not in k:
+            continue
+        vol = g[k.split("_top_")[0] + "_vol"]
+        num, thres = int(k.split("_n")[1].split("_")[0]), float(k.split("_t")[-1])
+        got = po.select_top(vol, num, thres)
+        assert np.array_equal(got.view(np.uint32), g[k].view(np.uint32)), k
+        n += 1
+    assert n == 5
+    # known answer by hand: costs [5, 2, 2, 7, 2.1], thres 1.08 -> d=1 (first of the equal minima), then d=2 (2 < 2.16),
+    # then d=4 (2.1 < 2.16), then 5 fails
+    v = np.array([[[5, 2, 2, 7, 2.1]]], np.float32)
+    t = po.select_top(v, 4, 1.08)[0, 0]
+    assert t[:, 0].tolist() == [1, 2, 4, 0, 3] and t[:3, 1].tolist() == [2, 2, np.float32(2.1)] and t[3].tolist() == [0, 0]
