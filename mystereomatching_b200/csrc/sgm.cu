@@ -37,6 +37,9 @@
 __device__ __forceinline__ void sgm_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void sgm_cp8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void sgm_cp4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -46,6 +49,11 @@ __device__ __forceinline__ void sgm_wait() { asm volatile("cp.async.wait_group %
 __device__ __forceinline__ float4 sgm_lds16(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 sgm_lds8(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t sgm_lds4(uint32_t a) {
@@ -300,7 +308,9 @@ __global__ void __launch_bounds__(32)
                  int D, int corDifThres, float redu, int16_t* __restrict__ disp) {
   extern __shared__ __align__(16) uint8_t sgm_smem[];
   constexpr int NS = SGM_NSTG + 1;                       // slots
-  constexpr int NQ = VPL / 4;                            // 16-byte pieces of one lane's run
+  constexpr int PB = VPL >= 4 ? 16 : 8;                  // bytes of a piece: 16, or the whole run of 2 (D <= 64: all 32 lanes work)
+  constexpr int PF = PB / 4;                             // floats of a piece
+  constexpr int NQ = VPL * 4 / PB;                       // pieces of one lane's run
   constexpr int RUNB = VPL * 4;                          // bytes of one lane's run
   constexpr uint32_t SLOTB = 32 * RUNB * (MODE >= 1 ? 2 : 1) + 128;   // C run | S run | pixel word, per lane
   const int lane = threadIdx.x;
@@ -326,9 +336,14 @@ __global__ void __launch_bounds__(32)
     if (ti < len) {
 #pragma unroll
       for (int k = 0; k < NQ; k++)
-        if (d0 + 4 * k < D) {  // D % 4 == 0: a piece is wholly in or out
-          sgm_cp16(cOff + wr + k * 16, cg + k * 16);
-          if (MODE >= 1) sgm_cp16(sOff + wr + k * 16, sg + k * 16);
+        if (d0 + PF * k < D) {  // D % 4 == 0: a piece is wholly in or out
+          if (PB == 16) {
+            sgm_cp16(cOff + wr + k * 16, cg + k * 16);
+            if (MODE >= 1) sgm_cp16(sOff + wr + k * 16, sg + k * 16);
+          } else {
+            sgm_cp8(cOff + wr, cg);
+            if (MODE >= 1) sgm_cp8(sOff + wr, sg);
+          }
         }
       sgm_cp4(xOff + wr, xg);
     }
@@ -346,22 +361,37 @@ __global__ void __launch_bounds__(32)
     sgm_wait<SGM_NSTG - 1>();
     float c[VPL], s[VPL];
 #pragma unroll
-    for (int k = 0; k < NQ; k++) {
-      float4 a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX), b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (d0 + 4 * k < D) {
-        a = sgm_lds16(cOff + rd + k * 16);
-        if (MODE >= 1) b = sgm_lds16(sOff + rd + k * 16);
+    if (PB == 16) {
+#pragma unroll
+      for (int k = 0; k < NQ; k++) {
+        float4 a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d0 + 4 * k < D) {
+          a = sgm_lds16(cOff + rd + k * 16);
+          if (MODE >= 1) b = sgm_lds16(sOff + rd + k * 16);
+        }
+        c[4 * k] = a.x; c[4 * k + 1] = a.y; c[4 * k + 2] = a.z; c[4 * k + 3] = a.w;
+        s[4 * k] = b.x; s[4 * k + 1] = b.y; s[4 * k + 2] = b.z; s[4 * k + 3] = b.w;
       }
-      c[4 * k] = a.x; c[4 * k + 1] = a.y; c[4 * k + 2] = a.z; c[4 * k + 3] = a.w;
-      s[4 * k] = b.x; s[4 * k + 1] = b.y; s[4 * k + 2] = b.z; s[4 * k + 3] = b.w;
+    } else {
+      float2 a = make_float2(FLT_MAX, FLT_MAX), b = make_float2(0.f, 0.f);
+      if (d0 < D) {
+        a = sgm_lds8(cOff + rd);
+        if (MODE >= 1) b = sgm_lds8(sOff + rd);
+      }
+      c[0] = a.x; c[1] = a.y;
+      s[0] = b.x; s[1] = b.y;
     }
     const uint32_t x = sgm_lds4(xOff + rd);
     issue();
     sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, pc);
+    if (PB == 16) {
 #pragma unroll
-    for (int k = 0; k < NQ; k++)
-      if (d0 + 4 * k < D)
-        *reinterpret_cast<float4*>(og + k * 16) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+      for (int k = 0; k < NQ; k++)
+        if (d0 + 4 * k < D)
+          *reinterpret_cast<float4*>(og + k * 16) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    } else if (d0 < D) {
+      *reinterpret_cast<float2*>(og) = make_float2(s[0], s[1]);
+    }
     og += stepB;
     pc += pstep;
     rd += SLOTB;
@@ -554,6 +584,10 @@ int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix,
   // small frames (few scan lines): the cp.async staged kernel in every direction, runs of >= 4 disparities per lane
   static const int small_env = getenv("SM_SGM_SMALL_LINES") ? atoi(getenv("SM_SGM_SMALL_LINES")) : 1024;   // 0: off
   if (vec && ((uintptr_t)d_pix & 3) == 0 && g.nLines <= small_env) {
+    // 32 < D <= 64: runs of 2, all 32 lanes at work (runs of 4 leave half the warp idle and cost ~25 more instructions
+    // per pixel); the TMA row kernel needs runs of >= 4
+    static const int v2_env = getenv("SM_SGM_SMALL_V2") ? atoi(getenv("SM_SGM_SMALL_V2")) : 1;
+    if (vpl == 2 && v2_env) return launch_sgm_s<2>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
     const int vs = max(vpl, 4);
     const bool tma = g.mv == 0 && staged_env == 2 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0;
     if (!tma) {
