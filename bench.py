@@ -300,7 +300,10 @@ def stage_bytes(name):
         st["sgm_path"] = {"bytes_per_launch": 3 * V * b, "launches": 4, "kernel": "k_sgm_path"}
     else:
         # first path writes S (2 V b), the others read-modify-write it (3 V b)
-        st["sgm"] = {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path"}
+        # <= 1024 scan lines per sweep: the cp.async-staged any-direction kernel (sgm.cu, SM_SGM_SMALL_LINES)
+        small = max(W, H) + (min(W, H) - 1 if P == 8 else 0) <= 1024
+        st["sgm"] = {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P,
+                     "kernel": "k_sgm_path_s" if small else "k_sgm_path"}
     return st
 
 
