@@ -138,21 +138,26 @@ __device__ __forceinline__ void sgm_step(bool first, const float (&c)[VPL], floa
     P1 = P1 - minC;
     float lo = __shfl_up_sync(0xffffffffu, prev[VPL - 1], 1);   // Lr'[d0-1]
     float hi = __shfl_down_sync(0xffffffffu, prev[0], 1);       // Lr'[d0+VPL]
+    // No per-disparity range test.  The reference's out-of-range neighbour is S = FLT_MAX, which can never be the
+    // minimum next to the finite P2; here the neighbour below d = 0 and above lane 31 is FLT_MAX, and a disparity >= D
+    // is a padding element whose Lr stays >= FLT_MAX from the first pixel on (c = FLT_MAX + a positive minimum), so
+    // S2 / S3 come out as FLT_MAX or +inf: never the minimum either, and no NaN (nothing subtracts inf from inf).
+    if (lane == 0) lo = FLT_MAX;
+    if (lane == 31) hi = FLT_MAX;
 #pragma unroll
     for (int j = 0; j < VPL; j++) {
-      const int d = d0 + j;
       const float pm = j == 0 ? lo : prev[j - 1];
       const float pp = j == VPL - 1 ? hi : prev[j + 1];
       const float S1 = prev[j] - minC;
-      const float S2 = d - 1 >= 0 ? pm + P1 : FLT_MAX;
-      const float S3 = d + 1 < D ? pp + P1 : FLT_MAX;
+      const float S2 = pm + P1;
+      const float S3 = pp + P1;
       lr[j] = c[j] + fminf(fminf(S1, S2), fminf(S3, P2));
     }
   }
-  // D-wide minimum of the new row (padding lanes hold FLT_MAX via c[])
+  // D-wide minimum of the new row (padding elements hold >= FLT_MAX via c[], every real Lr is below it)
   float m = FLT_MAX;
 #pragma unroll
-  for (int j = 0; j < VPL; j++) m = (d0 + j < D) ? fminf(m, lr[j]) : m;
+  for (int j = 0; j < VPL; j++) m = fminf(m, lr[j]);
   minC = key2f(__reduce_min_sync(0xffffffffu, f2key(m)));
 #pragma unroll
   for (int j = 0; j < VPL; j++) prev[j] = lr[j];
@@ -170,7 +175,7 @@ __device__ __forceinline__ void sgm_step(bool first, const float (&c)[VPL], floa
     int bd = 0x7fffffff;
 #pragma unroll
     for (int j = 0; j < VPL; j++)
-      if (d0 + j < D && bm > s[j]) { bm = s[j]; bd = d0 + j; }
+      if (bm > s[j]) { bm = s[j]; bd = d0 + j; }   // a padding element's sum is >= FLT_MAX: never below bm
     const uint32_t km = __reduce_min_sync(0xffffffffu, f2key(bm));
     const int cand = (f2key(bm) == km && bd != 0x7fffffff) ? bd : 0x7fffffff;
     const int best = (int)__reduce_min_sync(0xffffffffu, (unsigned)cand);
