@@ -266,6 +266,14 @@ int sm_wta(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int16_t* d_disp
  * entries the reference leaves unwritten are 0.  d_vol is not modified. */
 int sm_select_top_cost(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int num,
                        float thres, float* d_top);
+
+/* subpixelEnhancement (stereoMatching.cpp:6138-6166; off by default,
+ * Do_subpixelEnhancement, stereoMatching.h:79): for 0 < disp < D-1 the parabola
+ * offset diff = (c[+1]-c[-1]) / (2*(c[+1]+c[-1]-2*c[0])) is subtracted when
+ * denom != 0 and -1 < diff < 1 -- on the short, as the reference does
+ * (truncation toward zero), then converted.  d_floatDisp = float [H][W]. */
+int sm_subpixel_enhancement(sm_ctx* ctx, const int16_t* d_disp, const float* d_vol, int H, int W, int D,
+                            float* d_floatDisp);
 int sm_wta_co(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int scale, int16_t* d_D1,
               int16_t* d_D2);
 

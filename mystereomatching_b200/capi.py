@@ -98,6 +98,7 @@ SIGNATURES = {
     "sm_wta": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_wta_co": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
     "sm_select_top_cost": ([_P, _P, _I, _I, _I, _I, _F, _P], _I),
+    "sm_subpixel_enhancement": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "sm_lrc": ([_P, _P, _P, _I, _I, _F], _I),
     "sm_lrc_label": ([_P, _P, _P, _I, _I, _I, _F, _I, _I, _P], _I),
     "sm_region_vote": ([_P, _P, _P, _P, _I, _I, _I, _F, _I], _I),
@@ -378,6 +379,13 @@ class Ctx:
         H, W, D = vol.shape
         out = self.empty((H, W), self.torch.int16)
         check(self.L.sm_wta(self.h, _ptr(vol), H, W, D, _ptr(out)))
+        return out
+
+    def subpixel_enhancement(self, disp, vol):
+        """subpixelEnhancement (stereoMatching.cpp:6138-6166): float [H][W] from the short map and the view-0 volume."""
+        H, W, D = vol.shape
+        out = self.empty((H, W), self.torch.float32)
+        check(self.L.sm_subpixel_enhancement(self.h, _ptr(disp), _ptr(vol), H, W, D, _ptr(out)))
         return out
 
     def select_top_cost(self, vol, num, thres):

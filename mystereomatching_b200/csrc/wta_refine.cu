@@ -165,6 +165,37 @@ extern "C" int sm_select_top_cost(sm_ctx* ctx, const float* d_vol, int H, int W,
   return SM_OK;
 }
 
+// ------------------------------------------------------------------ sub-pixel enhancement
+// subpixelEnhancement (stereoMatching.cpp:6138-6166): parabola through the costs at disp-1, disp, disp+1 of view 0.
+// The reference applies the offset to the SHORT (`disp -= diff`, i.e. (short)((float)disp - diff), truncation toward
+// zero) and only then converts to float, so the output is integer-valued; kept as it is.  One thread per pixel: 2 B of
+// disparity in, three gathered floats (one 32 B sector when they do not straddle), 4 B out.
+__global__ void k_subpixel(const int16_t* __restrict__ disp, const float* __restrict__ vol, long long npix, int D,
+                           float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    short d = disp[i];
+    if (d > 0 && d < D - 1) {
+      const float* c = vol + i * D + d;
+      const float cost = c[0], costPlus = c[1], costMinus = c[-1];
+      const float denom = 2 * (costPlus + costMinus - 2 * cost);
+      if (denom != 0) {
+        const float diff = (costPlus - costMinus) / denom;
+        if (diff > -1 && diff < 1) d = (short)((float)d - diff);
+      }
+    }
+    out[i] = (float)d;
+  }
+}
+
+extern "C" int sm_subpixel_enhancement(sm_ctx* ctx, const int16_t* d_disp, const float* d_vol, int H, int W, int D,
+                                       float* d_floatDisp) {
+  SM_CHECK_ARG(ctx && d_disp && d_vol && d_floatDisp && H > 0 && W > 0 && D > 0);
+  const long long npix = (long long)H * W;
+  const int grid = (int)min((long long)ctx->num_sms * 8, (npix + 255) / 256);
+  SM_LAUNCH(ctx, k_subpixel, grid, 256, 0, d_disp, d_vol, npix, D, d_floatDisp);
+  return SM_OK;
+}
+
 // ------------------------------------------------------------------ LR check
 // In-place on D1 is safe: each thread reads D1 only at its own pixel.
 __global__ void k_lrc(int16_t* __restrict__ D1, const int16_t* __restrict__ D2, int H, int W, float maxDiff) {

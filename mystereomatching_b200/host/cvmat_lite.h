@@ -128,6 +128,7 @@ class Mat {
   }
   template <typename T> T& at(int i0, int i1) { return *ptr<T>(i0, i1); }
   template <typename T> const T& at(int i0, int i1) const { return *ptr<T>(i0, i1); }
+  template <typename T> T& at(int i0, int i1, int i2) { return *ptr<T>(i0, i1, i2); }
   // cv::Mat::inv() (DECOMP_LU) for a square CV_32F matrix, the way cv::invert evaluates it: n = 1, 3 closed forms in
   // double rounded once; n = 2 determinant in double, float products with (float)(1/det) (the SIMD128 branch);
   // n > 3 Gaussian elimination with partial pivoting in float.  Reproduces cv2.invert bit for bit on the matrices

@@ -721,6 +721,19 @@ void StereoMatching::wta_Co(cv::Mat& vm_, cv::Mat& D1, cv::Mat& D2) {
   download(D2.data, b.p, pb);
 }
 
+// subpixelEnhancement (stereoMatching.cpp:6138-6166): reads vm[0] of the object (device copy brought up to date first).
+void StereoMatching::subpixelEnhancement(Mat& disparity, Mat& floatDisp) {
+  CV_Assert(disparity.type() == CV_16S);
+  CV_Assert(floatDisp.type() == CV_32F);
+  CV_Assert(disparity.rows == h_ && disparity.cols == w_ && floatDisp.rows == h_ && floatDisp.cols == w_);
+  const size_t npix = (size_t)h_ * w_;
+  TmpDev d(ctx_, npix * 2), f(ctx_, npix * 4);
+  upload(d.p, disparity.data, npix * 2);
+  uploadVm(0);
+  check(sm_subpixel_enhancement(ctx_, d.as<int16_t>(), d_vol_[0], h_, w_, d_, f.as<float>()), "sm_subpixel_enhancement");
+  download(floatDisp.data, f.p, npix * 4);
+}
+
 // selectTopCostFromVolumn (stereoMatching.h:2405-2461): the candidates come from sm_select_top_cost; the reference also
 // overwrites the entries it takes in the Mat it is handed (its caller passes a clone, stereoMatching.cpp:1118), which
 // is replayed on the host copy from the candidate list.

@@ -143,6 +143,7 @@ class StereoMatching {
   void wta_Co(cv::Mat& vm, cv::Mat& D1, cv::Mat& D2);                                   // stereoMatching.cpp:2709-2792
   // topDisp: 4-D CV_32F {h, w, num + 1, 2}; like the reference, the Mat handed in has its taken entries set to FLT_MAX
   void selectTopCostFromVolumn(Mat& vm, Mat& topDisp, float thres);                     // stereoMatching.h:2405-2461
+  void subpixelEnhancement(Mat& disparity, Mat& floatDisp);                             // stereoMatching.cpp:6138-6166
 
   // ---- refinement
   void LRConsistencyCheck(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR = 0);         // :2284-2364

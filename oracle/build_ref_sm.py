@@ -65,6 +65,8 @@ CPP_FUNCS = [
     (r"^void StereoMatching::LRConsistencyCheck_new\(", "LRConsistencyCheck_new"),
     (r"^void StereoMatching::regionVote_my\(", "regionVote_my"),
     (r"^void StereoMatching::properIpol\(", "properIpol"),
+    # default-off refiner
+    (r"^void StereoMatching::subpixelEnhancement\(", "subpixelEnhancement"),
     # the gradient cost family: "censusGrad" is the selector main_.cpp:15 compiles in
     (r"^void StereoMatching::censusGrad\(", "censusGrad"),
     (r"^void StereoMatching::grad\(vector<Mat>& vm_grad, float Trunc\)", "grad"),

@@ -75,6 +75,7 @@ def lib():
         "orc_wta": ([f32p, I, I, I, i16p], None),
         "orc_wta_co": ([f32p, I, I, I, I, i16p, i16p], None),
         "orc_select_top": ([f32p, I, I, I, I, F, f32p], None),
+        "orc_subpixel": ([i16p, f32p, I, I, I, f32p], None),
         "orc_lrc_normal": ([i16p, i16p, I, I, F], None),
         "orc_lrc_label": ([i16p, i16p, I, I, I, F, I, I, u8p], None),
         "orc_region_vote": ([i16p, u16p, I, I, I, F, I], None),
@@ -284,6 +285,14 @@ def select_top(vol, num, thres):
     return out
 
 
+def subpixel(disp, vol):
+    """subpixelEnhancement (stereoMatching.cpp:6138-6166): float [H][W]."""
+    H, W, D = vol.shape
+    out = np.empty((H, W), np.float32)
+    lib().orc_subpixel(np.ascontiguousarray(disp, np.int16), np.ascontiguousarray(vol, np.float32), H, W, D, out)
+    return out
+
+
 def wta_co(vol, scale=16):
     H, W, D = vol.shape
     d1 = np.empty((H, W), np.int16)
@@ -487,6 +496,7 @@ def smref_lib():
         "smref_update_cost": ([P, I, f32p, I, I, I, I, I], None), "smref_cost_scan": ([P, I, I, f32p], None), "smref_sgm": ([P, I, I], None),
         "smref_wta": ([P, I, i16p], None), "smref_wta_co": ([P, I, i16p, i16p], None),
         "smref_select_top": ([P, I, I, F, f32p], None),
+        "smref_subpixel": ([P, i16p, f32p], None),
         "smref_lrc_normal": ([P, i16p, i16p], None), "smref_lrc_label": ([P, i16p, i16p, I, P], None),
         "smref_lrc_new": ([P, i16p, i16p, u8p], None),
         "smref_region_vote": ([P, i16p, F, I], None), "smref_proper_ipol": ([P, i16p], None),
@@ -637,6 +647,12 @@ class SmRef:
         """The reference's own selectTopCostFromVolumn on a clone of vm[view] (topDisp zero-initialised)."""
         o = np.empty((self.H, self.W, num + 1, 2), np.float32)
         self.L.smref_select_top(self.h, view, num, thres, o)
+        return o
+
+    def subpixel(self, disp):
+        """The reference's own subpixelEnhancement on the given disparity map and vm[0]."""
+        o = np.empty((self.H, self.W), np.float32)
+        self.L.smref_subpixel(self.h, np.ascontiguousarray(disp, np.int16), o)
         return o
 
     def wta_co(self, view=0):

@@ -487,6 +487,26 @@ void orc_wta(const float* vol, int H, int W, int D, i16* disp) {
   }
 }
 
+// subpixelEnhancement (stereoMatching.cpp:6138-6166): parabola offset from the costs at disp-1, disp, disp+1, only for
+// 0 < disp < D-1, denom != 0 and -1 < diff < 1.  `disp -= diff` acts on the short: (short)((float)disp - diff), so the
+// float map that comes out is integer-valued.
+void orc_subpixel(const short* disp, const float* vol, int H, int W, int D, float* out) {
+  ORC_PAR_FOR
+  for (long i = 0; i < (long)H * W; i++) {
+    short d = disp[i];
+    if (d > 0 && d < D - 1) {
+      const float* c = vol + i * D;
+      float cost = c[d], costPlus = c[d + 1], costMinus = c[d - 1];
+      float denom = 2 * (costPlus + costMinus - 2 * cost);
+      if (denom != 0) {
+        float diff = (costPlus - costMinus) / denom;
+        if (diff > -1 && diff < 1) d = (short)((float)d - diff);
+      }
+    }
+    out[i] = (float)d;
+  }
+}
+
 // selectTopCostFromVolumn (stereoMatching.h:2405-2461; the caller hands it a clone of vm,
 // stereoMatching.cpp:1118-1119): per pixel, up to num rounds of a first-minimum scan (strict '>'); the winner is taken
 // out by overwriting it with FLT_MAX; round 0 is always kept, round k > 0 only while cost < firstCost * thres.

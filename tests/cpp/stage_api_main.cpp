@@ -164,6 +164,11 @@ int main(int argc, char** argv) {
       sm.DP[0].create(H, W, CV_16SC1); sm.DP[1].create(H, W, CV_16SC1);
       for (int i = 0; i < 2; i++) sm.gen_dispFromVm(sm.vm[i], sm.DP[i]);
       dump(out + ".dp0_wta.i16", sm.hostDP(0).data, npix * 2);
+      {  // the default-off sub-pixel step as refine() would call it (stereoMatching.cpp:1482-1485)
+        cv::Mat dsp = sm.hostDP(0).clone(), SE(H, W, CV_32F);
+        sm.subpixelEnhancement(dsp, SE);
+        dump(out + ".se0.f32", SE.data, npix * 4);
+      }
       sm.refine();
       // explicit-argument forms: host Mats in, host Mats out
       cv::Mat ad, lr;

@@ -24,6 +24,7 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::costScan(cv::Mat&, cv::Mat&, int, int, bool)",
                 "StereoMatching::gen_dispFromVm(cv::Mat&, cv::Mat&)", "StereoMatching::wta_Co(",
                 "StereoMatching::selectTopCostFromVolumn(cv::Mat&, cv::Mat&, float)",
+                "StereoMatching::subpixelEnhancement(cv::Mat&, cv::Mat&)",
                 "StereoMatching::regionVote_my(cv::Mat&, float, int)", "StereoMatching::properIpol(",
                 "StereoMatching::LRConsistencyCheck_normal(", "StereoMatching::genCensusCode_NC_Sur(",
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
@@ -80,6 +81,11 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
         top = np.fromfile(prefix + ".top0.f32", np.float32).reshape(H, W, 7, 2)
         want = po.select_top(sg, 6, 1.08)
         assert np.array_equal(top.view(np.uint32), want.view(np.uint32))
+        # subpixelEnhancement on the WTA map of that volume
+        dw = np.fromfile(prefix + ".dp0_wta.i16", np.int16).reshape(H, W)
+        se = np.fromfile(prefix + ".se0.f32", np.float32).reshape(H, W)
+        se_want = po.subpixel(dw, sg)
+        assert np.array_equal(se.view(np.uint32), se_want.view(np.uint32)) and (se_want != dw).any()
         marked = np.fromfile(prefix + ".top0_vm.f32", np.float32).reshape(H, W, D)
         exp = sg.copy()
         for k in range(6):

@@ -555,6 +555,36 @@ def test_select_top_cost_matches_reference_golden(ctx, golden_dir):
         assert _bits_equal(dv.cpu().numpy(), vol)             # the volume itself is left alone (the reference clones it)
 
 
+# ---------------------------------------------------------------- sub-pixel step (default-off refiner)
+@pytest.mark.timeout(120)
+def test_subpixel_enhancement_matches_reference_golden(ctx, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "subpixel_ref.npz"))    # outputs of the reference's own subpixelEnhancement
+    n = 0
+    for k in g.files:
+        if "_se_" not in k:
+            continue
+        pre, tag = k.split("_se_")
+        got = ctx.subpixel_enhancement(ctx.dev(g[f"{pre}_disp_{tag}"].copy()), ctx.dev(g[pre + "_vol"].copy())).cpu().numpy()
+        assert _bits_equal(got, g[k]), k
+        n += 1
+    assert n == 3
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape", [(37, 53, 33), (24, 40, 256), (1, 1, 3), (9, 11, 2), (270, 480, 64)])
+def test_subpixel_enhancement_matches_oracle(ctx, shape):
+    H, W, D = shape
+    rng = np.random.default_rng(23)
+    vol = rng.random((H, W, D)).astype(np.float32) * 50
+    vol[::3] = np.round(vol[::3])                             # flat parabolas: denom == 0
+    vol[::4, ::2] = np.finfo(np.float32).max                  # out-of-range padding values: inf - inf -> NaN, unchanged
+    disp = rng.integers(-1, D, (H, W)).astype(np.int16)
+    disp[::7, ::5] = -32
+    got = ctx.subpixel_enhancement(ctx.dev(disp), ctx.dev(vol)).cpu().numpy()
+    assert _bits_equal(got, po.subpixel(disp, vol))
+
+
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("shape,num,thres", [((37, 53, 33), 6, 1.08), ((24, 40, 256), 6, 1.3), ((30, 31, 64), 2, 1.01),
                                              ((9, 11, 5), 8, 100.0)])

@@ -396,3 +396,27 @@ def test_select_top_equals_reference(golden_dir):
     v = np.array([[[5, 2, 2, 7, 2.1]]], np.float32)
     t = po.select_top(v, 4, 1.08)[0, 0]
     assert t[:, 0].tolist() == [1, 2, 4, 0, 3] and t[:3, 1].tolist() == [2, 2, np.float32(2.1)] and t[3].tolist() == [0, 0]
+
+
+def test_subpixel_equals_reference(golden_dir):
+    """orc_subpixel against the outputs of the reference's own subpixelEnhancement (tests/golden/subpixel_ref.npz)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "subpixel_ref.npz"))
+    n = changed = 0
+    for k in g.files:
+        if "_se_" not in k:
+            continue
+        pre, tag = k.split("_se_")
+        disp = g[f"{pre}_disp_{tag}"]
+        got = po.subpixel(disp, g[pre + "_vol"])
+        assert np.array_equal(got.view(np.uint32), g[k].view(np.uint32)), k
+        assert np.array_equal(got, np.trunc(got))           # the reference truncates on the short: integer-valued
+        changed += int((got != disp).sum())
+        n += 1
+    assert n == 3 and changed > 0
+    # known answers by hand (D=5): costs 4,1,2 around d=2 -> diff = (2-4)/(2*(2+4-2)) = -0.25 -> (short)2.25 = 2;
+    # costs 2,1,4 -> diff = +0.25 -> (short)1.75 = 1; flat 3,3,3 -> denom 0, unchanged; d = 0, D-1, negative: unchanged
+    v = np.array([[[9, 4, 1, 2, 9], [9, 2, 1, 4, 9], [9, 3, 3, 3, 9], [0, 5, 5, 5, 5], [5, 5, 5, 5, 0], [1, 2, 3, 4, 5]]],
+                 np.float32)
+    d = np.array([[2, 2, 2, 0, 4, -32]], np.int16)
+    assert po.subpixel(d, v).tolist() == [[2.0, 1.0, 2.0, 0.0, 4.0, -32.0]]
