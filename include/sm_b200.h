@@ -293,6 +293,10 @@ int sm_proper_ipol(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* 
                    int DISP_OCC);
 /* cv::medianBlur(CV_16S, 3) (stereoMatching.cpp:1499). d_dst != d_src. */
 int sm_median3_i16(sm_ctx* ctx, const int16_t* d_src, int16_t* d_dst, int H, int W);
+/* cv::medianBlur(SE, SE, 3) on the CV_32F map subpixelEnhancement returns
+ * (stereoMatching.cpp:1490): 3x3 median, replicated border, NaN-free input;
+ * d_src != d_dst. */
+int sm_median3_f32(sm_ctx* ctx, const float* d_src, float* d_dst, int H, int W);
 /* SolveAll with one pyramid level (stereoMatching.cpp:2142-2208, main_.cpp:158). */
 int sm_cross_scale_1level(sm_ctx* ctx, float* d_vol, size_t n, float lambda);
 /* ---- the caller's cross-scale step, any number of levels ---- */

@@ -104,6 +104,7 @@ SIGNATURES = {
     "sm_region_vote": ([_P, _P, _P, _P, _I, _I, _I, _F, _I], _I),
     "sm_proper_ipol": ([_P, _P, _P, _P, _I, _I, _I], _I),
     "sm_median3_i16": ([_P, _P, _P, _I, _I], _I),
+    "sm_median3_f32": ([_P, _P, _P, _I, _I], _I),
     "sm_cross_scale_1level": ([_P, _P, _Z, _F], _I),
     "sm_pipeline_create": ([_P, _I, _I, C.POINTER(SmParams), C.POINTER(_P)], _I),
     "sm_pipeline_destroy": ([_P], _I),
@@ -425,6 +426,13 @@ class Ctx:
         tmp = self.torch.empty_like(disp)
         check(self.L.sm_proper_ipol(self.h, _ptr(disp), _ptr(tmp), _ptr(bgr), H, W, occ))
         return disp
+
+    def median3_f32(self, disp):
+        """cv::medianBlur(CV_32F, 3) (stereoMatching.cpp:1490)."""
+        H, W = disp.shape
+        out = self.empty((H, W), self.torch.float32)
+        check(self.L.sm_median3_f32(self.h, _ptr(disp), _ptr(out), H, W))
+        return out
 
     def median3_i16(self, disp):
         H, W = disp.shape

@@ -484,6 +484,41 @@ extern "C" int sm_median3_i16(sm_ctx* ctx, const int16_t* d_src, int16_t* d_dst,
   return SM_OK;
 }
 
+// 3x3 median, float, replicated border: cv::medianBlur(SE, SE, 3) after subpixelEnhancement (stereoMatching.cpp:1490).
+// Same 19-exchange network on min/max; the input is NaN-free (SE holds converted shorts).
+__device__ __forceinline__ void cswapf(float& a, float& b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo; b = hi;
+}
+
+__global__ void k_median3_f32(const float* __restrict__ src, float* __restrict__ dst, int H, int W) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  float w[9];
+#pragma unroll
+  for (int dv = -1; dv <= 1; dv++)
+#pragma unroll
+    for (int du = -1; du <= 1; du++) {
+      const int y = min(max(v + dv, 0), H - 1), x = min(max(u + du, 0), W - 1);
+      w[(dv + 1) * 3 + du + 1] = src[(size_t)y * W + x];
+    }
+  cswapf(w[1], w[2]); cswapf(w[4], w[5]); cswapf(w[7], w[8]);
+  cswapf(w[0], w[1]); cswapf(w[3], w[4]); cswapf(w[6], w[7]);
+  cswapf(w[1], w[2]); cswapf(w[4], w[5]); cswapf(w[7], w[8]);
+  cswapf(w[0], w[3]); cswapf(w[5], w[8]); cswapf(w[4], w[7]);
+  cswapf(w[3], w[6]); cswapf(w[1], w[4]); cswapf(w[2], w[5]);
+  cswapf(w[4], w[7]); cswapf(w[4], w[2]); cswapf(w[6], w[4]);
+  cswapf(w[4], w[2]);
+  dst[(size_t)v * W + u] = w[4];
+}
+
+extern "C" int sm_median3_f32(sm_ctx* ctx, const float* d_src, float* d_dst, int H, int W) {
+  SM_CHECK_ARG(ctx && d_src && d_dst && d_src != d_dst && H > 0 && W > 0);
+  dim3 grid(sm_div_up(W, 128), H);
+  SM_LAUNCH(ctx, k_median3_f32, grid, 128, 0, d_src, d_dst, H, W);
+  return SM_OK;
+}
+
 // ------------------------------------------------------------------ 1-level cross-scale step
 __global__ void k_scale(float* __restrict__ vol, size_t n, float inv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;

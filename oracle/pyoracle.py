@@ -81,6 +81,7 @@ def lib():
         "orc_region_vote": ([i16p, u16p, I, I, I, F, I], None),
         "orc_proper_ipol": ([i16p, u8p, I, I, I], None),
         "orc_median3_i16": ([i16p, I, I, i16p], None),
+        "orc_median3_f32": ([f32p, I, I, f32p], None),
         "orc_solve_all_1level": ([f32p, C.c_long, F], None),
         "orc_cal_err": ([i16p, f32p, u8p, I, I, I, f32p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")], None),
         "orc_pyr_down_u8": ([u8p, I, I, I, u8p], None),
@@ -323,6 +324,14 @@ def region_vote(dp, arms_l, D, ratio=0.4, S=20):
 def proper_ipol(dp, bgr, occ=-32):
     out = np.ascontiguousarray(dp.copy())
     lib().orc_proper_ipol(out, np.ascontiguousarray(bgr), dp.shape[0], dp.shape[1], occ)
+    return out
+
+
+def median3_f32(dp):
+    """cv::medianBlur(CV_32F, 3) (stereoMatching.cpp:1490)."""
+    dp = np.ascontiguousarray(dp, np.float32)
+    out = np.empty_like(dp)
+    lib().orc_median3_f32(dp, dp.shape[0], dp.shape[1], out)
     return out
 
 

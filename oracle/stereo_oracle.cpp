@@ -683,6 +683,24 @@ void orc_median3_i16(const i16* src, int H, int W, i16* dst) {
     }
 }
 
+// cv::medianBlur(CV_32F, ksize 3) on the sub-pixel map (stereoMatching.cpp:1490): same window, replicated border
+// (pinned against cv2 in tests/golden/subpixel_ref.npz).
+void orc_median3_f32(const float* src, int H, int W, float* dst) {
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      float w[9];
+      int k = 0;
+      for (int dv = -1; dv <= 1; dv++)
+        for (int du = -1; du <= 1; du++) {
+          int y = std::min(std::max(v + dv, 0), H - 1), x = std::min(std::max(u + du, 0), W - 1);
+          w[k++] = src[(long)y * W + x];
+        }
+      std::nth_element(w, w + 4, w + 9);
+      dst[(long)v * W + u] = w[4];
+    }
+}
+
 // The caller's single-level cross-scale step: SolveAll with PY_LVL=1
 // (stereoMatching.cpp:2142-2208; main_.cpp:158): regInv = 1/(1+lambda) as a
 // float, vm = 0 + invWgt*vm.

@@ -37,6 +37,19 @@ out["flat_vol"] = flat
 out["flat_disp_rnd"] = rnd
 out["flat_se_rnd"] = r.subpixel(rnd)
 r.close()
+# refine() then runs cv::medianBlur(SE, SE, 3) on the float map (stereoMatching.cpp:1490): cv2 is that function
+import cv2  # noqa: E402
+for k in ("float_se_wta", "float_se_rnd", "flat_se_rnd"):
+    out[k.replace("_se_", "_semed_")] = cv2.medianBlur(out[k], 3)
+frac = (rng.random((H, W)) * 40 - 8).astype(np.float32)
+frac[3:6, 4:9] = 7.0                                  # equal values
+out["frac_map"] = frac
+out["frac_med"] = cv2.medianBlur(frac, 3)
+for shp in ((1, 1), (1, 9), (7, 1), (2, 2)):          # degenerate shapes: the replicated border does all the work
+    m = (rng.random(shp) * 10).astype(np.float32)
+    out["tiny%dx%d_map" % shp] = m
+    out["tiny%dx%d_med" % shp] = cv2.medianBlur(m, 3)
+out["cv2_version"] = np.array(cv2.__version__)
 path = os.path.join(os.path.dirname(__file__), "subpixel_ref.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, {k: v.shape for k, v in out.items()}, os.path.getsize(path), "bytes")

@@ -571,6 +571,20 @@ def test_subpixel_enhancement_matches_reference_golden(ctx, golden_dir):
     assert n == 3
 
 
+@pytest.mark.timeout(120)
+def test_median3_f32_matches_cv2_golden_and_oracle(ctx, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "subpixel_ref.npz"))    # cv2.medianBlur(CV_32F, 3) outputs
+    pairs = [(k.replace("_semed_", "_se_"), k) for k in g.files if "_semed_" in k]
+    pairs += [(k[:-4] + "_map", k) for k in g.files if k.endswith("_med")]
+    assert len(pairs) == 8
+    for src, want in pairs:
+        assert _bits_equal(ctx.median3_f32(ctx.dev(g[src].copy())).cpu().numpy(), g[want]), want
+    m = (np.random.default_rng(3).random((270, 481)) * 64).astype(np.float32)
+    m[::2] = np.floor(m[::2])
+    assert _bits_equal(ctx.median3_f32(ctx.dev(m)).cpu().numpy(), po.median3_f32(m))
+
+
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("shape", [(37, 53, 33), (24, 40, 256), (1, 1, 3), (9, 11, 2), (270, 480, 64)])
 def test_subpixel_enhancement_matches_oracle(ctx, shape):

@@ -420,3 +420,14 @@ def test_subpixel_equals_reference(golden_dir):
                  np.float32)
     d = np.array([[2, 2, 2, 0, 4, -32]], np.int16)
     assert po.subpixel(d, v).tolist() == [[2.0, 1.0, 2.0, 0.0, 4.0, -32.0]]
+
+
+def test_median3_f32_matches_cv2(golden_dir):
+    """orc_median3_f32 against cv2.medianBlur(CV_32F, 3) on the reference's sub-pixel maps and a fractional map."""
+    import os
+    g = np.load(os.path.join(golden_dir, "subpixel_ref.npz"))
+    pairs = [(k.replace("_semed_", "_se_"), k) for k in g.files if "_semed_" in k]
+    pairs += [(k[:-4] + "_map", k) for k in g.files if k.endswith("_med")]
+    assert len(pairs) == 8
+    for src, want in pairs:
+        assert np.array_equal(po.median3_f32(g[src]).view(np.uint32), g[want].view(np.uint32)), want
