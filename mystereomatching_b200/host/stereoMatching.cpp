@@ -19,6 +19,7 @@ bool StereoMatching::Do_LRConsis = true;
 bool StereoMatching::Do_regionVote = true;
 bool StereoMatching::Do_properIpol = true;
 bool StereoMatching::Do_lastMedianBlur = true;
+bool StereoMatching::Do_subpixelEnhancement = false;
 
 // reference defaults: stereoMatching.h:204-350
 StereoMatching::Parameters::Parameters(int maxDisp, int h, int w, int lamCen_, int lamG_, int M_, int lamc_, int ts_,
@@ -189,6 +190,16 @@ void StereoMatching::refine() {
   }
   if (Do_properIpol)
     for (int i = 0; i < param_.region_vote_nums; i++) properIpol(DP[0], I_c[0]);
+  if (Do_subpixelEnhancement) {   // stereoMatching.cpp:1482-1490: SE from DP[0] and vm[0], then its 3x3 median; DP[0] untouched
+    const size_t npix = (size_t)h_ * w_;
+    if (!dp_dev_fresh_[0]) { upload(d_disp_[0], DP[0].data, npix * 2); dp_dev_fresh_[0] = true; }
+    uploadVm(0);
+    TmpDev a(ctx_, npix * 4), b(ctx_, npix * 4);
+    check(sm_subpixel_enhancement(ctx_, d_disp_[0], d_vol_[0], h_, w_, d_, a.as<float>()), "sm_subpixel_enhancement");
+    check(sm_median3_f32(ctx_, a.as<float>(), b.as<float>(), h_, w_), "sm_median3_f32");
+    SE.create(h_, w_, CV_32FC1);
+    download(SE.data, b.p, npix * 4);
+  }
   if (Do_lastMedianBlur) {   // cv::medianBlur(DP[0], DP[0], 3)
     if (!dp_dev_fresh_[0]) { upload(d_disp_[0], DP[0].data, (size_t)h_ * w_ * 2); dp_dev_fresh_[0] = true; }
     check(sm_median3_i16(ctx_, d_disp_[0], d_tmp16_, h_, w_), "sm_median3_i16");

@@ -44,6 +44,7 @@ class StereoMatching {
 
   // step switches (stereoMatching.h:57-83); only the ones the path honours
   static bool Do_refine, Do_LRConsis, Do_regionVote, Do_properIpol, Do_lastMedianBlur;
+  static bool Do_subpixelEnhancement;   // stereoMatching.h:79 (0 in the reference; a run-time switch here)
   static const bool UniqCk = false, SubIpl = false;
 
   struct Parameters {  // stereoMatching.h:85-351 (fields read on the hot path; same names, same defaults)
@@ -181,6 +182,7 @@ class StereoMatching {
   cv::Mat DP[2];
   cv::Mat DT;
   cv::Mat LRC_Err_Mask;
+  cv::Mat SE;   // refine()'s sub-pixel map after its 3x3 median (a local the reference drops, stereoMatching.cpp:1484-1490)
   cv::Mat guideDisp;
 
  private:

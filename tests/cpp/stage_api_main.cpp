@@ -169,7 +169,19 @@ int main(int argc, char** argv) {
         sm.subpixelEnhancement(dsp, SE);
         dump(out + ".se0.f32", SE.data, npix * 4);
       }
-      sm.refine();
+      {  // refine() with the sub-pixel step on (stereoMatching.cpp:1482-1490), split in two calls so that the map the
+         // step reads (DP[0] before the last median) can be dumped; the end state equals a single refine()
+        StereoMatching::Do_subpixelEnhancement = true;
+        StereoMatching::Do_lastMedianBlur = false;
+        sm.refine();
+        dump(out + ".dp0_premed.i16", sm.hostDP(0).data, npix * 2);
+        dump(out + ".se_refine.f32", sm.SE.data, npix * 4);
+        StereoMatching::Do_subpixelEnhancement = false;
+        StereoMatching::Do_LRConsis = StereoMatching::Do_regionVote = StereoMatching::Do_properIpol = false;
+        StereoMatching::Do_lastMedianBlur = true;
+        sm.refine();
+        StereoMatching::Do_LRConsis = StereoMatching::Do_regionVote = StereoMatching::Do_properIpol = true;
+      }
       // explicit-argument forms: host Mats in, host Mats out
       cv::Mat ad, lr;
       sm.gen_ad_sd_vm(ad, 0, 0, 1000);

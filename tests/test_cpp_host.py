@@ -86,6 +86,11 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
         se = np.fromfile(prefix + ".se0.f32", np.float32).reshape(H, W)
         se_want = po.subpixel(dw, sg)
         assert np.array_equal(se.view(np.uint32), se_want.view(np.uint32)) and (se_want != dw).any()
+        # refine() with Do_subpixelEnhancement: SE = median3(subpixel(DP[0] before the last median, vm[0]))
+        pm = np.fromfile(prefix + ".dp0_premed.i16", np.int16).reshape(H, W)
+        ser = np.fromfile(prefix + ".se_refine.f32", np.float32).reshape(H, W)
+        assert np.array_equal(ser.view(np.uint32), po.median3_f32(po.subpixel(pm, sg)).view(np.uint32))
+        assert np.array_equal(po.median3_i16(pm), dp)            # and the two-call refine ends where one call does
         marked = np.fromfile(prefix + ".top0_vm.f32", np.float32).reshape(H, W, D)
         exp = sg.copy()
         for k in range(6):
