@@ -292,6 +292,20 @@ def test_pipeline_region_of_validity_errors(ctx):
         ctx.sgm_path(ctx.dev(np.zeros((2, 2, 2), np.float32)), ctx.dev(np.zeros((2, 2, 3), np.uint8)), 9)
 
 
+def test_subpixel_and_float_median_argument_errors(ctx):
+    L = capi.lib()
+    m = ctx.dev(np.zeros((4, 5), np.float32))
+    d = ctx.dev(np.zeros((4, 5), np.int16))
+    v = ctx.dev(np.zeros((4, 5, 3), np.float32))
+    p = capi._ptr
+    assert L.sm_median3_f32(ctx.h, p(m), p(m), 4, 5) != 0            # in place is not supported (reads neighbours)
+    assert L.sm_median3_f32(ctx.h, p(m), None, 4, 5) != 0
+    assert L.sm_subpixel_enhancement(ctx.h, p(d), None, 4, 5, 3, p(m)) != 0
+    assert L.sm_subpixel_enhancement(ctx.h, p(d), p(v), 4, 0, 3, p(m)) != 0
+    assert L.sm_subpixel_enhancement(ctx.h, p(d), p(v), 4, 5, 3, p(m)) == 0
+    assert b"" != L.sm_last_error()
+
+
 # ---------------------------------------------------------------- NL: MST + tree filter
 def _nl_images():
     rng = np.random.default_rng(5)
