@@ -67,6 +67,7 @@ CPP_FUNCS = [
     (r"^void StereoMatching::properIpol\(", "properIpol"),
     # default-off refiner
     (r"^void StereoMatching::subpixelEnhancement\(", "subpixelEnhancement"),
+    (r"^void StereoMatching::WM\(", "WM"),
     # the gradient cost family: "censusGrad" is the selector main_.cpp:15 compiles in
     (r"^void StereoMatching::censusGrad\(", "censusGrad"),
     (r"^void StereoMatching::grad\(vector<Mat>& vm_grad, float Trunc\)", "grad"),

@@ -82,6 +82,7 @@ def lib():
         "orc_proper_ipol": ([i16p, u8p, I, I, I], None),
         "orc_median3_i16": ([i16p, I, I, i16p], None),
         "orc_median3_f32": ([f32p, I, I, f32p], None),
+        "orc_wm": ([i16p, u8p, u8p, I, I, I], I),
         "orc_solve_all_1level": ([f32p, C.c_long, F], None),
         "orc_cal_err": ([i16p, f32p, u8p, I, I, I, f32p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")], None),
         "orc_pyr_down_u8": ([u8p, I, I, I, u8p], None),
@@ -327,6 +328,16 @@ def proper_ipol(dp, bgr, occ=-32):
     return out
 
 
+def wm(disp, mask, bgr, D):
+    """WM (stereoMatching.cpp:7340-7393): bilateral weighted median on the mask > 0 pixels; labels must lie in [0, D)."""
+    out = np.ascontiguousarray(disp, np.int16).copy()
+    H, W = out.shape
+    n = lib().orc_wm(out, np.ascontiguousarray(mask, np.uint8), np.ascontiguousarray(bgr, np.uint8), H, W, D)
+    if n < 0:
+        raise ValueError("WM: a label outside [0, D) inside a window: undefined in the reference (stereoMatching.cpp:7371)")
+    return out
+
+
 def median3_f32(dp):
     """cv::medianBlur(CV_32F, 3) (stereoMatching.cpp:1490)."""
     dp = np.ascontiguousarray(dp, np.float32)
@@ -506,6 +517,7 @@ def smref_lib():
         "smref_wta": ([P, I, i16p], None), "smref_wta_co": ([P, I, i16p, i16p], None),
         "smref_select_top": ([P, I, I, F, f32p], None),
         "smref_subpixel": ([P, i16p, f32p], None),
+        "smref_wm": ([P, i16p, u8p], None),
         "smref_lrc_normal": ([P, i16p, i16p], None), "smref_lrc_label": ([P, i16p, i16p, I, P], None),
         "smref_lrc_new": ([P, i16p, i16p, u8p], None),
         "smref_region_vote": ([P, i16p, F, I], None), "smref_proper_ipol": ([P, i16p], None),
@@ -662,6 +674,12 @@ class SmRef:
         """The reference's own subpixelEnhancement on the given disparity map and vm[0]."""
         o = np.empty((self.H, self.W), np.float32)
         self.L.smref_subpixel(self.h, np.ascontiguousarray(disp, np.int16), o)
+        return o
+
+    def wm(self, disp, mask):
+        """The reference's own WM on the given map and mask with I_c[0] as guidance."""
+        o = np.ascontiguousarray(disp, np.int16).copy()
+        self.L.smref_wm(self.h, o, np.ascontiguousarray(mask, np.uint8))
         return o
 
     def wta_co(self, view=0):

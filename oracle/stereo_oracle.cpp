@@ -683,6 +683,46 @@ void orc_median3_i16(const i16* src, int H, int W, i16* dst) {
     }
 }
 
+// WM (stereoMatching.cpp:7340-7393; default off, Do_WM): on every mask > 0 pixel, a 19x19 (REFLECT_101) bilateral
+// weighted median of the labels: w = exp(-|dI|^2 / 25^2 - |dx|^2 / 9^2) evaluated in float from exactly converted
+// integers, histogram and running sums in float in window raster order, first d with cum >= sum / 2.  The window
+// reads the ORIGINAL padded copy of the map, the result goes to the map.  DEFINED ONLY when every label inside the
+// windows is in [0, D): the reference indexes dispHist[q] unchecked (:7371); this restatement then restores the map and
+// returns -1.  Otherwise returns the number of pixels rewritten.
+int orc_wm(short* disp, const unsigned char* mask, const unsigned char* bgr, int H, int W, int D) {
+  const int R = 9;
+  auto refl = [](int p, int n) { if (n == 1) return 0; while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p; return p; };
+  std::vector<short> src(disp, disp + (long)H * W);
+  int num = 0;
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      if (!mask[(long)v * W + u]) continue;
+      std::vector<float> hist(D, 0.f);
+      float wsum = 0.f;
+      const unsigned char* ip = bgr + ((long)v * W + u) * 3;
+      for (int dv = -R; dv <= R; dv++)
+        for (int du = -R; du <= R; du++) {
+          const long j = (long)refl(v + dv, H) * W + refl(u + du, W);
+          const short q = src[j];
+          if (q < 0 || q >= D) { std::memcpy(disp, src.data(), sizeof(short) * H * W); return -1; }
+          const unsigned char* iq = bgr + j * 3;
+          int c2 = 0;
+          for (int c = 0; c < 3; c++) c2 += ((int)ip[c] - (int)iq[c]) * ((int)ip[c] - (int)iq[c]);
+          const float colDis = (float)c2, spaDis = (float)(dv * dv + du * du);
+          const float wgt = std::exp(-colDis / (25.f * 25.f) - spaDis / (9.f * 9.f));
+          hist[q] += wgt;
+          wsum += wgt;
+        }
+      const float half = wsum / 2;
+      float cum = 0.f;
+      for (int d = 0; d < D; d++) {
+        cum += hist[d];
+        if (cum >= half) { disp[(long)v * W + u] = (short)d; num++; break; }
+      }
+    }
+  return num;
+}
+
 // cv::medianBlur(CV_32F, ksize 3) on the sub-pixel map (stereoMatching.cpp:1490): same window, replicated border
 // (pinned against cv2 in tests/golden/subpixel_ref.npz).
 void orc_median3_f32(const float* src, int H, int W, float* dst) {

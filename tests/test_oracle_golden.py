@@ -431,3 +431,26 @@ def test_median3_f32_matches_cv2(golden_dir):
     assert len(pairs) == 8
     for src, want in pairs:
         assert np.array_equal(po.median3_f32(g[src]).view(np.uint32), g[want].view(np.uint32)), want
+
+
+def test_wm_equals_reference(golden_dir):
+    """orc_wm against the outputs of the reference's own WM (tests/golden/wm_ref.npz); labels outside [0, D) -- where the
+    reference is undefined (stereoMatching.cpp:7371) -- are refused."""
+    import os
+    g = np.load(os.path.join(golden_dir, "wm_ref.npz"))
+    n = changed = 0
+    for k in g.files:
+        if not k.endswith("_out"):
+            continue
+        tag = k.split("_")[0]
+        disp, mask = g[k[:-4] + "_in"], g[k[:-4] + "_mask"]
+        got = po.wm(disp, mask, g[tag + "_bgr"], int(g[tag + "_D"]))
+        assert np.array_equal(got, g[k]), k
+        assert np.array_equal(got[mask == 0], disp[mask == 0])      # only flagged pixels are rewritten
+        changed += int((got != disp).sum())
+        n += 1
+    assert n == 9 and changed > 0
+    bad = g["a_noisy_some_in"].copy()
+    bad[3, 3] = -32                                                 # DISP_OCC inside somebody's window
+    with pytest.raises(ValueError):
+        po.wm(bad, g["a_noisy_some_mask"], g["a_bgr"], int(g["a_D"]))
