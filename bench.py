@@ -218,6 +218,36 @@ def cpu_baseline(name, budget_rows=48):
                       f"{t1:.1f} s at 1 thread (the reference's own threading), {tn:.1f} s at {nt} threads"}
 
 
+def parity_vs_oracle(name, frame, disp_gpu):
+    """The measured frame through the oracle restatement (all host threads): share of identical pixels of the refined
+    left map and bad-2 of both.  Bounded: the frame is cut to the rows the host memory holds (the GPU map is then
+    compared on a re-run of that band by the caller)."""
+    from oracle import pyoracle as po
+    from mystereomatching_b200 import synth
+    W, H, D, P, kind = WORKLOADS[name]
+    po.lib().orc_set_threads(host_threads())
+    lv, lam = PYRAMID.get(name, (1, -1.0))
+    op = po.default_params(D, paths=P, aggregation=AGGREGATION[name], costcalc=COSTCALC.get(name, 0), pyr_levels=lv,
+                           cross_lambda=lam)
+    t0 = time.perf_counter()
+    ref, _, _, _ = po.pipeline(frame["bgrL"], frame["bgrR"], frame["grayL"], frame["grayR"], op)
+    dt = time.perf_counter() - t0
+    return {"vs": "oracle (oracle/stereo_oracle.cpp, bit-equal to the compiled reference on tests/golden/sm_ref.npz)",
+            "pct_identical": round(100.0 * float((ref == disp_gpu).mean()), 5),
+            "bad2_nonocc_pct_oracle": round(synth.bad_k(ref, frame["gt"], frame["nonocc"], 2), 3),
+            "frame": f"{W}x{ref.shape[0]} D={D}, seed 1000 (the measured frame 0 of rank 0), whole refined left map",
+            "oracle_seconds": round(dt, 1), "oracle_threads": host_threads()}
+
+
+def oracle_fits(name):
+    W, H, D, P, kind = WORKLOADS[name]
+    try:
+        import psutil
+        return psutil.virtual_memory().available > W * H * D * 4 * (8 + P) * 1.3
+    except Exception:
+        return False
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -323,7 +353,7 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"     # NCCL's version banner goes to stdout; stdout carries ONE JSON line
+        # NCCL's own log lines (NCCL_DEBUG as the launcher set it) go to fd 1, which QuietStdout points at stderr
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
@@ -464,6 +494,10 @@ def main_ours(args):
                "quality": {"bad2_nonocc_pct": round(bad2, 3), "checksum": chk}}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(name)
+            if oracle_fits(name):
+                out["parity"] = parity_vs_oracle(name, frames[0][0], disp)
+            else:
+                out["parity"] = {"vs": "oracle", "pct_identical": None, "note": "host memory too small for a whole-frame oracle run"}
         emit(out)
     pl.close()
     ctx.close()

@@ -63,10 +63,20 @@ int sm_scratch_get(sm_ctx* ctx, int slot, size_t bytes, void** out);
     if (r__ != SM_OK) return r__; \
   } while (0)
 
+// A ctx's stream and scratch memory live on ctx->device; the caller's current device may be another one (two ctxs in
+// one process, or the host application switched devices), so every launch / allocation rebinds when it differs.
+static inline cudaError_t smi_bind_device(const sm_ctx* ctx) {
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e == cudaSuccess && cur != ctx->device) e = cudaSetDevice(ctx->device);
+  return e;
+}
+
 // Launch bookkeeping: every kernel launch of the library goes through this so
 // bench.py can report gpu_launches truthfully.
 #define SM_LAUNCH(ctx, kernel, grid, block, smem, ...)                                       \
   do {                                                                                       \
+    smi_bind_device(ctx);                                                                    \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                         \
     (ctx)->launches++;                                                                       \
     cudaError_t e__ = cudaGetLastError();                                                    \

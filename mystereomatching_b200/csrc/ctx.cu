@@ -146,24 +146,28 @@ extern "C" int sm_host_free_pinned(void* h_ptr) {
 
 extern "C" int sm_memcpy_h2d(sm_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   SM_CHECK_ARG(ctx && d_dst && h_src);
+  SM_CUDA(smi_bind_device(ctx));
   SM_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return SM_OK;
 }
 
 extern "C" int sm_memcpy_d2h(sm_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
   SM_CHECK_ARG(ctx && h_dst && d_src);
+  SM_CUDA(smi_bind_device(ctx));
   SM_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return SM_OK;
 }
 
 extern "C" int sm_memset(sm_ctx* ctx, void* d_dst, int byte, size_t bytes) {
   SM_CHECK_ARG(ctx && d_dst);
+  SM_CUDA(smi_bind_device(ctx));
   SM_CUDA(cudaMemsetAsync(d_dst, byte, bytes, ctx->stream));
   return SM_OK;
 }
 
 extern "C" int sm_memcpy_d2d(sm_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
   SM_CHECK_ARG(ctx && d_dst && d_src);
+  SM_CUDA(smi_bind_device(ctx));
   SM_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return SM_OK;
 }
@@ -171,6 +175,7 @@ extern "C" int sm_memcpy_d2d(sm_ctx* ctx, void* d_dst, const void* d_src, size_t
 int sm_scratch_get(sm_ctx* ctx, int slot, size_t bytes, void** out) {
   sm_scratch& s = ctx->scr[slot];
   if (s.cap < bytes) {
+    SM_CUDA(smi_bind_device(ctx));
     // Growing is rare (first frame of a new size).  The old block may still be
     // read by queued kernels, so drain the stream before freeing it.
     if (s.p) {

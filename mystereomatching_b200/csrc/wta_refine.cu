@@ -244,55 +244,6 @@ extern "C" int sm_lrc_label(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int
 // arms of the left image) go into a per-warp shared-memory histogram.
 #define RV_WARPS 8
 
-__global__ void __launch_bounds__(RV_WARPS * 32)
-    k_region_vote(const int16_t* __restrict__ src, int16_t* __restrict__ dst, const uint16_t* __restrict__ arms, int H,
-                  int W, int D, float ratio, int S) {
-  extern __shared__ int hist_all[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int* hist = hist_all + warp * D;
-  const long long npix = (long long)H * W;
-  long long p = (long long)blockIdx.x * RV_WARPS + warp;
-  const long long stride = (long long)gridDim.x * RV_WARPS;
-  for (; p < npix; p += stride) {
-    const int16_t cur = src[p];
-    if (cur >= 0) { if (lane == 0) dst[p] = cur; continue; }
-    const int v = (int)(p / W), u = (int)(p - (long long)v * W);
-    for (int d = lane; d < D; d += 32) hist[d] = 0;
-    __syncwarp();
-    const uint16_t* a = arms + p * 5;
-    const int vb = v - a[2], ve = v + a[3];
-    int valid = 0;
-    for (int vn = vb; vn <= ve; vn++) {
-      const uint16_t* b = arms + ((size_t)vn * W + u) * 5;
-      const int ub = u - b[0], ue = u + b[1];
-      for (int un = ub + lane; un <= ue; un += 32) {
-        const int x = src[(size_t)vn * W + un];
-        if (x >= 0) { valid++; if (x < D) atomicAdd(&hist[x], 1); }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
-    __syncwarp();
-    int16_t res = cur;
-    if (valid > S) {
-      // mode with the lowest d on ties: maximise (count, -d)
-      int bc = -1, bd = 0;
-      for (int d = lane; d < D; d += 32) {
-        const int c = hist[d];
-        if (c > bc) { bc = c; bd = d; }
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, o), od = __shfl_xor_sync(0xffffffffu, bd, o);
-        if (oc > bc || (oc == bc && od < bd)) { bc = oc; bd = od; }
-      }
-      if ((float)(bc / valid) >= ratio) res = (int16_t)bd;  // integer division, as the reference
-    }
-    if (lane == 0) dst[p] = res;
-    __syncwarp();
-  }
-}
-
 // Two steps instead of one persistent sweep.  k_region_vote walks ALL pixels one per warp iteration (a dependent 2-byte
 // load each) and, inside a vote, reads one row's arms, then that row's disparities, row after row -- two dependent
 // global loads per row, ~20 rows per vote: a chain of latencies (0.26 ms per call at 1080p).  Here k_rv_scan copies the
@@ -380,24 +331,18 @@ __global__ void __launch_bounds__(RV_WARPS * 32)
 
 extern "C" int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint16_t* d_arms, int H, int W, int D,
                               float ratio, int S) {
-  SM_CHECK_ARG(ctx && d_disp && d_tmp && d_arms && H > 0 && W > 0 && D > 0 && D <= 4096);
+  SM_CHECK_ARG(ctx && d_disp && d_tmp && d_arms && H > 0 && W > 0 && D > 0 && D <= 1536);   // RV_WARPS histograms of D ints in 48 KB
   const long long npix = (long long)H * W;
-  static const int rv_list = getenv("SM_RV_LIST") ? atoi(getenv("SM_RV_LIST")) : 1;   // 0: the one-kernel sweep
-  if (rv_list && npix < (1ll << 31)) {
-    void* p;
-    SM_TRY(sm_scratch_get(ctx, SM_SCR_RVLIST, 256 + (size_t)npix * 4, &p));
-    int* count = (int*)p;
-    int* list = (int*)((uint8_t*)p + 256);
-    SM_CUDA(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream));
-    SM_LAUNCH(ctx, k_rv_scan, (int)((npix + 255) / 256), 256, 0, d_disp, d_tmp, npix, count, list);
-    const int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
-    SM_LAUNCH(ctx, k_rv_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio, S,
-              count, list);
-  } else {
-    int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
-    SM_LAUNCH(ctx, k_region_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio,
-              S);
-  }
+  SM_CHECK_ARG(npix < (1ll << 31));
+  void* p;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_RVLIST, 256 + (size_t)npix * 4, &p));
+  int* count = (int*)p;
+  int* list = (int*)((uint8_t*)p + 256);
+  SM_CUDA(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream));
+  SM_LAUNCH(ctx, k_rv_scan, (int)((npix + 255) / 256), 256, 0, d_disp, d_tmp, npix, count, list);
+  const int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
+  SM_LAUNCH(ctx, k_rv_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio, S,
+            count, list);
   SM_CUDA(cudaMemcpyAsync(d_disp, d_tmp, npix * sizeof(int16_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return SM_OK;
 }

@@ -89,6 +89,7 @@ def lib():
         "orc_cross_scale_weights": ([I, F, f32p], None),
         "orc_solve_all": ([C.POINTER(C.c_void_p), i32p, i32p, i32p, I, F], None),
         "orc_pipeline": ([u8p, u8p, u8p, u8p, I, I, C.POINTER(OrcParams), i16p, i16p, P, P], None),
+        "orc_pipeline_ex": ([u8p, u8p, u8p, u8p, I, I, C.POINTER(OrcParams), i16p, i16p, P, P, P], None),
         "orc_ctmf": ([u8p, u8p, I, I, I, I, I, I], None),
         "orc_mst": ([u8p, I, I, I, i32p, u8p, i32p, i32p, i32p, i32p, P], None),
         "orc_tree_table": ([C.c_double, f64p], None),
@@ -352,17 +353,24 @@ def median3_i16(dp):
     return out
 
 
-def pipeline(bgrL, bgrR, grayL, grayR, params, want_vol=False):
+def pipeline(bgrL, bgrR, grayL, grayR, params, want_vol=False, want_agg=False):
+    """The whole chain.  Returns (dispL, dispR, vm[0] after sgm or None, stage ms); with want_agg the dict also holds
+    "agg" = vm[0] as costCalculate() leaves it (aggregated, before sgm)."""
     H, W, _ = bgrL.shape
     dl = np.empty((H, W), np.int16)
     dr = np.empty((H, W), np.int16)
     vol = np.empty((H, W, params.D), np.float32) if want_vol else None
+    agg = np.empty((H, W, params.D), np.float32) if want_agg else None
     ms = np.zeros(8, np.float32)
-    lib().orc_pipeline(np.ascontiguousarray(bgrL), np.ascontiguousarray(bgrR),
-                       np.ascontiguousarray(grayL), np.ascontiguousarray(grayR), H, W,
-                       C.byref(params), dl, dr, vol.ctypes.data if want_vol else None, ms.ctypes.data)
+    lib().orc_pipeline_ex(np.ascontiguousarray(bgrL), np.ascontiguousarray(bgrR),
+                          np.ascontiguousarray(grayL), np.ascontiguousarray(grayR), H, W,
+                          C.byref(params), dl, dr, vol.ctypes.data if want_vol else None, ms.ctypes.data,
+                          agg.ctypes.data if want_agg else None)
     names = ("census", "cost", "arms", "cbca", "sgm", "wta", "refine", "total")
-    return dl, dr, vol, dict(zip(names, ms.tolist()))
+    info = dict(zip(names, ms.tolist()))
+    if want_agg:
+        info["agg"] = agg
+    return dl, dr, vol, info
 
 
 def ctmf(img, r):

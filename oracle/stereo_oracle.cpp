@@ -951,8 +951,10 @@ static void cost_calculate(const u8* bgrL, const u8* bgrR, const u8* grayL, cons
 }
 
 extern "C" {
-void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* grayR, int H, int W,
-                  const orc_params* p, i16* dispL, i16* dispR, float* volL_out, float* stage_ms) {
+// aggL_out (nullable): vm[0] as costCalculate() leaves it (after aggregation / SolveAll, before sgm) -- lets a test
+// compare the aggregated volume and the optimised one from a single run of the chain.
+void orc_pipeline_ex(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* grayR, int H, int W,
+                     const orc_params* p, i16* dispL, i16* dispR, float* volL_out, float* stage_ms, float* aggL_out) {
   const int D = p->D;
   const long n = (long)H * W * D;
   double t0 = now_ms(), t = t0, ms[8] = {0};
@@ -993,6 +995,7 @@ void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* gra
     t = now_ms();
   }
   lap(3);
+  if (aggL_out) std::memcpy(aggL_out, vm[0].data(), n * sizeof(float));
   for (int i = 0; i < views; i++)
     orc_sgm(vm[i].data(), i == 0 ? bgrL : bgrR, H, W, D, p->paths, p->corDifThres, p->reduCoeffi1);
   lap(4);
@@ -1012,5 +1015,10 @@ void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* gra
   ms[7] = now_ms() - t0;
   if (stage_ms)
     for (int k = 0; k < 8; k++) stage_ms[k] = (float)ms[k];
+}
+
+void orc_pipeline(const u8* bgrL, const u8* bgrR, const u8* grayL, const u8* grayR, int H, int W,
+                  const orc_params* p, i16* dispL, i16* dispR, float* volL_out, float* stage_ms) {
+  orc_pipeline_ex(bgrL, bgrR, grayL, grayR, H, W, p, dispL, dispR, volL_out, stage_ms, nullptr);
 }
 }  // extern "C"
