@@ -284,6 +284,13 @@ int sm_lrc(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int H, int W, float 
  * labelling; d_errMask (nullable) [H][W] u8. */
 int sm_lrc_label(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int H, int W, int D,
                  float LRmaxDiff, int DISP_OCC, int DISP_MIS, uint8_t* d_errMask);
+/* LRConsistencyCheck with either LOR (stereoMatching.cpp:2284-2364).  LOR 0: as sm_lrc_label (d_D1 labelled in
+ * place, d_errMask = flags, d_errMask1 = 0).  LOR 1 (:2336-2364): the RIGHT map d_D2 is checked against d_D1
+ * (u + d inside the image, |d - D1[u+d]| <= LRmaxDiff) and labelled in place; the reference leaves errMask all zero on
+ * this branch and puts the flags into a local errMask1 (written to LR1.png only): d_errMask <- 0, d_errMask1 <- flags.
+ * Both masks are nullable. */
+int sm_lrc_label_lor(sm_ctx* ctx, int16_t* d_D1, int16_t* d_D2, int H, int W, int D, float LRmaxDiff, int DISP_OCC,
+                     int DISP_MIS, int LOR, uint8_t* d_errMask, uint8_t* d_errMask1);
 /* regionVote_my (stereoMatching.cpp:7219-7277): one Jacobi sweep, in place.
  * d_arms = HVL[0]; d_tmp = scratch [H][W] int16. */
 int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint16_t* d_arms, int H, int W,

@@ -101,6 +101,7 @@ SIGNATURES = {
     "sm_subpixel_enhancement": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "sm_lrc": ([_P, _P, _P, _I, _I, _F], _I),
     "sm_lrc_label": ([_P, _P, _P, _I, _I, _I, _F, _I, _I, _P], _I),
+    "sm_lrc_label_lor": ([_P, _P, _P, _I, _I, _I, _F, _I, _I, _I, _P, _P], _I),
     "sm_region_vote": ([_P, _P, _P, _P, _I, _I, _I, _F, _I], _I),
     "sm_proper_ipol": ([_P, _P, _P, _P, _I, _I, _I], _I),
     "sm_median3_i16": ([_P, _P, _P, _I, _I], _I),
@@ -414,6 +415,14 @@ class Ctx:
         mask = self.empty((H, W), self.torch.uint8)
         check(self.L.sm_lrc_label(self.h, _ptr(d1), _ptr(d2), H, W, D, max_diff, occ, mis, _ptr(mask)))
         return d1, mask
+
+    def lrc_label_lor(self, d1, d2, D, LOR, max_diff=0.0, occ=-32, mis=-48):
+        """LRConsistencyCheck(D1, D2, errMask, LOR): returns (errMask, errMask1); d1 (LOR 0) or d2 (LOR 1) is labelled in place."""
+        H, W = d1.shape
+        mask = self.empty((H, W), self.torch.uint8)
+        mask1 = self.empty((H, W), self.torch.uint8)
+        check(self.L.sm_lrc_label_lor(self.h, _ptr(d1), _ptr(d2), H, W, D, max_diff, occ, mis, LOR, _ptr(mask), _ptr(mask1)))
+        return mask, mask1
 
     def region_vote(self, disp, arms_l, D, ratio=0.4, S=20):
         H, W = disp.shape

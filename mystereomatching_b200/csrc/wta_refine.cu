@@ -238,6 +238,40 @@ extern "C" int sm_lrc_label(sm_ctx* ctx, int16_t* d_D1, const int16_t* d_D2, int
   return SM_OK;
 }
 
+// LOR == 1 branch (stereoMatching.cpp:2336-2364): the right map is checked against the left one and labelled in place;
+// D1 is only read, so the sweep is data-parallel like the LOR == 0 one.  The reference's errMask stays all zero on this
+// branch (the flags go to a local errMask1 that is only written to LR1.png): mask <- 0, mask1 <- the flags.
+__global__ void k_lrc_label_right(const int16_t* __restrict__ D1, int16_t* __restrict__ D2, int H, int W, int D,
+                                  float maxDiff, int occ, int mis, uint8_t* __restrict__ mask, uint8_t* __restrict__ mask1) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t i = (size_t)v * W + u;
+  const int d = D2[i];
+  uint8_t m = 0;
+  if (d < 0 || u + d >= W || (float)abs(d - (int)D1[i + d]) > maxDiff) {
+    m = 255;
+    int disp = occ;
+    for (int dd = 0; dd < D && u + dd <= W - 1; dd++)
+      if (D1[i + dd] == dd) { disp = mis; break; }
+    D2[i] = (int16_t)disp;
+  }
+  if (mask) mask[i] = 0;
+  if (mask1) mask1[i] = m;
+}
+
+extern "C" int sm_lrc_label_lor(sm_ctx* ctx, int16_t* d_D1, int16_t* d_D2, int H, int W, int D, float LRmaxDiff,
+                                int DISP_OCC, int DISP_MIS, int LOR, uint8_t* d_errMask, uint8_t* d_errMask1) {
+  SM_CHECK_ARG(ctx && d_D1 && d_D2 && H > 0 && W > 0 && D > 0 && (LOR == 0 || LOR == 1));
+  dim3 grid(sm_div_up(W, 256), H);
+  if (LOR == 0) {
+    SM_LAUNCH(ctx, k_lrc_label, grid, 256, 0, d_D1, d_D2, H, W, D, LRmaxDiff, DISP_OCC, DISP_MIS, d_errMask);
+    if (d_errMask1) SM_CUDA(cudaMemsetAsync(d_errMask1, 0, (size_t)H * W, ctx->stream));   // Mat::zeros, untouched on this branch
+  } else {
+    SM_LAUNCH(ctx, k_lrc_label_right, grid, 256, 0, d_D1, d_D2, H, W, D, LRmaxDiff, DISP_OCC, DISP_MIS, d_errMask, d_errMask1);
+  }
+  return SM_OK;
+}
+
 // ------------------------------------------------------------------ region voting
 // One warp per pixel; valid pixels copy through.  The votes of the cross region
 // (vertical arm of the anchor, horizontal arm of each pixel on it; image-space

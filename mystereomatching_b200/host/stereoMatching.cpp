@@ -772,7 +772,7 @@ void StereoMatching::selectTopCostFromVolumn(Mat& vm_, Mat& topDisp, float thres
 // ------------------------------------------------------------------ refinement
 void StereoMatching::LRConsistencyCheck_normal(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR) {
   (void)errMask;
-  CV_Assert(LOR == 0);
+  if (LOR != 0) return;   // the reference's body is `if (LOR == 0) {...}` and nothing else (stereoMatching.cpp:2262-2282)
   if (&D1 == &DP[0] && &D2 == &DP[1]) {
     for (int i = 0; i < 2; i++)
       if (!dp_dev_fresh_[i]) { upload(d_disp_[i], DP[i].data, (size_t)h_ * w_ * 2); dp_dev_fresh_[i] = true; }
@@ -786,20 +786,23 @@ void StereoMatching::LRConsistencyCheck_normal(cv::Mat& D1, cv::Mat& D2, cv::Mat
   }
 }
 
+// LOR 0 labels D1 against D2, LOR 1 labels D2 against D1 (stereoMatching.cpp:2284-2364).  On the LOR 1 branch the
+// reference leaves errMask all zero (its flags go to a local mask that is only dumped to LR1.png; no file is written here).
 void StereoMatching::LRConsistencyCheck(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR) {
-  CV_Assert(LOR == 0);
+  CV_Assert(LOR == 0 || LOR == 1);
   const size_t pb = (size_t)h_ * w_ * 2;
   TmpDev a(ctx_, pb), b(ctx_, pb), m(ctx_, (size_t)h_ * w_);
   const bool member = &D1 == &DP[0] && &D2 == &DP[1];
   if (member && dp_dev_fresh_[0]) hostDP(0);
   if (member && dp_dev_fresh_[1]) hostDP(1);
   upload(a.p, D1.data, pb); upload(b.p, D2.data, pb);
-  check(sm_lrc_label(ctx_, a.as<int16_t>(), b.as<int16_t>(), h_, w_, d_, param_.LRmaxDiff, param_.DISP_OCC, param_.DISP_MIS,
-                     m.as<uint8_t>()), "sm_lrc_label");
-  download(D1.data, a.p, pb);
+  check(sm_lrc_label_lor(ctx_, a.as<int16_t>(), b.as<int16_t>(), h_, w_, d_, param_.LRmaxDiff, param_.DISP_OCC,
+                         param_.DISP_MIS, LOR, m.as<uint8_t>(), nullptr), "sm_lrc_label_lor");
+  if (LOR == 0) download(D1.data, a.p, pb);
+  else download(D2.data, b.p, pb);
   errMask.create(h_, w_, CV_8UC1);
   download(errMask.data, m.p, (size_t)h_ * w_);
-  if (member) dp_dev_fresh_[0] = false;
+  if (member) dp_dev_fresh_[LOR] = false;
 }
 
 void StereoMatching::regionVote_my(cv::Mat& Dp, float rv_ratio, int rv_s) {

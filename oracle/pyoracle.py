@@ -78,6 +78,7 @@ def lib():
         "orc_subpixel": ([i16p, f32p, I, I, I, f32p], None),
         "orc_lrc_normal": ([i16p, i16p, I, I, F], None),
         "orc_lrc_label": ([i16p, i16p, I, I, I, F, I, I, u8p], None),
+        "orc_lrc_label_right": ([i16p, i16p, I, I, I, F, I, I, u8p], None),
         "orc_region_vote": ([i16p, u16p, I, I, I, F, I], None),
         "orc_proper_ipol": ([i16p, u8p, I, I, I], None),
         "orc_median3_i16": ([i16p, I, I, i16p], None),
@@ -315,6 +316,14 @@ def lrc_label(d1, d2, D, max_diff=0.0, occ=-32, mis=-48):
     mask = np.empty(d1.shape, np.uint8)
     lib().orc_lrc_label(out, np.ascontiguousarray(d2), d1.shape[0], d1.shape[1], D, max_diff, occ, mis, mask)
     return out, mask
+
+
+def lrc_label_right(d1, d2, D, max_diff=0.0, occ=-32, mis=-48):
+    """LRConsistencyCheck, LOR = 1 (stereoMatching.cpp:2336-2364): returns (labelled right map, errMask1)."""
+    out = np.ascontiguousarray(d2.copy())
+    mask1 = np.empty(d2.shape, np.uint8)
+    lib().orc_lrc_label_right(np.ascontiguousarray(d1), out, d1.shape[0], d1.shape[1], D, max_diff, occ, mis, mask1)
+    return out, mask1
 
 
 def region_vote(dp, arms_l, D, ratio=0.4, S=20):

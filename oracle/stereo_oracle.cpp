@@ -587,6 +587,26 @@ void orc_lrc_label(i16* D1, const i16* D2, int H, int W, int D, float maxDiff, i
     }
 }
 
+// LRConsistencyCheck, LOR=1 branch (stereoMatching.cpp:2336-2364): the right map checked against the left one and
+// labelled in place (D1 is only read).  errMask1 = the flags of the reference's local mask (its errMask stays zero).
+void orc_lrc_label_right(const i16* D1, i16* D2, int H, int W, int D, float maxDiff, int DISP_OCC, int DISP_MIS,
+                         u8* errMask1) {
+  ORC_PAR_FOR
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      long i = (long)v * W + u;
+      i16 d = D2[i];
+      errMask1[i] = 0;
+      if (d < 0 || u + d >= W || std::abs(d - D1[i + d]) > maxDiff) {
+        int disp = DISP_OCC;
+        for (int dd = 0; dd < D && u + dd <= W - 1; dd++)
+          if (D1[i + dd] == dd) { disp = DISP_MIS; break; }
+        D2[i] = (i16)disp;
+        errMask1[i] = 255;
+      }
+    }
+}
+
 // regionVote_my (stereoMatching.cpp:7219-7277).  arms = HVL[0] (image-space
 // arms of the LEFT image, not intersected).  Note hist[mode]/validNum is an
 // integer division (line 7270).  Jacobi update (reads Dp, writes a clone).
