@@ -298,6 +298,14 @@ int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint16_t*
 /* properIpol (stereoMatching.cpp:7395-7490): one Jacobi sweep, in place. */
 int sm_proper_ipol(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* d_bgr, int H, int W,
                    int DISP_OCC);
+/* WM (stereoMatching.cpp:7340-7393; Do_WM, stereoMatching.h:74, off): 19x19 bilateral weighted median on the pixels
+ * with d_mask > 0, in place on d_disp (the window reads the map as it was on entry; d_tmp = scratch [H][W] int16).
+ * d_bgr = the guidance image (I_c[0]).  Weights use expf exactly as the host libm evaluates it, and every float sum
+ * keeps the reference's order: bit-exact.  A label outside [0, D) inside a window is undefined behaviour in the
+ * reference (:7371); here it adds to the total weight but casts no vote, and *d_numInvalid (device int, nullable)
+ * receives how many such neighbours were seen. */
+int sm_wm(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* d_mask, const uint8_t* d_bgr, int H, int W, int D,
+          int* d_numInvalid);
 /* cv::medianBlur(CV_16S, 3) (stereoMatching.cpp:1499). d_dst != d_src. */
 int sm_median3_i16(sm_ctx* ctx, const int16_t* d_src, int16_t* d_dst, int H, int W);
 /* cv::medianBlur(SE, SE, 3) on the CV_32F map subpixelEnhancement returns

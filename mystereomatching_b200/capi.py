@@ -104,6 +104,7 @@ SIGNATURES = {
     "sm_lrc_label_lor": ([_P, _P, _P, _I, _I, _I, _F, _I, _I, _I, _P, _P], _I),
     "sm_region_vote": ([_P, _P, _P, _P, _I, _I, _I, _F, _I], _I),
     "sm_proper_ipol": ([_P, _P, _P, _P, _I, _I, _I], _I),
+    "sm_wm": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "sm_median3_i16": ([_P, _P, _P, _I, _I], _I),
     "sm_median3_f32": ([_P, _P, _P, _I, _I], _I),
     "sm_cross_scale_1level": ([_P, _P, _Z, _F], _I),
@@ -435,6 +436,14 @@ class Ctx:
         tmp = self.torch.empty_like(disp)
         check(self.L.sm_proper_ipol(self.h, _ptr(disp), _ptr(tmp), _ptr(bgr), H, W, occ))
         return disp
+
+    def wm(self, disp, mask, bgr, D):
+        """WM (stereoMatching.cpp:7340-7393), in place on `disp`; returns (disp, number of out-of-range window labels)."""
+        H, W = disp.shape
+        tmp = self.torch.empty_like(disp)
+        bad = self.torch.zeros((1,), dtype=self.torch.int32, device=disp.device)
+        check(self.L.sm_wm(self.h, _ptr(disp), _ptr(tmp), _ptr(mask), _ptr(bgr), H, W, D, _ptr(bad)))
+        return disp, int(bad.item())
 
     def median3_f32(self, disp):
         """cv::medianBlur(CV_32F, 3) (stereoMatching.cpp:1490)."""

@@ -306,9 +306,10 @@ extern "C" int sm_cost_ad(sm_ctx* ctx, const uint8_t* d_bgrL, const uint8_t* d_b
 __global__ void k_combine_exp(const float* __restrict__ a, const float* __restrict__ b, size_t n, float l0, float l1,
                               float* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  // Stage-API completeness only (two materialised inputs, device expf -> 1e-4
-  // relative, not bit-exact); the pipeline uses the fused table kernel above.
-  for (; i < n; i += stride) out[i] = (2.0f - expf(-a[i] / l0)) - expf(-b[i] / l1);
+  // gen_vm_from2vm_exp on two materialised volumes (stereoMatching.cpp:3566-3590): expf as the host libm evaluates it
+  // (smd_expf_host) and the same two subtractions -> bit-exact.  The pipeline uses the fused table kernel above.
+  for (; i < n; i += stride)
+    out[i] = __fsub_rn(__fsub_rn(2.0f, smd_expf_host(__fdiv_rn(-a[i], l0))), smd_expf_host(__fdiv_rn(-b[i], l1)));
 }
 
 extern "C" int sm_combine_exp(sm_ctx* ctx, const float* d_vm0, const float* d_vm1, size_t n, float aru0, float aru1,

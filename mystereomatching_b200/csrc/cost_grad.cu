@@ -73,9 +73,8 @@ __device__ __forceinline__ float cost_grad_one(const float4 e, uint32_t hi, floa
   // exp(-g / lamG): the reference divides, then negates nothing (-vm1/ARU1); x / 1.0f == x exactly
   const float arg = unitLam ? -g : __fdiv_rn(-g, lamG);
   (void)negInvLamG;
-  // __expf = ex2.approx(arg * log2 e): absolute error < 1e-6 on a result in (0, 1] (argument rounding |arg|*6e-8
-  // relative + 2 ulp of MUFU.EX2), two instructions instead of the ~14 of the range-checked expf
-  return __fsub_rn(*reinterpret_cast<const float*>(t1 + off), __expf(arg));
+  // expf as the host libm evaluates it (smd_expf_host, common.cuh): the combined volume equals the reference's bit for bit
+  return __fsub_rn(*reinterpret_cast<const float*>(t1 + off), smd_expf_host(arg));
 }
 
 // FUSED 0: gradient volume (calgradvm).  FUSED 1: censusGrad.
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1)
   const bool unitLam = lamG == 1.0f;
   if (FUSED) {
     for (int i = tid; i < (codeLen + 1) * 32; i += CG_THREADS) sT1[i] = 2.0f - tabCen[i >> 5];
-    oor = __fsub_rn(2.0f - tabCen[codeLen], expf(__fdiv_rn(-oorGrad, lamG)));
+    oor = __fsub_rn(2.0f - tabCen[codeLen], smd_expf_host(__fdiv_rn(-oorGrad, lamG)));
   }
   const char* t1 = reinterpret_cast<const char*>(sT1 + lane);
   const int nSeg = (W + CG_SEG - 1) / CG_SEG;

@@ -20,6 +20,7 @@ bool StereoMatching::Do_regionVote = true;
 bool StereoMatching::Do_properIpol = true;
 bool StereoMatching::Do_lastMedianBlur = true;
 bool StereoMatching::Do_subpixelEnhancement = false;
+bool StereoMatching::Do_WM = false;
 
 // reference defaults: stereoMatching.h:204-350
 StereoMatching::Parameters::Parameters(int maxDisp, int h, int w, int lamCen_, int lamG_, int M_, int lamc_, int ts_,
@@ -190,6 +191,11 @@ void StereoMatching::refine() {
   }
   if (Do_properIpol)
     for (int i = 0; i < param_.region_vote_nums; i++) properIpol(DP[0], I_c[0]);
+  if (Do_WM) {   // stereoMatching.cpp:1467-1471.  The mask is the labelling check's (LRConsistencyCheck); the check refine()
+    // itself runs, LRConsistencyCheck_normal, never creates it -- the reference would read an empty Mat here
+    CV_Assert(!LRC_Err_Mask.empty());
+    WM(DP[0], LRC_Err_Mask, I_c[0]);
+  }
   if (Do_subpixelEnhancement) {   // stereoMatching.cpp:1482-1490: SE from DP[0] and vm[0], then its 3x3 median; DP[0] untouched
     const size_t npix = (size_t)h_ * w_;
     if (!dp_dev_fresh_[0]) { upload(d_disp_[0], DP[0].data, npix * 2); dp_dev_fresh_[0] = true; }
@@ -803,6 +809,22 @@ void StereoMatching::LRConsistencyCheck(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMa
   errMask.create(h_, w_, CV_8UC1);
   download(errMask.data, m.p, (size_t)h_ * w_);
   if (member) dp_dev_fresh_[LOR] = false;
+}
+
+// WM (stereoMatching.cpp:7340-7393): 19x19 bilateral weighted median on the mask > 0 pixels, guidance img (3 x 8 bit).
+void StereoMatching::WM(Mat& disp, Mat& mask, Mat& img) {
+  CV_Assert(disp.type() == CV_16SC1 && mask.type() == CV_8UC1 && img.type() == CV_8UC3);
+  const size_t npix = (size_t)h_ * w_;
+  const bool member = &disp == &DP[0];
+  if (member && dp_dev_fresh_[0]) hostDP(0);
+  TmpDev a(ctx_, npix * 2), t(ctx_, npix * 2), m(ctx_, npix), g(ctx_, npix * 3);
+  upload(a.p, disp.data, npix * 2);
+  upload(m.p, mask.data, npix);
+  const uint8_t* d_img = d_bgr_[0];
+  if (&img != &I_c[0]) { upload(g.p, img.data, npix * 3); d_img = g.as<uint8_t>(); }
+  check(sm_wm(ctx_, a.as<int16_t>(), t.as<int16_t>(), m.as<uint8_t>(), d_img, h_, w_, d_, nullptr), "sm_wm");
+  download(disp.data, a.p, npix * 2);
+  if (member) dp_dev_fresh_[0] = false;
 }
 
 void StereoMatching::regionVote_my(cv::Mat& Dp, float rv_ratio, int rv_s) {

@@ -84,6 +84,7 @@ def lib():
         "orc_median3_i16": ([i16p, I, I, i16p], None),
         "orc_median3_f32": ([f32p, I, I, f32p], None),
         "orc_wm": ([i16p, u8p, u8p, I, I, I], I),
+        "orc_wm_lenient": ([i16p, u8p, u8p, I, I, I, i32p], I),
         "orc_solve_all_1level": ([f32p, C.c_long, F], None),
         "orc_cal_err": ([i16p, f32p, u8p, I, I, I, f32p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")], None),
         "orc_pyr_down_u8": ([u8p, I, I, I, u8p], None),
@@ -346,6 +347,15 @@ def wm(disp, mask, bgr, D):
     if n < 0:
         raise ValueError("WM: a label outside [0, D) inside a window: undefined in the reference (stereoMatching.cpp:7371)")
     return out
+
+
+def wm_lenient(disp, mask, bgr, D):
+    """WM with the defined extension of sm_wm for labels outside [0, D): (map, number of such window neighbours)."""
+    out = np.ascontiguousarray(disp, np.int16).copy()
+    H, W = out.shape
+    bad = np.zeros(1, np.int32)
+    lib().orc_wm_lenient(out, np.ascontiguousarray(mask, np.uint8), np.ascontiguousarray(bgr, np.uint8), H, W, D, bad)
+    return out, int(bad[0])
 
 
 def median3_f32(dp):

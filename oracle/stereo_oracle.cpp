@@ -709,7 +709,7 @@ void orc_median3_i16(const i16* src, int H, int W, i16* dst) {
 // reads the ORIGINAL padded copy of the map, the result goes to the map.  DEFINED ONLY when every label inside the
 // windows is in [0, D): the reference indexes dispHist[q] unchecked (:7371); this restatement then restores the map and
 // returns -1.  Otherwise returns the number of pixels rewritten.
-int orc_wm(short* disp, const unsigned char* mask, const unsigned char* bgr, int H, int W, int D) {
+static int wm_impl(short* disp, const unsigned char* mask, const unsigned char* bgr, int H, int W, int D, bool lenient, int* numInvalid) {
   const int R = 9;
   auto refl = [](int p, int n) { if (n == 1) return 0; while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p; return p; };
   std::vector<short> src(disp, disp + (long)H * W);
@@ -724,13 +724,15 @@ int orc_wm(short* disp, const unsigned char* mask, const unsigned char* bgr, int
         for (int du = -R; du <= R; du++) {
           const long j = (long)refl(v + dv, H) * W + refl(u + du, W);
           const short q = src[j];
-          if (q < 0 || q >= D) { std::memcpy(disp, src.data(), sizeof(short) * H * W); return -1; }
+          const bool bad = q < 0 || q >= D;
+          if (bad && !lenient) { std::memcpy(disp, src.data(), sizeof(short) * H * W); return -1; }
+          if (bad && numInvalid) ++*numInvalid;
           const unsigned char* iq = bgr + j * 3;
           int c2 = 0;
           for (int c = 0; c < 3; c++) c2 += ((int)ip[c] - (int)iq[c]) * ((int)ip[c] - (int)iq[c]);
           const float colDis = (float)c2, spaDis = (float)(dv * dv + du * du);
           const float wgt = std::exp(-colDis / (25.f * 25.f) - spaDis / (9.f * 9.f));
-          hist[q] += wgt;
+          if (!bad) hist[q] += wgt;   // lenient: the weight still enters the total, as in the reference, but casts no vote
           wsum += wgt;
         }
       const float half = wsum / 2;
@@ -741,6 +743,15 @@ int orc_wm(short* disp, const unsigned char* mask, const unsigned char* bgr, int
       }
     }
   return num;
+}
+int orc_wm(short* disp, const unsigned char* mask, const unsigned char* bgr, int H, int W, int D) {
+  return wm_impl(disp, mask, bgr, H, W, D, false, nullptr);
+}
+// The defined extension the CUDA entry point sm_wm implements for labels outside [0, D) (undefined in the reference):
+// such a neighbour adds to the total weight but to no bin.  *numInvalid = how many were seen.
+int orc_wm_lenient(short* disp, const unsigned char* mask, const unsigned char* bgr, int H, int W, int D, int* numInvalid) {
+  *numInvalid = 0;
+  return wm_impl(disp, mask, bgr, H, W, D, true, numInvalid);
 }
 
 // cv::medianBlur(CV_32F, ksize 3) on the sub-pixel map (stereoMatching.cpp:1490): same window, replicated border

@@ -66,13 +66,17 @@ def test_cost_volumes_bit_exact(ctx, shape, LOR):
     assert _bits_equal(ctx.cost_ad(bL, bR, D, LOR).cpu().numpy(), ad)
 
 
-def test_combine_exp_within_1e4(ctx):
+def test_combine_exp_bit_exact(ctx):
+    """gen_vm_from2vm_exp on two materialised volumes: expf as the host libm evaluates it (smd_expf_host) -> identical bits."""
     rng = np.random.default_rng(4)
-    a = (rng.random(5000) * 255).astype(np.float32)
-    b = rng.integers(0, 72, 5000).astype(np.float32)
+    a = (rng.random(200000) * 255).astype(np.float32)
+    b = rng.integers(0, 72, 200000).astype(np.float32)
+    a[:7] = [0.0, 1e-30, 1000.0, 3e4, -2.5, -900.0, 1e38]        # underflow, overflow (negative cost), huge
     got = ctx.combine_exp(ctx.dev(a), ctx.dev(b)).cpu().numpy()
     ref = po.combine_exp(a, b)
-    assert np.all(np.abs(got - ref) <= 1e-4 * np.abs(ref))   # device expf: 1e-4 relative (north_star)
+    assert _bits_equal(got, ref)
+    for l0, l1 in ((13.0, 1.0), (0.7, 250.0)):
+        assert _bits_equal(ctx.combine_exp(ctx.dev(a), ctx.dev(b), l0, l1).cpu().numpy(), po.combine_exp(a, b, l0, l1))
 
 
 # ---------------------------------------------------------------- arms / CBCA
@@ -653,3 +657,43 @@ def test_lrc_label_right_view_matches_reference_golden_and_oracle(ctx, golden_di
         m0, m1 = ctx.lrc_label_lor(a, b, D, 0, md)
         want, wm = po.lrc_label(d1, d2, D, md)
         assert np.array_equal(a.cpu().numpy(), want) and np.array_equal(m0.cpu().numpy(), wm) and int(m1.max()) == 0
+
+
+# ---------------------------------------------------------------- WM (VERDICT r01 missing #2)
+@pytest.mark.timeout(300)
+def test_wm_matches_reference_golden(ctx, golden_dir):
+    """sm_wm against the outputs of the reference's OWN WM (tests/golden/wm_ref.npz): identical labels -- the weights come
+    from expf as the host libm computes it (smd_expf_host) and every float sum keeps the reference's order."""
+    import os
+    g = np.load(os.path.join(golden_dir, "wm_ref.npz"))
+    n = 0
+    for k in g.files:
+        if not k.endswith("_out"):
+            continue
+        tag = k.split("_")[0]
+        disp, mask = g[k[:-4] + "_in"], g[k[:-4] + "_mask"]
+        got, bad = ctx.wm(ctx.dev(disp.copy()), ctx.dev(mask), ctx.dev(g[tag + "_bgr"]), int(g[tag + "_D"]))
+        assert np.array_equal(got.cpu().numpy(), g[k]), k
+        assert bad == 0
+        n += 1
+    assert n == 9
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("shape", [(1, 1, 4), (3, 40, 9), (40, 3, 70), (96, 128, 32), (120, 160, 300)])
+def test_wm_matches_oracle(ctx, shape):
+    H, W, D = shape
+    rng = np.random.default_rng(H * 7 + W)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    bgr[:, : W // 2] //= 8                                   # flat half: colour weights near 1
+    disp = np.clip((np.arange(W)[None, :] * (D - 1) // max(W - 1, 1)) + rng.integers(-1, 2, (H, W)), 0, D - 1).astype(np.int16)
+    disp[rng.random((H, W)) < 0.1] = rng.integers(0, D)
+    mask = (rng.random((H, W)) < 0.35).astype(np.uint8) * 255
+    got, bad = ctx.wm(ctx.dev(disp.copy()), ctx.dev(mask), ctx.dev(bgr), D)
+    assert np.array_equal(got.cpu().numpy(), po.wm(disp, mask, bgr, D)) and bad == 0
+    # labels outside [0, D) (DISP_OCC, -1 ...): undefined in the reference; sm_wm's defined extension = the oracle's lenient form
+    disp2 = disp.copy()
+    disp2[rng.random((H, W)) < 0.2] = -32
+    got, bad = ctx.wm(ctx.dev(disp2.copy()), ctx.dev(mask), ctx.dev(bgr), D)
+    want, wbad = po.wm_lenient(disp2, mask, bgr, D)
+    assert np.array_equal(got.cpu().numpy(), want) and bad == wbad
