@@ -82,6 +82,19 @@ typedef struct sm_params {
   int pyramidLevels;        /* PY_LEV of main_.cpp:132 (1 there).  > 1 with crossScaleLambda >= 0: cost + aggregation run
                              * on every level of the pyrDown pyramid (maxDisp/2+1, arm lengths / 2 per level,
                              * main_.cpp:134-151) and SolveAll blends them into level 0 before SGM */
+  /* vmTop (stereoMatching.h:182-188, 320-326; dispOptimize, stereoMatching.cpp:1111-1121): instead of the plain WTA the
+   * map comes from the vmTop_Num best candidates per pixel (selectTopCostFromVolumn) through genDispFromTopCostVm2 */
+  int Do_vmTop;             /* 0   :320 */
+  int vmTop_method;         /* 0   :321 */
+  int vmTop_Num;            /* M of the constructor (2 in main_.cpp:62), <= 16   :322 */
+  float vmTop_thres;        /* lamc * 0.01 (1.09 in main_.cpp:63)   :323 */
+  int vmTop_ts;             /* Parameters::ts (10 in main_.cpp:64): disp_DifThres of genDispFromTopCostVm2 */
+  int vmTop_hasCir2;        /* 1   :325 */
+  int vmTop_cir3_doColorLimit; /* 0 :326 */
+  int keep_right_volume;    /* sm_pipeline only.  0 (default): the last sgm path of the right view feeds gen_dispFromVm
+                             * directly and its path sum is not stored -- nothing reads vm[1] after dispOptimize's WTA
+                             * (refine() works on DP[] and vm[0]); sm_pipeline_buffer(1) then holds the sum WITHOUT the last
+                             * path.  1: vm[1] = the finished sum, as the reference leaves it.  Disparity maps are identical. */
 } sm_params;
 
 void sm_params_default(sm_params* p, int maxDisp);
@@ -266,6 +279,20 @@ int sm_wta(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int16_t* d_disp
  * entries the reference leaves unwritten are 0.  d_vol is not modified. */
 int sm_select_top_cost(sm_ctx* ctx, const float* d_vol, int H, int W, int D, int num,
                        float thres, float* d_top);
+
+/* vmTop, second half (param_.Do_vmTop, stereoMatching.cpp:1111-1121): the disparity map from the candidate lists of
+ * sm_select_top_cost.  d_top = float [H][W][num+1][2], num <= 16.  Pixels whose candidate count is < 1 keep what
+ * d_disp holds on entry, as in the reference.
+ * sm_disp_from_top  = genDispFromTopCostVm  (stereoMatching.h:2466-2545): own + left / right neighbours' candidates
+ *   vote (count, then summed cost; the reference's `dNum = dispNum && cost_ < cost` assignment is reproduced).
+ * sm_disp_from_top2 = genDispFromTopCostVm2 (stereoMatching.cpp:1514-1886), method = param_.vmTop_method:
+ *   0: the author's heuristic over the 8-neighbourhood (ts = param_.ts, hasCir2 = vmTop_hasCir2, colorLimit =
+ *      vmTop_cir3_doColorLimit); its raster-order dependency (left / up / up-left / up-right results) is honoured;
+ *   1, 2: row scans against the previous pixel's result.  d_bgr = I_c[0] (methods 0 with colorLimit, and 2).
+ * Bit-exact (same float accumulation order per disparity). */
+int sm_disp_from_top(sm_ctx* ctx, const float* d_top, int H, int W, int num, int16_t* d_disp);
+int sm_disp_from_top2(sm_ctx* ctx, const float* d_top, const uint8_t* d_bgr, int H, int W, int num, int method, int ts,
+                      int hasCir2, int colorLimit, int16_t* d_disp);
 
 /* subpixelEnhancement (stereoMatching.cpp:6138-6166; off by default,
  * Do_subpixelEnhancement, stereoMatching.h:79): for 0 < disp < D-1 the parabola

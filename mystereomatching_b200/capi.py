@@ -32,6 +32,9 @@ class SmParams(C.Structure):
         ("crossScaleLambda", C.c_float), ("sgm_grouped", C.c_int),
         ("costcalculation", C.c_int), ("cg_lamCen", C.c_float), ("cg_lamG", C.c_float), ("gradTrunc", C.c_float),
         ("pyramidLevels", C.c_int),
+        ("Do_vmTop", C.c_int), ("vmTop_method", C.c_int), ("vmTop_Num", C.c_int), ("vmTop_thres", C.c_float),
+        ("vmTop_ts", C.c_int), ("vmTop_hasCir2", C.c_int), ("vmTop_cir3_doColorLimit", C.c_int),
+        ("keep_right_volume", C.c_int),
     ]
 
 
@@ -99,6 +102,8 @@ SIGNATURES = {
     "sm_wta_co": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
     "sm_select_top_cost": ([_P, _P, _I, _I, _I, _I, _F, _P], _I),
     "sm_subpixel_enhancement": ([_P, _P, _P, _I, _I, _I, _P], _I),
+    "sm_disp_from_top": ([_P, _P, _I, _I, _I, _P], _I),
+    "sm_disp_from_top2": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_lrc": ([_P, _P, _P, _I, _I, _F], _I),
     "sm_lrc_label": ([_P, _P, _P, _I, _I, _I, _F, _I, _I, _P], _I),
     "sm_lrc_label_lor": ([_P, _P, _P, _I, _I, _I, _F, _I, _I, _I, _P, _P], _I),
@@ -397,6 +402,17 @@ class Ctx:
         H, W, D = vol.shape
         out = self.empty((H, W, num + 1, 2), self.torch.float32)
         check(self.L.sm_select_top_cost(self.h, _ptr(vol), H, W, D, num, thres, _ptr(out)))
+        return out
+
+    def disp_from_top(self, top, bgr=None, version=2, method=0, ts=10, has_cir2=True, color_limit=False, init=None):
+        """genDispFromTopCostVm (version 1) / genDispFromTopCostVm2 (version 2) on a [H][W][num+1][2] candidate tensor."""
+        H, W, n1, _ = top.shape
+        out = self.torch.zeros((H, W), dtype=self.torch.int16, device=top.device) if init is None else init.clone()
+        if version == 1:
+            check(self.L.sm_disp_from_top(self.h, _ptr(top), H, W, n1 - 1, _ptr(out)))
+        else:
+            check(self.L.sm_disp_from_top2(self.h, _ptr(top), _ptr(bgr), H, W, n1 - 1, method, ts, int(has_cir2),
+                                           int(color_limit), _ptr(out)))
         return out
 
     def wta_co(self, vol, scale=16):

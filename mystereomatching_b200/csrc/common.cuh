@@ -113,7 +113,8 @@ int smi_arms_packed(sm_ctx* ctx, const uint32_t* d_pix, int H, int W, int L, int
 int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D);
 int smi_sgm_path_packed(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                         int corDifThres, int reduCoeffi1, int mode, float* d_out);
-// mode 2: accumulate and write the WTA of the finished sum into d_disp (last path of a view)
+// mode 2: accumulate and write the WTA of the finished sum into d_disp (last path of a view); mode 3: the WTA alone,
+// the finished sum is not stored
 int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                          int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp);
 
@@ -122,13 +123,13 @@ int smi_sgm_group2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const
                    int corDifThres, int reduCoeffi1, float* const* d_sum);
 int smi_sgm8_grouped2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int corDifThres,
                       int reduCoeffi1, float* const* d_sum, int16_t* const* d_disp, cudaEvent_t ev_after_sweeps = nullptr,
-                      bool* used_sweeps = nullptr);
+                      bool* used_sweeps = nullptr, const bool* keep_sum = nullptr);
 int smi_sgm_group(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int up, int mode,
                   int corDifThres, int reduCoeffi1, float* d_sum);
 
 int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int corDifThres,
                      int reduCoeffi1, float* d_sum, int16_t* d_disp, cudaEvent_t ev_after_sweeps = nullptr,
-                     bool* used_sweeps = nullptr);
+                     bool* used_sweeps = nullptr, bool keep_sum = true);
 
 __device__ __forceinline__ int smd_absdiff_max3(uint32_t a, uint32_t b) {
   // max over the three low bytes of |a_c - b_c|
@@ -146,16 +147,18 @@ __device__ __forceinline__ int smd_absdiff_max3(uint32_t a, uint32_t b) {
 // +inf above 0x1.62e42ep6 like libm.  This is
 // what lets exp-weighted stages (WM, censusGrad's gradient term, gen_vm_from2vm_exp on materialised volumes) match the
 // CPU reference bit for bit instead of to 1e-4.
-__device__ __forceinline__ float smd_expf_host(float x) {
-  // T[i] = bits(2^(i/32)) - (i << 47)
-  static const unsigned long long T[32] = {
-      0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull,
-      0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull,
-      0x3feedea64c123422ull, 0x3feece086061892dull, 0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull,
-      0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
-      0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull, 0x3feee89f995ad3adull,
-      0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
-      0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+// T[i] = bits(2^(i/32)) - (i << 47).  In GLOBAL memory (an L1-cached 8-byte gather: the 32 entries span two
+// 128-byte lines), not __constant__: the index differs per lane, and divergent constant-bank reads serialise
+// (measured: the censusGrad cost stage 3.1 ms with the constant-bank table).
+static __device__ const unsigned long long smd_expf_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull,
+    0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull,
+    0x3feedea64c123422ull, 0x3feece086061892dull, 0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull,
+    0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull, 0x3feee89f995ad3adull,
+    0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
+    0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+__device__ __forceinline__ float smd_expf_host(float x, const unsigned long long* __restrict__ T = smd_expf_tab) {
   if (x < -0x1.9fe368p6f) return 0.0f;                      // underflow (also -inf)
   if (!(x <= 0x1.62e42ep6f)) return x > 0.f ? __int_as_float(0x7f800000) : x + x;   // overflow -> +inf; NaN -> NaN
   const double InvLn2N = 0x1.71547652b82fep+0 * 32.0, SHIFT = 0x1.8p+52;

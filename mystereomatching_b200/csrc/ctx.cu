@@ -55,6 +55,14 @@ extern "C" void sm_params_default(sm_params* p, int maxDisp) {
   p->cg_lamG = 1.f;
   p->gradTrunc = 500.f;
   p->pyramidLevels = 1;
+  p->Do_vmTop = 0;
+  p->vmTop_method = 0;
+  p->vmTop_Num = 2;        // M = 2, lamc = 109, ts = 10 in main_.cpp:62-64
+  p->vmTop_thres = 1.09f;
+  p->vmTop_ts = 10;
+  p->vmTop_hasCir2 = 1;
+  p->vmTop_cir3_doColorLimit = 0;
+  p->keep_right_volume = 0;
 }
 
 extern "C" int sm_ctx_create(sm_ctx** out, int device, void* stream) {

@@ -25,6 +25,7 @@ struct sm_pipeline {
   float* grad[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // censusGrad: gx, gy per image
   double* nlwork = nullptr;
   int16_t *disp[2] = {nullptr, nullptr}, *dtmp = nullptr;
+  float* top = nullptr;      // vmTop candidate lists [H][W][vmTop_Num + 1][2] (Do_vmTop)
   uint8_t* h_in = nullptr;   // pinned staging: bgrL | bgrR | grayL | grayR
   int16_t* h_out = nullptr;  // pinned staging: dispL | dispR
   // small frames (a single-path SGM sweep is then a chain of H or W dependent steps on a few hundred warps, far from
@@ -61,6 +62,7 @@ extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
   if (pl->evFork) cudaEventDestroy(pl->evFork);
   if (pl->evJoin) cudaEventDestroy(pl->evJoin);
   cudaFree(pl->nlwork);
+  cudaFree(pl->top);
   cudaFree(pl->dtmp);
   if (pl->h_in) cudaFreeHost(pl->h_in);
   if (pl->h_out) cudaFreeHost(pl->h_out);
@@ -82,6 +84,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   SM_CHECK_ARG(p->costcalculation == 0 || (H >= 2 && W >= 2 && p->cg_lamCen > 0.f && p->cg_lamG > 0.f));
   SM_CHECK_ARG(p->pyramidLevels >= 1 && p->pyramidLevels <= SM_MAX_PYRAMID);
   SM_CHECK_ARG(p->cbca_crossL_out >= 0 && p->cbca_crossL_out <= 255);
+  SM_CHECK_ARG(!p->Do_vmTop || (p->vmTop_Num >= 1 && p->vmTop_Num <= 16 && p->vmTop_method >= 0 && p->vmTop_method <= 2));
   SM_CUDA(cudaSetDevice(ctx->device));
   sm_pipeline* pl = new sm_pipeline();
   pl->ctx = ctx; pl->H = H; pl->W = W; pl->D = p->numDisparities; pl->p = *p;
@@ -111,6 +114,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
       rc = SM_ERR_CUDA;
   }
   if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->dtmp, npix * 2);
+  if (rc == SM_OK && p->Do_vmTop) rc = pl_alloc(ctx, (void**)&pl->top, npix * (size_t)(p->vmTop_Num + 1) * 2 * sizeof(float));
   if (rc == SM_OK && p->aggregation == 2) rc = pl_alloc(ctx, (void**)&pl->nlwork, npix * (size_t)(pl->D + 1) * sizeof(double));
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_in, npix * 8) != cudaSuccess) rc = SM_ERR_NOMEM;
   if (rc == SM_OK && cudaMallocHost((void**)&pl->h_out, npix * 4) != cudaSuccess) rc = SM_ERR_NOMEM;
@@ -304,6 +308,10 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
   // ---- dispOptimize: sgm (stereoMatching.cpp:1051-1089) then WTA (:1108-1128)
   if (P.sgm_paths > 0) {
     bool done = false;
+    // vm[1]'s finished path sum has no reader after the WTA (the refinement works on DP[] and on vm[0]); unless the caller
+    // asks for it (keep_right_volume, vmTop) the last path of view 1 does the WTA without storing the sum: one volume
+    // write less per frame
+    const bool keep[2] = {true, P.keep_right_volume != 0 || P.Do_vmTop != 0};
     pl->sweeps[0] = pl->sweeps[1] = false;
     if (P.sgm_paths == 8 && P.sgm_grouped && views == 2 && pl->vol[3]) {
       // both views per sweep launch (two CTAs per SM); falls through to one view at a time if the shape does not fit
@@ -313,7 +321,7 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
       int16_t* disps[2] = {pl->disp[0], pl->disp[1]};
       if (pl->timing) SM_CUDA(cudaEventRecord(pl->evs[0][0], c->stream));
       const int rc = smi_sgm8_grouped2(c, vols, pixs, H, W, D, P.sgm_corDifThres, P.sgm_reduCoeffi1, sums, disps,
-                                       pl->timing ? pl->evs[0][1] : nullptr, &pl->sweeps[0]);
+                                       pl->timing ? pl->evs[0][1] : nullptr, &pl->sweeps[0], keep);
       if (rc == SM_OK) {
         for (int i = 0; i < 2; i++) {   // vm[i] <- path sum; the old cost volumes become the scratch
           float* t = pl->vol[i];
@@ -334,7 +342,7 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
       for (int i = 0; i < 2 && rc2 == SM_OK; i++) {
         c->stream = i == 0 ? main_stream : pl->stream2;
         for (int k = 0; k < P.sgm_paths && rc2 == SM_OK; k++) {
-          const int mode = k == 0 ? 0 : (k == P.sgm_paths - 1 ? 2 : 1);
+          const int mode = k == 0 ? 0 : (k == P.sgm_paths - 1 ? (keep[i] ? 2 : 3) : 1);
           rc2 = smi_sgm_path_packed2(c, pl->vol[i], pl->pix[i], H, W, D, k, P.sgm_corDifThres, P.sgm_reduCoeffi1, mode,
                                      pl->vol[2 + i], pl->disp[i]);
         }
@@ -355,11 +363,11 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
       if (P.sgm_paths == 8 && P.sgm_grouped) {
         if (pl->timing) SM_CUDA(cudaEventRecord(pl->evs[i][0], c->stream));
         SM_TRY(smi_sgm8_grouped(c, pl->vol[i], pl->pix[i], H, W, D, P.sgm_corDifThres, P.sgm_reduCoeffi1, pl->vol[2],
-                                pl->disp[i], pl->timing ? pl->evs[i][1] : nullptr, &pl->sweeps[i]));
+                                pl->disp[i], pl->timing ? pl->evs[i][1] : nullptr, &pl->sweeps[i], keep[i]));
       } else
       for (int k = 0; k < P.sgm_paths; k++) {
         // the last path also does gen_dispFromVm on the finished sum (saves one read of the volume)
-        const int mode = k == 0 ? 0 : (k == P.sgm_paths - 1 ? 2 : 1);
+        const int mode = k == 0 ? 0 : (k == P.sgm_paths - 1 ? (keep[i] ? 2 : 3) : 1);
         SM_TRY(smi_sgm_path_packed2(c, pl->vol[i], pl->pix[i], H, W, D, k, P.sgm_corDifThres, P.sgm_reduCoeffi1, mode,
                                     pl->vol[2], pl->disp[i]));
       }
@@ -369,7 +377,15 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
     }
   }
   PL_MARK(5);
-  if (P.sgm_paths < 2)   // otherwise the WTA was fused into the last SGM path
+  if (P.Do_vmTop) {
+    // stereoMatching.cpp:1111-1121: candidates of a clone of vm[i] (sm_select_top_cost leaves the volume alone), then the
+    // author's selection; the guidance image is I_c[0] for both views, as in the reference
+    for (int i = 0; i < views; i++) {
+      SM_TRY(sm_select_top_cost(c, pl->vol[i], H, W, D, P.vmTop_Num, P.vmTop_thres, pl->top));
+      SM_TRY(sm_disp_from_top2(c, pl->top, pl->bgr[0], H, W, P.vmTop_Num, P.vmTop_method, P.vmTop_ts, P.vmTop_hasCir2,
+                               P.vmTop_cir3_doColorLimit, pl->disp[i]));
+    }
+  } else if (P.sgm_paths < 2)   // otherwise the WTA was fused into the last SGM path
     for (int i = 0; i < views; i++) SM_TRY(sm_wta(c, pl->vol[i], H, W, D, pl->disp[i]));
   PL_MARK(6);
   // ---- refine (stereoMatching.cpp:1364-1506)

@@ -28,6 +28,7 @@
 #define SGM_NSTG 12   // staged variant: pixels in flight per warp (cp.async), one extra slot so a refill never
                       // targets the slot being read
 
+// MODE 3 = MODE 2 without the store of the finished sum (the pipeline's right view: nothing reads vm[1] after the WTA).
 // MODE 0: out = Lr.  MODE 1: out += Lr (path sum).  MODE 2: out += Lr and the final WTA of gen_dispFromVm
 // (stereoMatching.cpp:3928-3967: first minimum, -1 if nothing is below FLT_MAX) fused into the last path, which
 // saves the separate read of the summed volume.
@@ -169,7 +170,7 @@ __device__ __forceinline__ void sgm_step(bool first, const float (&c)[VPL], floa
 #pragma unroll
     for (int j = 0; j < VPL; j++) s[j] = lr[j];
   }
-  if (MODE == 2) {
+  if (MODE >= 2) {
     // gen_dispFromVm on the finished sum: strict '>' scan in increasing d -> the lowest d among the minima
     float bm = FLT_MAX;
     int bd = 0x7fffffff;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(SGM_WARPS * 32)
           xpf[i] = pix[q];
         }
         sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, p);
-        store_run<VPL, VEC>(out + p * D, d0, D, s);
+        if (MODE != 3) store_run<VPL, VEC>(out + p * D, d0, D, s);
         p += pstep;
       }
     }
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(32)
     sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, pc);
 #pragma unroll
     for (int k = 0; k < VPL / 4; k++)
-      if (k < nq) *reinterpret_cast<float4*>(out + pc * D + d0 + k * 4) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+      if (MODE != 3 && k < nq) *reinterpret_cast<float4*>(out + pc * D + d0 + k * 4) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
     pc += pstep;
     if (++rd == NS) rd = 0;
     if (++wr == NS) wr = 0;
@@ -389,7 +390,8 @@ __global__ void __launch_bounds__(32)
     const uint32_t x = sgm_lds4(xOff + rd);
     issue();
     sgm_step<VPL, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, redu, lane, disp, pc);
-    if (PB == 16) {
+    if (MODE == 3) {
+    } else if (PB == 16) {
 #pragma unroll
       for (int k = 0; k < NQ; k++)
         if (d0 + 4 * k < D)
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(32)
       sgm_step<VPL, MODE>(k == 0 && i == 0, c[i], s[i], prev, minC, x[i], xprev, d0, D, corDifThres, redu, lane, disp, p);
 #pragma unroll
       for (int q = 0; q < VPL / 4; q++)
-        if (q < nq)
+        if (MODE != 3 && q < nq)
           *reinterpret_cast<float4*>(out + p * D + d0 + q * 4) = make_float4(s[i][4 * q], s[i][4 * q + 1], s[i][4 * q + 2], s[i][4 * q + 3]);
     }
     // refill the stage: it was only read (generic proxy) and every lane has consumed what it read, so no proxy
@@ -522,8 +524,10 @@ static int launch_sgm(sm_ctx* ctx, const float* vol, const uint32_t* pix, float*
     SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 0>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu, disp);
   else if (mode == 1)
     SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 1>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu, disp);
-  else
+  else if (mode == 2)
     SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 2>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu, disp);
+  else
+    SM_LAUNCH(ctx, (k_sgm_path<VPL, PF, VEC, 3>), grid, SGM_WARPS * 32, 0, vol, pix, out, g, D, thr, redu, disp);
   return SM_OK;
 }
 
@@ -549,7 +553,8 @@ static int launch_sgm_t(sm_ctx* ctx, const float* vol, const uint32_t* pix, floa
                         int thr, float redu, int mode, int16_t* disp) {
   if (mode == 0) return launch_sgm_t1<VPL, 0>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
   if (mode == 1) return launch_sgm_t1<VPL, 1>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
-  return launch_sgm_t1<VPL, 2>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  if (mode == 2) return launch_sgm_t1<VPL, 2>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  return launch_sgm_t1<VPL, 3>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
 }
 
 template <int VPL>
@@ -557,7 +562,8 @@ static int launch_sgm_h(sm_ctx* ctx, const float* vol, const uint32_t* pix, floa
                         int thr, float redu, int mode, int16_t* disp) {
   if (mode == 0) return launch_sgm_h1<VPL, 0>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
   if (mode == 1) return launch_sgm_h1<VPL, 1>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
-  return launch_sgm_h1<VPL, 2>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  if (mode == 2) return launch_sgm_h1<VPL, 2>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
+  return launch_sgm_h1<VPL, 3>(ctx, vol, pix, out, H, W, mu, D, thr, redu, disp);
 }
 
 template <int VPL, int MODE>
@@ -573,10 +579,11 @@ static int launch_sgm_s(sm_ctx* ctx, const float* vol, const uint32_t* pix, floa
                         float redu, int mode, int16_t* disp) {
   if (mode == 0) return launch_sgm_s1<VPL, 0>(ctx, vol, pix, out, g, D, thr, redu, disp);
   if (mode == 1) return launch_sgm_s1<VPL, 1>(ctx, vol, pix, out, g, D, thr, redu, disp);
-  return launch_sgm_s1<VPL, 2>(ctx, vol, pix, out, g, D, thr, redu, disp);
+  if (mode == 2) return launch_sgm_s1<VPL, 2>(ctx, vol, pix, out, g, D, thr, redu, disp);
+  return launch_sgm_s1<VPL, 3>(ctx, vol, pix, out, g, D, thr, redu, disp);
 }
 
-// mode 0: d_out = Lr; 1: d_out += Lr; 2: d_out += Lr and d_disp = WTA of the finished sum
+// mode 0: d_out = Lr; 1: d_out += Lr; 2: d_out += Lr and d_disp = WTA of the finished sum; 3: the WTA alone (d_out is read, not written)
 int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                          int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp) {
   sgm_geom g;
@@ -649,13 +656,15 @@ extern "C" int sm_sgm_path(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr
 
 // 8 paths, row-wise groups first (see sgm_group.cu); d_disp (nullable): WTA of the finished sum fused into the last path
 int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int corDifThres,
-                     int reduCoeffi1, float* d_sum, int16_t* d_disp, cudaEvent_t ev_after_sweeps, bool* used_sweeps) {
+                     int reduCoeffi1, float* d_sum, int16_t* d_disp, cudaEvent_t ev_after_sweeps, bool* used_sweeps,
+                     bool keep_sum) {
+  const int last = d_disp ? (keep_sum ? 2 : 3) : 1;
   if (used_sweeps) *used_sweeps = false;
   int rc = smi_sgm_group(ctx, d_vol, d_pix, H, W, D, /*up*/1, /*mode*/0, corDifThres, reduCoeffi1, d_sum);
   if (rc == SM_ERR_UNSUPPORTED) {   // shape outside the grouped kernel: reference order, path by path
     for (int i = 0; i < 8; i++)
       SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, i, corDifThres, reduCoeffi1,
-                                  i == 0 ? 0 : (i == 7 && d_disp ? 2 : 1), d_sum, d_disp));
+                                  i == 0 ? 0 : (i == 7 ? last : 1), d_sum, d_disp));
     return SM_OK;
   }
   SM_TRY(rc);
@@ -663,14 +672,15 @@ int smi_sgm8_grouped(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int
   if (used_sweeps) *used_sweeps = true;
   if (ev_after_sweeps) SM_CUDA(cudaEventRecord(ev_after_sweeps, ctx->stream));
   SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, 2, corDifThres, reduCoeffi1, 1, d_sum, nullptr));
-  SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, 3, corDifThres, reduCoeffi1, d_disp ? 2 : 1, d_sum, d_disp));
+  SM_TRY(smi_sgm_path_packed2(ctx, d_vol, d_pix, H, W, D, 3, corDifThres, reduCoeffi1, last, d_sum, d_disp));
   return SM_OK;
 }
 
 // Both views of a frame: the two row sweeps run the left and the right volume in one launch each (two CTAs per SM),
 // then the horizontal paths per view.  SM_ERR_UNSUPPORTED when the shape does not fit two CTAs per SM.
 int smi_sgm8_grouped2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int corDifThres,
-                      int reduCoeffi1, float* const* d_sum, int16_t* const* d_disp, cudaEvent_t ev_after_sweeps, bool* used_sweeps) {
+                      int reduCoeffi1, float* const* d_sum, int16_t* const* d_disp, cudaEvent_t ev_after_sweeps, bool* used_sweeps,
+                      const bool* keep_sum) {
   if (used_sweeps) *used_sweeps = false;
   int rc = smi_sgm_group2(ctx, d_vol, d_pix, H, W, D, /*up*/1, /*mode*/0, corDifThres, reduCoeffi1, d_sum);
   if (rc != SM_OK) return rc;
@@ -680,7 +690,8 @@ int smi_sgm8_grouped2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* co
   for (int i = 0; i < 2; i++) {
     int16_t* dd = d_disp ? d_disp[i] : nullptr;
     SM_TRY(smi_sgm_path_packed2(ctx, d_vol[i], d_pix[i], H, W, D, 2, corDifThres, reduCoeffi1, 1, d_sum[i], nullptr));
-    SM_TRY(smi_sgm_path_packed2(ctx, d_vol[i], d_pix[i], H, W, D, 3, corDifThres, reduCoeffi1, dd ? 2 : 1, d_sum[i], dd));
+    SM_TRY(smi_sgm_path_packed2(ctx, d_vol[i], d_pix[i], H, W, D, 3, corDifThres, reduCoeffi1,
+                                dd ? ((!keep_sum || keep_sum[i]) ? 2 : 3) : 1, d_sum[i], dd));
   }
   return SM_OK;
 }

@@ -47,6 +47,8 @@ StereoMatching::Parameters::Parameters(int maxDisp, int h, int w, int lamCen_, i
   cbca_double_win = false; cbca_armHV = 1; cbca_armTile = 0;
   region_vote_nums = 2; regVote_SThres = 20; regVote_hratioThres = 0.4f;
   Do_vmTop = false;
+  vmTop_method = 0; vmTop_Num = M_; vmTop_thres = lamc_ * 0.01f; vmTop_thres_dirNum = 8;
+  vmTop_hasCir2 = true; vmTop_cir3_doColorLimit = false;
   lamCen = lamCen_; lamG = lamG_; M = M_; lamc = lamc_; ts = ts_; disSc = disSc_;
   errCsvName = errCsvName_;
 }
@@ -173,8 +175,16 @@ void StereoMatching::dispOptimize() {
     for (int i = 0; i < num; i++) sgm(vm[i], i == 0);
   else if (!optimization.empty())
     throw cv::Exception("dispOptimize: optimization \"" + optimization + "\" is outside the hot path");
-  CV_Assert(!param_.Do_vmTop);
-  for (int i = 0; i < num; i++) gen_dispFromVm(vm[i], DP[i]);
+  if (param_.Do_vmTop) {   // stereoMatching.cpp:1111-1121
+    int sizeVmTop[] = {h_, w_, param_.vmTop_Num + 1, 2};
+    Mat topDisp(4, sizeVmTop, CV_32F);
+    for (int i = 0; i < num; i++) {
+      Mat vm_copy = hostVm(i).clone();
+      selectTopCostFromVolumn(vm_copy, topDisp, param_.vmTop_thres);
+      genDispFromTopCostVm2(topDisp, DP[i]);
+    }
+  } else
+    for (int i = 0; i < num; i++) gen_dispFromVm(vm[i], DP[i]);
 }
 
 void StereoMatching::refine() {
@@ -773,6 +783,50 @@ void StereoMatching::selectTopCostFromVolumn(Mat& vm_, Mat& topDisp, float thres
   for (size_t i = 0; i < (size_t)h_ * w_; i++, c += d_, o += (size_t)(num + 1) * 2)
     for (int k = 0; k < (int)o[2 * num]; k++) c[(int)o[2 * k]] = std::numeric_limits<float>::max();
   if (idx >= 0) vm_dev_fresh_[idx] = false;
+}
+
+// genDispFromTopCostVm (stereoMatching.h:2466-2545) / genDispFromTopCostVm2 (stereoMatching.cpp:1514-1886): the map from
+// the candidate lists; disp keeps its content where a pixel has no candidate, as in the reference.
+static void top_to_disp(StereoMatching* self, sm_ctx* ctx, Mat& topDisp, Mat& disp, int version, const uint8_t* d_bgr, int h,
+                        int w, const StereoMatching::Parameters& P) {
+  CV_Assert(topDisp.dims == 4 && topDisp.type() == CV_32F);
+  CV_Assert(topDisp.size[0] == h && topDisp.size[1] == w && topDisp.size[2] >= 2 && topDisp.size[3] == 2);
+  CV_Assert(disp.type() == CV_16SC1 && disp.rows == h && disp.cols == w);
+  (void)self;
+  const int num = topDisp.size[2] - 1;
+  const size_t tb = (size_t)h * w * (num + 1) * 2 * 4, pb = (size_t)h * w * 2;
+  void *t = nullptr, *d = nullptr;
+  auto chk = [&](int rc, const char* what) {
+    if (rc != SM_OK) {
+      if (t) sm_dev_free(ctx, t);
+      if (d) sm_dev_free(ctx, d);
+      throw cv::Exception(std::string(what) + ": " + sm_last_error());
+    }
+  };
+  chk(sm_dev_alloc(ctx, &t, tb), "sm_dev_alloc");
+  chk(sm_dev_alloc(ctx, &d, pb), "sm_dev_alloc");
+  chk(sm_memcpy_h2d(ctx, t, topDisp.data, tb), "sm_memcpy_h2d");
+  chk(sm_memcpy_h2d(ctx, d, disp.data, pb), "sm_memcpy_h2d");
+  if (version == 1) chk(sm_disp_from_top(ctx, (const float*)t, h, w, num, (int16_t*)d), "sm_disp_from_top");
+  else
+    chk(sm_disp_from_top2(ctx, (const float*)t, d_bgr, h, w, num, P.vmTop_method, P.ts, P.vmTop_hasCir2 ? 1 : 0,
+                          P.vmTop_cir3_doColorLimit ? 1 : 0, (int16_t*)d), "sm_disp_from_top2");
+  chk(sm_memcpy_d2h(ctx, disp.data, d, pb), "sm_memcpy_d2h");
+  chk(sm_ctx_sync(ctx), "sm_ctx_sync");
+  sm_dev_free(ctx, t);
+  sm_dev_free(ctx, d);
+}
+void StereoMatching::genDispFromTopCostVm(Mat& topDisp, Mat& disp) {
+  const int i = &disp == &DP[0] ? 0 : (&disp == &DP[1] ? 1 : -1);
+  if (i >= 0 && dp_dev_fresh_[i]) hostDP(i);
+  top_to_disp(this, ctx_, topDisp, disp, 1, d_bgr_[0], h_, w_, param_);
+  if (i >= 0) dp_dev_fresh_[i] = false;
+}
+void StereoMatching::genDispFromTopCostVm2(Mat& topDisp, Mat& disp) {
+  const int i = &disp == &DP[0] ? 0 : (&disp == &DP[1] ? 1 : -1);
+  if (i >= 0 && dp_dev_fresh_[i]) hostDP(i);
+  top_to_disp(this, ctx_, topDisp, disp, 2, d_bgr_[0], h_, w_, param_);
+  if (i >= 0) dp_dev_fresh_[i] = false;
 }
 
 // ------------------------------------------------------------------ refinement

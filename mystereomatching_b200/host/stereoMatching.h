@@ -72,6 +72,10 @@ class StereoMatching {
     int regVote_SThres;
     float regVote_hratioThres;
     bool Do_vmTop;
+    int vmTop_method, vmTop_Num;       // stereoMatching.h:183-184 (0, M)
+    float vmTop_thres;                 // :185 (lamc * 0.01)
+    int vmTop_thres_dirNum;            // :186 (8; read by no live code)
+    bool vmTop_hasCir2, vmTop_cir3_doColorLimit;   // :187-188 (true, false)
     int lamCen, lamG, M, lamc, ts, disSc;
     std::string errCsvName;
 
@@ -146,6 +150,8 @@ class StereoMatching {
   // topDisp: 4-D CV_32F {h, w, num + 1, 2}; like the reference, the Mat handed in has its taken entries set to FLT_MAX
   void selectTopCostFromVolumn(Mat& vm, Mat& topDisp, float thres);                     // stereoMatching.h:2405-2461
   void subpixelEnhancement(Mat& disparity, Mat& floatDisp);                             // stereoMatching.cpp:6138-6166
+  void genDispFromTopCostVm(Mat& topDisp, Mat& disp);                                   // stereoMatching.h:2466-2545
+  void genDispFromTopCostVm2(Mat& topDisp, Mat& disp);                                  // stereoMatching.cpp:1514-1886
 
   // ---- refinement
   void LRConsistencyCheck(cv::Mat& D1, cv::Mat& D2, cv::Mat& errMask, int LOR = 0);         // :2284-2364

@@ -68,6 +68,8 @@ CPP_FUNCS = [
     # default-off refiner
     (r"^void StereoMatching::subpixelEnhancement\(", "subpixelEnhancement"),
     (r"^void StereoMatching::WM\(", "WM"),
+    # the sequential half of vmTop
+    (r"^void StereoMatching::genDispFromTopCostVm2\(", "genDispFromTopCostVm2"),
     # the gradient cost family: "censusGrad" is the selector main_.cpp:15 compiles in
     (r"^void StereoMatching::censusGrad\(", "censusGrad"),
     (r"^void StereoMatching::grad\(vector<Mat>& vm_grad, float Trunc\)", "grad"),
@@ -89,6 +91,7 @@ H_FUNCS = [
     (r"^\tstatic float min4\(", "min4"),
     (r"^\tvoid updateCost\(", "updateCost"),
     (r"^\tvoid selectTopCostFromVolumn\(", "selectTopCostFromVolumn"),
+    (r"^\tvoid genDispFromTopCostVm\(Mat& topDisp, Mat& disp\)", "genDispFromTopCostVm"),
 ]
 
 
@@ -177,7 +180,7 @@ def main():
             f.write(h_parts["Parameters"])
             f.write('#include "smref_class_decls.inc"\n')     # ours: declarations + data members
             for n in ("genCensusCode", "genCensusCode_NC_Sur", "gen_cenVM_XOR", "cal1DCost", "min4", "updateCost",
-                      "selectTopCostFromVolumn"):
+                      "selectTopCostFromVolumn", "genDispFromTopCostVm"):
                 f.write(h_parts[n])
             f.write("};\n")
             f.write('#include "smref_class_tail.inc"\n')      # ours: static member definitions, stubs

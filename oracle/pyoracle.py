@@ -75,6 +75,7 @@ def lib():
         "orc_wta": ([f32p, I, I, I, i16p], None),
         "orc_wta_co": ([f32p, I, I, I, I, i16p, i16p], None),
         "orc_select_top": ([f32p, I, I, I, I, F, f32p], None),
+        "orc_disp_from_top": ([f32p, u8p, I, I, I, I, I, I, I, I, i16p], None),
         "orc_subpixel": ([i16p, f32p, I, I, I, f32p], None),
         "orc_lrc_normal": ([i16p, i16p, I, I, F], None),
         "orc_lrc_label": ([i16p, i16p, I, I, I, F, I, I, u8p], None),
@@ -287,6 +288,16 @@ def select_top(vol, num, thres):
     H, W, D = vol.shape
     out = np.empty((H, W, num + 1, 2), np.float32)
     lib().orc_select_top(np.ascontiguousarray(vol, np.float32), H, W, D, num, thres, out)
+    return out
+
+
+def disp_from_top(top, bgr, version=2, method=0, ts=10, has_cir2=True, color_limit=False, init=None):
+    """genDispFromTopCostVm (version 1, stereoMatching.h:2466-2545) / genDispFromTopCostVm2 (version 2,
+    stereoMatching.cpp:1514-1886).  top: float [H][W][num+1][2]; init: the map's content on entry (zeros)."""
+    H, W, n1, _ = top.shape
+    out = np.zeros((H, W), np.int16) if init is None else np.ascontiguousarray(init, np.int16).copy()
+    lib().orc_disp_from_top(np.ascontiguousarray(top, np.float32), np.ascontiguousarray(bgr, np.uint8), H, W, n1 - 1, version,
+                            method, ts, int(has_cir2), int(color_limit), out)
     return out
 
 
@@ -544,6 +555,7 @@ def smref_lib():
         "smref_wta": ([P, I, i16p], None), "smref_wta_co": ([P, I, i16p, i16p], None),
         "smref_select_top": ([P, I, I, F, f32p], None),
         "smref_subpixel": ([P, i16p, f32p], None),
+        "smref_disp_from_top": ([P, f32p, I, I, I, I, I, I, i16p], None),
         "smref_wm": ([P, i16p, u8p], None),
         "smref_lrc_normal": ([P, i16p, i16p], None), "smref_lrc_label": ([P, i16p, i16p, I, P], None),
         "smref_lrc_new": ([P, i16p, i16p, u8p], None),
@@ -696,6 +708,13 @@ class SmRef:
         o = np.empty((self.H, self.W, num + 1, 2), np.float32)
         self.L.smref_select_top(self.h, view, num, thres, o)
         return o
+
+    def disp_from_top(self, top, version=2, method=0, ts=10, has_cir2=True, color_limit=False, init=None):
+        """The reference's own genDispFromTopCostVm (version 1) / genDispFromTopCostVm2 (version 2) on `top`."""
+        out = np.zeros((self.H, self.W), np.int16) if init is None else np.ascontiguousarray(init, np.int16).copy()
+        self.L.smref_disp_from_top(self.h, np.ascontiguousarray(top, np.float32), top.shape[2] - 1, version, method, ts,
+                                   int(has_cir2), int(color_limit), out)
+        return out
 
     def subpixel(self, disp):
         """The reference's own subpixelEnhancement on the given disparity map and vm[0]."""

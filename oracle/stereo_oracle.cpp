@@ -475,6 +475,179 @@ void orc_sgm(float* vol, const u8* bgr, int H, int W, int D, int P, int corDifTh
 // WTA: gen_dispFromVm (stereoMatching.cpp:3928-3967), ChooseSmall=true:
 // strict '>' so the lowest d wins ties; -1 when nothing beats FLT_MAX.
 // ---------------------------------------------------------------------------
+// vmTop, second half: the disparity of a pixel from its candidate list
+// topDisp[v][u][k] = {d, cost}, k < num, topDisp[v][u][num][0] = candidate count (selectTopCostFromVolumn).
+//
+// version 1 = genDispFromTopCostVm (stereoMatching.h:2466-2545): own candidates + those of the left / right
+//   neighbour vote per disparity (count, then summed cost); note the reference's `dNum = dispNum && cost_ < cost`
+//   (an assignment, :2531): the tie branch sets the running count to 1.  Reads topDisp only.
+// version 2 = genDispFromTopCostVm2 (stereoMatching.cpp:1514-1886), param_.vmTop_method 0 / 1 / 2.  Method 0:
+//   border pixels and single-candidate pixels take candidate 0; otherwise the candidates that have another candidate
+//   within `ts` disparities (vmTop_hasCir2) are kept, keyed by cost in a std::map (equal cost keys: first insertion
+//   wins); none kept -> the candidate nearest to one of the already written neighbours (left, up, up-left, up-right:
+//   the raster-order dependency); else the kept candidates + the 8 neighbours' candidates of the same disparity vote
+//   (count, then summed cost, then lowest disparity).  Methods 1 / 2: row scans against the previous pixel's result.
+// std::map<int, .> iteration = ascending disparity; std::map<float, int> iteration = ascending cost.
+// ---------------------------------------------------------------------------
+namespace {
+struct TopView {
+  const float* top; int H, W, num;
+  const float* at(int v, int u, int k) const { return top + (((long)v * W + u) * (num + 1) + k) * 2; }
+  int count(int v, int u) const { return (int)at(v, u, num)[0]; }
+};
+struct Vote { int d; int n; float c; };
+static void vote_add(std::vector<Vote>& vs, int d, float c, bool create) {
+  for (auto& x : vs) if (x.d == d) { x.n++; x.c += c; return; }
+  if (create) vs.push_back({d, 1, 0.f + c});   // map's operator[] value-initialises to 0, then += cost
+}
+}  // namespace
+
+void orc_disp_from_top(const float* top, const u8* bgr, int H, int W, int num, int version, int method, int ts,
+                       int hasCir2, int colorLimit, i16* disp) {
+  TopView T{top, H, W, num};
+  if (version == 1) {
+    for (int v = 0; v < H; v++)
+      for (int u = 0; u < W; u++) {
+        const float cntf = T.at(v, u, num)[0];
+        if (cntf == 1) { disp[(long)v * W + u] = (i16)T.at(v, u, 0)[0]; continue; }
+        if (!(cntf > 1)) continue;
+        std::vector<Vote> vs;
+        for (int i = 0; i < cntf; i++) vote_add(vs, (int)T.at(v, u, i)[0], T.at(v, u, i)[1], true);
+        for (int du = -1; du <= 1; du += 2) {
+          const int u_ = u + du;
+          if (u_ < 0 || u_ >= W) continue;
+          const int n_ = T.count(v, u_);
+          for (int k = 0; k < n_; k++) vote_add(vs, (int)T.at(v, u_, k)[0], T.at(v, u_, k)[1], false);
+        }
+        std::sort(vs.begin(), vs.end(), [](const Vote& a, const Vote& b) { return a.d < b.d; });
+        int best = -1, bestN = -1;
+        float bestC = std::numeric_limits<float>::max();
+        for (const auto& x : vs) {
+          int dNum = x.n;
+          bool take = dNum > bestN;
+          if (!take) { dNum = (bestN && x.c < bestC) ? 1 : 0; take = dNum != 0; }   // `dNum = dispNum && cost_ < cost`
+          if (take) { bestN = dNum; bestC = x.c; best = x.d; }
+        }
+        disp[(long)v * W + u] = (i16)best;
+      }
+    return;
+  }
+  if (method == 0) {
+    static const int NV[8] = {0, -1, 0, 1, -1, 1, -1, 1}, NU[8] = {-1, 0, 1, 0, -1, 1, 1, -1};
+    for (int v = 0; v < H; v++)
+      for (int u = 0; u < W; u++) {
+        i16& out = disp[(long)v * W + u];
+        if (u == 0 || v == 0) { out = (i16)T.at(v, u, 0)[0]; continue; }
+        const int n = T.count(v, u);
+        if (n == 1) { out = (i16)T.at(v, u, 0)[0]; continue; }
+        if (n < 1) continue;
+        // candidates kept, keyed by cost (std::map<float,int>::insert keeps the first entry of an equivalent key)
+        std::vector<std::pair<float, int>> kept;
+        auto insert = [&](float c, int d) {
+          for (auto& e : kept) if (!(e.first < c) && !(c < e.first)) return;
+          kept.push_back({c, d});
+        };
+        for (int i = 0; i < n; i++) {
+          const int d0 = (int)T.at(v, u, i)[0];
+          const float c0 = T.at(v, u, i)[1];
+          if (!hasCir2) { insert(c0, d0); continue; }
+          for (int j = i + 1; j < n; j++) {
+            const int d1 = (int)T.at(v, u, j)[0];
+            if (std::abs(d0 - d1) < ts) { insert(c0, d0); insert(T.at(v, u, j)[1], d1); }
+          }
+        }
+        if (kept.empty()) {
+          const int pre1 = disp[(long)v * W + u - 1], pre2 = disp[(long)(v - 1) * W + u], lt = disp[(long)(v - 1) * W + u - 1];
+          const int rt = u != W - 1 ? disp[(long)(v - 1) * W + u + 1] : 10000;
+          const int ref[4] = {pre1, pre2, rt, lt};
+          int small[4], pick[4];
+          for (int k = 0; k < 4; k++) { small[k] = std::numeric_limits<int>::max(); pick[k] = -1; }
+          for (int i = 0; i < n; i++) {
+            const int dd = (int)T.at(v, u, i)[0];
+            for (int k = 0; k < 4; k++) {
+              const int dif = std::abs(dd - ref[k]);
+              if (dif < small[k]) { small[k] = dif; pick[k] = dd; }
+            }
+          }
+          const int m = std::min(std::min(small[2], small[3]), std::min(small[0], small[1]));
+          int d = -1;
+          if (m == small[3]) d = pick[3];
+          else if (m == small[0]) d = pick[0];
+          else if (m == small[1]) d = pick[1];
+          else if (m == small[2]) d = pick[2];
+          out = m < 1000 ? (i16)d : (i16)T.at(v, u, 0)[0];
+        } else {
+          std::sort(kept.begin(), kept.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+          std::vector<Vote> vs;
+          for (auto& e : kept) vote_add(vs, e.second, e.first, true);
+          const u8* tar = bgr + ((long)v * W + u) * 3;
+          for (int k = 0; k < 8; k++) {
+            const int v_ = v + NV[k], u_ = u + NU[k];
+            if (v_ < 0 || v_ >= H || u_ < 0 || u_ >= W) continue;
+            if (colorLimit) {
+              const u8* nei = bgr + ((long)v_ * W + u_) * 3;
+              bool ok = true;
+              for (int c = 0; c < 3; c++) if (std::abs((int)tar[c] - (int)nei[c]) > 10) { ok = false; break; }
+              if (!ok) continue;
+            }
+            const int n_ = T.count(v_, u_);
+            for (int x = 0; x < n_; x++) vote_add(vs, (int)T.at(v_, u_, x)[0], T.at(v_, u_, x)[1], false);
+          }
+          std::sort(vs.begin(), vs.end(), [](const Vote& a, const Vote& b) { return a.d < b.d; });
+          int best = -1, bestN = -1;
+          float bestC = std::numeric_limits<float>::max();
+          for (const auto& x : vs)
+            if (x.n > bestN || (x.n == bestN && x.c < bestC)) { bestN = x.n; bestC = x.c; best = x.d; }
+          out = (i16)best;
+        }
+      }
+  } else if (method == 1) {
+    for (int v = 0; v < H; v++)
+      for (int u = 0; u < W; u++) {
+        i16& out = disp[(long)v * W + u];
+        const int n = T.count(v, u);
+        if (u == 0 || n == 1) { out = (i16)T.at(v, u, 0)[0]; continue; }
+        int dp = -1, best = 10000;
+        const i16 pre = disp[(long)v * W + u - 1];
+        for (int k = 0; k < n; k++) {
+          const int s_ = (int)std::fabs((float)pre - T.at(v, u, k)[0]);   // abs(short - float) -> float, then int
+          if (s_ < 2 && s_ < best) { best = s_; dp = (int)T.at(v, u, k)[0]; }
+        }
+        out = dp == -1 ? (i16)T.at(v, u, 0)[0] : (i16)dp;
+      }
+  } else if (method == 2) {
+    for (int v = 0; v < H; v++)
+      for (int u = 0; u < W; u++) {
+        i16& out = disp[(long)v * W + u];
+        const int n = T.count(v, u);
+        if (u == 0 || n == 1) { out = (i16)T.at(v, u, 0)[0]; continue; }
+        int bestPre = 1000000, bestAft = 1000000, d0 = -1, d1 = -1;
+        const int pre = disp[(long)v * W + u - 1];
+        for (int k = 0; k < n; k++) {
+          const int dif = (int)std::fabs(T.at(v, u, k)[0] - (float)pre);
+          if (dif < 2 && dif < bestPre) { bestPre = dif; d0 = (int)T.at(v, u, k)[0]; }
+        }
+        if (u < W - 1) {
+          const int aft = (int)T.at(v, u + 1, 0)[0];
+          for (int k = 0; k < n; k++) {
+            const int dif = (int)std::fabs(T.at(v, u, k)[0] - (float)aft);
+            if (dif < 2 && dif < bestAft) { bestAft = dif; d1 = (int)T.at(v, u, k)[0]; }
+          }
+        }
+        if (d0 != -1 && d1 == -1) out = (i16)d0;
+        else if (d0 == -1 && d1 != -1) out = (i16)d1;
+        else if (d0 == -1 && d1 == -1) out = (i16)T.at(v, u, 0)[0];
+        else {
+          int cpre = 0, caft = 0;
+          const u8* c = bgr + ((long)v * W + u) * 3;
+          for (int k = 0; k < 3; k++) { cpre += std::abs((int)c[k] - (int)c[k - 3]); caft += std::abs((int)c[k] - (int)c[k + 3]); }
+          out = cpre <= caft ? (i16)d0 : (i16)d1;
+        }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------
 void orc_wta(const float* vol, int H, int W, int D, i16* disp) {
   ORC_PAR_FOR
   for (long i = 0; i < (long)H * W; i++) {

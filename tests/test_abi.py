@@ -51,8 +51,8 @@ def test_params_default_and_struct_layout():
     assert p.DISP_OCC == -32 and p.DISP_MIS == -48 and p.crossScaleLambda < 0
     assert p.costcalculation == 0 and p.cg_lamCen == 13.0 and p.cg_lamG == 1.0 and p.gradTrunc == 500.0
     assert p.pyramidLevels == 1
-    # sizeof check: the header struct is 33 4-byte fields
-    assert ctypes.sizeof(capi.SmParams) == 33 * 4
+    # sizeof check: the header struct is 41 4-byte fields
+    assert ctypes.sizeof(capi.SmParams) == 41 * 4
 
 
 def test_no_cpu_fallback_without_device():

@@ -697,3 +697,113 @@ def test_wm_matches_oracle(ctx, shape):
     got, bad = ctx.wm(ctx.dev(disp2.copy()), ctx.dev(mask), ctx.dev(bgr), D)
     want, wbad = po.wm_lenient(disp2, mask, bgr, D)
     assert np.array_equal(got.cpu().numpy(), want) and bad == wbad
+
+
+# ---------------------------------------------------------------- vmTop, second half (VERDICT r01 missing #1)
+def _top_variants(g):
+    for k in g.files:
+        if k.startswith("top_") and "_out_" in k:
+            tag = k.split("_")[1]
+            f = k.split("_out_")[1].split("_")
+            yield k, tag, int(f[0][1:]), int(f[1][1:]), int(f[2][2:]), int(f[3][1:]), int(f[4][1:])
+
+
+@pytest.mark.timeout(300)
+def test_disp_from_top_cost_matches_reference_golden(ctx, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "r02_ref.npz"))     # outputs of the reference's own genDispFromTopCostVm{,2}
+    n = 0
+    for k, tag, ver, m, ts, c2, cl in _top_variants(g):
+        got = ctx.disp_from_top(ctx.dev(g[f"top_{tag}_in"]), ctx.dev(g[f"top_{tag}_bgr"]), ver, m, ts, c2, cl)
+        assert np.array_equal(got.cpu().numpy(), g[k]), k
+        n += 1
+    assert n == 56
+
+
+def _random_top(rng, H, W, D, num, spread):
+    """Candidate lists with distinct disparities per pixel, ascending costs on a coarse grid (many ties)."""
+    n = rng.integers(1, num + 1, (H, W))
+    base = rng.integers(0, D, (H, W, 1))
+    d = np.clip(base + rng.integers(-spread, spread + 1, (H, W, num)), 0, D - 1)
+    far = rng.random((H, W, num)) < 0.3
+    d = np.where(far, rng.integers(0, D, (H, W, num)), d)
+    for k in range(1, num):                      # make the disparities of a pixel distinct
+        for _ in range(4):
+            dup = (d[..., k:k + 1] == d[..., :k]).any(-1)
+            d[..., k] = np.where(dup, (d[..., k] + 1 + rng.integers(0, 3, (H, W))) % D, d[..., k])
+        dup = (d[..., k:k + 1] == d[..., :k]).any(-1)
+        n = np.where(dup & (n > k), k, n)         # still a duplicate: cut the list there
+    c = np.sort(np.round(rng.random((H, W, num)) * 8) / 8 + 1.0, axis=-1)
+    top = np.zeros((H, W, num + 1, 2), np.float32)
+    keep = np.arange(num)[None, None, :] < n[..., None]
+    top[..., :num, 0] = np.where(keep, d, 0)
+    top[..., :num, 1] = np.where(keep, c, 0)
+    top[..., num, 0] = n
+    return top
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("shape", [(97, 131, 64, 6, 2), (60, 333, 256, 2, 40), (200, 65, 32, 16, 1), (33, 1000, 128, 4, 60)])
+def test_disp_from_top_cost_matches_oracle(ctx, shape):
+    H, W, D, num, spread = shape
+    rng = np.random.default_rng(H + W)
+    top = _random_top(rng, H, W, D, num, spread)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    bgr[:, : W // 2] //= 32
+    dt, db = ctx.dev(top), ctx.dev(bgr)
+    for ver, m, ts, c2, cl in [(1, 0, 10, 1, 0), (2, 0, 10, 1, 0), (2, 0, 2, 1, 0), (2, 0, 10, 0, 0), (2, 0, 1, 1, 1), (2, 1, 10, 1, 0),
+                               (2, 2, 10, 1, 0)]:
+        got = ctx.disp_from_top(dt, db, ver, m, ts, c2, cl).cpu().numpy()
+        want = po.disp_from_top(top, bgr, ver, m, ts, c2, cl)
+        assert np.array_equal(got, want), (ver, m, ts, c2, cl, int((got != want).sum()))
+    # the raster-dependent case on nearly every pixel (ts = 0: no candidate ever has a partner), twice: same answer
+    a = ctx.disp_from_top(dt, db, 2, 0, 0, 1, 0).cpu().numpy()
+    assert np.array_equal(a, po.disp_from_top(top, bgr, 2, 0, 0, 1, 0))
+    assert np.array_equal(a, ctx.disp_from_top(dt, db, 2, 0, 0, 1, 0).cpu().numpy())
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_pipeline_with_vmtop_matches_oracle_chain(ctx, method):
+    """dispOptimize with param_.Do_vmTop (stereoMatching.cpp:1111-1121) inside sm_pipeline: the left map after the whole
+    refinement equals the oracle's stage functions composed the same way (M = 2, lamc = 109, ts = 10 as main_.cpp:62-64)."""
+    H, W, D = 60, 90, 24
+    p = _pair(H, W, D, "texture_warped", seed=17)
+    aL, aR = po.arms(p["bgrL"]), po.arms(p["bgrR"])
+    maps = []
+    for view, bgr in ((0, p["bgrL"]), (1, p["bgrR"])):
+        vol = po.adcensus_vol(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D, view)
+        vol = po.sgm(po.cbca(vol, aL, aR, 2, view), bgr, 4)
+        top = po.select_top(vol, 2, np.float32(1.09))
+        maps.append(po.disp_from_top(top, p["bgrL"], 2, method, 10, True, False))
+    d = po.lrc_normal(maps[0], maps[1], 0.0)
+    for _ in range(2):
+        d = po.region_vote(d, aL, D)
+    for _ in range(2):
+        d = po.proper_ipol(d, p["bgrL"])
+    want = po.median3_i16(d)
+    pl = capi.Pipeline(ctx, H, W, capi.default_params(D - 1, sgm_paths=4, Do_vmTop=1, vmTop_method=method))
+    got = pl.run(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"]).copy()
+    pl.close()
+    assert np.array_equal(got, want), float((got == want).mean())
+
+
+@pytest.mark.timeout(300)
+def test_pipeline_right_volume_kept_or_dropped_gives_the_same_maps(ctx):
+    """sm_params.keep_right_volume: the last sgm path of view 1 either stores its sum (vm[1] as the reference leaves it) or
+    only feeds the WTA -- identical maps, and with keep = 1 the stored volume equals the oracle's vm[1]."""
+    H, W, D = 80, 200, 160
+    p = _pair(H, W, D, "texture_warped", seed=23)
+    aL, aR = po.arms(p["bgrL"]), po.arms(p["bgrR"])
+    v1 = po.sgm(po.cbca(po.adcensus_vol(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D, 1), aL, aR, 2, 1), p["bgrR"], 8)
+    out = {}
+    for paths, grouped in ((8, 1), (8, 0), (4, 0)):
+        for keep in (0, 1):
+            pl = capi.Pipeline(ctx, H, W, capi.default_params(D - 1, sgm_paths=paths, sgm_grouped=grouped, keep_right_volume=keep))
+            pl.upload(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"])
+            pl.run_device()
+            out[keep] = pl.download(want_right=True)
+            if keep and paths == 8 and not grouped:
+                assert _bits_equal(pl.buffer(1, (H, W, D), torch.float32).cpu().numpy(), v1)
+            pl.close()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), (paths, grouped)
