@@ -44,8 +44,10 @@ WORKLOADS = {
     "c3cg": (1920, 1080, 256, 8, "texture_warped"),  # c3 with the cost main_.cpp:15 compiles in: censusGrad
     "c3main": (1920, 1080, 256, 8, "texture_warped"),  # the reference's main() as compiled: censusGrad + SolveAll(PY_LEV 1, 0.3)
     "c3py3": (1920, 1080, 256, 8, "texture_warped"),   # c3 with the caller's cross-scale step over a 3-level pyramid
+    "c5": (1920, 1080, 256, 8, "texture_warped"),      # BASELINE configs[4]: the c3 frame as a 64-frame stream, strong scaling
 }
-AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2, "c3cg": 1, "c3main": 1, "c3py3": 1}
+AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2, "c3cg": 1, "c3main": 1, "c3py3": 1, "c5": 1}
+STREAM_FRAMES = 64     # BASELINE configs[4]: "batched 1080p D=256 synthetic stereo stream, frame-parallel at 1/2/4/8 B200"
 COSTCALC = {"c3cg": 1, "c3main": 1}        # 0 = AD-Census (BASELINE configs), 1 = censusGrad
 PYRAMID = {"c3main": (1, 0.3), "c3py3": (3, 0.3)}   # (PY_LEV, REG_LAMBDA) of main_.cpp:132, 157; absent: no SolveAll
 
@@ -327,14 +329,78 @@ def stage_bytes(name):
         # (D <= 128: both views share a launch, two CTAs per SM: 2 launches of twice the bytes)
         nl = 2 if D <= 128 else 4
         st["sgm_group"] = {"bytes_per_launch": 10.0 / nl * V * b, "launches": nl, "kernel": "k_sgm_group"}
-        st["sgm_path"] = {"bytes_per_launch": 3 * V * b, "launches": 4, "kernel": "k_sgm_path"}
+        # paths 2 and 3 of both views: C, S in, S out = 3 V b each, except the right view's last path, whose finished sum
+        # only feeds the fused WTA and is not stored (keep_right_volume = 0): 2 V b
+        st["sgm_path"] = {"bytes_per_launch": 11.0 / 4 * V * b, "launches": 4, "kernel": "k_sgm_path"}
     else:
         # first path writes S (2 V b), the others read-modify-write it (3 V b)
         # <= 1024 scan lines per sweep: the cp.async-staged any-direction kernel (sgm.cu, SM_SGM_SMALL_LINES)
         small = max(W, H) + (min(W, H) - 1 if P == 8 else 0) <= 1024
-        st["sgm"] = {"bytes_per_launch": (3 * P - 1) * V * b / P, "launches": 2 * P,
+        st["sgm"] = {"bytes_per_launch": (3 * P - 1 - 0.5) * V * b / P, "launches": 2 * P,
                      "kernel": "k_sgm_path_s" if small else "k_sgm_path"}
     return st
+
+
+def stream_frame(name, i, base_cache):
+    """Frame i of the synthetic stream: 8 base pairs (seeds 1000 .. 1007, ~3 s of numpy each at 1080p), frame i = base
+    i % 8 rolled down by 16 * (i // 8) rows -- a vertical roll keeps the row-wise stereo geometry, and all 64 frames differ."""
+    import numpy as np
+    from mystereomatching_b200 import synth
+    W, H, D, P, kind = WORKLOADS[name]
+    b = i % 8
+    if b not in base_cache:
+        base_cache[b] = synth.make_pair(H, W, D, kind, seed=1000 + b)
+    shift = 16 * (i // 8)
+    pr = base_cache[b]
+    return {k: np.ascontiguousarray(np.roll(pr[k], shift, axis=0)) for k in ("bgrL", "bgrR", "grayL", "grayR")}
+
+
+def run_stream_bench(name, params, local, rank, world, barrier, max_over_ranks, n_frames=STREAM_FRAMES):
+    """BASELINE configs[4] through the C ABI's frame stream (sm_stream_*): this rank's frames (i mod world == rank) are
+    submitted from pinned host buffers, every left map comes back to the host; wall clock from the first submit to the last
+    retired frame, max over ranks.  Whole job = n_frames frames whatever N is (strong scaling)."""
+    import numpy as np
+    import torch
+    from mystereomatching_b200 import capi
+    W, H, D, P, kind = WORKLOADS[name]
+    mine = list(range(rank, n_frames, world))
+    cache = {}
+    host = []
+    for i in mine:
+        fr = stream_frame(name, i, cache)
+        host.append({k: torch.from_numpy(v).pin_memory() for k, v in fr.items()})
+    outs = [torch.empty((H, W), dtype=torch.int16).pin_memory() for _ in mine]
+    st = capi.Stream([local], H, W, params, queue_depth=4)
+
+    def go(idx):
+        tk = []
+        for j in idx:
+            h = host[j]
+            tk.append(st.submit(h["bgrL"].numpy(), h["bgrR"].numpy(), h["grayL"].numpy(), h["grayR"].numpy(), outs[j].numpy()))
+        st.drain()
+        return tk
+
+    go(range(min(3, len(mine))))           # warm-up: first-use allocations, clocks
+    l0 = st.launches()
+    barrier()
+    t0 = time.perf_counter()
+    go(range(len(mine)))
+    dt = time.perf_counter() - t0
+    barrier()
+    wall = max_over_ranks(dt)
+    launches = st.launches() - l0
+    chk = int(sum(int(o.numpy()[H // 2, W // 2]) for o in outs))
+    first = outs[0].numpy().copy() if mine else None
+    st.close()
+    mde = n_frames * W * H * D / 1e6
+    return {"workload": f"c5: {n_frames}-frame {W}x{H} D={D} stream (frame i = base pair 1000 + i%8 rolled by 16*(i//8) rows), "
+                        f"frame i -> rank i mod N, the c3 pipeline per frame",
+            "api": "sm_stream_create / sm_stream_submit / sm_stream_wait (C ABI): one worker thread + sm_pipeline per GPU, "
+                   "H2D of frame i+1 and D2H of frame i-1 overlapped with the compute of frame i; pinned host buffers",
+            "frames": n_frames, "frames_this_rank": len(mine), "wall_ms": 1e3 * wall, "fps": n_frames / wall,
+            "value": mde / wall, "unit": "MDE/s", "scaling": "strong", "timing": "wall clock, max over ranks",
+            "h2d_bytes_per_frame": 8 * W * H, "d2h_bytes_per_frame": 2 * W * H, "gpu_launches_this_rank": launches,
+            "checksum": chk}, first
 
 
 def main_ours(args):
@@ -447,6 +513,13 @@ def main_ours(args):
     disp = pl.run(*host_args(0)).copy()
     bad2 = synth.bad_k(disp, frames[0][0]["gt"], frames[0][0]["nonocc"], 2)
 
+    stream_res = None
+    if name in ("c3", "c5") and not args.no_stream:
+        stream_res, first_map = run_stream_bench(name, params, local, rank, world, barrier, max_over_ranks)
+        if rank == 0 and first_map is not None:
+            ref0 = pl.run(*[stream_frame(name, 0, {})[k] for k in ("bgrL", "bgrR", "grayL", "grayR")])
+            stream_res["frame0_equals_sm_pipeline_run"] = bool((ref0 == first_map).all())
+
     mde_frame = W * H * D / 1e6
     value = world * args.steps * mde_frame / (dev_ms / 1e3)
     e2e_val = world * args.steps * mde_frame / (e2e_ms / 1e3)
@@ -492,6 +565,16 @@ def main_ours(args):
                        "h2d_bytes_per_step": 8 * W * H, "d2h_bytes_per_step": 2 * W * H},
                "gpu_launches": launches, "roofline": roofline, "stages": stages, "clocks": clocks,
                "quality": {"bad2_nonocc_pct": round(bad2, 3), "checksum": chk}}
+        if stream_res is not None:
+            out["stream"] = stream_res
+            if name == "c5":     # the stream IS the workload: whole-job throughput over the 64 frames, strong scaling
+                out["value"], out["fps"], out["scaling"] = stream_res["value"], stream_res["fps"], "strong"
+                out["ms_per_step"] = stream_res["wall_ms"] / stream_res["frames"]
+                out["e2e"] = {"value": stream_res["value"], "unit": "MDE/s", "fps": stream_res["fps"],
+                              "ms_per_step": stream_res["wall_ms"] / stream_res["frames"],
+                              "h2d_bytes_per_step": 8 * W * H, "d2h_bytes_per_step": 2 * W * H}
+                out["config"]["note"] = ("value = e2e = the 64-frame stream through sm_stream_* with host buffers (wall clock, max "
+                                         "over ranks); the device-resident per-stage numbers below are the c3 frame's")
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(name)
             if oracle_fits(name):
@@ -546,6 +629,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-stream", action="store_true", help="skip the 64-frame stream leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     OUT = QuietStdout()

@@ -400,6 +400,10 @@ int sm_pipeline_download(sm_pipeline* pl, int16_t* h_dispL, int16_t* h_dispR);
 int sm_pipeline_run(sm_pipeline* pl, const uint8_t* h_bgrL, const uint8_t* h_bgrR,
                     const uint8_t* h_grayL, const uint8_t* h_grayR, int16_t* h_dispL,
                     int16_t* h_dispR);
+/* The next sm_pipeline_run_device reads the pair from caller-owned DEVICE buffers (bgr: [H][W][3] u8, gray: [H][W] u8,
+ * gray NULL = computed from BGR); all NULL restores the pipeline's own buffers.  No copy is made. */
+int sm_pipeline_bind_inputs(sm_pipeline* pl, const uint8_t* d_bgrL, const uint8_t* d_bgrR, const uint8_t* d_grayL,
+                            const uint8_t* d_grayR);
 /* device views of the pipeline's buffers (for tests / the C++ class): which =
  * 0 vm[0], 1 vm[1], 2 DP[0], 3 DP[1], 4 HVL[0], 5 HVL[1], 6 census L, 7 census R */
 void* sm_pipeline_buffer(sm_pipeline* pl, int which);
@@ -410,6 +414,28 @@ int sm_pipeline_stage_ms(sm_pipeline* pl, float* out8);
 /* split of the sgm stage of that run: out2[0] = the grouped row sweeps (k_sgm_group), out2[1] = the single-path
  * launches (k_sgm_path*); {0, sgm} when the grouped sweeps did not run */
 int sm_pipeline_sgm_split_ms(sm_pipeline* pl, float* out2);
+
+/* ---- frame stream over one or more GPUs (BASELINE config 5) ------------------------------------
+ * The reference runs one StereoMatching object per stereo pair (main_.cpp:138-166).  A stream of pairs parallelises BY
+ * FRAME (SGM paths do not shard along rows): sm_stream_create starts one worker per listed device -- a host thread
+ * with its own sm_ctx, sm_pipeline, copy stream and double-buffered device / pinned staging buffers -- and frame i
+ * (the i-th sm_stream_submit) runs on worker i mod n_devices.  Inside a worker the upload of frame i+1 and the
+ * download of frame i-1 overlap the compute of frame i.  No collective: the path has no exchange step.
+ *   sm_stream_submit  queues one pair (HOST buffers: pinned ones are copied from directly, pageable ones through the
+ *                     worker's staging); returns at once unless queue_depth frames are already waiting on that worker.
+ *                     The buffers must stay valid until sm_stream_wait(ticket) returns; h_gray* may be NULL.
+ *   sm_stream_wait    blocks until that frame's left disparity map is in h_dispL (status of the worker).
+ *   sm_stream_drain   waits for everything submitted so far. */
+typedef struct sm_stream sm_stream;
+int sm_stream_create(const int* devices, int n_devices, int H, int W, const sm_params* p, int queue_depth, sm_stream** out);
+int sm_stream_submit(sm_stream* s, const uint8_t* h_bgrL, const uint8_t* h_bgrR, const uint8_t* h_grayL,
+                     const uint8_t* h_grayR, int16_t* h_dispL, long long* ticket);
+int sm_stream_wait(sm_stream* s, long long ticket);
+int sm_stream_drain(sm_stream* s);
+int sm_stream_destroy(sm_stream* s);
+int sm_stream_device_count(sm_stream* s);
+long long sm_stream_frames_done(sm_stream* s, int worker);   /* frames retired by one worker */
+long long sm_stream_launch_count(sm_stream* s);              /* kernels launched by all workers */
 
 #ifdef __cplusplus
 }

@@ -120,6 +120,15 @@ SIGNATURES = {
     "sm_pipeline_download": ([_P, _P, _P], _I),
     "sm_pipeline_run": ([_P, _P, _P, _P, _P, _P, _P], _I),
     "sm_pipeline_buffer": ([_P, _I], _P),
+    "sm_pipeline_bind_inputs": ([_P, _P, _P, _P, _P], _I),
+    "sm_stream_create": ([C.POINTER(C.c_int), _I, _I, _I, C.POINTER(SmParams), _I, C.POINTER(_P)], _I),
+    "sm_stream_submit": ([_P, _P, _P, _P, _P, _P, C.POINTER(_LL)], _I),
+    "sm_stream_wait": ([_P, _LL], _I),
+    "sm_stream_drain": ([_P], _I),
+    "sm_stream_destroy": ([_P], _I),
+    "sm_stream_device_count": ([_P], _I),
+    "sm_stream_frames_done": ([_P, _I], _LL),
+    "sm_stream_launch_count": ([_P], _LL),
     "sm_pipeline_enable_timing": ([_P, _I], _I),
     "sm_pipeline_stage_ms": ([_P, C.POINTER(C.c_float)], _I),
     "sm_pipeline_sgm_split_ms": ([_P, C.POINTER(C.c_float)], _I),
@@ -648,3 +657,51 @@ class Pipeline:
         check(self.ctx.L.sm_pipeline_sgm_split_ms(self.h, sp))
         out["sgm_group"], out["sgm_path"] = float(sp[0]), float(sp[1])
         return out
+
+
+class Stream:
+    """sm_stream: frames submitted in order, frame i on device devices[i % n]; host buffers in, host disparity out."""
+
+    def __init__(self, devices, H, W, params, queue_depth=4):
+        self.L = lib()
+        if self.L.sm_device_count() <= 0:
+            raise SmError("no CUDA device visible: sm_b200 has no CPU fallback")
+        self.H, self.W = H, W
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        check(self.L.sm_stream_create(arr, len(devices), H, W, C.byref(params), queue_depth, C.byref(h)))
+        self.h = h
+        self._keep = {}
+
+    def submit(self, bgrL, bgrR, grayL, grayR, out):
+        """numpy host arrays (pinned or not); `out`: int16 [H][W] that receives the left map.  Returns the ticket."""
+        t = _LL(0)
+        g = (None, None) if grayL is None else (grayL.ctypes.data, grayR.ctypes.data)
+        check(self.L.sm_stream_submit(self.h, bgrL.ctypes.data, bgrR.ctypes.data, g[0], g[1], out.ctypes.data, C.byref(t)))
+        self._keep[t.value] = (bgrL, bgrR, grayL, grayR, out)      # the buffers must outlive the frame
+        return t.value
+
+    def wait(self, ticket):
+        check(self.L.sm_stream_wait(self.h, ticket))
+        self._keep.pop(ticket, None)
+
+    def drain(self):
+        check(self.L.sm_stream_drain(self.h))
+        self._keep.clear()
+
+    def frames_done(self, worker):
+        return int(self.L.sm_stream_frames_done(self.h, worker))
+
+    def launches(self):
+        return int(self.L.sm_stream_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sm_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

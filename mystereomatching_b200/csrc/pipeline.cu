@@ -17,7 +17,8 @@ struct sm_pipeline {
   sm_ctx* ctx = nullptr;
   int H = 0, W = 0, D = 0;
   sm_params p;
-  uint8_t *bgr[2] = {nullptr, nullptr}, *gray[2] = {nullptr, nullptr};
+  uint8_t *bgr[2] = {nullptr, nullptr}, *gray[2] = {nullptr, nullptr};          // the images the stages read
+  uint8_t *own_bgr[2] = {nullptr, nullptr}, *own_gray[2] = {nullptr, nullptr};  // the pipeline's own buffers (sm_pipeline_upload)
   uint32_t *pix[2] = {nullptr, nullptr}, *armpk[2] = {nullptr, nullptr};
   uint64_t* cen[2] = {nullptr, nullptr};
   uint16_t* arms[2] = {nullptr, nullptr};
@@ -53,7 +54,7 @@ extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 2; i++) {
-    cudaFree(pl->bgr[i]); cudaFree(pl->gray[i]); cudaFree(pl->pix[i]); cudaFree(pl->armpk[i]);
+    cudaFree(pl->own_bgr[i]); cudaFree(pl->own_gray[i]); cudaFree(pl->pix[i]); cudaFree(pl->armpk[i]);
     cudaFree(pl->cen[i]); cudaFree(pl->arms[i]); cudaFree(pl->disp[i]);
     cudaFree(pl->grad[i][0]); cudaFree(pl->grad[i][1]);
   }
@@ -92,8 +93,9 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   const int nw = sm_census_words(p->censusFunc);
   int rc = SM_OK;
   for (int i = 0; i < 2 && rc == SM_OK; i++) {
-    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->bgr[i], npix * 3);
-    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->gray[i], npix);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->own_bgr[i], npix * 3);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->own_gray[i], npix);
+    pl->bgr[i] = pl->own_bgr[i]; pl->gray[i] = pl->own_gray[i];
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->pix[i], npix * 4);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], (size_t)H * (W + 2 * smi_arm_pad(pl->D)) * 16);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->cen[i], npix * 8 * nw);
@@ -158,12 +160,32 @@ static int upload_one(sm_pipeline* pl, void* d_dst, const uint8_t* h_src, uint8_
   return SM_OK;
 }
 
+// The next sm_pipeline_run_device reads the stereo pair from caller-owned DEVICE buffers (a frame stream uploads
+// frame i+1 into a second set while frame i computes); all NULL: back to the pipeline's own buffers.
+extern "C" int sm_pipeline_bind_inputs(sm_pipeline* pl, const uint8_t* d_bgrL, const uint8_t* d_bgrR, const uint8_t* d_grayL,
+                                       const uint8_t* d_grayR) {
+  SM_CHECK_ARG(pl && !pl->is_child);
+  SM_CHECK_ARG((d_bgrL == nullptr) == (d_bgrR == nullptr) && (d_grayL == nullptr) == (d_grayR == nullptr));
+  SM_CHECK_ARG(d_bgrL || !d_grayL);
+  if (!d_bgrL) {
+    for (int i = 0; i < 2; i++) { pl->bgr[i] = pl->own_bgr[i]; pl->gray[i] = pl->own_gray[i]; }
+    pl->have_gray = false;
+    return SM_OK;
+  }
+  pl->bgr[0] = const_cast<uint8_t*>(d_bgrL); pl->bgr[1] = const_cast<uint8_t*>(d_bgrR);
+  pl->gray[0] = d_grayL ? const_cast<uint8_t*>(d_grayL) : pl->own_gray[0];
+  pl->gray[1] = d_grayR ? const_cast<uint8_t*>(d_grayR) : pl->own_gray[1];
+  pl->have_gray = d_grayL != nullptr;
+  return SM_OK;
+}
+
 extern "C" int sm_pipeline_upload(sm_pipeline* pl, const uint8_t* h_bgrL, const uint8_t* h_bgrR, const uint8_t* h_grayL,
                                   const uint8_t* h_grayR) {
   SM_CHECK_ARG(pl && h_bgrL && h_bgrR);
   SM_CHECK_ARG((h_grayL == nullptr) == (h_grayR == nullptr));
   const size_t npix = (size_t)pl->H * pl->W;
   SM_CUDA(cudaSetDevice(pl->ctx->device));
+  for (int i = 0; i < 2; i++) { pl->bgr[i] = pl->own_bgr[i]; pl->gray[i] = pl->own_gray[i]; }
   pl->stage_drained = !pl->stage_used;
   pl->stage_used = false;
   SM_TRY(upload_one(pl, pl->bgr[0], h_bgrL, pl->h_in, npix * 3));
