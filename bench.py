@@ -45,21 +45,24 @@ WORKLOADS = {
     "c3main": (1920, 1080, 256, 8, "texture_warped"),  # the reference's main() as compiled: censusGrad + SolveAll(PY_LEV 1, 0.3)
     "c3py3": (1920, 1080, 256, 8, "texture_warped"),   # c3 with the caller's cross-scale step over a 3-level pyramid
     "c5": (1920, 1080, 256, 8, "texture_warped"),      # BASELINE configs[4]: the c3 frame as a 64-frame stream, strong scaling
+    "c3cen": (1920, 1080, 256, 8, "texture_warped"),   # costcalculation "Census", no aggregation: the native uint16 path (b = 2)
 }
-AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2, "c3cg": 1, "c3main": 1, "c3py3": 1, "c5": 1}
+AGGREGATION = {"c1": 1, "c2": 1, "c3": 1, "c4": 2, "c3cg": 1, "c3main": 1, "c3py3": 1, "c5": 1, "c3cen": 0}
 STREAM_FRAMES = 64     # BASELINE configs[4]: "batched 1080p D=256 synthetic stereo stream, frame-parallel at 1/2/4/8 B200"
-COSTCALC = {"c3cg": 1, "c3main": 1}        # 0 = AD-Census (BASELINE configs), 1 = censusGrad
+COSTCALC = {"c3cg": 1, "c3main": 1, "c3cen": 2}   # 0 = AD-Census (BASELINE configs), 1 = censusGrad, 2 = Census (uint16 volumes)
 PYRAMID = {"c3main": (1, 0.3), "c3py3": (3, 0.3)}   # (PY_LEV, REG_LAMBDA) of main_.cpp:132, 157; absent: no SolveAll
 
 
 def workload_desc(name):
     W, H, D, P, kind = WORKLOADS[name]
-    agg = "CBCA(2 it, intersected arms)" if AGGREGATION[name] == 1 else "NL(MST tree filter, sigma 0.1, left view)"
-    cost = "censusGrad(71-bit census + arm-weighted x/y gradient)" if COSTCALC.get(name, 0) else "AD-Census(71-bit)"
+    agg = {0: "no aggregation", 1: "CBCA(2 it, intersected arms)", 2: "NL(MST tree filter, sigma 0.1, left view)"}[AGGREGATION[name]]
+    cost = {0: "AD-Census(71-bit)", 1: "censusGrad(71-bit census + arm-weighted x/y gradient)",
+            2: "Census(71-bit Hamming, uint16 volumes)"}[COSTCALC.get(name, 0)]
     if name in PYRAMID:
         agg += f"+SolveAll({PYRAMID[name][0]} level(s), lambda {PYRAMID[name][1]})"
     return (f"{name}: {W}x{H} D={D} {cost}+{agg}+{P}-path SGM+WTA+LRC+"
-            f"regionVote x2+properIpol x2+median3, 2 views, fp32 volumes, synthetic {kind} pairs")
+            f"regionVote x2+properIpol x2+median3, 2 views, {'uint16' if COSTCALC.get(name, 0) == 2 else 'fp32'} volumes, "
+            f"synthetic {kind} pairs")
 
 
 def peaks():
@@ -312,7 +315,11 @@ def stage_bytes(name):
     """Algorithmic HBM bytes per LAUNCH and launches per frame for each volume stage (b = 4)."""
     W, H, D, P, kind = WORKLOADS[name]
     V = W * H * D
-    b = 4
+    b = 2 if COSTCALC.get(name, 0) == 2 else 4
+    if COSTCALC.get(name, 0) == 2:     # native uint16 path: Hamming volume write, 8 single-path sweeps per view
+        return {"cost": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_cost<HAMMING_U16>"},
+                "sgm": {"bytes_per_launch": (3 * P - 1 - 0.5) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path_u16"},
+                "wta": {"bytes_per_launch": 0, "launches": 2, "kernel": "fused into k_sgm_path_u16 (mode 2 / 3)"}}
     agg = {"bytes_per_launch": 2 * V * b, "launches": 8, "kernel": "k_cbca_pass"}
     if AGGREGATION[name] == 2:   # k_nl = 4 volume passes (SURVEY.md 8d); MST build + rooting + two tree sweeps
         agg = {"bytes_per_launch": 4 * V * b, "launches": 1, "kernel": "nl (Boruvka MST + Euler-tour rooting + k_tf_cta_fast)"}
@@ -532,7 +539,7 @@ def main_ours(args):
         gbs = info["bytes_per_launch"] / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         stages[k] = {"ms_per_frame": round(ms, 4), "launches": info["launches"], "kernel": info["kernel"],
                      "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
-    for k in ("census", "arms", "refine", "total") + (("sgm",) if "sgm" not in sb else ()):
+    for k in ("census", "arms", "refine", "total") + (("sgm",) if "sgm" not in sb else ()) + (("aggregation",) if "aggregation" not in sb else ()):
         stages[k] = {"ms_per_frame": round(stage_acc.get(k, 0.0) / args.steps, 4)}
     dom = max(sb, key=lambda k: stages[k]["ms_per_frame"])
     traffic = None
@@ -554,8 +561,8 @@ def main_ours(args):
         out = {"metric": "MDE/s (W*H*D disparity evaluations per second), whole path",
                "value": value, "unit": "MDE/s", "fps": value * 1e6 / (W * H * D), "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic",
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u16" if COSTCALC.get(name, 0) == 2 else "f32", "data": "synthetic",
                "config": {"workload": workload_desc(name), "frames_per_step_per_gpu": 1,
                           "extra_untimed_warmup_steps": extra_warm,
                           "parallelism": f"frame-parallel x{world}, no collective",

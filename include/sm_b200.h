@@ -76,7 +76,11 @@ typedef struct sm_params {
                              * (one read of C and one read-modify-write of the sum for three paths); every path
                              * volume is still exact, only the order of the eight additions differs: integer-valued
                              * costs stay bit-exact, float sums agree to a few ulp (see sm_sgm_grouped). */
-  int costcalculation;      /* 0 "ADCensus" (BASELINE configs), 1 "censusGrad" (the selector main_.cpp:15 compiles in) */
+  int costcalculation;      /* 0 "ADCensus" (BASELINE configs), 1 "censusGrad" (the selector main_.cpp:15 compiles in),
+                             * 2 "Census" (censusCal(vm, 1), stereoMatching.cpp:975-976): Hamming volume.  With no
+                             * aggregation and a power-of-two sgm_reduCoeffi1 the whole frame runs on uint16 volumes
+                             * (sm_sgm_u16: exact, half the bytes); sm_pipeline_buffer(0 / 1) then are uint16 volumes in
+                             * fixed point (sgm_reduCoeffi1 x the float values).  Otherwise float32 as the reference. */
   float cg_lamCen, cg_lamG; /* censusGrad: Parameters::lamCen = 13, lamG = 1 (main_.cpp:60-61, stereoMatching.cpp:37-41) */
   float gradTrunc;          /* 500  (censusGrad -> grad(gradVm, 500), stereoMatching.cpp:34) */
   int pyramidLevels;        /* PY_LEV of main_.cpp:132 (1 there).  > 1 with crossScaleLambda >= 0: cost + aggregation run
@@ -248,6 +252,19 @@ int sm_sgm_path(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, in
  * into d_sum (must not alias d_vol). */
 int sm_sgm(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, int D, int paths,
            int corDifThres, int reduCoeffi1, float* d_sum);
+
+/* sgm() on a 16-bit INTEGER cost volume, natively (costScan's integer entry, stereoMatching.cpp:2007-2014:
+ * vm.depth() CV_8U / CV_16U -> updateCost<uchar | ushort>, stereoMatching.h:2205-2280).  d_vol: [H][W][D] uint16 raw
+ * costs (e.g. sm_cost_hamming_u16).  With integer costs and a power-of-two reduCoeffi1 every value of updateCost is a
+ * multiple of 1 / reduCoeffi1 and the reference's float arithmetic is exact; the kernels keep Lr and the path sum as
+ * uint16 fixed point: d_sum = reduCoeffi1 x (the float volume sgm() leaves in vm), exactly, and d_disp (nullable) =
+ * gen_dispFromVm of it.  Half the HBM bytes of the float path per pass.  maxCost bounds the raw costs (71 for the
+ * 71-bit census); SM_ERR_UNSUPPORTED unless reduCoeffi1 is a power of two and paths*(maxCost+3)*reduCoeffi1 <= 65535
+ * (then: sm_vol_to_f32 + sm_sgm). */
+int sm_sgm_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint8_t* d_bgr, int H, int W, int D, int paths, int corDifThres,
+               int reduCoeffi1, int maxCost, uint16_t* d_sum, int16_t* d_disp);
+/* gen_dispFromVm (stereoMatching.cpp:3928-3967) on a uint16 volume: first minimum. */
+int sm_wta_u16(sm_ctx* ctx, const uint16_t* d_vol, int H, int W, int D, int16_t* d_disp);
 
 /* gen_sgm_vm's inner statement `sum += Lr[num]` (stereoMatching.cpp:2051) for one
  * materialised path volume: d_acc[i] = d_acc[i] + d_x[i]. */

@@ -96,6 +96,8 @@ SIGNATURES = {
     "sm_sgm_path": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_sgm": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "sm_sgm_grouped": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "sm_sgm_u16": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P], _I),
+    "sm_wta_u16": ([_P, _P, _I, _I, _I, _P], _I),
     "sm_sgm_grouped2": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "sm_vol_accumulate": ([_P, _P, _P, _Z], _I),
     "sm_wta": ([_P, _P, _I, _I, _I, _P], _I),
@@ -377,6 +379,21 @@ class Ctx:
         H, W, D = vol.shape
         out = self.torch.empty_like(vol)
         check(self.L.sm_sgm(self.h, _ptr(vol), _ptr(bgr), H, W, D, paths, thr, redu, _ptr(out)))
+        return out
+
+    def sgm_u16(self, vol, bgr, paths=4, thr=15, redu=4, max_cost=71, want_disp=True):
+        """sgm() on a uint16 volume (int16 tensor holding the bit patterns): (sum volume in fixed point = redu x the float
+        sum, disparity map or None)."""
+        H, W, D = vol.shape
+        out = self.torch.empty_like(vol)
+        disp = self.empty((H, W), self.torch.int16) if want_disp else None
+        check(self.L.sm_sgm_u16(self.h, _ptr(vol), _ptr(bgr), H, W, D, paths, thr, redu, max_cost, _ptr(out), _ptr(disp)))
+        return out, disp
+
+    def wta_u16(self, vol):
+        H, W, D = vol.shape
+        out = self.empty((H, W), self.torch.int16)
+        check(self.L.sm_wta_u16(self.h, _ptr(vol), H, W, D, _ptr(out)))
         return out
 
     def sgm_grouped(self, vol, bgr, thr=15, redu=4):

@@ -118,6 +118,11 @@ int smi_sgm_path_packed(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, 
 int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                          int corDifThres, int reduCoeffi1, int mode, float* d_out, int16_t* d_disp);
 
+// 16-bit integer-cost SGM (sgm_u16.cu): fixed point = reduCoeffi1 x the reference's float values
+bool smi_sgm_u16_ok(int D, int paths, int reduCoeffi1, int maxCost);
+int smi_sgm_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, int H, int W, int D, int paths, int corDifThres,
+                int reduCoeffi1, uint16_t* d_sum, int16_t* d_disp, bool keep_sum);
+
 // grouped SGM sweep (sgm_group.cu): up = 1 -> paths {0,4,5}, up = 0 -> paths {1,6,7}; mode 0 writes, 1 accumulates
 int smi_sgm_group2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int up, int mode,
                    int corDifThres, int reduCoeffi1, float* const* d_sum);

@@ -36,6 +36,7 @@ struct sm_pipeline {
   sm_pipeline* child = nullptr;   // next pyramid level (cost + aggregation only), pyramidLevels > 1
   bool is_child = false;
   bool have_gray = false, have_arms = false, scale_folded = false;
+  bool u16 = false;          // "Census" without aggregation: the volumes are uint16 (vol[] then point at uint16 data)
   bool stage_used = false, stage_drained = true;
   bool timing = false;
   cudaEvent_t ev[ST_COUNT + 1];
@@ -81,8 +82,8 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   SM_CHECK_ARG(p->censusFunc == 0 || p->censusFunc == 3);
   SM_CHECK_ARG(p->sgm_paths >= 0 && p->sgm_paths <= 8);
   SM_CHECK_ARG(p->aggregation >= 0 && p->aggregation <= 2);
-  SM_CHECK_ARG(p->costcalculation == 0 || p->costcalculation == 1);
-  SM_CHECK_ARG(p->costcalculation == 0 || (H >= 2 && W >= 2 && p->cg_lamCen > 0.f && p->cg_lamG > 0.f));
+  SM_CHECK_ARG(p->costcalculation >= 0 && p->costcalculation <= 2);
+  SM_CHECK_ARG(p->costcalculation != 1 || (H >= 2 && W >= 2 && p->cg_lamCen > 0.f && p->cg_lamG > 0.f));
   SM_CHECK_ARG(p->pyramidLevels >= 1 && p->pyramidLevels <= SM_MAX_PYRAMID);
   SM_CHECK_ARG(p->cbca_crossL_out >= 0 && p->cbca_crossL_out <= 255);
   SM_CHECK_ARG(!p->Do_vmTop || (p->vmTop_Num >= 1 && p->vmTop_Num <= 16 && p->vmTop_method >= 0 && p->vmTop_method <= 2));
@@ -91,6 +92,11 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
   pl->ctx = ctx; pl->H = H; pl->W = W; pl->D = p->numDisparities; pl->p = *p;
   const size_t npix = (size_t)H * W, nvol = npix * pl->D;
   const int nw = sm_census_words(p->censusFunc);
+  // "Census" + no aggregation + a power-of-two sgm_reduCoeffi1: every value on the path is an exact multiple of
+  // 1 / reduCoeffi1, so the frame runs on uint16 volumes (sgm_u16.cu)
+  pl->u16 = p->costcalculation == 2 && p->aggregation == 0 && !p->Do_vmTop && p->crossScaleLambda < 0.f &&
+            (p->sgm_paths == 0 || smi_sgm_u16_ok(pl->D, p->sgm_paths, p->sgm_reduCoeffi1, sm_census_code_length(p->censusFunc)));
+  const size_t volB = nvol * (pl->u16 ? sizeof(uint16_t) : sizeof(float));
   int rc = SM_OK;
   for (int i = 0; i < 2 && rc == SM_OK; i++) {
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->own_bgr[i], npix * 3);
@@ -105,10 +111,10 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
       if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->grad[i][k], npix * sizeof(float));
   }
   // a fourth volume only where the two views' SGM sweeps can share a launch (two sums are written at once)
-  const bool two_view_sgm = p->sgm_paths == 8 && p->sgm_grouped && p->Do_refine && p->Do_LRConsis;
-  const bool two_stream_sgm = !two_view_sgm && p->sgm_paths > 0 && p->Do_refine && p->Do_LRConsis && nvol <= ((size_t)48 << 20);
+  const bool two_view_sgm = !pl->u16 && p->sgm_paths == 8 && p->sgm_grouped && p->Do_refine && p->Do_LRConsis;
+  const bool two_stream_sgm = !two_view_sgm && !pl->u16 && p->sgm_paths > 0 && p->Do_refine && p->Do_LRConsis && nvol <= ((size_t)48 << 20);
   for (int i = 0; i < ((two_view_sgm || two_stream_sgm) ? 4 : 3) && rc == SM_OK; i++)
-    rc = pl_alloc(ctx, (void**)&pl->vol[i], nvol * sizeof(float));
+    rc = pl_alloc(ctx, (void**)&pl->vol[i], volB);
   if (rc == SM_OK && two_stream_sgm) {
     if (cudaStreamCreateWithFlags(&pl->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming) != cudaSuccess ||
@@ -238,6 +244,12 @@ static int pl_cost_calculate(sm_pipeline* pl) {
     for (int i = 0; i < imgNum; i++)
       SM_TRY(smi_cost_adcensus_packed(c, pl->pix[0], pl->pix[1], pl->cen[0], pl->cen[1], H, W, D, P.censusFunc,
                                       P.adTrunc, P.lamAD, P.lamCen, i, pl->vol[i]));
+  } else if (P.costcalculation == 2) {
+    // "Census": censusCal(vm, 1) (stereoMatching.cpp:975-976, 807-892) = the Hamming volume of both views
+    for (int i = 0; i < imgNum; i++) {
+      if (pl->u16) SM_TRY(sm_cost_hamming_u16(c, pl->cen[0], pl->cen[1], H, W, D, P.censusFunc, i, (uint16_t*)pl->vol[i]));
+      else SM_TRY(sm_cost_hamming(c, pl->cen[0], pl->cen[1], H, W, D, P.censusFunc, i, pl->vol[i]));
+    }
   } else {
     // censusGrad (stereoMatching.cpp:25-48): grad() computes the arms first (stereoMatching.cpp:628-631)
     for (int i = 0; i < 2; i++) SM_TRY(sm_grad_xy(c, pl->gray[i], H, W, pl->grad[i][0], pl->grad[i][1]));
@@ -334,8 +346,18 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
     // asks for it (keep_right_volume, vmTop) the last path of view 1 does the WTA without storing the sum: one volume
     // write less per frame
     const bool keep[2] = {true, P.keep_right_volume != 0 || P.Do_vmTop != 0};
+    if (pl->u16) {
+      for (int i = 0; i < views; i++) {
+        SM_TRY(smi_sgm_u16(c, (const uint16_t*)pl->vol[i], pl->pix[i], H, W, D, P.sgm_paths, P.sgm_corDifThres, P.sgm_reduCoeffi1,
+                           (uint16_t*)pl->vol[2], pl->disp[i], keep[i]));
+        float* t = pl->vol[i];
+        pl->vol[i] = pl->vol[2];
+        pl->vol[2] = t;
+      }
+      done = true;
+    }
     pl->sweeps[0] = pl->sweeps[1] = false;
-    if (P.sgm_paths == 8 && P.sgm_grouped && views == 2 && pl->vol[3]) {
+    if (!done && P.sgm_paths == 8 && P.sgm_grouped && views == 2 && pl->vol[3]) {
       // both views per sweep launch (two CTAs per SM); falls through to one view at a time if the shape does not fit
       const float* vols[2] = {pl->vol[0], pl->vol[1]};
       const uint32_t* pixs[2] = {pl->pix[0], pl->pix[1]};
@@ -407,6 +429,9 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
       SM_TRY(sm_disp_from_top2(c, pl->top, pl->bgr[0], H, W, P.vmTop_Num, P.vmTop_method, P.vmTop_ts, P.vmTop_hasCir2,
                                P.vmTop_cir3_doColorLimit, pl->disp[i]));
     }
+  } else if (pl->u16) {
+    if (P.sgm_paths == 0)
+      for (int i = 0; i < views; i++) SM_TRY(sm_wta_u16(c, (const uint16_t*)pl->vol[i], H, W, D, pl->disp[i]));
   } else if (P.sgm_paths < 2)   // otherwise the WTA was fused into the last SGM path
     for (int i = 0; i < views; i++) SM_TRY(sm_wta(c, pl->vol[i], H, W, D, pl->disp[i]));
   PL_MARK(6);

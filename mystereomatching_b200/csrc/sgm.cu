@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "sgm_common.cuh"
 
 #define SGM_WARPS 2
 #define SGM_NSTG 12   // staged variant: pixels in flight per warp (cp.async), one extra slot so a refill never
@@ -97,29 +98,6 @@ __device__ __forceinline__ void store_run(float* __restrict__ p, int d0, int D, 
 #pragma unroll
     for (int k = 0; k < VPL; k++)
       if (d0 + k < D) p[d0 + k] = r[k];
-  }
-}
-
-// Scan-line geometry.  (mv,mu) = direction of travel = -(rv,ru).
-struct sgm_geom {
-  int H, W, mv, mu, nLines;
-};
-
-__device__ __forceinline__ void line_start(const sgm_geom& g, int k, int& v, int& u, int& len) {
-  if (g.mv == 0) {  // horizontal: line = row
-    v = k; u = g.mu > 0 ? 0 : g.W - 1; len = g.W;
-  } else if (g.mu == 0) {  // vertical: line = column
-    u = k; v = g.mv > 0 ? 0 : g.H - 1; len = g.H;
-  } else {  // diagonal: W lines start on the first row, H-1 more on the entry column
-    if (k < g.W) {
-      u = k; v = g.mv > 0 ? 0 : g.H - 1;
-    } else {
-      int j = k - g.W + 1;
-      v = g.mv > 0 ? j : g.H - 1 - j;
-      u = g.mu > 0 ? 0 : g.W - 1;
-    }
-    int lv = g.mv > 0 ? g.H - v : v + 1, lu = g.mu > 0 ? g.W - u : u + 1;
-    len = min(lv, lu);
   }
 }
 
@@ -513,8 +491,6 @@ __global__ void __launch_bounds__(32)
   }
 }
 
-static const int SGM_RV[8] = {+1, -1, 0, 0, +1, +1, -1, -1};
-static const int SGM_RU[8] = {0, 0, +1, -1, -1, +1, +1, -1};
 
 template <int VPL, int PF, bool VEC>
 static int launch_sgm(sm_ctx* ctx, const float* vol, const uint32_t* pix, float* out, const sgm_geom& g, int D,

@@ -1129,6 +1129,13 @@ static void cost_calculate(const u8* bgrL, const u8* bgrR, const u8* grayL, cons
     }
     lap(1);
     arms();
+  } else if (p->costcalc == 2) {  // "Census": censusCal(vm, 1) (stereoMatching.cpp:975-976): the Hamming volumes
+    for (int i = 0; i < 2; i++) {
+      vm[i].resize(n);
+      orc_hamming_vol(cL.data(), cR.data(), H, W, D, nw, codeLen, 1.0f, i, vm[i].data());
+    }
+    lap(1);
+    arms();
   } else {  // censusGrad (stereoMatching.cpp:25-48); grad() needs the arms first (:628-631)
     const long np = (long)H * W;
     std::vector<float> g(4 * np), gr(n), cen(n);

@@ -192,3 +192,26 @@ def test_c3_full_width_band_equals_compiled_reference(ctx):
     pl.close()
     got = ctx.sgm(ctx.dev(a0), bL, 4)
     assert _bits_equal_dev(got, s0), "sgm() 4 paths on the aggregated band"
+
+
+# ------------------------------------------------------------------------------------------------ "Census", uint16 volumes
+@pytest.mark.timeout(900)
+def test_c3_census_uint16_frame_vs_oracle(ctx):
+    """1920x1080 D=256, costcalculation "Census", 8-path SGM on uint16 volumes: the fixed-point sum is 4 x the oracle's
+    float volume exactly and the refined map is identical."""
+    W, H, D = 1920, 1080, 256
+    rows = _fit_rows(W, H, D, 8)
+    p = synth.make_pair(rows, W, D, "texture_warped", seed=1000)
+    po.lib().orc_set_threads(_threads())
+    op = po.default_params(D, paths=8, aggregation=0, costcalc=2)
+    dl, dr, vol, _ = po.pipeline(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], op, want_vol=True)
+    disp, pl = _gpu_frame(ctx, p, rows, W, D, sgm_paths=8, aggregation=0, costcalculation=2)
+    got = pl.buffer(0, (rows, W, D), torch.int16)
+    ref16 = torch.from_numpy((vol * 4).astype(np.uint16).view(np.int16))
+    assert float(np.abs(vol * 4 - np.rint(vol * 4)).max()) == 0.0            # the float sum IS a multiple of 1/4
+    step = 1 << 27
+    flat, rf = got.reshape(-1), ref16.reshape(-1)
+    for i in range(0, rf.numel(), step):
+        assert torch.equal(flat[i:i + step], rf[i:i + step].to(flat.device)), "uint16 path sum"
+    pl.close()
+    assert np.array_equal(disp, dl), f"{(disp == dl).mean():.6f} identical"

