@@ -259,7 +259,7 @@ int sm_sgm(sm_ctx* ctx, const float* d_vol, const uint8_t* d_bgr, int H, int W, 
  * multiple of 1 / reduCoeffi1 and the reference's float arithmetic is exact; the kernels keep Lr and the path sum as
  * uint16 fixed point: d_sum = reduCoeffi1 x (the float volume sgm() leaves in vm), exactly, and d_disp (nullable) =
  * gen_dispFromVm of it.  Half the HBM bytes of the float path per pass.  maxCost bounds the raw costs (71 for the
- * 71-bit census); SM_ERR_UNSUPPORTED unless reduCoeffi1 is a power of two and paths*(maxCost+3)*reduCoeffi1 <= 65535
+ * 71-bit census); SM_ERR_UNSUPPORTED unless reduCoeffi1 is a power of two and paths*(maxCost+3)*reduCoeffi1 <= 16000
  * (then: sm_vol_to_f32 + sm_sgm). */
 int sm_sgm_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint8_t* d_bgr, int H, int W, int D, int paths, int corDifThres,
                int reduCoeffi1, int maxCost, uint16_t* d_sum, int16_t* d_disp);

@@ -4,8 +4,8 @@
 // With integer costs every quantity of updateCost is a multiple of 1 / reduCoeffi1 (P1 = 1 or 1 / reduCoeffi1, P2 = 3
 // or 3 / reduCoeffi1), so for a power-of-two reduCoeffi1 the reference's float arithmetic is EXACT, and
 //       Lr * reduCoeffi1   is an integer  <= (Cmax + 3) * reduCoeffi1,
-// and the P-path sum times reduCoeffi1 fits 16 bits whenever P * (Cmax + 3) * reduCoeffi1 <= 65535 (Hamming costs:
-// Cmax = 71, 8 paths, reduCoeffi1 = 4 -> 2368).  The kernels below keep Lr and the path sum in that fixed point:
+// and the P-path sum times reduCoeffi1 fits 16 bits with room for an "outside" sentinel whenever
+// P * (Cmax + 3) * reduCoeffi1 <= 16000 (Hamming costs: Cmax = 71, 8 paths, reduCoeffi1 = 4 -> 2368).  The kernels below keep Lr and the path sum in that fixed point:
 // the volume is read as uint16 (2 B per disparity instead of 4), the sum is written as uint16 = reduCoeffi1 x the
 // reference's float sum, exactly, and gen_dispFromVm on it (first minimum) picks the same disparity.  Every volume
 // pass moves half the bytes of the float path (b = 2).
@@ -16,65 +16,66 @@
 #include "sgm_common.cuh"
 
 #define SGMU_WARPS 2
-#define SGMU_BIG 0x3fff0000   // "outside [0, D)": never the minimum, never overflows when P1 is added
+#define SGMU_BIG 0x3fffu          // "outside [0, D)": above every real value (<= 16000), survives + P1 without wrapping
+#define SGMU_BIG2 0x3fff3fffu
+#define SGMU_MAXSUM 16000         // bound on paths * (maxCost + 3) * reduCoeffi1 (see smi_sgm_u16_ok)
 
-template <int VPL, bool VEC>
-__device__ __forceinline__ void u16_load_run(const uint16_t* __restrict__ p, int d0, int D, int (&r)[VPL]) {
-  if (VEC && VPL >= 2) {
+// A run of VPL uint16 values of one lane as NW = VPL / 2 packed words (low half = lower disparity).  All arithmetic below
+// is the packed 16-bit integer SIMD of sm_100a (VIADD.16x2, VIMNMX.U16x2, VIADDMNMX.U16x2): two disparities per instruction.
+template <int NW, bool VEC>
+__device__ __forceinline__ void u16_load_run(const uint16_t* __restrict__ p, int d0, int D, uint32_t (&r)[NW]) {
+  if (VEC) {
     if (d0 < D) {   // D % VPL == 0: a run is entirely inside or outside [0, D)
-      if (VPL == 2) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(p + d0);
-        r[0] = w & 0xffff; r[1 % VPL] = w >> 16;
-      } else if (VPL == 4) {
-        const uint2 w = *reinterpret_cast<const uint2*>(p + d0);
-        r[0] = w.x & 0xffff; r[1 % VPL] = w.x >> 16; r[2 % VPL] = w.y & 0xffff; r[3 % VPL] = w.y >> 16;
-      } else {
+      if (NW == 1) r[0] = *reinterpret_cast<const uint32_t*>(p + d0);
+      else if (NW == 2) { const uint2 w = *reinterpret_cast<const uint2*>(p + d0); r[0] = w.x; r[1 % NW] = w.y; }
+      else {
 #pragma unroll
-        for (int k = 0; k < VPL; k += 8) {
-          const uint4 w = *reinterpret_cast<const uint4*>(p + d0 + k);
-          r[k] = w.x & 0xffff; r[(k + 1) % VPL] = w.x >> 16; r[(k + 2) % VPL] = w.y & 0xffff; r[(k + 3) % VPL] = w.y >> 16;
-          r[(k + 4) % VPL] = w.z & 0xffff; r[(k + 5) % VPL] = w.z >> 16; r[(k + 6) % VPL] = w.w & 0xffff; r[(k + 7) % VPL] = w.w >> 16;
+        for (int k = 0; k < NW; k += 4) {
+          const uint4 w = *reinterpret_cast<const uint4*>(p + d0 + 2 * k);
+          r[k] = w.x; r[(k + 1) % NW] = w.y; r[(k + 2) % NW] = w.z; r[(k + 3) % NW] = w.w;
         }
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < VPL; k++) r[k] = SGMU_BIG;
+      for (int k = 0; k < NW; k++) r[k] = SGMU_BIG2;
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < VPL; k++) r[k] = (d0 + k < D) ? (int)p[d0 + k] : SGMU_BIG;
+    for (int k = 0; k < NW; k++) {
+      const uint32_t lo = d0 + 2 * k < D ? p[d0 + 2 * k] : SGMU_BIG, hi = d0 + 2 * k + 1 < D ? p[d0 + 2 * k + 1] : SGMU_BIG;
+      r[k] = lo | (hi << 16);
+    }
   }
 }
 
-template <int VPL, bool VEC>
-__device__ __forceinline__ void u16_store_run(uint16_t* __restrict__ p, int d0, int D, const int (&r)[VPL]) {
-  if (VEC && VPL >= 2) {
+template <int NW, bool VEC>
+__device__ __forceinline__ void u16_store_run(uint16_t* __restrict__ p, int d0, int D, const uint32_t (&r)[NW]) {
+  if (VEC) {
     if (d0 < D) {
-      if (VPL == 2) {
-        *reinterpret_cast<uint32_t*>(p + d0) = (uint32_t)r[0] | ((uint32_t)r[1 % VPL] << 16);
-      } else if (VPL == 4) {
-        *reinterpret_cast<uint2*>(p + d0) = make_uint2((uint32_t)r[0] | ((uint32_t)r[1 % VPL] << 16), (uint32_t)r[2 % VPL] | ((uint32_t)r[3 % VPL] << 16));
-      } else {
+      if (NW == 1) *reinterpret_cast<uint32_t*>(p + d0) = r[0];
+      else if (NW == 2) *reinterpret_cast<uint2*>(p + d0) = make_uint2(r[0], r[1 % NW]);
+      else {
 #pragma unroll
-        for (int k = 0; k < VPL; k += 8)
-          *reinterpret_cast<uint4*>(p + d0 + k) =
-              make_uint4((uint32_t)r[k] | ((uint32_t)r[(k + 1) % VPL] << 16), (uint32_t)r[(k + 2) % VPL] | ((uint32_t)r[(k + 3) % VPL] << 16),
-                         (uint32_t)r[(k + 4) % VPL] | ((uint32_t)r[(k + 5) % VPL] << 16), (uint32_t)r[(k + 6) % VPL] | ((uint32_t)r[(k + 7) % VPL] << 16));
+        for (int k = 0; k < NW; k += 4)
+          *reinterpret_cast<uint4*>(p + d0 + 2 * k) = make_uint4(r[k], r[(k + 1) % NW], r[(k + 2) % NW], r[(k + 3) % NW]);
       }
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < VPL; k++)
-      if (d0 + k < D) p[d0 + k] = (uint16_t)r[k];
+    for (int k = 0; k < NW; k++) {
+      if (d0 + 2 * k < D) p[d0 + 2 * k] = (uint16_t)(r[k] & 0xffffu);
+      if (d0 + 2 * k + 1 < D) p[d0 + 2 * k + 1] = (uint16_t)(r[k] >> 16);
+    }
   }
 }
 
 // MODE 0: out = Lr.  1: out += Lr.  2: out += Lr and d_disp = gen_dispFromVm of the finished sum.  3: that WTA alone.
-// FIRST (MODE 0 only): the volume holds raw costs, which are scaled here; the sum volume is already in fixed point.
+// The cost volume holds raw costs (scaled here by the shift); the sum volume is in fixed point already.
 template <int VPL, int PF, bool VEC, int MODE>
 __global__ void __launch_bounds__(SGMU_WARPS * 32)
     k_sgm_path_u16(const uint16_t* __restrict__ vol, const uint32_t* __restrict__ pix, uint16_t* __restrict__ out, sgm_geom g,
-                   int D, int corDifThres, int scale, int16_t* __restrict__ disp) {
+                   int D, int corDifThres, int shift, int16_t* __restrict__ disp) {
+  constexpr int NW = VPL / 2;
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * SGMU_WARPS + (threadIdx.x >> 5);
   if (k >= g.nLines) return;
@@ -83,78 +84,86 @@ __global__ void __launch_bounds__(SGMU_WARPS * 32)
   const int d0 = lane * VPL;
   const long long pstep = (long long)g.mv * g.W + g.mu;
   long long p = (long long)v * g.W + u;
+  const uint32_t scale = 1u << shift;
+  // padding halves (d >= D) of a run: kept at BIG in the cost so they never win a minimum
+  uint32_t padMask[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++)
+    padMask[w] = (d0 + 2 * w < D ? 0u : 0xffffu) | (d0 + 2 * w + 1 < D ? 0u : 0xffff0000u);
 
-  int cpf[PF][VPL], spf[MODE >= 1 ? PF : 1][VPL];
-  uint32_t xpf[PF];
+  uint32_t cpf[PF][NW], spf[MODE >= 1 ? PF : 1][NW], xpf[PF];
 #pragma unroll
   for (int i = 0; i < PF; i++) {
     if (i < len) {
       const long long q = p + pstep * i;
-      u16_load_run<VPL, VEC>(vol + q * D, d0, D, cpf[i]);
-      if (MODE >= 1) u16_load_run<VPL, VEC>(out + q * D, d0, D, spf[i]);
+      u16_load_run<NW, VEC>(vol + q * D, d0, D, cpf[i]);
+      if (MODE >= 1) u16_load_run<NW, VEC>(out + q * D, d0, D, spf[i]);
       xpf[i] = pix[q];
     }
   }
-  int prev[VPL];
-  int minC = 0;
-  uint32_t xprev = 0;
+  uint32_t prev[NW];
+  uint32_t minC = 0, xprev = 0;
   for (int t0 = 0; t0 < len; t0 += PF) {
 #pragma unroll
     for (int i = 0; i < PF; i++) {
       const int t = t0 + i;
       if (t < len) {
-        int c[VPL], s[VPL], lr[VPL];
+        uint32_t c[NW], s[NW], lr[NW];
 #pragma unroll
-        for (int j = 0; j < VPL; j++) {
-          c[j] = d0 + j < D ? cpf[i][j] * scale : SGMU_BIG;       // raw cost -> fixed point
-          s[j] = MODE >= 1 ? spf[MODE >= 1 ? i : 0][j] : 0;
+        for (int w = 0; w < NW; w++) {
+          c[w] = ((cpf[i][w] << shift) & ~padMask[w]) | (SGMU_BIG2 & padMask[w]);   // raw cost -> fixed point (halves < 2^14)
+          s[w] = MODE >= 1 ? spf[MODE >= 1 ? i : 0][w] : 0u;
         }
         const uint32_t x = xpf[i];
         if (t + PF < len) {
           const long long q = p + pstep * PF;
-          u16_load_run<VPL, VEC>(vol + q * D, d0, D, cpf[i]);
-          if (MODE >= 1) u16_load_run<VPL, VEC>(out + q * D, d0, D, spf[MODE >= 1 ? i : 0]);
+          u16_load_run<NW, VEC>(vol + q * D, d0, D, cpf[i]);
+          if (MODE >= 1) u16_load_run<NW, VEC>(out + q * D, d0, D, spf[MODE >= 1 ? i : 0]);
           xpf[i] = pix[q];
         }
         if (t == 0) {
 #pragma unroll
-          for (int j = 0; j < VPL; j++) lr[j] = c[j];
+          for (int w = 0; w < NW; w++) lr[w] = c[w];
         } else {
+          // updateCost in fixed point: with a = Lr' - minC (>= 0),  Lr = C + min(a[d], a[d-1] + P1, a[d+1] + P1, P2)
           const bool step = (int)smd_absdiff_max3(x, xprev) > corDifThres;
-          const int P2 = step ? 3 : 3 * scale;                     // 3 / reduCoeffi1 resp. 3, times reduCoeffi1
-          const int P1 = (step ? 1 : scale) - minC;                // P1 -= minC
-          int lo = __shfl_up_sync(0xffffffffu, prev[VPL - 1], 1);
-          int hi = __shfl_down_sync(0xffffffffu, prev[0], 1);
-          if (lane == 0) lo = SGMU_BIG;
-          if (lane == 31) hi = SGMU_BIG;
+          const uint32_t P1 = (step ? 1u : scale) * 0x10001u, P2 = (step ? 3u : 3u * scale) * 0x10001u;
+          const uint32_t negm = ((0x10000u - minC) & 0xffffu) * 0x10001u;      // a = prev - minC, modulo 2^16 per half
+          uint32_t a[NW];
 #pragma unroll
-          for (int j = 0; j < VPL; j++) {
-            const int pm = j == 0 ? lo : prev[j - 1];
-            const int pp = j == VPL - 1 ? hi : prev[j + 1];
-            lr[j] = c[j] + min(min(prev[j] - minC, pm + P1), min(pp + P1, P2));
+          for (int w = 0; w < NW; w++) a[w] = __vadd2(prev[w], negm);
+          uint32_t lo = __shfl_up_sync(0xffffffffu, a[NW - 1], 1);   // ... | a'[d0-1] in its high half
+          uint32_t hi = __shfl_down_sync(0xffffffffu, a[0], 1);      // a'[d0+VPL] in its low half
+          if (lane == 0) lo = SGMU_BIG2;
+          if (lane == 31) hi = SGMU_BIG2;
+#pragma unroll
+          for (int w = 0; w < NW; w++) {
+            const uint32_t pm = __byte_perm(w == 0 ? lo : a[w - 1], a[w], 0x5432);        // {a[d-1] of both halves}
+            const uint32_t pp = __byte_perm(a[w], w == NW - 1 ? hi : a[w + 1], 0x5432);   // {a[d+1] of both halves}
+            const uint32_t t1 = __viaddmin_u16x2(pm, P1, a[w]);                            // min(a[d-1] + P1, a[d])
+            const uint32_t t2 = __viaddmin_u16x2(pp, P1, P2);                              // min(a[d+1] + P1, P2)
+            lr[w] = __vadd2(c[w], __vminu2(t1, t2));
           }
         }
-        int m = SGMU_BIG;
+        uint32_t m2 = SGMU_BIG2;
 #pragma unroll
-        for (int j = 0; j < VPL; j++) m = min(m, lr[j]);
-        minC = __reduce_min_sync(0xffffffffu, m);
+        for (int w = 0; w < NW; w++) m2 = __vminu2(m2, lr[w]);
+        minC = __reduce_min_sync(0xffffffffu, min(m2 & 0xffffu, m2 >> 16));
 #pragma unroll
-        for (int j = 0; j < VPL; j++) prev[j] = lr[j];
+        for (int w = 0; w < NW; w++) { prev[w] = lr[w]; s[w] = MODE >= 1 ? __vadd2(s[w], lr[w]) : lr[w]; }
         xprev = x;
-#pragma unroll
-        for (int j = 0; j < VPL; j++) s[j] = MODE >= 1 ? s[j] + lr[j] : lr[j];
         if (MODE >= 2) {
-          // gen_dispFromVm: strict '>' in increasing d -> the lowest d among the minima
-          int bm = 0x7fffffff, bd = 0x7fffffff;
+          // gen_dispFromVm: strict '>' in increasing d -> the lowest d among the minima: key = sum << 16 | d
+          uint32_t best = 0xffffffffu;
 #pragma unroll
-          for (int j = 0; j < VPL; j++)
-            if (d0 + j < D && bm > s[j]) { bm = s[j]; bd = d0 + j; }
-          const int gm = __reduce_min_sync(0xffffffffu, bm);
-          const int cand = bm == gm ? bd : 0x7fffffff;
-          const int best = __reduce_min_sync(0xffffffffu, cand);
-          if (lane == 0) disp[p] = (int16_t)(best == 0x7fffffff ? -1 : best);
+          for (int w = 0; w < NW; w++) {
+            if (d0 + 2 * w < D) best = min(best, (s[w] << 16) | (uint32_t)(d0 + 2 * w));
+            if (d0 + 2 * w + 1 < D) best = min(best, (s[w] & 0xffff0000u) | (uint32_t)(d0 + 2 * w + 1));
+          }
+          best = __reduce_min_sync(0xffffffffu, best);
+          if (lane == 0) disp[p] = (int16_t)(best & 0xffffu);
         }
-        if (MODE != 3) u16_store_run<VPL, VEC>(out + p * D, d0, D, s);
+        if (MODE != 3) u16_store_run<NW, VEC>(out + p * D, d0, D, s);
         p += pstep;
       }
     }
@@ -164,6 +173,9 @@ __global__ void __launch_bounds__(SGMU_WARPS * 32)
 template <int VPL, int PF, bool VEC>
 static int launch_u16(sm_ctx* ctx, const uint16_t* vol, const uint32_t* pix, uint16_t* out, const sgm_geom& g, int D, int thr,
                       int scale, int mode, int16_t* disp) {
+  int sh = 0;
+  while ((1 << sh) < scale) sh++;
+  scale = sh;   // the kernels take log2(reduCoeffi1)
   const int grid = sm_div_up(g.nLines, SGMU_WARPS);
   if (mode == 0) SM_LAUNCH(ctx, (k_sgm_path_u16<VPL, PF, VEC, 0>), grid, SGMU_WARPS * 32, 0, vol, pix, out, g, D, thr, scale, disp);
   else if (mode == 1) SM_LAUNCH(ctx, (k_sgm_path_u16<VPL, PF, VEC, 1>), grid, SGMU_WARPS * 32, 0, vol, pix, out, g, D, thr, scale, disp);
@@ -178,26 +190,25 @@ int smi_sgm_path_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, 
   g.H = H; g.W = W; g.mv = -SGM_RV[path]; g.mu = -SGM_RU[path];
   g.nLines = g.mv == 0 ? H : (g.mu == 0 ? W : W + H - 1);
   const int per = sm_div_up(D, 32);
-  const int vpl = per <= 1 ? 1 : (per <= 2 ? 2 : (per <= 4 ? 4 : (per <= 8 ? 8 : 16)));
-  const bool vec = vpl >= 2 && D % vpl == 0 && ((((uintptr_t)d_vol | (uintptr_t)d_out) & 15) == 0);
+  const int vpl = per <= 2 ? 2 : (per <= 4 ? 4 : (per <= 8 ? 8 : 16));
+  const bool vec = D % vpl == 0 && ((((uintptr_t)d_vol | (uintptr_t)d_out) & 15) == 0);
   switch (vpl) {
-    case 1: return launch_u16<1, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
     case 2: return vec ? launch_u16<2, 8, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp)
                        : launch_u16<2, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
     case 4: return vec ? launch_u16<4, 8, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp)
                        : launch_u16<4, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
     case 8: return vec ? launch_u16<8, 8, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp)
-                       : launch_u16<8, 4, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
-    default: return vec ? launch_u16<16, 4, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp)
-                        : launch_u16<16, 2, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
+                       : launch_u16<8, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
+    default: return vec ? launch_u16<16, 8, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp)
+                        : launch_u16<16, 4, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
   }
 }
 
-// The fixed point holds iff reduCoeffi1 is a power of two and paths * (maxCost + 3) * reduCoeffi1 fits 16 bits.
+// The fixed point holds iff reduCoeffi1 is a power of two and paths * (maxCost + 3) * reduCoeffi1 stays below the sentinel.
 bool smi_sgm_u16_ok(int D, int paths, int reduCoeffi1, int maxCost) {
   if (D < 1 || D > 512 || paths < 1 || paths > 8 || reduCoeffi1 < 1 || reduCoeffi1 > 64) return false;
   if (reduCoeffi1 & (reduCoeffi1 - 1)) return false;
-  return (long long)paths * (maxCost + 3) * reduCoeffi1 <= 65535;
+  return (long long)paths * (maxCost + 3) * reduCoeffi1 <= SGMU_MAXSUM;   // headroom below the "outside" sentinel 0x3fff
 }
 
 int smi_sgm_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, int H, int W, int D, int paths, int corDifThres,
@@ -235,7 +246,7 @@ extern "C" int sm_sgm_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint8_t* d_b
                           int corDifThres, int reduCoeffi1, int maxCost, uint16_t* d_sum, int16_t* d_disp) {
   SM_CHECK_ARG(ctx && d_vol && d_bgr && d_sum && H > 0 && W > 0 && (const void*)d_vol != (const void*)d_sum);
   if (!smi_sgm_u16_ok(D, paths, reduCoeffi1, maxCost)) {
-    sm_set_error("sm_sgm_u16: needs a power-of-two reduCoeffi1 and paths * (maxCost + 3) * reduCoeffi1 <= 65535 "
+    sm_set_error("sm_sgm_u16: needs a power-of-two reduCoeffi1 and paths * (maxCost + 3) * reduCoeffi1 <= 16000 "
                  "(got D %d, paths %d, reduCoeffi1 %d, maxCost %d); use sm_vol_to_f32 + sm_sgm", D, paths, reduCoeffi1, maxCost);
     return SM_ERR_UNSUPPORTED;
   }
