@@ -35,6 +35,9 @@ struct sm_ctx {
   int tab_codeLen = -1;
   float h_tab[767 + 72];  // host staging of those tables (must outlive the async upload)
   int num_sms = SM_NUM_SMS;
+  // edge hand-off buffers of the grouped SGM sweeps: armed (all sentinel) up to this many bytes at this address
+  void* sgm_edge_ptr = nullptr;
+  size_t sgm_edge_armed = 0;
 };
 
 void sm_set_error(const char* fmt, ...);
@@ -92,9 +95,13 @@ static inline int sm_div_up(long long a, long long b) { return (int)((a + b - 1)
 // ---- internal cross-file helpers ------------------------------------------------
 // BGR u8x3 interleaved -> one uint32 per pixel (b | g<<8 | r<<16), 4-byte loads.
 int smi_pack_bgr(sm_ctx* ctx, const uint8_t* d_bgr, long long npix, uint32_t* d_out);
-// arms [H][W][5] u16 -> three maps of one uint32 per entry over rows of W + 2*PAD entries (pixel u sits at index PAD + u,
-// the PAD entries on either side are zero = partner outside the image): the byte map {left, right, up, down}, the
-// armH plane (left | right << 16, x 128) and the armV plane (up | down << 16, x 128): d_out holds 3 * H * (W + 2*PAD) words.
+// arms [H][W][5] u16 -> one uint2 per pixel {armH = left | right<<16, armV = up | down<<16} in rows of W + 2*PAD
+// entries: pixel u sits at index PAD + u and the PAD entries on either side are zero (partner outside the image).
+// Followed by the armH plane and the armV plane (one u32 per entry each): d_out holds 4 * H * (W + 2*PAD) words.
+// (Tried in round 2 and dropped: one uint32 {left, right, up, down} per pixel for the second passes -- VIMNMX.U8x4 +
+// IDP.4A + PRMT, half the staged arm bytes: bit-exact but SLOWER at equal occupancy, V second 1.66 -> 1.77 ms, H second
+// 1.29 -> 1.33 ms at 1080p D=256, and the freed shared memory let a sixth warp in, which costs the vertical second pass
+// its L1 carve-out: 2.11 ms.  profiles/r02_cbca_experiments.md.)
 int smi_pack_arms(sm_ctx* ctx, const uint16_t* d_arms, int H, int W, int PAD, uint32_t* d_out);
 static inline int smi_arm_pad(int D) { return (D + 31) / 32 * 32 + 4; }   // +4: 16-byte aligned supersets stay in the row
 // the two exp lookup tables of the fused AD-Census kernel (see cost.cu)

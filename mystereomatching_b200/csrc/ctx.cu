@@ -229,16 +229,15 @@ __global__ void k_pack_arms(const uint16_t* __restrict__ arms, int H, int W, int
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     const int v = (int)(i / Wp), u = (int)(i - (long long)v * Wp) - PAD;
-    uint32_t wh = 0, wv = 0, wb = 0;
+    uint32_t wh = 0, wv = 0;
     if (u >= 0 && u < W) {
       const uint16_t* a = arms + 5 * ((size_t)v * W + u);
       wh = (uint32_t)a[0] | ((uint32_t)a[1] << 16);
       wv = (uint32_t)a[2] | ((uint32_t)a[3] << 16);
-      wb = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16) | ((uint32_t)a[3] << 24);   // arms <= 255
     }
-    out[i] = wb;                                             // byte map {left, right, up, down} (second passes)
-    out[n + i] = wh << 7;                                    // armH plane, lengths x 128 (ring bytes of the first pass)
-    out[2 * n + i] = wv << 7;                                // armV plane, likewise
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(wh, wv);   // pair map
+    out[2 * n + i] = wh << 7;                                // armH plane, lengths x 128 (ring bytes of the first pass)
+    out[3 * n + i] = wv << 7;                                // armV plane, likewise
   }
 }
 

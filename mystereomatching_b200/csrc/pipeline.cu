@@ -103,7 +103,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->own_gray[i], npix);
     pl->bgr[i] = pl->own_bgr[i]; pl->gray[i] = pl->own_gray[i];
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->pix[i], npix * 4);
-    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], (size_t)H * (W + 2 * smi_arm_pad(pl->D)) * 12);
+    if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->armpk[i], (size_t)H * (W + 2 * smi_arm_pad(pl->D)) * 16);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->cen[i], npix * 8 * nw);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->arms[i], npix * 5 * 2);
     if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->disp[i], npix * 2);

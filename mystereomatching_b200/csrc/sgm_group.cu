@@ -176,19 +176,28 @@ __device__ __forceinline__ void g_edge_issue(const float* src, int nq, int D, g_
   }
   e.m = g_ld_relaxed4(src + D);   // src is lane-relative: the minimum sits at D - d0
 }
+// The consumer also RE-ARMS what it has read: every word goes back to the sentinel, so the buffers are all-sentinel
+// again when the launch ends and the next launch needs no fill (each word is written once by its producer and read by
+// exactly one consumer lane; the producer's next write to it happens in a later launch).
 template <int VPL>
 __device__ __forceinline__ void g_edge_finish(const float* src, int nq, int D, const g_edge_regs<VPL>& e, float (&pr)[VPL], float& pm,
                                               int& polls) {
+  float* w = const_cast<float*>(src);
 #pragma unroll
   for (int q = 0; q < VPL / 4; q++) {
     uint4 t = e.t[q];
     while (t.x == SGMG_SENTINEL || t.y == SGMG_SENTINEL || t.z == SGMG_SENTINEL || t.w == SGMG_SENTINEL) { t = g_ld_relaxed16(src + q * 4); polls++; }
     pr[4 * q] = __uint_as_float(t.x); pr[4 * q + 1] = __uint_as_float(t.y);
     pr[4 * q + 2] = __uint_as_float(t.z); pr[4 * q + 3] = __uint_as_float(t.w);
+    if (q < nq) __stcg(reinterpret_cast<uint4*>(w + q * 4), make_uint4(SGMG_SENTINEL, SGMG_SENTINEL, SGMG_SENTINEL, SGMG_SENTINEL));
   }
+  // the row minimum is ONE word all lanes read: nobody may re-arm it before everybody has it
   uint32_t m = e.m;
-  while (m == SGMG_SENTINEL) m = g_ld_relaxed4(src + D);
+  while (__any_sync(0xffffffffu, m == SGMG_SENTINEL)) {
+    if (m == SGMG_SENTINEL) m = g_ld_relaxed4(src + D);
+  }
   pm = __uint_as_float(m);
+  if ((threadIdx.x & 31) == 0) __stcg(reinterpret_cast<uint32_t*>(w + D), SGMG_SENTINEL);
 }
 
 // UP = 0: rows 0 .. H-1, paths {1, 6, 7} (predecessor columns u, u+1, u-1).
@@ -324,7 +333,7 @@ __global__ void __launch_bounds__(448, NV)
         g_strow<VPL, XQ>(myB, nq, c); g_strow<VPL, XQ>(myC, nq, c);
         if (lane == 0) { g_sts4(myMinB, m); g_sts4(myMinC, m); }
       } else {
-        if (nbrCta) {
+        if (nbrCta && H > 1) {   // (the last row of a sweep is never read: not published, see g_edge_finish)
 #pragma unroll
           for (int q = 0; q < VPL / 4; q++)
             if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]));
@@ -366,10 +375,12 @@ __global__ void __launch_bounds__(448, NV)
       g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
       minA = mA;
       if (nbrCta) {
+        if (r + 1 < H) {   // the neighbour reads this row at ITS row r + 1
 #pragma unroll
-        for (int q = 0; q < VPL / 4; q++)
-          if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(lrN[4 * q], lrN[4 * q + 1], lrN[4 * q + 2], lrN[4 * q + 3]));
-        if (lane == 0) __stcg(pubRow + D, mN);
+          for (int q = 0; q < VPL / 4; q++)
+            if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(lrN[4 * q], lrN[4 * q + 1], lrN[4 * q + 2], lrN[4 * q + 3]));
+          if (lane == 0) __stcg(pubRow + D, mN);
+        }
         if (tr && lane == 0) tr[0] = g_now();
         float prF[VPL], pmF;
         int polls = 0;
@@ -447,7 +458,13 @@ static int launch_group(sm_ctx* ctx, const float* const* vol, const uint32_t* co
   const size_t rowsBytes = (size_t)nb * H * Dp * sizeof(float);
   void* p;
   SM_TRY(sm_scratch_get(ctx, SM_SCR_SGMEDGE, 2 * NV * rowsBytes, &p));
-  SM_CUDA(cudaMemsetAsync(p, 0xFF, 2 * NV * rowsBytes, ctx->stream));   // sentinel: "row not published yet"
+  // sentinel fill ("row not published yet") only for memory that has never been armed: the consumers restore the
+  // sentinel in every word they read, so a completed launch leaves the buffers armed for the next one
+  if (ctx->sgm_edge_ptr != p || ctx->sgm_edge_armed < 2 * NV * rowsBytes) {
+    SM_CUDA(cudaMemsetAsync(p, 0xFF, 2 * NV * rowsBytes, ctx->stream));
+    ctx->sgm_edge_ptr = p;
+    ctx->sgm_edge_armed = 2 * NV * rowsBytes;
+  }
   sgmg_view v[2];
   for (int i = 0; i < 2; i++) {
     const int k = i < NV ? i : 0;
@@ -456,7 +473,11 @@ static int launch_group(sm_ctx* ctx, const float* const* vol, const uint32_t* co
     v[i].rowsM = (float*)((uint8_t*)p + (size_t)(2 * k + 1) * rowsBytes);
   }
   unsigned long long* trace = nullptr;
+#ifdef SM_SGMG_TRACE_BUILD   // diagnostics build only (scripts/sgmg_timeline.py): time stamps of the hand-offs of one launch
   const char* traceFile = NV == 1 ? getenv("SM_SGMG_TRACE") : nullptr;
+#else
+  const char* traceFile = nullptr;
+#endif
   const size_t traceBytes = ((size_t)nb * 2 * H * 4 + 16 * 32 * 8) * sizeof(unsigned long long);
   if (traceFile) { SM_CUDA(cudaMalloc((void**)&trace, traceBytes)); SM_CUDA(cudaMemsetAsync(trace, 0, traceBytes, ctx->stream)); }
   void* args[] = {(void*)&v[0], (void*)&v[1], (void*)&H, (void*)&W, (void*)&D, (void*)&corDifThres, (void*)&redu, (void*)&Dp,
@@ -468,7 +489,14 @@ static int launch_group(sm_ctx* ctx, const float* const* vol, const uint32_t* co
   int perSM = 0;
   SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, CW * 32, smem));
   if (perSM * ctx->num_sms < NV * nb) return SM_ERR_UNSUPPORTED;   // the CTAs wait on each other: all must be resident
-  SM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(NV * nb), dim3(CW * 32), args, smem, ctx->stream));
+  {
+    const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(NV * nb), dim3(CW * 32), args, smem, ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->sgm_edge_ptr = nullptr;   // state of the edge buffers unknown: fill again next time
+      sm_set_error("%s:%d: cudaLaunchCooperativeKernel -> %s", __FILE__, __LINE__, cudaGetErrorString(e));
+      return SM_ERR_CUDA;
+    }
+  }
   ctx->launches++;
   if (traceFile) {   // diagnostics only: synchronous dump of the hand-off time stamps of this launch
     std::vector<unsigned long long> h(traceBytes / 8);
