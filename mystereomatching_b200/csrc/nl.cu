@@ -12,18 +12,19 @@
 // NL/qx_mst_kruskals_image.cpp:46-69).  Any algorithm that uses the same total order yields the same tree; here it
 // is Boruvka: every component picks its minimum outgoing edge by 64-bit atomicMin on that key, components hook
 // (mutual picks keep the smaller label as the root), labels are flattened by pointer jumping; <= log2(N) rounds.
-// The tree is then rooted at pixel 0 (NL/qx_mst_kruskals_image.cpp:233) by a level-synchronous BFS inside ONE
-// kernel running as a single thread-block cluster (hardware cluster barrier per level), which also yields the
-// per-level node lists the filter needs.
+// The tree is then rooted at pixel 0 (NL/qx_mst_kruskals_image.cpp:233) WITHOUT a level-by-level walk: parent, depth
+// and the level order follow from the tree's Euler tour by list ranking (pointer jumping), an inclusive scan and a
+// stable sort by depth (nl_root_euler; O(log N) data-parallel steps).
 // A node's children are kept in increasing key order, which is the order Kruskal appended them to the adjacency
 // list and therefore the order in which the reference's leaf-to-root pass adds them (bit-identical f64 sums).
 //
-// Filter.  Level-synchronous, one persistent kernel (a single 8-CTA cluster): leaf-to-root over the levels deepest-1 .. 0
-// (A[p] = cost[p] + sum_children w(c) * A[c], children already final), then root-to-leaf over levels 1 .. deepest
-// (out[v] = w * (out[parent] - w * A[v]) + A[v], written over A[v], which no one needs any more).  Threads run
-// along (node, d) with d fastest, so every access is a coalesced run of D doubles.  The all-ones volume of
+// Filter.  Leaf-to-root over the levels deepest-1 .. 0 (A[p] = cost[p] + sum_children w(c) * A[c], children already
+// final), then root-to-leaf over levels 1 .. deepest (out[v] = w * (out[parent] - w * A[v]) + A[v], written over A[v]).
+// Planes never interact, so the work volume is split BY PLANE: one CTA per plane walks all levels on one SM with
+// __syncthreads between levels (k_tf_cta_fast / k_tf_cta; any barrier across SMs costs 2.6 us per level), the
+// level-ordered records and the plane's values streamed through shared memory by the TMA unit.  The all-ones volume of
 // StereoMatching::NL has identical planes, so its filter result is ONE extra plane (index D) carried through the
-// same two sweeps; the division happens in the final conversion.  Time is bound by tree depth x barrier latency,
+// same two sweeps; the division happens in the final conversion.  Time is bound by tree depth x per-level latency,
 // not by bandwidth.
 #include <math.h>
 
@@ -177,8 +178,6 @@ __global__ void k_tree_adj(int H, int W, const uint8_t* __restrict__ ew, const u
 // next).  Measured on B200: any barrier ACROSS SMs costs 2.6-2.8 us per level (hardware cluster barrier of 8 CTAs and
 // a grid-wide atomic barrier alike: store acknowledge + release/acquire + dependent L2 load).  Both kernels therefore
 // keep every dependency inside ONE SM and synchronise with __syncthreads only:
-//   * k_tree_bfs: a single CTA, the frontier as (node, parent) pairs in shared memory -> one dependent global access
-//     (the adjacency record) per level, ~1.0 us per level;
 //   * k_tf_sweeps: the volume is split by PLANE (planes never interact), one CTA per plane walking all levels, the
 //     values of the adjacent level in shared memory, records and own values fetched four levels ahead, level bounds in
 //     shared memory: ~0.9 us per level (what remains is the dependent instruction chain of the few working threads).
@@ -193,65 +192,8 @@ struct nl_sync {
 };
 
 
-// BFS from pixel 0 over the tree adjacency: parent, depth (rank), weight of the edge to the parent, the node list
-// grouped by level (order) and the level boundaries (level_start[l] .. level_start[l+1]).  One barrier per level:
-// the per-level append counters rotate over three slots so a counter is reset two levels after its last reader.
-// ONE CTA: a level holds tens of nodes on average (image MSTs are deep: 4366 levels for 640x480), so the time is
-// (levels) x (hand-off latency), and a CTA barrier plus an L1/L2 access on one SM (~0.5 us per level) beats any
-// barrier across SMs (cluster or grid: ~2.6 us per level, measured).
-#define NL_BFS_FCAP 8192   // frontier entries (node, parent) kept in shared memory per level (2 x 64 KB)
-__global__ void __launch_bounds__(NL_CTA)
-    k_tree_bfs(int N, const int4* __restrict__ nbr, const uchar4* __restrict__ nbw, const uint8_t* __restrict__ deg,
-               int* parent, uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* s) {
-  // The frontier of a level lives in shared memory as (node, parent) pairs, so a level costs ONE dependent global
-  // access (the node's adjacency record) instead of order -> parent -> adjacency.
-  extern __shared__ int2 fr[];   // [2][NL_BFS_FCAP]
-  __shared__ int cnt[2];
-  const int tid = threadIdx.x, nth = blockDim.x;
-  if (tid == 0) {
-    parent[0] = 0; wpar[0] = 0; rank[0] = 0; order[0] = 0; level_start[0] = 0;
-    cnt[0] = 0; cnt[1] = 0;
-    fr[0] = make_int2(0, 0);
-  }
-  __syncthreads();
-  int head = 0, tail = 1, level = 0;
-  while (head < tail) {
-    int* cnt_next = &cnt[(level + 1) & 1];
-    const int2* cur = fr + (size_t)(level & 1) * NL_BFS_FCAP;
-    int2* nxt = fr + (size_t)((level + 1) & 1) * NL_BFS_FCAP;
-    for (int i = tid; i < tail - head; i += nth) {
-      int v, p;
-      if (i < NL_BFS_FCAP) { const int2 e = cur[i]; v = e.x; p = e.y; }
-      else { v = order[head + i]; p = parent[v]; }
-      const int n = deg[v];
-      const int4 nb = nbr[v];
-      const uchar4 nw = nbw[v];
-      const int c4[4] = {nb.x, nb.y, nb.z, nb.w};
-      const uint8_t w4[4] = {nw.x, nw.y, nw.z, nw.w};
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (k >= n) continue;
-        const int c = c4[k];
-        if (c == p) continue;   // the root's parent is itself and never appears among its neighbours
-        parent[c] = v;
-        rank[c] = level + 1;
-        wpar[c] = w4[k];
-        const int slot = atomicAdd(cnt_next, 1);
-        order[tail + slot] = c;
-        if (slot < NL_BFS_FCAP) nxt[slot] = make_int2(c, v);
-      }
-    }
-    __syncthreads();                        // all appends of this level are done and visible
-    const int added = *cnt_next;
-    head = tail; tail += added; level++;
-    if (tid == 0) { level_start[level] = head; cnt[level & 1 ^ 1] = 0; }   // the counter of the level after next
-    __syncthreads();
-  }
-  if (tid == 0) { s->nlevels = level; level_start[level] = head; }
-}
-
 // ------------------------------------------------------------------ rooting without a level-by-level walk
-// The BFS above costs one dependent global access per LEVEL (0.75 us x 4366 levels at 640x480, x 17051 at 1080p).  The
+// A level-by-level BFS costs one dependent global access per LEVEL (0.75 us x 4366 levels at 640x480, x 17051 at 1080p).  The
 // same parent / depth / level order follow from the tree's EULER TOUR in O(log N) data-parallel steps:
 //   * directed edge (u -> k-th neighbour v) has id 4u + k; its successor in the tour is (v -> the neighbour after u in
 //     v's adjacency list, cyclically); the tour starts with edge (0 -> first neighbour of 0), the edge whose successor
@@ -323,7 +265,7 @@ __global__ void k_et_keys(int N, int T, const int* __restrict__ scan, const int*
 }
 
 // rooted tree from the adjacency by the Euler tour; returns SM_OK and fills parent / wpar / rank / order /
-// level_start / sync->nlevels exactly as k_tree_bfs does (order: grouped by level)
+// level_start / sync->nlevels (order: grouped by level)
 struct nl_tree;
 static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw, const uint8_t* deg, int* parent,
                          uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* sync);
@@ -1085,18 +1027,9 @@ static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn
   }
   SM_LAUNCH(ctx, k_tree_adj, gN, TB, 0, H, W, ew, inMST, nbr, nbw, deg);
   SM_CUDA(cudaMemsetAsync(t.sync, 0, sizeof(nl_sync), ctx->stream));
-  static const int euler_env = getenv("SM_NL_EULER") ? atoi(getenv("SM_NL_EULER")) : 1;   // 0: the level-by-level BFS
-  if (euler_env) return nl_root_euler(ctx, N, nbr, nbw, deg, t.parent, t.wpar, t.rank, t.order, t.level_start, t.sync);
-  {
-    void* args[] = {(void*)&N, (void*)&nbr, (void*)&nbw, (void*)&deg, (void*)&t.parent, (void*)&t.wpar, (void*)&t.rank,
-                    (void*)&t.order, (void*)&t.level_start, (void*)&t.sync};
-    const size_t smem = 2 * (size_t)NL_BFS_FCAP * sizeof(int2);
-    SM_CUDA(cudaFuncSetAttribute(k_tree_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const int bfs_cta = getenv("SM_NL_BFS_CTA") ? atoi(getenv("SM_NL_BFS_CTA")) : 256;   // measured (MST + rooting): 1024 -> 5.56 ms, 512 -> 5.28, 256 -> 5.15, 128 -> 5.41
-    SM_CUDA(cudaLaunchKernel((const void*)k_tree_bfs, dim3(1), dim3(bfs_cta), args, smem, ctx->stream));
-    ctx->launches++;
-  }
-  return SM_OK;
+  // rooting: Euler tour + list ranking (nl_root_euler).  (The level-by-level BFS it replaced -- one CTA, frontier in shared
+  // memory, 5.15 ms for MST + rooting at 640x480 against 0.78 ms -- is gone; DESIGN.md keeps the numbers.)
+  return nl_root_euler(ctx, N, nbr, nbw, deg, t.parent, t.wpar, t.rank, t.order, t.level_start, t.sync);
 }
 
 // scratch layout of the tree arrays the filter derives (children, levels, barrier state)
@@ -1153,9 +1086,8 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
   SM_LAUNCH(ctx, k_tf_records, gr, TB, 0, n, t.order, t.pos, t.rank, t.level_start, t.parent, t.wpar, t.child, t.nchild,
             t.rcp, t.rcw, t.rnc, t.rpp, t.rw, t.rup, t.rdn);
   if (d_vol) SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp, t.order);
-  static const int tfw_env = getenv("SM_NL_TF_STREAM") ? atoi(getenv("SM_NL_TF_STREAM")) : 1;   // 0: k_tf_sweeps
   const size_t tfwFixed = 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40;
-  if (d_vol && tfw_env) {
+  if (d_vol) {
     // one CTA per plane, records and values streamed (k_tf_cta); level bounds in shared memory as far as they fit
     int h_nlev = 0;
     SM_CUDA(cudaMemcpyAsync(&h_nlev, &t.sync->nlevels, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1166,11 +1098,10 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     int n_ = (int)N, dp = Dp;
     void* args[] = {(void*)&a, (void*)&n_, (void*)&dp, (void*)&lsCap, (void*)&t.level_start, (void*)&t.rup, (void*)&t.rdn,
                     (void*)&d_tab, (void*)&t.sync};
-    static const int tfw_fast = getenv("SM_NL_TF_FAST") ? atoi(getenv("SM_NL_TF_FAST")) : 1;   // 0: k_tf_cta (general code at every level)
-    const void* fn = (tfw_fast && h_nlev < lsCap && N % 2 == 0) ? (const void*)k_tf_cta_fast : (const void*)k_tf_cta;
+    // the lean level loop needs every level bound in shared memory and an even N; otherwise the general code at every level
+    const void* fn = (h_nlev < lsCap && N % 2 == 0) ? (const void*)k_tf_cta_fast : (const void*)k_tf_cta;
     SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const int tfw_t = getenv("SM_NL_TFW_T") ? atoi(getenv("SM_NL_TFW_T")) : TFW_T;   // tuning switch (<= 256)
-    SM_CUDA(cudaLaunchKernel(fn, dim3(Dp), dim3(tfw_t), args, smem, ctx->stream));
+    SM_CUDA(cudaLaunchKernel(fn, dim3(Dp), dim3(TFW_T), args, smem, ctx->stream));
     ctx->launches++;
   } else {
     // one CTA per plane while there are SMs for them, else the same number of planes for every CTA
@@ -1186,8 +1117,8 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     void* args[] = {(void*)&a, (void*)&sn, (void*)&sd, (void*)&dp, (void*)&pp, (void*)&cp, (void*)&t.order, (void*)&t.level_start,
                     (void*)&t.rcp, (void*)&t.rcw, (void*)&t.rnc, (void*)&t.rpp, (void*)&t.rw, (void*)&d_tab, (void*)&t.sync};
     SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const int tf_cta = getenv("SM_NL_TF_CTA") ? atoi(getenv("SM_NL_TF_CTA")) : 256;   // measured 640x480 D=64: 512 -> 8.12 ms, 256 -> 7.78, 128 -> 8.31, 64 -> 11.07
-    SM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(tf_cta), args, smem, ctx->stream));
+    // 256 threads: measured at 640x480 D=64: 512 -> 8.12 ms, 256 -> 7.78, 128 -> 8.31, 64 -> 11.07
+    SM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(256), args, smem, ctx->stream));
     ctx->launches++;
   }
   if (d_vol) SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp, t.pos);

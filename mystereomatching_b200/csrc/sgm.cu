@@ -568,16 +568,13 @@ int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix,
   const float redu = (float)reduCoeffi1;
   const bool vec = (D % 4 == 0) && (((uintptr_t)d_vol | (uintptr_t)d_out) % 16 == 0);
   const int vpl = D <= 32 ? 1 : D <= 64 ? 2 : D <= 128 ? 4 : D <= 256 ? 8 : 16;
-  static const int staged_env = getenv("SM_SGM_STAGED") ? atoi(getenv("SM_SGM_STAGED")) : 2;   // tuning switch
-  // small frames (few scan lines): the cp.async staged kernel in every direction, runs of >= 4 disparities per lane
-  static const int small_env = getenv("SM_SGM_SMALL_LINES") ? atoi(getenv("SM_SGM_SMALL_LINES")) : 1024;   // 0: off
-  if (vec && ((uintptr_t)d_pix & 3) == 0 && g.nLines <= small_env) {
+  // small frames (<= 1024 scan lines): the cp.async staged kernel in every direction, runs of >= 4 disparities per lane
+  if (vec && ((uintptr_t)d_pix & 3) == 0 && g.nLines <= 1024) {
     // 32 < D <= 64: runs of 2, all 32 lanes at work (runs of 4 leave half the warp idle and cost ~25 more instructions
     // per pixel); the TMA row kernel needs runs of >= 4
-    static const int v2_env = getenv("SM_SGM_SMALL_V2") ? atoi(getenv("SM_SGM_SMALL_V2")) : 1;
-    if (vpl == 2 && v2_env) return launch_sgm_s<2>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
+    if (vpl == 2) return launch_sgm_s<2>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
     const int vs = max(vpl, 4);
-    const bool tma = g.mv == 0 && staged_env == 2 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0;
+    const bool tma = g.mv == 0 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0;
     if (!tma) {
       if (vs == 4) return launch_sgm_s<4>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
       if (vs == 8) return launch_sgm_s<8>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, redu, mode, d_disp);
@@ -585,13 +582,13 @@ int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix,
     }
     if (vs == 4) return launch_sgm_t<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
   }
-  // horizontal: few, contiguous lines.  2 = TMA bulk staging, 1 = cp.async staging, 0 = the generic kernel
-  if (g.mv == 0 && vec && vpl >= 4 && staged_env == 2 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0) {
+  // horizontal: few, contiguous lines: TMA bulk staging when the row tiles into groups of SGM_TK pixels, else cp.async staging
+  if (g.mv == 0 && vec && vpl >= 4 && W % SGM_TK == 0 && ((uintptr_t)d_pix & 15) == 0) {
     if (vpl == 4) return launch_sgm_t<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
     if (vpl == 8) return launch_sgm_t<8>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
     return launch_sgm_t<16>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
   }
-  if (g.mv == 0 && vec && vpl >= 4 && staged_env) {   // cp.async staged variant
+  if (g.mv == 0 && vec && vpl >= 4) {   // cp.async staged variant (W % SGM_TK != 0)
     if (vpl == 4) return launch_sgm_h<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
     if (vpl == 8) return launch_sgm_h<8>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
     return launch_sgm_h<16>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, redu, mode, d_disp);
