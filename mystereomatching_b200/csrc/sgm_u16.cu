@@ -69,6 +69,57 @@ __device__ __forceinline__ void u16_store_run(uint16_t* __restrict__ p, int d0, 
   }
 }
 
+// One pixel of the recurrence, in fixed point: with a = Lr' - minC (>= 0),
+//   Lr = C + min(a[d], a[d-1] + P1, a[d+1] + P1, P2)       (updateCost<T>, stereoMatching.h:2205-2280)
+// c: scaled costs (padding halves = BIG), s: the path sum so far (MODE >= 1), prev / minC / xprev: state of the path.
+template <int NW, int MODE>
+__device__ __forceinline__ void u16_step(bool first, const uint32_t (&c)[NW], uint32_t (&s)[NW], uint32_t (&prev)[NW],
+                                         uint32_t& minC, uint32_t x, uint32_t& xprev, int d0, int D, int corDifThres,
+                                         uint32_t scale, int lane, int16_t* __restrict__ disp, long long p) {
+  uint32_t lr[NW];
+  if (first) {
+#pragma unroll
+    for (int w = 0; w < NW; w++) lr[w] = c[w];
+  } else {
+    const bool step = (int)smd_absdiff_max3(x, xprev) > corDifThres;
+    const uint32_t P1 = (step ? 1u : scale) * 0x10001u, P2 = (step ? 3u : 3u * scale) * 0x10001u;
+    const uint32_t negm = ((0x10000u - minC) & 0xffffu) * 0x10001u;      // a = prev - minC, modulo 2^16 per half
+    uint32_t a[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) a[w] = __vadd2(prev[w], negm);
+    uint32_t lo = __shfl_up_sync(0xffffffffu, a[NW - 1], 1);   // a'[d0-1] in its high half
+    uint32_t hi = __shfl_down_sync(0xffffffffu, a[0], 1);      // a'[d0+VPL] in its low half
+    if (lane == 0) lo = SGMU_BIG2;
+    if (lane == 31) hi = SGMU_BIG2;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      const uint32_t pm = __byte_perm(w == 0 ? lo : a[w - 1], a[w], 0x5432);        // {a[d-1] of both halves}
+      const uint32_t pp = __byte_perm(a[w], w == NW - 1 ? hi : a[w + 1], 0x5432);   // {a[d+1] of both halves}
+      const uint32_t t1 = __viaddmin_u16x2(pm, P1, a[w]);                            // min(a[d-1] + P1, a[d])
+      const uint32_t t2 = __viaddmin_u16x2(pp, P1, P2);                              // min(a[d+1] + P1, P2)
+      lr[w] = __vadd2(c[w], __vminu2(t1, t2));
+    }
+  }
+  uint32_t m2 = SGMU_BIG2;
+#pragma unroll
+  for (int w = 0; w < NW; w++) m2 = __vminu2(m2, lr[w]);
+  minC = __reduce_min_sync(0xffffffffu, min(m2 & 0xffffu, m2 >> 16));
+#pragma unroll
+  for (int w = 0; w < NW; w++) { prev[w] = lr[w]; s[w] = MODE >= 1 ? __vadd2(s[w], lr[w]) : lr[w]; }
+  xprev = x;
+  if (MODE >= 2) {
+    // gen_dispFromVm: strict '>' in increasing d -> the lowest d among the minima: key = sum << 16 | d
+    uint32_t best = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      if (d0 + 2 * w < D) best = min(best, (s[w] << 16) | (uint32_t)(d0 + 2 * w));
+      if (d0 + 2 * w + 1 < D) best = min(best, (s[w] & 0xffff0000u) | (uint32_t)(d0 + 2 * w + 1));
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0) disp[p] = (int16_t)(best & 0xffffu);
+  }
+}
+
 // MODE 0: out = Lr.  1: out += Lr.  2: out += Lr and d_disp = gen_dispFromVm of the finished sum.  3: that WTA alone.
 // The cost volume holds raw costs (scaled here by the shift); the sum volume is in fixed point already.
 template <int VPL, int PF, bool VEC, int MODE>
@@ -108,7 +159,7 @@ __global__ void __launch_bounds__(SGMU_WARPS * 32)
     for (int i = 0; i < PF; i++) {
       const int t = t0 + i;
       if (t < len) {
-        uint32_t c[NW], s[NW], lr[NW];
+        uint32_t c[NW], s[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
           c[w] = ((cpf[i][w] << shift) & ~padMask[w]) | (SGMU_BIG2 & padMask[w]);   // raw cost -> fixed point (halves < 2^14)
@@ -121,53 +172,109 @@ __global__ void __launch_bounds__(SGMU_WARPS * 32)
           if (MODE >= 1) u16_load_run<NW, VEC>(out + q * D, d0, D, spf[MODE >= 1 ? i : 0]);
           xpf[i] = pix[q];
         }
-        if (t == 0) {
-#pragma unroll
-          for (int w = 0; w < NW; w++) lr[w] = c[w];
-        } else {
-          // updateCost in fixed point: with a = Lr' - minC (>= 0),  Lr = C + min(a[d], a[d-1] + P1, a[d+1] + P1, P2)
-          const bool step = (int)smd_absdiff_max3(x, xprev) > corDifThres;
-          const uint32_t P1 = (step ? 1u : scale) * 0x10001u, P2 = (step ? 3u : 3u * scale) * 0x10001u;
-          const uint32_t negm = ((0x10000u - minC) & 0xffffu) * 0x10001u;      // a = prev - minC, modulo 2^16 per half
-          uint32_t a[NW];
-#pragma unroll
-          for (int w = 0; w < NW; w++) a[w] = __vadd2(prev[w], negm);
-          uint32_t lo = __shfl_up_sync(0xffffffffu, a[NW - 1], 1);   // ... | a'[d0-1] in its high half
-          uint32_t hi = __shfl_down_sync(0xffffffffu, a[0], 1);      // a'[d0+VPL] in its low half
-          if (lane == 0) lo = SGMU_BIG2;
-          if (lane == 31) hi = SGMU_BIG2;
-#pragma unroll
-          for (int w = 0; w < NW; w++) {
-            const uint32_t pm = __byte_perm(w == 0 ? lo : a[w - 1], a[w], 0x5432);        // {a[d-1] of both halves}
-            const uint32_t pp = __byte_perm(a[w], w == NW - 1 ? hi : a[w + 1], 0x5432);   // {a[d+1] of both halves}
-            const uint32_t t1 = __viaddmin_u16x2(pm, P1, a[w]);                            // min(a[d-1] + P1, a[d])
-            const uint32_t t2 = __viaddmin_u16x2(pp, P1, P2);                              // min(a[d+1] + P1, P2)
-            lr[w] = __vadd2(c[w], __vminu2(t1, t2));
-          }
-        }
-        uint32_t m2 = SGMU_BIG2;
-#pragma unroll
-        for (int w = 0; w < NW; w++) m2 = __vminu2(m2, lr[w]);
-        minC = __reduce_min_sync(0xffffffffu, min(m2 & 0xffffu, m2 >> 16));
-#pragma unroll
-        for (int w = 0; w < NW; w++) { prev[w] = lr[w]; s[w] = MODE >= 1 ? __vadd2(s[w], lr[w]) : lr[w]; }
-        xprev = x;
-        if (MODE >= 2) {
-          // gen_dispFromVm: strict '>' in increasing d -> the lowest d among the minima: key = sum << 16 | d
-          uint32_t best = 0xffffffffu;
-#pragma unroll
-          for (int w = 0; w < NW; w++) {
-            if (d0 + 2 * w < D) best = min(best, (s[w] << 16) | (uint32_t)(d0 + 2 * w));
-            if (d0 + 2 * w + 1 < D) best = min(best, (s[w] & 0xffff0000u) | (uint32_t)(d0 + 2 * w + 1));
-          }
-          best = __reduce_min_sync(0xffffffffu, best);
-          if (lane == 0) disp[p] = (int16_t)(best & 0xffffu);
-        }
+        u16_step<NW, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, scale, lane, disp, p);
         if (MODE != 3) u16_store_run<NW, VEC>(out + p * D, d0, D, s);
         p += pstep;
       }
     }
   }
+}
+
+// Horizontal paths: a row is contiguous and there are only H of them (7 warps per SM at 1080p), so a register prefetch
+// of 8 pixels cannot keep enough bytes in flight (measured 1.39 ms against 0.85 ms for the other directions at 1080p
+// D=256).  Here the C and S runs and the pixel word of the next SGMU_NSTG pixels are staged with cp.async into per-lane
+// shared-memory slots (as k_sgm_path_h does for the float volumes).  D % VPL == 0, VPL in {4, 8, 16}, aligned volumes.
+#define SGMU_NSTG 12
+template <int VPL, int MODE>
+__global__ void __launch_bounds__(32)
+    k_sgm_path_u16_h(const uint16_t* __restrict__ vol, const uint32_t* __restrict__ pix, uint16_t* __restrict__ out, int H, int W,
+                     int mu, int D, int corDifThres, int shift, int16_t* __restrict__ disp) {
+  extern __shared__ __align__(16) uint8_t sgmu_smem[];
+  constexpr int NW = VPL / 2;
+  constexpr int NS = SGMU_NSTG + 1;
+  constexpr int RUNB = VPL * 2;                                   // bytes of one lane's run
+  constexpr int SLOTB = 32 * RUNB * (MODE >= 1 ? 2 : 1) + 128;    // C runs | S runs | pixel words
+  const int lane = threadIdx.x;
+  const int v = blockIdx.x;
+  const int d0 = lane * VPL;
+  const bool act = d0 < D;
+  const uint32_t scale = 1u << shift;
+  const long long p0 = (long long)v * W + (mu > 0 ? 0 : W - 1);
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sgmu_smem);
+  const uint32_t cOff = base + lane * RUNB, sOff = cOff + 32 * RUNB, xOff = base + 32 * RUNB * (MODE >= 1 ? 2 : 1) + lane * 4;
+  auto cp_run = [&](uint32_t dst, const uint16_t* src) {
+    if (RUNB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else {
+#pragma unroll
+      for (int k = 0; k < RUNB / 16; k++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 16), "l"(src + k * 8) : "memory");
+    }
+  };
+  auto issue = [&](int t, int slot) {
+    if (t < W) {
+      const long long q = p0 + (long long)mu * t;
+      const uint32_t so = slot * SLOTB;
+      if (act) {
+        cp_run(cOff + so, vol + q * D + d0);
+        if (MODE >= 1) cp_run(sOff + so, out + q * D + d0);
+      }
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(xOff + so), "l"(pix + q) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int t = 0; t < SGMU_NSTG; t++) issue(t, t);
+  uint32_t prev[NW];
+  uint32_t minC = 0, xprev = 0;
+  int rd = 0, wr = SGMU_NSTG;
+  long long pc = p0;
+  for (int t = 0; t < W; t++) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(SGMU_NSTG - 1) : "memory");
+    uint32_t c[NW], s[NW];
+    const uint32_t so = rd * SLOTB;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { c[w] = SGMU_BIG2; s[w] = 0u; }
+    if (act) {
+      if (RUNB == 8) {
+        uint2 a;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(cOff + so) : "memory");
+        c[0] = a.x << shift; c[1 % NW] = a.y << shift;
+        if (MODE >= 1) { asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(sOff + so) : "memory"); s[0] = a.x; s[1 % NW] = a.y; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < RUNB / 16; k++) {
+          uint4 a;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(cOff + so + k * 16) : "memory");
+          c[(4 * k) % NW] = a.x << shift; c[(4 * k + 1) % NW] = a.y << shift; c[(4 * k + 2) % NW] = a.z << shift; c[(4 * k + 3) % NW] = a.w << shift;
+          if (MODE >= 1) {
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sOff + so + k * 16) : "memory");
+            s[(4 * k) % NW] = a.x; s[(4 * k + 1) % NW] = a.y; s[(4 * k + 2) % NW] = a.z; s[(4 * k + 3) % NW] = a.w;
+          }
+        }
+      }
+    }
+    uint32_t x;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(xOff + so) : "memory");
+    issue(t + SGMU_NSTG, wr);
+    u16_step<NW, MODE>(t == 0, c, s, prev, minC, x, xprev, d0, D, corDifThres, scale, lane, disp, pc);
+    if (MODE != 3 && act) u16_store_run<NW, true>(out + pc * D, d0, D, s);
+    pc += mu;
+    if (++rd == NS) rd = 0;
+    if (++wr == NS) wr = 0;
+  }
+}
+
+template <int VPL>
+static int launch_u16_h(sm_ctx* ctx, const uint16_t* vol, const uint32_t* pix, uint16_t* out, int H, int W, int mu, int D, int thr,
+                        int shift, int mode, int16_t* disp) {
+#define SGMU_H_LAUNCH(M)                                                                                                  \
+  do {                                                                                                                    \
+    const size_t smem = (size_t)(SGMU_NSTG + 1) * (32 * VPL * 2 * ((M) >= 1 ? 2 : 1) + 128);                              \
+    SM_CUDA(cudaFuncSetAttribute(k_sgm_path_u16_h<VPL, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    SM_LAUNCH(ctx, (k_sgm_path_u16_h<VPL, M>), H, 32, smem, vol, pix, out, H, W, mu, D, thr, shift, disp);                 \
+  } while (0)
+  if (mode == 0) SGMU_H_LAUNCH(0); else if (mode == 1) SGMU_H_LAUNCH(1); else if (mode == 2) SGMU_H_LAUNCH(2); else SGMU_H_LAUNCH(3);
+#undef SGMU_H_LAUNCH
+  return SM_OK;
 }
 
 template <int VPL, int PF, bool VEC>
@@ -192,6 +299,13 @@ int smi_sgm_path_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, 
   const int per = sm_div_up(D, 32);
   const int vpl = per <= 2 ? 2 : (per <= 4 ? 4 : (per <= 8 ? 8 : 16));
   const bool vec = D % vpl == 0 && ((((uintptr_t)d_vol | (uintptr_t)d_out) & 15) == 0);
+  if (g.mv == 0 && vec && vpl >= 4 && ((uintptr_t)d_pix & 3) == 0) {   // horizontal: cp.async staged rows
+    int sh = 0;
+    while ((1 << sh) < scale) sh++;
+    if (vpl == 4) return launch_u16_h<4>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, sh, mode, d_disp);
+    if (vpl == 8) return launch_u16_h<8>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, sh, mode, d_disp);
+    return launch_u16_h<16>(ctx, d_vol, d_pix, d_out, H, W, g.mu, D, corDifThres, sh, mode, d_disp);
+  }
   switch (vpl) {
     case 2: return vec ? launch_u16<2, 8, true>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp)
                        : launch_u16<2, 8, false>(ctx, d_vol, d_pix, d_out, g, D, corDifThres, scale, mode, d_disp);
