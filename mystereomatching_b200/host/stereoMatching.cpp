@@ -1,6 +1,9 @@
 // stereoMatching.cpp -- host wrappers of the StereoMatching stage API over the sm_b200 C ABI.
 // Each method names the reference body it replaces (file:line under the reference root) in stereoMatching.h.
 #include "stereoMatching.h"
+#include "sm_io.h"
+
+#include <sys/stat.h>
 
 #include <cmath>
 #include <iostream>
@@ -51,6 +54,9 @@ StereoMatching::Parameters::Parameters(int maxDisp, int h, int w, int lamCen_, i
   vmTop_hasCir2 = true; vmTop_cir3_doColorLimit = false;
   lamCen = lamCen_; lamG = lamG_; M = M_; lamc = lamc_; ts = ts_; disSc = disSc_;
   errCsvName = errCsvName_;
+  err_ip_dispV = -50; cor_ip_dispV = -100;
+  savePath = StereoMatching::root + StereoMatching::object + "/" + StereoMatching::costcalculation + "-" +
+             StereoMatching::aggregation + "-" + StereoMatching::optimization + "/" + "20200627_test_so" + "/";
 }
 
 // ------------------------------------------------------------------ plumbing
@@ -545,6 +551,29 @@ void StereoMatching::calErr(Mat& DP_, Mat& DT_, string procedure, bool calCSV) {
   }
 }
 template void StereoMatching::calErr<short>(Mat&, Mat&, string, bool);
+
+template <typename T, int imgNum>
+void StereoMatching::saveDispMap(const cv::Mat& dispM, const Mat& trueM, string method, bool calErr) {
+  static_assert(sizeof(T) == sizeof(short), "the path saves CV_16S disparity maps");
+  CV_Assert(dispM.depth() == CV_16S && dispM.channels() == 1 && dispM.rows > 0 && dispM.cols > 0);
+  const int h = dispM.rows, w = dispM.cols;
+  // "IF NOT EXIST path (mkdir path)" (stereoMatching.h:2080): every missing component of savePath
+  for (size_t i = 1; i <= param_.savePath.size(); i++)
+    if (i == param_.savePath.size() || param_.savePath[i] == '/') ::mkdir(param_.savePath.substr(0, i).c_str(), 0777);
+  std::vector<uint8_t> bgr;
+  std::string err;
+  smio::disp_to_bgr((const int16_t*)dispM.data, h, w, param_.DISP_OCC, param_.DISP_MIS, param_.DISP_PKR, bgr, nullptr, nullptr,
+                    param_.err_ip_dispV, param_.cor_ip_dispV);
+  if (!smio::write_png(param_.savePath + method + ".png", bgr.data(), h, w, 3, &err)) throw cv::Exception("saveDispMap: " + err);
+  if (calErr) {
+    CV_Assert(trueM.depth() == CV_32F && trueM.rows == h && trueM.cols == w);
+    CV_Assert(I_mask.size() > 1 && !I_mask[1].empty() && I_mask[1].rows == h && I_mask[1].cols == w);
+    smio::disp_to_bgr((const int16_t*)dispM.data, h, w, param_.DISP_OCC, param_.DISP_MIS, param_.DISP_PKR, bgr,
+                      (const float*)trueM.data, I_mask[1].data, param_.err_ip_dispV, param_.cor_ip_dispV);
+    if (!smio::write_png(param_.savePath + method + "_err.png", bgr.data(), h, w, 3, &err)) throw cv::Exception("saveDispMap: " + err);
+  }
+}
+template void StereoMatching::saveDispMap<short, 1>(const cv::Mat&, const Mat&, string, bool);
 
 void StereoMatching::LRConsistencyCheck_new(Mat& errorMask) {
   CV_Assert(errorMask.depth() == CV_8U && errorMask.rows == h_ && errorMask.cols == w_);

@@ -78,6 +78,8 @@ class StereoMatching {
     bool vmTop_hasCir2, vmTop_cir3_doColorLimit;   // :187-188 (true, false)
     int lamCen, lamG, M, lamc, ts, disSc;
     std::string errCsvName;
+    int err_ip_dispV, cor_ip_dispV;    // stereoMatching.h:316-317 (-50, -100): marker values saveDispMap colours
+    std::string savePath;              // stereoMatching.h:348: root + object + "/" + method names + "/20200627_test_so/"
 
     Parameters(int maxDisp, int h, int w, int lamCen_, int lamG_, int M_, int lamc_, int ts_, string errCsvName_,
                int disSc_);
@@ -169,6 +171,12 @@ class StereoMatching {
   void calErr(Mat& DP, Mat& DT, string procedure, bool calCSV = false);
   struct ErrPair { float PBM = 0.f, RMS = 0.f; bool valid = false; };
   ErrPair lastErr[3];
+  // saveDispMap<short> (stereoMatching.h:2005-2110): the disparity map as an 8-bit BGR picture written to
+  // param_.savePath + method + ".png" (valid pixels stretched to [0, 255], DISP_OCC blue, DISP_MIS red, DISP_PKR yellow,
+  // err_ip_dispV magenta, cor_ip_dispV cyan), and with calErr the "_err.png" variant (error > 1 on I_mask[1] painted red).
+  // PNG encoding: sm_io.h (zlib), since OpenCV's imgcodecs is not linked; the directory is created when missing.
+  template <typename T, int imgNum = 1>
+  void saveDispMap(const cv::Mat& dispM, const Mat& trueM, string method, bool calErr = false);
 
   // ---- device <-> host mirroring (additions; everything above is the reference's surface)
   void syncToHost(bool volumes = true);   // refresh vm[], HVL[], DP[] host Mats from the device
