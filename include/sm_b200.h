@@ -350,6 +350,14 @@ int sm_proper_ipol(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* 
  * receives how many such neighbours were seen. */
 int sm_wm(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint8_t* d_mask, const uint8_t* d_bgr, int H, int W, int D,
           int* d_numInvalid);
+/* discontinuityAdjust (stereoMatching.cpp:6057-6135; Do_discontinuityAdjust, stereoMatching.h:78, off), in place on
+ * d_disp: the map as an 8-bit picture (saturating convertTo) -> equalizeHist -> GaussianBlur(3x3, sigma 4) ->
+ * Canny(20, 60, 3) (integer kernels, pinned against cv2 4.13), then every interior edge pixel whose 3x3 edge
+ * neighbourhood names a direction takes the cheapest (in d_vol = vm[0]) of its own label and the two neighbours' across
+ * that direction, with the reference's raster-order semantics (the first neighbour may already be adjusted).
+ * d_edge (nullable, [H][W] u8) receives the Canny map.  Labels >= D are never used as indices (undefined in the
+ * reference): such a centre stays, such a neighbour is no candidate. */
+int sm_discontinuity_adjust(sm_ctx* ctx, int16_t* d_disp, const float* d_vol, int H, int W, int D, uint8_t* d_edge);
 /* cv::medianBlur(CV_16S, 3) (stereoMatching.cpp:1499). d_dst != d_src. */
 int sm_median3_i16(sm_ctx* ctx, const int16_t* d_src, int16_t* d_dst, int H, int W);
 /* cv::medianBlur(SE, SE, 3) on the CV_32F map subpixelEnhancement returns

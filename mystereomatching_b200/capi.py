@@ -112,6 +112,7 @@ SIGNATURES = {
     "sm_region_vote": ([_P, _P, _P, _P, _I, _I, _I, _F, _I], _I),
     "sm_proper_ipol": ([_P, _P, _P, _P, _I, _I, _I], _I),
     "sm_wm": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "sm_discontinuity_adjust": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "sm_median3_i16": ([_P, _P, _P, _I, _I], _I),
     "sm_median3_f32": ([_P, _P, _P, _I, _I], _I),
     "sm_cross_scale_1level": ([_P, _P, _Z, _F], _I),
@@ -486,6 +487,13 @@ class Ctx:
         bad = self.torch.zeros((1,), dtype=self.torch.int32, device=disp.device)
         check(self.L.sm_wm(self.h, _ptr(disp), _ptr(tmp), _ptr(mask), _ptr(bgr), H, W, D, _ptr(bad)))
         return disp, int(bad.item())
+
+    def discontinuity_adjust(self, disp, vol, want_edge=False):
+        """discontinuityAdjust (stereoMatching.cpp:6057-6135), in place on `disp`; returns disp or (disp, edge map)."""
+        H, W, D = vol.shape
+        edge = self.empty((H, W), self.torch.uint8) if want_edge else None
+        check(self.L.sm_discontinuity_adjust(self.h, _ptr(disp), _ptr(vol), H, W, D, _ptr(edge) if want_edge else None))
+        return (disp, edge) if want_edge else disp
 
     def median3_f32(self, disp):
         """cv::medianBlur(CV_32F, 3) (stereoMatching.cpp:1490)."""

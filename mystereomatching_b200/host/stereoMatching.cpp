@@ -24,6 +24,7 @@ bool StereoMatching::Do_properIpol = true;
 bool StereoMatching::Do_lastMedianBlur = true;
 bool StereoMatching::Do_subpixelEnhancement = false;
 bool StereoMatching::Do_WM = false;
+bool StereoMatching::Do_discontinuityAdjust = false;
 
 // reference defaults: stereoMatching.h:204-350
 StereoMatching::Parameters::Parameters(int maxDisp, int h, int w, int lamCen_, int lamG_, int M_, int lamc_, int ts_,
@@ -212,6 +213,7 @@ void StereoMatching::refine() {
     CV_Assert(!LRC_Err_Mask.empty());
     WM(DP[0], LRC_Err_Mask, I_c[0]);
   }
+  if (Do_discontinuityAdjust) discontinuityAdjust(DP[0]);   // stereoMatching.cpp:1473-1480
   if (Do_subpixelEnhancement) {   // stereoMatching.cpp:1482-1490: SE from DP[0] and vm[0], then its 3x3 median; DP[0] untouched
     const size_t npix = (size_t)h_ * w_;
     if (!dp_dev_fresh_[0]) { upload(d_disp_[0], DP[0].data, npix * 2); dp_dev_fresh_[0] = true; }
@@ -908,6 +910,21 @@ void StereoMatching::WM(Mat& disp, Mat& mask, Mat& img) {
   check(sm_wm(ctx_, a.as<int16_t>(), t.as<int16_t>(), m.as<uint8_t>(), d_img, h_, w_, d_, nullptr), "sm_wm");
   download(disp.data, a.p, npix * 2);
   if (member) dp_dev_fresh_[0] = false;
+}
+
+void StereoMatching::discontinuityAdjust(cv::Mat& disp) {
+  CV_Assert(disp.type() == CV_16SC1 && disp.rows == h_ && disp.cols == w_);
+  const size_t npix = (size_t)h_ * w_;
+  uploadVm(0);
+  if (&disp == &DP[0]) {   // the member map stays on the device
+    if (!dp_dev_fresh_[0]) { upload(d_disp_[0], DP[0].data, npix * 2); dp_dev_fresh_[0] = true; }
+    check(sm_discontinuity_adjust(ctx_, d_disp_[0], d_vol_[0], h_, w_, d_, nullptr), "sm_discontinuity_adjust");
+    return;
+  }
+  TmpDev a(ctx_, npix * 2);
+  upload(a.p, disp.data, npix * 2);
+  check(sm_discontinuity_adjust(ctx_, a.as<int16_t>(), d_vol_[0], h_, w_, d_, nullptr), "sm_discontinuity_adjust");
+  download(disp.data, a.p, npix * 2);
 }
 
 void StereoMatching::regionVote_my(cv::Mat& Dp, float rv_ratio, int rv_s) {

@@ -46,6 +46,7 @@ class StereoMatching {
   static bool Do_refine, Do_LRConsis, Do_regionVote, Do_properIpol, Do_lastMedianBlur;
   static bool Do_subpixelEnhancement;   // stereoMatching.h:79 (0 in the reference; a run-time switch here)
   static bool Do_WM;                    // stereoMatching.h:74 (0 in the reference; a run-time switch here)
+  static bool Do_discontinuityAdjust;   // stereoMatching.h:78 (0 in the reference; a run-time switch here)
   static const bool UniqCk = false, SubIpl = false;
 
   struct Parameters {  // stereoMatching.h:85-351 (fields read on the hot path; same names, same defaults)
@@ -162,6 +163,7 @@ class StereoMatching {
   void regionVote_my(cv::Mat& Dp, float rv_ratio, int rv_s);                            // stereoMatching.cpp:7219-7277
   void properIpol(cv::Mat& Dp, cv::Mat& I1_c);                                          // stereoMatching.cpp:7395-7490
   void WM(Mat& disp, Mat& mask, Mat& img);                                              // stereoMatching.cpp:7340-7393
+  void discontinuityAdjust(cv::Mat& ipol);                                              // stereoMatching.cpp:6057-6135 (reads vm[0])
 
   // ---- evaluation (stereoMatching.h:1748-1825).  Same arithmetic and the same console line per region
   // ("nonocc" / "all" / "disc" = I_mask[0..2], skipped when empty); the reference also appends to

@@ -68,6 +68,7 @@ CPP_FUNCS = [
     # default-off refiner
     (r"^void StereoMatching::subpixelEnhancement\(", "subpixelEnhancement"),
     (r"^void StereoMatching::WM\(", "WM"),
+    (r"^void StereoMatching::discontinuityAdjust\(", "discontinuityAdjust"),
     # the sequential half of vmTop
     (r"^void StereoMatching::genDispFromTopCostVm2\(", "genDispFromTopCostVm2"),
     # the gradient cost family: "censusGrad" is the selector main_.cpp:15 compiles in

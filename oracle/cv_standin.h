@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 #include "cvmat_lite.h"
+#include "opencv_restated.h"
 
 namespace cv {
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4 };
@@ -41,6 +42,29 @@ inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int le
       memcpy(out.data + v * out.step[0] + u * es, src.data + sv * src.step[0] + su * es, es);
     }
   }
+  dst = out;
+}
+// discontinuityAdjust's three imgproc calls (stereoMatching.cpp:6061-6064) -> the cv2-pinned restatements of
+// opencv_restated.h; only the argument combinations that function uses are accepted
+struct Size { int width, height; Size(int w, int h) : width(w), height(h) {} };
+inline void equalizeHist(const Mat& src, Mat& dst) {
+  if (src.dims != 2 || src.type() != CV_8UC1) { fprintf(stderr, "cv_standin: unsupported equalizeHist\n"); abort(); }
+  Mat out(src.rows, src.cols, CV_8UC1);
+  orc_cv::equalize_hist(src.data, out.data, src.rows, src.cols);
+  dst = out;
+}
+inline void GaussianBlur(const Mat& src, Mat& dst, Size k, double sx, double sy) {
+  if (src.dims != 2 || src.type() != CV_8UC1 || k.width != 3 || k.height != 3 || sx != 4 || sy != 4) {
+    fprintf(stderr, "cv_standin: unsupported GaussianBlur\n"); abort();
+  }
+  Mat out(src.rows, src.cols, CV_8UC1);
+  orc_cv::gauss3_sigma4(src.data, out.data, src.rows, src.cols);
+  dst = out;
+}
+inline void Canny(const Mat& src, Mat& dst, double low, double high, int aperture) {
+  if (src.dims != 2 || src.type() != CV_8UC1 || aperture != 3) { fprintf(stderr, "cv_standin: unsupported Canny\n"); abort(); }
+  Mat out(src.rows, src.cols, CV_8UC1);
+  orc_cv::canny3_l1(src.data, out.data, src.rows, src.cols, (int)std::floor(low), (int)std::floor(high));
   dst = out;
 }
 inline bool imwrite(const std::string&, const Mat&) { return true; }  // debug dumps of the reference: dropped

@@ -84,6 +84,11 @@ def lib():
         "orc_proper_ipol": ([i16p, u8p, I, I, I], None),
         "orc_median3_i16": ([i16p, I, I, i16p], None),
         "orc_median3_f32": ([f32p, I, I, f32p], None),
+        "orc_da_edges": ([i16p, I, I, u8p], None),
+        "orc_equalize_hist": ([u8p, I, I, u8p], None),
+        "orc_gauss3_sigma4": ([u8p, I, I, u8p], None),
+        "orc_canny3_l1": ([u8p, I, I, I, I, u8p], None),
+        "orc_disc_adjust": ([i16p, f32p, I, I, I, u8p], I),
         "orc_wm": ([i16p, u8p, u8p, I, I, I], I),
         "orc_wm_lenient": ([i16p, u8p, u8p, I, I, I, i32p], I),
         "orc_solve_all_1level": ([f32p, C.c_long, F], None),
@@ -350,6 +355,42 @@ def proper_ipol(dp, bgr, occ=-32):
     return out
 
 
+def equalize_hist(img):
+    out = np.empty_like(np.ascontiguousarray(img, np.uint8))
+    lib().orc_equalize_hist(np.ascontiguousarray(img, np.uint8), img.shape[0], img.shape[1], out)
+    return out
+
+
+def gauss3_sigma4(img):
+    out = np.empty_like(np.ascontiguousarray(img, np.uint8))
+    lib().orc_gauss3_sigma4(np.ascontiguousarray(img, np.uint8), img.shape[0], img.shape[1], out)
+    return out
+
+
+def canny3_l1(img, low, high):
+    out = np.empty_like(np.ascontiguousarray(img, np.uint8))
+    lib().orc_canny3_l1(np.ascontiguousarray(img, np.uint8), img.shape[0], img.shape[1], int(low), int(high), out)
+    return out
+
+
+def da_edges(disp):
+    """The edge map discontinuityAdjust works on (stereoMatching.cpp:6059-6064): convertTo(8U) -> equalizeHist ->
+    GaussianBlur(3x3, 4) -> Canny(20, 60, 3)."""
+    d = np.ascontiguousarray(disp, np.int16)
+    out = np.empty(d.shape, np.uint8)
+    lib().orc_da_edges(d, d.shape[0], d.shape[1], out)
+    return out
+
+
+def disc_adjust(disp, vol):
+    """discontinuityAdjust (stereoMatching.cpp:6057-6135): (adjusted map, edge map, number of labels >= D met)."""
+    H, W, D = vol.shape
+    out = np.ascontiguousarray(disp, np.int16).copy()
+    edge = np.empty((H, W), np.uint8)
+    bad = lib().orc_disc_adjust(out, np.ascontiguousarray(vol, np.float32), H, W, D, edge)
+    return out, edge, bad
+
+
 def wm(disp, mask, bgr, D):
     """WM (stereoMatching.cpp:7340-7393): bilateral weighted median on the mask > 0 pixels; labels must lie in [0, D)."""
     out = np.ascontiguousarray(disp, np.int16).copy()
@@ -557,6 +598,7 @@ def smref_lib():
         "smref_subpixel": ([P, i16p, f32p], None),
         "smref_disp_from_top": ([P, f32p, I, I, I, I, I, I, i16p], None),
         "smref_wm": ([P, i16p, u8p], None),
+        "smref_disc_adjust": ([P, i16p], None),
         "smref_lrc_normal": ([P, i16p, i16p], None), "smref_lrc_label": ([P, i16p, i16p, I, P], None),
         "smref_lrc_new": ([P, i16p, i16p, u8p], None),
         "smref_region_vote": ([P, i16p, F, I], None), "smref_proper_ipol": ([P, i16p], None),
@@ -720,6 +762,13 @@ class SmRef:
         """The reference's own subpixelEnhancement on the given disparity map and vm[0]."""
         o = np.empty((self.H, self.W), np.float32)
         self.L.smref_subpixel(self.h, np.ascontiguousarray(disp, np.int16), o)
+        return o
+
+    def disc_adjust(self, disp):
+        """The reference's own discontinuityAdjust on the given map and vm[0] (its three OpenCV calls go to the restated,
+        cv2-pinned functions of oracle/opencv_restated.h)."""
+        o = np.ascontiguousarray(disp, np.int16).copy()
+        self.L.smref_disc_adjust(self.h, o)
         return o
 
     def wm(self, disp, mask):

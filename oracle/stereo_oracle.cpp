@@ -33,6 +33,8 @@
 #include <cstring>
 #include <limits>
 #include <vector>
+
+#include "opencv_restated.h"
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -925,6 +927,58 @@ int orc_wm(short* disp, const unsigned char* mask, const unsigned char* bgr, int
 int orc_wm_lenient(short* disp, const unsigned char* mask, const unsigned char* bgr, int H, int W, int D, int* numInvalid) {
   *numInvalid = 0;
   return wm_impl(disp, mask, bgr, H, W, D, true, numInvalid);
+}
+
+// discontinuityAdjust (stereoMatching.cpp:6057-6135; Do_discontinuityAdjust, stereoMatching.h:78, off): the map as an
+// 8-bit picture (saturating convertTo) -> equalizeHist -> GaussianBlur(3x3, sigma 4) -> Canny(20, 60, 3); an edge pixel
+// whose 3x3 edge neighbourhood names a direction takes the disparity of whichever of itself and the two neighbours ACROSS
+// that direction has the smallest cost in vm[0] -- in place and in raster order, so the first neighbour (above or to the
+// left) may already carry its adjusted value.  edge (optional) receives the Canny map.  Returns the number of labels
+// >= D met on the way (the reference would index vm[0] out of bounds there: undefined; here such a centre pixel is left
+// alone and such a neighbour is not a candidate -- the same defined extension sm_discontinuity_adjust implements).
+void orc_da_edges(const short* disp, int H, int W, u8* edge) {
+  std::vector<u8> a((size_t)H * W), b((size_t)H * W);
+  for (long i = 0; i < (long)H * W; i++) a[i] = (u8)(disp[i] < 0 ? 0 : disp[i] > 255 ? 255 : disp[i]);
+  orc_cv::equalize_hist(a.data(), b.data(), H, W);
+  orc_cv::gauss3_sigma4(b.data(), a.data(), H, W);
+  orc_cv::canny3_l1(a.data(), edge, H, W, 20, 60);
+}
+void orc_equalize_hist(const u8* src, int H, int W, u8* dst) { orc_cv::equalize_hist(src, dst, H, W); }
+void orc_gauss3_sigma4(const u8* src, int H, int W, u8* dst) { orc_cv::gauss3_sigma4(src, dst, H, W); }
+void orc_canny3_l1(const u8* src, int H, int W, int low, int high, u8* dst) { orc_cv::canny3_l1(src, dst, H, W, low, high); }
+int orc_disc_adjust(short* disp, const float* vol, int H, int W, int D, u8* edge_out) {
+  std::vector<u8> E((size_t)H * W);
+  orc_da_edges(disp, H, W, E.data());
+  if (edge_out) memcpy(edge_out, E.data(), E.size());
+  static const int dH[8] = {-1, 1, -1, 1, -1, 1, 0, 0}, dW[8] = {-1, 1, 0, 0, 1, -1, -1, 1};
+  int bad = 0;
+  auto e = [&](int v, int u) { return E[(size_t)v * W + u] != 0; };
+  for (int v = 1; v < H - 1; v++)
+    for (int u = 1; u < W - 1; u++) {
+      if (!e(v, u)) continue;
+      int dir = -1;
+      if (e(v - 1, u - 1) && e(v + 1, u + 1)) dir = 4;
+      else if (e(v - 1, u + 1) && e(v + 1, u - 1)) dir = 0;
+      else if (e(v - 1, u) || e(v - 1, u - 1) || e(v - 1, u + 1)) {
+        if (e(v + 1, u) || e(v + 1, u - 1) || e(v + 1, u + 1)) dir = 6;
+      } else if ((e(v - 1, u - 1) || e(v, u - 1) || e(v + 1, u - 1)) && (e(v - 1, u + 1) || e(v, u + 1) || e(v + 1, u + 1)))
+        dir = 2;
+      if (dir < 0) continue;
+      short dp = disp[(size_t)v * W + u];
+      if (dp < 0) continue;
+      if (dp >= D) { bad++; continue; }
+      float cost = vol[((size_t)v * W + u) * D + dp];
+      const int v1 = v + dH[dir], u1 = u + dW[dir], v2 = v + dH[dir + 1], u2 = u + dW[dir + 1];
+      const short d1 = disp[(size_t)v1 * W + u1], d2 = disp[(size_t)v2 * W + u2];
+      if (d1 >= D) bad++;
+      if (d2 >= D) bad++;
+      const float cost1 = (d1 >= 0 && d1 < D) ? vol[((size_t)v1 * W + u1) * D + d1] : -1;
+      const float cost2 = (d2 >= 0 && d2 < D) ? vol[((size_t)v2 * W + u2) * D + d2] : -1;
+      if (cost1 >= 0 && cost1 < cost) { dp = d1; cost = cost1; }
+      if (cost2 != -1 && cost2 < cost) dp = d2;
+      disp[(size_t)v * W + u] = dp;
+    }
+  return bad;
 }
 
 // cv::medianBlur(CV_32F, ksize 3) on the sub-pixel map (stereoMatching.cpp:1490): same window, replicated border

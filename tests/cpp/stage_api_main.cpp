@@ -169,6 +169,11 @@ int main(int argc, char** argv) {
         sm.subpixelEnhancement(dsp, SE);
         dump(out + ".se0.f32", SE.data, npix * 4);
       }
+      {  // the default-off discontinuity step as refine() would call it (stereoMatching.cpp:1473-1475), on a host clone
+        cv::Mat dsp = sm.hostDP(0).clone();
+        sm.discontinuityAdjust(dsp);
+        dump(out + ".da0.i16", dsp.data, npix * 2);
+      }
       {  // refine() with the sub-pixel step on (stereoMatching.cpp:1482-1490), split in two calls so that the map the
          // step reads (DP[0] before the last median) can be dumped; the end state equals a single refine()
         StereoMatching::Do_subpixelEnhancement = true;

@@ -24,7 +24,7 @@ def test_host_library_exports_the_stage_api():
                 "StereoMatching::costScan(cv::Mat&, cv::Mat&, int, int, bool)",
                 "StereoMatching::gen_dispFromVm(cv::Mat&, cv::Mat&)", "StereoMatching::wta_Co(",
                 "StereoMatching::selectTopCostFromVolumn(cv::Mat&, cv::Mat&, float)",
-                "StereoMatching::subpixelEnhancement(cv::Mat&, cv::Mat&)",
+                "StereoMatching::subpixelEnhancement(cv::Mat&, cv::Mat&)", "StereoMatching::discontinuityAdjust(cv::Mat&)",
                 "StereoMatching::regionVote_my(cv::Mat&, float, int)", "StereoMatching::properIpol(",
                 "StereoMatching::LRConsistencyCheck_normal(", "StereoMatching::genCensusCode_NC_Sur(",
                 "StereoMatching::gen_cenVM_XOR(", "StereoMatching::cbca_core(", "StereoMatching::genTrueHorVerArms(",
@@ -86,6 +86,10 @@ def test_cpp_class_matches_oracle(tmp_path, mode):
         se = np.fromfile(prefix + ".se0.f32", np.float32).reshape(H, W)
         se_want = po.subpixel(dw, sg)
         assert np.array_equal(se.view(np.uint32), se_want.view(np.uint32)) and (se_want != dw).any()
+        # discontinuityAdjust on a clone of the WTA map over vm[0]
+        da = np.fromfile(prefix + ".da0.i16", np.int16).reshape(H, W)
+        da_want, _, bad = po.disc_adjust(dw, sg)
+        assert bad == 0 and np.array_equal(da, da_want)
         # refine() with Do_subpixelEnhancement: SE = median3(subpixel(DP[0] before the last median, vm[0]))
         pm = np.fromfile(prefix + ".dp0_premed.i16", np.int16).reshape(H, W)
         ser = np.fromfile(prefix + ".se_refine.f32", np.float32).reshape(H, W)

@@ -454,3 +454,43 @@ def test_wm_equals_reference(golden_dir):
     bad[3, 3] = -32                                                 # DISP_OCC inside somebody's window
     with pytest.raises(ValueError):
         po.wm(bad, g["a_noisy_some_mask"], g["a_bgr"], int(g["a_D"]))
+
+
+def test_opencv_restatements_equal_cv2(golden_dir):
+    """oracle/opencv_restated.h (equalizeHist, GaussianBlur(3x3, 4), Canny(20, 60, 3)) against cv2 4.13's outputs
+    (tests/golden/da_ref.npz): every image incl. the constant one and the 1x1 ... 3x3 shapes, bit for bit."""
+    from oracle import pyoracle as po
+    g = np.load(os.path.join(golden_dir, "da_ref.npz"))
+    names = [k[4:] for k in g.files if k.startswith("img_")]
+    assert len(names) >= 9
+    for k in names:
+        im = g["img_" + k]
+        assert np.array_equal(po.equalize_hist(im), g["eq_" + k]), k
+        assert np.array_equal(po.gauss3_sigma4(im), g["gb_" + k]), k
+        assert np.array_equal(po.canny3_l1(im, 20, 60), g["cn_" + k]), k
+        assert np.array_equal(po.canny3_l1(g["gb_" + k], 20, 60), g["cnb_" + k]), k
+
+
+def test_disc_adjust_equals_reference(golden_dir):
+    """orc_disc_adjust against the reference's own discontinuityAdjust (da_ref.npz), and its edge chain against cv2's."""
+    from oracle import pyoracle as po
+    g = np.load(os.path.join(golden_dir, "da_ref.npz"))
+    for pre in ("a", "b0", "b1", "b2"):
+        disp, vol = g[pre + "_disp"], g[pre + "_vol"]
+        assert np.array_equal(po.da_edges(disp), g[pre + "_edge_cv2"]), pre
+        got, edge, bad = po.disc_adjust(disp, vol)
+        assert bad == 0
+        assert np.array_equal(edge, g[pre + "_edge_cv2"])
+        assert np.array_equal(got, g[pre + "_out"]), pre
+        assert (got != disp).sum() > 20          # the case exercises the update
+        if po.smref_lib() is not None and pre == "b0":
+            H, W, D = vol.shape
+            z = np.zeros((H, W, 3), np.uint8)
+            r = po.SmRef(z, z, z[..., 0].copy(), z[..., 0].copy(), D)
+            r.adcensus()
+            r.arms()
+            r.cbca(1)                                # leaves vm[0] as the 3-D Mat the function indexes (after ADCensusCal
+                                                     # alone it is a 2-D multi-channel header, on which at(h, w, d) is undefined)
+            r.set_vm(0, vol)
+            assert np.array_equal(r.disc_adjust(disp), got)
+            r.close()
