@@ -202,7 +202,7 @@ def run_reference(name, rows, threads, seed0=1000):
 def cpu_baseline(name, budget_rows=48):
     W, H, D, P, kind = WORKLOADS[name]
     if have_compiled_reference(name):
-        rows = min(H, 48)
+        rows = min(H, 96)   # tall enough for the vertical arms (<= 34 rows either way)
         nt = reference_threads(name, rows)
         mde = W * rows * D / 1e6
         t1 = run_reference(name, rows, 1)
@@ -262,10 +262,13 @@ def main_reference(args):
     total = args.steps + args.warmup
     compiled = have_compiled_reference(name)
     if compiled:
-        rows = min(H, 24 if total <= 20 else 12)
+        # band height of a timed step: tall enough that the vertical arms (<= 34 rows either way) and the vertical SGM
+        # paths are not cut short the way a 12-row band cuts them; whole frames for the small workloads.  Sized so that
+        # the default K = 10 stays within a few minutes on 16 host threads (~0.17 s per 1920-wide D=256 row and step).
+        rows = H if H * W * D <= 64 * 2 ** 20 else min(H, 96 if args.steps <= 12 else (64 if args.steps <= 20 else 32))
         nt = reference_threads(name, rows)
-        for i in range(args.warmup):
-            run_reference(name, rows, nt, 1000 + 100 * i)
+        for i in range(args.warmup):   # warm-up steps only touch code and caches: a short band each
+            run_reference(name, min(rows, 24), nt, 1000 + 100 * i)
         dt = 0.0
         for i in range(args.steps):
             dt += run_reference(name, rows, nt, 5000 + 100 * i)

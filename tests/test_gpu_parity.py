@@ -2,6 +2,8 @@
 the same seeded inputs.  Bit-exact for integer/byte/index work; float volumes: see each test's tolerance
 (north_star: 1e-4 relative; most stages are in fact bit-exact because the kernels keep the reference's
 float operation order)."""
+import os
+
 import numpy as np
 import pytest
 import torch
