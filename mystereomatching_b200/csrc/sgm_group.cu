@@ -162,37 +162,55 @@ __device__ __forceinline__ void g_strow(uint32_t a, int nq, const float (&x)[VPL
   for (int q = 0; q < VPL / 4; q++)
     if (q < nq) g_sts16(a + q * QS, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
 }
-// This lane's part of a neighbour CTA's published row (and the row minimum).  g_edge_issue starts the loads (at the
-// top of the row, so the L2 round trip overlaps the other two recurrences); g_edge_finish re-polls whatever still
-// carries the sentinel.
-template <int VPL>
-struct g_edge_regs { uint4 t[VPL / 4]; uint32_t m; };
-template <int VPL>
-__device__ __forceinline__ void g_edge_issue(const float* src, int nq, int D, g_edge_regs<VPL>& e) {
-#pragma unroll
-  for (int q = 0; q < VPL / 4; q++) {
-    e.t[q] = make_uint4(0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu);   // FLT_MAX padding
-    if (q < nq) e.t[q] = g_ld_relaxed16(src + q * 4);
-  }
-  e.m = g_ld_relaxed4(src + D);   // src is lane-relative: the minimum sits at D - d0
+// The consumer of a neighbour CTA's published row also RE-ARMS what it has read: every word goes back to the sentinel, so
+// the buffers are all-sentinel again when the launch ends and the next launch needs no fill (each word is written once by
+// its producer and read by exactly one consumer lane; the producer's next write to it happens in a later launch).  The
+// row minimum is ONE word all lanes read: nobody re-arms it before everybody has it.
+// The far row by prefetch: the edge column copies ITS words of the neighbour CTA's row into shared memory with cp.async
+// (L2 -> shared, no registers, no scoreboard) at the END of the previous sweep row, so the L2 round trip (0.7 us under load)
+// runs under the pair barriers and the near diagonal (which is computed first and published at once) instead of sitting
+// between the row top and the far diagonal.  Same flag-free protocol: a word still carrying the sentinel after the copy was fetched too early and is
+// polled directly, as before.
+__device__ __forceinline__ void g_cpasync16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-// The consumer also RE-ARMS what it has read: every word goes back to the sentinel, so the buffers are all-sentinel
-// again when the launch ends and the next launch needs no fill (each word is written once by its producer and read by
-// exactly one consumer lane; the producer's next write to it happens in a later launch).
+__device__ __forceinline__ void g_cpasync_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void g_cpasync_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 g_lds16u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
 template <int VPL>
-__device__ __forceinline__ void g_edge_finish(const float* src, int nq, int D, const g_edge_regs<VPL>& e, float (&pr)[VPL], float& pm,
-                                              int& polls) {
+__device__ __forceinline__ void g_edge_prefetch(const float* src, int nq, int Dlane, uint32_t dst, int lane) {
+#pragma unroll
+  for (int q = 0; q < VPL / 4; q++)
+    if (q < nq) g_cpasync16(dst + q * 16, src + q * 4);
+  if (lane == 0) g_cpasync16(dst + Dlane * 4, src + Dlane);   // the quad that holds the row minimum (lane 0: Dlane = D)
+  g_cpasync_commit();
+}
+// dst: this lane's words of the prefetched row in shared memory; minAddr: the row minimum's word there.
+// (Tried and dropped: a second, EARLY copy issued in the middle of the previous row so that nothing is waited for at
+// all -- it is fetched before the neighbour has published too often (2.5 polls per row on average, rows of 2.8 us):
+// 5.70 instead of 5.31 ms per view.)
+template <int VPL>
+__device__ __forceinline__ void g_edge_take(const float* src, int nq, int D, uint32_t dst, uint32_t minAddr, float (&pr)[VPL], float& pm,
+                                            int& polls) {
   float* w = const_cast<float*>(src);
+  g_cpasync_wait0();
+  __syncwarp();
 #pragma unroll
   for (int q = 0; q < VPL / 4; q++) {
-    uint4 t = e.t[q];
-    while (t.x == SGMG_SENTINEL || t.y == SGMG_SENTINEL || t.z == SGMG_SENTINEL || t.w == SGMG_SENTINEL) { t = g_ld_relaxed16(src + q * 4); polls++; }
+    uint4 t = make_uint4(0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu);   // FLT_MAX padding
+    if (q < nq) {
+      t = g_lds16u(dst + q * 16);
+      while (t.x == SGMG_SENTINEL || t.y == SGMG_SENTINEL || t.z == SGMG_SENTINEL || t.w == SGMG_SENTINEL) { t = g_ld_relaxed16(src + q * 4); polls++; }
+      __stcg(reinterpret_cast<uint4*>(w + q * 4), make_uint4(SGMG_SENTINEL, SGMG_SENTINEL, SGMG_SENTINEL, SGMG_SENTINEL));
+    }
     pr[4 * q] = __uint_as_float(t.x); pr[4 * q + 1] = __uint_as_float(t.y);
     pr[4 * q + 2] = __uint_as_float(t.z); pr[4 * q + 3] = __uint_as_float(t.w);
-    if (q < nq) __stcg(reinterpret_cast<uint4*>(w + q * 4), make_uint4(SGMG_SENTINEL, SGMG_SENTINEL, SGMG_SENTINEL, SGMG_SENTINEL));
   }
-  // the row minimum is ONE word all lanes read: nobody may re-arm it before everybody has it
-  uint32_t m = e.m;
+  uint32_t m = __float_as_uint(g_lds4(minAddr));
   while (__any_sync(0xffffffffu, m == SGMG_SENTINEL)) {
     if (m == SGMG_SENTINEL) m = g_ld_relaxed4(src + D);
   }
@@ -257,6 +275,8 @@ __global__ void __launch_bounds__(448, NV)
   const uint32_t minLo = exLo + 2 * exPathB;
   const uint32_t minBufB = (uint32_t)nwarp * 4, minPathB = 2u * minBufB;
   const uint32_t bars = minLo + 2 * minPathB + (uint32_t)warp * NS * 8;   // (8-byte aligned: see host)
+  // prefetched far rows of the two edge columns: [first | last][row parity][Dp floats]
+  const uint32_t farLo = (minLo + 2 * minPathB + (uint32_t)nwarp * NS * 8 + 15u) & ~15u;
 
   const long long rowStep = UP ? -(long long)W : (long long)W;   // pixels from one row of the sweep to the next
   const size_t p0 = (size_t)(UP ? H - 1 : 0) * W + u;            // first pixel of this column in sweep order
@@ -284,6 +304,8 @@ __global__ void __launch_bounds__(448, NV)
   const bool nbrCta = isFirst ? b > 0 : b + 1 < nb;   // the CTA on the far side exists (else: image border)
   float* pubRow = (isFirst ? E.rowsP : E.rowsM) + (size_t)b * H * E.Dp + d0;
   const float* farRow = (isFirst ? E.rowsM : E.rowsP) + (size_t)(nbrCta ? (isFirst ? b - 1 : b + 1) : b) * H * E.Dp + d0;
+  const float* farNext = farRow;   // the row the NEXT sweep row consumes (prefetched at the end of this one)
+  const uint32_t farBuf = farLo + (isLast ? 2u : 0u) * (uint32_t)E.Dp * 4u;
   const float P1r = 1.0f / redu, P2r = 3.0f / redu;
 
   // pixel words (BGR packed), 32 rows at a time: lane i holds sweep row 32 * chunk + i of this column and of the two
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(448, NV)
         g_strow<VPL, XQ>(myB, nq, c); g_strow<VPL, XQ>(myC, nq, c);
         if (lane == 0) { g_sts4(myMinB, m); g_sts4(myMinC, m); }
       } else {
-        if (nbrCta && H > 1) {   // (the last row of a sweep is never read: not published, see g_edge_finish)
+        if (nbrCta && H > 1) {   // (the last row of a sweep is never read: not published, see g_edge_take)
 #pragma unroll
           for (int q = 0; q < VPL / 4; q++)
             if (q < nq) __stcg(reinterpret_cast<float4*>(pubRow + q * 4), make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]));
@@ -357,23 +379,17 @@ __global__ void __launch_bounds__(448, NV)
       g_strow<VPL, XQ>(myB, nq, lrB); g_strow<VPL, XQ>(myC, nq, lrC);
       if (lane == 0) { g_sts4(myMinB, mB); g_sts4(myMinC, mC); }
     } else {
-      // edge column.  The far diagonal's previous row is requested first and used last: the neighbour CTA stored it
-      // early in ITS previous row, and the L2 round trip runs under the near diagonal and the vertical path, which
-      // are independent and interleave.  The near row goes to the neighbour CTA as soon as it exists.
+      // edge column.  The near diagonal comes first and goes to the neighbour CTA as soon as it exists; the far
+      // diagonal's previous row was prefetched into shared memory at the end of the previous sweep row.
       float prN[VPL], lrN[VPL], lrF[VPL], mN, mF, mA;
-      g_edge_regs<VPL> er;
       unsigned long long* tr = E.trace ? E.trace + ((size_t)(b * 2 + (isLast ? 1 : 0)) * H + r) * 4 : nullptr;
       if (tr && lane == 0) tr[1] = g_now();
-      // (requesting the row one row period earlier, alone or in addition, was measured and is slower: a loop-carried
-      //  register set is copied at the loop head, which waits for the loads in flight)
-      if (nbrCta) g_edge_issue<VPL>(farRow, nq, D - d0, er);
+      if (tl) tl[5] = g_now();
       const uint32_t nearPath = nearIsB ? 0u : exPathB, nearMin = nearIsB ? 0u : minPathB;
       g_ldrow<VPL, XQ>(exLo + nearPath + pbufOff + (uint32_t)(warp + nearOff) * runB + exOff, nq, prN);
       const float pmN = g_lds4(minLo + nearMin + mpbufOff + (uint32_t)(warp + nearOff) * 4);
       const uint32_t xpN = nearIsB ? xpB : xpC, xpF = nearIsB ? xpC : xpB;
       g_lr<VPL>(c, prN, pmN, (int)smd_absdiff_max3(xrow, xpN) > corDifThres, P1r, P2r, lane, lrN, mN);
-      g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
-      minA = mA;
       if (nbrCta) {
         if (r + 1 < H) {   // the neighbour reads this row at ITS row r + 1
 #pragma unroll
@@ -382,16 +398,22 @@ __global__ void __launch_bounds__(448, NV)
           if (lane == 0) __stcg(pubRow + D, mN);
         }
         if (tr && lane == 0) tr[0] = g_now();
+        if (tl) tl[6] = g_now();
         float prF[VPL], pmF;
         int polls = 0;
-        g_edge_finish<VPL>(farRow, nq, D - d0, er, prF, pmF, polls);
+        const uint32_t fb = farBuf + ((r & 1) ? (uint32_t)E.Dp * 4u : 0u);
+        g_edge_take<VPL>(farRow, nq, D - d0, fb + (uint32_t)d0 * 4u, fb + (uint32_t)D * 4u, prF, pmF, polls);
         if (tr && lane == 0) { tr[2] = g_now(); tr[3] = (unsigned long long)polls; }
+        if (tl) tl[7] = g_now();
+        g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
         g_lr<VPL>(c, prF, pmF, (int)smd_absdiff_max3(xrow, xpF) > corDifThres, P1r, P2r, lane, lrF, mF);
       } else {   // predecessor column outside the image: Lr = C
+        g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
 #pragma unroll
         for (int j = 0; j < VPL; j++) lrF[j] = c[j];
         mF = g_rowmin<VPL>(c);
       }
+      minA = mA;
       g_strow<VPL, XQ>(nearIsB ? myC : myB, nq, lrF);
       if (lane == 0) g_sts4(nearIsB ? myMinC : myMinB, mF);
 #pragma unroll
@@ -413,6 +435,9 @@ __global__ void __launch_bounds__(448, NV)
         }
         *reinterpret_cast<float4*>(o + q * 4) = t;
       }
+    // the far row of the NEXT sweep row: the neighbour published it early in this row period
+    if (special && nbrCta && r + 1 < H)
+      g_edge_prefetch<VPL>(farNext, nq, D - d0, farBuf + (((r + 1) & 1) ? (uint32_t)E.Dp * 4u : 0u) + (uint32_t)d0 * 4u, lane);
     // advance to the next row of the sweep
     xpA = xrow;
     xpB = __shfl_sync(0xffffffffu, curB, r & 31);
@@ -425,6 +450,7 @@ __global__ void __launch_bounds__(448, NV)
     o += oStep;
     pubRow += E.Dp;
     if (r > 0) farRow += E.Dp;   // the far row read at row r is the neighbour's row r-1
+    farNext += E.Dp;
     // Refill this stage.  No proxy fence: the stage was only READ through the generic proxy, and every lane's reads
     // have been consumed by arithmetic above (a fence.proxy.async here also waits for the warp's outstanding global
     // stores and edge loads: measured 250 ns per row, 700 ns on the edge columns).
@@ -453,8 +479,9 @@ static int launch_group(sm_ctx* ctx, const float* const* vol, const uint32_t* co
   size_t smem = (size_t)CW * NS * stageB + 2 * 2 * CW * runB + 2 * 2 * CW * 4;
   smem = (smem + 7) & ~(size_t)7;
   smem += (size_t)CW * NS * 8;
-  SM_CHECK_ARG(smem <= 227 * 1024);
   int Dp = (D + 1 + 3) & ~3;
+  smem = ((smem + 15) & ~(size_t)15) + 2 * 2 * (size_t)Dp * 4;   // prefetched far rows of the two edge columns
+  SM_CHECK_ARG(smem <= 227 * 1024);
   const size_t rowsBytes = (size_t)nb * H * Dp * sizeof(float);
   void* p;
   SM_TRY(sm_scratch_get(ctx, SM_SCR_SGMEDGE, 2 * NV * rowsBytes, &p));
@@ -517,7 +544,7 @@ static bool group_shape_ok(sm_ctx* ctx, int H, int W, int D, int mode, int nv) {
   const int ns = nv == 2 ? 2 : 4;
   const int nb = min(ctx->num_sms, W / 4);
   const int CW = sm_div_up(W, nb);
-  const size_t smem = (size_t)CW * ns * D * 4 * (mode >= 1 ? 2 : 1) + 4 * (size_t)CW * D * 4 + 16 * CW + CW * ns * 8 + 8;
+  const size_t smem = (size_t)CW * ns * D * 4 * (mode >= 1 ? 2 : 1) + 4 * (size_t)CW * D * 4 + 16 * CW + CW * ns * 8 + 8 + 16 + 16 * (size_t)(D + 4);
   return CW <= 14 && smem <= (size_t)(nv == 2 ? 113 : 227) * 1024;
 }
 

@@ -10,4 +10,8 @@ for r in range(4, 10):
     for w in range(16):
         if t[w, r, 0] == 0: continue
         x = t[w, r, :5] - t0
-        print(f"  col {w:2d}: start {x[0]:7d}  +tma/ld {x[1]-x[0]:5d}  +compute {x[2]-x[1]:5d}  +sum {x[3]-x[2]:5d}  +barriers {x[4]-x[3]:5d}   = {x[4]-x[0]:5d}")
+        extra = ""
+        if t[w, r, 5]:   # edge column: near diagonal + publish, wait for the far row, the other two recurrences
+            y = t[w, r, 5:8] - t0
+            extra = f"   [edge: near+publish {y[1]-y[0]:5d}  far-row wait {y[2]-y[1]:5d}  A+F {x[2]-y[2]:5d}]"
+        print(f"  col {w:2d}: start {x[0]:7d}  +tma/ld {x[1]-x[0]:5d}  +compute {x[2]-x[1]:5d}  +sum {x[3]-x[2]:5d}  +barriers {x[4]-x[3]:5d}   = {x[4]-x[0]:5d}{extra}")

@@ -2,8 +2,9 @@
 import sys
 import numpy as np
 H = int(sys.argv[2])
-t = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, 2, H, 4).astype(np.int64)
-nb = t.shape[0]
+a = np.fromfile(sys.argv[1], dtype=np.uint64).astype(np.int64)
+nb = (a.size - 16 * 32 * 8) // (2 * H * 4)
+t = a[:nb * 2 * H * 4].reshape(nb, 2, H, 4)
 print("ctas", nb)
 for b in (10, 70, 130):
     # last column of CTA b reads what the first column of CTA b+1 published one row earlier
