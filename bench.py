@@ -152,10 +152,13 @@ def host_threads():
 
 
 def have_compiled_reference(name):
-    """oracle/_ref/libsmref.so = the reference's own stereoMatching.{h,cpp} function bodies (oracle/build_ref_sm.py).
-    It covers the CBCA workloads; c4 (NL aggregation inside StereoMatching::NL) stays on the oracle port."""
+    """oracle/_ref/libsmref.so = the reference's own stereoMatching.{h,cpp} function bodies (oracle/build_ref_sm.py);
+    for c4 (aggregation == "NL") also its StereoMatching::NL + NL/NLCCA.cpp over the compiled NL/ sources (libqxref.so)."""
     from oracle import pyoracle as po
-    return AGGREGATION[name] == 1 and po.smref_lib() is not None
+    L = po.smref_lib()
+    if L is None:
+        return False
+    return AGGREGATION[name] == 1 or hasattr(L, "smref_pipeline_nl")
 
 
 def reference_threads(name, rows):
@@ -184,7 +187,9 @@ def run_reference(name, rows, threads, seed0=1000):
 
     def work(p):
         r = po.SmRef(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D)
-        if name in PYRAMID:
+        if AGGREGATION[name] == 2:
+            r.pipeline_nl(P)
+        elif name in PYRAMID:
             r.pipeline_pyr(PYRAMID[name][0], PYRAMID[name][1], P, 2, COSTCALC.get(name, 0))
         else:
             r.pipeline(P, 2, costcalc=COSTCALC.get(name, 0))   # ctypes releases the GIL for the duration of the call
@@ -202,7 +207,7 @@ def run_reference(name, rows, threads, seed0=1000):
 def cpu_baseline(name, budget_rows=48):
     W, H, D, P, kind = WORKLOADS[name]
     if have_compiled_reference(name):
-        rows = min(H, 96)   # tall enough for the vertical arms (<= 34 rows either way)
+        rows = H if H * W * D <= 64 * 2 ** 20 else min(H, 96)   # whole frames when small; else tall enough for the vertical arms (<= 34 rows either way)
         nt = reference_threads(name, rows)
         mde = W * rows * D / 1e6
         t1 = run_reference(name, rows, 1)

@@ -198,15 +198,16 @@ class Mat {
     if (bytes()) memcpy(dst.data, data, bytes());
   }
   // convertTo without scale, for the one conversion the path uses (discontinuityAdjust, stereoMatching.cpp:6060:
-  // CV_16S -> CV_8U with saturate_cast) plus the identity; anything else is a CV_Assert failure
+  // CV_16S -> CV_8U with saturate_cast; NL's CV_16S -> CV_32F) plus the identity; anything else is a CV_Assert failure
   void convertTo(Mat& dst, int rtype) const {
     const int ddepth = rtype & 7;
     if (ddepth == depth()) { Mat t = clone(); dst = t; return; }
-    CV_Assert(depth() == CV_16S && ddepth == CV_8U && dims <= 2);
-    Mat out(rows, cols, CV_MAKETYPE(CV_8U, channels()));
+    CV_Assert(depth() == CV_16S && (ddepth == CV_8U || ddepth == CV_32F) && dims <= 2);
+    Mat out(rows, cols, CV_MAKETYPE(ddepth, channels()));
     const size_t n = total() * channels();
     const short* s = (const short*)data;
-    for (size_t i = 0; i < n; i++) out.data[i] = (uchar)(s[i] < 0 ? 0 : s[i] > 255 ? 255 : s[i]);
+    if (ddepth == CV_8U) for (size_t i = 0; i < n; i++) out.data[i] = (uchar)(s[i] < 0 ? 0 : s[i] > 255 ? 255 : s[i]);
+    else for (size_t i = 0; i < n; i++) ((float*)out.data)[i] = (float)s[i];   // StereoMatching::NL, stereoMatching.cpp:4915
     dst = out;
   }
   Mat& setZero() { if (bytes()) memset(data, 0, bytes()); return *this; }

@@ -69,6 +69,8 @@ CPP_FUNCS = [
     (r"^void StereoMatching::subpixelEnhancement\(", "subpixelEnhancement"),
     (r"^void StereoMatching::WM\(", "WM"),
     (r"^void StereoMatching::discontinuityAdjust\(", "discontinuityAdjust"),
+    # aggregation == "NL": the caller of NLCCA::aggreCV (NL/NLCCA.cpp is compiled as its own translation unit below)
+    (r"^void StereoMatching::NL\(\)", "NL"),
     # the sequential half of vmTop
     (r"^void StereoMatching::genDispFromTopCostVm2\(", "genDispFromTopCostVm2"),
     # the gradient cost family: "censusGrad" is the selector main_.cpp:15 compiles in
@@ -169,13 +171,47 @@ def main():
         raise SystemExit("build_ref_sm: compile-time switch block of stereoMatching.h not found")
     switches = [re.sub(r"\bDo_refine = 0;", "Do_refine = 1;", l) for l in switches]
     h_parts = {n: cut(H, p, n, "stereoMatching.h") for p, n in H_FUNCS}
-    c_parts = [cut(Cc, p, n, "stereoMatching.cpp") for p, n in CPP_FUNCS]
+    c_named = [(n, cut(Cc, p, n, "stereoMatching.cpp")) for p, n in CPP_FUNCS]
 
     tmp = tempfile.mkdtemp(prefix="smref_")
     try:
         tu = os.path.join(tmp, "smref_tu.cpp")
+        # NL/NLCCA.cpp (the glue between StereoMatching::NL and Yang's classes) compiles unchanged next to transient
+        # copies of the NL headers with the same mechanical MSVC -> gcc fixes as build_ref.sh; <opencv2/core.hpp> is
+        # the stand-in.  The qx classes themselves come from oracle/_ref/libqxref.so (build_ref.sh ran first).
+        nl_ok = os.path.isfile(os.path.join(OUT, "libqxref.so")) and os.path.isfile(os.path.join(REF, "NL", "NLCCA.cpp"))
+        nl_objs = []
+        if nl_ok:
+            nld = os.path.join(tmp, "nl")
+            os.makedirs(os.path.join(nld, "opencv2"))
+            for h in ("process.h", "direct.h", "io.h"):
+                open(os.path.join(nld, h), "w").close()
+            for hpp in ("core.hpp", "opencv.hpp"):
+                with open(os.path.join(nld, "opencv2", hpp), "w") as f:
+                    f.write('#pragma once\n#include "cv_standin.h"\n')
+            with open(os.path.join(nld, "prelude.h"), "w") as f:
+                f.write("#include <algorithm>\n#include <cstring>\n#include <cmath>\n#include <cstdlib>\n#include <iostream>\nusing namespace std;\n")
+            for h in ("qx_basic.h", "qx_mst_kruskals_image.h", "qx_tree_filter.h", "ctmf.h", "qx_nonlocal_cost_aggregation.h",
+                      "NLCCA.h", "NLCCA.cpp"):
+                txt = open(os.path.join(REF, "NL", h), "rb").read().decode("latin-1").replace("\r\n", "\n")
+                if h == "qx_basic.h":
+                    txt = re.sub(r"return\(unsigned char\((.*)\)\);}", r"return((unsigned char)(\1));}", txt)
+                with open(os.path.join(nld, h), "w", encoding="latin-1") as f:
+                    f.write(txt)
+            nl_o = os.path.join(tmp, "nlcca.o")
+            cxx0 = os.environ.get("CXX", "g++")
+            r0 = subprocess.run([cxx0, "-O2", "-fPIC", "-std=c++17", "-w", "-fpermissive", "-ffp-contract=off", "-D__int64=long long",
+                                 "-include", os.path.join(nld, "prelude.h"), "-I", nld, "-I", HERE,
+                                 "-I", os.path.join(HERE, "..", "mystereomatching_b200", "host"),
+                                 "-c", os.path.join(nld, "NLCCA.cpp"), "-o", nl_o], capture_output=True, text=True)
+            if r0.returncode != 0:
+                sys.stderr.write(r0.stderr[-4000:])
+                raise SystemExit("build_ref_sm: NLCCA.cpp compile failed")
+            nl_objs = [nl_o, "-L", OUT, "-lqxref", "-Wl,-rpath,$ORIGIN"]
         with open(tu, "w", encoding="latin-1") as f:
             f.write('#include "cv_standin.h"\n')
+            if nl_ok:
+                f.write('#define SMREF_HAVE_NL 1\n#include "%s"\n' % os.path.join(nld, "NLCCA.h"))
             f.write('#include "smref_class_head.inc"\n')      # ours: `class StereoMatching { public:` + statics
             f.write("\n".join(switches) + "\n")
             f.write(h_parts["Parameters"])
@@ -185,14 +221,16 @@ def main():
                 f.write(h_parts[n])
             f.write("};\n")
             f.write('#include "smref_class_tail.inc"\n')      # ours: static member definitions, stubs
-            for part in c_parts:
+            for n, part in c_named:
+                if n == "NL" and not nl_ok:
+                    continue
                 f.write(part)
             f.write('#include "smref_shim.inc"\n')            # ours: extern "C" entry points
         os.makedirs(OUT, exist_ok=True)
         cxx = os.environ.get("CXX", "g++")
         cmd = [cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-w", "-fpermissive", "-ffp-contract=off",
                "-I", HERE, "-I", os.path.join(HERE, "..", "mystereomatching_b200", "host"),
-               tu, "-o", os.path.join(OUT, "libsmref.so")]
+               tu] + (["-D__int64=long long", "-I", os.path.join(tmp, "nl")] if nl_ok else []) + nl_objs + ["-o", os.path.join(OUT, "libsmref.so")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stderr[-6000:])

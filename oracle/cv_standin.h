@@ -87,6 +87,16 @@ inline void pyrDown(const Mat& src, Mat& dst) {
       }
   dst = out;
 }
+// `vm[0] /= wetNL` (StereoMatching::NL, stereoMatching.cpp:4910): element-wise float division of two CV_32F Mats holding
+// the same number of values (both are h x w x d there, as 2-D multi-channel Mats)
+inline Mat& operator/=(Mat& a, const Mat& b) {
+  const size_t n = a.total() * a.channels();
+  if (a.depth() != CV_32F || b.depth() != CV_32F || n != b.total() * b.channels()) { fprintf(stderr, "cv_standin: unsupported operator/=\n"); abort(); }
+  float* x = (float*)a.data;
+  const float* y = (const float*)b.data;
+  for (size_t i = 0; i < n; i++) x[i] = x[i] / y[i];
+  return a;
+}
 namespace ximgproc {
 inline void guidedFilter(const Mat&, const Mat&, Mat&, int, double) {
   fprintf(stderr, "cv_standin: ximgproc::guidedFilter is not available (doGF_bef_calArm must stay false)\n");

@@ -609,6 +609,8 @@ def smref_lib():
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
         fn.argtypes, fn.restype = args, res
+    if hasattr(L, "smref_pipeline_nl"):   # present when NL/NLCCA.cpp + libqxref.so were available at build time
+        L.smref_pipeline_nl.argtypes, L.smref_pipeline_nl.restype = [P, I, P, P, P, P], None
     _SMREF = L
     return L
 
@@ -816,6 +818,20 @@ class SmRef:
         v0, v1 = self._vol(), self._vol()
         self.L.smref_pipeline_pyr(self.h, costcalc, paths, iters, levels, lam, rf.ctypes.data, v0.ctypes.data, v1.ctypes.data)
         return rf, v0, v1
+
+    def has_nl(self):
+        return hasattr(self.L, "smref_pipeline_nl")
+
+    def pipeline_nl(self, paths=4, want_vol=False):
+        """aggregation == "NL": ADCensusCal, the reference's own StereoMatching::NL() over its own NLCCA / qx_tree_filter,
+        dispOptimize, refine.  Returns (wtaL, wtaR, refined, vm[0] right after NL() or None)."""
+        wl = np.empty((self.H, self.W), np.int16)
+        wr = np.empty((self.H, self.W), np.int16)
+        rf = np.empty((self.H, self.W), np.int16)
+        vol = self._vol() if want_vol else None
+        self.L.smref_pipeline_nl(self.h, paths, wl.ctypes.data, wr.ctypes.data, rf.ctypes.data,
+                                 vol.ctypes.data if want_vol else None)
+        return wl, wr, rf, vol
 
     def pipeline(self, paths=4, iters=2, want_vol=False, costcalc=0):
         wl = np.empty((self.H, self.W), np.int16)
