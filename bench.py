@@ -324,9 +324,15 @@ def stage_bytes(name):
     W, H, D, P, kind = WORKLOADS[name]
     V = W * H * D
     b = 2 if COSTCALC.get(name, 0) == 2 else 4
-    if COSTCALC.get(name, 0) == 2:     # native uint16 path: Hamming volume write, 8 single-path sweeps per view
+    if COSTCALC.get(name, 0) == 2:     # native uint16 path: Hamming volume write, then SGM on uint16 volumes
+        if P == 8 and D in (128, 256) and -(-W // min(148, W // 4)) <= 14:
+            # per view: grouped sweep UP (C in, S out = 2 V b), grouped sweep DOWN (3 V b), paths 2 and 3 (3 V b each; the right
+            # view's last path only feeds the fused WTA: 2 V b) -> 21 V b per frame in 8 launches
+            sg = {"bytes_per_launch": 21.0 / 8 * V * b, "launches": 8, "kernel": "k_sgm_group_u16 + k_sgm_path_u16_h"}
+        else:                          # 8 single-path sweeps per view
+            sg = {"bytes_per_launch": (3 * P - 1 - 0.5) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path_u16"}
         return {"cost": {"bytes_per_launch": V * b, "launches": 2, "kernel": "k_cost<HAMMING_U16>"},
-                "sgm": {"bytes_per_launch": (3 * P - 1 - 0.5) * V * b / P, "launches": 2 * P, "kernel": "k_sgm_path_u16"},
+                "sgm": sg,
                 "wta": {"bytes_per_launch": 0, "launches": 2, "kernel": "fused into k_sgm_path_u16 (mode 2 / 3)"}}
     agg = {"bytes_per_launch": 2 * V * b, "launches": 8, "kernel": "k_cbca_pass"}
     if AGGREGATION[name] == 2:   # k_nl = 4 volume passes; MST build + rooting + two tree sweeps

@@ -127,8 +127,14 @@ int smi_sgm_path_packed2(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix,
 
 // 16-bit integer-cost SGM (sgm_u16.cu): fixed point = reduCoeffi1 x the reference's float values
 bool smi_sgm_u16_ok(int D, int paths, int reduCoeffi1, int maxCost);
+// grouped = true: the 8-path table runs as two three-path row sweeps (smi_sgm_group_u16) + the two horizontal sweeps when the
+// shape fits; integer sums are associative, so the result is the same volume either way
 int smi_sgm_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, int H, int W, int D, int paths, int corDifThres,
-                int reduCoeffi1, uint16_t* d_sum, int16_t* d_disp, bool keep_sum);
+                int reduCoeffi1, uint16_t* d_sum, int16_t* d_disp, bool keep_sum, bool grouped = true);
+int smi_sgm_path_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, int H, int W, int D, int path, int corDifThres,
+                     int scale, int mode, uint16_t* d_out, int16_t* d_disp);
+int smi_sgm_group_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, int H, int W, int D, int up, int mode,
+                      int corDifThres, int reduCoeffi1, uint16_t* d_sum);
 
 // grouped SGM sweep (sgm_group.cu): up = 1 -> paths {0,4,5}, up = 0 -> paths {1,6,7}; mode 0 writes, 1 accumulates
 int smi_sgm_group2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const* d_pix, int H, int W, int D, int up, int mode,

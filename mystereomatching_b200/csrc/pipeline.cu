@@ -349,7 +349,7 @@ extern "C" int sm_pipeline_run_device(sm_pipeline* pl) {
     if (pl->u16) {
       for (int i = 0; i < views; i++) {
         SM_TRY(smi_sgm_u16(c, (const uint16_t*)pl->vol[i], pl->pix[i], H, W, D, P.sgm_paths, P.sgm_corDifThres, P.sgm_reduCoeffi1,
-                           (uint16_t*)pl->vol[2], pl->disp[i], keep[i]));
+                           (uint16_t*)pl->vol[2], pl->disp[i], keep[i], P.sgm_grouped != 0));
         float* t = pl->vol[i];
         pl->vol[i] = pl->vol[2];
         pl->vol[2] = t;

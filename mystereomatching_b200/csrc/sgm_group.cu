@@ -572,3 +572,343 @@ int smi_sgm_group2(sm_ctx* ctx, const float* const* d_vol, const uint32_t* const
   return up ? launch_group<8, 1, 2>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu)
             : launch_group<8, 0, 2>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, redu);
 }
+
+// =====================================================================================================================
+// Grouped sweeps on 16-bit integer cost volumes (the native form of the "Census" path, sgm_u16.cu): the same shape as
+// k_sgm_group -- one cooperative launch, one CTA per SM, a warp owns a column, three recurrences per sweep row on one
+// read of C and one read-modify-write of S -- in the fixed point of sgm_u16.cu (Lr * reduCoeffi1, exact), two disparities
+// per packed 16x2 instruction.  Rows are D * 2 bytes; a lane's run of VPL values is NW = VPL / 2 words (one 16- or 8-byte
+// access, conflict-free as it is).  Integer sums are associative, so the grouped order is bit-identical to gen_sgm_vm's.
+// Full shapes only (D == 32 * VPL, VPL = 4 or 8); everything else stays on the single-path kernels.
+#define SGMGU_BIG2 0x3fff3fffu   // "outside [0, D)" in both halves (sgm_u16.cu: SGMU_BIG2)
+
+template <int NW>
+__device__ __forceinline__ void gu_lds(uint32_t a, uint32_t (&x)[NW]) {
+  if (NW == 4) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2 % NW]), "=r"(x[3 % NW]) : "r"(a) : "memory");
+  else asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x[0]), "=r"(x[1]) : "r"(a) : "memory");
+}
+template <int NW>
+__device__ __forceinline__ void gu_sts(uint32_t a, const uint32_t (&x)[NW]) {
+  if (NW == 4) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x[0]), "r"(x[1]), "r"(x[2 % NW]), "r"(x[3 % NW]) : "memory");
+  else asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x[0]), "r"(x[1]) : "memory");
+}
+template <int NW>
+__device__ __forceinline__ void gu_stcg(void* p, const uint32_t (&x)[NW]) {
+  if (NW == 4) __stcg(reinterpret_cast<uint4*>(p), make_uint4(x[0], x[1], x[2 % NW], x[3 % NW]));
+  else __stcg(reinterpret_cast<uint2*>(p), make_uint2(x[0], x[1]));
+}
+template <int NW>
+__device__ __forceinline__ void gu_ld_relaxed(const void* p, uint32_t (&x)[NW]) {
+  if (NW == 4) asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2 % NW]), "=r"(x[3 % NW]) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(x[0]), "=r"(x[1]) : "l"(p) : "memory");
+}
+template <int NW>
+__device__ __forceinline__ bool gu_any_sentinel(const uint32_t (&x)[NW]) {
+  bool s = false;
+#pragma unroll
+  for (int w = 0; w < NW; w++) s |= x[w] == SGMG_SENTINEL;
+  return s;
+}
+
+// One pixel of one path in fixed point (u16_step of sgm_u16.cu): a = Lr' - minP, Lr = C + min(a[d], a[d-1] + P1, a[d+1] + P1, P2)
+template <int NW>
+__device__ __forceinline__ void gu_lr(const uint32_t (&c)[NW], const uint32_t (&pr)[NW], uint32_t minP, bool step, uint32_t scale,
+                                      int lane, uint32_t (&lr)[NW], uint32_t& minNew) {
+  const uint32_t P1 = (step ? 1u : scale) * 0x10001u, P2 = (step ? 3u : 3u * scale) * 0x10001u;
+  const uint32_t negm = ((0x10000u - minP) & 0xffffu) * 0x10001u;
+  uint32_t a[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) a[w] = __vadd2(pr[w], negm);
+  uint32_t lo = __shfl_up_sync(0xffffffffu, a[NW - 1], 1);
+  uint32_t hi = __shfl_down_sync(0xffffffffu, a[0], 1);
+  if (lane == 0) lo = SGMGU_BIG2;
+  if (lane == 31) hi = SGMGU_BIG2;
+  uint32_t m2 = SGMGU_BIG2;
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    const uint32_t pm = __byte_perm(w == 0 ? lo : a[w - 1], a[w], 0x5432);
+    const uint32_t pp = __byte_perm(a[w], w == NW - 1 ? hi : a[w + 1], 0x5432);
+    const uint32_t t1 = __viaddmin_u16x2(pm, P1, a[w]);
+    const uint32_t t2 = __viaddmin_u16x2(pp, P1, P2);
+    lr[w] = __vadd2(c[w], __vminu2(t1, t2));
+    m2 = __vminu2(m2, lr[w]);
+  }
+  minNew = __reduce_min_sync(0xffffffffu, min(m2 & 0xffffu, m2 >> 16));
+}
+template <int NW>
+__device__ __forceinline__ uint32_t gu_rowmin(const uint32_t (&lr)[NW]) {
+  uint32_t m2 = SGMGU_BIG2;
+#pragma unroll
+  for (int w = 0; w < NW; w++) m2 = __vminu2(m2, lr[w]);
+  return __reduce_min_sync(0xffffffffu, min(m2 & 0xffffu, m2 >> 16));
+}
+
+struct sgmgu_view {
+  const uint16_t* vol;
+  const uint32_t* pix;
+  uint16_t* out;
+  uint8_t* rowsP;   // [nb][H][pitchB]: first column of CTA b, the path whose predecessor is column u+1 (read by CTA b-1)
+  uint8_t* rowsM;   // [nb][H][pitchB]: last column of CTA b, the path whose predecessor is column u-1 (read by CTA b+1)
+};
+
+template <int VPL, int UP, int MODE, int NS>
+__global__ void __launch_bounds__(448, 1)
+    k_sgm_group_u16(const sgmgu_view V, int H, int W, int D, int corDifThres, int shift, int pitchB) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  constexpr int NW = VPL / 2;
+  constexpr uint32_t RUN = VPL * 2;          // bytes of a lane's run
+  const int lane = threadIdx.x & 31;
+  const int nwarp = blockDim.x >> 5;
+  const int nb = gridDim.x, b = blockIdx.x;
+  const uint16_t* __restrict__ vol = V.vol;
+  const uint32_t* __restrict__ pix = V.pix;
+  uint16_t* __restrict__ out = V.out;
+  const int u0 = (int)(((long long)b * W) / nb);
+  const int nCols = (int)(((long long)(b + 1) * W) / nb) - u0;
+  if ((int)(threadIdx.x >> 5) >= nCols) return;
+  const int warp = ((int)(threadIdx.x >> 5) + nCols - 2) % nCols;
+  const int u = u0 + warp;
+  const uint32_t runB = (uint32_t)D * 2;     // bytes of a row
+  const uint32_t laneOff = (uint32_t)lane * RUN;
+  const uint32_t scale = 1u << shift;
+  constexpr int ob = UP ? -1 : +1, oc = -ob;
+
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(gsm);
+  const uint32_t stageB = runB * (MODE >= 1 ? 2 : 1);
+  const uint32_t stLo = base + (uint32_t)warp * NS * stageB;
+  const uint32_t exLo = base + (uint32_t)nwarp * NS * stageB;
+  const uint32_t exBufB = (uint32_t)nwarp * runB, exPathB = 2u * exBufB;
+  const uint32_t minLo = exLo + 2 * exPathB;
+  const uint32_t minBufB = (uint32_t)nwarp * 4, minPathB = 2u * minBufB;
+  const uint32_t bars = minLo + 2 * minPathB + (uint32_t)warp * NS * 8;
+  const uint32_t farLo = (minLo + 2 * minPathB + (uint32_t)nwarp * NS * 8 + 15u) & ~15u;
+
+  const long long rowStep = UP ? -(long long)W : (long long)W;
+  const size_t p0 = (size_t)(UP ? H - 1 : 0) * W + u;
+  auto issue = [&](int r, int slot) {
+    const size_t p = (size_t)((long long)p0 + rowStep * r);
+    const uint32_t st = stLo + slot * stageB, bar = bars + slot * 8;
+    g_mbar_expect(bar, stageB);
+    g_bulk(st, vol + p * D, runB, bar);
+    if (MODE >= 1) g_bulk(st + runB, out + p * D, runB, bar);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < NS; s++) g_mbar_init(bars + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int r = 0; r < NS && r < H; r++) issue(r, r);
+  }
+  __syncwarp();
+
+  const bool isFirst = warp == 0, isLast = warp == nCols - 1;
+  const bool special = isFirst || isLast;
+  const int nearOff = isFirst ? +1 : -1;
+  const bool nearIsB = nearOff == ob;
+  const bool nbrCta = isFirst ? b > 0 : b + 1 < nb;
+  uint8_t* pubRow = (isFirst ? V.rowsP : V.rowsM) + (size_t)b * H * pitchB + laneOff;
+  const uint8_t* farRow = (isFirst ? V.rowsM : V.rowsP) + (size_t)(nbrCta ? (isFirst ? b - 1 : b + 1) : b) * H * pitchB + laneOff;
+  const uint8_t* farNext = farRow;
+  const uint32_t minOff = runB - laneOff;   // from a lane's run to the row minimum's word
+  const uint32_t farBuf = farLo + (isLast ? 2u : 0u) * (uint32_t)pitchB;
+
+  const int ub = min(max(u + ob, 0), W - 1) - u, uc = min(max(u + oc, 0), W - 1) - u;
+  uint32_t curO = 0, curB = 0, curC = 0, nxtO = 0, nxtB = 0, nxtC = 0;
+  auto loadChunk = [&](int chunk, uint32_t& o_, uint32_t& b_, uint32_t& c_) {
+    const int rr = chunk * 32 + lane;
+    if (rr < H) {
+      const uint32_t* q = pix + (size_t)((long long)p0 + rowStep * rr);
+      o_ = q[0]; b_ = q[ub]; c_ = q[uc];
+    }
+  };
+  loadChunk(0, curO, curB, curC);
+  loadChunk(1, nxtO, nxtB, nxtC);
+  uint32_t xrow = __shfl_sync(0xffffffffu, curO, 0), xpA = 0, xpB = 0, xpC = 0;
+  uint16_t* o = out + p0 * D + lane * VPL;
+  const long long oStep = rowStep * D;
+
+  uint32_t prevA[NW], minA = 0;
+  int slot = 0;
+  uint32_t parity = 0;
+  const int barL = warp, barR = warp + 1;
+  const bool hasL = warp > 0, hasR = warp + 1 < nCols;
+
+  for (int r = 0; r < H; r++) {
+    const uint32_t bufOff = (r & 1) ? exBufB : 0u, pbufOff = exBufB - bufOff;
+    const uint32_t mbufOff = (r & 1) ? minBufB : 0u, mpbufOff = minBufB - mbufOff;
+    uint32_t c[NW], s[NW], lrA[NW], lrB[NW], lrC[NW];
+    const uint32_t st = stLo + slot * stageB + laneOff;
+    g_mbar_wait(bars + slot * 8, parity);
+    gu_lds<NW>(st, c);
+#pragma unroll
+    for (int w = 0; w < NW; w++) c[w] <<= shift;      // raw cost -> fixed point (halves stay below 2^14: smi_sgm_u16_ok)
+    if (MODE >= 1) gu_lds<NW>(st + runB, s);
+    const uint32_t myB = exLo + bufOff + (uint32_t)warp * runB + laneOff, myC = myB + exPathB;
+    const uint32_t myMinB = minLo + mbufOff + (uint32_t)warp * 4, myMinC = myMinB + minPathB;
+    if (r == 0) {
+      const uint32_t m = gu_rowmin<NW>(c);
+#pragma unroll
+      for (int w = 0; w < NW; w++) lrA[w] = lrB[w] = lrC[w] = c[w];
+      minA = m;
+      if (!special) {
+        gu_sts<NW>(myB, c); gu_sts<NW>(myC, c);
+        if (lane == 0) { g_sts4(myMinB, __uint_as_float(m)); g_sts4(myMinC, __uint_as_float(m)); }
+      } else {
+        if (nbrCta && H > 1) {
+          gu_stcg<NW>(pubRow, c);
+          if (lane == 0) __stcg(reinterpret_cast<uint32_t*>(pubRow + minOff), m);
+        }
+        gu_sts<NW>(nearIsB ? myC : myB, c);
+        if (lane == 0) g_sts4(nearIsB ? myMinC : myMinB, __uint_as_float(m));
+      }
+    } else if (!special) {
+      uint32_t prB[NW], prC[NW];
+      gu_lds<NW>(exLo + pbufOff + (uint32_t)(warp + ob) * runB + laneOff, prB);
+      gu_lds<NW>(exLo + exPathB + pbufOff + (uint32_t)(warp + oc) * runB + laneOff, prC);
+      const uint32_t pmB = __float_as_uint(g_lds4(minLo + mpbufOff + (uint32_t)(warp + ob) * 4));
+      const uint32_t pmC = __float_as_uint(g_lds4(minLo + minPathB + mpbufOff + (uint32_t)(warp + oc) * 4));
+      uint32_t mB, mC, mA;
+      gu_lr<NW>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, scale, lane, lrA, mA);
+      gu_lr<NW>(c, prB, pmB, (int)smd_absdiff_max3(xrow, xpB) > corDifThres, scale, lane, lrB, mB);
+      gu_lr<NW>(c, prC, pmC, (int)smd_absdiff_max3(xrow, xpC) > corDifThres, scale, lane, lrC, mC);
+      minA = mA;
+      gu_sts<NW>(myB, lrB); gu_sts<NW>(myC, lrC);
+      if (lane == 0) { g_sts4(myMinB, __uint_as_float(mB)); g_sts4(myMinC, __uint_as_float(mC)); }
+    } else {
+      uint32_t prN[NW], lrN[NW], lrF[NW], mN, mF, mA;
+      const uint32_t nearPath = nearIsB ? 0u : exPathB, nearMin = nearIsB ? 0u : minPathB;
+      gu_lds<NW>(exLo + nearPath + pbufOff + (uint32_t)(warp + nearOff) * runB + laneOff, prN);
+      const uint32_t pmN = __float_as_uint(g_lds4(minLo + nearMin + mpbufOff + (uint32_t)(warp + nearOff) * 4));
+      const uint32_t xpN = nearIsB ? xpB : xpC, xpF = nearIsB ? xpC : xpB;
+      gu_lr<NW>(c, prN, pmN, (int)smd_absdiff_max3(xrow, xpN) > corDifThres, scale, lane, lrN, mN);
+      if (nbrCta) {
+        if (r + 1 < H) {
+          gu_stcg<NW>(pubRow, lrN);
+          if (lane == 0) __stcg(reinterpret_cast<uint32_t*>(pubRow + minOff), mN);
+        }
+        // the far row: prefetched into shared memory at the end of the previous sweep row; words still carrying the
+        // sentinel were fetched too early and are polled; every word read is re-armed
+        uint32_t prF[NW];
+        const uint32_t fb = farBuf + ((r & 1) ? (uint32_t)pitchB : 0u);
+        g_cpasync_wait0();
+        __syncwarp();
+        gu_lds<NW>(fb + laneOff, prF);
+        while (gu_any_sentinel<NW>(prF)) gu_ld_relaxed<NW>(farRow, prF);
+        {
+          uint32_t arm[NW];
+#pragma unroll
+          for (int w = 0; w < NW; w++) arm[w] = SGMG_SENTINEL;
+          gu_stcg<NW>(const_cast<uint8_t*>(farRow), arm);
+        }
+        uint32_t pmF = __float_as_uint(g_lds4(fb + runB));
+        while (__any_sync(0xffffffffu, pmF == SGMG_SENTINEL)) {
+          if (pmF == SGMG_SENTINEL) pmF = g_ld_relaxed4(farRow + minOff);
+        }
+        if (lane == 0) __stcg(reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(farRow) + minOff), SGMG_SENTINEL);
+        gu_lr<NW>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, scale, lane, lrA, mA);
+        gu_lr<NW>(c, prF, pmF, (int)smd_absdiff_max3(xrow, xpF) > corDifThres, scale, lane, lrF, mF);
+      } else {
+        gu_lr<NW>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, scale, lane, lrA, mA);
+#pragma unroll
+        for (int w = 0; w < NW; w++) lrF[w] = c[w];
+        mF = gu_rowmin<NW>(c);
+      }
+      minA = mA;
+      gu_sts<NW>(nearIsB ? myC : myB, lrF);
+      if (lane == 0) g_sts4(nearIsB ? myMinC : myMinB, __uint_as_float(mF));
+#pragma unroll
+      for (int w = 0; w < NW; w++) { lrB[w] = nearIsB ? lrN[w] : lrF[w]; lrC[w] = nearIsB ? lrF[w] : lrN[w]; }
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) prevA[w] = lrA[w];
+    // ---- path sum (integer: any order is the reference's sum)
+    {
+      uint32_t t[NW];
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        t[w] = __vadd2(__vadd2(lrA[w], lrB[w]), lrC[w]);
+        if (MODE >= 1) t[w] = __vadd2(t[w], s[w]);
+      }
+      if (NW == 4) *reinterpret_cast<uint4*>(o) = make_uint4(t[0], t[1], t[2 % NW], t[3 % NW]);
+      else *reinterpret_cast<uint2*>(o) = make_uint2(t[0], t[1]);
+    }
+    if (special && nbrCta && r + 1 < H) {
+      const uint32_t dst = farBuf + (((r + 1) & 1) ? (uint32_t)pitchB : 0u);
+      if (NW == 4) g_cpasync16(dst + laneOff, farNext);
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + laneOff), "l"(farNext) : "memory");
+      if (lane == 0) g_cpasync16(dst + runB, farNext + runB);   // the quad that holds the row minimum
+      g_cpasync_commit();
+    }
+    xpA = xrow;
+    xpB = __shfl_sync(0xffffffffu, curB, r & 31);
+    xpC = __shfl_sync(0xffffffffu, curC, r & 31);
+    if ((r & 31) == 31) {
+      curO = nxtO; curB = nxtB; curC = nxtC;
+      loadChunk((r >> 5) + 2, nxtO, nxtB, nxtC);
+    }
+    xrow = __shfl_sync(0xffffffffu, curO, (r + 1) & 31);
+    o += oStep;
+    pubRow += pitchB;
+    if (r > 0) farRow += pitchB;
+    farNext += pitchB;
+    __syncwarp();
+    if (lane == 0 && r + NS < H) issue(r + NS, slot);
+    if (++slot == NS) { slot = 0; parity ^= 1u; }
+    if (warp & 1) { if (hasL) g_pair_bar(barL); if (hasR) g_pair_bar(barR); }
+    else          { if (hasR) g_pair_bar(barR); if (hasL) g_pair_bar(barL); }
+  }
+}
+
+template <int VPL, int UP>
+static int launch_group_u16(sm_ctx* ctx, const uint16_t* vol, const uint32_t* pix, uint16_t* out, int H, int W, int D, int mode,
+                            int corDifThres, int shift) {
+  constexpr int NS = 4;
+  const int nb = min(ctx->num_sms, W / 4);
+  const int CW = sm_div_up(W, nb);
+  SM_CHECK_ARG(nb >= 1 && CW <= 14);
+  const size_t runB = (size_t)D * 2;
+  const size_t stageB = runB * (mode >= 1 ? 2 : 1);
+  size_t smem = (size_t)CW * NS * stageB + 2 * 2 * CW * runB + 2 * 2 * CW * 4;
+  smem = (smem + 7) & ~(size_t)7;
+  smem += (size_t)CW * NS * 8;
+  int pitchB = (int)runB + 16;                                  // D values + the row minimum's quad
+  smem = ((smem + 15) & ~(size_t)15) + 2 * 2 * (size_t)pitchB;   // prefetched far rows of the two edge columns
+  SM_CHECK_ARG(smem <= 227 * 1024);
+  const size_t rowsBytes = (size_t)nb * H * pitchB;
+  void* p;
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_SGMEDGE, 2 * rowsBytes, &p));
+  if (ctx->sgm_edge_ptr != p || ctx->sgm_edge_armed < 2 * rowsBytes) {
+    SM_CUDA(cudaMemsetAsync(p, 0xFF, 2 * rowsBytes, ctx->stream));
+    ctx->sgm_edge_ptr = p;
+    ctx->sgm_edge_armed = 2 * rowsBytes;
+  }
+  sgmgu_view v{vol, pix, out, (uint8_t*)p, (uint8_t*)p + rowsBytes};
+  void* args[] = {(void*)&v, (void*)&H, (void*)&W, (void*)&D, (void*)&corDifThres, (void*)&shift, (void*)&pitchB};
+  const void* fn = mode == 0 ? (const void*)k_sgm_group_u16<VPL, UP, 0, NS> : (const void*)k_sgm_group_u16<VPL, UP, 1, NS>;
+  SM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = 0;
+  SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, CW * 32, smem));
+  if (perSM * ctx->num_sms < nb) return SM_ERR_UNSUPPORTED;
+  const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(CW * 32), args, smem, ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->sgm_edge_ptr = nullptr;
+    sm_set_error("%s:%d: cudaLaunchCooperativeKernel -> %s", __FILE__, __LINE__, cudaGetErrorString(e));
+    return SM_ERR_CUDA;
+  }
+  ctx->launches++;
+  return SM_OK;
+}
+
+// up = 1: paths {0, 4, 5}; up = 0: paths {1, 6, 7}.  mode 0: d_sum = group sum, 1: d_sum += group sum (fixed point, as
+// smi_sgm_path_u16).  SM_ERR_UNSUPPORTED when the shape does not fit: the caller runs the three single-path sweeps.
+int smi_sgm_group_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, int H, int W, int D, int up, int mode,
+                      int corDifThres, int reduCoeffi1, uint16_t* d_sum) {
+  if (!(D == 256 || D == 128) || H < 2 || W < 8 || ((((uintptr_t)d_vol | (uintptr_t)d_sum) & 15) != 0)) return SM_ERR_UNSUPPORTED;
+  const int nb = min(ctx->num_sms, W / 4);
+  if (sm_div_up(W, nb) > 14) return SM_ERR_UNSUPPORTED;
+  int sh = 0;
+  while ((1 << sh) < reduCoeffi1) sh++;
+  if (D == 256) return up ? launch_group_u16<8, 1>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, sh)
+                          : launch_group_u16<8, 0>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, sh);
+  return up ? launch_group_u16<4, 1>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, sh)
+            : launch_group_u16<4, 0>(ctx, d_vol, d_pix, d_sum, H, W, D, mode, corDifThres, sh);
+}

@@ -326,7 +326,18 @@ bool smi_sgm_u16_ok(int D, int paths, int reduCoeffi1, int maxCost) {
 }
 
 int smi_sgm_u16(sm_ctx* ctx, const uint16_t* d_vol, const uint32_t* d_pix, int H, int W, int D, int paths, int corDifThres,
-                int reduCoeffi1, uint16_t* d_sum, int16_t* d_disp, bool keep_sum) {
+                int reduCoeffi1, uint16_t* d_sum, int16_t* d_disp, bool keep_sum, bool grouped) {
+  if (paths == 8 && grouped) {
+    // paths {0,4,5} in one upward row sweep, {1,6,7} in one downward sweep (sgm_group.cu), then the two horizontal paths
+    const int rc = smi_sgm_group_u16(ctx, d_vol, d_pix, H, W, D, /*up*/1, /*mode*/0, corDifThres, reduCoeffi1, d_sum);
+    if (rc == SM_OK) {
+      SM_TRY(smi_sgm_group_u16(ctx, d_vol, d_pix, H, W, D, /*up*/0, /*mode*/1, corDifThres, reduCoeffi1, d_sum));
+      SM_TRY(smi_sgm_path_u16(ctx, d_vol, d_pix, H, W, D, 2, corDifThres, reduCoeffi1, 1, d_sum, nullptr));
+      SM_TRY(smi_sgm_path_u16(ctx, d_vol, d_pix, H, W, D, 3, corDifThres, reduCoeffi1, d_disp ? (keep_sum ? 2 : 3) : 1, d_sum, d_disp));
+      return SM_OK;
+    }
+    if (rc != SM_ERR_UNSUPPORTED) return rc;
+  }
   for (int i = 0; i < paths; i++) {
     const int mode = i == 0 ? 0 : (i == paths - 1 && d_disp ? (keep_sum ? 2 : 3) : 1);
     SM_TRY(smi_sgm_path_u16(ctx, d_vol, d_pix, H, W, D, i, corDifThres, reduCoeffi1, mode, d_sum, d_disp));

@@ -817,7 +817,8 @@ def _u16(t):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("shape", [(37, 53, 19), (64, 160, 64), (40, 150, 130), (48, 96, 256), (33, 70, 300), (1, 30, 16), (30, 1, 16)])
+@pytest.mark.parametrize("shape", [(37, 53, 19), (64, 160, 64), (40, 150, 130), (48, 96, 256), (33, 70, 300), (1, 30, 16), (30, 1, 16),
+                                   (40, 700, 128), (36, 1930, 256), (2, 40, 256)])   # D = 128 / 256: the grouped row sweeps (k_sgm_group_u16)
 def test_sgm_u16_is_the_float_reference_exactly(ctx, shape):
     """costScan's integer entry (stereoMatching.cpp:2007-2014) as a native uint16 path: for every path count and power-of-two
     reduCoeffi1 the fixed-point sum equals reduCoeffi1 x the float volume the reference's sgm() leaves, and the fused WTA
