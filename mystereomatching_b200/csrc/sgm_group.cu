@@ -422,6 +422,11 @@ __global__ void __launch_bounds__(448, NV)
 #pragma unroll
     for (int j = 0; j < VPL; j++) prevA[j] = lrA[j];
     if (tl) tl[2] = g_now();
+    // the far row of the NEXT sweep row: the neighbour published it early in this row period (0.25 us after the row top);
+    // requested here, before the path sum, so that its L2 round trip also runs under the sum and the S store (measured
+    // neutral for the float kernel -- the take's own ~0.2 us of instructions remains -- and -1 % for the uint16 one)
+    if (special && nbrCta && r + 1 < H)
+      g_edge_prefetch<VPL>(farNext, nq, D - d0, farBuf + (((r + 1) & 1) ? (uint32_t)E.Dp * 4u : 0u) + (uint32_t)d0 * 4u, lane);
     // ---- path sum (gen_sgm_vm: sum += L[num], within the group in reference path order)
 #pragma unroll
     for (int q = 0; q < VPL / 4; q++)
@@ -435,9 +440,6 @@ __global__ void __launch_bounds__(448, NV)
         }
         *reinterpret_cast<float4*>(o + q * 4) = t;
       }
-    // the far row of the NEXT sweep row: the neighbour published it early in this row period
-    if (special && nbrCta && r + 1 < H)
-      g_edge_prefetch<VPL>(farNext, nq, D - d0, farBuf + (((r + 1) & 1) ? (uint32_t)E.Dp * 4u : 0u) + (uint32_t)d0 * 4u, lane);
     // advance to the next row of the sweep
     xpA = xrow;
     xpB = __shfl_sync(0xffffffffu, curB, r & 31);
@@ -820,6 +822,13 @@ __global__ void __launch_bounds__(448, 1)
     }
 #pragma unroll
     for (int w = 0; w < NW; w++) prevA[w] = lrA[w];
+    if (special && nbrCta && r + 1 < H) {
+      const uint32_t dst = farBuf + (((r + 1) & 1) ? (uint32_t)pitchB : 0u);
+      if (NW == 4) g_cpasync16(dst + laneOff, farNext);
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + laneOff), "l"(farNext) : "memory");
+      if (lane == 0) g_cpasync16(dst + runB, farNext + runB);   // the quad that holds the row minimum
+      g_cpasync_commit();
+    }
     // ---- path sum (integer: any order is the reference's sum)
     {
       uint32_t t[NW];
@@ -830,13 +839,6 @@ __global__ void __launch_bounds__(448, 1)
       }
       if (NW == 4) *reinterpret_cast<uint4*>(o) = make_uint4(t[0], t[1], t[2 % NW], t[3 % NW]);
       else *reinterpret_cast<uint2*>(o) = make_uint2(t[0], t[1]);
-    }
-    if (special && nbrCta && r + 1 < H) {
-      const uint32_t dst = farBuf + (((r + 1) & 1) ? (uint32_t)pitchB : 0u);
-      if (NW == 4) g_cpasync16(dst + laneOff, farNext);
-      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + laneOff), "l"(farNext) : "memory");
-      if (lane == 0) g_cpasync16(dst + runB, farNext + runB);   // the quad that holds the row minimum
-      g_cpasync_commit();
     }
     xpA = xrow;
     xpB = __shfl_sync(0xffffffffu, curB, r & 31);
