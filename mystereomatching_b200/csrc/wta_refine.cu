@@ -363,6 +363,68 @@ __global__ void __launch_bounds__(RV_WARPS * 32)
   }
 }
 
+// 0 < ratio <= 1: the reference's test `(float)(maxCount / validCount) >= ratio` divides two ints, so it holds iff the
+// quotient is 1, i.e. iff EVERY valid vote of the region names the same disparity (< D).  No histogram is needed then: a
+// running minimum and maximum of the votes decide, and the scan of a region stops at the first group of rows in which two
+// different votes (or one >= D) have been seen -- which, around the occlusion borders where the invalid pixels sit, is
+// almost always the first.  Same result as k_rv_vote for these ratios (the tests run both); the other ratios (<= 0: always
+// the mode; > 1: never) keep the histogram kernel.
+__global__ void __launch_bounds__(RV_WARPS * 32)
+    k_rv_vote_agree(const int16_t* __restrict__ src, int16_t* __restrict__ dst, const uint16_t* __restrict__ arms, int H, int W,
+                    int D, int S, const int* __restrict__ count, const int* __restrict__ list) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = *count;
+  for (int e = blockIdx.x * RV_WARPS + warp; e < n; e += gridDim.x * RV_WARPS) {
+    const int p = list[e];
+    const int16_t cur = src[p];
+    const int v = p / W, u = p - v * W;
+    const uint16_t* a = arms + (size_t)p * 5;
+    const int vb = v - a[2], ve = v + a[3];
+    const int nrows = ve - vb + 1;
+    int valid = 0;
+    unsigned lo = 0xffffffffu, hi = 0u;      // votes + 1 (0 = none seen)
+    bool mixed = false;
+    for (int r0 = 0; r0 < nrows && !mixed; r0 += 32) {
+      int ub = 0, ue = -1;
+      if (r0 + lane < nrows) {
+        const uint16_t* b = arms + ((size_t)(vb + r0 + lane) * W + u) * 5;
+        ub = u - b[0]; ue = u + b[1];
+      }
+      const int nr = min(32, nrows - r0);
+      for (int r = 0; r < nr && !mixed; r += 4) {
+        int x[4], un[4], uE[4];
+        const int16_t* row[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int rr = min(r + k, nr - 1);
+          const int b0 = __shfl_sync(0xffffffffu, ub, rr);
+          uE[k] = r + k < nr ? __shfl_sync(0xffffffffu, ue, rr) : INT_MIN;
+          un[k] = b0 + lane;
+          row[k] = src + (size_t)(vb + r0 + rr) * W;
+          x[k] = un[k] <= uE[k] ? (int)row[k][un[k]] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (x[k] >= 0) { valid++; lo = min(lo, (unsigned)x[k] + 1u); hi = max(hi, (unsigned)x[k] + 1u); }
+          for (int w = un[k] + 32; w <= uE[k]; w += 32) {
+            const int y = row[k][w];
+            if (y >= 0) { valid++; lo = min(lo, (unsigned)y + 1u); hi = max(hi, (unsigned)y + 1u); }
+          }
+        }
+        const unsigned wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+        mixed = whi != 0u && (wlo != whi || whi > (unsigned)D);
+      }
+    }
+    int16_t res = cur;
+    if (!mixed) {
+      valid = __reduce_add_sync(0xffffffffu, valid);
+      const unsigned whi = __reduce_max_sync(0xffffffffu, hi);
+      if (valid > S && whi != 0u) res = (int16_t)(whi - 1u);
+    }
+    if (lane == 0) dst[p] = res;
+  }
+}
+
 extern "C" int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, const uint16_t* d_arms, int H, int W, int D,
                               float ratio, int S) {
   SM_CHECK_ARG(ctx && d_disp && d_tmp && d_arms && H > 0 && W > 0 && D > 0 && D <= 1536);   // RV_WARPS histograms of D ints in 48 KB
@@ -375,8 +437,11 @@ extern "C" int sm_region_vote(sm_ctx* ctx, int16_t* d_disp, int16_t* d_tmp, cons
   SM_CUDA(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream));
   SM_LAUNCH(ctx, k_rv_scan, (int)((npix + 255) / 256), 256, 0, d_disp, d_tmp, npix, count, list);
   const int grid = (int)min((long long)ctx->num_sms * 8, (npix + RV_WARPS - 1) / RV_WARPS);
-  SM_LAUNCH(ctx, k_rv_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio, S,
-            count, list);
+  if (ratio > 0.f && ratio <= 1.f)
+    SM_LAUNCH(ctx, k_rv_vote_agree, grid, RV_WARPS * 32, 0, d_disp, d_tmp, d_arms, H, W, D, S, count, list);
+  else
+    SM_LAUNCH(ctx, k_rv_vote, grid, RV_WARPS * 32, RV_WARPS * D * sizeof(int), d_disp, d_tmp, d_arms, H, W, D, ratio, S,
+              count, list);
   SM_CUDA(cudaMemcpyAsync(d_disp, d_tmp, npix * sizeof(int16_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return SM_OK;
 }

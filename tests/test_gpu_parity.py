@@ -933,3 +933,24 @@ def test_disc_adjust_out_of_range_labels_are_not_indices(ctx):
     assert np.array_equal(out.cpu().numpy(), want)
     L = ctx.L
     assert L.sm_discontinuity_adjust(ctx.h, None, None, H, W, D, None) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ratio", [0.4, 1.0, 0.0])
+def test_region_vote_unanimous_regions_and_out_of_range_votes(ctx, ratio):
+    """regionVote_my's integer test (stereoMatching.cpp:7263: maxCount / validCount is an int division): for 0 < ratio <= 1 a
+    pixel changes iff every valid vote of its region agrees -- the early-exit kernel -- incl. regions holding a vote >= D
+    (counted as valid, in no bin: never unanimous); ratio 0 keeps the histogram kernel.  Both against the oracle."""
+    H, W, D = 90, 150, 24
+    rng = np.random.default_rng(77)
+    p = _pair(H, W, D, "texture_warped", seed=31)
+    arms = po.arms(p["bgrL"])
+    d = np.full((H, W), 7, np.int16)
+    d[:, W // 2:] = 11                                   # two constant halves: unanimous regions away from the seam
+    d[40:50, 20:60] = rng.integers(0, D, (10, 40))       # a noisy patch: mixed regions
+    d[rng.random((H, W)) < 0.3] = -32
+    d[10, 10:14] = D + 5                                 # votes >= D
+    ref = po.region_vote(d, arms, D, ratio, 20)
+    got = ctx.region_vote(ctx.dev(d.copy()), ctx.dev(arms.view(np.int16)), D, ratio, 20).cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert ((ref != d) & (d < 0)).sum() > 500            # the unanimous regions did fill their holes
