@@ -84,6 +84,10 @@ __device__ __forceinline__ void g_st_release(int* p, int v) {
 // One pixel of one path: updateCost<float> given the predecessor's Lr row (pr), its minimum and the colour step.
 // Disparities outside [0, D) are FLT_MAX in pr and c: FLT_MAX + P1 rounds back to FLT_MAX, which never wins a
 // minimum against the finite candidates, so no per-disparity range predicate is needed.
+// The additions are issued as packed pairs (add.rn.f32x2 -> FADD2 on sm_100a: two IEEE single-precision additions per
+// instruction, each rounded exactly like the scalar one): pr + P1 is formed once per disparity and serves both as the
+// "d - 1" term of d + 1 and the "d + 1" term of d - 1, so a step costs 1.5 packed additions per disparity pair instead
+// of 3 scalar ones per disparity.  Same operands, same single rounding per sum: bit-identical Lr.
 template <int VPL>
 __device__ __forceinline__ void g_lr(const float (&c)[VPL], const float (&pr)[VPL], float minP, bool step, float P1r, float P2r,
                                      int lane, float (&lr)[VPL], float& minNew) {
@@ -93,13 +97,26 @@ __device__ __forceinline__ void g_lr(const float (&c)[VPL], const float (&pr)[VP
   float hi = __shfl_down_sync(0xffffffffu, pr[0], 1);
   lo = lane == 0 ? FLT_MAX : lo;
   hi = lane == 31 ? FLT_MAX : hi;
+  const float2 P1v = make_float2(P1, P1), nMv = make_float2(-minP, -minP);
+  float q[VPL + 2];   // q[k + 1] = pr[k] + P1, k = -1 .. VPL
+  float a[VPL];       // pr[j] - minP
+  q[0] = lo + P1;
+  q[VPL + 1] = hi + P1;
+#pragma unroll
+  for (int j = 0; j < VPL; j += 2) {
+    const float2 p2 = make_float2(pr[j], pr[j + 1]);
+    const float2 t = __fadd2_rn(p2, P1v), u = __fadd2_rn(p2, nMv);
+    q[j + 1] = t.x; q[j + 2] = t.y;
+    a[j] = u.x; a[j + 1] = u.y;
+  }
   float m = FLT_MAX;
 #pragma unroll
-  for (int j = 0; j < VPL; j++) {
-    const float pm = j == 0 ? lo : pr[j - 1];
-    const float pp = j == VPL - 1 ? hi : pr[j + 1];
-    lr[j] = c[j] + fminf(fminf(pr[j] - minP, pm + P1), fminf(pp + P1, P2));
-    m = fminf(m, lr[j]);
+  for (int j = 0; j < VPL; j += 2) {
+    const float m0 = fminf(fminf(a[j], q[j]), fminf(q[j + 2], P2));
+    const float m1 = fminf(fminf(a[j + 1], q[j + 1]), fminf(q[j + 3], P2));
+    const float2 r = __fadd2_rn(make_float2(c[j], c[j + 1]), make_float2(m0, m1));
+    lr[j] = r.x; lr[j + 1] = r.y;
+    m = fminf(m, fminf(r.x, r.y));
   }
   minNew = g_key2f(__reduce_min_sync(0xffffffffu, g_f2key(m)));
 }
@@ -432,12 +449,14 @@ __global__ void __launch_bounds__(448, NV)
     for (int q = 0; q < VPL / 4; q++)
       if (q < nq) {
         float4 t;
-        float* tp = &t.x;
+        float2 h[2];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int j = 4 * q + e;
-          tp[e] = MODE >= 1 ? ((s[j] + lrA[j]) + lrB[j]) + lrC[j] : (lrA[j] + lrB[j]) + lrC[j];
+        for (int e = 0; e < 2; e++) {
+          const int j = 4 * q + 2 * e;
+          const float2 la = make_float2(lrA[j], lrA[j + 1]), lb = make_float2(lrB[j], lrB[j + 1]), lc = make_float2(lrC[j], lrC[j + 1]);
+          h[e] = MODE >= 1 ? __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(s[j], s[j + 1]), la), lb), lc) : __fadd2_rn(__fadd2_rn(la, lb), lc);
         }
+        t.x = h[0].x; t.y = h[0].y; t.z = h[1].x; t.w = h[1].y;
         *reinterpret_cast<float4*>(o + q * 4) = t;
       }
     // advance to the next row of the sweep
