@@ -9,6 +9,8 @@ the multi-threaded oracle restatement (bit-equal to that library on every golden
   C3  1920x1080 D=256 8 paths, CBCA       grouped-sweep SGM volume <= 1e-6 relative, map >= 99.5 % (in fact identical
                                           for the path order), bad-2 within 0.1 pp
   band 1920x48 D=256                    full-width band vs the compiled reference: bit-equal after cost, CBCA and sgm()
+  C4 and C2 whole frames also vs the COMPILED REFERENCE (its own NL chain; its 8-path composition): bit-equal volumes,
+  identical refined maps (the two tests at the end of the file)
 
 All GPU work goes through the C ABI (libsm_b200.so via ctypes)."""
 import numpy as np
@@ -215,3 +217,46 @@ def test_c3_census_uint16_frame_vs_oracle(ctx):
         assert torch.equal(flat[i:i + step], rf[i:i + step].to(flat.device)), "uint16 path sum"
     pl.close()
     assert np.array_equal(disp, dl), f"{(disp == dl).mean():.6f} identical"
+
+
+# ------------------------------------------------------------------------------------------------ C4 / C2 vs the compiled reference
+@pytest.mark.timeout(600)
+def test_c4_nl_whole_frame_equals_compiled_reference(ctx):
+    """C4 against the reference's OWN chain: ADCensusCal, StereoMatching::NL over NL/NLCCA.cpp + qx_tree_filter (compiled into
+    oracle/_ref/libsmref.so / libqxref.so), 4-path sgm, WTA, refine: vm[0] after NL() bit-equal, refined map identical."""
+    L = po.smref_lib()
+    if L is None or not hasattr(L, "smref_pipeline_nl"):
+        pytest.fail("oracle/_ref/libsmref.so without the NL chain: build() compiles it where /root/reference exists")
+    W, H, D = 640, 480, 64
+    p = synth.make_pair(H, W, D, "texture_warped", seed=1000)
+    r = po.SmRef(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D)
+    wl, wr, rf, vol = r.pipeline_nl(4, True)
+    r.close()
+    _, pl = _gpu_frame(ctx, p, H, W, D, sgm_paths=0, aggregation=2)
+    assert _bits_equal_dev(pl.buffer(0, (H, W, D), torch.float32), vol), "vm[0] after StereoMatching::NL"
+    pl.close()
+    disp, pl = _gpu_frame(ctx, p, H, W, D, sgm_paths=4, aggregation=2)
+    pl.close()
+    assert np.array_equal(disp, rf), f"refined map: {(disp == rf).mean():.6f} identical"
+
+
+@pytest.mark.timeout(900)
+def test_c2_whole_frame_equals_compiled_reference(ctx):
+    """C2 (1280x720 D=128, 8 paths) against the compiled reference's own functions (8-path composition: its direction table,
+    costScan and gen_sgm_vm): with the reference's path order (sgm_grouped = 0) vm[0] after sgm is bit-equal and the refined map
+    identical; the default grouped sweeps give the same map."""
+    if po.smref_lib() is None:
+        pytest.fail("oracle/_ref/libsmref.so missing")
+    W, H, D = 1280, 720, 128
+    p = synth.make_pair(H, W, D, "texture_warped", seed=1000)
+    r = po.SmRef(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D)
+    wl, wr, rf, vol = r.pipeline(paths=8, iters=2, want_vol=True)
+    r.close()
+    disp, pl = _gpu_frame(ctx, p, H, W, D, sgm_paths=8, sgm_grouped=0)
+    assert _bits_equal_dev(pl.buffer(0, (H, W, D), torch.float32), vol), "vm[0] after the 8-path sum in path order"
+    pl.close()
+    assert np.array_equal(disp, rf), f"refined map: {(disp == rf).mean():.6f} identical"
+    disp_g, pl = _gpu_frame(ctx, p, H, W, D, sgm_paths=8)
+    pl.close()
+    assert (disp_g == rf).mean() >= 0.995
+    assert abs(synth.bad_k(disp_g, p["gt"], p["nonocc"], 2) - synth.bad_k(rf, p["gt"], p["nonocc"], 2)) <= 0.1
