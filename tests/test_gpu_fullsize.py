@@ -8,7 +8,7 @@ the multi-threaded oracle restatement (bit-equal to that library on every golden
   C2  1280x720 D=128 8 paths, CBCA      whole frame vs the oracle: CBCA and path-order SGM volumes bit-equal,
   C3  1920x1080 D=256 8 paths, CBCA       grouped-sweep SGM volume <= 1e-6 relative, map >= 99.5 % (in fact identical
                                           for the path order), bad-2 within 0.1 pp
-  band 1920x48 D=256                    full-width band vs the compiled reference: bit-equal after cost, CBCA and sgm()
+  band 1920x144 D=256                   full-width band vs the compiled reference: bit-equal after cost, CBCA and sgm()
   C4 and C2 whole frames also vs the COMPILED REFERENCE (its own NL chain; its 8-path composition): bit-equal volumes,
   identical refined maps (the two tests at the end of the file)
 
@@ -177,7 +177,7 @@ def test_c3_whole_frame_vs_oracle(ctx):
 def test_c3_full_width_band_equals_compiled_reference(ctx):
     if po.smref_lib() is None:
         pytest.fail("oracle/_ref/libsmref.so missing")
-    W, H, D = 1920, 48, 256
+    W, H, D = 1920, 144, 256          # 144 rows: the vertical arms (<= 34 rows either way) reach their full length inside the band
     p = synth.make_pair(H, W, D, "texture_warped", seed=1003)
     r = po.SmRef(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"], D)
     c0, c1 = r.adcensus()
