@@ -84,11 +84,11 @@ __device__ __forceinline__ void g_st_release(int* p, int v) {
 // One pixel of one path: updateCost<float> given the predecessor's Lr row (pr), its minimum and the colour step.
 // Disparities outside [0, D) are FLT_MAX in pr and c: FLT_MAX + P1 rounds back to FLT_MAX, which never wins a
 // minimum against the finite candidates, so no per-disparity range predicate is needed.
-// The additions are issued as packed pairs (add.rn.f32x2 -> FADD2 on sm_100a: two IEEE single-precision additions per
-// instruction, each rounded exactly like the scalar one): pr + P1 is formed once per disparity and serves both as the
-// "d - 1" term of d + 1 and the "d + 1" term of d - 1, so a step costs 1.5 packed additions per disparity pair instead
-// of 3 scalar ones per disparity.  Same operands, same single rounding per sum: bit-identical Lr.
-template <int VPL>
+// PACK (one view per launch, 128 registers at hand): the additions are issued as packed pairs (add.rn.f32x2 -> FADD2 on
+// sm_100a: two IEEE single-precision additions per instruction, each rounded exactly like the scalar one); pr + P1 is formed
+// once per disparity and serves both as the "d - 1" term of d + 1 and the "d + 1" term of d - 1.  Same operands, same
+// single rounding per sum: bit-identical Lr.  The two-view launch (72 registers) keeps the scalar form, which does not spill.
+template <int VPL, bool PACK>
 __device__ __forceinline__ void g_lr(const float (&c)[VPL], const float (&pr)[VPL], float minP, bool step, float P1r, float P2r,
                                      int lane, float (&lr)[VPL], float& minNew) {
   const float P2 = step ? P2r : 3.0f;
@@ -97,26 +97,36 @@ __device__ __forceinline__ void g_lr(const float (&c)[VPL], const float (&pr)[VP
   float hi = __shfl_down_sync(0xffffffffu, pr[0], 1);
   lo = lane == 0 ? FLT_MAX : lo;
   hi = lane == 31 ? FLT_MAX : hi;
-  const float2 P1v = make_float2(P1, P1), nMv = make_float2(-minP, -minP);
-  float q[VPL + 2];   // q[k + 1] = pr[k] + P1, k = -1 .. VPL
-  float a[VPL];       // pr[j] - minP
-  q[0] = lo + P1;
-  q[VPL + 1] = hi + P1;
-#pragma unroll
-  for (int j = 0; j < VPL; j += 2) {
-    const float2 p2 = make_float2(pr[j], pr[j + 1]);
-    const float2 t = __fadd2_rn(p2, P1v), u = __fadd2_rn(p2, nMv);
-    q[j + 1] = t.x; q[j + 2] = t.y;
-    a[j] = u.x; a[j + 1] = u.y;
-  }
   float m = FLT_MAX;
+  if (PACK) {
+    const float2 P1v = make_float2(P1, P1), nMv = make_float2(-minP, -minP);
+    float q[VPL + 2];   // q[k + 1] = pr[k] + P1, k = -1 .. VPL
+    float a[VPL];       // pr[j] - minP
+    q[0] = lo + P1;
+    q[VPL + 1] = hi + P1;
 #pragma unroll
-  for (int j = 0; j < VPL; j += 2) {
-    const float m0 = fminf(fminf(a[j], q[j]), fminf(q[j + 2], P2));
-    const float m1 = fminf(fminf(a[j + 1], q[j + 1]), fminf(q[j + 3], P2));
-    const float2 r = __fadd2_rn(make_float2(c[j], c[j + 1]), make_float2(m0, m1));
-    lr[j] = r.x; lr[j + 1] = r.y;
-    m = fminf(m, fminf(r.x, r.y));
+    for (int j = 0; j < VPL; j += 2) {
+      const float2 p2 = make_float2(pr[j], pr[j + 1]);
+      const float2 t = __fadd2_rn(p2, P1v), u = __fadd2_rn(p2, nMv);
+      q[j + 1] = t.x; q[j + 2] = t.y;
+      a[j] = u.x; a[j + 1] = u.y;
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; j += 2) {
+      const float m0 = fminf(fminf(a[j], q[j]), fminf(q[j + 2], P2));
+      const float m1 = fminf(fminf(a[j + 1], q[j + 1]), fminf(q[j + 3], P2));
+      const float2 r = __fadd2_rn(make_float2(c[j], c[j + 1]), make_float2(m0, m1));
+      lr[j] = r.x; lr[j + 1] = r.y;
+      m = fminf(m, fminf(r.x, r.y));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < VPL; j++) {
+      const float pm = j == 0 ? lo : pr[j - 1];
+      const float pp = j == VPL - 1 ? hi : pr[j + 1];
+      lr[j] = c[j] + fminf(fminf(pr[j] - minP, pm + P1), fminf(pp + P1, P2));
+      m = fminf(m, lr[j]);
+    }
   }
   minNew = g_key2f(__reduce_min_sync(0xffffffffu, g_f2key(m)));
 }
@@ -389,9 +399,9 @@ __global__ void __launch_bounds__(448, NV)
       const float pmB = g_lds4(minLo + mpbufOff + (uint32_t)(warp + ob) * 4);
       const float pmC = g_lds4(minLo + minPathB + mpbufOff + (uint32_t)(warp + oc) * 4);
       float mB, mC, mA;
-      g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
-      g_lr<VPL>(c, prB, pmB, (int)smd_absdiff_max3(xrow, xpB) > corDifThres, P1r, P2r, lane, lrB, mB);
-      g_lr<VPL>(c, prC, pmC, (int)smd_absdiff_max3(xrow, xpC) > corDifThres, P1r, P2r, lane, lrC, mC);
+      g_lr<VPL, NV == 1>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
+      g_lr<VPL, NV == 1>(c, prB, pmB, (int)smd_absdiff_max3(xrow, xpB) > corDifThres, P1r, P2r, lane, lrB, mB);
+      g_lr<VPL, NV == 1>(c, prC, pmC, (int)smd_absdiff_max3(xrow, xpC) > corDifThres, P1r, P2r, lane, lrC, mC);
       minA = mA;
       g_strow<VPL, XQ>(myB, nq, lrB); g_strow<VPL, XQ>(myC, nq, lrC);
       if (lane == 0) { g_sts4(myMinB, mB); g_sts4(myMinC, mC); }
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(448, NV)
       g_ldrow<VPL, XQ>(exLo + nearPath + pbufOff + (uint32_t)(warp + nearOff) * runB + exOff, nq, prN);
       const float pmN = g_lds4(minLo + nearMin + mpbufOff + (uint32_t)(warp + nearOff) * 4);
       const uint32_t xpN = nearIsB ? xpB : xpC, xpF = nearIsB ? xpC : xpB;
-      g_lr<VPL>(c, prN, pmN, (int)smd_absdiff_max3(xrow, xpN) > corDifThres, P1r, P2r, lane, lrN, mN);
+      g_lr<VPL, NV == 1>(c, prN, pmN, (int)smd_absdiff_max3(xrow, xpN) > corDifThres, P1r, P2r, lane, lrN, mN);
       if (nbrCta) {
         if (r + 1 < H) {   // the neighbour reads this row at ITS row r + 1
 #pragma unroll
@@ -422,10 +432,10 @@ __global__ void __launch_bounds__(448, NV)
         g_edge_take<VPL>(farRow, nq, D - d0, fb + (uint32_t)d0 * 4u, fb + (uint32_t)D * 4u, prF, pmF, polls);
         if (tr && lane == 0) { tr[2] = g_now(); tr[3] = (unsigned long long)polls; }
         if (tl) tl[7] = g_now();
-        g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
-        g_lr<VPL>(c, prF, pmF, (int)smd_absdiff_max3(xrow, xpF) > corDifThres, P1r, P2r, lane, lrF, mF);
+        g_lr<VPL, NV == 1>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
+        g_lr<VPL, NV == 1>(c, prF, pmF, (int)smd_absdiff_max3(xrow, xpF) > corDifThres, P1r, P2r, lane, lrF, mF);
       } else {   // predecessor column outside the image: Lr = C
-        g_lr<VPL>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
+        g_lr<VPL, NV == 1>(c, prevA, minA, (int)smd_absdiff_max3(xrow, xpA) > corDifThres, P1r, P2r, lane, lrA, mA);
 #pragma unroll
         for (int j = 0; j < VPL; j++) lrF[j] = c[j];
         mF = g_rowmin<VPL>(c);
@@ -449,14 +459,23 @@ __global__ void __launch_bounds__(448, NV)
     for (int q = 0; q < VPL / 4; q++)
       if (q < nq) {
         float4 t;
-        float2 h[2];
+        if (NV == 1) {
+          float2 h[2];
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int j = 4 * q + 2 * e;
-          const float2 la = make_float2(lrA[j], lrA[j + 1]), lb = make_float2(lrB[j], lrB[j + 1]), lc = make_float2(lrC[j], lrC[j + 1]);
-          h[e] = MODE >= 1 ? __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(s[j], s[j + 1]), la), lb), lc) : __fadd2_rn(__fadd2_rn(la, lb), lc);
+          for (int e = 0; e < 2; e++) {
+            const int j = 4 * q + 2 * e;
+            const float2 la = make_float2(lrA[j], lrA[j + 1]), lb = make_float2(lrB[j], lrB[j + 1]), lc = make_float2(lrC[j], lrC[j + 1]);
+            h[e] = MODE >= 1 ? __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(s[j], s[j + 1]), la), lb), lc) : __fadd2_rn(__fadd2_rn(la, lb), lc);
+          }
+          t.x = h[0].x; t.y = h[0].y; t.z = h[1].x; t.w = h[1].y;
+        } else {
+          float* tp = &t.x;
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int j = 4 * q + e;
+            tp[e] = MODE >= 1 ? ((s[j] + lrA[j]) + lrB[j]) + lrC[j] : (lrA[j] + lrB[j]) + lrC[j];
+          }
         }
-        t.x = h[0].x; t.y = h[0].y; t.z = h[1].x; t.w = h[1].y;
         *reinterpret_cast<float4*>(o + q * 4) = t;
       }
     // advance to the next row of the sweep
