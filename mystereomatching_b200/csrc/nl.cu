@@ -14,7 +14,7 @@
 // (mutual picks keep the smaller label as the root), labels are flattened by pointer jumping; <= log2(N) rounds.
 // The tree is then rooted at pixel 0 (NL/qx_mst_kruskals_image.cpp:233) WITHOUT a level-by-level walk: parent, depth
 // and the level order follow from the tree's Euler tour by list ranking (pointer jumping), an inclusive scan and a
-// stable sort by depth (nl_root_euler; O(log N) data-parallel steps).
+// stable sort by depth (nl_root_euler; O(log N) data-parallel steps; scan and radix sort are kernels of this file).
 // A node's children are kept in increasing key order, which is the order Kruskal appended them to the adjacency
 // list and therefore the order in which the reference's leaf-to-root pass adds them (bit-identical f64 sums).
 //
@@ -30,8 +30,6 @@
 
 #include <stdlib.h>
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -201,7 +199,7 @@ struct nl_sync {
 //   * list ranking by pointer jumping gives every edge its position in the tour;
 //   * an edge is DOWNWARD (u is v's parent) iff it comes before its reverse; parent[v] = u, wpar[v] = its weight;
 //   * +1 for downward, -1 for upward edges, inclusive scan over the tour: the value at a downward edge is depth(v);
-//   * a stable radix sort of the nodes by depth (tour order within a level) is the level order.
+//   * a stable radix sort of the nodes by depth (node order within a level) is the level order.
 // Identical parent / weight / rank to the BFS (a rooted tree has one parent function); `order` is grouped by level,
 // which is all the filter needs (its results do not depend on the order inside a level).
 #define ET_END (-1)
@@ -253,15 +251,139 @@ __global__ void k_et_classify(int N, int T, const int4* __restrict__ nbr, const 
   node_at[pe] = down ? v : -1;
   if (down) { parent[v] = u; wpar[v] = (uint8_t)wk; }
 }
-// after the inclusive scan: depth of the node entered by the downward edge at tour position p; sort keys / values
-__global__ void k_et_keys(int N, int T, const int* __restrict__ scan, const int* __restrict__ node_at, int* __restrict__ rank,
-                          unsigned* __restrict__ keys, int* __restrict__ vals) {
+// after the inclusive scan: depth of the node entered by the downward edge at tour position p
+__global__ void k_et_depth(int T, const int* __restrict__ scan, const int* __restrict__ node_at, int* __restrict__ rank) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > T) return;
-  if (i == 0) { keys[0] = 0u; vals[0] = 0; rank[0] = 0; return; }   // the root leads the order
+  if (i == 0) { rank[0] = 0; return; }
   const int p = i - 1, v = node_at[p];
-  if (v >= 0) { const int d = scan[p]; rank[v] = d; keys[i] = (unsigned)d; vals[i] = v; }
-  else { keys[i] = 0x7fffffffu; vals[i] = -1; }                     // upward edges sort behind every node
+  if (v >= 0) rank[v] = scan[p];
+}
+
+// ------------------------------------------------------------------ scan and stable radix sort (the two library-shaped steps
+// of the rooting, written out: a three-kernel tile scan and an LSD radix sort, 8 bits per pass)
+#define NLP_TB 256
+#define NLP_IT 8
+#define NLP_TILE (NLP_TB * NLP_IT)
+
+// inclusive (EXCL = false) or exclusive scan of every 2048-element tile on its own; sums[tile] = the tile's total
+template <bool EXCL>
+__global__ void __launch_bounds__(NLP_TB) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ sums) {
+  __shared__ int wsum[NLP_TB / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int base = blockIdx.x * NLP_TILE + tid * NLP_IT;
+  int v[NLP_IT], run = 0;
+#pragma unroll
+  for (int j = 0; j < NLP_IT; j++) { v[j] = base + j < n ? in[base + j] : 0; run += v[j]; }
+  int inc = run;   // inclusive scan of the thread totals inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; w++) woff += wsum[w];
+  int acc = woff + inc - run;   // exclusive prefix of this thread inside the tile
+#pragma unroll
+  for (int j = 0; j < NLP_IT; j++) {
+    const int e = acc;
+    acc += v[j];
+    if (base + j < n) out[base + j] = EXCL ? e : acc;
+  }
+  if (tid == NLP_TB - 1) sums[blockIdx.x] = acc;
+}
+// exclusive scan of the tile totals in place (one block; any number of tiles, 1024 at a time with a carry)
+__global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ sums, int nt) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < nt; c0 += 1024) {
+    const int i = c0 + tid;
+    const int x = i < nt ? sums[i] : 0;
+    int inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; w++) woff += wsum[w];
+    const int c = carry;
+    if (i < nt) sums[i] = c + woff + inc - x;
+    __syncthreads();
+    if (tid == 1023) carry = c + woff + inc;
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(int* __restrict__ out, int n, const int* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += sums[i / NLP_TILE];
+}
+// out = scan(in) over n ints; sums: ceil(n / 2048) ints of scratch
+template <bool EXCL>
+static int nl_scan(sm_ctx* ctx, const int* in, int* out, int n, int* sums) {
+  const int nt = sm_div_up(n, NLP_TILE);
+  SM_LAUNCH(ctx, k_scan_tiles<EXCL>, nt, NLP_TB, 0, in, out, n, sums);
+  if (nt > 1) {
+    SM_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, sums, nt);
+    SM_LAUNCH(ctx, k_scan_add, sm_div_up(n, 256), 256, 0, out, n, sums);
+  }
+  return SM_OK;
+}
+
+// one 8-bit pass of a stable LSD radix sort: per-tile digit histogram, hist[digit][tile]
+__global__ void __launch_bounds__(NLP_TB) k_rs_hist(const unsigned* __restrict__ keys, int n, int shift, int* __restrict__ hist, int nt) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * NLP_TILE;
+  for (int j = 0; j < NLP_IT; j++) {
+    const int i = base + j * NLP_TB + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nt + blockIdx.x] = h[threadIdx.x];
+}
+// scatter with the scanned histogram: an item goes to offs[digit][tile] + (items of the same digit before it in the tile).
+// Rounds of 256 consecutive items; inside a round the rank comes from a warp match + the counts of the warps before.
+__global__ void __launch_bounds__(NLP_TB) k_rs_scatter(const unsigned* __restrict__ keys, const int* __restrict__ vals, unsigned* __restrict__ keys2,
+                                                      int* __restrict__ vals2, int n, int shift, const int* __restrict__ offs, int nt) {
+  __shared__ int basePos[256];
+  __shared__ int cnt[NLP_TB / 32][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  basePos[tid] = offs[(size_t)tid * nt + blockIdx.x];
+  const int base = blockIdx.x * NLP_TILE;
+  for (int j = 0; j < NLP_IT; j++) {
+    const int i = base + j * NLP_TB + tid;
+    const bool valid = i < n;
+    const unsigned key = valid ? keys[i] : 0u;
+    const int val = valid ? vals[i] : 0;
+    const unsigned dg = valid ? ((key >> shift) & 255u) : 256u;   // 256: the items past the end group among themselves
+#pragma unroll
+    for (int w = 0; w < NLP_TB / 32; w++) cnt[w][tid] = 0;
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, dg);
+    const int lrank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && lrank == 0) cnt[warp][dg] = __popc(peers);
+    __syncthreads();
+    int pos = 0;
+    if (valid) {
+      int before = 0;
+      for (int w = 0; w < warp; w++) before += cnt[w][dg];
+      pos = basePos[dg] + before + lrank;
+    }
+    __syncthreads();
+    int add = 0;
+#pragma unroll
+    for (int w = 0; w < NLP_TB / 32; w++) add += cnt[w][tid];
+    basePos[tid] += add;
+    __syncthreads();
+    if (valid) { keys2[pos] = key; vals2[pos] = val; }
+  }
+}
+__global__ void k_rs_init(int N, const int* __restrict__ rank, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) { keys[v] = (unsigned)rank[v]; vals[v] = v; }
 }
 
 // rooted tree from the adjacency by the Euler tour; returns SM_OK and fills parent / wpar / rank / order /
@@ -954,20 +1076,19 @@ static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw,
                          uint8_t* wpar, int* rank, int* order, int* level_start, nl_sync* sync) {
   if (N == 1) { SM_LAUNCH(ctx, k_root_single, 1, 1, 0, parent, wpar, rank, order, level_start, sync); return SM_OK; }
   const int T = 2 * (N - 1), n4 = 4 * N, TB = 256;
-  size_t tmpScan = 0, tmpSort = 0;
-  SM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpScan, (const int*)nullptr, (int*)nullptr, T, ctx->stream));
-  SM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
-                                          (int*)nullptr, T + 1, 0, 32, ctx->stream));
-  const size_t tmpB = (max(tmpScan, tmpSort) + 255) & ~(size_t)255;
-  // succ | dist | succ2 | dist2 (4N ints each) ; pm | node_at | scan (T) ; keys | keys2 | vals | vals2 (T+1) ; cub
-  const size_t ints = (size_t)4 * n4 + (size_t)3 * T + (size_t)4 * (T + 1) + 64;
+  const int nt = sm_div_up(N, NLP_TILE);            // tiles of a sort pass
+  const int nh = 256 * nt;                          // histogram entries of a pass
+  // succ | dist | succ2 | dist2 (4N ints each) ; pm | node_at | scan (T) ; keys | keys2 | vals | vals2 (N) ;
+  // hist | offs (256 nt) ; sums (tiles of the longest scan)
+  const int nsums = max(sm_div_up(T, NLP_TILE), sm_div_up(nh, NLP_TILE)) + 8;
+  const size_t ints = (size_t)4 * n4 + (size_t)3 * T + (size_t)4 * N + (size_t)2 * nh + nsums + 64;
   void* p;
-  SM_TRY(sm_scratch_get(ctx, SM_SCR_NLEULER, ints * 4 + tmpB, &p));
+  SM_TRY(sm_scratch_get(ctx, SM_SCR_NLEULER, ints * 4, &p));
   int* succ = (int*)p; int* dist = succ + n4; int* succ2 = dist + n4; int* dist2 = succ2 + n4;
   int* pm = dist2 + n4; int* node_at = pm + T; int* scan = node_at + T;
-  unsigned* keys = (unsigned*)(scan + T); unsigned* keys2 = keys + (T + 1);
-  int* vals = (int*)(keys2 + (T + 1)); int* vals2 = vals + (T + 1);
-  void* tmp = (void*)(((uintptr_t)(vals2 + (T + 1)) + 255) & ~(uintptr_t)255);
+  unsigned* keys = (unsigned*)(scan + T); unsigned* keys2 = keys + N;
+  int* vals = (int*)(keys2 + N); int* vals2 = vals + N;
+  int* hist = vals2 + N; int* offs = hist + nh; int* sums = offs + nh;
   SM_LAUNCH(ctx, k_et_init, sm_div_up(n4, TB), TB, 0, N, (const int4*)nbr, deg, succ, dist);
   for (long long span = 1; span < T; span *= 2) {   // list ranking: ceil(log2 T) jumps
     SM_LAUNCH(ctx, k_et_jump, sm_div_up(n4, TB), TB, 0, n4, succ, dist, succ2, dist2);
@@ -977,16 +1098,21 @@ static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw,
   SM_LAUNCH(ctx, k_et_classify, sm_div_up(n4, TB), TB, 0, N, T, (const int4*)nbr, (const uchar4*)nbw, deg, dist, parent, wpar, pm,
             node_at);
   SM_LAUNCH(ctx, k_root_fix, 1, 1, 0, parent, wpar);
-  size_t tb = tmpB;
-  SM_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, pm, scan, T, ctx->stream));
-  ctx->launches += 2;
-  SM_LAUNCH(ctx, k_et_keys, sm_div_up(T + 1, TB), TB, 0, N, T, scan, node_at, rank, keys, vals);
+  SM_TRY(nl_scan<false>(ctx, pm, scan, T, sums));   // +1 / -1 along the tour: the value at a downward edge is the depth
+  SM_LAUNCH(ctx, k_et_depth, sm_div_up(T + 1, TB), TB, 0, T, scan, node_at, rank);
+  // level order = the nodes sorted by depth (stable, from node order): depth < N, 8 bits per pass
+  SM_LAUNCH(ctx, k_rs_init, sm_div_up(N, TB), TB, 0, N, rank, keys, vals);
   int bits = 1;
-  while (bits < 31 && (1ll << bits) <= (long long)N) bits++;   // depth < N; the sentinel 0x7fffffff needs bit 30..: sort all 31 bits
-  tb = tmpB;
-  SM_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, vals, vals2, T + 1, 0, 31, ctx->stream));
-  ctx->launches += 8;
-  SM_CUDA(cudaMemcpyAsync(order, vals2, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  while (bits < 31 && (1ll << bits) < (long long)N) bits++;
+  const int passes = sm_div_up(bits, 8);
+  for (int ps = 0; ps < passes; ps++) {
+    int* vout = ps == passes - 1 ? order : vals2;   // the last pass writes the level order itself
+    SM_LAUNCH(ctx, k_rs_hist, nt, NLP_TB, 0, keys, N, 8 * ps, hist, nt);
+    SM_TRY(nl_scan<true>(ctx, hist, offs, nh, sums));
+    SM_LAUNCH(ctx, k_rs_scatter, nt, NLP_TB, 0, keys, vals, keys2, vout, N, 8 * ps, offs, nt);
+    unsigned* tk = keys; keys = keys2; keys2 = tk;
+    int* tv = vals; vals = vals2; vals2 = tv;
+  }
   SM_LAUNCH(ctx, k_level_bounds, min(sm_div_up(N, TB), ctx->num_sms * 8), TB, 0, N, rank, order, level_start, sync);
   return SM_OK;
 }

@@ -340,6 +340,27 @@ def test_mst_identical_to_reference_tree(ctx, name):
     assert np.array_equal(ctx.median_u8(ctx.dev(img), 1).cpu().numpy(), po.ctmf(img, 1))
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("shape", [(1080, 1920), (480, 640), (9, 2049)])
+def test_mst_rooting_large_frames(ctx, shape):
+    """The rooting's own scan / radix sort across many tiles (1080p: 2 M nodes, a 4 M-edge tour = 2025 scan tiles, more
+    than one round of the tile-sum kernel; depths need three 8-bit passes): same tree, depth and a level-grouped order."""
+    H, W = shape
+    rng = np.random.default_rng(H + W)
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = ((xx // 7 + yy // 5) % 256).astype(np.uint8)
+    img = np.stack([base, base // 2, rng.integers(0, 4, (H, W), dtype=np.uint8)], -1).astype(np.uint8)
+    t = ctx.mst_build(ctx.dev(img))
+    ref = po.mst(img)
+    parent, weight, rank, order = (t[k].cpu().numpy() for k in ("parent", "weight", "rank", "order"))
+    assert np.array_equal(parent[1:], ref["parent"][1:]) and parent[0] == 0
+    assert np.array_equal(weight[1:], ref["weight"][1:])
+    assert np.array_equal(rank, ref["rank"])
+    assert np.array_equal(np.sort(order), np.arange(H * W))
+    assert np.all(np.diff(rank[order]) >= 0)
+    assert order[0] == 0
+
+
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("name,D", [("noisy", 6), ("smooth", 5), ("flat", 3), ("tex", 33)])
 def test_tree_filter_bit_exact(ctx, name, D):
