@@ -33,6 +33,9 @@ struct sm_pipeline {
   // filling the GPU): the two views' sweeps run concurrently, view 1 on a second stream
   cudaStream_t stream2 = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaStream_t streamA = nullptr;   // arms of both images under the cost kernels (ADCensus + CBCA frames)
+  cudaEvent_t evA0 = nullptr, evA1 = nullptr;
+  bool arms_pending = false;
   sm_pipeline* child = nullptr;   // next pyramid level (cost + aggregation only), pyramidLevels > 1
   bool is_child = false;
   bool have_gray = false, have_arms = false, scale_folded = false;
@@ -63,6 +66,9 @@ extern "C" int sm_pipeline_destroy(sm_pipeline* pl) {
   if (pl->stream2) cudaStreamDestroy(pl->stream2);
   if (pl->evFork) cudaEventDestroy(pl->evFork);
   if (pl->evJoin) cudaEventDestroy(pl->evJoin);
+  if (pl->streamA) cudaStreamDestroy(pl->streamA);
+  if (pl->evA0) cudaEventDestroy(pl->evA0);
+  if (pl->evA1) cudaEventDestroy(pl->evA1);
   cudaFree(pl->nlwork);
   cudaFree(pl->top);
   cudaFree(pl->dtmp);
@@ -119,6 +125,12 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
     if (cudaStreamCreateWithFlags(&pl->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming) != cudaSuccess)
+      rc = SM_ERR_CUDA;
+  }
+  if (rc == SM_OK && p->aggregation == 1 && p->costcalculation == 0) {
+    if (cudaStreamCreateWithFlags(&pl->streamA, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evA0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evA1, cudaEventDisableTiming) != cudaSuccess)
       rc = SM_ERR_CUDA;
   }
   if (rc == SM_OK) rc = pl_alloc(ctx, (void**)&pl->dtmp, npix * 2);
@@ -241,6 +253,18 @@ static int pl_cost_calculate(sm_pipeline* pl) {
   pl->have_arms = false;
   auto ensure_arms = [&]() -> int { return pl_ensure_arms(pl); };
   if (P.costcalculation == 0) {
+    if (pl->streamA && P.aggregation == 1) {
+      // the arm maps depend on the packed images alone: built on a side stream while the cost kernels run
+      SM_CUDA(cudaEventRecord(pl->evA0, c->stream));
+      SM_CUDA(cudaStreamWaitEvent(pl->streamA, pl->evA0, 0));
+      cudaStream_t main_stream = c->stream;
+      c->stream = pl->streamA;
+      const int rcA = pl_ensure_arms(pl);
+      c->stream = main_stream;
+      SM_TRY(rcA);
+      SM_CUDA(cudaEventRecord(pl->evA1, pl->streamA));
+      pl->arms_pending = true;
+    }
     for (int i = 0; i < imgNum; i++)
       SM_TRY(smi_cost_adcensus_packed(c, pl->pix[0], pl->pix[1], pl->cen[0], pl->cen[1], H, W, D, P.censusFunc,
                                       P.adTrunc, P.lamAD, P.lamCen, i, pl->vol[i]));
@@ -260,6 +284,10 @@ static int pl_cost_calculate(sm_pipeline* pl) {
   }
   PL_MARK(2);
   // ---- aggregation
+  if (pl->arms_pending) {
+    SM_CUDA(cudaStreamWaitEvent(c->stream, pl->evA1, 0));
+    pl->arms_pending = false;
+  }
   if (P.aggregation == 1) {
     SM_TRY(ensure_arms());
     PL_MARK(3);
