@@ -118,6 +118,8 @@ int smi_cbca_packed(sm_ctx* ctx, float* d_vol, float* d_tmp, const uint32_t* d_a
 int smi_arms_packed(sm_ctx* ctx, const uint32_t* d_pix, int H, int W, int L, int L_out, int tau, int tau_out, int minL,
                     uint16_t* d_arms);
 int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D);
+int smi_nl_tree(sm_ctx* ctx, const uint8_t* d_bgrL, int H, int W);
+int smi_nl_filter(sm_ctx* ctx, float* d_vol, double* d_work, int H, int W, int D);
 int smi_sgm_path_packed(sm_ctx* ctx, const float* d_vol, const uint32_t* d_pix, int H, int W, int D, int path,
                         int corDifThres, int reduCoeffi1, int mode, float* d_out);
 // mode 2: accumulate and write the WTA of the finished sum into d_disp (last path of a view); mode 3: the WTA alone,

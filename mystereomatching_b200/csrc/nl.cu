@@ -1307,8 +1307,9 @@ extern "C" int sm_tree_filter_f64(sm_ctx* ctx, double* d_cost, int H, int W, int
   return nl_filter(ctx, nullptr, d_cost, H, W, D, false, t, sigma);
 }
 
-int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D) {
-  // d_work: H*W*(D+1) doubles
+// StereoMatching::NL in two halves, so that the pipeline can build the tree (which needs the image alone) on a side stream
+// while the cost kernels run: the tree lives in the ctx scratch slots between the two calls.
+int smi_nl_tree(sm_ctx* ctx, const uint8_t* d_bgrL, int H, int W) {
   const int N = H * W;
   void* p_img;
   SM_TRY(sm_scratch_get(ctx, SM_SCR_IMG0, (size_t)N * 3, &p_img));
@@ -1318,7 +1319,17 @@ int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int
   SM_TRY(nl_build_tree(ctx, (const uint8_t*)p_img, H, W, 3, t));
   const int TB = 256;
   SM_LAUNCH(ctx, k_children_from_parent, sm_div_up(N, TB), TB, 0, H, W, t.parent, t.wpar, t.child, t.nchild);
+  return SM_OK;
+}
+int smi_nl_filter(sm_ctx* ctx, float* d_vol, double* d_work, int H, int W, int D) {
+  // d_work: H*W*(D+1) doubles
+  nl_tree t;
+  SM_TRY(nl_tree_scratch(ctx, H * W, t, true));   // (same sizes as in smi_nl_tree: the same buffers)
   return nl_filter(ctx, d_vol, d_work, H, W, D, true, t, 0.1);   // sigma: NL/NLCCA.cpp:33
+}
+int smi_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, double* d_work, int H, int W, int D) {
+  SM_TRY(smi_nl_tree(ctx, d_bgrL, H, W));
+  return smi_nl_filter(ctx, d_vol, d_work, H, W, D);
 }
 
 extern "C" int sm_nl(sm_ctx* ctx, const uint8_t* d_bgrL, float* d_vol, int H, int W, int D) {

@@ -33,7 +33,8 @@ struct sm_pipeline {
   // filling the GPU): the two views' sweeps run concurrently, view 1 on a second stream
   cudaStream_t stream2 = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
-  cudaStream_t streamA = nullptr;   // arms of both images under the cost kernels (ADCensus + CBCA frames)
+  cudaStream_t streamA = nullptr;   // arms of both images (CBCA frames) / the MST build (NL frames) under the cost kernels
+  bool nl_tree_pending = false;     // NL frames: the tree is being built on streamA
   cudaEvent_t evA0 = nullptr, evA1 = nullptr;
   bool arms_pending = false;
   sm_pipeline* child = nullptr;   // next pyramid level (cost + aggregation only), pyramidLevels > 1
@@ -127,7 +128,7 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
         cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming) != cudaSuccess)
       rc = SM_ERR_CUDA;
   }
-  if (rc == SM_OK && p->aggregation == 1 && p->costcalculation == 0) {
+  if (rc == SM_OK && (p->aggregation == 1 || p->aggregation == 2) && p->costcalculation == 0) {
     if (cudaStreamCreateWithFlags(&pl->streamA, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evA0, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evA1, cudaEventDisableTiming) != cudaSuccess)
@@ -252,6 +253,7 @@ static int pl_cost_calculate(sm_pipeline* pl) {
   const int views = (P.Do_refine && P.Do_LRConsis) ? 2 : 1;  // stereoMatching.cpp:1054, 5592
   pl->have_arms = false;
   auto ensure_arms = [&]() -> int { return pl_ensure_arms(pl); };
+  bool marked2 = false;
   if (P.costcalculation == 0) {
     if (pl->streamA && P.aggregation == 1) {
       // the arm maps depend on the packed images alone: built on a side stream while the cost kernels run
@@ -265,9 +267,30 @@ static int pl_cost_calculate(sm_pipeline* pl) {
       SM_CUDA(cudaEventRecord(pl->evA1, pl->streamA));
       pl->arms_pending = true;
     }
+    const bool nl_side = pl->streamA && P.aggregation == 2;   // NL frames: the MST build under the cost kernels
+    if (nl_side) {   // fork before the cost kernels are queued: the tree needs the image alone
+      SM_CUDA(cudaEventRecord(pl->evA0, c->stream));
+      SM_CUDA(cudaStreamWaitEvent(pl->streamA, pl->evA0, 0));
+    }
     for (int i = 0; i < imgNum; i++)
       SM_TRY(smi_cost_adcensus_packed(c, pl->pix[0], pl->pix[1], pl->cen[0], pl->cen[1], H, W, D, P.censusFunc,
                                       P.adTrunc, P.lamAD, P.lamCen, i, pl->vol[i]));
+    if (nl_side) {
+      // (tried on top: view 1's sweeps -- vm[1] is final here, NL aggregates vm[0] only -- queued before the tree so that they
+      // run under the MST build as well: the MST's ~90 small dependent launches then take 1.2 instead of 0.78 ms, c4 246
+      // instead of 260 fps; with the cost kernels alone under it 266 fps.  Under the tree FILTER they measured slower too.)
+      PL_MARK(2);   // the cost kernels end here; what is left of the tree build counts as aggregation
+      PL_MARK(3);
+      marked2 = true;
+      // the tree on the side stream (its rounds synchronise the host with THAT stream only; everything above is queued)
+      cudaStream_t main_stream = c->stream;
+      c->stream = pl->streamA;
+      const int rcT = smi_nl_tree(c, pl->bgr[0], H, W);
+      c->stream = main_stream;
+      SM_TRY(rcT);
+      SM_CUDA(cudaEventRecord(pl->evA1, pl->streamA));
+      pl->nl_tree_pending = true;
+    }
   } else if (P.costcalculation == 2) {
     // "Census": censusCal(vm, 1) (stereoMatching.cpp:975-976, 807-892) = the Hamming volume of both views
     for (int i = 0; i < imgNum; i++) {
@@ -282,7 +305,7 @@ static int pl_cost_calculate(sm_pipeline* pl) {
       SM_TRY(sm_cost_censusgrad(c, pl->cen[0], pl->cen[1], pl->grad[0][0], pl->grad[0][1], pl->grad[1][0], pl->grad[1][1],
                                 pl->arms[i], H, W, D, P.censusFunc, P.cg_lamCen, P.cg_lamG, P.gradTrunc, i, pl->vol[i]));
   }
-  PL_MARK(2);
+  if (!marked2) PL_MARK(2);
   // ---- aggregation
   if (pl->arms_pending) {
     SM_CUDA(cudaStreamWaitEvent(c->stream, pl->evA1, 0));
@@ -321,11 +344,17 @@ static int pl_cost_calculate(sm_pipeline* pl) {
       SM_TRY(smi_cbca_packed(c, pl->vol[i], pl->vol[2], pl->armpk[0], pl->armpk[1], H, W, D, P.cbca_iterationNum, i,
                              Lmax, smi_arm_pad(D), post));
   } else if (P.aggregation == 2) {
-    PL_MARK(3);
+    if (!marked2) PL_MARK(3);
     // (tried: view 1's SGM sweeps on the second stream under the MST build and tree filter of view 0 -- its volume is final
     // before the aggregation in NL mode.  Slower: the filter is a latency chain of one CTA per SM, and the sweeps' warps on
     // the same SMs stretch it, 2.93 -> 3.13 ms against 0.14 ms saved.)
-    SM_TRY(smi_nl(c, pl->bgr[0], pl->vol[0], pl->nlwork, H, W, D));
+    if (pl->nl_tree_pending) {
+      SM_CUDA(cudaStreamWaitEvent(c->stream, pl->evA1, 0));
+      pl->nl_tree_pending = false;
+      SM_TRY(smi_nl_filter(c, pl->vol[0], pl->nlwork, H, W, D));
+    } else {
+      SM_TRY(smi_nl(c, pl->bgr[0], pl->vol[0], pl->nlwork, H, W, D));
+    }
   } else {
     PL_MARK(3);
   }
