@@ -75,6 +75,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def l2_note(W, H, D, b):
+    """How the timed steps relate to the 126 MB L2 (timing rule: inputs larger than L2, or a flush)."""
+    vol = W * H * D * b / 1e6
+    if vol > 126:
+        return f"inputs larger than L2: each pass streams {vol / 1e3:.1f} GB volumes (L2 = 126 MB)"
+    return (f"a frame touches 3-4 volumes of {vol:.0f} MB plus their scratch (more than the 126 MB L2 in total, every pass "
+            f"writes a volume the next one reads); no separate flush between steps: the only data that survives from one "
+            f"step to the next is the {8 * W * H / 1e6:.1f} MB of input images")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -580,7 +590,7 @@ def main_ours(args):
                "config": {"workload": workload_desc(name), "frames_per_step_per_gpu": 1,
                           "extra_untimed_warmup_steps": extra_warm,
                           "parallelism": f"frame-parallel x{world}, no collective",
-                          "l2": "inputs larger than L2: each pass streams 2.1 GB volumes (L2 = 126 MB)"},
+                          "l2": l2_note(W, H, D, 2 if COSTCALC.get(name, 0) == 2 else 4)},
                "e2e": {"value": e2e_val, "unit": "MDE/s", "fps": e2e_val * 1e6 / (W * H * D),
                        "ms_per_step": e2e_ms / args.steps,
                        "h2d_bytes_per_step": 8 * W * H, "d2h_bytes_per_step": 2 * W * H},
