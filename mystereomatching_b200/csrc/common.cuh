@@ -24,6 +24,15 @@ struct sm_scratch {
 enum { SM_SCR_IMG0 = 0, SM_SCR_IMG1, SM_SCR_ARM0, SM_SCR_ARM1, SM_SCR_TAB, SM_SCR_MISC0, SM_SCR_MISC1,
        SM_SCR_MISC2, SM_SCR_MISC3, SM_SCR_MISC4, SM_SCR_MISC5, SM_SCR_NLWORK, SM_SCR_SGMEDGE, SM_SCR_NLREC, SM_SCR_NLEULER, SM_SCR_RVLIST, SM_SCR_COUNT };
 
+// A launch-bound chain of small kernels with fixed arguments (the MST rounds and the Euler-tour rooting of nl.cu: ~90
+// launches of a few microseconds each) replayed as a CUDA graph: see smi_graphed below.
+struct sm_graph_slot {
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long key = 0, last_key = 0;   // arguments the instantiated graph was captured with / seen last
+  long long launches = 0;                     // kernel launches inside (for the ctx's launch counter)
+};
+enum { SM_GRAPH_BORUVKA = 0, SM_GRAPH_EULER, SM_GRAPH_COUNT };
+
 struct sm_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -38,6 +47,7 @@ struct sm_ctx {
   // edge hand-off buffers of the grouped SGM sweeps: armed (all sentinel) up to this many bytes at this address
   void* sgm_edge_ptr = nullptr;
   size_t sgm_edge_armed = 0;
+  sm_graph_slot graphs[SM_GRAPH_COUNT];
 };
 
 void sm_set_error(const char* fmt, ...);
@@ -65,6 +75,43 @@ int sm_scratch_get(sm_ctx* ctx, int slot, size_t bytes, void** out);
     int r__ = (call);           \
     if (r__ != SM_OK) return r__; \
   } while (0)
+
+static inline unsigned long long smi_key_mix(unsigned long long h, unsigned long long v) {
+  return (h ^ v) * 1099511628211ull;   // FNV-1a over 64-bit words
+}
+// body(): a sequence of SM_LAUNCH / cudaMemsetAsync calls on ctx->stream without host synchronisation or allocation,
+// fully determined by `key` (every pointer and size it uses).  First call with a key: run eagerly.  Second consecutive
+// call with the same key: capture into a graph, instantiate, launch.  From then on: one cudaGraphLaunch.  A different key
+// (other buffers, other size) falls back to eager and starts over, so callers that pass fresh buffers every time
+// (the stage API from a test) never pay for a capture.
+template <class F>
+static inline int smi_graphed(sm_ctx* ctx, sm_graph_slot& g, unsigned long long key, F body) {
+  if (g.exec && g.key == key) {
+    SM_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+    ctx->launches += g.launches;
+    return SM_OK;
+  }
+  if (g.last_key != key) { g.last_key = key; return body(); }
+  if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  const long long l0 = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return body(); }
+  const int rc = body();
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != SM_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    ctx->launches = l0;
+    return rc != SM_OK ? rc : body();
+  }
+  e = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { g.exec = nullptr; cudaGetLastError(); ctx->launches = l0; return body(); }
+  g.key = key;
+  g.launches = ctx->launches - l0;
+  SM_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+  return SM_OK;
+}
 
 // A ctx's stream and scratch memory live on ctx->device; the caller's current device may be another one (two ctxs in
 // one process, or the host application switched devices), so every launch / allocation rebinds when it differs.

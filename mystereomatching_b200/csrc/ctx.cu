@@ -104,6 +104,8 @@ extern "C" int sm_ctx_destroy(sm_ctx* ctx) {
   if (!ctx) return SM_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < SM_GRAPH_COUNT; i++)
+    if (ctx->graphs[i].exec) cudaGraphExecDestroy(ctx->graphs[i].exec);
   for (int i = 0; i < SM_SCR_COUNT; i++)
     if (ctx->scr[i].p) cudaFree(ctx->scr[i].p);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -1089,6 +1089,18 @@ static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw,
   unsigned* keys = (unsigned*)(scan + T); unsigned* keys2 = keys + N;
   int* vals = (int*)(keys2 + N); int* vals2 = vals + N;
   int* hist = vals2 + N; int* offs = hist + nh; int* sums = offs + nh;
+  // ~50 dependent launches of a few microseconds each, every argument fixed by (N, the buffers): replayed as a CUDA graph
+  // from the third frame on (smi_graphed)
+  unsigned long long key = smi_key_mix(14695981039346656037ull, (unsigned long long)N);
+  for (const void* q : {(const void*)p, (const void*)nbr, (const void*)nbw, (const void*)deg, (const void*)parent, (const void*)wpar,
+                        (const void*)rank, (const void*)order, (const void*)level_start, (const void*)sync})
+    key = smi_key_mix(key, (unsigned long long)(uintptr_t)q);
+  int* const succ0 = succ; int* const dist0 = dist; int* const succ20 = succ2; int* const dist20 = dist2;
+  unsigned* const keys0 = keys; unsigned* const keys20 = keys2; int* const vals0 = vals; int* const vals20 = vals2;
+  return smi_graphed(ctx, ctx->graphs[SM_GRAPH_EULER], key, [&]() -> int {
+  // (the body may run twice -- capture, then an eager retry: it starts from the same buffers each time)
+  int *succ = succ0, *dist = dist0, *succ2 = succ20, *dist2 = dist20, *vals = vals0, *vals2 = vals20;
+  unsigned *keys = keys0, *keys2 = keys20;
   SM_LAUNCH(ctx, k_et_init, sm_div_up(n4, TB), TB, 0, N, (const int4*)nbr, deg, succ, dist);
   for (long long span = 1; span < T; span *= 2) {   // list ranking: ceil(log2 T) jumps
     SM_LAUNCH(ctx, k_et_jump, sm_div_up(n4, TB), TB, 0, n4, succ, dist, succ2, dist2);
@@ -1115,6 +1127,7 @@ static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw,
   }
   SM_LAUNCH(ctx, k_level_bounds, min(sm_div_up(N, TB), ctx->num_sms * 8), TB, 0, N, rank, order, level_start, sync);
   return SM_OK;
+  });
 }
 
 // MST + rooting.  img: [H][W][cn] u8 (already median-filtered).  Fills t (buffers must be allocated).
@@ -1143,19 +1156,40 @@ static int nl_build_tree(sm_ctx* ctx, const uint8_t* d_img, int H, int W, int cn
   // whether anything hooked costs a host round trip each (the GPU idles ~20 us); a round on a finished forest is a no-op
   // (no edge leaves a component: nothing hooks, labels and links stay), so the first rounds run unconditionally and the
   // question is asked after every second round from the sixth on.
-  for (int round = 0; E > 0 && round < 40; round++) {
+  auto half_round_a = [&]() -> int {   // find + hook
     SM_CUDA(cudaMemsetAsync(cnt, 0, 8, ctx->stream));
     SM_LAUNCH(ctx, k_bor_find, gE, TB, 0, ew, comp, H, W, best);
     SM_LAUNCH(ctx, k_bor_hook, gN, TB, 0, N, H, W, comp, best, link, inMST, cnt);
+    return SM_OK;
+  };
+  auto half_round_b = [&]() -> int {   // every label points at its root
+    SM_LAUNCH(ctx, k_bor_chase, gN, TB, 0, N, link);
+    SM_LAUNCH(ctx, k_bor_relabel, gN, TB, 0, N, comp, link, best);
+    SM_LAUNCH(ctx, k_bor_fixlink, gN, TB, 0, N, link);
+    return SM_OK;
+  };
+  // the unconditional rounds 0..4 and the first half of round 5 are one fixed chain of 28 launches: a CUDA graph
+  // (smi_graphed); the rounds with a question to the device follow as they were
+  int round = 0;
+  if (E > 0) {
+    unsigned long long key = smi_key_mix(smi_key_mix(14695981039346656037ull, (unsigned long long)N), ((unsigned long long)H << 32) | (unsigned)W);
+    for (const void* q : {(const void*)ew, (const void*)inMST, (const void*)comp, (const void*)best, (const void*)cnt})
+      key = smi_key_mix(key, (unsigned long long)(uintptr_t)q);
+    SM_TRY(smi_graphed(ctx, ctx->graphs[SM_GRAPH_BORUVKA], key, [&]() -> int {
+      for (int r = 0; r < 5; r++) { SM_TRY(half_round_a()); SM_TRY(half_round_b()); }
+      return half_round_a();
+    }));
+    round = 5;
+  }
+  for (; E > 0 && round < 40; round++) {
+    if (round > 5) SM_TRY(half_round_a());
     if (round >= 5 && (round & 1)) {
       int h_cnt[2] = {0, 0};
       SM_CUDA(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
       SM_CUDA(cudaStreamSynchronize(ctx->stream));
       if (h_cnt[0] == 0) break;   // no component has an outgoing edge: the forest is the spanning tree
     }
-    SM_LAUNCH(ctx, k_bor_chase, gN, TB, 0, N, link);   // every label points at its root
-    SM_LAUNCH(ctx, k_bor_relabel, gN, TB, 0, N, comp, link, best);
-    SM_LAUNCH(ctx, k_bor_fixlink, gN, TB, 0, N, link);
+    SM_TRY(half_round_b());
   }
   SM_LAUNCH(ctx, k_tree_adj, gN, TB, 0, H, W, ew, inMST, nbr, nbw, deg);
   SM_CUDA(cudaMemsetAsync(t.sync, 0, sizeof(nl_sync), ctx->stream));

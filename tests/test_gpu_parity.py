@@ -454,6 +454,33 @@ def test_pipeline_nl_matches_oracle_composition(ctx):
     assert (got == d).mean() >= 0.995
 
 
+@pytest.mark.timeout(180)
+def test_pipeline_nl_stream_of_frames_replays_the_mst_graph(ctx):
+    """A stream of NL frames through one pipeline: the tree build runs on the pipeline's side stream, where the fixed
+    launch chains of the MST (Boruvka rounds, Euler-tour rooting) are captured into CUDA graphs on the second frame and
+    replayed from the third on (smi_graphed).  Every frame must equal what a fresh pipeline (eager launches) gives for
+    it, different images included, and the launch counter must advance as it does without graphs."""
+    H, W, D = 72, 104, 32
+    params = capi.default_params(D - 1, sgm_paths=4, aggregation=2)
+    pairs = [_pair(H, W, D, "texture_warped", seed=40 + i) for i in range(3)]
+    fresh = []
+    for p in pairs:
+        pl = capi.Pipeline(ctx, H, W, params)
+        fresh.append(pl.run(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"]).copy())
+        pl.close()
+    pl = capi.Pipeline(ctx, H, W, params)
+    per_frame = []
+    for k in range(7):                       # eager, capture, then replays; the images change under the graph
+        p = pairs[k % 3]
+        l0 = ctx.launches()
+        got = pl.run(p["bgrL"], p["bgrR"], p["grayL"], p["grayR"])
+        per_frame.append(ctx.launches() - l0)
+        assert np.array_equal(got, fresh[k % 3]), f"frame {k}"
+    pl.close()
+    # a replayed frame counts the launches the same frame made eagerly (the number of Boruvka rounds depends on the image)
+    assert all(per_frame[k] == per_frame[k - 3] for k in range(3, 7)), per_frame
+
+
 # ---------------------------------------------------------------- Yang's driver (qx_nonlocal_cost_aggregation)
 @pytest.mark.timeout(180)
 def test_nlca_stages_bit_exact(ctx, golden_dir):
