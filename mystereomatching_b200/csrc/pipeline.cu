@@ -128,7 +128,11 @@ extern "C" int sm_pipeline_create(sm_ctx* ctx, int H, int W, const sm_params* p,
         cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming) != cudaSuccess)
       rc = SM_ERR_CUDA;
   }
-  if (rc == SM_OK && (p->aggregation == 1 || p->aggregation == 2) && p->costcalculation == 0) {
+  // side stream: the arm maps (CBCA frames; frames without aggregation whose refinement votes over the arms) or the MST
+  // build (NL frames) under the cost kernels.  censusGrad needs the arms BEFORE its cost kernel: nothing to overlap there.
+  const bool side_arms = p->costcalculation != 1 && (p->aggregation == 1 || (p->aggregation == 0 && p->Do_refine && p->Do_regionVote));
+  const bool side_tree = p->costcalculation == 0 && p->aggregation == 2;
+  if (rc == SM_OK && (side_arms || side_tree)) {
     if (cudaStreamCreateWithFlags(&pl->streamA, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evA0, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evA1, cudaEventDisableTiming) != cudaSuccess)
@@ -254,19 +258,20 @@ static int pl_cost_calculate(sm_pipeline* pl) {
   pl->have_arms = false;
   auto ensure_arms = [&]() -> int { return pl_ensure_arms(pl); };
   bool marked2 = false;
+  if (pl->streamA && P.costcalculation != 1 && (P.aggregation == 1 || (P.aggregation == 0 && P.Do_refine && P.Do_regionVote))) {
+    // the arm maps depend on the packed images alone: built on a side stream while the cost kernels run (CBCA needs them
+    // right after; without aggregation the refinement's region vote is their first reader)
+    SM_CUDA(cudaEventRecord(pl->evA0, c->stream));
+    SM_CUDA(cudaStreamWaitEvent(pl->streamA, pl->evA0, 0));
+    cudaStream_t main_stream = c->stream;
+    c->stream = pl->streamA;
+    const int rcA = pl_ensure_arms(pl);
+    c->stream = main_stream;
+    SM_TRY(rcA);
+    SM_CUDA(cudaEventRecord(pl->evA1, pl->streamA));
+    pl->arms_pending = true;
+  }
   if (P.costcalculation == 0) {
-    if (pl->streamA && P.aggregation == 1) {
-      // the arm maps depend on the packed images alone: built on a side stream while the cost kernels run
-      SM_CUDA(cudaEventRecord(pl->evA0, c->stream));
-      SM_CUDA(cudaStreamWaitEvent(pl->streamA, pl->evA0, 0));
-      cudaStream_t main_stream = c->stream;
-      c->stream = pl->streamA;
-      const int rcA = pl_ensure_arms(pl);
-      c->stream = main_stream;
-      SM_TRY(rcA);
-      SM_CUDA(cudaEventRecord(pl->evA1, pl->streamA));
-      pl->arms_pending = true;
-    }
     const bool nl_side = pl->streamA && P.aggregation == 2;   // NL frames: the MST build under the cost kernels
     if (nl_side) {   // fork before the cost kernels are queued: the tree needs the image alone
       SM_CUDA(cudaEventRecord(pl->evA0, c->stream));
