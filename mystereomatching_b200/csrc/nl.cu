@@ -433,13 +433,32 @@ __global__ void k_level_bounds(int N, const int* __restrict__ rank, const int* _
 // A: Dp planes of N doubles (Dp = D, or D+1 with the all-ones plane at index D), element (v, d) at A[v * sn + d * sd]:
 // plane-major (sn = 1, sd = N) for the work buffer the filter owns, node-major (sn = D, sd = 1) in place for
 // qx_tree_filter::filter's own layout.
-__global__ void k_tf_load(const float* __restrict__ vol, double* __restrict__ A, size_t N, int D, int Dp,
-                          const int* __restrict__ order) {
+// Both directions go through a 32-position x 64-plane tile in shared memory: a pixel's D floats are contiguous in the
+// volume and a plane's positions are contiguous in A, so each side is read / written in 128-256-byte runs (one thread per
+// element of A gathered 4 bytes from 32 different pixels per warp instruction: 0.124 + 0.101 ms per frame at 640x480 D=64).
+#define TFX_Q 32
+#define TFX_D 64
+__global__ void __launch_bounds__(256)
+    k_tf_load(const float* __restrict__ vol, double* __restrict__ A, size_t N, int D, int Dp, const int* __restrict__ order) {
   // work buffer: plane-major AND level-ordered, element (position q of `order`, plane d) at A[d * N + q]
-  const size_t n = N * Dp;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t d = i / N, q = i - d * N;
-    A[i] = d < (size_t)D ? (double)vol[(size_t)order[q] * D + d] : 1.0;
+  __shared__ float tile[TFX_D][TFX_Q + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t q0 = (size_t)blockIdx.x * TFX_Q; q0 < N; q0 += (size_t)gridDim.x * TFX_Q) {
+    if (Dp > D && warp == 0 && q0 + lane < N) A[(size_t)D * N + q0 + lane] = 1.0;
+    for (int d0 = 0; d0 < D; d0 += TFX_D) {
+      const int nd = min(TFX_D, D - d0);
+      for (int k = warp; k < TFX_Q; k += 8) {          // a pixel's run of planes, coalesced
+        const size_t q = q0 + k;
+        if (q < N) {
+          const float* src = vol + (size_t)order[q] * D + d0;
+          for (int d = lane; d < nd; d += 32) tile[d][k] = src[d];
+        }
+      }
+      __syncthreads();
+      for (int d = warp; d < nd; d += 8)               // a plane's run of positions, coalesced
+        if (q0 + lane < N) A[(size_t)(d0 + d) * N + q0 + lane] = (double)tile[d][lane];
+      __syncthreads();
+    }
   }
 }
 
@@ -1043,15 +1062,31 @@ __global__ void __launch_bounds__(TFW_T)
   }
 }
 
-__global__ void k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp,
-                           const int* __restrict__ pos) {
-  const size_t n = N * D;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t v = i / D;
-    const int d = (int)(i - v * D);
-    const size_t q = (size_t)pos[v];
-    const float x = (float)A[(size_t)d * N + q];                     // NLCCA::aggreCV: (float)nlcP[d]
-    vol[i] = Dp > D ? x / (float)A[(size_t)D * N + q] : x;           // StereoMatching::NL: vm[0] /= wetNL
+__global__ void __launch_bounds__(256)
+    k_tf_store(const double* __restrict__ A, float* __restrict__ vol, size_t N, int D, int Dp, const int* __restrict__ order) {
+  __shared__ float tile[TFX_D][TFX_Q + 1];
+  __shared__ float wet[TFX_Q];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t q0 = (size_t)blockIdx.x * TFX_Q; q0 < N; q0 += (size_t)gridDim.x * TFX_Q) {
+    if (Dp > D && warp == 0) wet[lane] = q0 + lane < N ? (float)A[(size_t)D * N + q0 + lane] : 1.0f;
+    for (int d0 = 0; d0 < D; d0 += TFX_D) {
+      const int nd = min(TFX_D, D - d0);
+      for (int d = warp; d < nd; d += 8)
+        if (q0 + lane < N) tile[d][lane] = (float)A[(size_t)(d0 + d) * N + q0 + lane];   // NLCCA::aggreCV: (float)nlcP[d]
+      __syncthreads();
+      for (int k = warp; k < TFX_Q; k += 8) {
+        const size_t q = q0 + k;
+        if (q < N) {
+          float* dst = vol + (size_t)order[q] * D + d0;
+          const float w = Dp > D ? wet[k] : 1.0f;
+          for (int d = lane; d < nd; d += 32) {
+            const float x = tile[d][k];
+            dst[d] = Dp > D ? x / w : x;                                                  // StereoMatching::NL: vm[0] /= wetNL
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -1251,7 +1286,8 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
   SM_LAUNCH(ctx, k_tf_positions, gr, TB, 0, n, t.order, t.pos);
   SM_LAUNCH(ctx, k_tf_records, gr, TB, 0, n, t.order, t.pos, t.rank, t.level_start, t.parent, t.wpar, t.child, t.nchild,
             t.rcp, t.rcw, t.rnc, t.rpp, t.rw, t.rup, t.rdn);
-  if (d_vol) SM_LAUNCH(ctx, k_tf_load, g, TB, 0, d_vol, d_A, N, D, Dp, t.order);
+  const int gx = (int)min((size_t)ctx->num_sms * 8, (N + TFX_Q - 1) / TFX_Q);   // tiles of 32 positions
+  if (d_vol) SM_LAUNCH(ctx, k_tf_load, gx, 256, 0, d_vol, d_A, N, D, Dp, t.order);
   const size_t tfwFixed = 2 * (size_t)TFW_CAP * 8 + (size_t)TFW_S * TFW_C * 40;
   if (d_vol) {
     // one CTA per plane, records and values streamed (k_tf_cta); level bounds in shared memory as far as they fit
@@ -1287,7 +1323,7 @@ static int nl_filter(sm_ctx* ctx, float* d_vol, double* d_A, int H, int W, int D
     SM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(256), args, smem, ctx->stream));
     ctx->launches++;
   }
-  if (d_vol) SM_LAUNCH(ctx, k_tf_store, g, TB, 0, d_A, d_vol, N, D, Dp, t.pos);
+  if (d_vol) SM_LAUNCH(ctx, k_tf_store, gx, 256, 0, d_A, d_vol, N, D, Dp, t.order);
   return SM_OK;
 }
 
