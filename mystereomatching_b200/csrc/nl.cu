@@ -203,8 +203,9 @@ struct nl_sync {
 // Identical parent / weight / rank to the BFS (a rooted tree has one parent function); `order` is grouped by level,
 // which is all the filter needs (its results do not depend on the order inside a level).
 #define ET_END (-1)
-__global__ void k_et_init(int N, const int4* __restrict__ nbr, const uint8_t* __restrict__ deg, int* __restrict__ succ,
-                          int* __restrict__ dist) {
+// (successor, distance) of a directed edge live in ONE int2: a jump gathers one 8-byte entry instead of two 4-byte ones from
+// two arrays (each a 32-byte sector of its own)
+__global__ void k_et_init(int N, const int4* __restrict__ nbr, const uint8_t* __restrict__ deg, int2* __restrict__ sd) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 4 * N) return;
   const int u = e >> 2, k = e & 3;
@@ -220,20 +221,18 @@ __global__ void k_et_init(int N, const int4* __restrict__ nbr, const uint8_t* __
     if (s == 0) s = ET_END;   // edge (0, 0) starts the tour: whoever precedes it is the last edge
     d = s == ET_END ? 0 : 1;
   }
-  succ[e] = s; dist[e] = d;
+  sd[e] = make_int2(s, d);
 }
-__global__ void k_et_jump(int n, const int* __restrict__ succ, const int* __restrict__ dist, int* __restrict__ succ2,
-                          int* __restrict__ dist2) {
+__global__ void k_et_jump(int n, const int2* __restrict__ sd, int2* __restrict__ sd2) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  const int s = succ[e];
-  int d = dist[e], s2 = s;
-  if (s != ET_END) { d += dist[s]; s2 = succ[s]; }
-  succ2[e] = s2; dist2[e] = d;
+  int2 a = sd[e];
+  if (a.x != ET_END) { const int2 b = sd[a.x]; a.y += b.y; a.x = b.x; }
+  sd2[e] = a;
 }
 // dist = number of edges after e in the tour; T = 2(N-1) edges; position = T - 1 - dist
 __global__ void k_et_classify(int N, int T, const int4* __restrict__ nbr, const uchar4* __restrict__ nbw,
-                              const uint8_t* __restrict__ deg, const int* __restrict__ dist, int* __restrict__ parent,
+                              const uint8_t* __restrict__ deg, const int2* __restrict__ sd, int* __restrict__ parent,
                               uint8_t* __restrict__ wpar, int* __restrict__ pm, int* __restrict__ node_at) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 4 * N) return;
@@ -245,7 +244,7 @@ __global__ void k_et_classify(int N, int T, const int4* __restrict__ nbr, const 
   const int wk = k == 0 ? w.x : (k == 1 ? w.y : (k == 2 ? w.z : w.w));
   const int4 b = nbr[v];
   const int j = b.x == u ? 0 : (b.y == u ? 1 : (b.z == u ? 2 : 3));
-  const int pe = T - 1 - dist[e], pr = T - 1 - dist[4 * v + j];
+  const int pe = T - 1 - sd[e].y, pr = T - 1 - sd[4 * v + j].y;
   const bool down = pe < pr;
   pm[pe] = down ? 1 : -1;
   node_at[pe] = down ? v : -1;
@@ -1113,14 +1112,14 @@ static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw,
   const int T = 2 * (N - 1), n4 = 4 * N, TB = 256;
   const int nt = sm_div_up(N, NLP_TILE);            // tiles of a sort pass
   const int nh = 256 * nt;                          // histogram entries of a pass
-  // succ | dist | succ2 | dist2 (4N ints each) ; pm | node_at | scan (T) ; keys | keys2 | vals | vals2 (N) ;
+  // (succ, dist) x 2 (4N int2 each) ; pm | node_at | scan (T) ; keys | keys2 | vals | vals2 (N) ;
   // hist | offs (256 nt) ; sums (tiles of the longest scan)
   const int nsums = max(sm_div_up(T, NLP_TILE), sm_div_up(nh, NLP_TILE)) + 8;
   const size_t ints = (size_t)4 * n4 + (size_t)3 * T + (size_t)4 * N + (size_t)2 * nh + nsums + 64;
   void* p;
   SM_TRY(sm_scratch_get(ctx, SM_SCR_NLEULER, ints * 4, &p));
-  int* succ = (int*)p; int* dist = succ + n4; int* succ2 = dist + n4; int* dist2 = succ2 + n4;
-  int* pm = dist2 + n4; int* node_at = pm + T; int* scan = node_at + T;
+  int2* sdA = (int2*)p; int2* sdB = sdA + n4;   // (succ, dist) ping-pong: 4 n4 ints (the scratch base is 256-byte aligned)
+  int* pm = (int*)(sdB + n4); int* node_at = pm + T; int* scan = node_at + T;
   unsigned* keys = (unsigned*)(scan + T); unsigned* keys2 = keys + N;
   int* vals = (int*)(keys2 + N); int* vals2 = vals + N;
   int* hist = vals2 + N; int* offs = hist + nh; int* sums = offs + nh;
@@ -1130,20 +1129,19 @@ static int nl_root_euler(sm_ctx* ctx, int N, const int* nbr, const uint8_t* nbw,
   for (const void* q : {(const void*)p, (const void*)nbr, (const void*)nbw, (const void*)deg, (const void*)parent, (const void*)wpar,
                         (const void*)rank, (const void*)order, (const void*)level_start, (const void*)sync})
     key = smi_key_mix(key, (unsigned long long)(uintptr_t)q);
-  int* const succ0 = succ; int* const dist0 = dist; int* const succ20 = succ2; int* const dist20 = dist2;
   unsigned* const keys0 = keys; unsigned* const keys20 = keys2; int* const vals0 = vals; int* const vals20 = vals2;
   return smi_graphed(ctx, ctx->graphs[SM_GRAPH_EULER], key, [&]() -> int {
   // (the body may run twice -- capture, then an eager retry: it starts from the same buffers each time)
-  int *succ = succ0, *dist = dist0, *succ2 = succ20, *dist2 = dist20, *vals = vals0, *vals2 = vals20;
+  int2 *sd = sdA, *sd2 = sdB;
+  int *vals = vals0, *vals2 = vals20;
   unsigned *keys = keys0, *keys2 = keys20;
-  SM_LAUNCH(ctx, k_et_init, sm_div_up(n4, TB), TB, 0, N, (const int4*)nbr, deg, succ, dist);
+  SM_LAUNCH(ctx, k_et_init, sm_div_up(n4, TB), TB, 0, N, (const int4*)nbr, deg, sd);
   for (long long span = 1; span < T; span *= 2) {   // list ranking: ceil(log2 T) jumps
-    SM_LAUNCH(ctx, k_et_jump, sm_div_up(n4, TB), TB, 0, n4, succ, dist, succ2, dist2);
-    int* t = succ; succ = succ2; succ2 = t;
-    t = dist; dist = dist2; dist2 = t;
+    SM_LAUNCH(ctx, k_et_jump, sm_div_up(n4, TB), TB, 0, n4, (const int2*)sd, sd2);
+    int2* t = sd; sd = sd2; sd2 = t;
   }
-  SM_LAUNCH(ctx, k_et_classify, sm_div_up(n4, TB), TB, 0, N, T, (const int4*)nbr, (const uchar4*)nbw, deg, dist, parent, wpar, pm,
-            node_at);
+  SM_LAUNCH(ctx, k_et_classify, sm_div_up(n4, TB), TB, 0, N, T, (const int4*)nbr, (const uchar4*)nbw, deg, (const int2*)sd, parent, wpar,
+            pm, node_at);
   SM_LAUNCH(ctx, k_root_fix, 1, 1, 0, parent, wpar);
   SM_TRY(nl_scan<false>(ctx, pm, scan, T, sums));   // +1 / -1 along the tour: the value at a downward edge is the depth
   SM_LAUNCH(ctx, k_et_depth, sm_div_up(T + 1, TB), TB, 0, T, scan, node_at, rank);
